@@ -1,0 +1,166 @@
+/*
+ * toucan_cuda.h -- C ABI of libtoucan_cuda.so: the sm_100a kernels behind toucan's
+ * per-frame render path.
+ *
+ * This is the drop-in boundary for the pixel work.  In the reference every effect
+ * plug-in's _render() body is a call into OpenImageIO::ImageBufAlgo on host memory;
+ * each entry point below replaces one of those call sites (cited per function, paths
+ * relative to the reference tree) and runs on DEVICE memory, stream-ordered.
+ *
+ * Conventions
+ *   - images are interleaved RGBA (4 channels), row-major, top row first, tightly
+ *     packed (row bytes = w * 4 * sizeof(type)), as produced by
+ *     lib/toucanRender/PropertySet.cpp:431-471 (bufToPropSet).
+ *   - tc_image::data is a device pointer, 16-byte aligned.
+ *   - arithmetic is float32; storage conversion happens at load/store with OIIO's rules
+ *     (u8/u16: round-half-up with clamp; half: round-to-nearest-even).
+ *   - reads outside a source image return 0 (OIIO black wrap) unless stated.
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and returns TC_OK or a
+ *     negative tc_status; tc_last_error() gives the message for the calling thread.
+ *   - no CPU fallback exists: without a CUDA device every compute call fails.
+ */
+#ifndef TOUCAN_CUDA_H
+#define TOUCAN_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tc_type { TC_U8 = 0, TC_U16 = 1, TC_F16 = 2, TC_F32 = 3 } tc_type;
+
+typedef enum tc_status {
+    TC_OK = 0,
+    TC_ERR_INVALID = -1,     /* bad argument (null image, size <= 0, unknown name, ...) */
+    TC_ERR_CUDA = -2,        /* a CUDA runtime call failed; see tc_last_error() */
+    TC_ERR_UNSUPPORTED = -3, /* valid in the reference but outside this build's scope */
+    TC_ERR_NO_DEVICE = -4
+} tc_status;
+
+typedef struct tc_image {
+    void* data; /* device pointer */
+    int w, h;
+    int type;   /* tc_type */
+} tc_image;
+
+typedef void* tc_stream; /* cudaStream_t */
+
+/* ---- runtime ---------------------------------------------------------------------- */
+const char* tc_version(void);
+const char* tc_last_error(void);
+int tc_device_count(int* count);
+int tc_set_device(int device);
+int tc_stream_create(tc_stream* out);
+int tc_stream_destroy(tc_stream s);
+int tc_stream_sync(tc_stream s);
+size_t tc_type_size(int type);
+size_t tc_image_bytes(int w, int h, int type);
+/* result type of op(A,B) into an uninitialised destination (OIIO TypeDesc::basetype_merge) */
+int tc_type_merge(int a, int b);
+
+/* stream-ordered device pool (replaces the per-node malloc+memset of
+   lib/toucanRender/ImageEffect.cpp:93,108,126).  Memory is NOT zeroed. */
+int tc_malloc(void** out, size_t bytes, tc_stream s);
+int tc_free(void* p, tc_stream s);
+int tc_pool_trim(void);
+/* pinned host staging + copies (upload of decoded frames: Read.cpp:64-101; download
+   for the writers: bin/toucan-render/App.cpp:238-262) */
+int tc_host_alloc(void** out, size_t bytes);
+int tc_host_free(void* p);
+int tc_upload(void* dst_dev, const void* src_host, size_t bytes, tc_stream s);
+int tc_download(void* dst_host, const void* src_dev, size_t bytes, tc_stream s);
+int tc_memset(void* dst_dev, int value, size_t bytes, tc_stream s);
+/* count of kernels launched by this library in the calling process (bench evidence) */
+unsigned long long tc_launch_count(void);
+
+/* ---- generators: plugins/GeneratorPlugin.cpp -------------------------------------- */
+/* ImageBufAlgo::fill(out, color)                          GeneratorPlugin.cpp:296-303 */
+int tc_fill(const tc_image* dst, const float color[4], tc_stream s);
+/* ImageBufAlgo::checker(out, cw, ch, 1, c1, c2)           GeneratorPlugin.cpp:205-221 */
+int tc_checkers(const tc_image* dst, int cw, int ch, const float c1[4], const float c2[4], tc_stream s);
+/* fill(out, top, bottom) | u8 temp + rotate270 + copy     GeneratorPlugin.cpp:393-431 */
+int tc_gradient(const tc_image* dst, const float c1[4], const float c2[4], int vertical, tc_stream s);
+/* ImageBufAlgo::noise(out, type, a, b, mono, seed) on a zeroed buffer  GeneratorPlugin.cpp:525-531
+   type: "gaussian"|"normal"|"white"|"uniform"|"salt" */
+int tc_noise(const tc_image* dst, const char* type, float a, float b, int mono, int seed, tc_stream s);
+
+/* ---- filters: plugins/FilterPlugin.cpp -------------------------------------------- */
+/* make_kernel("gaussian", r, r) + convolve(out, src, k, true)   FilterPlugin.cpp:188-202 */
+int tc_blur(const tc_image* dst, const tc_image* src, float radius, tc_stream s);
+/* color_map(out, src, -1, name) + copy alpha              FilterPlugin.cpp:271-295 */
+int tc_color_map(const tc_image* dst, const tc_image* src, const char* map_name, tc_stream s);
+/* invert(out, src, ch 0..2) + copy alpha                  FilterPlugin.cpp:335-361 */
+int tc_invert(const tc_image* dst, const tc_image* src, tc_stream s);
+/* pow(out, src, value) on all 4 channels                  FilterPlugin.cpp:430-438 */
+int tc_pow(const tc_image* dst, const tc_image* src, float value, tc_stream s);
+/* saturate(out, src, value, 0)                            FilterPlugin.cpp:507-516 */
+int tc_saturate(const tc_image* dst, const tc_image* src, float value, tc_stream s);
+/* unsharp_mask(out, src, kernel, width, contrast, threshold)   FilterPlugin.cpp:607-618 */
+int tc_unsharp_mask(const tc_image* dst, const tc_image* src, const char* kernel, float width, float contrast,
+                    float threshold, tc_stream s);
+
+/* ---- colour: plugins/ColorPlugin.cpp ---------------------------------------------- */
+/* colorconvert(out, src, from, to, premult=0, key, val, cfg)   ColorPlugin.cpp:220-248.
+   Baked decode-curve -> 3x3 -> encode-curve for the colour spaces of OCIO's built-in config. */
+int tc_color_convert(const tc_image* dst, const tc_image* src, const char* fromspace, const char* tospace, tc_stream s);
+int tc_color_space_known(const char* name);
+/* premult(out, src)                                       ColorPlugin.cpp:286 */
+int tc_premult(const tc_image* dst, const tc_image* src, tc_stream s);
+/* unpremult(out, src)                                     ColorPlugin.cpp:324 */
+int tc_unpremult(const tc_image* dst, const tc_image* src, tc_stream s);
+
+/* ---- transforms: plugins/TransformPlugin.cpp -------------------------------------- */
+/* cut(src, ROI(pos, pos+size)) + copy(out, crop)          TransformPlugin.cpp:197-200 */
+int tc_crop(const tc_image* dst, const tc_image* src, int px, int py, int cw, int ch, tc_stream s);
+/* flip(out, src)                                          TransformPlugin.cpp:239-246 */
+int tc_flip(const tc_image* dst, const tc_image* src, tc_stream s);
+/* flop(out, src)                                          TransformPlugin.cpp:284-291 */
+int tc_flop(const tc_image* dst, const tc_image* src, tc_stream s);
+/* resize(out, src, filter, width, ROI(0,w,0,h))           TransformPlugin.cpp:374-379,
+   lib/toucanRender/Comp.cpp:51-55, TransitionPlugin.cpp:226-230.
+   filter_name: "" (default choice) | "lanczos3" | "blackman-harris" */
+int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name, float filter_width, tc_stream s);
+/* rotate(out, src, angle_radians, filter, width)          TransformPlugin.cpp:462-467 */
+int tc_rotate(const tc_image* dst, const tc_image* src, float angle_radians, const char* filter_name,
+              float filter_width, tc_stream s);
+
+/* ---- transitions: plugins/TransitionPlugin.cpp ------------------------------------ */
+/* fill, fill, mul, mul, add in ONE pass (sizes equal)     TransitionPlugin.cpp:242-264 */
+int tc_dissolve(const tc_image* dst, const tc_image* from, const tc_image* to, double value, tc_stream s);
+/* matte build + mul, mul, add in ONE pass                 TransitionPlugin.cpp:303-342 (vertical=0), :392-432 (1) */
+int tc_wipe(const tc_image* dst, const tc_image* from, const tc_image* to, double value, int vertical, tc_stream s);
+
+/* ---- compositing: lib/toucanRender/Comp.cpp --------------------------------------- */
+/* premult (Comp.cpp:41, optional) + over (Comp.cpp:72) in ONE pass; fg, bg, dst same size */
+int tc_over(const tc_image* dst, const tc_image* fg, const tc_image* bg, int premult_fg, tc_stream s);
+/* paste(dst, ox, oy, src) into a ZEROED dst of another size/type   Comp.cpp:56-67.
+   Writes every dst pixel (0 outside the pasted rectangle). */
+int tc_paste_on_black(const tc_image* dst, int ox, int oy, const tc_image* src, tc_stream s);
+/* storage-type conversion / copy, 0 outside src           bin/toucan-render/App.cpp:285-291 */
+int tc_convert(const tc_image* dst, const tc_image* src, tc_stream s);
+
+/* ---- fused track stack (cross-node fusion of the hot chain) ------------------------
+ * One pass over the output for a whole stack of tracks:
+ *   acc = background colour
+ *   for each layer (bottom to top):
+ *       a = blur_a ? blur(src_a, radius_a) : src_a
+ *       if (src_b) { b = blur_b ? blur(src_b, radius_b) : src_b;  a = dissolve(a, b, value) }
+ *       acc = over(premult(a), acc)
+ * i.e. ImageGraph.cpp:165-198 (_track + CompNode chain) with toucan:Blur
+ * (FilterPlugin.cpp:188-202) and toucan:Dissolve (TransitionPlugin.cpp:242-264) per track.
+ * All sources float32 and of the output size. */
+typedef struct tc_stack_layer {
+    const void* src_a; /* device, float32 RGBA, w*h */
+    const void* src_b; /* optional second source (transition), or NULL */
+    float radius_a;    /* toucan:Blur radius on a (0 = none) */
+    float radius_b;
+    double value;      /* dissolve value */
+} tc_stack_layer;
+int tc_stack_f32(const tc_image* dst, const float background[4], const tc_stack_layer* layers, int n_layers,
+                 tc_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOUCAN_CUDA_H */

@@ -1,0 +1,270 @@
+"""GPU parity: every C-ABI kernel against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): bit-exact for Fill / Checkers / Flip / Flop / Crop / Invert /
+Wipes / seeded Noise (and everything else that is pure select/copy); <= 1e-5 abs (float32)
+or +-1 LSB (u8 / u16 / half storage) for filtering, resampling and colour ops.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NP_TYPES = [np.uint8, np.uint16, np.float16, np.float32]
+SIZES = [(333, 217), (64, 48), (1, 1), (37, 5)]
+
+
+def rand_img(w, h, dt, seed, alpha="frac"):
+    rng = np.random.default_rng(seed)
+    f = rng.random((h, w, 4), dtype=np.float32)
+    if alpha == "one":
+        f[..., 3] = 1.0
+    elif alpha == "mixed":
+        f[..., 3] = np.where(rng.random((h, w)) < 0.3, 1.0, np.where(rng.random((h, w)) < 0.3, 0.0, f[..., 3]))
+    if dt == np.uint8:
+        return np.ascontiguousarray((f * 255).astype(np.uint8))
+    if dt == np.uint16:
+        return np.ascontiguousarray((f * 65535).astype(np.uint16))
+    return np.ascontiguousarray(f.astype(dt))
+
+
+def to_dev(a):
+    if a.dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+    return torch.from_numpy(a).cuda()
+
+
+def to_host(t):
+    if t.dtype == torch.uint16:
+        return t.view(torch.int16).cpu().numpy().view(np.uint16)
+    return t.cpu().numpy()
+
+
+def assert_exact(got, want, what=""):
+    got = to_host(got)
+    assert got.dtype == want.dtype and got.shape == want.shape, (what, got.dtype, want.dtype, got.shape, want.shape)
+    if got.dtype.kind == "f":
+        same = (got.view(np.uint16 if got.dtype == np.float16 else np.uint32) ==
+                want.view(np.uint16 if got.dtype == np.float16 else np.uint32)) | ((got == want))
+        bad = ~same
+    else:
+        bad = got != want
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.size} values differ; first at {np.argwhere(bad)[0]}: got {got[bad][0]} want {want[bad][0]}"
+
+
+def assert_close(got, want, what="", tol=1e-5, lsb=1, rtol=0.0):
+    got = to_host(got)
+    assert got.dtype == want.dtype and got.shape == want.shape, (what, got.dtype, want.dtype, got.shape, want.shape)
+    if got.dtype == np.float32:
+        d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        assert np.isfinite(got).all() or not np.isfinite(want).all(), what
+        d = d - rtol * np.abs(want.astype(np.float64))
+        m = float(np.nanmax(d)) if d.size else 0.0
+        assert m <= tol, f"{what}: max abs diff {m:.3e} > {tol}"
+    elif got.dtype == np.float16:
+        # +-1 LSB of half storage: neighbouring representable values
+        gi = got.view(np.int16).astype(np.int32)
+        wi = want.view(np.int16).astype(np.int32)
+        gi = np.where(gi < 0, -(gi & 0x7FFF), gi)
+        wi = np.where(wi < 0, -(wi & 0x7FFF), wi)
+        ulp = np.abs(gi - wi)
+        # near zero a 1e-6 difference spans several (sub)normal half steps: accept the float bar too
+        bad = (ulp > lsb) & (np.abs(got.astype(np.float64) - want.astype(np.float64)) > tol)
+        assert not bad.any(), f"{what}: max half-ULP diff {int(ulp[bad].max())} at {np.argwhere(bad)[0]}"
+    else:
+        m = int(np.abs(got.astype(np.int64) - want.astype(np.int64)).max()) if got.size else 0
+        assert m <= lsb, f"{what}: max LSB diff {m}"
+
+
+@pytest.fixture(scope="module")
+def T(cuda):
+    from toucan_b200 import ops
+
+    return ops
+
+
+C1 = [0.25, 0.5, 0.75, 1.0]
+C2 = [1.0, 0.1, 0.333, 0.6]
+
+
+@pytest.mark.parametrize("size", [(1280, 720), (333, 217), (1, 1)])
+def test_generators_bit_exact(T, size):
+    w, h = size
+    assert_exact(T.fill(w, h, C1), O.fill(w, h, C1), "fill")
+    assert_exact(T.fill(w, h, [0.0, 0.0, 1.0, 1.0]), O.fill(w, h, [0.0, 0.0, 1.0, 1.0]), "fill")
+    for cs in [(100, 100), (200, 200), (300, 300), (7, 3)]:
+        assert_exact(T.checkers(w, h, cs[0], cs[1], C1, C2), O.checkers(w, h, cs[0], cs[1], C1, C2), f"checkers {cs}")
+    for vertical in (True, False):
+        assert_exact(T.gradient(w, h, C1, C2, vertical), O.gradient(w, h, C1, C2, vertical), f"gradient v={vertical}")
+        assert_exact(T.gradient(w, h, [1, 0, 0, 1], [0, 0, 1, 1], vertical), O.gradient(w, h, [1, 0, 0, 1], [0, 0, 1, 1], vertical), "gradient")
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+def test_generators_other_types(T, dt):
+    t = O._DT[np.dtype(dt)]
+    w, h = 129, 67
+    assert_exact(T.fill(w, h, C2, t), O.fill(w, h, C2, t), "fill")
+    assert_exact(T.checkers(w, h, 10, 9, C1, C2, t), O.checkers(w, h, 10, 9, C1, C2, t), "checkers")
+    assert_exact(T.gradient(w, h, C1, C2, True, t), O.gradient(w, h, C1, C2, True, t), "gradient v")
+    assert_exact(T.gradient(w, h, C1, C2, False, t), O.gradient(w, h, C1, C2, False, t), "gradient h")
+
+
+@pytest.mark.parametrize("ntype,a,b,mono,seed", [("gaussian", 1.0, 1.0, False, 0), ("gaussian", 0.5, 0.1, True, 7),
+                                                 ("uniform", 0.1, 0.9, False, 3), ("white", 0.0, 1.0, True, 11),
+                                                 ("salt", 1.0, 0.05, False, 5), ("bogus", 1.0, 1.0, False, 0)])
+def test_noise_bit_exact(T, ntype, a, b, mono, seed):
+    for (w, h) in [(1280, 720), (97, 33)]:
+        assert_exact(T.noise(w, h, ntype, a, b, mono, seed), O.noise(w, h, ntype, a, b, mono, seed), f"noise {ntype} u8")
+    t = O.F32
+    assert_exact(T.noise(333, 217, ntype, a, b, mono, seed, t), O.noise(333, 217, ntype, a, b, mono, seed, t), f"noise {ntype} f32")
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+@pytest.mark.parametrize("size", SIZES)
+def test_exact_unary(T, dt, size):
+    w, h = size
+    src = rand_img(w, h, dt, 1)
+    d = to_dev(src)
+    assert_exact(T.invert(d), O.invert(src), "invert")
+    assert_exact(T.flip(d), O.flip(src), "flip")
+    assert_exact(T.flop(d), O.flop(src), "flop")
+    assert_exact(T.flip(T.flip(d)), src, "flip∘flip")
+    pos, csz = (w // 3, h // 4), (max(1, w // 2), max(1, h // 2))
+    assert_exact(T.crop(d, pos, csz), O.crop(src, pos, csz), "crop")
+    assert_exact(T.crop(d, (w // 2, h // 2), (w, h)), O.crop(src, (w // 2, h // 2), (w, h)), "crop past the edge")
+    for t in range(4):
+        assert_exact(T.convert(d, t), O.convert(src, t), f"convert ->{t}")
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+@pytest.mark.parametrize("size", SIZES[:2])
+def test_pointwise_filters(T, dt, size):
+    w, h = size
+    src = rand_img(w, h, dt, 2, alpha="mixed")
+    d = to_dev(src)
+    assert_close(T.saturate(d, 0.0), O.saturate(src, 0.0), "saturate 0")
+    assert_close(T.saturate(d, 1.7), O.saturate(src, 1.7), "saturate 1.7")
+    assert_close(T.pow_(d, 2.0), O.pow_(src, 2.0), "pow 2")
+    assert_close(T.pow_(d, 3.0), O.pow_(src, 3.0), "pow 3")
+    assert_close(T.pow_(d, 0.4545), O.pow_(src, 0.4545), "pow .45")
+    for name in ["plasma", "inferno", "magma", "viridis", "turbo", "blue-red", "spectrum", "heat", "nonesuch"]:
+        assert_close(T.color_map(d, name), O.color_map(src, name), f"color_map {name}")
+    assert_close(T.premult(d), O.premult(src), "premult")
+    assert_close(T.unpremult(d), O.unpremult(src), "unpremult")
+    assert_close(T.colorconvert(d, "Linear Rec.709 (sRGB)", "ACEScct"), O.colorconvert(src, "Linear Rec.709 (sRGB)", "ACEScct"), "cc1")
+    assert_close(T.colorconvert(d, "Gamma 2.4 Rec.709 - Texture", "Linear P3-D65"),
+                 O.colorconvert(src, "Gamma 2.4 Rec.709 - Texture", "Linear P3-D65"), "cc2")
+    assert_close(T.colorconvert(d, "sRGB - Texture", "ACEScg"), O.colorconvert(src, "sRGB - Texture", "ACEScg"), "cc3")
+    assert_close(T.colorconvert(d, "ACEScc", "Linear Rec.2020"), O.colorconvert(src, "ACEScc", "Linear Rec.2020"), "cc4", rtol=1e-6)  # ACEScc decode reaches ~220: relative bar
+    assert_close(T.colorconvert(d, "nope", "ACEScg"), O.colorconvert(src, "nope", "ACEScg"), "cc unknown")
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+@pytest.mark.parametrize("radius", [10.0, 20.0, 3.0, 1.0, 7.5])
+def test_blur_unsharp(T, dt, radius):
+    for (w, h) in [(333, 217), (40, 30)]:
+        src = rand_img(w, h, dt, 3)
+        d = to_dev(src)
+        assert_close(T.blur(d, radius), O.blur(src, radius), f"blur {radius}")
+        assert_close(T.unsharp_mask(d, "gaussian", radius, 1.0, 0.0), O.unsharp_mask(src, "gaussian", radius, 1.0, 0.0), "unsharp")
+        assert_close(T.unsharp_mask(d, "gaussian", radius, 0.7, 0.05), O.unsharp_mask(src, "gaussian", radius, 0.7, 0.05),
+                     "unsharp thr", lsb=1)
+
+
+def test_blur_constant_image(T):
+    # known answer: blurring a constant image returns the constant (to rounding)
+    src = np.full((50, 70, 4), 0.375, np.float32)
+    got = to_host(T.blur(to_dev(src), 10.0))
+    assert np.abs(got - 0.375).max() < 1e-6
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+def test_resize(T, dt):
+    src = rand_img(160, 90, dt, 4)
+    d = to_dev(src)
+    for size in [(320, 180), (80, 45), (160, 90), (200, 50), (33, 77)]:
+        assert_close(T.resize(d, size), O.resize(src, size), f"resize {size}")
+    assert_close(T.resize(d, (100, 60), "lanczos3", 0.0), O.resize(src, (100, 60), "lanczos3", 0.0), "resize lanczos3")
+    assert_close(T.resize(d, (300, 200), "blackman-harris", 0.0), O.resize(src, (300, 200), "blackman-harris", 0.0), "resize bh")
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+@pytest.mark.parametrize("angle", [45.0, 0.0, 90.0, -30.0, 360.0, 181.5])
+def test_rotate(T, dt, angle):
+    src = rand_img(160, 90, dt, 5)
+    assert_close(T.rotate(to_dev(src), angle), O.rotate(src, angle), f"rotate {angle}")
+
+
+@pytest.mark.parametrize("dta", NP_TYPES)
+@pytest.mark.parametrize("dtb", NP_TYPES)
+def test_transitions_and_over(T, dta, dtb):
+    w, h = 333, 217
+    a, b = rand_img(w, h, dta, 6), rand_img(w, h, dtb, 7)
+    da, db = to_dev(a), to_dev(b)
+    exact_ok = True
+    for v in [0.0, 1.0 / 6.0, 0.5, 5.0 / 6.0, 1.0]:
+        assert_exact(T.dissolve(da, db, v), O.dissolve(a, b, v), f"dissolve {v}")
+        for vertical in (False, True):
+            assert_exact(T.wipe(da, db, v, vertical), O.wipe(a, b, v, vertical), f"wipe {v} {vertical}")
+    assert_exact(T.over(da, db, premult_fg=True), O.over(O.premult(a), b), "premult+over")
+    assert_exact(T.over(da, db, premult_fg=False), O.over(a, b), "over")
+    assert exact_ok
+
+
+def test_wipe_wide_frame(T):
+    # the 200 px ramp needs a frame wider than the fixtures' test sizes
+    a, b = rand_img(1280, 720, np.uint8, 8, "one"), rand_img(1280, 720, np.uint8, 9)
+    da, db = to_dev(a), to_dev(b)
+    for v in [0.0, 0.25, 0.5, 0.75, 0.999]:
+        assert_exact(T.wipe(da, db, v, False), O.wipe(a, b, v, False), "hwipe")
+        assert_exact(T.wipe(da, db, v, True), O.wipe(a, b, v, True), "vwipe")
+
+
+def test_dissolve_known_answers(T):
+    a, b = rand_img(64, 48, np.float32, 10), rand_img(64, 48, np.float32, 11)
+    assert_exact(T.dissolve(to_dev(a), to_dev(b), 0.0), a, "dissolve(0) = from")
+    assert_exact(T.dissolve(to_dev(a), to_dev(b), 1.0), b, "dissolve(1) = to")
+
+
+def test_paste_and_comp_resize(T):
+    # CompNode's fit-resize path: resize fg into bg's box, paste on transparent, over
+    fg = rand_img(64, 36, np.uint8, 12)
+    bg = rand_img(128, 72, np.uint8, 13, "one")
+    want = O.comp(fg, bg, True)
+    dfg = T.premult(to_dev(fg))
+    box = O.fit((128, 72), (64, 36))
+    r = T.resize(dfg, (box[2], box[3]))
+    p = T.paste_on_black(r, (128, 72), box[0], box[1], O.U8)
+    assert_close(T.over(p, to_dev(bg)), want, "comp with fit-resize")
+
+
+@pytest.mark.parametrize("n_layers,trans", [(1, False), (3, True), (10, True)])
+def test_stack_fused_matches_unfused_and_oracle(T, n_layers, trans):
+    w, h = 200, 120
+    rng = np.random.default_rng(20)
+    layers_np, layers_dev = [], []
+    for l in range(n_layers):
+        a = rand_img(w, h, np.float32, 100 + l)
+        b = rand_img(w, h, np.float32, 200 + l) if (trans and l % 2 == 0) else None
+        v = float(rng.random())
+        layers_np.append((a, b, 10.0, 10.0, v))
+        layers_dev.append((to_dev(a), None if b is None else to_dev(b), 10.0, 10.0, v))
+    # oracle: the unfused node chain
+    acc = O.fill(w, h, [0, 0, 0, 1])
+    for a, b, ra, rb, v in layers_np:
+        x = O.blur(a, ra)
+        if b is not None:
+            x = O.dissolve(x, O.blur(b, rb), v)
+        acc = O.comp(x, acc, True)
+    got = T.stack_f32(w, h, [0, 0, 0, 1], layers_dev)
+    assert_close(got, acc, "fused stack vs oracle chain")
+    # unfused CUDA chain
+    acc_d = T.fill(w, h, [0, 0, 0, 1])
+    for a, b, ra, rb, v in layers_dev:
+        x = T.blur(a, ra)
+        if b is not None:
+            x = T.dissolve(x, T.blur(b, rb), v)
+        acc_d = T.over(x, acc_d, premult_fg=True)
+    assert_close(got, to_host(acc_d), "fused stack vs unfused kernels")

@@ -1,0 +1,187 @@
+// tc_api.cu -- runtime part of the C ABI: errors, device/stream management, the
+// stream-ordered frame pool and pinned staging.  See include/toucan_cuda.h.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace tc {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches { 0 };
+
+int fail(int status, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int check_cuda(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return TC_OK;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return fail(TC_ERR_NO_DEVICE, "%s: %s (no CUDA device; there is no CPU fallback)", what, cudaGetErrorString(e));
+    return fail(TC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaDeviceProp p;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) sms = p.multiProcessorCount;
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+int validate(const tc_image* im, const char* name)
+{
+    if (!im) return fail(TC_ERR_INVALID, "%s: null image", name);
+    if (!im->data) return fail(TC_ERR_INVALID, "%s: null data pointer", name);
+    if (im->w <= 0 || im->h <= 0) return fail(TC_ERR_INVALID, "%s: empty image %dx%d", name, im->w, im->h);
+    if (im->type < TC_U8 || im->type > TC_F32) return fail(TC_ERR_INVALID, "%s: unknown pixel type %d", name, im->type);
+    if ((reinterpret_cast<uintptr_t>(im->data) & 15u) != 0) return fail(TC_ERR_INVALID, "%s: data not 16-byte aligned", name);
+    return TC_OK;
+}
+
+} // namespace tc
+
+using namespace tc;
+
+extern "C" {
+
+const char* tc_version(void) { return "toucan_b200 0.1 (sm_100a)"; }
+const char* tc_last_error(void) { return g_err; }
+
+int tc_device_count(int* count)
+{
+    if (!count) return fail(TC_ERR_INVALID, "tc_device_count: null");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return check_cuda(e, "cudaGetDeviceCount");
+    }
+    return TC_OK;
+}
+
+int tc_set_device(int device)
+{
+    TC_CUDA(cudaSetDevice(device));
+    // keep freed blocks cached in the stream-ordered pool: no cudaMalloc in the frame loop
+    cudaMemPool_t pool;
+    TC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long thr = ~0ull;
+    TC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    return TC_OK;
+}
+
+int tc_stream_create(tc_stream* out)
+{
+    if (!out) return fail(TC_ERR_INVALID, "tc_stream_create: null");
+    cudaStream_t s;
+    TC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = s;
+    return TC_OK;
+}
+int tc_stream_destroy(tc_stream s)
+{
+    TC_CUDA(cudaStreamDestroy((cudaStream_t)s));
+    return TC_OK;
+}
+int tc_stream_sync(tc_stream s)
+{
+    TC_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+    return TC_OK;
+}
+
+size_t tc_type_size(int type)
+{
+    static const size_t sz[4] = { 1, 2, 2, 4 };
+    return (type >= 0 && type < 4) ? sz[type] : 0;
+}
+size_t tc_image_bytes(int w, int h, int type)
+{
+    if (w <= 0 || h <= 0) return 0;
+    return (size_t)w * (size_t)h * 4 * tc_type_size(type);
+}
+int tc_type_merge(int a, int b)
+{
+    if (a == b) return a;
+    if (tc_type_size(a) < tc_type_size(b)) {
+        int t = a;
+        a = b;
+        b = t;
+    }
+    if (a == TC_F32) return TC_F32;
+    if ((a == TC_U16 || a == TC_F16) && b == TC_U8) return a;
+    return TC_F32;
+}
+
+int tc_malloc(void** out, size_t bytes, tc_stream s)
+{
+    if (!out) return fail(TC_ERR_INVALID, "tc_malloc: null");
+    *out = nullptr;
+    if (bytes == 0) return TC_OK;
+    TC_CUDA(cudaMallocAsync(out, bytes, (cudaStream_t)s));
+    return TC_OK;
+}
+int tc_free(void* p, tc_stream s)
+{
+    if (!p) return TC_OK;
+    TC_CUDA(cudaFreeAsync(p, (cudaStream_t)s));
+    return TC_OK;
+}
+int tc_pool_trim(void)
+{
+    int dev = 0;
+    TC_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    TC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    TC_CUDA(cudaDeviceSynchronize());
+    TC_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return TC_OK;
+}
+int tc_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return fail(TC_ERR_INVALID, "tc_host_alloc: null");
+    TC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return TC_OK;
+}
+int tc_host_free(void* p)
+{
+    if (!p) return TC_OK;
+    TC_CUDA(cudaFreeHost(p));
+    return TC_OK;
+}
+int tc_upload(void* dst, const void* src, size_t bytes, tc_stream s)
+{
+    if (!dst || !src) return fail(TC_ERR_INVALID, "tc_upload: null pointer");
+    TC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)s));
+    return TC_OK;
+}
+int tc_download(void* dst, const void* src, size_t bytes, tc_stream s)
+{
+    if (!dst || !src) return fail(TC_ERR_INVALID, "tc_download: null pointer");
+    TC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+    return TC_OK;
+}
+int tc_memset(void* dst, int value, size_t bytes, tc_stream s)
+{
+    if (!dst) return fail(TC_ERR_INVALID, "tc_memset: null pointer");
+    TC_CUDA(cudaMemsetAsync(dst, value, bytes, (cudaStream_t)s));
+    return TC_OK;
+}
+unsigned long long tc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+} // extern "C"

@@ -1,0 +1,198 @@
+// tc_conv.cu -- toucan:Blur and toucan:UnsharpMask: the reference's 2-D Gaussian
+// convolve (O(k^2) taps per pixel, plugins/FilterPlugin.cpp:188-202 / :607-618) as a
+// separable shared-memory tiled stencil, one read of the source and one write of the
+// result per pixel.  Edge handling = clamp (OIIO convolve uses WrapClamp), so border
+// tiles are staged with clamped coordinates rather than zero-filling bulk copies.
+//
+// Tolerance op (<= 1e-5 abs / +-1 LSB), so FMA contraction is allowed in this file.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int CONV_MAX_R = 24;   // live taps up to 49 (radius parameter up to ~50)
+constexpr int CONV_TW = 32;
+constexpr int CONV_TH = 32;
+constexpr int CONV_THREADS = 256;
+
+struct ConvParams {
+    int R;           // live half-width: taps -R..R
+    float scale;     // (1/sum K2D) * (1/sum g g): final normalisation
+    float contrast;  // unsharp only
+    float threshold; // unsharp only
+    float g[2 * CONV_MAX_R + 1];
+};
+
+__device__ __forceinline__ float4 fma4(float w, float4 p, float4 a)
+{
+    return make_float4(fmaf(w, p.x, a.x), fmaf(w, p.y, a.y), fmaf(w, p.z, a.z), fmaf(w, p.w, a.w));
+}
+
+// Generic tile kernel: any storage type in/out.
+template <bool UNSHARP>
+__global__ void __launch_bounds__(CONV_THREADS) k_gauss_tile(const Img src, const Img dst, const __grid_constant__ ConvParams P)
+{
+    extern __shared__ float4 smem[];
+    const int R = P.R;
+    const int IW = CONV_TW + 2 * R, IH = CONV_TH + 2 * R;
+    float4* in = smem;            // [IH][IW]
+    float4* mid = smem + IH * IW; // [IH][CONV_TW]
+    const int x0 = blockIdx.x * CONV_TW, y0 = blockIdx.y * CONV_TH;
+
+    for (int i = threadIdx.x; i < IH * IW; i += CONV_THREADS) {
+        const int iy = i / IW, ix = i - iy * IW;
+        in[i] = load_clamp(src, x0 - R + ix, y0 - R + iy);
+    }
+    __syncthreads();
+    // horizontal pass
+    for (int i = threadIdx.x; i < IH * CONV_TW; i += CONV_THREADS) {
+        const int row = i / CONV_TW, col = i - row * CONV_TW;
+        const float4* p = in + row * IW + col;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t <= 2 * R; ++t) acc = fma4(P.g[t], p[t], acc);
+        mid[i] = acc;
+    }
+    __syncthreads();
+    // vertical pass + epilogue
+    for (int i = threadIdx.x; i < CONV_TH * CONV_TW; i += CONV_THREADS) {
+        const int row = i / CONV_TW, col = i - row * CONV_TW;
+        const int x = x0 + col, y = y0 + row;
+        if (x >= dst.w || y >= dst.h) continue;
+        const float4* p = mid + row * CONV_TW + col;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t <= 2 * R; ++t) acc = fma4(P.g[t], p[t * CONV_TW], acc);
+        float4 o = make_float4(acc.x * P.scale, acc.y * P.scale, acc.z * P.scale, acc.w * P.scale);
+        if (UNSHARP) {
+            // Diff = src - Blurry; threshold; *contrast; dst = src + Diff  (OIIO unsharp_mask)
+            const float4 sp = load_black(src, x, y);
+            float d[4] = { sp.x - o.x, sp.y - o.y, sp.z - o.z, sp.w - o.w };
+            const float s4[4] = { sp.x, sp.y, sp.z, sp.w };
+            float r[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float dd = d[c];
+                if (P.threshold > 0.0f && fabsf(dd) < P.threshold) dd = 0.0f;
+                dd = __fmul_rn(dd, P.contrast);
+                r[c] = __fadd_rn(s4[c], dd);
+            }
+            o = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
+    }
+}
+
+// ---- host: kernel weights exactly as OIIO builds them ---------------------------------
+// OIIO fmath.h fast_exp2 / fast_exp (no FMA on the reference build).
+static float fast_exp2_host(float xval)
+{
+    float x = xval < -126.0f ? -126.0f : (xval > 126.0f ? 126.0f : xval);
+    int m = (int)x;
+    x -= (float)m;
+    x = 1.0f - (1.0f - x);
+    volatile float r = 1.33336498402e-3f; // volatile: keep every step rounded to float, unfused
+    r = x * r;
+    r = r + 9.810352697968e-3f;
+    r = x * r;
+    r = r + 5.551834031939e-2f;
+    r = x * r;
+    r = r + 0.2401793301105f;
+    r = x * r;
+    r = r + 0.693144857883f;
+    r = x * r;
+    r = r + 1.0f;
+    float rr = r;
+    uint32_t bits;
+    memcpy(&bits, &rr, 4);
+    bits += ((uint32_t)m << 23);
+    memcpy(&rr, &bits, 4);
+    return rr;
+}
+static float fast_exp_host(float x) { return fast_exp2_host(x * (float)(1.0 / M_LN2)); }
+
+// make_kernel("gaussian", width, width) + convolve(normalize=true): separable factors.
+static int build_params(float width, ConvParams* P)
+{
+    if (!(width > 0.0f)) return fail(TC_ERR_INVALID, "gaussian kernel width must be > 0 (got %g)", width);
+    int n = (int)ceilf(width);
+    if (n < 1) n = 1;
+    if (!(n & 1)) ++n;
+    const int r = n / 2;
+    std::vector<float> g(n);
+    const float radinv = 2.0f / width;
+    for (int i = 0; i < n; ++i) {
+        const float u = fabsf((float)(i - r) * radinv);
+        g[i] = u < 1.0f ? fast_exp_host(-2.0f * (u * u)) : 0.0f;
+    }
+    // 2-D kernel sum in the reference's order (make_kernel normalisation), then the
+    // convolve() normalisation over the normalised kernel.
+    volatile float sum = 0.0f;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) sum = sum + g[i] * g[j];
+    volatile float ksum = 0.0f;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) ksum = ksum + (g[i] * g[j]) / sum;
+    // trim zero-weight edge taps
+    int live = r;
+    while (live > 0 && g[r - live] == 0.0f && g[r + live] == 0.0f) --live;
+    if (live > CONV_MAX_R)
+        return fail(TC_ERR_UNSUPPORTED, "gaussian kernel of width %g needs %d taps per side (max %d)", width, live, CONV_MAX_R);
+    P->R = live;
+    P->scale = (1.0f / ksum) / sum;
+    memset(P->g, 0, sizeof(P->g));
+    for (int i = -live; i <= live; ++i) P->g[i + live] = g[r + i];
+    return TC_OK;
+}
+
+static int launch_conv(const tc_image* dst, const tc_image* src, const ConvParams& P, bool unsharp, tc_stream s)
+{
+    const int IW = CONV_TW + 2 * P.R, IH = CONV_TH + 2 * P.R;
+    const size_t smem = (size_t)(IH * IW + IH * CONV_TW) * sizeof(float4);
+    dim3 grid((dst->w + CONV_TW - 1) / CONV_TW, (dst->h + CONV_TH - 1) / CONV_TH);
+    auto kern = unsharp ? k_gauss_tile<true> : k_gauss_tile<false>;
+    static size_t configured[2] = { 0, 0 };
+    if (smem > configured[unsharp]) {
+        TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[unsharp] = smem;
+    }
+    kern<<<grid, CONV_THREADS, smem, (cudaStream_t)s>>>(view(src), view(dst), P);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_gauss_tile launch");
+}
+
+} // namespace tc
+
+using namespace tc;
+
+extern "C" {
+
+int tc_blur(const tc_image* dst, const tc_image* src, float radius, tc_stream s)
+{
+    int v;
+    if ((v = validate(dst, "tc_blur dst")) != TC_OK) return v;
+    if ((v = validate(src, "tc_blur src")) != TC_OK) return v;
+    ConvParams P;
+    if ((v = build_params(radius, &P)) != TC_OK) return v;
+    P.contrast = 0.f;
+    P.threshold = 0.f;
+    return launch_conv(dst, src, P, false, s);
+}
+
+int tc_unsharp_mask(const tc_image* dst, const tc_image* src, const char* kernel, float width, float contrast,
+                    float threshold, tc_stream s)
+{
+    int v;
+    if ((v = validate(dst, "tc_unsharp_mask dst")) != TC_OK) return v;
+    if ((v = validate(src, "tc_unsharp_mask src")) != TC_OK) return v;
+    if (!kernel || strcmp(kernel, "gaussian") != 0)
+        return fail(TC_ERR_UNSUPPORTED, "tc_unsharp_mask: kernel '%s' (only 'gaussian' is in scope)", kernel ? kernel : "(null)");
+    ConvParams P;
+    if ((v = build_params(width, &P)) != TC_OK) return v;
+    P.contrast = contrast;
+    P.threshold = threshold;
+    return launch_conv(dst, src, P, true, s);
+}
+
+} // extern "C"

@@ -1,0 +1,625 @@
+// tc_pointwise.cu -- every per-pixel effect of the toucan render path as ONE pass over
+// HBM: generators, pointwise filters, address-only transforms, transitions and the
+// premult+over compositor.  Compiled with -fmad=false: the reference (OIIO on baseline
+// x86-64) has no fused multiply-add, and Fill/Checkers/Invert/Flip/Flop/Crop/Wipe/Noise
+// must be bit-exact.
+//
+// Kernel shape: grid-stride over pixels, one RGBA pixel per thread-iteration (128-bit
+// load/store for float, 64-bit for half/u16, 32-bit for u8), 4 independent pixels in
+// flight per thread, grid sized as a multiple of the SM count.
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int PW_THREADS = 256;
+constexpr int PW_UNROLL = 4;
+
+template <class Op>
+__global__ void __launch_bounds__(PW_THREADS) k_pointwise(const __grid_constant__ Op op, const Img dst)
+{
+    const unsigned total = (unsigned)dst.w * (unsigned)dst.h;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < total; base += PW_UNROLL * stride) {
+        float4 v[PW_UNROLL];
+#pragma unroll
+        for (int k = 0; k < PW_UNROLL; ++k) {
+            const unsigned idx = base + k * stride;
+            if (idx < total) {
+                const int y = idx / (unsigned)dst.w;
+                const int x = idx - y * (unsigned)dst.w;
+                v[k] = op(x, y, idx);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PW_UNROLL; ++k) {
+            const unsigned idx = base + k * stride;
+            if (idx < total) store_px(dst.p, dst.type, idx, v[k]);
+        }
+    }
+}
+
+template <class Op>
+static int launch(const Op& op, const tc_image* dst, tc_stream s)
+{
+    const size_t total = (size_t)dst->w * dst->h;
+    if (total >= (1ull << 31)) return fail(TC_ERR_UNSUPPORTED, "image too large (%d x %d)", dst->w, dst->h);
+    const size_t per_block = (size_t)PW_THREADS * PW_UNROLL;
+    size_t blocks = (total + per_block - 1) / per_block;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    k_pointwise<Op><<<(unsigned)blocks, PW_THREADS, 0, (cudaStream_t)s>>>(op, view(dst));
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_pointwise launch");
+}
+
+// A source image read at the destination's pixel position (0 outside).
+struct Src {
+    Img im;
+    int same; // same dimensions as the destination -> linear index can be reused
+    __device__ __forceinline__ float4 at(int x, int y, unsigned idx) const
+    {
+        return same ? load_px(im.p, im.type, idx) : load_black(im, x, y);
+    }
+};
+static Src make_src(const tc_image* src, const tc_image* dst)
+{
+    return Src { view(src), (src->w == dst->w && src->h == dst->h) ? 1 : 0 };
+}
+
+__device__ __forceinline__ float lerp_oiio(float a, float b, float x)
+{
+    // OIIO fmath.h lerp: v0*(1-x) + v1*x
+    return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, x)), __fmul_rn(b, x));
+}
+__device__ __forceinline__ float luma709(float4 p)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, p.x), __fmul_rn(0.7152f, p.y)), __fmul_rn(0.0722f, p.z));
+}
+
+// ---- generators ------------------------------------------------------------------------
+struct FillOp {
+    float4 c;
+    __device__ float4 operator()(int, int, unsigned) const { return c; }
+};
+struct CheckerOp {
+    float4 c1, c2;
+    int cw, ch;
+    __device__ float4 operator()(int x, int y, unsigned) const { return ((x / cw + y / ch) & 1) ? c2 : c1; }
+};
+struct GradientOp {
+    float4 c1, c2;
+    float denom;
+    int vertical;
+    __device__ float4 operator()(int x, int y, unsigned) const
+    {
+        const float v = __fdiv_rn((float)(vertical ? y : x), denom);
+        float4 r = make_float4(lerp_oiio(c1.x, c2.x, v), lerp_oiio(c1.y, c2.y, v), lerp_oiio(c1.z, c2.z, v),
+                               lerp_oiio(c1.w, c2.w, v));
+        // horizontal: the reference ramps a UINT8 temporary, rotates and copies it
+        return vertical ? r : quant4(r, TC_U8);
+    }
+};
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
+__device__ __forceinline__ uint32_t bjfinal(uint32_t a, uint32_t b, uint32_t c)
+{
+    c ^= b; c -= rotl32(b, 14);
+    a ^= c; a -= rotl32(c, 11);
+    b ^= a; b -= rotl32(a, 25);
+    c ^= b; c -= rotl32(b, 16);
+    a ^= c; a -= rotl32(c, 4);
+    b ^= a; b -= rotl32(a, 14);
+    c ^= b; c -= rotl32(b, 24);
+    return c;
+}
+__device__ __forceinline__ float hashrand(uint32_t xy, int c, int seed)
+{
+    const uint32_t h = bjfinal(xy, (uint32_t)c, (uint32_t)seed) & 0xfffffu;
+    return __fmul_rn((float)h, 1.0f / 1048576.0f);
+}
+// ln(x) in double from + - * / only (the fdlibm e_log scheme), so host restatements of the
+// same sequence agree to the bit.  Callers pass normal positive finite x.
+__device__ double det_log(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    int i = (hx + 0x95f64) & 0x100000;
+    x = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
+    k += (i >> 20);
+    const double f = __dsub_rn(x, 1.0), dk = (double)k;
+    if ((0x000fffff & (2 + hx)) < 3) {
+        if (f == 0.0) {
+            if (k == 0) return 0.0;
+            return __dadd_rn(__dmul_rn(dk, ln2_hi), __dmul_rn(dk, ln2_lo));
+        }
+        const double R = __dmul_rn(__dmul_rn(f, f), __dsub_rn(0.5, __dmul_rn(0.33333333333333333, f)));
+        if (k == 0) return __dsub_rn(f, R);
+        return __dsub_rn(__dmul_rn(dk, ln2_hi), __dsub_rn(__dsub_rn(R, __dmul_rn(dk, ln2_lo)), f));
+    }
+    const double s = __ddiv_rn(f, __dadd_rn(2.0, f));
+    const double z = __dmul_rn(s, s);
+    i = hx - 0x6147a;
+    const double w = __dmul_rn(z, z);
+    const int j = 0x6b851 - hx;
+    const double t1 = __dmul_rn(w, __dadd_rn(Lg2, __dmul_rn(w, __dadd_rn(Lg4, __dmul_rn(w, Lg6)))));
+    const double t2 = __dmul_rn(
+        z, __dadd_rn(Lg1, __dmul_rn(w, __dadd_rn(Lg3, __dmul_rn(w, __dadd_rn(Lg5, __dmul_rn(w, Lg7)))))));
+    i |= j;
+    const double R = __dadd_rn(t2, t1);
+    if (i > 0) {
+        const double hfsq = __dmul_rn(__dmul_rn(0.5, f), f);
+        if (k == 0) return __dsub_rn(f, __dsub_rn(hfsq, __dmul_rn(s, __dadd_rn(hfsq, R))));
+        return __dsub_rn(__dmul_rn(dk, ln2_hi),
+                         __dsub_rn(__dsub_rn(hfsq, __dadd_rn(__dmul_rn(s, __dadd_rn(hfsq, R)), __dmul_rn(dk, ln2_lo))), f));
+    }
+    if (k == 0) return __dsub_rn(f, __dmul_rn(s, __dsub_rn(f, R)));
+    return __dsub_rn(__dmul_rn(dk, ln2_hi), __dsub_rn(__dsub_rn(__dmul_rn(s, __dsub_rn(f, R)), __dmul_rn(dk, ln2_lo)), f));
+}
+// Marsaglia polar method on the position hash.
+__device__ float hashnormal(uint32_t xy, int c, int seed)
+{
+    float xr, yr, r2;
+    int s = seed - 1;
+    do {
+        s++;
+        xr = (float)__dsub_rn(__dmul_rn(2.0, (double)hashrand(xy, c, s)), 1.0);
+        yr = (float)__dsub_rn(__dmul_rn(2.0, (double)hashrand(xy, c, s + 139)), 1.0);
+        r2 = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(yr, yr));
+    } while (r2 > 1.0f || r2 == 0.0f);
+    const double q = __ddiv_rn(__dmul_rn(-2.0, det_log((double)r2)), (double)r2);
+    const float M = (float)__dsqrt_rn(q);
+    return __fmul_rn(xr, M);
+}
+struct NoiseOp {
+    float A, B;
+    int type, mono, seed;
+    __device__ float4 operator()(int x, int y, unsigned) const
+    {
+        const uint32_t xy = bjfinal((uint32_t)x, (uint32_t)y, 0u);
+        float p[4] = { 0.f, 0.f, 0.f, 0.f }; // the output buffer is zero-initialised (ImageEffect.cpp:93)
+        float n = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (type == 0) {
+                if (c == 0 || !mono) n = __fadd_rn(A, __fmul_rn(B, hashnormal(xy, c, seed)));
+                p[c] = __fadd_rn(p[c], n);
+            } else if (type == 1) {
+                if (c == 0 || !mono) n = __fadd_rn(A, __fmul_rn(__fsub_rn(B, A), hashrand(xy, c, seed)));
+                p[c] = __fadd_rn(p[c], n);
+            } else {
+                if (c == 0 || !mono) n = hashrand(xy, c, seed);
+                if (n < B) p[c] = A;
+            }
+        }
+        return make_float4(p[0], p[1], p[2], p[3]);
+    }
+};
+
+// ---- pointwise filters -----------------------------------------------------------------
+struct InvertOp {
+    Src s;
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        float4 p = s.at(x, y, i);
+        p.x = __fadd_rn(__fmul_rn(p.x, -1.0f), 1.0f);
+        p.y = __fadd_rn(__fmul_rn(p.y, -1.0f), 1.0f);
+        p.z = __fadd_rn(__fmul_rn(p.z, -1.0f), 1.0f);
+        return p;
+    }
+};
+struct PowOp {
+    Src s;
+    float v;
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        float4 p = s.at(x, y, i);
+        return make_float4(powf(p.x, v), powf(p.y, v), powf(p.z, v), powf(p.w, v));
+    }
+};
+struct SaturateOp {
+    Src s;
+    float v;
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        float4 p = s.at(x, y, i);
+        const float l = luma709(p);
+        p.x = lerp_oiio(l, p.x, v);
+        p.y = lerp_oiio(l, p.y, v);
+        p.z = lerp_oiio(l, p.z, v);
+        return p;
+    }
+};
+struct ColorMapOp {
+    Src s;
+    int n; // knots (0 = unknown map: RGB stays zero, alpha copied)
+    float k[17 * 3];
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        const float4 p = s.at(x, y, i);
+        float4 o = make_float4(0.f, 0.f, 0.f, p.w);
+        if (n) {
+            float t = fminf(fmaxf(luma709(p), 0.0f), 1.0f);
+            const int nsegs = n - 1;
+            const float xs = __fmul_rn(t, (float)nsegs);
+            const float fl = floorf(xs);
+            const int seg = (int)fl;
+            const float fr = __fsub_rn(xs, fl);
+            const int nxt = min(seg + 1, nsegs);
+            o.x = lerp_oiio(k[seg * 3 + 0], k[nxt * 3 + 0], fr);
+            o.y = lerp_oiio(k[seg * 3 + 1], k[nxt * 3 + 1], fr);
+            o.z = lerp_oiio(k[seg * 3 + 2], k[nxt * 3 + 2], fr);
+        }
+        return o;
+    }
+};
+struct PremultOp {
+    Src s;
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        float4 p = s.at(x, y, i);
+        if (p.w != 1.0f) {
+            p.x = __fmul_rn(p.x, p.w);
+            p.y = __fmul_rn(p.y, p.w);
+            p.z = __fmul_rn(p.z, p.w);
+        }
+        return p;
+    }
+};
+struct UnpremultOp {
+    Src s;
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        float4 p = s.at(x, y, i);
+        if (p.w != 0.0f && p.w != 1.0f) {
+            p.x = __fdiv_rn(p.x, p.w);
+            p.y = __fdiv_rn(p.y, p.w);
+            p.z = __fdiv_rn(p.z, p.w);
+        }
+        return p;
+    }
+};
+
+// colour convert: decode curve -> 3x3 -> encode curve (alpha untouched)
+__device__ __forceinline__ float cc_curve(int id, int encode, float p, float x)
+{
+    switch (id) {
+    case 1:
+        if (x <= 0.0f) return x;
+        return powf(x, encode ? __fdiv_rn(1.0f, p) : p);
+    case 2:
+        if (!encode) return x <= 0.04045f ? __fdiv_rn(x, 12.92f) : powf(__fdiv_rn(__fadd_rn(x, 0.055f), 1.055f), 2.4f);
+        return x <= 0.0031308f ? __fmul_rn(x, 12.92f) : __fsub_rn(__fmul_rn(1.055f, powf(x, 1.0f / 2.4f)), 0.055f);
+    case 3:
+        if (encode)
+            return x <= 0.0078125f ? __fadd_rn(__fmul_rn(10.5402377416545f, x), 0.0729055341958355f)
+                                   : __fdiv_rn(__fadd_rn(log2f(x), 9.72f), 17.52f);
+        return x <= 0.155251141552511f ? __fdiv_rn(__fsub_rn(x, 0.0729055341958355f), 10.5402377416545f)
+                                       : exp2f(__fsub_rn(__fmul_rn(x, 17.52f), 9.72f));
+    case 4:
+        if (encode) {
+            if (x <= 0.0f) return -0.3584474886f;
+            if (x < 0.000030517578125f)
+                return __fdiv_rn(__fadd_rn(log2f(__fadd_rn(0.0000152587890625f, __fmul_rn(x, 0.5f))), 9.72f), 17.52f);
+            return __fdiv_rn(__fadd_rn(log2f(x), 9.72f), 17.52f);
+        }
+        if (x <= -0.3013698630f)
+            return __fmul_rn(__fsub_rn(exp2f(__fsub_rn(__fmul_rn(x, 17.52f), 9.72f)), 0.0000152587890625f), 2.0f);
+        return exp2f(__fsub_rn(__fmul_rn(x, 17.52f), 9.72f));
+    default: return x;
+    }
+}
+struct ColorConvertOp {
+    Src s;
+    int curve_in, curve_out;
+    float p_in, p_out;
+    float m[9];
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        const float4 p = s.at(x, y, i);
+        const float l0 = cc_curve(curve_in, 0, p_in, p.x), l1 = cc_curve(curve_in, 0, p_in, p.y),
+                    l2 = cc_curve(curve_in, 0, p_in, p.z);
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __fadd_rn(__fadd_rn(__fmul_rn(m[c * 3 + 0], l0), __fmul_rn(m[c * 3 + 1], l1)),
+                                      __fmul_rn(m[c * 3 + 2], l2));
+            o[c] = cc_curve(curve_out, 1, p_out, v);
+        }
+        return make_float4(o[0], o[1], o[2], p.w);
+    }
+};
+
+// ---- address-only transforms ---------------------------------------------------------
+struct CropOp {
+    Img src;
+    int px, py, cw, ch;
+    __device__ float4 operator()(int x, int y, unsigned) const
+    {
+        if (x >= cw || y >= ch) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return load_black(src, px + x, py + y);
+    }
+};
+struct FlipOp {
+    Img src;
+    __device__ float4 operator()(int x, int y, unsigned) const { return load_black(src, x, src.h - 1 - y); }
+};
+struct FlopOp {
+    Img src;
+    __device__ float4 operator()(int x, int y, unsigned) const { return load_black(src, src.w - 1 - x, y); }
+};
+struct ConvertOp {
+    Src s;
+    __device__ float4 operator()(int x, int y, unsigned i) const { return s.at(x, y, i); }
+};
+struct PasteOp {
+    Img src;
+    int ox, oy;
+    __device__ float4 operator()(int x, int y, unsigned) const { return load_black(src, x - ox, y - oy); }
+};
+
+// ---- transitions -----------------------------------------------------------------------
+struct DissolveOp {
+    Src a, b;
+    float qiv, qv; // the fill constants, already quantised to each source's storage type
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        const float4 p = a.at(x, y, i), q = b.at(x, y, i);
+        const int ta = a.im.type, tb = b.im.type;
+        return make_float4(__fadd_rn(quant(__fmul_rn(p.x, qiv), ta), quant(__fmul_rn(q.x, qv), tb)),
+                           __fadd_rn(quant(__fmul_rn(p.y, qiv), ta), quant(__fmul_rn(q.y, qv), tb)),
+                           __fadd_rn(quant(__fmul_rn(p.z, qiv), ta), quant(__fmul_rn(q.z, qv), tb)),
+                           __fadd_rn(quant(__fmul_rn(p.w, qiv), ta), quant(__fmul_rn(q.w, qv), tb)));
+    }
+};
+struct WipeOp {
+    Src a, b;
+    int mw, mh; // matte size (= `from` size)
+    int edge, vertical;
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        float mf = 0.f, mt = 0.f;
+        if (x < mw && y < mh) {
+            const int k = (vertical ? y : x) - edge;
+            if (k < 0) {
+                mf = 0.f;
+                mt = 1.f;
+            } else if (k < 200) {
+                // 200-row UINT8 ramp: row r = u8(lerp(0, 1, r/199))
+                mf = quant(lerp_oiio(0.f, 1.f, __fdiv_rn((float)k, 199.0f)), TC_U8);
+                mt = quant(lerp_oiio(0.f, 1.f, __fdiv_rn((float)(199 - k), 199.0f)), TC_U8);
+            } else {
+                mf = 1.f;
+                mt = 0.f;
+            }
+        }
+        const float4 p = a.at(x, y, i), q = b.at(x, y, i);
+        const int ta = a.im.type, tb = b.im.type;
+        return make_float4(__fadd_rn(quant(__fmul_rn(p.x, mf), ta), quant(__fmul_rn(q.x, mt), tb)),
+                           __fadd_rn(quant(__fmul_rn(p.y, mf), ta), quant(__fmul_rn(q.y, mt), tb)),
+                           __fadd_rn(quant(__fmul_rn(p.z, mf), ta), quant(__fmul_rn(q.z, mt), tb)),
+                           __fadd_rn(quant(__fmul_rn(p.w, mf), ta), quant(__fmul_rn(q.w, mt), tb)));
+    }
+};
+
+// ---- compositor: premult(fg) (stored in fg's type) + over ---------------------------
+struct OverOp {
+    Src fg, bg;
+    int premult;
+    __device__ float4 operator()(int x, int y, unsigned i) const
+    {
+        float4 a = fg.at(x, y, i);
+        const float4 b = bg.at(x, y, i);
+        if (premult) {
+            if (a.w != 1.0f) {
+                a.x = __fmul_rn(a.x, a.w);
+                a.y = __fmul_rn(a.y, a.w);
+                a.z = __fmul_rn(a.z, a.w);
+            }
+            a = quant4(a, fg.im.type);
+        }
+        const float alpha = fminf(fmaxf(a.w, 0.0f), 1.0f);
+        const float oma = __fsub_rn(1.0f, alpha);
+        return make_float4(__fadd_rn(a.x, __fmul_rn(oma, b.x)), __fadd_rn(a.y, __fmul_rn(oma, b.y)),
+                           __fadd_rn(a.z, __fmul_rn(oma, b.z)), __fadd_rn(a.w, __fmul_rn(oma, b.w)));
+    }
+};
+
+// colour-map knot tables (tc_tables.cpp)
+int color_map_knots(const char* name, const float** knots);
+// colour-space table (tc_tables.cpp)
+int color_convert_setup(const char* from, const char* to, int* curve_in, float* p_in, float m[9], int* curve_out, float* p_out);
+
+static inline float4 f4(const float c[4]) { return make_float4(c[0], c[1], c[2], c[3]); }
+
+// host-side restatement of the storage round trip (for constants baked on the host)
+static float quant_host(float v, int type)
+{
+    auto q = [](float f, float scale) {
+        float s = f * scale;
+        s += (s < 0.0f ? -0.5f : 0.5f);
+        s = s < 0.0f ? 0.0f : (s > scale ? scale : s);
+        return (float)(unsigned)s * (1.0f / scale);
+    };
+    switch (type) {
+    case TC_U8: return q(v, 255.0f);
+    case TC_U16: return q(v, 65535.0f);
+    case TC_F16: return __half2float(__float2half_rn(v));
+    default: return v;
+    }
+}
+
+} // namespace tc
+
+using namespace tc;
+
+#define TC_VALIDATE(im, name)                   \
+    do {                                        \
+        int _v = validate(im, name);            \
+        if (_v != TC_OK) return _v;             \
+    } while (0)
+
+extern "C" {
+
+int tc_fill(const tc_image* dst, const float color[4], tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_fill dst");
+    if (!color) return fail(TC_ERR_INVALID, "tc_fill: null color");
+    return launch(FillOp { f4(color) }, dst, s);
+}
+
+int tc_checkers(const tc_image* dst, int cw, int ch, const float c1[4], const float c2[4], tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_checkers dst");
+    if (!c1 || !c2) return fail(TC_ERR_INVALID, "tc_checkers: null color");
+    if (cw <= 0 || ch <= 0) return fail(TC_ERR_INVALID, "tc_checkers: checker size %dx%d (the reference divides by zero here)", cw, ch);
+    return launch(CheckerOp { f4(c1), f4(c2), cw, ch }, dst, s);
+}
+
+int tc_gradient(const tc_image* dst, const float c1[4], const float c2[4], int vertical, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_gradient dst");
+    if (!c1 || !c2) return fail(TC_ERR_INVALID, "tc_gradient: null color");
+    const int n = (vertical ? dst->h : dst->w) - 1;
+    return launch(GradientOp { f4(c1), f4(c2), (float)(n > 1 ? n : 1), vertical ? 1 : 0 }, dst, s);
+}
+
+int tc_noise(const tc_image* dst, const char* type, float a, float b, int mono, int seed, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_noise dst");
+    int t = -1;
+    if (type) {
+        if (!strcmp(type, "gaussian") || !strcmp(type, "normal")) t = 0;
+        else if (!strcmp(type, "white") || !strcmp(type, "uniform")) t = 1;
+        else if (!strcmp(type, "salt")) t = 2;
+    }
+    if (t < 0) {
+        // OIIO noise() fails on an unknown type and the zero-initialised buffer is returned
+        const float z[4] = { 0.f, 0.f, 0.f, 0.f };
+        return launch(FillOp { f4(z) }, dst, s);
+    }
+    return launch(NoiseOp { a, b, t, mono ? 1 : 0, seed }, dst, s);
+}
+
+int tc_invert(const tc_image* dst, const tc_image* src, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_invert dst");
+    TC_VALIDATE(src, "tc_invert src");
+    return launch(InvertOp { make_src(src, dst) }, dst, s);
+}
+int tc_pow(const tc_image* dst, const tc_image* src, float value, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_pow dst");
+    TC_VALIDATE(src, "tc_pow src");
+    return launch(PowOp { make_src(src, dst), value }, dst, s);
+}
+int tc_saturate(const tc_image* dst, const tc_image* src, float value, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_saturate dst");
+    TC_VALIDATE(src, "tc_saturate src");
+    return launch(SaturateOp { make_src(src, dst), value }, dst, s);
+}
+int tc_color_map(const tc_image* dst, const tc_image* src, const char* map_name, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_color_map dst");
+    TC_VALIDATE(src, "tc_color_map src");
+    ColorMapOp op;
+    op.s = make_src(src, dst);
+    const float* knots = nullptr;
+    op.n = map_name ? color_map_knots(map_name, &knots) : 0;
+    memset(op.k, 0, sizeof(op.k));
+    if (op.n) memcpy(op.k, knots, sizeof(float) * 3 * op.n);
+    return launch(op, dst, s);
+}
+int tc_premult(const tc_image* dst, const tc_image* src, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_premult dst");
+    TC_VALIDATE(src, "tc_premult src");
+    return launch(PremultOp { make_src(src, dst) }, dst, s);
+}
+int tc_unpremult(const tc_image* dst, const tc_image* src, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_unpremult dst");
+    TC_VALIDATE(src, "tc_unpremult src");
+    return launch(UnpremultOp { make_src(src, dst) }, dst, s);
+}
+int tc_color_convert(const tc_image* dst, const tc_image* src, const char* fromspace, const char* tospace, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_color_convert dst");
+    TC_VALIDATE(src, "tc_color_convert src");
+    ColorConvertOp op;
+    op.s = make_src(src, dst);
+    if (!fromspace || !tospace ||
+        !color_convert_setup(fromspace, tospace, &op.curve_in, &op.p_in, op.m, &op.curve_out, &op.p_out)) {
+        // OIIO colorconvert() fails on an unknown colour space; the output keeps its zero fill
+        const float z[4] = { 0.f, 0.f, 0.f, 0.f };
+        return launch(FillOp { f4(z) }, dst, s);
+    }
+    return launch(op, dst, s);
+}
+
+int tc_crop(const tc_image* dst, const tc_image* src, int px, int py, int cw, int ch, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_crop dst");
+    TC_VALIDATE(src, "tc_crop src");
+    return launch(CropOp { view(src), px, py, cw, ch }, dst, s);
+}
+int tc_flip(const tc_image* dst, const tc_image* src, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_flip dst");
+    TC_VALIDATE(src, "tc_flip src");
+    return launch(FlipOp { view(src) }, dst, s);
+}
+int tc_flop(const tc_image* dst, const tc_image* src, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_flop dst");
+    TC_VALIDATE(src, "tc_flop src");
+    return launch(FlopOp { view(src) }, dst, s);
+}
+int tc_convert(const tc_image* dst, const tc_image* src, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_convert dst");
+    TC_VALIDATE(src, "tc_convert src");
+    return launch(ConvertOp { make_src(src, dst) }, dst, s);
+}
+int tc_paste_on_black(const tc_image* dst, int ox, int oy, const tc_image* src, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_paste_on_black dst");
+    TC_VALIDATE(src, "tc_paste_on_black src");
+    return launch(PasteOp { view(src), ox, oy }, dst, s);
+}
+
+int tc_dissolve(const tc_image* dst, const tc_image* from, const tc_image* to, double value, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_dissolve dst");
+    TC_VALIDATE(from, "tc_dissolve from");
+    TC_VALIDATE(to, "tc_dissolve to");
+    const float v = (float)value;
+    const float iv = (float)(1.0 - value);
+    return launch(DissolveOp { make_src(from, dst), make_src(to, dst), quant_host(iv, from->type), quant_host(v, to->type) },
+                  dst, s);
+}
+int tc_wipe(const tc_image* dst, const tc_image* from, const tc_image* to, double value, int vertical, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_wipe dst");
+    TC_VALIDATE(from, "tc_wipe from");
+    TC_VALIDATE(to, "tc_wipe to");
+    const int edge = vertical ? (int)(from->h * value) : (int)(from->w * value);
+    return launch(WipeOp { make_src(from, dst), make_src(to, dst), from->w, from->h, edge, vertical ? 1 : 0 }, dst, s);
+}
+int tc_over(const tc_image* dst, const tc_image* fg, const tc_image* bg, int premult_fg, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_over dst");
+    TC_VALIDATE(fg, "tc_over fg");
+    TC_VALIDATE(bg, "tc_over bg");
+    return launch(OverOp { make_src(fg, dst), make_src(bg, dst), premult_fg ? 1 : 0 }, dst, s);
+}
+
+} // extern "C"
