@@ -108,8 +108,8 @@ PLUGIN_MODULES = {
 def build_host(verbose=False, force=False):
     """C++ host library, OFX plug-in modules and the CLI.  Needs libtoucan_cuda.so."""
     src_dir = os.path.join(HOST, "toucanRender")
-    if not os.path.isdir(src_dir):
-        return None
+    if not os.path.isdir(src_dir) or not all(os.path.exists(os.path.join(src_dir, f)) for f in HOST_LIB_SOURCES):
+        return None  # host tree incomplete: nothing to build yet
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.join(LIB, "plugins"), exist_ok=True)
     hdrs = _headers(HOST) + _headers(os.path.join(ROOT, "include"))

@@ -1,0 +1,109 @@
+#include "Comp.h"
+
+#include "StackFusion.h"
+#include "Util.h"
+
+namespace toucan
+{
+    CompNode::CompNode(const std::vector<std::shared_ptr<IImageNode> >& inputs) :
+        IImageNode("Comp", inputs)
+    {}
+
+    CompNode::~CompNode()
+    {}
+
+    void CompNode::setPremult(bool premult) { _premult = premult; }
+
+    void CompNode::setResize(bool resize) { _resize = resize; }
+
+    Image CompNode::composite(const Image& fgIn, const Image& bg) const
+    {
+        const ImageSpec& fgSpec = fgIn.spec();
+        const ImageSpec& bgSpec = bg.spec();
+        const bool fgValid = fgSpec.width > 0 && fgSpec.height > 0;
+        const bool bgValid = bgSpec.width > 0 && bgSpec.height > 0;
+        if (!fgValid)
+        {
+            return bg;
+        }
+        tc_stream stream = DeviceContext::stream();
+        if (bgValid && (fgSpec.width != bgSpec.width || fgSpec.height != bgSpec.height))
+        {
+            // Slow path (Comp.cpp:37-68): premult -> resize into the fitted box -> paste on a
+            // transparent buffer of the background's size and type -> over.
+            Image fg = fgIn;
+            if (_premult)
+            {
+                Image pm(fgSpec);
+                const tc_image s = fgIn.view(), d = pm.view();
+                tcCheck(tc_premult(&d, &s, stream), "tc_premult");
+                fg = pm;
+            }
+            const IMATH_NAMESPACE::Box2i box = fit(
+                IMATH_NAMESPACE::V2i(bgSpec.width, bgSpec.height),
+                IMATH_NAMESPACE::V2i(fgSpec.width, fgSpec.height));
+            const int bw = box.max.x - box.min.x + 1;
+            const int bh = box.max.y - box.min.y + 1;
+            Image pasted(ImageSpec(bgSpec.width, bgSpec.height, bgSpec.nchannels, bgSpec.format));
+            if (bw > 0 && bh > 0)
+            {
+                Image resized(ImageSpec(bw, bh, fgSpec.nchannels, fgSpec.format));
+                const tc_image s = fg.view(), r = resized.view(), p = pasted.view();
+                tcCheck(tc_resize(&r, &s, "", 0.f, stream), "tc_resize");
+                tcCheck(tc_paste_on_black(&p, box.min.x, box.min.y, &r, stream), "tc_paste_on_black");
+            }
+            else
+            {
+                tcCheck(tc_memset(pasted.data(), 0, pasted.spec().image_bytes(), stream), "tc_memset");
+            }
+            Image out(ImageSpec(bgSpec.width, bgSpec.height, 4, tc_type_merge(bgSpec.format, bgSpec.format)));
+            const tc_image f = pasted.view(), b = bg.view(), o = out.view();
+            tcCheck(tc_over(&o, &f, &b, 0, stream), "tc_over");
+            return out;
+        }
+        if (!bgValid)
+        {
+            // over() with an empty background: the foreground alone
+            if (!_premult) return fgIn;
+            Image pm(fgSpec);
+            const tc_image s = fgIn.view(), d = pm.view();
+            tcCheck(tc_premult(&d, &s, stream), "tc_premult");
+            return pm;
+        }
+        // Fast path: premult + over fused into one pass.
+        Image out(ImageSpec(bgSpec.width, bgSpec.height, 4, tc_type_merge(fgSpec.format, bgSpec.format)));
+        const tc_image f = fgIn.view(), b = bg.view(), o = out.view();
+        tcCheck(tc_over(&o, &f, &b, _premult ? 1 : 0, stream), "tc_over");
+        return out;
+    }
+
+    Image CompNode::exec()
+    {
+        Image buf;
+        if (_inputs.size() > 1 && _inputs[0] && _inputs[1])
+        {
+            // Cross-node fusion: a chain of CompNodes over [Dissolve of] [Blur of] float
+            // sources collapses into one pass (StackFusion.h).  Falls through when the
+            // pattern does not match.
+            if (_premult && tryFusedStack(*this, buf))
+            {
+                return buf;
+            }
+            const Image fg = _inputs[0]->exec();
+            const Image bg = _inputs[1]->exec();
+            buf = composite(fg, bg);
+        }
+        else if (1 == _inputs.size() && _inputs[0])
+        {
+            buf = _inputs[0]->exec();
+            if (_premult && buf.spec().width > 0 && buf.spec().height > 0)
+            {
+                Image pm(buf.spec());
+                const tc_image s = buf.view(), d = pm.view();
+                tcCheck(tc_premult(&d, &s, DeviceContext::stream()), "tc_premult");
+                buf = pm;
+            }
+        }
+        return buf;
+    }
+}

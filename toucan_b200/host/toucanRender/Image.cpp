@@ -1,0 +1,138 @@
+#include "Image.h"
+
+#include <sstream>
+
+namespace toucan
+{
+    namespace
+    {
+        struct Binding
+        {
+            bool bound = false;
+            int device = 0;
+            tc_stream stream = nullptr;
+            bool ownStream = false;
+        };
+        thread_local Binding binding;
+    }
+
+    void tcCheck(int status, const char* what)
+    {
+        if (status != TC_OK)
+        {
+            std::stringstream ss;
+            ss << what << ": " << tc_last_error() << " (status " << status << ")";
+            throw std::runtime_error(ss.str());
+        }
+    }
+
+    void DeviceContext::bind(int device, tc_stream stream)
+    {
+        tcCheck(tc_set_device(device), "tc_set_device");
+        if (binding.bound && binding.ownStream && binding.stream)
+        {
+            tc_stream_destroy(binding.stream);
+        }
+        binding.device = device;
+        binding.ownStream = false;
+        binding.stream = stream;
+        if (!stream)
+        {
+            tcCheck(tc_stream_create(&binding.stream), "tc_stream_create");
+            binding.ownStream = true;
+        }
+        binding.bound = true;
+    }
+
+    bool DeviceContext::isBound() { return binding.bound; }
+
+    int DeviceContext::device()
+    {
+        if (!binding.bound) bind(0);
+        return binding.device;
+    }
+
+    tc_stream DeviceContext::stream()
+    {
+        if (!binding.bound) bind(0);
+        return binding.stream;
+    }
+
+    void DeviceContext::synchronize()
+    {
+        tcCheck(tc_stream_sync(stream()), "tc_stream_sync");
+    }
+
+    std::string toImageDataType(int format)
+    {
+        switch (format)
+        {
+        case TC_U8: return "u8";
+        case TC_U16: return "u16";
+        case TC_F16: return "half";
+        case TC_F32: return "float";
+        default: break;
+        }
+        return "Unknown";
+    }
+
+    struct Image::Buffer
+    {
+        void* p = nullptr;
+        tc_stream stream = nullptr;
+        ~Buffer()
+        {
+            if (p) tc_free(p, stream);
+        }
+    };
+
+    Image::Image(const ImageSpec& spec) : _spec(spec)
+    {
+        const size_t bytes = spec.image_bytes();
+        if (bytes > 0)
+        {
+            if (spec.nchannels != 4)
+            {
+                throw std::runtime_error("toucan::Image: only 4-channel (RGBA) device images are supported");
+            }
+            _buffer = std::make_shared<Buffer>();
+            _buffer->stream = DeviceContext::stream();
+            tcCheck(tc_malloc(&_buffer->p, bytes, _buffer->stream), "tc_malloc");
+            _data = _buffer->p;
+        }
+    }
+
+    Image Image::wrap(void* devicePtr, const ImageSpec& spec)
+    {
+        Image out;
+        out._spec = spec;
+        out._data = devicePtr;
+        return out;
+    }
+
+    Image Image::upload(const void* hostPixels, const ImageSpec& spec)
+    {
+        Image out(spec);
+        if (out._data)
+        {
+            tcCheck(tc_upload(out._data, hostPixels, spec.image_bytes(), DeviceContext::stream()), "tc_upload");
+        }
+        return out;
+    }
+
+    void Image::download(void* hostPixels) const
+    {
+        if (_data)
+        {
+            tcCheck(tc_download(hostPixels, _data, _spec.image_bytes(), DeviceContext::stream()), "tc_download");
+            DeviceContext::synchronize();
+        }
+    }
+
+    std::vector<unsigned char> Image::download() const
+    {
+        std::vector<unsigned char> out(_spec.image_bytes());
+        download(out.data());
+        return out;
+    }
+}

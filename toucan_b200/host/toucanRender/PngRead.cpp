@@ -1,0 +1,222 @@
+#include "PngRead.h"
+
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace toucan
+{
+    namespace
+    {
+        uint32_t be32(const unsigned char* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }
+
+        int paeth(int a, int b, int c)
+        {
+            const int p = a + b - c;
+            const int pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+            if (pa <= pb && pa <= pc) return a;
+            return pb <= pc ? b : c;
+        }
+
+        // OIIO convert_type float -> unsigned: clamp(f*max + 0.5) truncated
+        template <class T>
+        T toUnsigned(float f, float maxv)
+        {
+            float s = f * maxv + 0.5f;
+            if (s < 0.f) s = 0.f;
+            if (s > maxv) s = maxv;
+            return static_cast<T>(s);
+        }
+    }
+
+    bool readPng(const std::string& path, MediaFrame& out)
+    {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) return false;
+        std::vector<unsigned char> file;
+        unsigned char buf[65536];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof(buf), f)) > 0) file.insert(file.end(), buf, buf + n);
+        fclose(f);
+        static const unsigned char sig[8] = { 0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a };
+        if (file.size() < 33 || memcmp(file.data(), sig, 8) != 0) return false;
+
+        uint32_t width = 0, height = 0;
+        int depth = 0, colorType = 0, interlace = 0;
+        std::vector<unsigned char> idat, palette, trns;
+        size_t pos = 8;
+        while (pos + 12 <= file.size())
+        {
+            const uint32_t len = be32(&file[pos]);
+            const char* type = reinterpret_cast<const char*>(&file[pos + 4]);
+            const unsigned char* data = &file[pos + 8];
+            if (pos + 12 + len > file.size()) return false;
+            if (!memcmp(type, "IHDR", 4))
+            {
+                width = be32(data);
+                height = be32(data + 4);
+                depth = data[8];
+                colorType = data[9];
+                interlace = data[12];
+            }
+            else if (!memcmp(type, "PLTE", 4)) palette.assign(data, data + len);
+            else if (!memcmp(type, "tRNS", 4)) trns.assign(data, data + len);
+            else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+            else if (!memcmp(type, "IEND", 4)) break;
+            pos += 12 + len;
+        }
+        if (!width || !height || interlace != 0) return false;
+        int channels = 0;
+        switch (colorType)
+        {
+        case 2: channels = 3; break;
+        case 6: channels = 4; break;
+        case 3: channels = 1; break;
+        default: return false; // grey images are 1-channel in the reference: outside the RGBA path
+        }
+        if (!(depth == 8 || (depth == 16 && colorType != 3))) return false;
+        const size_t bpp = static_cast<size_t>(channels) * depth / 8;
+        const size_t stride = bpp * width;
+        std::vector<unsigned char> raw((stride + 1) * height);
+        uLongf rawLen = static_cast<uLongf>(raw.size());
+        if (uncompress(raw.data(), &rawLen, idat.data(), static_cast<uLong>(idat.size())) != Z_OK || rawLen != raw.size()) return false;
+
+        // undo the scanline filters in place
+        std::vector<unsigned char> pix(stride * height);
+        for (uint32_t y = 0; y < height; ++y)
+        {
+            const unsigned char* in = &raw[(stride + 1) * y];
+            const int ft = in[0];
+            ++in;
+            unsigned char* cur = &pix[stride * y];
+            const unsigned char* up = y ? &pix[stride * (y - 1)] : nullptr;
+            for (size_t i = 0; i < stride; ++i)
+            {
+                const int a = i >= bpp ? cur[i - bpp] : 0;
+                const int b = up ? up[i] : 0;
+                const int c = (up && i >= bpp) ? up[i - bpp] : 0;
+                int v = in[i];
+                switch (ft)
+                {
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) / 2; break;
+                case 4: v += paeth(a, b, c); break;
+                default: break;
+                }
+                cur[i] = static_cast<unsigned char>(v);
+            }
+        }
+
+        const size_t count = static_cast<size_t>(width) * height;
+        out = MediaFrame();
+        out.width = static_cast<int>(width);
+        out.height = static_cast<int>(height);
+        out.nchannels = 4;
+        if (depth == 8)
+        {
+            out.format = TC_U8;
+            out.owned = std::make_shared<std::vector<unsigned char> >(count * 4);
+            unsigned char* o = out.owned->data();
+            for (size_t i = 0; i < count; ++i)
+            {
+                unsigned char r, g, b, a = 255;
+                if (colorType == 3)
+                {
+                    const unsigned idx = pix[i];
+                    if (idx * 3 + 2 >= palette.size()) return false;
+                    r = palette[idx * 3];
+                    g = palette[idx * 3 + 1];
+                    b = palette[idx * 3 + 2];
+                    if (idx < trns.size()) a = trns[idx];
+                }
+                else
+                {
+                    const unsigned char* p = &pix[i * channels];
+                    r = p[0];
+                    g = p[1];
+                    b = p[2];
+                    if (channels == 4) a = p[3];
+                }
+                if (a != 255)
+                {
+                    const float af = a * (1.0f / 255.0f);
+                    r = toUnsigned<unsigned char>(af * (r * (1.0f / 255.0f)), 255.f);
+                    g = toUnsigned<unsigned char>(af * (g * (1.0f / 255.0f)), 255.f);
+                    b = toUnsigned<unsigned char>(af * (b * (1.0f / 255.0f)), 255.f);
+                }
+                o[i * 4 + 0] = r;
+                o[i * 4 + 1] = g;
+                o[i * 4 + 2] = b;
+                o[i * 4 + 3] = a;
+            }
+        }
+        else
+        {
+            out.format = TC_U16;
+            out.owned = std::make_shared<std::vector<unsigned char> >(count * 8);
+            uint16_t* o = reinterpret_cast<uint16_t*>(out.owned->data());
+            for (size_t i = 0; i < count; ++i)
+            {
+                const unsigned char* p = &pix[i * channels * 2];
+                uint16_t v[4] = { 0, 0, 0, 65535 };
+                for (int c = 0; c < channels; ++c) v[c] = static_cast<uint16_t>((p[c * 2] << 8) | p[c * 2 + 1]);
+                if (v[3] != 65535)
+                {
+                    const float af = v[3] * (1.0f / 65535.0f);
+                    for (int c = 0; c < 3; ++c) v[c] = toUnsigned<uint16_t>(af * (v[c] * (1.0f / 65535.0f)), 65535.f);
+                }
+                memcpy(o + i * 4, v, 8);
+            }
+        }
+        out.host = out.owned->data();
+        return true;
+    }
+
+    bool writePng(const std::string& path, const unsigned char* rgba, int width, int height, bool rgb)
+    {
+        const int ch = rgb ? 3 : 4;
+        std::vector<unsigned char> raw((static_cast<size_t>(width) * ch + 1) * height);
+        for (int y = 0; y < height; ++y)
+        {
+            unsigned char* row = &raw[(static_cast<size_t>(width) * ch + 1) * y];
+            row[0] = 0;
+            for (int x = 0; x < width; ++x)
+                for (int c = 0; c < ch; ++c) row[1 + x * ch + c] = rgba[(static_cast<size_t>(y) * width + x) * 4 + c];
+        }
+        uLongf zlen = compressBound(static_cast<uLong>(raw.size()));
+        std::vector<unsigned char> z(zlen);
+        if (compress2(z.data(), &zlen, raw.data(), static_cast<uLong>(raw.size()), 3) != Z_OK) return false;
+        FILE* f = fopen(path.c_str(), "wb");
+        if (!f) return false;
+        auto chunk = [&](const char* type, const unsigned char* data, uint32_t len) {
+            unsigned char hdr[8] = { static_cast<unsigned char>(len >> 24), static_cast<unsigned char>(len >> 16),
+                                     static_cast<unsigned char>(len >> 8), static_cast<unsigned char>(len),
+                                     static_cast<unsigned char>(type[0]), static_cast<unsigned char>(type[1]),
+                                     static_cast<unsigned char>(type[2]), static_cast<unsigned char>(type[3]) };
+            fwrite(hdr, 1, 8, f);
+            if (len) fwrite(data, 1, len, f);
+            uLong crc = crc32(0L, hdr + 4, 4);
+            if (len) crc = crc32(crc, data, len);
+            const unsigned char c[4] = { static_cast<unsigned char>(crc >> 24), static_cast<unsigned char>(crc >> 16),
+                                         static_cast<unsigned char>(crc >> 8), static_cast<unsigned char>(crc) };
+            fwrite(c, 1, 4, f);
+        };
+        static const unsigned char sig[8] = { 0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a };
+        fwrite(sig, 1, 8, f);
+        unsigned char ihdr[13] = { static_cast<unsigned char>(width >> 24), static_cast<unsigned char>(width >> 16),
+                                   static_cast<unsigned char>(width >> 8), static_cast<unsigned char>(width),
+                                   static_cast<unsigned char>(height >> 24), static_cast<unsigned char>(height >> 16),
+                                   static_cast<unsigned char>(height >> 8), static_cast<unsigned char>(height),
+                                   8, static_cast<unsigned char>(rgb ? 2 : 6), 0, 0, 0 };
+        chunk("IHDR", ihdr, 13);
+        chunk("IDAT", z.data(), static_cast<uint32_t>(zlen));
+        chunk("IEND", nullptr, 0);
+        fclose(f);
+        return true;
+    }
+}

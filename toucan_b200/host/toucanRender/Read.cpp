@@ -1,0 +1,206 @@
+#include "Read.h"
+
+#include "PngRead.h"
+#include "Util.h"
+
+#include <sstream>
+
+namespace toucan
+{
+    void MediaStore::set(const std::string& path, const MediaFrame& frame)
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        _frames[path] = frame;
+    }
+
+    bool MediaStore::get(const std::string& path, MediaFrame& out)
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        const auto i = _frames.find(path);
+        if (i == _frames.end())
+        {
+            return false;
+        }
+        out = i->second;
+        return true;
+    }
+
+    void MediaStore::erase(const std::string& path)
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        _frames.erase(path);
+    }
+
+    void MediaStore::clear()
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        _frames.clear();
+    }
+
+    const std::shared_ptr<MediaStore>& MediaStore::global()
+    {
+        static const std::shared_ptr<MediaStore> store = std::make_shared<MediaStore>();
+        return store;
+    }
+
+    bool readMedia(const std::shared_ptr<MediaStore>& store, const std::string& path, MediaFrame& out)
+    {
+        if (store && store->get(path, out))
+        {
+            return true;
+        }
+        // Built-in reader: PNG only (zlib).  The decoded frame is parked in the store so a
+        // still is decoded once; it is still uploaded on every exec().
+        if (toLower(std::filesystem::path(path).extension().string()) == ".png" && readPng(path, out))
+        {
+            if (store) store->set(path, out);
+            return true;
+        }
+        return false;
+    }
+
+    IReadNode::IReadNode(const std::string& name) :
+        IImageNode(name)
+    {}
+
+    IReadNode::~IReadNode()
+    {}
+
+    const ImageSpec& IReadNode::getSpec() const { return _spec; }
+
+    const OTIO_NS::TimeRange& IReadNode::getTimeRange() const { return _timeRange; }
+
+    Image IReadNode::_toDevice(const MediaFrame& frame) const
+    {
+        if (frame.nchannels != 4)
+        {
+            // RGB sources are padded with A = 1 at decode time (Read.cpp:86-94)
+            throw std::runtime_error("read node: frames must be RGBA (pad RGB with A=1 at decode)");
+        }
+        const ImageSpec spec(frame.width, frame.height, 4, frame.format);
+        if (frame.device)
+        {
+            return Image::wrap(frame.device, spec);
+        }
+        return Image::upload(frame.host, spec);
+    }
+
+    ImageReadNode::ImageReadNode(
+        const std::filesystem::path& path,
+        const std::shared_ptr<MediaStore>& store) :
+        IReadNode("ImageRead"),
+        _path(path),
+        _store(store)
+    {
+        MediaFrame frame;
+        if (!readMedia(_store, _path.string(), frame))
+        {
+            std::stringstream ss;
+            ss << "Cannot open file: " << _path.string();
+            throw std::runtime_error(ss.str());
+        }
+        _spec = ImageSpec(frame.width, frame.height, frame.nchannels, frame.format);
+    }
+
+    ImageReadNode::~ImageReadNode()
+    {}
+
+    std::string ImageReadNode::getLabel() const
+    {
+        return "Read: " + _path.filename().string();
+    }
+
+    Image ImageReadNode::exec()
+    {
+        MediaFrame frame;
+        if (!readMedia(_store, _path.string(), frame))
+        {
+            return Image();
+        }
+        return _toDevice(frame);
+    }
+
+    std::vector<std::string> ImageReadNode::getExtensions()
+    {
+        return { ".exr", ".tif", ".tiff", ".jpg", ".jpeg", ".png" };
+    }
+
+    SequenceReadNode::SequenceReadNode(
+        const std::string& base,
+        const std::string& namePrefix,
+        const std::string& nameSuffix,
+        int startFrame,
+        int frameStep,
+        double rate,
+        int frameZeroPadding,
+        const std::shared_ptr<MediaStore>& store) :
+        IReadNode("SequenceRead"),
+        _base(base),
+        _namePrefix(namePrefix),
+        _nameSuffix(nameSuffix),
+        _startFrame(startFrame),
+        _frameStep(frameStep),
+        _rate(rate),
+        _frameZeroPadding(frameZeroPadding),
+        _store(store)
+    {
+        // Image information comes from the first frame; a missing first frame leaves an
+        // empty spec instead of throwing (Read.cpp:138-150).
+        MediaFrame frame;
+        if (readMedia(_store, getSequenceFrame(_base, _namePrefix, _startFrame, _frameZeroPadding, _nameSuffix), frame))
+        {
+            _spec = ImageSpec(frame.width, frame.height, frame.nchannels, frame.format);
+        }
+        _timeRange = OTIO_NS::TimeRange(
+            OTIO_NS::RationalTime(_startFrame, _rate),
+            OTIO_NS::RationalTime(1.0, _rate));
+    }
+
+    SequenceReadNode::~SequenceReadNode()
+    {}
+
+    std::string SequenceReadNode::getLabel() const
+    {
+        // the frame the node is currently set to (the reference prints the first frame)
+        return "Read: " + std::filesystem::path(
+            getSequenceFrame(_base, _namePrefix, _time.to_frames(), _frameZeroPadding, _nameSuffix)).filename().string();
+    }
+
+    Image SequenceReadNode::exec()
+    {
+        // The clip-local time IS the file number (Read.cpp:169-174).
+        const std::string url = getSequenceFrame(_base, _namePrefix, _time.to_frames(), _frameZeroPadding, _nameSuffix);
+        MediaFrame frame;
+        if (!readMedia(_store, url, frame))
+        {
+            return Image();
+        }
+        return _toDevice(frame);
+    }
+
+    std::vector<std::string> SequenceReadNode::getExtensions()
+    {
+        return { ".exr", ".tif", ".tiff", ".jpg", ".jpeg", ".png" };
+    }
+
+    std::shared_ptr<IReadNode> createReadNode(
+        const std::filesystem::path& path,
+        const std::shared_ptr<MediaStore>& store)
+    {
+        return std::make_shared<ImageReadNode>(path, store);
+    }
+
+    std::shared_ptr<IReadNode> createReadNode(
+        const std::string& base,
+        const std::string& namePrefix,
+        const std::string& nameSuffix,
+        int startFrame,
+        int frameStep,
+        double rate,
+        int frameZeroPadding,
+        const std::shared_ptr<MediaStore>& store)
+    {
+        return std::make_shared<SequenceReadNode>(
+            base, namePrefix, nameSuffix, startFrame, frameStep, rate, frameZeroPadding, store);
+    }
+}

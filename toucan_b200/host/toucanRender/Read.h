@@ -1,0 +1,139 @@
+// Read nodes: the leaves of the image graph.  In the reference these decode a file with
+// OpenImageIO / FFmpeg / lunasvg on EVERY exec() (lib/toucanRender/Read.cpp:64-101,164-216);
+// here a leaf is a decoded RGBA frame taken from a MediaStore -- host memory (uploaded on
+// every exec, mirroring the per-frame decode) or device memory kept resident -- so the hot
+// path starts at the decoded frame.  File decode itself is outside the
+// kernel scope; PNG files are decoded by a small built-in reader when no frame was
+// registered for the path.
+#pragma once
+
+#include <toucanRender/ImageNode.h>
+
+#include <filesystem>
+#include <map>
+#include <mutex>
+
+namespace toucan
+{
+    //! One decoded frame: tightly packed interleaved pixels on the host or the device.
+    struct MediaFrame
+    {
+        const void* host = nullptr;
+        void* device = nullptr;
+        int width = 0;
+        int height = 0;
+        int nchannels = 4;
+        int format = TC_U8;
+        std::shared_ptr<std::vector<unsigned char> > owned; // storage for frames decoded by the built-in reader
+    };
+
+    //! Registry path -> decoded frame, shared by all read nodes of a timeline.
+    class MediaStore
+    {
+    public:
+        void set(const std::string& path, const MediaFrame&);
+        bool get(const std::string& path, MediaFrame&);
+        void erase(const std::string& path);
+        void clear();
+
+        //! Process-wide default store.
+        static const std::shared_ptr<MediaStore>& global();
+
+    private:
+        std::mutex _mutex;
+        std::map<std::string, MediaFrame> _frames;
+    };
+
+    //! Base class for read nodes.
+    class IReadNode : public IImageNode
+    {
+    public:
+        IReadNode(const std::string& name);
+
+        virtual ~IReadNode() = 0;
+
+        const ImageSpec& getSpec() const;
+
+        const OTIO_NS::TimeRange& getTimeRange() const;
+
+    protected:
+        Image _toDevice(const MediaFrame&) const;
+
+        ImageSpec _spec;
+        OTIO_NS::TimeRange _timeRange;
+    };
+
+    //! Image read node.
+    class ImageReadNode : public IReadNode
+    {
+    public:
+        ImageReadNode(
+            const std::filesystem::path&,
+            const std::shared_ptr<MediaStore>& = MediaStore::global());
+
+        virtual ~ImageReadNode();
+
+        std::string getLabel() const override;
+
+        Image exec() override;
+
+        static std::vector<std::string> getExtensions();
+
+    private:
+        std::filesystem::path _path;
+        std::shared_ptr<MediaStore> _store;
+    };
+
+    //! Image sequence read node.
+    class SequenceReadNode : public IReadNode
+    {
+    public:
+        SequenceReadNode(
+            const std::string& base,
+            const std::string& namePrefix,
+            const std::string& nameSuffix,
+            int startFrame,
+            int frameStep,
+            double rate,
+            int frameZeroPadding,
+            const std::shared_ptr<MediaStore>& = MediaStore::global());
+
+        virtual ~SequenceReadNode();
+
+        std::string getLabel() const override;
+
+        Image exec() override;
+
+        static std::vector<std::string> getExtensions();
+
+    private:
+        std::string _base;
+        std::string _namePrefix;
+        std::string _nameSuffix;
+        int _startFrame = 1;
+        int _frameStep = 1;
+        double _rate = 1.0;
+        int _frameZeroPadding = 0;
+        std::shared_ptr<MediaStore> _store;
+    };
+
+    //! Look a frame up in the store, falling back to the built-in file readers.
+    bool readMedia(const std::shared_ptr<MediaStore>&, const std::string& path, MediaFrame&);
+
+    //! Create a read node for a single image.  Throws std::runtime_error if the media cannot
+    //! be opened (the caller logs it and the clip yields no node, ImageGraph.cpp:355-367).
+    std::shared_ptr<IReadNode> createReadNode(
+        const std::filesystem::path&,
+        const std::shared_ptr<MediaStore>& = MediaStore::global());
+
+    //! Create a read node for an image sequence.
+    std::shared_ptr<IReadNode> createReadNode(
+        const std::string& base,
+        const std::string& namePrefix,
+        const std::string& nameSuffix,
+        int startFrame,
+        int frameStep,
+        double rate,
+        int frameZeroPadding,
+        const std::shared_ptr<MediaStore>& = MediaStore::global());
+}
