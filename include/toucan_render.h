@@ -1,0 +1,77 @@
+/*
+ * toucan_render.h -- C ABI of libtoucan_render.so: the C++ host of the render path
+ * (toucan::ImageEffectHost + toucan::TimelineWrapper + toucan::ImageGraph, the same classes
+ * as the reference's lib/toucanRender) for callers that are not C++ -- the Python test and
+ * bench harness here, a cgo/JNI/ctypes binding elsewhere.
+ *
+ * One call = one step of bin/toucan-render/App.cpp:152-265:
+ *   tr_host_create        ImageEffectHost(context, searchPath)               App.cpp:199
+ *   tr_timeline_open*     TimelineWrapper(path) + ImageGraph(context, ...)    App.cpp:162-170
+ *   tr_timeline_render    graph->exec(host, time) ; node->exec() ; download   App.cpp:232-262
+ * Every function returns 0 on success or a negative value; tr_last_error() holds the
+ * message for the calling thread.  Rendering needs a CUDA device; there is no CPU path.
+ */
+#ifndef TOUCAN_RENDER_H
+#define TOUCAN_RENDER_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tr_host tr_host;
+typedef struct tr_timeline tr_timeline;
+
+const char* tr_last_error(void);
+
+/* Bind the calling thread to a CUDA device (one render thread per GPU). */
+int tr_bind_device(int device);
+/* Wait for everything the calling thread enqueued. */
+int tr_sync(void);
+
+/* OpenFX host: loads every *.ofx module under plugin_dir (NULL: the directory next to this
+   library, then $OFX_PLUGIN_PATH).  Works without a GPU (describe only). */
+int tr_host_create(const char* plugin_dir, tr_host** out);
+void tr_host_destroy(tr_host* host);
+int tr_host_plugin_count(const tr_host* host);
+const char* tr_host_plugin_identifier(const tr_host* host, int index);
+
+/* Timelines.  Each timeline owns a media store: decoded frames registered by resolved path. */
+int tr_timeline_open(const char* otio_path, tr_timeline** out);
+int tr_timeline_open_json(const char* json, const char* directory, tr_timeline** out);
+void tr_timeline_close(tr_timeline* timeline);
+/* Resolve a media URL the way TimelineWrapper::getMediaPath does. */
+int tr_timeline_media_path(const tr_timeline* timeline, const char* url, char* out, size_t capacity);
+/* Register a decoded RGBA frame (tightly packed, `type` = tc_type) under a resolved path.
+   The pixels are BORROWED: host memory is uploaded on every render that reads it, device
+   memory (device != 0) is used in place.  Must be called before tr_timeline_prepare. */
+int tr_timeline_set_media(tr_timeline* timeline, const char* path, const void* pixels, int device, int width, int height, int type);
+/* Build the ImageGraph (reads the first clip's media information). */
+int tr_timeline_prepare(tr_timeline* timeline);
+/* start/rate of the first frame, number of frames (App.cpp:222-224), image size and tc_type. */
+int tr_timeline_info(const tr_timeline* timeline, double* start_value, double* rate, int* frames, int* width, int* height, int* type);
+
+/* The node tree ImageGraph::exec builds for a time, one node per line, inputs indented. */
+int tr_timeline_describe(tr_timeline* timeline, tr_host* host, double time_value, char* out, size_t capacity);
+/* Render a frame into host memory (blocks until the frame is complete).  width/height/type
+   return the frame's format; capacity must hold it. */
+int tr_timeline_render(tr_timeline* timeline, tr_host* host, double time_value, void* out, size_t capacity, int* width, int* height,
+                       int* type);
+/* Render a frame and leave it in device memory: *out is the device pointer of the finished
+   frame, enqueued on the thread's stream (tr_sync before reading from another stream or
+   the host).  The frame stays valid until the next render_resident call on this timeline. */
+int tr_timeline_render_resident(tr_timeline* timeline, tr_host* host, double time_value, void** out, int* width, int* height, int* type);
+
+/* The built-in PNG reader used when no decoded frame was registered for a path (RGBA out,
+   A = 1 appended to RGB, alpha associated on read like OIIO's reader).  out may be NULL to
+   query the size. */
+int tr_decode_png(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
+
+/* Cross-node fusion of the track stack (default on). */
+void tr_set_fusion(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOUCAN_RENDER_H */

@@ -560,3 +560,47 @@ def _blur_sized(src, ow, oh, radius):
     out = O.new(ow, oh, src.dtype)
     O.lib().o_blur(O.ctypes.byref(O._img(out)), O.ctypes.byref(O._img(src)), O.ctypes.c_float(radius))
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# Text form of a node tree, identical to toucan::IImageNode::describeTree of the C++ host
+# (one node per line, inputs indented by two spaces) -- lets the graph builders be compared
+# without a GPU.
+def _fmt_any(v):
+    if v is None:
+        return "null"
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, int):
+        return str(v)
+    if isinstance(v, float):
+        s = "%.17g" % v
+        if math.isfinite(v) and abs(v) < 9.2e18 and v == int(v):
+            s += ".0"
+        return s
+    if isinstance(v, str):
+        return '"' + v + '"'
+    if isinstance(v, list):
+        return "[" + ",".join(_fmt_any(x) for x in v) + "]"
+    return "?"
+
+
+def describe_tree(node, depth=0, out=None):
+    out = [] if out is None else out
+    pad = "  " * depth
+    if node is None:
+        out.append(pad + "(null)")
+        return out
+    if node[0] == "read":
+        out.append(pad + "Read: " + os.path.basename(node[1]))
+        return out
+    if node[0] == "comp":
+        out.append(pad + "Comp")
+        for i in node[1]:
+            describe_tree(i, depth + 1, out)
+        return out
+    _, name, meta, inputs = node
+    out.append(pad + name + " {" + ", ".join(k + "=" + _fmt_any(meta[k]) for k in sorted(meta)) + "}")
+    for i in inputs:
+        describe_tree(i, depth + 1, out)
+    return out

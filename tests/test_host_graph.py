@@ -1,0 +1,96 @@
+"""CPU: the C++ host (ImageEffectHost + OpenFX modules + TimelineWrapper + ImageGraph) builds,
+for every frame of every fixture timeline, the same node tree as the oracle's restatement of
+lib/toucanRender/ImageGraph.cpp:144-466 (golden trees in tests/golden/frames.json).  No GPU:
+only graph construction and the OpenFX describe actions run."""
+import os
+
+import pytest
+
+from tests import timelines as TL
+
+GOLD = TL.golden()
+
+IDENTIFIERS = {
+    "toucan:Checkers", "toucan:Fill", "toucan:Gradient", "toucan:Noise",
+    "toucan:Blur", "toucan:ColorMap", "toucan:Invert", "toucan:Pow", "toucan:Saturate", "toucan:UnsharpMask",
+    "toucan:Crop", "toucan:Flip", "toucan:Flop", "toucan:Resize", "toucan:Rotate",
+    "toucan:Dissolve", "toucan:HorizontalWipe", "toucan:VerticalWipe",
+    "toucan:ColorConvert", "toucan:Premult", "toucan:Unpremult",
+}
+
+
+@pytest.fixture(scope="module")
+def host(built):
+    from toucan_b200 import render
+
+    return render.Host()
+
+
+def test_render_abi_exports(built):
+    import re
+
+    from toucan_b200 import render
+
+    lib = render.lib()
+    txt = open(os.path.join(os.path.dirname(TL.GOLDEN), "..", "include", "toucan_render.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(tr_[a-z0-9_]+)\s*\(", txt)))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in toucan_render.h but not exported"
+    assert set(render.EXPORTS) == set(names)
+
+
+def test_host_loads_all_effects(host):
+    # the 21 in-scope plug-in identifiers of SURVEY 8b, served by 5 *.ofx modules
+    assert set(host.identifiers()) == IDENTIFIERS
+
+
+def test_ofx_modules_export_entry_points(built):
+    import ctypes
+
+    from toucan_b200 import capi, render
+
+    capi.lib()
+    mods = sorted(f for f in os.listdir(render.PLUGIN_DIR) if f.endswith(".ofx"))
+    assert len(mods) == 5
+    total = 0
+    for m in mods:
+        so = ctypes.CDLL(os.path.join(render.PLUGIN_DIR, m))
+        so.OfxGetNumberOfPlugins.restype = ctypes.c_int
+        n = so.OfxGetNumberOfPlugins()
+        assert n >= 3 and hasattr(so, "OfxGetPlugin")
+        total += n
+    assert total == 21
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_graph_matches_golden_tree(host, name):
+    g = GOLD[name]
+    tl = TL.open_timeline(name)
+    info = tl.info()
+    assert info["frames"] == len(g["frames"])
+    assert info["rate"] == g["rate"] and info["start"] == g["start"]
+    assert [info["width"], info["height"]] == g["size"]
+    for rec in g["frames"]:
+        got = tl.describe(host, rec["time"]).rstrip("\n").split("\n")
+        assert got == rec["tree"], f"{name} @ {rec['time']}"
+    tl.close()
+
+
+def test_unknown_effect_is_skipped_and_unknown_transition_dissolves(host):
+    from toucan_b200 import render, workloads
+
+    doc = workloads.stack_timeline(tracks=1, frames=96)
+    track = doc["tracks"]["children"][0]
+    track["children"][1]["transition_type"] = "SMPTE_Dissolve"
+    track["children"][0]["effects"].insert(0, {"OTIO_SCHEMA": "Effect.1", "effect_name": "nonesuch:Effect", "metadata": {}})
+    tl = render.Timeline(json_doc=doc, directory="/nonexistent")
+    import numpy as np
+
+    for k in range(2):
+        tl.set_media(tl.media_path(workloads.still_url(0, k)), np.zeros((8, 8, 4), np.float32))
+    tl.prepare()
+    tree = tl.describe(host, 40.0)
+    assert "toucan:Dissolve {value=0.16666666666666666}" in tree
+    assert "nonesuch" not in tree and tree.count("toucan:Blur") == 2

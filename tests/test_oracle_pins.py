@@ -1,0 +1,144 @@
+"""CPU: what pins the oracle.
+
+The reference's own tests hold no golden pixels and OpenImageIO is not available, so parity is
+UNPINNED against a real toucan-render.  What can be pinned here:
+  * regression: the oracle renders every frame of every fixture timeline to the committed
+    sha256 (tests/golden/frames.json, made by tests/golden/make_golden.py);
+  * closed-form known answers of SURVEY 8c (identities, constant images, wipe/dissolve endpoints);
+  * the derived integer facts of SURVEY 9.1;
+  * constants that can be cross-checked without OIIO (fast_sinpi error bound, colour-map knots
+    against OpenCV's copies of the matplotlib tables);
+  * the time-math worked examples of SURVEY 9.8.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import graph as G
+from oracle import oracle as O
+from tests import media
+from tests import timelines as TL
+
+GOLD = TL.golden()
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_oracle_renders_golden_frames(name):
+    tl = G.Timeline(os.path.join(TL.DATA, name))
+    g = G.ImageGraph(tl, media.decode)
+    frames = tl.frames()
+    assert len(frames) == len(GOLD[name]["frames"])
+    for t, rec in zip(frames, GOLD[name]["frames"]):
+        assert t.value == rec["time"]
+        node = g.exec(t)
+        assert G.describe_tree(node) == rec["tree"]
+        img = g.eval(node)
+        if rec["sha256"]:
+            assert list(img.shape) == rec["shape"] and str(img.dtype) == rec["dtype"]
+            assert hashlib.sha256(img.tobytes()).hexdigest() == rec["sha256"], f"{name} @ {rec['time']}"
+        else:
+            assert img is None or img.size == 0
+
+
+def test_time_math_worked_examples():
+    # Transition.otio -- frames 0-1 plain, 2-7 inside the dissolve with value (f-2)/6, 8-9 the Fill
+    trees = [r["tree"] for r in GOLD["Transition.otio"]["frames"]]
+    assert all("toucan:Dissolve" not in "".join(t) for t in trees[:2] + trees[8:])
+    for f in range(2, 8):
+        line = [ln for ln in trees[f] if "toucan:Dissolve" in ln][0]
+        assert "value=" + G._fmt_any((f - 2) / 6.0) in line
+        assert any(f"Read: Counter.{f}.png" in ln for ln in trees[f])
+    # LinearTimeWarp.otio: clip 1 (x2.0) reads Counter.0,2,4; clip 2 (x0.5) reads 0,1,1,2,2,3,3,4
+    reads = ["".join(r["tree"]).split("Read: Counter.")[1].split(".png")[0] for r in GOLD["LinearTimeWarp.otio"]["frames"]]
+    assert reads == ["0", "2", "4", "0", "1", "1", "2", "2", "3", "3", "4"]
+    # Markers.otio starts at global_start_time 100
+    assert GOLD["Markers.otio"]["start"] == 100.0
+
+
+def test_u8_derived_facts():
+    # u8 load -> store is the identity; invert == 255 - v; the u8 x u8 product through the
+    # float path equals integer round-half-up
+    v = np.arange(256, dtype=np.uint8).reshape(1, 64, 4)
+    assert np.array_equal(O.convert(v, O.U8), v)
+    inv = O.invert(v)
+    assert np.array_equal(inv[..., :3], 255 - v[..., :3]) and np.array_equal(inv[..., 3], v[..., 3])
+    a = np.zeros((256, 256, 4), np.uint8)
+    a[..., 0] = np.arange(256)[:, None]
+    a[..., 3] = np.arange(256)[None, :]
+    pm = O.premult(a)
+    aa, cc = a[..., 0].astype(np.int64), a[..., 3].astype(np.int64)
+    want = np.where(cc == 255, aa, (2 * aa * cc + 255) // 510)
+    assert np.array_equal(pm[..., 0], want)
+    v16 = np.arange(65536, dtype=np.uint16).reshape(64, 256, 4)
+    assert np.array_equal(O.convert(v16, O.U16), v16)
+
+
+def test_known_answers():
+    rng = np.random.default_rng(5)
+    f = rng.random((37, 53, 4), dtype=np.float32)
+    u = (f * 255).astype(np.uint8)
+    assert np.array_equal(O.flip(O.flip(u)), u) and np.array_equal(O.flop(O.flop(f)), f)
+    assert np.array_equal(O.invert(O.invert(u)), u)
+    assert np.array_equal(O.dissolve(f, f[::-1].copy(), 0.0), f)
+    assert np.array_equal(O.dissolve(f, f[::-1].copy(), 1.0), f[::-1])
+    const = np.full((40, 60, 4), 0.375, np.float32)
+    assert np.abs(O.blur(const, 10.0) - 0.375).max() < 1e-6
+    assert np.abs(O.resize(f, (53, 37)) - f).max() < 1e-5       # same size: identity (fast_sinpi ripple)
+    assert np.abs(O.rotate(f, 0.0) - f).max() < 1e-5            # no rotation: identity
+    opaque = f.copy()
+    opaque[..., 3] = 1.0
+    assert np.array_equal(O.over(opaque, f[::-1].copy()), opaque)  # alpha = 1 fg covers
+    clear = np.zeros_like(f)
+    assert np.array_equal(O.over(clear, f), f)                    # alpha = 0 fg shows bg
+    black = np.zeros((4, 4, 4), np.float32)
+    white = np.ones((4, 4, 4), np.float32)
+    assert np.allclose(O.color_map(black, "plasma")[0, 0, :3], [0.050383, 0.029803, 0.527975])
+    assert np.allclose(O.color_map(white, "plasma")[0, 0, :3], [0.940015, 0.975158, 0.131326])
+    assert O.fit((1280, 720), (640, 360)) == (0, 0, 1280, 720)
+    assert O.fit((1280, 720), (100, 100)) == (280, 0, 720, 720)
+    # wipes at the ends: value 0 -> the 200 px ramp starts at 0; far right is all `from`
+    a = rng.random((8, 1280, 4), dtype=np.float32)
+    b = rng.random((8, 1280, 4), dtype=np.float32)
+    w0 = O.wipe(a, b, 0.0, False)
+    assert np.array_equal(w0[:, 200:], a[:, 200:]) and np.array_equal(w0[:, 0], b[:, 0])
+
+
+def test_fast_sinpi_error_bound():
+    # OIIO documents max abs error 0.000918954611 for fast_sinpi on [-1, 1]
+    x = np.linspace(-1, 1, 20001, dtype=np.float32)
+    got = np.array([O.lib().o_fast_sinpi(float(v)) for v in x[::10]])
+    err = np.abs(got - np.sin(np.pi * x[::10].astype(np.float64))).max()
+    assert 0.0008 < err < 0.00093, err
+
+
+def test_colour_map_knots_against_opencv():
+    # The knot tables are restated from OIIO's published color_map tables [V].  What can be checked
+    # without OIIO: every knot is a genuine sample of the matplotlib map (OpenCV ships the same
+    # 256-entry tables at 8-bit precision), the samples run in increasing order, and the first and
+    # last knots are the ends of the map.
+    cv2 = pytest.importorskip("cv2")
+    import ctypes
+
+    for name, code in [("plasma", cv2.COLORMAP_PLASMA), ("inferno", cv2.COLORMAP_INFERNO), ("magma", cv2.COLORMAP_MAGMA),
+                       ("viridis", cv2.COLORMAP_VIRIDIS), ("turbo", cv2.COLORMAP_TURBO)]:
+        lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), code)[0, :, ::-1].astype(np.float64) / 255.0
+        p = ctypes.POINTER(ctypes.c_float)()
+        n = O.lib().o_color_map_knots(name.encode(), ctypes.byref(p))
+        assert 15 <= n <= 17
+        knots = np.array([p[i] for i in range(3 * n)]).reshape(n, 3)
+        best = [int(np.argmin(np.abs(lut - k).sum(1))) for k in knots]
+        assert best[0] == 0 and best[-1] == 255, (name, best)
+        assert all(b > a for a, b in zip(best, best[1:])), (name, best)
+        assert max(float(np.abs(lut[b] - k).max()) for b, k in zip(best, knots)) < 1.0 / 255 + 1e-3, name
+
+
+def test_builtin_png_reader_matches_harness_decode(built):
+    # the C++ host's built-in reader and the test harness' Pillow decode apply the same two
+    # read-side conventions (A = 1 for RGB, alpha association with OIIO's u8 rounding)
+    from toucan_b200 import render
+
+    for f in ["Counter.3.png", "Letter_A.png", "Gradient.png"]:
+        p = os.path.join(TL.DATA, f)
+        assert np.array_equal(render.decode_png(p), media.decode(p)), f

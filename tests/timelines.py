@@ -1,0 +1,31 @@
+"""Shared helpers for the timeline-level tests: the golden fixtures and the C++ host set-up."""
+from __future__ import annotations
+
+import json
+import os
+
+from tests import media
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DATA = os.path.join(GOLDEN, "data")
+
+
+def golden():
+    with open(os.path.join(GOLDEN, "frames.json")) as f:
+        return json.load(f)
+
+
+def open_timeline(name):
+    """toucan::TimelineWrapper on a fixture with every raster medium of the data directory
+    registered as a decoded frame (decode stays outside the hot path and identical for the
+    oracle and the CUDA path)."""
+    from toucan_b200 import render
+
+    tl = render.Timeline(os.path.join(DATA, name))
+    for f in sorted(os.listdir(DATA)):
+        if f.lower().endswith((".png", ".jpg")):
+            frame = media.decode(os.path.join(DATA, f))
+            if frame is not None:
+                tl.set_media(os.path.join(DATA, f), frame)
+    tl.prepare()
+    return tl

@@ -95,7 +95,7 @@ def build_cuda(verbose=False, force=False):
 
 
 HOST_LIB_SOURCES = ["otio.cpp", "PropertySet.cpp", "Plugin.cpp", "Util.cpp", "Image.cpp", "ImageNode.cpp", "ImageEffect.cpp",
-                    "ImageEffectHost.cpp", "Comp.cpp", "Read.cpp", "TimelineWrapper.cpp", "ImageGraph.cpp", "render_capi.cpp"]
+                    "ImageEffectHost.cpp", "Comp.cpp", "StackFusion.cpp", "Read.cpp", "PngRead.cpp", "TimelineWrapper.cpp", "ImageGraph.cpp", "render_capi.cpp"]
 PLUGIN_MODULES = {
     "toucanGeneratorPlugin.ofx": ["GeneratorPlugin.cpp"],
     "toucanFilterPlugin.ofx": ["FilterPlugin.cpp"],
@@ -138,7 +138,7 @@ def build_host(verbose=False, force=False):
     rpath = ["-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/.."]
     out = os.path.join(LIB, "libtoucan_render.so")
     if objs and (force or jobs or _newer(out, objs)):
-        _run([CXX, "-shared", "-o", out] + objs + ["-L", LIB, "-ltoucan_cuda", "-ldl", "-lpthread"] + rpath, verbose)
+        _run([CXX, "-shared", "-o", out] + objs + ["-L", LIB, "-ltoucan_cuda", "-lz", "-ldl", "-lpthread"] + rpath, verbose)
     for mod, files in PLUGIN_MODULES.items():
         mobjs = [plug_objs[f] for f in files + ["Plugin.cpp", "Util.cpp"] if f in plug_objs]
         if len(mobjs) < 3:
@@ -150,7 +150,7 @@ def build_host(verbose=False, force=False):
     if os.path.exists(main_src):
         exe = os.path.join(LIB, "toucan-render")
         if force or jobs or _newer(exe, [main_src, out] + hdrs):
-            _run([CXX] + CXX_FLAGS + [main_src, "-o", exe, "-L", LIB, "-ltoucan_render", "-ltoucan_cuda", "-ldl", "-lpthread"] + rpath, verbose)
+            _run([CXX] + CXX_FLAGS + [main_src, "-o", exe, "-L", LIB, "-ltoucan_render", "-ltoucan_cuda", "-lz", "-ldl", "-lpthread"] + rpath, verbose)
     return out
 
 

@@ -1,0 +1,45 @@
+// toucanColorPlugin.ofx: toucan:ColorConvert, :Premult, :Unpremult.
+// Parameter sets and local initialisers: plugins/ColorPlugin.cpp:157-179,207-218.
+#include "Plugin.h"
+
+namespace toucan_ofx
+{
+    namespace
+    {
+        int colorConvert(const RenderArgs& a, const Params& p)
+        {
+            const std::string fromSpace = p.getString("fromspace", "");
+            const std::string toSpace = p.getString("tospace", "");
+            // `int premult = 0` receives the described default `true` as a plain int, which
+            // the host never delivers: the effective flag is what the metadata says, else 0.
+            const int premult = p.getBoolAsInt("premult", 0);
+            const std::string contextKey = p.getString("context_key", "");
+            const std::string contextValue = p.getString("context_value", "");
+            const std::string colorConfig = p.getString("color_config", "");
+            if (!colorConfig.empty() || !contextKey.empty() || premult)
+            {
+                // Only OCIO's built-in config, baked per (from, to) pair, is in scope.
+                return TC_ERR_UNSUPPORTED;
+            }
+            return tc_color_convert(&a.output, &a.source[0], fromSpace.c_str(), toSpace.c_str(), a.stream);
+        }
+
+        int premult(const RenderArgs& a, const Params&) { return tc_premult(&a.output, &a.source[0], a.stream); }
+
+        int unpremult(const RenderArgs& a, const Params&) { return tc_unpremult(&a.output, &a.source[0], a.stream); }
+    }
+
+    const std::vector<EffectDef>& effects()
+    {
+        static const std::vector<EffectDef> table = {
+            { "toucan:ColorConvert", "ColorConvert", Context::Filter,
+              { paramString("fromspace", "From Space", ""), paramString("tospace", "To Space", ""), paramBool("premult", "Premultiplied", 1),
+                paramString("context_key", "Context Key", ""), paramString("context_value", "Context Value", ""),
+                paramString("color_config", "ColorConfig", "") },
+              &colorConvert },
+            { "toucan:Premult", "Premult", Context::Filter, {}, &premult },
+            { "toucan:Unpremult", "Unpremult", Context::Filter, {}, &unpremult },
+        };
+        return table;
+    }
+}

@@ -1,0 +1,67 @@
+// toucanFilterPlugin.ofx: toucan:Blur, :ColorMap, :Invert, :Pow, :Saturate, :UnsharpMask.
+// Parameter sets and local initialisers: plugins/FilterPlugin.cpp:160-162,185-186,243-245,
+// 269-270,402-404,427-428,479-481,504-505,557-571,597-604.
+#include "Plugin.h"
+
+namespace toucan_ofx
+{
+    namespace
+    {
+        int blur(const RenderArgs& a, const Params& p)
+        {
+            const double radius = p.getDouble("radius", 0.0);
+            return tc_blur(&a.output, &a.source[0], static_cast<float>(radius), a.stream);
+        }
+
+        int colorMap(const RenderArgs& a, const Params& p)
+        {
+            // color_map on RGB + copy of the alpha channel: one pass
+            const std::string mapName = p.getString("map_name", "plasma");
+            return tc_color_map(&a.output, &a.source[0], mapName.c_str(), a.stream);
+        }
+
+        int invert(const RenderArgs& a, const Params&)
+        {
+            // invert on channels [0,3) + copy of the alpha channel: one pass
+            return tc_invert(&a.output, &a.source[0], a.stream);
+        }
+
+        int pow(const RenderArgs& a, const Params& p)
+        {
+            const double value = p.getDouble("value", 1.0);
+            return tc_pow(&a.output, &a.source[0], static_cast<float>(value), a.stream);
+        }
+
+        int saturate(const RenderArgs& a, const Params& p)
+        {
+            const double value = p.getDouble("value", 1.0);
+            return tc_saturate(&a.output, &a.source[0], static_cast<float>(value), a.stream);
+        }
+
+        int unsharpMask(const RenderArgs& a, const Params& p)
+        {
+            const std::string kernel = p.getString("kernel", "gaussian");
+            const double width = p.getDouble("width", 3.0);
+            const double contrast = p.getDouble("contrast", 1.0);
+            const double threshold = p.getDouble("threshold", 0.0);
+            return tc_unsharp_mask(&a.output, &a.source[0], kernel.c_str(), static_cast<float>(width), static_cast<float>(contrast),
+                                   static_cast<float>(threshold), a.stream);
+        }
+    }
+
+    const std::vector<EffectDef>& effects()
+    {
+        static const std::vector<EffectDef> table = {
+            { "toucan:Blur", "Blur", Context::Filter, { paramDouble("radius", "Radius", 10.0) }, &blur },
+            { "toucan:ColorMap", "ColorMap", Context::Filter, { paramString("map_name", "Map Name", "plasma") }, &colorMap },
+            { "toucan:Invert", "Invert", Context::Filter, {}, &invert },
+            { "toucan:Pow", "Pow", Context::Filter, { paramDouble("value", "Value", 1.0) }, &pow },
+            { "toucan:Saturate", "Saturate", Context::Filter, { paramDouble("value", "Value", 1.0) }, &saturate },
+            { "toucan:UnsharpMask", "UnsharpMask", Context::Filter,
+              { paramString("kernel", "Kernel", "gaussian"), paramDouble("width", "Width", 1.0), paramDouble("contrast", "Contrast", 1.0),
+                paramDouble("threshold", "Threshold", 1.0) },
+              &unsharpMask },
+        };
+        return table;
+    }
+}

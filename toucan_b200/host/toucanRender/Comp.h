@@ -16,6 +16,7 @@ namespace toucan
 
         //! Set whether images are pre-multiplied before compositing.
         void setPremult(bool);
+        bool getPremult() const { return _premult; }
 
         //! Set whether images are resized before compositing (stored, never consulted:
         //! same as the reference, Comp.cpp:24-27 vs :29-84).

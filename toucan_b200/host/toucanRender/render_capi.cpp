@@ -1,0 +1,297 @@
+// C ABI over the C++ host (include/toucan_render.h).
+#include <toucan_render.h>
+
+#include "ImageEffectHost.h"
+#include "ImageGraph.h"
+#include "PngRead.h"
+#include "StackFusion.h"
+#include "TimelineWrapper.h"
+#include "Util.h"
+
+#include <dlfcn.h>
+
+#include <cstring>
+#include <sstream>
+
+using namespace toucan;
+
+struct tr_host
+{
+    std::shared_ptr<ftk::Context> context;
+    std::shared_ptr<ImageEffectHost> host;
+    std::vector<std::string> identifiers;
+};
+
+struct tr_timeline
+{
+    std::shared_ptr<ftk::Context> context;
+    std::shared_ptr<MediaStore> store;
+    std::shared_ptr<TimelineWrapper> wrapper;
+    std::shared_ptr<ImageGraph> graph;
+    Image resident; // the frame handed out by tr_timeline_render_resident
+};
+
+namespace
+{
+    thread_local std::string lastError;
+
+    int fail(const std::string& what)
+    {
+        lastError = what;
+        return -1;
+    }
+
+    template <class F>
+    int guarded(F&& f)
+    {
+        try
+        {
+            return f();
+        }
+        catch (const std::exception& e)
+        {
+            return fail(e.what());
+        }
+    }
+
+    std::filesystem::path libraryDirectory()
+    {
+        Dl_info info;
+        if (dladdr(reinterpret_cast<const void*>(&tr_last_error), &info) && info.dli_fname)
+        {
+            return std::filesystem::path(info.dli_fname).parent_path();
+        }
+        return std::filesystem::current_path();
+    }
+
+    int copyOut(const std::string& s, char* out, size_t capacity)
+    {
+        if (!out || capacity < s.size() + 1)
+        {
+            return fail("output buffer too small");
+        }
+        memcpy(out, s.c_str(), s.size() + 1);
+        return 0;
+    }
+
+    int ensureGraph(tr_timeline* t)
+    {
+        if (!t->graph)
+        {
+            t->graph = std::make_shared<ImageGraph>(t->context, t->wrapper->getPath().parent_path(), t->wrapper);
+        }
+        return 0;
+    }
+
+    OTIO_NS::RationalTime timeOf(const tr_timeline* t, double value)
+    {
+        return OTIO_NS::RationalTime(value, t->wrapper->getTimeRange().duration().rate());
+    }
+
+    Image renderImage(tr_timeline* t, tr_host* h, double value)
+    {
+        ensureGraph(t);
+        auto node = t->graph->exec(h->host, timeOf(t, value));
+        return node ? node->exec() : Image();
+    }
+}
+
+extern "C"
+{
+    const char* tr_last_error(void) { return lastError.c_str(); }
+
+    int tr_bind_device(int device)
+    {
+        return guarded([&] { DeviceContext::bind(device); return 0; });
+    }
+
+    int tr_sync(void)
+    {
+        return guarded([&] { DeviceContext::synchronize(); return 0; });
+    }
+
+    int tr_host_create(const char* plugin_dir, tr_host** out)
+    {
+        if (!out) return fail("tr_host_create: null");
+        *out = nullptr;
+        return guarded([&] {
+            auto h = std::make_unique<tr_host>();
+            h->context = ftk::Context::create();
+            std::vector<std::filesystem::path> searchPath;
+            if (plugin_dir && *plugin_dir)
+            {
+                searchPath.push_back(plugin_dir);
+            }
+            else
+            {
+                searchPath = getOpenFXPluginPaths(libraryDirectory() / "toucan-render");
+            }
+            h->host = std::make_shared<ImageEffectHost>(h->context, searchPath);
+            h->identifiers = h->host->getPluginIdentifiers();
+            *out = h.release();
+            return 0;
+        });
+    }
+
+    void tr_host_destroy(tr_host* host) { delete host; }
+
+    int tr_host_plugin_count(const tr_host* host) { return host ? static_cast<int>(host->identifiers.size()) : 0; }
+
+    const char* tr_host_plugin_identifier(const tr_host* host, int index)
+    {
+        if (!host || index < 0 || index >= static_cast<int>(host->identifiers.size())) return "";
+        return host->identifiers[static_cast<size_t>(index)].c_str();
+    }
+
+    int tr_timeline_open(const char* otio_path, tr_timeline** out)
+    {
+        if (!out || !otio_path) return fail("tr_timeline_open: null");
+        *out = nullptr;
+        return guarded([&] {
+            auto t = std::make_unique<tr_timeline>();
+            t->context = ftk::Context::create();
+            t->store = std::make_shared<MediaStore>();
+            t->wrapper = std::make_shared<TimelineWrapper>(std::filesystem::path(otio_path));
+            t->wrapper->setMediaStore(t->store);
+            *out = t.release();
+            return 0;
+        });
+    }
+
+    int tr_timeline_open_json(const char* json, const char* directory, tr_timeline** out)
+    {
+        if (!out || !json) return fail("tr_timeline_open_json: null");
+        *out = nullptr;
+        return guarded([&] {
+            auto t = std::make_unique<tr_timeline>();
+            t->context = ftk::Context::create();
+            t->store = std::make_shared<MediaStore>();
+            t->wrapper = std::make_shared<TimelineWrapper>(std::string(json), std::filesystem::path(directory ? directory : ""));
+            t->wrapper->setMediaStore(t->store);
+            *out = t.release();
+            return 0;
+        });
+    }
+
+    void tr_timeline_close(tr_timeline* timeline) { delete timeline; }
+
+    int tr_timeline_media_path(const tr_timeline* timeline, const char* url, char* out, size_t capacity)
+    {
+        if (!timeline || !url) return fail("tr_timeline_media_path: null");
+        return guarded([&] { return copyOut(timeline->wrapper->getMediaPath(url), out, capacity); });
+    }
+
+    int tr_timeline_set_media(tr_timeline* timeline, const char* path, const void* pixels, int device, int width, int height, int type)
+    {
+        if (!timeline || !path || !pixels) return fail("tr_timeline_set_media: null");
+        if (width <= 0 || height <= 0 || type < TC_U8 || type > TC_F32) return fail("tr_timeline_set_media: bad frame description");
+        MediaFrame frame;
+        if (device) frame.device = const_cast<void*>(pixels);
+        else frame.host = pixels;
+        frame.width = width;
+        frame.height = height;
+        frame.nchannels = 4;
+        frame.format = type;
+        timeline->store->set(path, frame);
+        return 0;
+    }
+
+    int tr_timeline_prepare(tr_timeline* timeline)
+    {
+        if (!timeline) return fail("tr_timeline_prepare: null");
+        return guarded([&] { return ensureGraph(timeline); });
+    }
+
+    int tr_timeline_info(const tr_timeline* timeline, double* start_value, double* rate, int* frames, int* width, int* height, int* type)
+    {
+        if (!timeline) return fail("tr_timeline_info: null");
+        return guarded([&] {
+            const OTIO_NS::TimeRange& range = timeline->wrapper->getTimeRange();
+            if (start_value) *start_value = range.start_time().value();
+            if (rate) *rate = range.duration().rate();
+            if (frames)
+            {
+                // the frame loop of App.cpp:222-224
+                int n = 0;
+                const OTIO_NS::RationalTime inc(1.0, range.duration().rate());
+                for (OTIO_NS::RationalTime t = range.start_time(); t <= range.end_time_inclusive(); t += inc) ++n;
+                *frames = n;
+            }
+            if (timeline->graph)
+            {
+                if (width) *width = timeline->graph->getImageSize().x;
+                if (height) *height = timeline->graph->getImageSize().y;
+                if (type)
+                {
+                    const std::string& s = timeline->graph->getImageDataType();
+                    *type = s == "u8" ? TC_U8 : s == "u16" ? TC_U16 : s == "half" ? TC_F16 : s == "float" ? TC_F32 : -1;
+                }
+            }
+            return 0;
+        });
+    }
+
+    int tr_timeline_describe(tr_timeline* timeline, tr_host* host, double time_value, char* out, size_t capacity)
+    {
+        if (!timeline || !host) return fail("tr_timeline_describe: null");
+        return guarded([&] {
+            ensureGraph(timeline);
+            auto node = timeline->graph->exec(host->host, timeOf(timeline, time_value));
+            std::vector<std::string> lines;
+            if (node) node->describeTree(lines);
+            std::stringstream ss;
+            for (const auto& line : lines) ss << line << "\n";
+            return copyOut(ss.str(), out, capacity);
+        });
+    }
+
+    int tr_timeline_render(tr_timeline* timeline, tr_host* host, double time_value, void* out, size_t capacity, int* width, int* height, int* type)
+    {
+        if (!timeline || !host || !out) return fail("tr_timeline_render: null");
+        return guarded([&] {
+            const Image image = renderImage(timeline, host, time_value);
+            const ImageSpec& spec = image.spec();
+            if (width) *width = spec.width;
+            if (height) *height = spec.height;
+            if (type) *type = spec.format;
+            if (spec.image_bytes() > capacity) return fail("tr_timeline_render: output buffer too small");
+            image.download(out);
+            return 0;
+        });
+    }
+
+    int tr_timeline_render_resident(tr_timeline* timeline, tr_host* host, double time_value, void** out, int* width, int* height, int* type)
+    {
+        if (!timeline || !host || !out) return fail("tr_timeline_render_resident: null");
+        return guarded([&] {
+            timeline->resident = renderImage(timeline, host, time_value);
+            const ImageSpec& spec = timeline->resident.spec();
+            *out = timeline->resident.data();
+            if (width) *width = spec.width;
+            if (height) *height = spec.height;
+            if (type) *type = spec.format;
+            return 0;
+        });
+    }
+
+    int tr_decode_png(const char* path, void* out, size_t capacity, int* width, int* height, int* type)
+    {
+        if (!path) return fail("tr_decode_png: null");
+        return guarded([&] {
+            MediaFrame frame;
+            if (!readPng(path, frame)) return fail(std::string("tr_decode_png: cannot read ") + path);
+            if (width) *width = frame.width;
+            if (height) *height = frame.height;
+            if (type) *type = frame.format;
+            const size_t bytes = tc_image_bytes(frame.width, frame.height, frame.format);
+            if (out)
+            {
+                if (bytes > capacity) return fail("tr_decode_png: output buffer too small");
+                memcpy(out, frame.host, bytes);
+            }
+            return 0;
+        });
+    }
+
+    void tr_set_fusion(int enabled) { setStackFusionEnabled(enabled != 0); }
+}

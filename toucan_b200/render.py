@@ -1,0 +1,198 @@
+"""ctypes binding of libtoucan_render.so (include/toucan_render.h): the C++ host --
+ImageEffectHost + TimelineWrapper + ImageGraph -- for the Python test and bench harness.
+
+Plumbing only.  Frames are numpy arrays / torch tensors of shape (h, w, 4); the render
+itself is the C++ graph evaluation enqueuing the sm_100a kernels.  No fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import capi
+
+RENDER_LIB = os.path.join(capi.LIB_DIR, "libtoucan_render.so")
+PLUGIN_DIR = os.path.join(capi.LIB_DIR, "plugins")
+
+_NP_OF = {capi.U8: np.uint8, capi.U16: np.uint16, capi.F16: np.float16, capi.F32: np.float32}
+_T_OF = {np.dtype(np.uint8): capi.U8, np.dtype(np.uint16): capi.U16, np.dtype(np.float16): capi.F16, np.dtype(np.float32): capi.F32}
+
+_lib = None
+_VP = ctypes.c_void_p
+_IP = ctypes.POINTER(ctypes.c_int)
+_DP = ctypes.POINTER(ctypes.c_double)
+_SIGS = {
+    "tr_bind_device": [ctypes.c_int],
+    "tr_sync": [],
+    "tr_host_create": [ctypes.c_char_p, ctypes.POINTER(_VP)],
+    "tr_host_plugin_count": [_VP],
+    "tr_timeline_open": [ctypes.c_char_p, ctypes.POINTER(_VP)],
+    "tr_timeline_open_json": [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_VP)],
+    "tr_timeline_media_path": [_VP, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t],
+    "tr_timeline_set_media": [_VP, ctypes.c_char_p, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int],
+    "tr_timeline_prepare": [_VP],
+    "tr_timeline_info": [_VP, _DP, _DP, _IP, _IP, _IP, _IP],
+    "tr_timeline_describe": [_VP, _VP, ctypes.c_double, ctypes.c_char_p, ctypes.c_size_t],
+    "tr_timeline_render": [_VP, _VP, ctypes.c_double, _VP, ctypes.c_size_t, _IP, _IP, _IP],
+    "tr_decode_png": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
+    "tr_timeline_render_resident": [_VP, _VP, ctypes.c_double, ctypes.POINTER(_VP), _IP, _IP, _IP],
+}
+EXPORTS = sorted(set(_SIGS) | {"tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion"})
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        capi.lib()  # libtoucan_cuda.so first (RTLD_GLOBAL)
+        if not os.path.exists(RENDER_LIB):
+            raise capi.TcError(f"{RENDER_LIB} is missing: run `python -m toucan_b200.build`")
+        _lib = ctypes.CDLL(RENDER_LIB, mode=ctypes.RTLD_GLOBAL)
+        for name, sig in _SIGS.items():
+            fn = getattr(_lib, name)
+            fn.argtypes = sig
+            fn.restype = ctypes.c_int
+        _lib.tr_last_error.restype = ctypes.c_char_p
+        _lib.tr_host_destroy.argtypes = [_VP]
+        _lib.tr_host_destroy.restype = None
+        _lib.tr_timeline_close.argtypes = [_VP]
+        _lib.tr_timeline_close.restype = None
+        _lib.tr_host_plugin_identifier.argtypes = [_VP, ctypes.c_int]
+        _lib.tr_host_plugin_identifier.restype = ctypes.c_char_p
+        _lib.tr_set_fusion.argtypes = [ctypes.c_int]
+        _lib.tr_set_fusion.restype = None
+    return _lib
+
+
+def _check(status, what):
+    if status != 0:
+        raise capi.TcError(f"{what} failed: {lib().tr_last_error().decode()}")
+
+
+def bind_device(device: int = 0):
+    _check(lib().tr_bind_device(device), "tr_bind_device")
+
+
+def sync():
+    _check(lib().tr_sync(), "tr_sync")
+
+
+def set_fusion(enabled: bool):
+    lib().tr_set_fusion(1 if enabled else 0)
+
+
+def decode_png(path: str) -> np.ndarray:
+    """The C++ host's built-in PNG reader (RGBA, alpha associated like OIIO's reader)."""
+    w, h, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _check(lib().tr_decode_png(path.encode(), None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_png")
+    out = np.empty((h.value, w.value, 4), _NP_OF[t.value])
+    _check(lib().tr_decode_png(path.encode(), out.ctypes.data, out.nbytes, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_png")
+    return out
+
+
+class Host:
+    """toucan::ImageEffectHost over the in-tree *.ofx modules."""
+
+    def __init__(self, plugin_dir: str = PLUGIN_DIR):
+        self._h = _VP()
+        _check(lib().tr_host_create(plugin_dir.encode(), ctypes.byref(self._h)), "tr_host_create")
+
+    def identifiers(self):
+        n = lib().tr_host_plugin_count(self._h)
+        return [lib().tr_host_plugin_identifier(self._h, i).decode() for i in range(n)]
+
+    def close(self):
+        if self._h:
+            lib().tr_host_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Timeline:
+    """toucan::TimelineWrapper + toucan::ImageGraph + the timeline's media store."""
+
+    def __init__(self, path: str | None = None, json_doc=None, directory: str = ""):
+        self._t = _VP()
+        self._keep = []  # registered frames are borrowed by the C++ side
+        if path is not None:
+            _check(lib().tr_timeline_open(path.encode(), ctypes.byref(self._t)), "tr_timeline_open")
+        else:
+            text = json_doc if isinstance(json_doc, str) else json.dumps(json_doc)
+            _check(lib().tr_timeline_open_json(text.encode(), directory.encode(), ctypes.byref(self._t)), "tr_timeline_open_json")
+
+    def media_path(self, url: str) -> str:
+        buf = ctypes.create_string_buffer(4096)
+        _check(lib().tr_timeline_media_path(self._t, url.encode(), buf, len(buf)), "tr_timeline_media_path")
+        return buf.value.decode()
+
+    def set_media(self, path: str, frame):
+        """frame: numpy (h, w, 4) host array, or a torch CUDA tensor (kept resident)."""
+        if isinstance(frame, np.ndarray):
+            assert frame.ndim == 3 and frame.shape[2] == 4 and frame.flags.c_contiguous
+            ptr, dev, t = frame.ctypes.data, 0, _T_OF[frame.dtype]
+        else:
+            import torch
+
+            from .ops import _DT
+
+            assert frame.dim() == 3 and frame.shape[2] == 4 and frame.is_contiguous()
+            ptr, dev, t = frame.data_ptr(), (1 if frame.is_cuda else 0), _DT[frame.dtype]
+            del torch
+        self._keep.append(frame)
+        _check(lib().tr_timeline_set_media(self._t, path.encode(), ptr, dev, frame.shape[1], frame.shape[0], t), "tr_timeline_set_media")
+
+    def prepare(self):
+        _check(lib().tr_timeline_prepare(self._t), "tr_timeline_prepare")
+
+    def info(self):
+        s, r = ctypes.c_double(), ctypes.c_double()
+        n, w, h, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int(-1)
+        _check(lib().tr_timeline_info(self._t, ctypes.byref(s), ctypes.byref(r), ctypes.byref(n), ctypes.byref(w), ctypes.byref(h),
+                                      ctypes.byref(t)), "tr_timeline_info")
+        return {"start": s.value, "rate": r.value, "frames": n.value, "width": w.value, "height": h.value, "type": t.value}
+
+    def describe(self, host: Host, time_value: float) -> str:
+        buf = ctypes.create_string_buffer(1 << 20)
+        _check(lib().tr_timeline_describe(self._t, host._h, float(time_value), buf, len(buf)), "tr_timeline_describe")
+        return buf.value.decode()
+
+    def render(self, host: Host, time_value: float, max_bytes: int | None = None) -> np.ndarray:
+        """graph->exec(host, time); node->exec(); download -- returns (h, w, 4) numpy."""
+        i = self.info()
+        cap = max_bytes or max(16, i["width"] * i["height"] * 16)
+        raw = np.empty(cap, np.uint8)
+        w, h, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(lib().tr_timeline_render(self._t, host._h, float(time_value), raw.ctypes.data, cap, ctypes.byref(w), ctypes.byref(h),
+                                        ctypes.byref(t)), "tr_timeline_render")
+        if w.value <= 0 or h.value <= 0:
+            return np.zeros((0, 0, 4), np.uint8)
+        dt = np.dtype(_NP_OF[t.value])
+        n = w.value * h.value * 4
+        return raw[: n * dt.itemsize].view(dt).reshape(h.value, w.value, 4).copy()
+
+    def render_resident(self, host: Host, time_value: float):
+        """Render and leave the frame in HBM: returns (device_ptr, w, h, tc_type).  Valid
+        until the next call; enqueued on the bound thread's stream (sync() before use)."""
+        p = _VP()
+        w, h, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(lib().tr_timeline_render_resident(self._t, host._h, float(time_value), ctypes.byref(p), ctypes.byref(w), ctypes.byref(h),
+                                                 ctypes.byref(t)), "tr_timeline_render_resident")
+        return p.value, w.value, h.value, t.value
+
+    def close(self):
+        if self._t:
+            lib().tr_timeline_close(self._t)
+            self._t = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
