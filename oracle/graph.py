@@ -81,6 +81,14 @@ class TR:
         return self.start.secs() <= t.secs() and t.secs() < self.end_exclusive().secs()
 
 
+def _media_ref(j):
+    """Clip.1 `media_reference`, or Clip.2 `media_references[active_media_reference_key]`."""
+    mr = j.get("media_reference")
+    if mr is None and isinstance(j.get("media_references"), dict):
+        mr = j["media_references"].get(j.get("active_media_reference_key", "DEFAULT_MEDIA"))
+    return mr or {}
+
+
 def _rt(j):
     return RT(float(j["value"]), float(j["rate"])) if j else None
 
@@ -123,7 +131,7 @@ class Node:
     def available_range(self) -> TR:
         k = self.kind
         if k == "Clip":
-            mr = self.j.get("media_reference") or {}
+            mr = _media_ref(self.j)
             ar = _tr(mr.get("available_range"))
             return ar if ar is not None else TR()
         if k == "Track":
@@ -309,7 +317,7 @@ class ImageGraph:
         self.dtype = ""
         # ImageGraph.cpp:53-123
         for clip in timeline.video_clips():
-            mr = clip.j.get("media_reference") or {}
+            mr = _media_ref(clip.j)
             s = mr.get("OTIO_SCHEMA", "")
             if s.startswith("ExternalReference") or s.startswith("ImageSequenceReference"):
                 path = self._first_path(mr)
@@ -415,7 +423,7 @@ class ImageGraph:
         out = None
         t = self._time_warps(time, item.available_range(), item.effects)
         if item.kind == "Clip":
-            mr = item.j.get("media_reference") or {}
+            mr = _media_ref(item.j)
             s = mr.get("OTIO_SCHEMA", "")
             if s.startswith("ExternalReference"):
                 path = self._media_path(mr.get("target_url", ""))

@@ -1,11 +1,27 @@
 // tc_stack.cu -- cross-node fusion of the hot chain of a multi-track timeline:
 //   per track:  [toucan:Blur] -> [toucan:Dissolve with the neighbouring clip] -> CompNode(premult + over)
 // evaluated for ALL tracks in one pass over the output tile, accumulator in registers.
-// Compulsory HBM traffic = every referenced source frame read once (+ halo) and the
-// final frame written once, instead of one read+write of a full frame per graph node
-// (lib/toucanRender/ImageGraph.cpp:165-198, Comp.cpp:29-84, FilterPlugin.cpp:188-202,
+// Compulsory HBM traffic = every referenced source frame read once (+ halo, served by L2)
+// and the final frame written once, instead of one read+write of a full frame per graph
+// node (lib/toucanRender/ImageGraph.cpp:165-198, Comp.cpp:29-84, FilterPlugin.cpp:188-202,
 // TransitionPlugin.cpp:242-264).  float32 RGBA only (the working format of the 8K config).
+//
+// Kernel shape (k_stack_f32<R>): one CTA of 256 threads per 64 x 24 output tile, three
+// CTAs resident per SM.  Per blurred layer:
+//   stage   (64+2R) x (24+2R) source pixels -> shared memory, coordinates clamped to the
+//           frame (OIIO convolve clamps); a Dissolve whose two inputs carry the same blur
+//           is mixed HERE, before the blur (convolution is linear, so blur(a)*iv + blur(b)*v
+//           = blur(a*iv + b*v) to float rounding) -- one blur instead of two;
+//   rows    horizontal taps: each thread owns 8 adjacent pixels of one row and slides the
+//           2R+1 taps over 8+2R shared-memory reads (2 reads per output instead of 2R+1);
+//   columns vertical taps: each thread owns 6 consecutive rows of one column (6+2R reads),
+//           then blends the finished layer into its 6 accumulator pixels.
+// Row strides of both shared tiles are odd multiples of 16 bytes so the row-per-lane
+// accesses of the horizontal pass are bank-conflict free.
+//
+// Tolerance path (<= 1e-5 abs), FMA contraction allowed.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -13,129 +29,241 @@
 
 namespace tc {
 
-constexpr int ST_MAX_R = 12;     // live taps per side (radius parameter up to ~26)
+constexpr int ST_MAX_R = 12;      // live taps per side (radius parameter up to ~26)
 constexpr int ST_MAX_KERNELS = 4; // distinct blur kernels per launch
 constexpr int ST_MAX_LAYERS = 32;
-constexpr int ST_TW = 32, ST_TH = 32, ST_THREADS = 256;
-constexpr int ST_PER_THREAD = ST_TW * ST_TH / ST_THREADS;
+constexpr int ST_MAX_UNITS = 2 * ST_MAX_LAYERS;
+constexpr int ST_TW = 64, ST_THREADS = 256;
+constexpr int ST_HB = 8; // pixels per thread in the horizontal pass
 
 struct StKernel {
     int R;
     float scale;
-    float g[2 * ST_MAX_R + 1];
+    float g[2 * ST_MAX_R + 1]; // already multiplied by sqrt(scale)
 };
-struct StLayer {
-    const float4* a;
-    const float4* b;
-    int ka, kb; // kernel index or -1
-    float v, iv;
+// One step of the per-tile pipeline.  A blurred layer is one staged unit; a blurred Dissolve
+// is two (H-pass of `from` weighted by iv, H-pass of `to` weighted by v accumulated on top,
+// ONE vertical pass: blur is linear).  An unblurred layer is a DIRECT unit (no staging).
+enum { ST_FIRST = 1, ST_LAST = 2, ST_DIRECT = 4 };
+struct StUnit {
+    const float4* src;
+    const float4* src2; // DIRECT units only: the Dissolve's second input (or null)
+    float w;            // weight folded into the horizontal taps (1, iv or v)
+    float w2;           // DIRECT units: v (src weight = w)
+    short kernel;
+    short flags;
+    int next_staged; // index of the next staged unit (prefetch target), or -1
 };
 struct StParams {
-    int w, h, n_layers;
+    int w, h, n_units, first_staged;
     float4 background;
     StKernel k[ST_MAX_KERNELS];
-    StLayer layer[ST_MAX_LAYERS];
+    StUnit unit[ST_MAX_UNITS];
 };
 
-__device__ __forceinline__ float4 fma4s(float w, float4 p, float4 a)
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2): one issue slot per two multiply-adds.  The
+// kernel is issue-bound, not FMA-pipe-bound, so halving the FMA issue slots is the lever.
+__device__ __forceinline__ float4 fma4p(float w, float4 p, float4 a)
 {
-    return make_float4(fmaf(w, p.x, a.x), fmaf(w, p.y, a.y), fmaf(w, p.z, a.z), fmaf(w, p.w, a.w));
+    const float2 ww = make_float2(w, w);
+    const float2 lo = __ffma2_rn(ww, make_float2(p.x, p.y), make_float2(a.x, a.y));
+    const float2 hi = __ffma2_rn(ww, make_float2(p.z, p.w), make_float2(a.z, a.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 mul4p(float w, float4 p)
+{
+    const float2 ww = make_float2(w, w);
+    const float2 lo = __fmul2_rn(ww, make_float2(p.x, p.y));
+    const float2 hi = __fmul2_rn(ww, make_float2(p.z, p.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-// Blur one source over the CTA's tile; results for this thread's pixels in out[].
-__device__ __forceinline__ void tile_blur(const float4* __restrict__ src, int w, int h, int x0, int y0, const StKernel& K,
-                                          float4* in, float4* mid, float4 out[ST_PER_THREAD])
+// Dissolve: add(mul(from, iv), mul(to, v)) (float storage: nothing is quantised)
+__device__ __forceinline__ float4 mix4(float4 a, float4 b, float iv, float v)
 {
-    const int R = K.R;
-    const int IW = ST_TW + 2 * R, IH = ST_TH + 2 * R;
-    __syncthreads(); // previous users of in/mid are done
-    for (int i = threadIdx.x; i < IH * IW; i += ST_THREADS) {
-        const int iy = i / IW, ix = i - iy * IW;
-        const int sx = min(max(x0 - R + ix, 0), w - 1), sy = min(max(y0 - R + iy, 0), h - 1);
-        in[i] = __ldg(src + (size_t)sy * w + sx);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < IH * ST_TW; i += ST_THREADS) {
-        const int row = i / ST_TW, col = i - row * ST_TW;
-        const float4* p = in + row * IW + col;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = 0; t <= 2 * R; ++t) acc = fma4s(K.g[t], p[t], acc);
-        mid[i] = acc;
-    }
-    __syncthreads();
+    return make_float4(__fadd_rn(__fmul_rn(a.x, iv), __fmul_rn(b.x, v)), __fadd_rn(__fmul_rn(a.y, iv), __fmul_rn(b.y, v)),
+                       __fadd_rn(__fmul_rn(a.z, iv), __fmul_rn(b.z, v)), __fadd_rn(__fmul_rn(a.w, iv), __fmul_rn(b.w, v)));
+}
+
+template <int R, int TH, int NBUF = 2>
+struct StTile {
+    static constexpr int PX = ST_TW * TH / ST_THREADS; // output pixels per thread: one column segment
+    static constexpr int IW = ST_TW + 2 * R;  // staged columns
+    static constexpr int IH = TH + 2 * R;     // staged rows
+    static constexpr int IWP = IW | 1;        // odd row stride (float4 units)
+    static constexpr int MWP = ST_TW | 1;
+    static constexpr int IN_ELEMS = IH * IWP;
+    static constexpr int MID_ELEMS = IH * MWP;
+    static constexpr size_t SMEM = (size_t)(NBUF * IN_ELEMS + MID_ELEMS) * sizeof(float4); // staging buffer(s) + mid
+    static constexpr int STAGE_ROWS = ST_THREADS / IW;                 // rows staged per pass
+    static constexpr int STAGE_N = (IH + STAGE_ROWS - 1) / STAGE_ROWS; // passes
+};
+
+__device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Asynchronous stage of one source tile (with halo, coordinates clamped to the frame as
+// OIIO's convolve does) into shared memory: thread = one staged column, STAGE_ROWS rows per
+// pass, no registers held while the copies are in flight.
+template <int R, int TH>
+__device__ __forceinline__ void tile_prefetch(const float4* __restrict__ src, int w, int h, int x0, int y0, float4* in)
+{
+    using T = StTile<R, TH>;
+    const int tid = threadIdx.x;
+    if (tid < T::STAGE_ROWS * T::IW) {
+        const int ry = tid / T::IW, ix = tid - ry * T::IW;
+        const float4* p = src + min(max(x0 - R + ix, 0), w - 1);
+        float4* d = in + ix;
 #pragma unroll
-    for (int k = 0; k < ST_PER_THREAD; ++k) {
-        const int i = threadIdx.x + k * ST_THREADS;
-        const int row = i / ST_TW, col = i - row * ST_TW;
-        const float4* p = mid + row * ST_TW + col;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = 0; t <= 2 * R; ++t) acc = fma4s(K.g[t], p[t * ST_TW], acc);
-        out[k] = make_float4(acc.x * K.scale, acc.y * K.scale, acc.z * K.scale, acc.w * K.scale);
+        for (int u = 0; u < T::STAGE_N; ++u) {
+            const int iy = ry + u * T::STAGE_ROWS;
+            if (iy < T::IH) cp_async16(d + iy * T::IWP, p + (size_t)min(max(y0 - R + iy, 0), h - 1) * w);
+        }
     }
+    cp_async_commit();
 }
 
-__device__ __forceinline__ void tile_load(const float4* __restrict__ src, int w, int h, int x0, int y0, float4 out[ST_PER_THREAD])
+// rows: 8 adjacent outputs per thread, lanes on consecutive rows; FIRST writes mid, else adds
+template <int R, int TH, bool FIRST>
+__device__ __forceinline__ void tile_rows(const float4* in, float4* mid, const float (&g)[2 * R + 1])
 {
+    using T = StTile<R, TH>;
+    constexpr int N_H = T::IH * (ST_TW / ST_HB);
+    for (int item = threadIdx.x; item < N_H; item += ST_THREADS) {
+        const int row = item % T::IH, xb = item / T::IH;
+        const float4* p = in + row * T::IWP + xb * ST_HB;
+        float4* m = mid + row * T::MWP + xb * ST_HB;
+        float4 o[ST_HB];
+        if (!FIRST) {
 #pragma unroll
-    for (int k = 0; k < ST_PER_THREAD; ++k) {
-        const int i = threadIdx.x + k * ST_THREADS;
-        const int row = i / ST_TW, col = i - row * ST_TW;
-        const int x = min(x0 + col, w - 1), y = min(y0 + row, h - 1);
-        out[k] = __ldg(src + (size_t)y * w + x);
+            for (int k = 0; k < ST_HB; ++k) o[k] = m[k];
+        }
+#pragma unroll
+        for (int j = 0; j < ST_HB + 2 * R; ++j) {
+            const float4 q = p[j];
+#pragma unroll
+            for (int k = 0; k < ST_HB; ++k) {
+                const int t = j - k;
+                if (FIRST && t == 0) o[k] = mul4p(g[0], q);
+                else if (t >= 0 && t <= 2 * R) o[k] = fma4p(g[t], q, o[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ST_HB; ++k) m[k] = o[k];
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS) k_stack_f32(float4* __restrict__ dst, const __grid_constant__ StParams P)
+// columns: PX consecutive rows per thread, lanes on consecutive columns
+template <int R, int TH>
+__device__ __forceinline__ void tile_cols(const float4* mid, const float (&g)[2 * R + 1], float4 out[StTile<R, TH>::PX])
 {
+    using T = StTile<R, TH>;
+    const int col = threadIdx.x % ST_TW, seg = threadIdx.x / ST_TW;
+    const float4* p = mid + (seg * T::PX) * T::MWP + col;
+#pragma unroll
+    for (int j = 0; j < T::PX + 2 * R; ++j) {
+        const float4 q = p[j * T::MWP];
+#pragma unroll
+        for (int k = 0; k < T::PX; ++k) {
+            const int t = j - k;
+            if (t == 0) out[k] = mul4p(g[0], q);
+            else if (t > 0 && t <= 2 * R) out[k] = fma4p(g[t], q, out[k]);
+        }
+    }
+}
+
+template <int ST_PX>
+__device__ __forceinline__ void tile_load(const float4* __restrict__ src, int w, int h, int x, int y, float4 out[ST_PX])
+{
+    x = min(x, w - 1);
+#pragma unroll
+    for (int k = 0; k < ST_PX; ++k) out[k] = __ldg(src + (size_t)min(y + k, h - 1) * w + x);
+}
+
+// NBUF = 2: the next unit's tile streams into the other staging buffer while this one is
+// filtered (2 CTAs per SM at radius 10).  NBUF = 1: one staging buffer, the next tile streams
+// in during the vertical pass and the blend (3 CTAs per SM at radius 10).
+template <int R, int TH, int NBUF, int OCC>
+__global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restrict__ dst, const __grid_constant__ StParams P)
+{
+    using T = StTile<R, TH, NBUF>;
+    constexpr int ST_PX = T::PX;
     extern __shared__ float4 smem[];
-    float4* in = smem;
-    float4* mid = smem + (ST_TH + 2 * ST_MAX_R) * (ST_TW + 2 * ST_MAX_R);
-    const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * ST_TH;
+    float4* mid = smem + NBUF * T::IN_ELEMS;
+    const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * TH;
+    const int col = threadIdx.x % ST_TW, seg = threadIdx.x / ST_TW;
+    const int x = x0 + col, y = y0 + seg * ST_PX;
 
-    float4 acc[ST_PER_THREAD];
+    float4 acc[ST_PX];
 #pragma unroll
-    for (int k = 0; k < ST_PER_THREAD; ++k) acc[k] = P.background;
+    for (int k = 0; k < ST_PX; ++k) acc[k] = P.background;
 
-    for (int l = 0; l < P.n_layers; ++l) {
-        const StLayer& L = P.layer[l];
-        float4 a[ST_PER_THREAD];
-        if (L.ka >= 0) tile_blur(L.a, P.w, P.h, x0, y0, P.k[L.ka], in, mid, a);
-        else tile_load(L.a, P.w, P.h, x0, y0, a);
-        if (L.b) {
-            float4 b[ST_PER_THREAD];
-            if (L.kb >= 0) tile_blur(L.b, P.w, P.h, x0, y0, P.k[L.kb], in, mid, b);
-            else tile_load(L.b, P.w, P.h, x0, y0, b);
-            // Dissolve: add(mul(from, iv), mul(to, v))
+    int slot = 0;
+    if (P.first_staged >= 0) tile_prefetch<R, TH>(P.unit[P.first_staged].src, P.w, P.h, x0, y0, smem);
+
+    for (int u = 0; u < P.n_units; ++u) {
+        const StUnit& U = P.unit[u];
+        float4 f[ST_PX];
+        if (U.flags & ST_DIRECT) {
+            tile_load<ST_PX>(U.src, P.w, P.h, x, y, f);
+            if (U.src2) {
+                float4 fb[ST_PX];
+                tile_load<ST_PX>(U.src2, P.w, P.h, x, y, fb);
 #pragma unroll
-            for (int k = 0; k < ST_PER_THREAD; ++k) {
-                a[k].x = __fadd_rn(__fmul_rn(a[k].x, L.iv), __fmul_rn(b[k].x, L.v));
-                a[k].y = __fadd_rn(__fmul_rn(a[k].y, L.iv), __fmul_rn(b[k].y, L.v));
-                a[k].z = __fadd_rn(__fmul_rn(a[k].z, L.iv), __fmul_rn(b[k].z, L.v));
-                a[k].w = __fadd_rn(__fmul_rn(a[k].w, L.iv), __fmul_rn(b[k].w, L.v));
+                for (int k = 0; k < ST_PX; ++k) f[k] = mix4(f[k], fb[k], U.w, U.w2);
             }
+        } else {
+            const StKernel& K = P.k[U.kernel];
+            // taps centred on R (zero padded when this kernel is narrower than the template)
+            float g[2 * R + 1], gw[2 * R + 1];
+#pragma unroll
+            for (int t = 0; t <= 2 * R; ++t) {
+                const int s = t - R + K.R;
+                g[t] = (s >= 0 && s <= 2 * K.R) ? K.g[s] : 0.0f;
+                gw[t] = g[t] * U.w;
+            }
+            cp_async_wait_all();
+            __syncthreads(); // this unit's tile has landed; `mid` (and the other buffer) are free again
+            const float4* in = smem + slot * T::IN_ELEMS;
+            if (NBUF == 2) {
+                slot ^= 1;
+                if (U.next_staged >= 0)
+                    tile_prefetch<R, TH>(P.unit[U.next_staged].src, P.w, P.h, x0, y0, smem + slot * T::IN_ELEMS);
+            }
+            if (U.flags & ST_FIRST) tile_rows<R, TH, true>(in, mid, gw);
+            else tile_rows<R, TH, false>(in, mid, gw);
+            if (NBUF == 1) {
+                __syncthreads(); // every row pass is done with the staging buffer
+                if (U.next_staged >= 0) tile_prefetch<R, TH>(P.unit[U.next_staged].src, P.w, P.h, x0, y0, smem);
+                if (!(U.flags & ST_LAST)) continue;
+            } else {
+                if (!(U.flags & ST_LAST)) continue;
+                __syncthreads();
+            }
+            tile_cols<R, TH>(mid, g, f);
         }
-        // CompNode: premult(fg) then over(fg, acc)
+        // CompNode: premult(fg) then over(fg, acc); tolerance path, so fused multiply-adds
 #pragma unroll
-        for (int k = 0; k < ST_PER_THREAD; ++k) {
-            float4 f = a[k];
-            if (f.w != 1.0f) {
-                f.x = __fmul_rn(f.x, f.w);
-                f.y = __fmul_rn(f.y, f.w);
-                f.z = __fmul_rn(f.z, f.w);
-            }
-            const float oma = __fsub_rn(1.0f, fminf(fmaxf(f.w, 0.0f), 1.0f));
-            acc[k].x = __fadd_rn(f.x, __fmul_rn(oma, acc[k].x));
-            acc[k].y = __fadd_rn(f.y, __fmul_rn(oma, acc[k].y));
-            acc[k].z = __fadd_rn(f.z, __fmul_rn(oma, acc[k].z));
-            acc[k].w = __fadd_rn(f.w, __fmul_rn(oma, acc[k].w));
+        for (int k = 0; k < ST_PX; ++k) {
+            float4 p = f[k];
+            const float a = p.w;
+            const float pm = a != 1.0f ? a : 1.0f;
+            p.x *= pm;
+            p.y *= pm;
+            p.z *= pm;
+            const float oma = 1.0f - fminf(fmaxf(a, 0.0f), 1.0f);
+            acc[k] = fma4p(oma, acc[k], p);
         }
     }
+    if (x < P.w) {
 #pragma unroll
-    for (int k = 0; k < ST_PER_THREAD; ++k) {
-        const int i = threadIdx.x + k * ST_THREADS;
-        const int row = i / ST_TW, col = i - row * ST_TW;
-        const int x = x0 + col, y = y0 + row;
-        if (x < P.w && y < P.h) dst[(size_t)y * P.w + x] = acc[k];
+        for (int k = 0; k < ST_PX; ++k)
+            if (y + k < P.h) __stcs(dst + (size_t)(y + k) * P.w + x, acc[k]);
     }
 }
 
@@ -183,9 +311,33 @@ static int st_build_kernel(float width, StKernel* K)
     if (live > ST_MAX_R) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: blur radius %g needs %d taps per side (max %d)", width, live, ST_MAX_R);
     K->R = live;
     K->scale = (1.0f / ksum) / sum;
+    // the two 1-D passes each carry sqrt(scale): their product is the normalised 2-D kernel
+    const float root = sqrtf(K->scale);
     memset(K->g, 0, sizeof(K->g));
-    for (int i = -live; i <= live; ++i) K->g[i + live] = g[r + i];
+    for (int i = -live; i <= live; ++i) K->g[i + live] = g[r + i] * root;
     return TC_OK;
+}
+
+// CTAs per SM the shared-memory footprint allows (227 KB usable, 1 KB reserved per CTA)
+template <int R, int TH, int NBUF>
+constexpr int st_occ() { return StTile<R, TH, NBUF>::SMEM <= 74 * 1024 ? 3 : (StTile<R, TH, NBUF>::SMEM <= 112 * 1024 ? 2 : 1); }
+
+template <int R, int TH, int NBUF, int OCC = st_occ<R, TH, NBUF>()>
+static int launch_stack(const tc_image* dst, const StParams& P, cudaStream_t st)
+{
+    using T = StTile<R, TH, NBUF>;
+    static_assert(T::SMEM <= 227 * 1024, "tile does not fit in shared memory");
+    static bool configured = false;
+    if (!configured) {
+        TC_CUDA(cudaFuncSetAttribute(k_stack_f32<R, TH, NBUF, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+        TC_CUDA(cudaFuncSetAttribute(k_stack_f32<R, TH, NBUF, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
+    dim3 grid((dst->w + ST_TW - 1) / ST_TW, (dst->h + TH - 1) / TH);
+    k_stack_f32<R, TH, NBUF, OCC><<<grid, ST_THREADS, T::SMEM, st>>>((float4*)dst->data, P);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_stack_f32 launch");
 }
 
 } // namespace tc
@@ -203,10 +355,9 @@ extern "C" int tc_stack_f32(const tc_image* dst, const float background[4], cons
     memset(&P, 0, sizeof(P));
     P.w = dst->w;
     P.h = dst->h;
-    P.n_layers = n_layers;
     P.background = make_float4(background[0], background[1], background[2], background[3]);
     float radii[ST_MAX_KERNELS];
-    int nk = 0;
+    int nk = 0, maxR = 1;
     auto kernel_of = [&](float radius, int* idx) -> int {
         *idx = -1;
         if (!(radius > 0.0f)) return TC_OK;
@@ -218,28 +369,56 @@ extern "C" int tc_stack_f32(const tc_image* dst, const float background[4], cons
         if (nk == ST_MAX_KERNELS) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: more than %d distinct blur radii", ST_MAX_KERNELS);
         int st = st_build_kernel(radius, &P.k[nk]);
         if (st != TC_OK) return st;
+        if (P.k[nk].R > maxR) maxR = P.k[nk].R;
         radii[nk] = radius;
         *idx = nk++;
         return TC_OK;
     };
+    int nu = 0, last_staged = -1;
+    P.first_staged = -1;
+    auto staged = [&](const void* src, float w, int kernel, int flags) {
+        StUnit& U = P.unit[nu];
+        U.src = (const float4*)src;
+        U.w = w;
+        U.kernel = (short)kernel;
+        U.flags = (short)flags;
+        U.next_staged = -1;
+        if (last_staged >= 0) P.unit[last_staged].next_staged = nu;
+        else P.first_staged = nu;
+        last_staged = nu++;
+    };
     for (int l = 0; l < n_layers; ++l) {
         if (!layers[l].src_a) return fail(TC_ERR_INVALID, "tc_stack_f32: layer %d has no source", l);
-        P.layer[l].a = (const float4*)layers[l].src_a;
-        P.layer[l].b = (const float4*)layers[l].src_b;
-        if ((v = kernel_of(layers[l].radius_a, &P.layer[l].ka)) != TC_OK) return v;
-        P.layer[l].kb = -1;
-        if (layers[l].src_b && (v = kernel_of(layers[l].radius_b, &P.layer[l].kb)) != TC_OK) return v;
-        P.layer[l].v = (float)layers[l].value;
-        P.layer[l].iv = (float)(1.0 - layers[l].value);
+        int ka = -1, kb = -1;
+        if ((v = kernel_of(layers[l].radius_a, &ka)) != TC_OK) return v;
+        if (layers[l].src_b && (v = kernel_of(layers[l].radius_b, &kb)) != TC_OK) return v;
+        if (layers[l].src_b && ka != kb)
+            return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: layer %d dissolves inputs with different blurs (%g, %g)", l,
+                        layers[l].radius_a, layers[l].radius_b);
+        const float fv = (float)layers[l].value, fiv = (float)(1.0 - layers[l].value);
+        if (ka < 0) {
+            StUnit& U = P.unit[nu++];
+            U.src = (const float4*)layers[l].src_a;
+            U.src2 = (const float4*)layers[l].src_b;
+            U.w = fiv;
+            U.w2 = fv;
+            U.kernel = -1;
+            U.flags = ST_DIRECT;
+            U.next_staged = -1;
+        } else if (layers[l].src_b) {
+            staged(layers[l].src_a, fiv, ka, ST_FIRST);
+            staged(layers[l].src_b, fv, ka, ST_LAST);
+        } else {
+            staged(layers[l].src_a, 1.0f, ka, ST_FIRST | ST_LAST);
+        }
     }
-    const size_t smem = (size_t)((ST_TH + 2 * ST_MAX_R) * (ST_TW + 2 * ST_MAX_R) + (ST_TH + 2 * ST_MAX_R) * ST_TW) * sizeof(float4);
-    static bool configured = false;
-    if (!configured) {
-        TC_CUDA(cudaFuncSetAttribute(k_stack_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    dim3 grid((dst->w + ST_TW - 1) / ST_TW, (dst->h + ST_TH - 1) / ST_TH);
-    k_stack_f32<<<grid, ST_THREADS, smem, (cudaStream_t)s>>>((float4*)dst->data, P);
-    count_launch();
-    return check_cuda(cudaGetLastError(), "k_stack_f32 launch");
+    P.n_units = nu;
+    // tuning knob for the radius-10 (R = 4) case: number of staging buffers
+    static const int nbuf = getenv("TOUCAN_STACK_NBUF") ? atoi(getenv("TOUCAN_STACK_NBUF")) : 2;
+    cudaStream_t st = (cudaStream_t)s;
+    if (maxR <= 2) return launch_stack<2, 24, 2>(dst, P, st);
+    if (maxR <= 4) return nbuf == 1 ? launch_stack<4, 24, 1>(dst, P, st) : launch_stack<4, 24, 2>(dst, P, st);
+    if (maxR <= 6) return launch_stack<6, 24, 1>(dst, P, st);
+    if (maxR <= 9) return launch_stack<9, 24, 1>(dst, P, st);
+    return launch_stack<12, 24, 1>(dst, P, st);
 }
