@@ -58,7 +58,7 @@ class Clocks:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -96,10 +96,10 @@ class Clocks:
 
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle on a band of the frame (bench.py is one of the places allowed to run oracle/)
-def cpu_band_setup(cfg):
+def cpu_band_setup(cfg, div=BAND_DIV):
     import numpy as np
 
-    w, h = cfg["width"], cfg["height"] // BAND_DIV
+    w, h = cfg["width"], cfg["height"] // div
     src = {}
     yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
     for t in range(cfg["tracks"]):
@@ -123,12 +123,23 @@ def cpu_band_frame(O, w, h, src, layers):
     return acc
 
 
-def cpu_arm(cfg, frames, warmup):
+def cpu_arm(cfg, frames, warmup, target_step_s=None):
     from oracle import oracle as O
 
     O.lib()
-    w, h, src = cpu_band_setup(cfg)
+    div = BAND_DIV
+    w, h, src = cpu_band_setup(cfg, div)
     cores = os.cpu_count() or 1
+    if target_step_s:
+        # bounded sample: shrink the band until one step fits the time budget (per-pixel cost is unchanged)
+        t0 = time.perf_counter()
+        cpu_band_frame(O, w, h, src, workloads.stack_layers(frames[-1], **cfg))
+        dt = time.perf_counter() - t0
+        while dt > target_step_s and div < 256:
+            div *= 2
+            dt /= 2
+        if div != BAND_DIV:
+            w, h, src = cpu_band_setup(cfg, div)
     for f in frames[:warmup]:
         cpu_band_frame(O, w, h, src, workloads.stack_layers(f, **cfg))
     t0 = time.perf_counter()
@@ -136,14 +147,21 @@ def cpu_arm(cfg, frames, warmup):
         cpu_band_frame(O, w, h, src, workloads.stack_layers(f, **cfg))
     dt = time.perf_counter() - t0
     n = len(frames) - warmup
-    fps = n / (dt * BAND_DIV)
-    return fps, dt, cores, f"{n} frames x rows 0..{h - 1} of {cfg['height']} (1/{BAND_DIV} of each {cfg['width']}x{cfg['height']} frame), time scaled x{BAND_DIV}"
+    fps = n / (dt * div)
+    return fps, dt, cores, f"{n} frames x rows 0..{h - 1} of {cfg['height']} (1/{div} of each {cfg['width']}x{cfg['height']} frame), time scaled x{div}"
 
 
 def frames_for(rank, world, cfg, count):
+    """Frames a rank renders, inside its own contiguous block.  The window starts in the middle of a clip
+    and wraps at a multiple of half a clip, so every rank (and every multiple of 24 steps) sees the same
+    half-plain / half-transition mix."""
     lo, hi = workloads.frame_block(rank, world, cfg["frames"])
-    start = lo + cfg["clip_frames"] // 2  # 24-frame windows from here hold 50% transition frames
-    return [min(start + s, hi - 1) for s in range(count)]
+    period, half = cfg["clip_frames"], cfg["clip_frames"] // 2
+    start = lo + (half - lo) % period
+    avail = ((hi - start) // half) * half
+    if avail < half:
+        start, avail = lo, max(1, hi - lo)
+    return [start + s % avail for s in range(count)]
 
 
 def config_json(cfg, world):
@@ -159,7 +177,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     frames = frames_for(0, 1, cfg, args.steps + args.warmup)
-    fps, dt, cores, sample = cpu_arm(cfg, frames, args.warmup)
+    fps, dt, cores, sample = cpu_arm(cfg, frames, args.warmup, target_step_s=90.0 / max(1, args.steps + args.warmup))
     line = {"impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_json(cfg, 1),
@@ -174,8 +192,7 @@ def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
 
-    from toucan_b200 import capi, ops
-    from toucan_b200.scheduler import StackFrameScheduler
+    from toucan_b200 import capi, render
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,6 +202,8 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     capi.check(capi.lib().tc_set_device(local), "tc_set_device")
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -202,7 +221,7 @@ def run_ours(args, cfg):
 
     w, h = cfg["width"], cfg["height"]
     F = w * h * 16
-    # synthetic decoded stills, resident in HBM
+    # synthetic decoded stills
     ys = torch.arange(h, device=dev, dtype=torch.float32).view(h, 1)
     xs = torch.arange(w, device=dev, dtype=torch.float32).view(1, w)
     src = {}
@@ -215,25 +234,33 @@ def run_ours(args, cfg):
             a[..., 3] = torch.clamp(1.2 - 2.0 * r, 0.0, 1.0)
             src[(t, k)] = a
     del ys, xs
-    out = torch.empty((h, w, 4), dtype=torch.float32, device=dev)
-    bg = [0.0, 0.0, 0.0, 1.0]
+
+    # the reference-facing path: OTIO timeline -> toucan::ImageGraph -> OpenFX host/plug-ins -> kernels
+    doc = workloads.stack_timeline(**cfg)
+    ofx = render.Host()
+    tl = render.Timeline(json_doc=doc, directory="/synthetic")
+    for (t, k), a in src.items():
+        tl.set_media(tl.media_path(workloads.still_url(t, k)), a)  # resident in HBM
+    tl.prepare()
+    info = tl.info()
+    assert (info["width"], info["height"], info["type"]) == (w, h, capi.F32), info
+    stream = torch.cuda.Stream(dev)  # the render stream: CUDA events below are recorded on it
+    torch.cuda.set_stream(stream)
+    render.bind_stream(local, stream.cuda_stream)
 
     frames = frames_for(rank, world, cfg, args.steps + args.warmup)
-    plans = []
-    for f in frames:
-        layers = workloads.stack_layers(f, **cfg)
-        plans.append([(src[a], None if b is None else src[b], ra, rb, v) for a, b, ra, rb, v in layers])
-    nsrc = [sum(1 + (la[1] is not None) for la in p) for p in plans]
+    nsrc = [sum(1 + (la[1] is not None) for la in workloads.stack_layers(f, **cfg)) for f in frames]
+    start = info["start"]
 
-    for p in plans[:args.warmup]:
-        ops.stack_f32(w, h, bg, p, out=out)
+    for f in frames[:args.warmup]:
+        tl.render_resident(ofx, start + f)
     barrier()
     clocks = Clocks(local) if rank == 0 else None
     l0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for p in plans[args.warmup:]:
-        ops.stack_f32(w, h, bg, p, out=out)
+    for f in frames[args.warmup:]:
+        ptr, ow, oh, ot = tl.render_resident(ofx, start + f)
     e1.record()
     barrier()
     launches = capi.launch_count() - l0
@@ -243,35 +270,60 @@ def run_ours(args, cfg):
     alg_bytes = sum((n + 1) * F for n in nsrc[args.warmup:])
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms * 1e-3) / 1e9
-    checksum = float(out[::97, ::89].double().sum().item())
+    out_host = torch.empty((h, w, 4), dtype=torch.float32).pin_memory()
+    capi.check(capi.lib().tc_download(ctypes.c_void_p(out_host.data_ptr()), ctypes.c_void_p(ptr), F,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "tc_download")
+    torch.cuda.synchronize()
+    checksum = float(out_host[::97, ::89].double().sum().item())
+    del out_host
 
-    # ---- end to end: host buffers in, host buffers out, copies inside the timed region ----
+    # ---- end to end: host buffers in, host buffers out, every copy inside the timed region ----
     e2e = None
+    e2e_cached = None
     e2e_steps = int(os.environ.get("TOUCAN_BENCH_E2E_STEPS", str(min(args.steps, 24))))
+    sink = {"n": 0, "acc": 0.0}
+
+    def writer(frame, pixels):
+        sink["n"] += 1
+        sink["acc"] += float(pixels[0, 0, 0])  # the writer's read of the finished frame
+
     if e2e_steps > 0:
-        del out
-        host = {k: v.cpu().pin_memory() for k, v in src.items()}
-        del src, plans
-        torch.cuda.empty_cache()
-        sched = StackFrameScheduler(w, h, 2 * cfg["tracks"], dev, bg)
-        fr = frames_for(rank, world, cfg, e2e_steps + 2)
-        lay = [workloads.stack_layers(f, **cfg) for f in fr]
-        for _ in sched.render(lay[:2], host):
-            pass
-        sched.h2d_bytes = sched.d2h_bytes = 0
+        # (informational) the deployment shape for stills: sources cached in HBM, every frame downloaded
+        fr = frames_for(rank, world, cfg, e2e_steps)
+        tl.render_range(fr[12 % len(fr)], fr[12 % len(fr)] + 2, writer, devices=[local])
         barrier()
         t0 = time.perf_counter()
-        acc = 0.0
-        for _, frame in sched.render(lay[2:], host):
-            acc += float(frame[0, 0, 0])  # the writer's read of the finished frame
-        torch.cuda.synchronize()
+        tl.render_range(fr[0], fr[0] + e2e_steps, writer, devices=[local])
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_cached = {"value": world * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": F,
+                      "note": "informational: source stills cached in HBM (the scheduler's source cache), finished frames downloaded"}
+        sink["n"] = 0
+        tl.close()
+        host_src = {k: v.cpu().pin_memory() for k, v in src.items()}
+        src.clear()
+        torch.cuda.empty_cache()
+        capi.lib().tc_pool_trim()
+        tl2 = render.Timeline(json_doc=doc, directory="/synthetic")
+        for (t, k), a in host_src.items():
+            tl2.set_media(tl2.media_path(workloads.still_url(t, k)), a)  # pinned host: uploaded on every frame that reads it
+        tl2.prepare()
+        fr = frames_for(rank, world, cfg, e2e_steps)
+        # warm-up on two mid-transition frames (20 sources): pool growth, pinned ring, plug-in load
+        tl2.render_range(fr[12 % len(fr)], fr[12 % len(fr)] + 2, writer, devices=[local])
+        h2d = sum(sum(1 + (la[1] is not None) for la in workloads.stack_layers(f, **cfg)) for f in range(fr[0], fr[0] + e2e_steps)) * F
+        barrier()
+        t0 = time.perf_counter()
+        tl2.render_range(fr[0], fr[0] + e2e_steps, writer, devices=[local])
         dt = time.perf_counter() - t0
         barrier()
         dt = max_over_ranks(dt)
-        e2e = {"value": world * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": sched.h2d_bytes // e2e_steps,
-               "d2h_bytes_per_step": sched.d2h_bytes // e2e_steps, "steps": e2e_steps,
-               "note": "every step uploads all source frames the frame references (pinned host -> HBM), renders, and "
-                       "downloads the finished float32 frame; 3 streams, 2 buffer sets; wall clock, max over ranks"}
+        assert sink["n"] == e2e_steps + 2
+        e2e = {"value": world * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d // e2e_steps,
+               "d2h_bytes_per_step": F, "steps": e2e_steps,
+               "note": "toucan::FrameScheduler through the C API: every step uploads all source frames the frame references "
+                       "(pinned host -> HBM, as the reference re-reads its media every frame), renders, and downloads the finished "
+                       "float32 frame into a pinned ring for the ordered writer; wall clock, max over ranks"}
 
     cpu = None
     if rank == 0 and world == 1 and os.environ.get("TOUCAN_BENCH_CPU", "1") != "0":
@@ -284,6 +336,7 @@ def run_ours(args, cfg):
         line = {"metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_json(cfg, world),
+                "api": "toucan::ImageGraph::exec + IImageNode::exec through libtoucan_render.so (OpenFX host + 5 .ofx modules)",
                 "hbm_gbs_algorithmic": achieved * world,
                 "roofline": {"bound": "hbm", "kernel": "k_stack_f32", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
@@ -291,7 +344,9 @@ def run_ours(args, cfg):
                              "algorithmic_bytes_per_launch": alg_bytes / args.steps,
                              "note": "bytes = (sources referenced + 1 output) x 530,841,600 B per frame; one launch per frame; "
                                      "rank-0-equivalent (max-over-ranks time)"},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "checksum": checksum}
+                "cpu_baseline": cpu, "e2e": e2e, "e2e_sources_cached": e2e_cached, "gpu_launches": int(launches), "clocks": clk, "checksum": checksum}
+        if args.scale != 1.0:
+            line["INVALID"] = "debug run at reduced frame size (--scale)"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -300,7 +355,7 @@ def run_ours(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=96)
+    ap.add_argument("--steps", type=int, default=240)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=["c5"])

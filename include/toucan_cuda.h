@@ -45,6 +45,7 @@ typedef struct tc_image {
 } tc_image;
 
 typedef void* tc_stream; /* cudaStream_t */
+typedef void* tc_event;  /* cudaEvent_t */
 
 /* ---- runtime ---------------------------------------------------------------------- */
 const char* tc_version(void);
@@ -54,6 +55,13 @@ int tc_set_device(int device);
 int tc_stream_create(tc_stream* out);
 int tc_stream_destroy(tc_stream s);
 int tc_stream_sync(tc_stream s);
+/* events: hand a finished frame from the render stream to the download stream / the writer
+   (the frame scheduler that replaces the serial loop of bin/toucan-render/App.cpp:222-264) */
+int tc_event_create(tc_event* out);
+int tc_event_destroy(tc_event e);
+int tc_event_record(tc_event e, tc_stream s);
+int tc_event_sync(tc_event e);
+int tc_stream_wait_event(tc_stream s, tc_event e);
 size_t tc_type_size(int type);
 size_t tc_image_bytes(int w, int h, int type);
 /* result type of op(A,B) into an uninitialised destination (OIIO TypeDesc::basetype_merge) */

@@ -27,6 +27,8 @@ const char* tr_last_error(void);
 
 /* Bind the calling thread to a CUDA device (one render thread per GPU). */
 int tr_bind_device(int device);
+/* Same, rendering on a stream the caller owns (a cudaStream_t). */
+int tr_bind_stream(int device, void* stream);
 /* Wait for everything the calling thread enqueued. */
 int tr_sync(void);
 
@@ -62,6 +64,19 @@ int tr_timeline_render(tr_timeline* timeline, tr_host* host, double time_value, 
    frame, enqueued on the thread's stream (tr_sync before reading from another stream or
    the host).  The frame stays valid until the next render_resident call on this timeline. */
 int tr_timeline_render_resident(tr_timeline* timeline, tr_host* host, double time_value, void** out, int* width, int* height, int* type);
+
+/* The frame scheduler (replaces the serial loop of App.cpp:222-264): renders frames
+   [first, last) of the timeline on the given GPUs -- contiguous blocks of frames per GPU, one
+   worker thread + OpenFX host + ImageGraph per GPU, finished frames downloaded into pinned ring
+   buffers while the next frame renders -- and calls `callback` on the calling thread once per
+   frame in timeline order.  `pixels` is pinned host memory, valid during the callback. */
+typedef void (*tr_frame_callback)(void* user, int frame, const void* pixels, int width, int height, int type);
+int tr_render_range(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
+                    int frames_in_flight, tr_frame_callback callback, void* user);
+
+/* The scheduler's partition: frames [first, last) -> the contiguous block [*lo, *hi) owned by
+   worker `index` of `count` (ceil(N / G) frames per GPU). */
+void tr_frame_block(int first, int last, int index, int count, int* lo, int* hi);
 
 /* The built-in PNG reader used when no decoded frame was registered for a path (RGBA out,
    A = 1 appended to RGB, alpha associated on read like OIIO's reader).  out may be NULL to

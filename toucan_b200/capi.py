@@ -70,6 +70,11 @@ _SIGS = {
     "tc_host_alloc": [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t],
     "tc_host_free": [ctypes.c_void_p],
     "tc_type_merge": [ctypes.c_int, ctypes.c_int],
+    "tc_event_create": [ctypes.POINTER(ctypes.c_void_p)],
+    "tc_event_destroy": [ctypes.c_void_p],
+    "tc_event_record": [ctypes.c_void_p, _S],
+    "tc_event_sync": [ctypes.c_void_p],
+    "tc_stream_wait_event": [_S, ctypes.c_void_p],
     "tc_color_space_known": [ctypes.c_char_p],
 }
 

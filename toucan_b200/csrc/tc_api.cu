@@ -105,6 +105,36 @@ int tc_stream_sync(tc_stream s)
     return TC_OK;
 }
 
+int tc_event_create(tc_event* out)
+{
+    if (!out) return fail(TC_ERR_INVALID, "tc_event_create: null");
+    cudaEvent_t e;
+    TC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out = e;
+    return TC_OK;
+}
+int tc_event_destroy(tc_event e)
+{
+    if (!e) return TC_OK;
+    TC_CUDA(cudaEventDestroy((cudaEvent_t)e));
+    return TC_OK;
+}
+int tc_event_record(tc_event e, tc_stream s)
+{
+    TC_CUDA(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s));
+    return TC_OK;
+}
+int tc_event_sync(tc_event e)
+{
+    TC_CUDA(cudaEventSynchronize((cudaEvent_t)e));
+    return TC_OK;
+}
+int tc_stream_wait_event(tc_stream s, tc_event e)
+{
+    TC_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0));
+    return TC_OK;
+}
+
 size_t tc_type_size(int type)
 {
     static const size_t sz[4] = { 1, 2, 2, 4 };

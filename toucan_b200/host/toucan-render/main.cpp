@@ -1,11 +1,11 @@
-// toucan-render: render a timeline to raw frames.  Mirrors the frame loop of
-// bin/toucan-render/App.cpp:152-265 for the in-scope outputs: raw frames in the timeline's
-// working format to a file or stdout ("-").  Encoders (FFmpeg, PNG, y4m) are host-side
-// writers outside the hot path.
+// toucan-render: render a timeline to raw frames.  Mirrors bin/toucan-render/App.cpp:152-265
+// for the in-scope outputs: raw frames in the timeline's working format to a file or stdout
+// ("-").  The serial frame loop of App.cpp:222-264 is replaced by toucan::FrameScheduler:
+// frames are sharded in contiguous blocks over the GPUs and written in order.  Encoders
+// (FFmpeg, PNG, y4m) are host-side writers outside the hot path.
 //
-//   toucan-render input.otio output.raw|- [-gpu N] [-print_start] [-print_duration] [-print_rate] [-print_size]
-#include <toucanRender/ImageEffectHost.h>
-#include <toucanRender/ImageGraph.h>
+//   toucan-render input.otio output.raw|- [-gpus N] [-print_start] [-print_duration] [-print_rate] [-print_size]
+#include <toucanRender/FrameScheduler.h>
 #include <toucanRender/TimelineWrapper.h>
 #include <toucanRender/Util.h>
 
@@ -20,12 +20,12 @@ int main(int argc, char** argv)
     try
     {
         std::string input, output;
-        int gpu = 0;
+        int gpus = 1;
         bool printStart = false, printDuration = false, printRate = false, printSize = false;
         for (int i = 1; i < argc; ++i)
         {
             const std::string a = argv[i];
-            if (a == "-gpu" && i + 1 < argc) gpu = std::atoi(argv[++i]);
+            if (a == "-gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
             else if (a == "-print_start") printStart = true;
             else if (a == "-print_duration") printDuration = true;
             else if (a == "-print_rate") printRate = true;
@@ -35,7 +35,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-gpu N] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-gpus N] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 
@@ -43,38 +43,39 @@ int main(int argc, char** argv)
         auto timelineWrapper = std::make_shared<TimelineWrapper>(std::filesystem::path(input));
         const OTIO_NS::TimeRange& timeRange = timelineWrapper->getTimeRange();
         const OTIO_NS::RationalTime timeInc(1.0, timeRange.duration().rate());
-        const int frames = timeRange.duration().to_frames();
-        auto graph = std::make_shared<ImageGraph>(context, std::filesystem::path(input).parent_path(), timelineWrapper);
 
         if (printStart) { std::cout << timeRange.start_time().value() << std::endl; return 0; }
         if (printDuration) { std::cout << timeRange.duration().value() << std::endl; return 0; }
         if (printRate) { std::cout << timeRange.duration().rate() << std::endl; return 0; }
-        if (printSize) { std::cout << graph->getImageSize().x << "x" << graph->getImageSize().y << std::endl; return 0; }
+        if (printSize)
+        {
+            ImageGraph graph(context, std::filesystem::path(input).parent_path(), timelineWrapper);
+            std::cout << graph.getImageSize().x << "x" << graph.getImageSize().y << std::endl;
+            return 0;
+        }
 
-        DeviceContext::bind(gpu);
-        auto host = std::make_shared<ImageEffectHost>(context, getOpenFXPluginPaths(argv[0]));
+        // the frame loop of App.cpp:222-224: start .. end_time_inclusive in steps of 1/rate
+        int frames = 0;
+        for (OTIO_NS::RationalTime time = timeRange.start_time(); time <= timeRange.end_time_inclusive(); time += timeInc) ++frames;
 
         FILE* f = output == "-" ? stdout : fopen(output.c_str(), "wb");
         if (!f)
         {
             throw std::runtime_error("Cannot open: " + output);
         }
-        std::vector<unsigned char> pixels;
-        int n = 0;
-        for (OTIO_NS::RationalTime time = timeRange.start_time(); time <= timeRange.end_time_inclusive(); time += timeInc, ++n)
+        FrameSchedulerOptions options;
+        options.devices.clear();
+        for (int i = 0; i < std::max(1, gpus); ++i) options.devices.push_back(i);
+        options.pluginSearchPath = getOpenFXPluginPaths(argv[0]);
+        FrameScheduler scheduler(context, timelineWrapper, options);
+        scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec& spec)
         {
             if (output != "-")
             {
-                std::cout << (time - timeRange.start_time()).value() << "/" << frames << std::endl;
+                std::cout << frame << "/" << frames << std::endl;
             }
-            if (auto node = graph->exec(host, time))
-            {
-                const Image image = node->exec();
-                pixels.resize(image.spec().image_bytes());
-                image.download(pixels.data());
-                fwrite(pixels.data(), 1, pixels.size(), f);
-            }
-        }
+            fwrite(pixels, 1, spec.image_bytes(), f);
+        });
         if (f != stdout) fclose(f);
     }
     catch (const std::exception& e)

@@ -1,0 +1,265 @@
+#include "FrameScheduler.h"
+
+#include "ImageEffectHost.h"
+
+#include <condition_variable>
+#include <deque>
+#include <exception>
+#include <mutex>
+#include <thread>
+
+namespace toucan
+{
+    std::pair<int, int> frameBlock(int first, int last, int index, int count)
+    {
+        const int n = last > first ? last - first : 0;
+        const int per = count > 0 ? (n + count - 1) / count : n;
+        const int lo = std::min(first + index * per, last);
+        return { lo, std::min(lo + per, last) };
+    }
+
+    namespace
+    {
+        // Pinned staging buffers are expensive to create (cudaHostAlloc of a 531 MB 8K frame takes
+        // ~0.1 s), so slots draw from a process-wide free list that outlives a scheduler run.
+        class PinnedPool
+        {
+        public:
+            void* acquire(size_t bytes, size_t& capacity)
+            {
+                {
+                    std::lock_guard<std::mutex> lock(_mutex);
+                    for (size_t i = 0; i < _free.size(); ++i)
+                    {
+                        if (_free[i].second >= bytes)
+                        {
+                            void* p = _free[i].first;
+                            capacity = _free[i].second;
+                            _free.erase(_free.begin() + static_cast<long>(i));
+                            return p;
+                        }
+                    }
+                }
+                void* p = nullptr;
+                tcCheck(tc_host_alloc(&p, bytes), "tc_host_alloc");
+                capacity = bytes;
+                return p;
+            }
+            void release(void* p, size_t capacity)
+            {
+                if (!p) return;
+                std::lock_guard<std::mutex> lock(_mutex);
+                _free.emplace_back(p, capacity);
+            }
+
+        private:
+            std::mutex _mutex;
+            std::vector<std::pair<void*, size_t> > _free;
+        };
+        PinnedPool pinnedPool;
+
+        struct Slot
+        {
+            void* pinned = nullptr;
+            size_t capacity = 0;
+            tc_event done = nullptr;
+            Image image; // keeps the device frame alive until its download has been consumed
+            ImageSpec spec;
+            int frame = -1;
+        };
+
+        struct Worker
+        {
+            int device = 0;
+            int first = 0, last = 0;
+            std::vector<Slot> slots;
+            std::mutex mutex;
+            std::condition_variable cv;
+            std::deque<int> ready;  // slot indices, in frame order
+            std::deque<int> free_;  // slot indices the writer has released
+            std::exception_ptr error;
+            bool finished = false;
+            std::thread thread;
+        };
+    }
+
+    FrameScheduler::FrameScheduler(
+        const std::shared_ptr<ftk::Context>& context,
+        const std::shared_ptr<TimelineWrapper>& timelineWrapper,
+        const FrameSchedulerOptions& options) :
+        _context(context),
+        _timelineWrapper(timelineWrapper),
+        _options(options)
+    {
+        if (_options.devices.empty()) _options.devices = { 0 };
+        if (_options.framesInFlight < 1) _options.framesInFlight = 1;
+    }
+
+    void FrameScheduler::run(int first, int last, const Writer& writer)
+    {
+        const OTIO_NS::TimeRange& timeRange = _timelineWrapper->getTimeRange();
+        const double rate = timeRange.duration().rate();
+        const int count = static_cast<int>(_options.devices.size());
+        std::vector<std::unique_ptr<Worker> > workers;
+        for (int i = 0; i < count; ++i)
+        {
+            auto w = std::make_unique<Worker>();
+            w->device = _options.devices[static_cast<size_t>(i)];
+            const auto block = frameBlock(first, last, i, count);
+            w->first = block.first;
+            w->last = block.second;
+            w->slots.resize(static_cast<size_t>(_options.framesInFlight));
+            for (int s = 0; s < _options.framesInFlight; ++s) w->free_.push_back(s);
+            workers.push_back(std::move(w));
+        }
+
+        auto body = [this, rate, &timeRange](Worker& w)
+        {
+            tc_stream copyStream = nullptr;
+            tc_event rendered = nullptr;
+            try
+            {
+                DeviceContext::bind(w.device);
+                tcCheck(tc_stream_create(&copyStream), "tc_stream_create");
+                tcCheck(tc_event_create(&rendered), "tc_event_create");
+                for (Slot& slot : w.slots) tcCheck(tc_event_create(&slot.done), "tc_event_create");
+                std::shared_ptr<ImageEffectHost> host;
+                {
+                    // the OpenFX modules keep module-wide state while they load: one host at a time
+                    static std::mutex hostMutex;
+                    std::lock_guard<std::mutex> lock(hostMutex);
+                    host = std::make_shared<ImageEffectHost>(_context, _options.pluginSearchPath);
+                }
+                auto graph = std::make_shared<ImageGraph>(_context, _timelineWrapper->getPath().parent_path(), _timelineWrapper);
+                for (int frame = w.first; frame < w.last; ++frame)
+                {
+                    int index = -1;
+                    {
+                        std::unique_lock<std::mutex> lock(w.mutex);
+                        w.cv.wait(lock, [&w] { return !w.free_.empty(); });
+                        index = w.free_.front();
+                        w.free_.pop_front();
+                    }
+                    Slot& slot = w.slots[static_cast<size_t>(index)];
+                    slot.image = Image(); // released here, on the thread bound to the device
+                    const OTIO_NS::RationalTime time = timeRange.start_time() + OTIO_NS::RationalTime(frame, rate);
+                    if (auto node = graph->exec(host, time))
+                    {
+                        slot.image = node->exec();
+                    }
+                    slot.spec = slot.image.spec();
+                    slot.frame = frame;
+                    const size_t bytes = slot.spec.image_bytes();
+                    if (bytes > slot.capacity)
+                    {
+                        pinnedPool.release(slot.pinned, slot.capacity);
+                        slot.pinned = nullptr;
+                        slot.capacity = 0;
+                        slot.pinned = pinnedPool.acquire(bytes, slot.capacity);
+                    }
+                    if (bytes)
+                    {
+                        // download on the copy stream so the next frame's uploads and kernels overlap it
+                        tcCheck(tc_event_record(rendered, DeviceContext::stream()), "tc_event_record");
+                        tcCheck(tc_stream_wait_event(copyStream, rendered), "tc_stream_wait_event");
+                        tcCheck(tc_download(slot.pinned, slot.image.data(), bytes, copyStream), "tc_download");
+                    }
+                    tcCheck(tc_event_record(slot.done, copyStream), "tc_event_record");
+                    {
+                        std::lock_guard<std::mutex> lock(w.mutex);
+                        w.ready.push_back(index);
+                    }
+                    w.cv.notify_all();
+                }
+                // drain: every handed-out slot comes back before the device objects go away
+                {
+                    std::unique_lock<std::mutex> lock(w.mutex);
+                    w.cv.wait(lock, [&w] { return w.free_.size() == w.slots.size(); });
+                }
+                DeviceContext::synchronize();
+            }
+            catch (...)
+            {
+                std::lock_guard<std::mutex> lock(w.mutex);
+                w.error = std::current_exception();
+            }
+            for (Slot& slot : w.slots)
+            {
+                slot.image = Image();
+                pinnedPool.release(slot.pinned, slot.capacity);
+                if (slot.done) tc_event_destroy(slot.done);
+                slot.pinned = nullptr;
+                slot.done = nullptr;
+            }
+            if (rendered) tc_event_destroy(rendered);
+            if (copyStream) tc_stream_destroy(copyStream);
+            {
+                std::lock_guard<std::mutex> lock(w.mutex);
+                w.finished = true;
+            }
+            w.cv.notify_all();
+        };
+
+        for (auto& w : workers)
+        {
+            Worker* wp = w.get();
+            wp->thread = std::thread([body, wp] { body(*wp); });
+        }
+
+        // The writer: frames in order, each from the worker that owns its block.
+        std::exception_ptr error;
+        for (auto& w : workers)
+        {
+            for (int frame = w->first; frame < w->last && !error; ++frame)
+            {
+                int index = -1;
+                {
+                    std::unique_lock<std::mutex> lock(w->mutex);
+                    w->cv.wait(lock, [&w] { return !w->ready.empty() || w->error || w->finished; });
+                    if (w->error) { error = w->error; break; }
+                    if (w->ready.empty()) { error = std::make_exception_ptr(std::runtime_error("frame scheduler: worker ended early")); break; }
+                    index = w->ready.front();
+                    w->ready.pop_front();
+                }
+                Slot& slot = w->slots[static_cast<size_t>(index)];
+                try
+                {
+                    tcCheck(tc_event_sync(slot.done), "tc_event_sync");
+                    writer(slot.frame, slot.pinned, slot.spec);
+                }
+                catch (...)
+                {
+                    error = std::current_exception();
+                }
+                {
+                    std::lock_guard<std::mutex> lock(w->mutex);
+                    w->free_.push_back(index);
+                }
+                w->cv.notify_all();
+            }
+        }
+        if (error)
+        {
+            // unblock workers waiting for a slot: release everything they may have queued
+            for (auto& w : workers)
+            {
+                std::unique_lock<std::mutex> lock(w->mutex);
+                while (!w->finished)
+                {
+                    while (!w->ready.empty()) { w->free_.push_back(w->ready.front()); w->ready.pop_front(); }
+                    w->cv.notify_all();
+                    w->cv.wait_for(lock, std::chrono::milliseconds(10));
+                }
+            }
+        }
+        for (auto& w : workers)
+        {
+            if (w->thread.joinable()) w->thread.join();
+            if (!error && w->error) error = w->error;
+        }
+        if (error)
+        {
+            std::rethrow_exception(error);
+        }
+    }
+}

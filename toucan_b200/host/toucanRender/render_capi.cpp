@@ -2,6 +2,7 @@
 #include <toucan_render.h>
 
 #include "ImageEffectHost.h"
+#include "FrameScheduler.h"
 #include "ImageGraph.h"
 #include "PngRead.h"
 #include "StackFusion.h"
@@ -103,6 +104,11 @@ extern "C"
     int tr_bind_device(int device)
     {
         return guarded([&] { DeviceContext::bind(device); return 0; });
+    }
+
+    int tr_bind_stream(int device, void* stream)
+    {
+        return guarded([&] { DeviceContext::bind(device, stream); return 0; });
     }
 
     int tr_sync(void)
@@ -272,6 +278,33 @@ extern "C"
             if (type) *type = spec.format;
             return 0;
         });
+    }
+
+    int tr_render_range(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
+                        int frames_in_flight, tr_frame_callback callback, void* user)
+    {
+        if (!timeline || !callback) return fail("tr_render_range: null");
+        return guarded([&] {
+            FrameSchedulerOptions options;
+            options.devices.clear();
+            for (int i = 0; i < n_devices; ++i) options.devices.push_back(devices ? devices[i] : i);
+            if (options.devices.empty()) options.devices.push_back(0);
+            if (plugin_dir && *plugin_dir) options.pluginSearchPath.push_back(plugin_dir);
+            else options.pluginSearchPath = getOpenFXPluginPaths(libraryDirectory() / "toucan-render");
+            if (frames_in_flight > 0) options.framesInFlight = frames_in_flight;
+            FrameScheduler scheduler(timeline->context, timeline->wrapper, options);
+            scheduler.run(first, last, [&](int frame, const void* pixels, const ImageSpec& spec) {
+                callback(user, frame, pixels, spec.width, spec.height, spec.format);
+            });
+            return 0;
+        });
+    }
+
+    void tr_frame_block(int first, int last, int index, int count, int* lo, int* hi)
+    {
+        const auto block = frameBlock(first, last, index, count);
+        if (lo) *lo = block.first;
+        if (hi) *hi = block.second;
     }
 
     int tr_decode_png(const char* path, void* out, size_t capacity, int* width, int* height, int* type)

@@ -27,6 +27,7 @@ _DP = ctypes.POINTER(ctypes.c_double)
 _SIGS = {
     "tr_bind_device": [ctypes.c_int],
     "tr_sync": [],
+    "tr_bind_stream": [ctypes.c_int, _VP],
     "tr_host_create": [ctypes.c_char_p, ctypes.POINTER(_VP)],
     "tr_host_plugin_count": [_VP],
     "tr_timeline_open": [ctypes.c_char_p, ctypes.POINTER(_VP)],
@@ -40,7 +41,9 @@ _SIGS = {
     "tr_decode_png": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_timeline_render_resident": [_VP, _VP, ctypes.c_double, ctypes.POINTER(_VP), _IP, _IP, _IP],
 }
-EXPORTS = sorted(set(_SIGS) | {"tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion"})
+FRAME_CALLBACK = ctypes.CFUNCTYPE(None, _VP, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int)
+_SIGS["tr_render_range"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, FRAME_CALLBACK, _VP]
+EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion"})
 
 
 def lib() -> ctypes.CDLL:
@@ -75,12 +78,27 @@ def bind_device(device: int = 0):
     _check(lib().tr_bind_device(device), "tr_bind_device")
 
 
+def bind_stream(device: int, stream_ptr: int):
+    """Render on a stream the caller owns (e.g. torch's current stream, for CUDA-event timing)."""
+    _check(lib().tr_bind_stream(device, _VP(stream_ptr)), "tr_bind_stream")
+
+
 def sync():
     _check(lib().tr_sync(), "tr_sync")
 
 
 def set_fusion(enabled: bool):
     lib().tr_set_fusion(1 if enabled else 0)
+
+
+def frame_block(first: int, last: int, index: int, count: int):
+    """toucan::frameBlock -- the scheduler's contiguous block of frames for worker `index` of `count`."""
+    lo, hi = ctypes.c_int(), ctypes.c_int()
+    f = lib().tr_frame_block
+    f.argtypes = [ctypes.c_int] * 4 + [_IP, _IP]
+    f.restype = None
+    f(first, last, index, count, ctypes.byref(lo), ctypes.byref(hi))
+    return lo.value, hi.value
 
 
 def decode_png(path: str) -> np.ndarray:
@@ -185,6 +203,22 @@ class Timeline:
         _check(lib().tr_timeline_render_resident(self._t, host._h, float(time_value), ctypes.byref(p), ctypes.byref(w), ctypes.byref(h),
                                                  ctypes.byref(t)), "tr_timeline_render_resident")
         return p.value, w.value, h.value, t.value
+
+    def render_range(self, first: int, last: int, writer, devices=(0,), frames_in_flight: int = 2, plugin_dir: str = PLUGIN_DIR):
+        """toucan::FrameScheduler: frames [first, last) on `devices`, writer(frame, ndarray) called in
+        order on this thread; the array aliases pinned memory valid only during the call."""
+        def cb(_user, frame, pixels, w, h, t):
+            if w > 0 and h > 0 and pixels:
+                dt = np.dtype(_NP_OF[t])
+                buf = (ctypes.c_char * (w * h * 4 * dt.itemsize)).from_address(pixels)
+                writer(frame, np.frombuffer(buf, dtype=dt).reshape(h, w, 4))
+            else:
+                writer(frame, np.zeros((0, 0, 4), np.uint8))
+
+        c_cb = FRAME_CALLBACK(cb)
+        devs = (ctypes.c_int * len(devices))(*devices)
+        _check(lib().tr_render_range(self._t, plugin_dir.encode(), devs, len(devices), int(first), int(last), int(frames_in_flight), c_cb,
+                                     None), "tr_render_range")
 
     def close(self):
         if self._t:
