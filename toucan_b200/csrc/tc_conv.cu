@@ -9,7 +9,7 @@
 #include <cstring>
 #include <vector>
 
-#include "tc_common.cuh"
+#include "tc_tile.cuh"
 
 namespace tc {
 
@@ -31,9 +31,85 @@ __device__ __forceinline__ float4 fma4(float w, float4 p, float4 a)
     return make_float4(fmaf(w, p.x, a.x), fmaf(w, p.y, a.y), fmaf(w, p.z, a.z), fmaf(w, p.w, a.w));
 }
 
-// Generic tile kernel: any storage type in/out.
+// Diff = src - Blurry; threshold; *contrast; dst = src + Diff  (OIIO unsharp_mask)
+__device__ __forceinline__ float4 unsharp_px(float4 sp, float4 o, float contrast, float threshold)
+{
+    float d[4] = { sp.x - o.x, sp.y - o.y, sp.z - o.z, sp.w - o.w };
+    const float s4[4] = { sp.x, sp.y, sp.z, sp.w };
+    float r[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float dd = d[c];
+        if (threshold > 0.0f && fabsf(dd) < threshold) dd = 0.0f;
+        dd = __fmul_rn(dd, contrast);
+        r[c] = __fadd_rn(s4[c], dd);
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// Register-blocked tile kernel (tc_tile.cuh), any storage type in/out, R <= 12.
+// One CTA per 64 x 24 output tile: stage (typed load -> float, clamped) -> rows -> columns ->
+// [unsharp epilogue] -> typed store.  P.g carries sqrt(scale).
+template <int R, bool UNSHARP, int OCC>
+__global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tile(const Img src, const Img dst, const __grid_constant__ ConvParams P)
+{
+    constexpr int TH = 24;
+    using T = StTile<R, TH, 1>;
+    extern __shared__ float4 smem[];
+    float4* in = smem;
+    float4* mid = smem + T::IN_ELEMS;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * TH;
+
+    if (tid < T::STAGE_ROWS * T::IW) {
+        const int ry = tid / T::IW, ix = tid - ry * T::IW;
+        const int sx = min(max(x0 - R + ix, 0), src.w - 1);
+        constexpr int BATCH = 6;
+#pragma unroll
+        for (int u0 = 0; u0 < T::STAGE_N; u0 += BATCH) {
+            float4 v[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int iy = ry + (u0 + u) * T::STAGE_ROWS;
+                if (u0 + u < T::STAGE_N && iy < T::IH)
+                    v[u] = load_px(src.p, src.type, (size_t)min(max(y0 - R + iy, 0), src.h - 1) * src.w + sx);
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int iy = ry + (u0 + u) * T::STAGE_ROWS;
+                if (u0 + u < T::STAGE_N && iy < T::IH) in[iy * T::IWP + ix] = v[u];
+            }
+        }
+    }
+    float g[2 * R + 1];
+#pragma unroll
+    for (int t = 0; t <= 2 * R; ++t) {
+        const int s = t - R + P.R;
+        g[t] = (s >= 0 && s <= 2 * P.R) ? P.g[s] : 0.0f;
+    }
+    __syncthreads();
+    tile_rows<R, TH, true>(in, mid, g);
+    __syncthreads();
+    float4 f[T::PX];
+    tile_cols<R, TH>(mid, g, f);
+
+    const int col = tid % ST_TW, seg = tid / ST_TW;
+    const int x = x0 + col, y = y0 + seg * T::PX;
+    if (x < dst.w) {
+#pragma unroll
+        for (int k = 0; k < T::PX; ++k) {
+            if (y + k < dst.h) {
+                float4 o = f[k];
+                if (UNSHARP) o = unsharp_px(load_black(src, x, y + k), o, P.contrast, P.threshold);
+                store_px(dst.p, dst.type, (size_t)(y + k) * dst.w + x, o);
+            }
+        }
+    }
+}
+
+// Generic fallback for very wide kernels (R > 12): 32 x 32 tiles, one tap per shared-memory read.
 template <bool UNSHARP>
-__global__ void __launch_bounds__(CONV_THREADS) k_gauss_tile(const Img src, const Img dst, const __grid_constant__ ConvParams P)
+__global__ void __launch_bounds__(CONV_THREADS) k_gauss_wide(const Img src, const Img dst, const __grid_constant__ ConvParams P)
 {
     extern __shared__ float4 smem[];
     const int R = P.R;
@@ -47,7 +123,6 @@ __global__ void __launch_bounds__(CONV_THREADS) k_gauss_tile(const Img src, cons
         in[i] = load_clamp(src, x0 - R + ix, y0 - R + iy);
     }
     __syncthreads();
-    // horizontal pass
     for (int i = threadIdx.x; i < IH * CONV_TW; i += CONV_THREADS) {
         const int row = i / CONV_TW, col = i - row * CONV_TW;
         const float4* p = in + row * IW + col;
@@ -56,30 +131,14 @@ __global__ void __launch_bounds__(CONV_THREADS) k_gauss_tile(const Img src, cons
         mid[i] = acc;
     }
     __syncthreads();
-    // vertical pass + epilogue
     for (int i = threadIdx.x; i < CONV_TH * CONV_TW; i += CONV_THREADS) {
         const int row = i / CONV_TW, col = i - row * CONV_TW;
         const int x = x0 + col, y = y0 + row;
         if (x >= dst.w || y >= dst.h) continue;
         const float4* p = mid + row * CONV_TW + col;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = 0; t <= 2 * R; ++t) acc = fma4(P.g[t], p[t * CONV_TW], acc);
-        float4 o = make_float4(acc.x * P.scale, acc.y * P.scale, acc.z * P.scale, acc.w * P.scale);
-        if (UNSHARP) {
-            // Diff = src - Blurry; threshold; *contrast; dst = src + Diff  (OIIO unsharp_mask)
-            const float4 sp = load_black(src, x, y);
-            float d[4] = { sp.x - o.x, sp.y - o.y, sp.z - o.z, sp.w - o.w };
-            const float s4[4] = { sp.x, sp.y, sp.z, sp.w };
-            float r[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float dd = d[c];
-                if (P.threshold > 0.0f && fabsf(dd) < P.threshold) dd = 0.0f;
-                dd = __fmul_rn(dd, P.contrast);
-                r[c] = __fadd_rn(s4[c], dd);
-            }
-            o = make_float4(r[0], r[1], r[2], r[3]);
-        }
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t <= 2 * R; ++t) o = fma4(P.g[t], p[t * CONV_TW], o);
+        if (UNSHARP) o = unsharp_px(load_black(src, x, y), o, P.contrast, P.threshold);
         store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
     }
 }
@@ -141,25 +200,55 @@ static int build_params(float width, ConvParams* P)
         return fail(TC_ERR_UNSUPPORTED, "gaussian kernel of width %g needs %d taps per side (max %d)", width, live, CONV_MAX_R);
     P->R = live;
     P->scale = (1.0f / ksum) / sum;
+    // each 1-D pass carries sqrt(scale): the two passes multiply out to the normalised 2-D kernel
+    const float root = sqrtf(P->scale);
     memset(P->g, 0, sizeof(P->g));
-    for (int i = -live; i <= live; ++i) P->g[i + live] = g[r + i];
+    for (int i = -live; i <= live; ++i) P->g[i + live] = g[r + i] * root;
     return TC_OK;
+}
+
+template <int R, bool UNSHARP>
+static int launch_tile(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
+{
+    using T = StTile<R, 24, 1>;
+    constexpr int OCC = T::SMEM <= 74 * 1024 ? 3 : (T::SMEM <= 112 * 1024 ? 2 : 1);
+    static bool configured = false;
+    if (!configured) {
+        TC_CUDA(cudaFuncSetAttribute(k_gauss_tile<R, UNSHARP, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+        TC_CUDA(cudaFuncSetAttribute(k_gauss_tile<R, UNSHARP, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
+    dim3 grid((dst->w + ST_TW - 1) / ST_TW, (dst->h + 23) / 24);
+    k_gauss_tile<R, UNSHARP, OCC><<<grid, ST_THREADS, T::SMEM, st>>>(view(src), view(dst), P);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_gauss_tile launch");
+}
+
+template <bool UNSHARP>
+static int launch_conv_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
+{
+    if (P.R <= 2) return launch_tile<2, UNSHARP>(dst, src, P, st);
+    if (P.R <= 4) return launch_tile<4, UNSHARP>(dst, src, P, st);
+    if (P.R <= 6) return launch_tile<6, UNSHARP>(dst, src, P, st);
+    if (P.R <= 9) return launch_tile<9, UNSHARP>(dst, src, P, st);
+    if (P.R <= 12) return launch_tile<12, UNSHARP>(dst, src, P, st);
+    const int IW = CONV_TW + 2 * P.R, IH = CONV_TH + 2 * P.R;
+    const size_t smem = (size_t)(IH * IW + IH * CONV_TW) * sizeof(float4);
+    static size_t configured = 0;
+    if (smem > configured) {
+        TC_CUDA(cudaFuncSetAttribute(k_gauss_wide<UNSHARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((dst->w + CONV_TW - 1) / CONV_TW, (dst->h + CONV_TH - 1) / CONV_TH);
+    k_gauss_wide<UNSHARP><<<grid, CONV_THREADS, smem, st>>>(view(src), view(dst), P);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_gauss_wide launch");
 }
 
 static int launch_conv(const tc_image* dst, const tc_image* src, const ConvParams& P, bool unsharp, tc_stream s)
 {
-    const int IW = CONV_TW + 2 * P.R, IH = CONV_TH + 2 * P.R;
-    const size_t smem = (size_t)(IH * IW + IH * CONV_TW) * sizeof(float4);
-    dim3 grid((dst->w + CONV_TW - 1) / CONV_TW, (dst->h + CONV_TH - 1) / CONV_TH);
-    auto kern = unsharp ? k_gauss_tile<true> : k_gauss_tile<false>;
-    static size_t configured[2] = { 0, 0 };
-    if (smem > configured[unsharp]) {
-        TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[unsharp] = smem;
-    }
-    kern<<<grid, CONV_THREADS, smem, (cudaStream_t)s>>>(view(src), view(dst), P);
-    count_launch();
-    return check_cuda(cudaGetLastError(), "k_gauss_tile launch");
+    return unsharp ? launch_conv_t<true>(dst, src, P, (cudaStream_t)s) : launch_conv_t<false>(dst, src, P, (cudaStream_t)s);
 }
 
 } // namespace tc

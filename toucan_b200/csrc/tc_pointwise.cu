@@ -8,36 +8,98 @@
 // load/store for float, 64-bit for half/u16, 32-bit for u8), 4 independent pixels in
 // flight per thread, grid sized as a multiple of the SM count.
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "tc_common.cuh"
 
 namespace tc {
 
 constexpr int PW_THREADS = 256;
-constexpr int PW_UNROLL = 4;
+constexpr int PW_PIXELS = 4; // pixels per thread-iteration
 
-template <class Op>
+// VEC pixels per 128-bit access: 1 (float), 2 (half / u16), 4 (u8).  Every thread-iteration moves
+// PW_PIXELS / VEC independent 16-byte groups, so small storage types get the same bytes in flight as float.
+template <int VEC>
+__device__ __forceinline__ void store_vec(void* __restrict__ base, int type, unsigned idx0, const float4 (&v)[VEC])
+{
+    if (VEC == 1) {
+        store_px(base, type, idx0, v[0]);
+    } else if (VEC == 4) {
+        uint4 o;
+        unsigned* w = &o.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            w[j] = f_to_u8(v[j].x) | (f_to_u8(v[j].y) << 8) | (f_to_u8(v[j].z) << 16) | (f_to_u8(v[j].w) << 24);
+        reinterpret_cast<uint4*>(base)[idx0 >> 2] = o;
+    } else {
+        uint4 o;
+        unsigned* w = &o.x;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (type == TC_U16) {
+                w[2 * j] = f_to_u16(v[j].x) | (f_to_u16(v[j].y) << 16);
+                w[2 * j + 1] = f_to_u16(v[j].z) | (f_to_u16(v[j].w) << 16);
+            } else {
+                __half2 a = __floats2half2_rn(v[j].x, v[j].y), b = __floats2half2_rn(v[j].z, v[j].w);
+                w[2 * j] = *reinterpret_cast<unsigned*>(&a);
+                w[2 * j + 1] = *reinterpret_cast<unsigned*>(&b);
+            }
+        }
+        reinterpret_cast<uint4*>(base)[idx0 >> 1] = o;
+    }
+}
+
+template <class Op, int VEC>
 __global__ void __launch_bounds__(PW_THREADS) k_pointwise(const __grid_constant__ Op op, const Img dst)
 {
-    const unsigned total = (unsigned)dst.w * (unsigned)dst.h;
+    constexpr int PW_UNROLL = PW_PIXELS / VEC; // independent 128-bit groups per thread-iteration
+    const unsigned groups = ((unsigned)dst.w * (unsigned)dst.h) / VEC;
     const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < total; base += PW_UNROLL * stride) {
-        float4 v[PW_UNROLL];
+    for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < groups; base += PW_UNROLL * stride) {
+        float4 v[PW_UNROLL][VEC];
+        typename Op::template Cache<VEC> cache[PW_UNROLL];
 #pragma unroll
         for (int k = 0; k < PW_UNROLL; ++k) {
-            const unsigned idx = base + k * stride;
-            if (idx < total) {
-                const int y = idx / (unsigned)dst.w;
-                const int x = idx - y * (unsigned)dst.w;
-                v[k] = op(x, y, idx);
+            const unsigned g = base + k * stride;
+            if (g < groups) op.template preload<VEC>(cache[k], g * VEC);
+        }
+#pragma unroll
+        for (int k = 0; k < PW_UNROLL; ++k) {
+            const unsigned g = base + k * stride;
+            if (g < groups) {
+                const unsigned idx0 = g * VEC;
+                int y = idx0 / (unsigned)dst.w;
+                int x = idx0 - y * (unsigned)dst.w;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    v[k][j] = op.template eval<VEC>(cache[k], x, y, idx0 + j, j);
+                    if (++x == dst.w) {
+                        x = 0;
+                        ++y;
+                    }
+                }
             }
         }
 #pragma unroll
         for (int k = 0; k < PW_UNROLL; ++k) {
-            const unsigned idx = base + k * stride;
-            if (idx < total) store_px(dst.p, dst.type, idx, v[k]);
+            const unsigned g = base + k * stride;
+            if (g < groups) store_vec<VEC>(dst.p, dst.type, g * VEC, v[k]);
         }
     }
+}
+
+template <class Op, int VEC>
+static int launch_vec(const Op& op, const tc_image* dst, tc_stream s)
+{
+    const size_t groups = (size_t)dst->w * dst->h / VEC;
+    const size_t per_block = (size_t)PW_THREADS * (PW_PIXELS / VEC);
+    size_t blocks = (groups + per_block - 1) / per_block;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    k_pointwise<Op, VEC><<<(unsigned)blocks, PW_THREADS, 0, (cudaStream_t)s>>>(op, view(dst));
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_pointwise launch");
 }
 
 template <class Op>
@@ -45,28 +107,65 @@ static int launch(const Op& op, const tc_image* dst, tc_stream s)
 {
     const size_t total = (size_t)dst->w * dst->h;
     if (total >= (1ull << 31)) return fail(TC_ERR_UNSUPPORTED, "image too large (%d x %d)", dst->w, dst->h);
-    const size_t per_block = (size_t)PW_THREADS * PW_UNROLL;
-    size_t blocks = (total + per_block - 1) / per_block;
-    const size_t cap = (size_t)num_sms() * 16;
-    if (blocks > cap) blocks = cap;
-    k_pointwise<Op><<<(unsigned)blocks, PW_THREADS, 0, (cudaStream_t)s>>>(op, view(dst));
-    count_launch();
-    return check_cuda(cudaGetLastError(), "k_pointwise launch");
+    // 128-bit groups need every same-sized source in the destination's storage type
+    const int vec = dst->type == TC_F32 ? 1 : (dst->type == TC_U8 ? 4 : 2);
+    if (vec > 1 && total % vec == 0 && op.vec_ok(dst->type)) {
+        if (vec == 4) return launch_vec<Op, 4>(op, dst, s);
+        return launch_vec<Op, 2>(op, dst, s);
+    }
+    return launch_vec<Op, 1>(op, dst, s);
 }
 
 // A source image read at the destination's pixel position (0 outside).
 struct Src {
     Img im;
     int same; // same dimensions as the destination -> linear index can be reused
-    __device__ __forceinline__ float4 at(int x, int y, unsigned idx) const
+    bool vec_ok(int t) const { return !same || im.type == t; }
+    template <int VEC>
+    __device__ __forceinline__ void preload(uint4& c, unsigned idx0) const
     {
-        return same ? load_px(im.p, im.type, idx) : load_black(im, x, y);
+        if (VEC > 1 && same) c = __ldg(reinterpret_cast<const uint4*>(im.p) + idx0 / VEC);
+    }
+    template <int VEC>
+    __device__ __forceinline__ float4 at(const uint4& c, int x, int y, unsigned idx, int j) const
+    {
+        if (VEC == 1) return same ? load_px(im.p, im.type, idx) : load_black(im, x, y);
+        if (!same) return load_black(im, x, y);
+        const unsigned* w = &c.x;
+        if (VEC == 4) {
+            const unsigned v = w[j];
+            return make_float4(u8_to_f(v & 0xffu), u8_to_f((v >> 8) & 0xffu), u8_to_f((v >> 16) & 0xffu), u8_to_f(v >> 24));
+        }
+        const unsigned lo = w[2 * j], hi = w[2 * j + 1];
+        if (im.type == TC_U16) return make_float4(u16_to_f(lo & 0xffffu), u16_to_f(lo >> 16), u16_to_f(hi & 0xffffu), u16_to_f(hi >> 16));
+        const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&lo)), fb = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
     }
 };
 static Src make_src(const tc_image* src, const tc_image* dst)
 {
     return Src { view(src), (src->w == dst->w && src->h == dst->h) ? 1 : 0 };
 }
+
+// Boilerplate of an op: N same-position sources (0, 1 or 2) cached as one 128-bit word each.
+struct NoCache {};
+#define TC_OP_0()                                                                             \
+    template <int VEC> using Cache = NoCache;                                                 \
+    bool vec_ok(int) const { return true; }                                                   \
+    template <int VEC> __device__ __forceinline__ void preload(NoCache&, unsigned) const {}   \
+    template <int VEC> __device__ __forceinline__ float4 eval(const NoCache&, int x, int y, unsigned i, int) const { return (*this)(x, y, i); }
+struct Cache1 { uint4 a; };
+struct Cache2 { uint4 a, b; };
+#define TC_OP_1(S)                                                                                      \
+    template <int VEC> using Cache = Cache1;                                                            \
+    bool vec_ok(int t) const { return S.vec_ok(t); }                                                    \
+    template <int VEC> __device__ __forceinline__ void preload(Cache1& c, unsigned i0) const { S.template preload<VEC>(c.a, i0); } \
+    template <int VEC> __device__ __forceinline__ float4 eval(const Cache1& c, int x, int y, unsigned i, int j) const { return apply(S.template at<VEC>(c.a, x, y, i, j)); }
+#define TC_OP_2(SA, SB)                                                                                 \
+    template <int VEC> using Cache = Cache2;                                                            \
+    bool vec_ok(int t) const { return SA.vec_ok(t) && SB.vec_ok(t); }                                   \
+    template <int VEC> __device__ __forceinline__ void preload(Cache2& c, unsigned i0) const { SA.template preload<VEC>(c.a, i0); SB.template preload<VEC>(c.b, i0); } \
+    template <int VEC> __device__ __forceinline__ float4 eval(const Cache2& c, int x, int y, unsigned i, int j) const { return apply(SA.template at<VEC>(c.a, x, y, i, j), SB.template at<VEC>(c.b, x, y, i, j), x, y); }
 
 __device__ __forceinline__ float lerp_oiio(float a, float b, float x)
 {
@@ -80,15 +179,18 @@ __device__ __forceinline__ float luma709(float4 p)
 
 // ---- generators ------------------------------------------------------------------------
 struct FillOp {
+    TC_OP_0()
     float4 c;
     __device__ float4 operator()(int, int, unsigned) const { return c; }
 };
 struct CheckerOp {
+    TC_OP_0()
     float4 c1, c2;
     int cw, ch;
     __device__ float4 operator()(int x, int y, unsigned) const { return ((x / cw + y / ch) & 1) ? c2 : c1; }
 };
 struct GradientOp {
+    TC_OP_0()
     float4 c1, c2;
     float denom;
     int vertical;
@@ -179,6 +281,7 @@ __device__ float hashnormal(uint32_t xy, int c, int seed)
     return __fmul_rn(xr, M);
 }
 struct NoiseOp {
+    TC_OP_0()
     float A, B;
     int type, mono, seed;
     __device__ float4 operator()(int x, int y, unsigned) const
@@ -206,9 +309,9 @@ struct NoiseOp {
 // ---- pointwise filters -----------------------------------------------------------------
 struct InvertOp {
     Src s;
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const
     {
-        float4 p = s.at(x, y, i);
         p.x = __fadd_rn(__fmul_rn(p.x, -1.0f), 1.0f);
         p.y = __fadd_rn(__fmul_rn(p.y, -1.0f), 1.0f);
         p.z = __fadd_rn(__fmul_rn(p.z, -1.0f), 1.0f);
@@ -218,18 +321,21 @@ struct InvertOp {
 struct PowOp {
     Src s;
     float v;
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const
     {
-        float4 p = s.at(x, y, i);
+        // small integer exponents (the fixtures use 2 and 3) as products: within 1 ulp of powf
+        if (v == 2.0f) return make_float4(p.x * p.x, p.y * p.y, p.z * p.z, p.w * p.w);
+        if (v == 3.0f) return make_float4(p.x * p.x * p.x, p.y * p.y * p.y, p.z * p.z * p.z, p.w * p.w * p.w);
         return make_float4(powf(p.x, v), powf(p.y, v), powf(p.z, v), powf(p.w, v));
     }
 };
 struct SaturateOp {
     Src s;
     float v;
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const
     {
-        float4 p = s.at(x, y, i);
         const float l = luma709(p);
         p.x = lerp_oiio(l, p.x, v);
         p.y = lerp_oiio(l, p.y, v);
@@ -239,11 +345,12 @@ struct SaturateOp {
 };
 struct ColorMapOp {
     Src s;
-    int n; // knots (0 = unknown map: RGB stays zero, alpha copied)
-    float k[17 * 3];
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    int n;          // knots (0 = unknown map: RGB stays zero, alpha copied)
+    const float* k; // n x RGB knots in device memory: neighbouring pixels look up different segments,
+                    // which a constant-bank operand would serialise; L1-cached global loads do not
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(const float4 p) const
     {
-        const float4 p = s.at(x, y, i);
         float4 o = make_float4(0.f, 0.f, 0.f, p.w);
         if (n) {
             float t = fminf(fmaxf(luma709(p), 0.0f), 1.0f);
@@ -253,18 +360,18 @@ struct ColorMapOp {
             const int seg = (int)fl;
             const float fr = __fsub_rn(xs, fl);
             const int nxt = min(seg + 1, nsegs);
-            o.x = lerp_oiio(k[seg * 3 + 0], k[nxt * 3 + 0], fr);
-            o.y = lerp_oiio(k[seg * 3 + 1], k[nxt * 3 + 1], fr);
-            o.z = lerp_oiio(k[seg * 3 + 2], k[nxt * 3 + 2], fr);
+            o.x = lerp_oiio(__ldg(k + seg * 3 + 0), __ldg(k + nxt * 3 + 0), fr);
+            o.y = lerp_oiio(__ldg(k + seg * 3 + 1), __ldg(k + nxt * 3 + 1), fr);
+            o.z = lerp_oiio(__ldg(k + seg * 3 + 2), __ldg(k + nxt * 3 + 2), fr);
         }
         return o;
     }
 };
 struct PremultOp {
     Src s;
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const
     {
-        float4 p = s.at(x, y, i);
         if (p.w != 1.0f) {
             p.x = __fmul_rn(p.x, p.w);
             p.y = __fmul_rn(p.y, p.w);
@@ -275,9 +382,9 @@ struct PremultOp {
 };
 struct UnpremultOp {
     Src s;
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const
     {
-        float4 p = s.at(x, y, i);
         if (p.w != 0.0f && p.w != 1.0f) {
             p.x = __fdiv_rn(p.x, p.w);
             p.y = __fdiv_rn(p.y, p.w);
@@ -321,9 +428,9 @@ struct ColorConvertOp {
     int curve_in, curve_out;
     float p_in, p_out;
     float m[9];
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(const float4 p) const
     {
-        const float4 p = s.at(x, y, i);
         const float l0 = cc_curve(curve_in, 0, p_in, p.x), l1 = cc_curve(curve_in, 0, p_in, p.y),
                     l2 = cc_curve(curve_in, 0, p_in, p.z);
         float o[3];
@@ -339,6 +446,7 @@ struct ColorConvertOp {
 
 // ---- address-only transforms ---------------------------------------------------------
 struct CropOp {
+    TC_OP_0()
     Img src;
     int px, py, cw, ch;
     __device__ float4 operator()(int x, int y, unsigned) const
@@ -348,18 +456,22 @@ struct CropOp {
     }
 };
 struct FlipOp {
+    TC_OP_0()
     Img src;
     __device__ float4 operator()(int x, int y, unsigned) const { return load_black(src, x, src.h - 1 - y); }
 };
 struct FlopOp {
+    TC_OP_0()
     Img src;
     __device__ float4 operator()(int x, int y, unsigned) const { return load_black(src, src.w - 1 - x, y); }
 };
 struct ConvertOp {
     Src s;
-    __device__ float4 operator()(int x, int y, unsigned i) const { return s.at(x, y, i); }
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const { return p; }
 };
 struct PasteOp {
+    TC_OP_0()
     Img src;
     int ox, oy;
     __device__ float4 operator()(int x, int y, unsigned) const { return load_black(src, x - ox, y - oy); }
@@ -369,9 +481,9 @@ struct PasteOp {
 struct DissolveOp {
     Src a, b;
     float qiv, qv; // the fill constants, already quantised to each source's storage type
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_2(a, b)
+    __device__ __forceinline__ float4 apply(const float4 p, const float4 q, int, int) const
     {
-        const float4 p = a.at(x, y, i), q = b.at(x, y, i);
         const int ta = a.im.type, tb = b.im.type;
         return make_float4(__fadd_rn(quant(__fmul_rn(p.x, qiv), ta), quant(__fmul_rn(q.x, qv), tb)),
                            __fadd_rn(quant(__fmul_rn(p.y, qiv), ta), quant(__fmul_rn(q.y, qv), tb)),
@@ -383,7 +495,8 @@ struct WipeOp {
     Src a, b;
     int mw, mh; // matte size (= `from` size)
     int edge, vertical;
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_2(a, b)
+    __device__ __forceinline__ float4 apply(const float4 p, const float4 q, int x, int y) const
     {
         float mf = 0.f, mt = 0.f;
         if (x < mw && y < mh) {
@@ -400,7 +513,6 @@ struct WipeOp {
                 mt = 0.f;
             }
         }
-        const float4 p = a.at(x, y, i), q = b.at(x, y, i);
         const int ta = a.im.type, tb = b.im.type;
         return make_float4(__fadd_rn(quant(__fmul_rn(p.x, mf), ta), quant(__fmul_rn(q.x, mt), tb)),
                            __fadd_rn(quant(__fmul_rn(p.y, mf), ta), quant(__fmul_rn(q.y, mt), tb)),
@@ -413,10 +525,9 @@ struct WipeOp {
 struct OverOp {
     Src fg, bg;
     int premult;
-    __device__ float4 operator()(int x, int y, unsigned i) const
+    TC_OP_2(fg, bg)
+    __device__ __forceinline__ float4 apply(float4 a, const float4 b, int, int) const
     {
-        float4 a = fg.at(x, y, i);
-        const float4 b = bg.at(x, y, i);
         if (premult) {
             if (a.w != 1.0f) {
                 a.x = __fmul_rn(a.x, a.w);
@@ -436,6 +547,32 @@ struct OverOp {
 int color_map_knots(const char* name, const float** knots);
 // colour-space table (tc_tables.cpp)
 int color_convert_setup(const char* from, const char* to, int* curve_in, float* p_in, float m[9], int* curve_out, float* p_out);
+
+// Knot tables resident in device memory, uploaded once per (device, table).
+static int device_knots(const float* host_knots, int n, tc_stream s, const float** out)
+{
+    struct Entry {
+        int device;
+        const float* host;
+        float* dev;
+    };
+    static std::mutex mutex;
+    static std::vector<Entry> entries;
+    int device = 0;
+    TC_CUDA(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lock(mutex);
+    for (const Entry& e : entries)
+        if (e.device == device && e.host == host_knots) {
+            *out = e.dev;
+            return TC_OK;
+        }
+    float* d = nullptr;
+    TC_CUDA(cudaMalloc(&d, sizeof(float) * 3 * n));
+    TC_CUDA(cudaMemcpy(d, host_knots, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    entries.push_back(Entry { device, host_knots, d });
+    *out = d;
+    return TC_OK;
+}
 
 static inline float4 f4(const float c[4]) { return make_float4(c[0], c[1], c[2], c[3]); }
 
@@ -534,8 +671,11 @@ int tc_color_map(const tc_image* dst, const tc_image* src, const char* map_name,
     op.s = make_src(src, dst);
     const float* knots = nullptr;
     op.n = map_name ? color_map_knots(map_name, &knots) : 0;
-    memset(op.k, 0, sizeof(op.k));
-    if (op.n) memcpy(op.k, knots, sizeof(float) * 3 * op.n);
+    op.k = nullptr;
+    if (op.n) {
+        int st = device_knots(knots, op.n, s, &op.k);
+        if (st != TC_OK) return st;
+    }
     return launch(op, dst, s);
 }
 int tc_premult(const tc_image* dst, const tc_image* src, tc_stream s)

@@ -2,8 +2,9 @@
 // CompNode / Dissolve): OIIO's filtered resample restated as gathers.
 //
 //   resize: separable weights (blackman-harris when enlarging, lanczos3 otherwise) are
-//           built once per launch by a tiny per-axis kernel into tap tables, then one
-//           gather kernel accumulates  sum_j sum_i (wy_j * wx_i) * src(clamp)  per pixel
+//           built once per launch by a tiny per-axis kernel into tap tables, then a row
+//           pass and a column pass evaluate  sum_j wy_j sum_i wx_i src(clamp)  with
+//           2(2r+1) taps per pixel instead of (2r+1)^2
 //           (plugins/TransformPlugin.cpp:374-379 -> OIIO resize_, separable branch).
 //   rotate: inverse-maps each pixel centre and filters a lanczos3 footprint with black
 //           outside the source (TransformPlugin.cpp:462-467 -> OIIO rotate/warp_/filtered_sample).
@@ -94,37 +95,57 @@ __global__ void k_resize_axis(const AxisParams A, int* __restrict__ first, float
     total[d * 2 + 1] = resum;
 }
 
-__global__ void __launch_bounds__(256) k_resize(const Img src, const Img dst, const int* __restrict__ xf,
-                                                const float* __restrict__ xw, const float* __restrict__ xt, int xtaps,
-                                                const int* __restrict__ yf, const float* __restrict__ yw,
-                                                const float* __restrict__ yt, int ytaps)
+// Separable evaluation of  sum_j wy_j sum_i wx_i src(clamp)  in two passes through a float32
+// scratch image (the reference loops all (2r+1)^2 taps per pixel with the same separable weights;
+// the two-pass order differs from it by float rounding only, far inside the 1e-5 tolerance):
+//   k_resize_rows:  tmp(x, sy) = sum_i wx_i(x) * src(clamp(fx(x) + i), sy)      dw x sh
+//   k_resize_cols:  dst(x, y)  = sum_j wy_j(y) * tmp(x, clamp(fy(y) + j))       dw x dh
+__global__ void __launch_bounds__(256) k_resize_rows(const Img src, float4* __restrict__ tmp, int dw, const int* __restrict__ xf,
+                                                      const float* __restrict__ xw, const float* __restrict__ xt, int xtaps)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || sy >= src.h) return;
+    float4 pel = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xt[x * 2 + 1] != 0.0f) {
+        const float* wxp = xw + (size_t)x * xtaps;
+        const int fx = xf[x];
+        const size_t row = (size_t)sy * src.w;
+        for (int i = 0; i < xtaps; ++i) {
+            const float w = wxp[i];
+            if (w != 0.0f) {
+                const float4 p = load_px(src.p, src.type, row + min(max(fx + i, 0), src.w - 1));
+                pel.x = __fadd_rn(pel.x, __fmul_rn(w, p.x));
+                pel.y = __fadd_rn(pel.y, __fmul_rn(w, p.y));
+                pel.z = __fadd_rn(pel.z, __fmul_rn(w, p.z));
+                pel.w = __fadd_rn(pel.w, __fmul_rn(w, p.w));
+            }
+        }
+    }
+    tmp[(size_t)sy * dw + x] = pel;
+}
+
+__global__ void __launch_bounds__(256) k_resize_cols(const float4* __restrict__ tmp, int sh, const Img dst, const int* __restrict__ yf,
+                                                      const float* __restrict__ yw, const float* __restrict__ yt, int ytaps)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dst.w || y >= dst.h) return;
     float4 pel = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* wxp = xw + (size_t)x * xtaps;
-    const float* wyp = yw + (size_t)y * ytaps;
-    const int fx = xf[x], fy = yf[y];
-    if (xt[x * 2 + 1] != 0.0f) {
+    if (yt[y * 2 + 0] != 0.0f) {
+        const float* wyp = yw + (size_t)y * ytaps;
+        const int fy = yf[y];
         for (int j = 0; j < ytaps; ++j) {
-            const float wy = wyp[j];
-            if (wy == 0.0f) continue;
-            const int sy = min(max(fy + j, 0), src.h - 1);
-            for (int i = 0; i < xtaps; ++i) {
-                const float w = __fmul_rn(wy, wxp[i]);
-                if (w != 0.0f) {
-                    const int sx = min(max(fx + i, 0), src.w - 1);
-                    const float4 p = load_px(src.p, src.type, (size_t)sy * src.w + sx);
-                    pel.x = __fadd_rn(pel.x, __fmul_rn(w, p.x));
-                    pel.y = __fadd_rn(pel.y, __fmul_rn(w, p.y));
-                    pel.z = __fadd_rn(pel.z, __fmul_rn(w, p.z));
-                    pel.w = __fadd_rn(pel.w, __fmul_rn(w, p.w));
-                }
+            const float w = wyp[j];
+            if (w != 0.0f) {
+                const float4 p = __ldg(tmp + (size_t)min(max(fy + j, 0), sh - 1) * dst.w + x);
+                pel.x = __fadd_rn(pel.x, __fmul_rn(w, p.x));
+                pel.y = __fadd_rn(pel.y, __fmul_rn(w, p.y));
+                pel.z = __fadd_rn(pel.z, __fmul_rn(w, p.z));
+                pel.w = __fadd_rn(pel.w, __fmul_rn(w, p.w));
             }
         }
     }
-    if (yt[y * 2 + 0] == 0.0f) pel = make_float4(0.f, 0.f, 0.f, 0.f);
     store_px(dst.p, dst.type, (size_t)y * dst.w + x, pel);
 }
 
@@ -215,13 +236,15 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
     if (ax.taps > 4096 || ay.taps > 4096) return fail(TC_ERR_UNSUPPORTED, "tc_resize: %d x %d taps", ax.taps, ay.taps);
 
     cudaStream_t st = (cudaStream_t)s;
-    // scratch: [xf | yf | xtot | ytot | xw | yw]
+    // scratch: [tmp (dw x sh float4) | xf | yf | xtot | ytot | xw | yw]
+    const size_t n_tmp = (size_t)dst->w * src->h * 4;
     const size_t n_int = (size_t)dst->w + dst->h;
     const size_t n_tot = 2 * ((size_t)dst->w + dst->h);
     const size_t n_w = (size_t)dst->w * ax.taps + (size_t)dst->h * ay.taps;
     void* scratch = nullptr;
-    TC_CUDA(cudaMallocAsync(&scratch, (n_int + n_tot + n_w) * 4, st));
-    int* xf = (int*)scratch;
+    TC_CUDA(cudaMallocAsync(&scratch, (n_tmp + n_int + n_tot + n_w) * 4, st));
+    float4* tmp = (float4*)scratch;
+    int* xf = (int*)((float*)scratch + n_tmp);
     int* yf = xf + dst->w;
     float* xt = (float*)(yf + dst->h);
     float* yt = xt + 2 * (size_t)dst->w;
@@ -229,9 +252,10 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
     float* yw = xw + (size_t)dst->w * ax.taps;
     k_resize_axis<<<(dst->w + 127) / 128, 128, 0, st>>>(ax, xf, xw, xt);
     k_resize_axis<<<(dst->h + 127) / 128, 128, 0, st>>>(ay, yf, yw, yt);
-    dim3 block(32, 8), grid((dst->w + 31) / 32, (dst->h + 7) / 8);
-    k_resize<<<grid, block, 0, st>>>(view(src), view(dst), xf, xw, xt, ax.taps, yf, yw, yt, ay.taps);
-    count_launch(3);
+    dim3 block(32, 8);
+    k_resize_rows<<<dim3((dst->w + 31) / 32, (src->h + 7) / 8), block, 0, st>>>(view(src), tmp, dst->w, xf, xw, xt, ax.taps);
+    k_resize_cols<<<dim3((dst->w + 31) / 32, (dst->h + 7) / 8), block, 0, st>>>(tmp, src->h, view(dst), yf, yw, yt, ay.taps);
+    count_launch(4);
     int st_launch = check_cuda(cudaGetLastError(), "k_resize launch");
     cudaFreeAsync(scratch, st);
     return st_launch;

@@ -25,7 +25,7 @@
 #include <cstring>
 #include <vector>
 
-#include "tc_common.cuh"
+#include "tc_tile.cuh"
 
 namespace tc {
 
@@ -33,8 +33,6 @@ constexpr int ST_MAX_R = 12;      // live taps per side (radius parameter up to 
 constexpr int ST_MAX_KERNELS = 4; // distinct blur kernels per launch
 constexpr int ST_MAX_LAYERS = 32;
 constexpr int ST_MAX_UNITS = 2 * ST_MAX_LAYERS;
-constexpr int ST_TW = 64, ST_THREADS = 256;
-constexpr int ST_HB = 8; // pixels per thread in the horizontal pass
 
 struct StKernel {
     int R;
@@ -61,43 +59,12 @@ struct StParams {
     StUnit unit[ST_MAX_UNITS];
 };
 
-// Packed fp32x2 arithmetic (FFMA2 / FMUL2): one issue slot per two multiply-adds.  The
-// kernel is issue-bound, not FMA-pipe-bound, so halving the FMA issue slots is the lever.
-__device__ __forceinline__ float4 fma4p(float w, float4 p, float4 a)
-{
-    const float2 ww = make_float2(w, w);
-    const float2 lo = __ffma2_rn(ww, make_float2(p.x, p.y), make_float2(a.x, a.y));
-    const float2 hi = __ffma2_rn(ww, make_float2(p.z, p.w), make_float2(a.z, a.w));
-    return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ float4 mul4p(float w, float4 p)
-{
-    const float2 ww = make_float2(w, w);
-    const float2 lo = __fmul2_rn(ww, make_float2(p.x, p.y));
-    const float2 hi = __fmul2_rn(ww, make_float2(p.z, p.w));
-    return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-
 // Dissolve: add(mul(from, iv), mul(to, v)) (float storage: nothing is quantised)
 __device__ __forceinline__ float4 mix4(float4 a, float4 b, float iv, float v)
 {
     return make_float4(__fadd_rn(__fmul_rn(a.x, iv), __fmul_rn(b.x, v)), __fadd_rn(__fmul_rn(a.y, iv), __fmul_rn(b.y, v)),
                        __fadd_rn(__fmul_rn(a.z, iv), __fmul_rn(b.z, v)), __fadd_rn(__fmul_rn(a.w, iv), __fmul_rn(b.w, v)));
 }
-
-template <int R, int TH, int NBUF = 2>
-struct StTile {
-    static constexpr int PX = ST_TW * TH / ST_THREADS; // output pixels per thread: one column segment
-    static constexpr int IW = ST_TW + 2 * R;  // staged columns
-    static constexpr int IH = TH + 2 * R;     // staged rows
-    static constexpr int IWP = IW | 1;        // odd row stride (float4 units)
-    static constexpr int MWP = ST_TW | 1;
-    static constexpr int IN_ELEMS = IH * IWP;
-    static constexpr int MID_ELEMS = IH * MWP;
-    static constexpr size_t SMEM = (size_t)(NBUF * IN_ELEMS + MID_ELEMS) * sizeof(float4); // staging buffer(s) + mid
-    static constexpr int STAGE_ROWS = ST_THREADS / IW;                 // rows staged per pass
-    static constexpr int STAGE_N = (IH + STAGE_ROWS - 1) / STAGE_ROWS; // passes
-};
 
 __device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc)
 {
@@ -126,55 +93,6 @@ __device__ __forceinline__ void tile_prefetch(const float4* __restrict__ src, in
         }
     }
     cp_async_commit();
-}
-
-// rows: 8 adjacent outputs per thread, lanes on consecutive rows; FIRST writes mid, else adds
-template <int R, int TH, bool FIRST>
-__device__ __forceinline__ void tile_rows(const float4* in, float4* mid, const float (&g)[2 * R + 1])
-{
-    using T = StTile<R, TH>;
-    constexpr int N_H = T::IH * (ST_TW / ST_HB);
-    for (int item = threadIdx.x; item < N_H; item += ST_THREADS) {
-        const int row = item % T::IH, xb = item / T::IH;
-        const float4* p = in + row * T::IWP + xb * ST_HB;
-        float4* m = mid + row * T::MWP + xb * ST_HB;
-        float4 o[ST_HB];
-        if (!FIRST) {
-#pragma unroll
-            for (int k = 0; k < ST_HB; ++k) o[k] = m[k];
-        }
-#pragma unroll
-        for (int j = 0; j < ST_HB + 2 * R; ++j) {
-            const float4 q = p[j];
-#pragma unroll
-            for (int k = 0; k < ST_HB; ++k) {
-                const int t = j - k;
-                if (FIRST && t == 0) o[k] = mul4p(g[0], q);
-                else if (t >= 0 && t <= 2 * R) o[k] = fma4p(g[t], q, o[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < ST_HB; ++k) m[k] = o[k];
-    }
-}
-
-// columns: PX consecutive rows per thread, lanes on consecutive columns
-template <int R, int TH>
-__device__ __forceinline__ void tile_cols(const float4* mid, const float (&g)[2 * R + 1], float4 out[StTile<R, TH>::PX])
-{
-    using T = StTile<R, TH>;
-    const int col = threadIdx.x % ST_TW, seg = threadIdx.x / ST_TW;
-    const float4* p = mid + (seg * T::PX) * T::MWP + col;
-#pragma unroll
-    for (int j = 0; j < T::PX + 2 * R; ++j) {
-        const float4 q = p[j * T::MWP];
-#pragma unroll
-        for (int k = 0; k < T::PX; ++k) {
-            const int t = j - k;
-            if (t == 0) out[k] = mul4p(g[0], q);
-            else if (t > 0 && t <= 2 * R) out[k] = fma4p(g[t], q, out[k]);
-        }
-    }
 }
 
 template <int ST_PX>
