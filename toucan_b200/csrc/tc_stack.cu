@@ -32,25 +32,25 @@ namespace tc {
 constexpr int ST_MAX_R = 12;      // live taps per side (radius parameter up to ~26)
 constexpr int ST_MAX_KERNELS = 4; // distinct blur kernels per launch
 constexpr int ST_MAX_LAYERS = 32;
-constexpr int ST_MAX_UNITS = 2 * ST_MAX_LAYERS;
+constexpr int ST_MAX_UNITS = ST_MAX_LAYERS;
 
 struct StKernel {
     int R;
     float scale;
     float g[2 * ST_MAX_R + 1]; // already multiplied by sqrt(scale)
 };
-// One step of the per-tile pipeline.  A blurred layer is one staged unit; a blurred Dissolve
-// is two (H-pass of `from` weighted by iv, H-pass of `to` weighted by v accumulated on top,
-// ONE vertical pass: blur is linear).  An unblurred layer is a DIRECT unit (no staging).
-enum { ST_FIRST = 1, ST_LAST = 2, ST_DIRECT = 4 };
+// One step of the per-tile pipeline = one layer.  PLAIN: a blurred source.  MIX: a blurred
+// Dissolve whose two inputs carry the same blur -- both tiles are staged, mixed in place in
+// shared memory (a*iv + b*v) and blurred ONCE (convolution is linear).  DIRECT: an unblurred
+// layer read straight from global memory.
+enum { ST_MIX = 1, ST_DIRECT = 4, ST_NEXT_EARLY = 8 };
 struct StUnit {
     const float4* src;
-    const float4* src2; // DIRECT units only: the Dissolve's second input (or null)
-    float w;            // weight folded into the horizontal taps (1, iv or v)
-    float w2;           // DIRECT units: v (src weight = w)
+    const float4* src2; // MIX / DIRECT Dissolve: the second input (or null)
+    float w, w2;        // Dissolve weights (iv, v)
     short kernel;
-    short flags;
-    int next_staged; // index of the next staged unit (prefetch target), or -1
+    short flags;        // ST_NEXT_EARLY: the next staged unit may stream in while this one is filtered
+    int next_staged;    // index of the next staged unit (prefetch target), or -1
 };
 struct StParams {
     int w, h, n_units, first_staged;
@@ -103,12 +103,13 @@ __device__ __forceinline__ void tile_load(const float4* __restrict__ src, int w,
     for (int k = 0; k < ST_PX; ++k) out[k] = __ldg(src + (size_t)min(y + k, h - 1) * w + x);
 }
 
-// NBUF = 2: the next unit's tile streams into the other staging buffer while this one is
-// filtered (2 CTAs per SM at radius 10).  NBUF = 1: one staging buffer, the next tile streams
-// in during the vertical pass and the blend (3 CTAs per SM at radius 10).
+// Two staging buffers + mid, 2 CTAs per SM at radius 10.  A plain layer following a plain layer
+// streams in (cp.async) while its predecessor is filtered; a Dissolve layer needs both buffers, so
+// its two tiles stream in during the predecessor's vertical pass and blend.
 template <int R, int TH, int NBUF, int OCC>
 __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restrict__ dst, const __grid_constant__ StParams P)
 {
+    static_assert(NBUF == 2, "the pipeline uses two staging buffers");
     using T = StTile<R, TH, NBUF>;
     constexpr int ST_PX = T::PX;
     extern __shared__ float4 smem[];
@@ -121,8 +122,15 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restric
 #pragma unroll
     for (int k = 0; k < ST_PX; ++k) acc[k] = P.background;
 
+    // stage the tile(s) of a unit: `a` into buffer `slot`, a Dissolve's `b` into the other one
+    auto prefetch = [&](int index, int slot) {
+        const StUnit& N = P.unit[index];
+        tile_prefetch<R, TH>(N.src, P.w, P.h, x0, y0, smem + slot * T::IN_ELEMS);
+        if (N.flags & ST_MIX) tile_prefetch<R, TH>(N.src2, P.w, P.h, x0, y0, smem + (slot ^ 1) * T::IN_ELEMS);
+    };
+
     int slot = 0;
-    if (P.first_staged >= 0) tile_prefetch<R, TH>(P.unit[P.first_staged].src, P.w, P.h, x0, y0, smem);
+    if (P.first_staged >= 0) prefetch(P.first_staged, 0);
 
     for (int u = 0; u < P.n_units; ++u) {
         const StUnit& U = P.unit[u];
@@ -138,30 +146,41 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restric
         } else {
             const StKernel& K = P.k[U.kernel];
             // taps centred on R (zero padded when this kernel is narrower than the template)
-            float g[2 * R + 1], gw[2 * R + 1];
+            float g[2 * R + 1];
 #pragma unroll
             for (int t = 0; t <= 2 * R; ++t) {
                 const int s = t - R + K.R;
                 g[t] = (s >= 0 && s <= 2 * K.R) ? K.g[s] : 0.0f;
-                gw[t] = g[t] * U.w;
             }
             cp_async_wait_all();
-            __syncthreads(); // this unit's tile has landed; `mid` (and the other buffer) are free again
-            const float4* in = smem + slot * T::IN_ELEMS;
-            if (NBUF == 2) {
-                slot ^= 1;
-                if (U.next_staged >= 0)
-                    tile_prefetch<R, TH>(P.unit[U.next_staged].src, P.w, P.h, x0, y0, smem + slot * T::IN_ELEMS);
-            }
-            if (U.flags & ST_FIRST) tile_rows<R, TH, true>(in, mid, gw);
-            else tile_rows<R, TH, false>(in, mid, gw);
-            if (NBUF == 1) {
-                __syncthreads(); // every row pass is done with the staging buffer
-                if (U.next_staged >= 0) tile_prefetch<R, TH>(P.unit[U.next_staged].src, P.w, P.h, x0, y0, smem);
-                if (!(U.flags & ST_LAST)) continue;
-            } else {
-                if (!(U.flags & ST_LAST)) continue;
+            __syncthreads(); // this unit's tile(s) have landed; `mid` is free again
+            float4* in = smem + slot * T::IN_ELEMS;
+            const bool early = (U.flags & ST_NEXT_EARLY) != 0;
+            if (early) prefetch(U.next_staged, slot ^ 1);
+            if (U.flags & ST_MIX) {
+                // in-place Dissolve of the two staged tiles; every thread mixes the elements it staged
+                const float4* inb = smem + (slot ^ 1) * T::IN_ELEMS;
+                const int tid = threadIdx.x;
+                if (tid < T::STAGE_ROWS * T::IW) {
+                    const int ry = tid / T::IW, ix = tid - ry * T::IW;
+#pragma unroll
+                    for (int v = 0; v < T::STAGE_N; ++v) {
+                        const int iy = ry + v * T::STAGE_ROWS;
+                        if (iy < T::IH) {
+                            const int o = iy * T::IWP + ix;
+                            in[o] = fma4p(U.w, in[o], mul4p(U.w2, inb[o]));
+                        }
+                    }
+                }
                 __syncthreads();
+            }
+            tile_rows<R, TH, true>(in, mid, g);
+            __syncthreads(); // row pass done: `mid` is complete, both staging buffers are free
+            if (!early && U.next_staged >= 0) {
+                slot = 0;
+                prefetch(U.next_staged, 0);
+            } else {
+                slot ^= 1;
             }
             tile_cols<R, TH>(mid, g, f);
         }
@@ -294,17 +313,6 @@ extern "C" int tc_stack_f32(const tc_image* dst, const float background[4], cons
     };
     int nu = 0, last_staged = -1;
     P.first_staged = -1;
-    auto staged = [&](const void* src, float w, int kernel, int flags) {
-        StUnit& U = P.unit[nu];
-        U.src = (const float4*)src;
-        U.w = w;
-        U.kernel = (short)kernel;
-        U.flags = (short)flags;
-        U.next_staged = -1;
-        if (last_staged >= 0) P.unit[last_staged].next_staged = nu;
-        else P.first_staged = nu;
-        last_staged = nu++;
-    };
     for (int l = 0; l < n_layers; ++l) {
         if (!layers[l].src_a) return fail(TC_ERR_INVALID, "tc_stack_f32: layer %d has no source", l);
         int ka = -1, kb = -1;
@@ -313,30 +321,34 @@ extern "C" int tc_stack_f32(const tc_image* dst, const float background[4], cons
         if (layers[l].src_b && ka != kb)
             return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: layer %d dissolves inputs with different blurs (%g, %g)", l,
                         layers[l].radius_a, layers[l].radius_b);
-        const float fv = (float)layers[l].value, fiv = (float)(1.0 - layers[l].value);
+        StUnit& U = P.unit[nu];
+        U.src = (const float4*)layers[l].src_a;
+        U.src2 = (const float4*)layers[l].src_b;
+        U.w = (float)(1.0 - layers[l].value);
+        U.w2 = (float)layers[l].value;
+        U.kernel = (short)ka;
+        U.next_staged = -1;
         if (ka < 0) {
-            StUnit& U = P.unit[nu++];
-            U.src = (const float4*)layers[l].src_a;
-            U.src2 = (const float4*)layers[l].src_b;
-            U.w = fiv;
-            U.w2 = fv;
-            U.kernel = -1;
             U.flags = ST_DIRECT;
-            U.next_staged = -1;
-        } else if (layers[l].src_b) {
-            staged(layers[l].src_a, fiv, ka, ST_FIRST);
-            staged(layers[l].src_b, fv, ka, ST_LAST);
         } else {
-            staged(layers[l].src_a, 1.0f, ka, ST_FIRST | ST_LAST);
+            U.flags = layers[l].src_b ? ST_MIX : 0;
+            if (last_staged >= 0) {
+                StUnit& prev = P.unit[last_staged];
+                prev.next_staged = nu;
+                // a plain layer after a plain layer streams in while its predecessor is filtered
+                if (!(prev.flags & ST_MIX) && !(U.flags & ST_MIX)) prev.flags |= ST_NEXT_EARLY;
+            } else {
+                P.first_staged = nu;
+            }
+            last_staged = nu;
         }
+        ++nu;
     }
     P.n_units = nu;
-    // tuning knob for the radius-10 (R = 4) case: number of staging buffers
-    static const int nbuf = getenv("TOUCAN_STACK_NBUF") ? atoi(getenv("TOUCAN_STACK_NBUF")) : 2;
     cudaStream_t st = (cudaStream_t)s;
     if (maxR <= 2) return launch_stack<2, 24, 2>(dst, P, st);
-    if (maxR <= 4) return nbuf == 1 ? launch_stack<4, 24, 1>(dst, P, st) : launch_stack<4, 24, 2>(dst, P, st);
-    if (maxR <= 6) return launch_stack<6, 24, 1>(dst, P, st);
-    if (maxR <= 9) return launch_stack<9, 24, 1>(dst, P, st);
-    return launch_stack<12, 24, 1>(dst, P, st);
+    if (maxR <= 4) return launch_stack<4, 24, 2>(dst, P, st);
+    if (maxR <= 6) return launch_stack<6, 24, 2>(dst, P, st);
+    if (maxR <= 9) return launch_stack<9, 24, 2>(dst, P, st);
+    return launch_stack<12, 24, 2>(dst, P, st);
 }
