@@ -268,3 +268,42 @@ def test_stack_fused_matches_unfused_and_oracle(T, n_layers, trans):
             x = T.dissolve(x, T.blur(b, rb), v)
         acc_d = T.over(x, acc_d, premult_fg=True)
     assert_close(got, to_host(acc_d), "fused stack vs unfused kernels")
+
+
+@pytest.mark.parametrize("radius", [30.0, 49.0])
+def test_blur_wide_kernel_fallback(T, radius):
+    # more than 12 live taps per side: the generic wide-kernel path
+    src = rand_img(150, 97, np.float32, 21)
+    assert_close(T.blur(to_dev(src), radius), O.blur(src, radius), f"blur {radius}")
+    assert_close(T.unsharp_mask(to_dev(src), "gaussian", radius, 0.5, 0.0), O.unsharp_mask(src, "gaussian", radius, 0.5, 0.0), "unsharp wide")
+
+
+@pytest.mark.parametrize("radius", [3.0, 14.0, 20.0, 26.0])
+def test_stack_other_radii_and_mixed_layers(T, radius):
+    # template instantiations R = 2, 6, 9, 12; blurred, unblurred and dissolve layers in one stack;
+    # odd frame size (partial tiles on both axes)
+    w, h = 203, 77
+    a = [rand_img(w, h, np.float32, 300 + i) for i in range(6)]
+    d = [to_dev(x) for x in a]
+    layers_np = [(a[0], None, radius, 0.0, 0.0), (a[1], a[2], radius, radius, 0.3), (a[3], None, 0.0, 0.0, 0.0),
+                 (a[4], a[5], 0.0, 0.0, 0.75)]
+    layers_dev = [(d[0], None, radius, 0.0, 0.0), (d[1], d[2], radius, radius, 0.3), (d[3], None, 0.0, 0.0, 0.0),
+                  (d[4], d[5], 0.0, 0.0, 0.75)]
+    acc = O.fill(w, h, [0.1, 0.2, 0.3, 1.0], O.F32)
+    for sa, sb, ra, rb, v in layers_np:
+        x = O.blur(sa, ra) if ra > 0 else sa
+        if sb is not None:
+            x = O.dissolve(x, O.blur(sb, rb) if rb > 0 else sb, v)
+        acc = O.comp(x, acc, True)
+    got = T.stack_f32(w, h, [0.1, 0.2, 0.3, 1.0], layers_dev)
+    assert_close(got, acc, f"stack radius {radius}")
+
+
+def test_stack_rejects_what_it_cannot_fuse(T):
+    from toucan_b200 import capi
+
+    a, b = to_dev(rand_img(64, 48, np.float32, 1)), to_dev(rand_img(64, 48, np.float32, 2))
+    with pytest.raises(capi.TcError):  # different blurs on the two dissolve inputs
+        T.stack_f32(64, 48, [0, 0, 0, 1], [(a, b, 10.0, 4.0, 0.5)])
+    with pytest.raises(capi.TcError):  # radius beyond the fused kernel's range
+        T.stack_f32(64, 48, [0, 0, 0, 1], [(a, None, 60.0, 0.0, 0.0)])
