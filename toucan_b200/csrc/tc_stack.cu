@@ -43,13 +43,13 @@ struct StKernel {
 // Dissolve whose two inputs carry the same blur -- both tiles are staged, mixed in place in
 // shared memory (a*iv + b*v) and blurred ONCE (convolution is linear).  DIRECT: an unblurred
 // layer read straight from global memory.
-enum { ST_MIX = 1, ST_DIRECT = 4, ST_NEXT_EARLY = 8 };
+enum { ST_MIX = 1, ST_DIRECT = 4 };
 struct StUnit {
     const float4* src;
     const float4* src2; // MIX / DIRECT Dissolve: the second input (or null)
     float w, w2;        // Dissolve weights (iv, v)
     short kernel;
-    short flags;        // ST_NEXT_EARLY: the next staged unit may stream in while this one is filtered
+    short flags;
     int next_staged;    // index of the next staged unit (prefetch target), or -1
 };
 struct StParams {
@@ -103,9 +103,8 @@ __device__ __forceinline__ void tile_load(const float4* __restrict__ src, int w,
     for (int k = 0; k < ST_PX; ++k) out[k] = __ldg(src + (size_t)min(y + k, h - 1) * w + x);
 }
 
-// Two staging buffers + mid, 2 CTAs per SM at radius 10.  A plain layer following a plain layer
-// streams in (cp.async) while its predecessor is filtered; a Dissolve layer needs both buffers, so
-// its two tiles stream in during the predecessor's vertical pass and blend.
+// Two staging buffers + mid, 2 CTAs per SM at radius 10; tiles stream in (cp.async) while the
+// previous layer is filtered.
 template <int R, int TH, int NBUF, int OCC>
 __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restrict__ dst, const __grid_constant__ StParams P)
 {
@@ -122,15 +121,17 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restric
 #pragma unroll
     for (int k = 0; k < ST_PX; ++k) acc[k] = P.background;
 
-    // stage the tile(s) of a unit: `a` into buffer `slot`, a Dissolve's `b` into the other one
-    auto prefetch = [&](int index, int slot) {
-        const StUnit& N = P.unit[index];
-        tile_prefetch<R, TH>(N.src, P.w, P.h, x0, y0, smem + slot * T::IN_ELEMS);
-        if (N.flags & ST_MIX) tile_prefetch<R, TH>(N.src2, P.w, P.h, x0, y0, smem + (slot ^ 1) * T::IN_ELEMS);
-    };
-
+    // Buffer roles: the unit being filtered has its tile `a` in buffer `slot` and, for a Dissolve,
+    // tile `b` in the other one (mixed on the fly by the row pass).  A plain layer leaves the other
+    // buffer free, so the next unit's `a` streams into it during the whole filter; after the row
+    // pass both buffers are free and whatever the next unit still needs streams in during the
+    // column pass and the blend.  The next unit then sees a / b in (slot^1, slot).
     int slot = 0;
-    if (P.first_staged >= 0) prefetch(P.first_staged, 0);
+    if (P.first_staged >= 0) {
+        const StUnit& N = P.unit[P.first_staged];
+        tile_prefetch<R, TH>(N.src, P.w, P.h, x0, y0, smem);
+        if (N.flags & ST_MIX) tile_prefetch<R, TH>(N.src2, P.w, P.h, x0, y0, smem + T::IN_ELEMS);
+    }
 
     for (int u = 0; u < P.n_units; ++u) {
         const StUnit& U = P.unit[u];
@@ -155,33 +156,19 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restric
             cp_async_wait_all();
             __syncthreads(); // this unit's tile(s) have landed; `mid` is free again
             float4* in = smem + slot * T::IN_ELEMS;
-            const bool early = (U.flags & ST_NEXT_EARLY) != 0;
-            if (early) prefetch(U.next_staged, slot ^ 1);
-            if (U.flags & ST_MIX) {
-                // in-place Dissolve of the two staged tiles; every thread mixes the elements it staged
-                const float4* inb = smem + (slot ^ 1) * T::IN_ELEMS;
-                const int tid = threadIdx.x;
-                if (tid < T::STAGE_ROWS * T::IW) {
-                    const int ry = tid / T::IW, ix = tid - ry * T::IW;
-#pragma unroll
-                    for (int v = 0; v < T::STAGE_N; ++v) {
-                        const int iy = ry + v * T::STAGE_ROWS;
-                        if (iy < T::IH) {
-                            const int o = iy * T::IWP + ix;
-                            in[o] = fma4p(U.w, in[o], mul4p(U.w2, inb[o]));
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            tile_rows<R, TH, true>(in, mid, g);
-            __syncthreads(); // row pass done: `mid` is complete, both staging buffers are free
-            if (!early && U.next_staged >= 0) {
-                slot = 0;
-                prefetch(U.next_staged, 0);
+            float4* other = smem + (slot ^ 1) * T::IN_ELEMS;
+            const StUnit* N = U.next_staged >= 0 ? &P.unit[U.next_staged] : nullptr;
+            const bool mix = (U.flags & ST_MIX) != 0;
+            if (mix) {
+                tile_rows_mix<R, TH>(in, other, U.w, U.w2, mid, g);
             } else {
-                slot ^= 1;
+                if (N) tile_prefetch<R, TH>(N->src, P.w, P.h, x0, y0, other);
+                tile_rows<R, TH, true>(in, mid, g);
             }
+            __syncthreads(); // row pass done: `mid` is complete, the staging buffers are free
+            if (N && mix) tile_prefetch<R, TH>(N->src, P.w, P.h, x0, y0, other);
+            if (N && (N->flags & ST_MIX)) tile_prefetch<R, TH>(N->src2, P.w, P.h, x0, y0, in);
+            slot ^= 1;
             tile_cols<R, TH>(mid, g, f);
         }
         // CompNode: premult(fg) then over(fg, acc); tolerance path, so fused multiply-adds
@@ -333,10 +320,7 @@ extern "C" int tc_stack_f32(const tc_image* dst, const float background[4], cons
         } else {
             U.flags = layers[l].src_b ? ST_MIX : 0;
             if (last_staged >= 0) {
-                StUnit& prev = P.unit[last_staged];
-                prev.next_staged = nu;
-                // a plain layer after a plain layer streams in while its predecessor is filtered
-                if (!(prev.flags & ST_MIX) && !(U.flags & ST_MIX)) prev.flags |= ST_NEXT_EARLY;
+                P.unit[last_staged].next_staged = nu;
             } else {
                 P.first_staged = nu;
             }

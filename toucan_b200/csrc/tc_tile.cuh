@@ -76,6 +76,36 @@ __device__ __forceinline__ void tile_rows(const float4* in, float4* mid, const f
     }
 }
 
+// rows of the Dissolve of two staged tiles, mixed on the fly: every input is read once from each
+// tile (a*wa + b*wb) and fed to the taps -- no separate mixing pass over shared memory
+template <int R, int TH>
+__device__ __forceinline__ void tile_rows_mix(const float4* ina, const float4* inb, float wa, float wb, float4* mid,
+                                              const float (&g)[2 * R + 1])
+{
+    using T = StTile<R, TH>;
+    constexpr int N_H = T::IH * (ST_TW / ST_HB);
+    for (int item = threadIdx.x; item < N_H; item += ST_THREADS) {
+        const int row = item % T::IH, xb = item / T::IH;
+        const int base = row * T::IWP + xb * ST_HB;
+        const float4* pa = ina + base;
+        const float4* pb = inb + base;
+        float4* m = mid + row * T::MWP + xb * ST_HB;
+        float4 o[ST_HB];
+#pragma unroll
+        for (int j = 0; j < ST_HB + 2 * R; ++j) {
+            const float4 q = fma4p(wa, pa[j], mul4p(wb, pb[j]));
+#pragma unroll
+            for (int k = 0; k < ST_HB; ++k) {
+                const int t = j - k;
+                if (t == 0) o[k] = mul4p(g[0], q);
+                else if (t > 0 && t <= 2 * R) o[k] = fma4p(g[t], q, o[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ST_HB; ++k) m[k] = o[k];
+    }
+}
+
 // columns: PX consecutive rows per thread, lanes on consecutive columns
 template <int R, int TH>
 __device__ __forceinline__ void tile_cols(const float4* mid, const float (&g)[2 * R + 1], float4 out[StTile<R, TH>::PX])
