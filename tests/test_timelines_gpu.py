@@ -213,3 +213,34 @@ def test_frame_scheduler_reports_worker_errors(cuda):
     with pytest.raises(capi.TcError):
         tl.render_range(0, 4, lambda f, p: None, devices=[99])  # no such device: the worker's error reaches the caller
     tl.close()
+
+
+def test_frame_scheduler_across_gpus(cuda):
+    """One process driving every visible GPU (toucan-render -gpus N): frames sharded in contiguous
+    blocks, gathered in order; the fused stack kernel's attributes are set on every device."""
+    import torch
+
+    from toucan_b200 import render, workloads
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    name = "Transition2.otio"
+    tl = TL.open_timeline(name)
+    got = []
+    tl.render_range(0, len(GOLD[name]["frames"]), lambda f, p: got.append((f, hashlib.sha256(p.tobytes()).hexdigest())),
+                    devices=list(range(n)))
+    assert got == [(i, r["sha256"]) for i, r in enumerate(GOLD[name]["frames"])]
+    tl.close()
+    # float stack timeline: host media uploaded on each worker's device, fused kernel on each device
+    w, h = 320, 180
+    doc, tl, frames = _stack_setup(w, h, 3)
+    otl = G.Timeline(doc)
+    otl.dir = "/synthetic"
+    og = G.ImageGraph(otl, lambda p: frames.get(p))
+    out = {}
+    tl.render_range(30, 30 + 4 * n, lambda f, p: out.__setitem__(f, p.copy()), devices=list(range(n)))
+    assert sorted(out) == list(range(30, 30 + 4 * n))
+    for f, img in out.items():
+        assert np.abs(img - og.render(G.RT(float(f), 24.0))).max() <= 1e-5, f
+    tl.close()

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -42,6 +43,22 @@ int num_sms()
         if (sms <= 0) sms = 148;
     }
     return sms;
+}
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes)
+{
+    static std::mutex mutex;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int device = 0;
+    TC_CUDA(cudaGetDevice(&device));
+    std::lock_guard<std::mutex> lock(mutex);
+    size_t& have = done[std::make_pair(kernel, device)];
+    if (bytes > have) {
+        TC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        TC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        have = bytes;
+    }
+    return TC_OK;
 }
 
 int validate(const tc_image* im, const char* name)

@@ -15,6 +15,10 @@ int fail(int status, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch(unsigned n = 1);
 int num_sms();
+// Opt a kernel into `bytes` of dynamic shared memory (and the maximum shared-memory carve-out)
+// on the CURRENT device.  Function attributes are per device, so this is tracked per
+// (kernel, device): one process may drive all GPUs of a box (toucan::FrameScheduler).
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 #define TC_CUDA(call)                                      \
     do {                                                   \

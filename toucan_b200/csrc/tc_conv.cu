@@ -212,13 +212,8 @@ static int launch_tile(const tc_image* dst, const tc_image* src, const ConvParam
 {
     using T = StTile<R, 24, 1>;
     constexpr int OCC = T::SMEM <= 74 * 1024 ? 3 : (T::SMEM <= 112 * 1024 ? 2 : 1);
-    static bool configured = false;
-    if (!configured) {
-        TC_CUDA(cudaFuncSetAttribute(k_gauss_tile<R, UNSHARP, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-        TC_CUDA(cudaFuncSetAttribute(k_gauss_tile<R, UNSHARP, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
+    int st_attr = ensure_dynamic_smem((const void*)k_gauss_tile<R, UNSHARP, OCC>, T::SMEM);
+    if (st_attr != TC_OK) return st_attr;
     dim3 grid((dst->w + ST_TW - 1) / ST_TW, (dst->h + 23) / 24);
     k_gauss_tile<R, UNSHARP, OCC><<<grid, ST_THREADS, T::SMEM, st>>>(view(src), view(dst), P);
     count_launch();
@@ -235,11 +230,8 @@ static int launch_conv_t(const tc_image* dst, const tc_image* src, const ConvPar
     if (P.R <= 12) return launch_tile<12, UNSHARP>(dst, src, P, st);
     const int IW = CONV_TW + 2 * P.R, IH = CONV_TH + 2 * P.R;
     const size_t smem = (size_t)(IH * IW + IH * CONV_TW) * sizeof(float4);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TC_CUDA(cudaFuncSetAttribute(k_gauss_wide<UNSHARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    int st_attr = ensure_dynamic_smem((const void*)k_gauss_wide<UNSHARP>, smem);
+    if (st_attr != TC_OK) return st_attr;
     dim3 grid((dst->w + CONV_TW - 1) / CONV_TW, (dst->h + CONV_TH - 1) / CONV_TH);
     k_gauss_wide<UNSHARP><<<grid, CONV_THREADS, smem, st>>>(view(src), view(dst), P);
     count_launch();

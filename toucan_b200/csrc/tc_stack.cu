@@ -251,13 +251,8 @@ static int launch_stack(const tc_image* dst, const StParams& P, cudaStream_t st)
 {
     using T = StTile<R, TH, NBUF>;
     static_assert(T::SMEM <= 227 * 1024, "tile does not fit in shared memory");
-    static bool configured = false;
-    if (!configured) {
-        TC_CUDA(cudaFuncSetAttribute(k_stack_f32<R, TH, NBUF, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-        TC_CUDA(cudaFuncSetAttribute(k_stack_f32<R, TH, NBUF, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
+    int st_attr = ensure_dynamic_smem((const void*)k_stack_f32<R, TH, NBUF, OCC>, T::SMEM);
+    if (st_attr != TC_OK) return st_attr;
     dim3 grid((dst->w + ST_TW - 1) / ST_TW, (dst->h + TH - 1) / TH);
     k_stack_f32<R, TH, NBUF, OCC><<<grid, ST_THREADS, T::SMEM, st>>>((float4*)dst->data, P);
     count_launch();
