@@ -148,6 +148,12 @@ int tc_paste_on_black(const tc_image* dst, int ox, int oy, const tc_image* src, 
 /* storage-type conversion / copy, 0 outside src           bin/toucan-render/App.cpp:285-291 */
 int tc_convert(const tc_image* dst, const tc_image* src, tc_stream s);
 
+/* raw output packing on the device, so the download moves the writer's bytes and not the
+   working format's: paste(tmp(rawSpec), 0, 0, 0, 0, buf)    bin/toucan-render/App.cpp:267-300
+   (rgb24, rgba, rgb48, rgba64, rgbaf16, rgbf32, rgbaf32 = `channels` x `type`, tightly packed).
+   channels: 3 (alpha dropped) or 4. */
+int tc_pack_raw(void* dst_dev, const tc_image* src, int type, int channels, tc_stream s);
+
 /* ---- fused track stack (cross-node fusion of the hot chain) ------------------------
  * One pass over the output for a whole stack of tracks:
  *   acc = background colour

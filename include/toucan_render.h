@@ -74,6 +74,13 @@ typedef void (*tr_frame_callback)(void* user, int frame, const void* pixels, int
 int tr_render_range(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
                     int frames_in_flight, tr_frame_callback callback, void* user);
 
+/* Same with the output stage of `toucan-render - -raw <format>` (App.cpp:267-300) on the device:
+   raw_format = "rgb24" | "rgba" | "rgb48" | "rgba64" | "rgbaf16" | "rgbf32" | "rgbaf32" (NULL = the
+   working format).  Frames whose storage type differs from the format's are converted before the
+   download; the callback's `type` then carries the raw type, plus 0x100 for 3-channel formats. */
+int tr_render_range_raw(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
+                        int frames_in_flight, const char* raw_format, tr_frame_callback callback, void* user);
+
 /* The scheduler's partition: frames [first, last) -> the contiguous block [*lo, *hi) owned by
    worker `index` of `count` (ceil(N / G) frames per GPU). */
 void tr_frame_block(int first, int last, int index, int count, int* lo, int* hi);

@@ -244,3 +244,25 @@ def test_frame_scheduler_across_gpus(cuda):
     for f, img in out.items():
         assert np.abs(img - og.render(G.RT(float(f), 24.0))).max() <= 1e-5, f
     tl.close()
+
+
+@pytest.mark.parametrize("fmt,dtype,nch", [("rgbaf32", np.float32, 4), ("rgbf32", np.float32, 3), ("rgba64", np.uint16, 4),
+                                          ("rgb48", np.uint16, 3), ("rgbaf16", np.float16, 4), ("rgba", np.uint8, 4), ("rgb24", np.uint8, 3)])
+def test_raw_output_formats_on_device(cuda, fmt, dtype, nch):
+    """`toucan-render - -raw <fmt>` (App.cpp:267-300): the frame is converted to the raw format's storage type on
+    the device.  Like the reference, a frame whose type already matches is written as it is (4 channels)."""
+    name = "Transition.otio"  # configs[0]: u8 working format -> raw output
+    tl = TL.open_timeline(name)
+    otl = G.Timeline(os.path.join(TL.DATA, name))
+    og = G.ImageGraph(otl, media.decode)
+    frames = otl.frames()[3:6]
+    got = {}
+    tl.render_range(3, 6, lambda f, p: got.__setitem__(f, p.copy()), raw_format=fmt)
+    for i, t in enumerate(frames):
+        want = og.render(t)
+        if want.dtype != dtype:
+            want = O.convert(want, O._DT[np.dtype(dtype)])[..., :nch]
+        g = got[3 + i]
+        assert g.dtype == want.dtype and g.shape == want.shape, (fmt, g.dtype, g.shape, want.dtype, want.shape)
+        assert np.array_equal(g, want), fmt
+    tl.close()

@@ -593,6 +593,31 @@ static float quant_host(float v, int type)
     }
 }
 
+// raw output packing: RGBA working format -> `channels` x `type`, tightly packed
+template <int CH>
+__global__ void __launch_bounds__(256) k_pack_raw(void* __restrict__ dst, const Img src, int type)
+{
+    const unsigned total = (unsigned)src.w * (unsigned)src.h;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const float4 p = load_px(src.p, src.type, i);
+        const float v[4] = { p.x, p.y, p.z, p.w };
+        if (CH == 4) {
+            store_px(dst, type, i, p);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const size_t o = (size_t)i * 3 + c;
+                switch (type) {
+                case TC_U8: reinterpret_cast<unsigned char*>(dst)[o] = (unsigned char)f_to_u8(v[c]); break;
+                case TC_U16: reinterpret_cast<unsigned short*>(dst)[o] = (unsigned short)f_to_u16(v[c]); break;
+                case TC_F16: reinterpret_cast<__half*>(dst)[o] = __float2half_rn(v[c]); break;
+                default: reinterpret_cast<float*>(dst)[o] = v[c]; break;
+                }
+            }
+        }
+    }
+}
+
 } // namespace tc
 
 using namespace tc;
@@ -734,6 +759,21 @@ int tc_paste_on_black(const tc_image* dst, int ox, int oy, const tc_image* src, 
     TC_VALIDATE(dst, "tc_paste_on_black dst");
     TC_VALIDATE(src, "tc_paste_on_black src");
     return launch(PasteOp { view(src), ox, oy }, dst, s);
+}
+
+int tc_pack_raw(void* dst_dev, const tc_image* src, int type, int channels, tc_stream s)
+{
+    TC_VALIDATE(src, "tc_pack_raw src");
+    if (!dst_dev) return fail(TC_ERR_INVALID, "tc_pack_raw: null destination");
+    if (type < TC_U8 || type > TC_F32 || (channels != 3 && channels != 4)) return fail(TC_ERR_INVALID, "tc_pack_raw: %d x type %d", channels, type);
+    const size_t total = (size_t)src->w * src->h;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (channels == 4) k_pack_raw<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(dst_dev, view(src), type);
+    else k_pack_raw<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(dst_dev, view(src), type);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_pack_raw launch");
 }
 
 int tc_dissolve(const tc_image* dst, const tc_image* from, const tc_image* to, double value, tc_stream s)

@@ -4,7 +4,8 @@
 // frames are sharded in contiguous blocks over the GPUs and written in order.  Encoders
 // (FFmpeg, PNG, y4m) are host-side writers outside the hot path.
 //
-//   toucan-render input.otio output.raw|- [-gpus N] [-print_start] [-print_duration] [-print_rate] [-print_size]
+//   toucan-render input.otio output.raw|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32] [-gpus N]
+//                 [-print_start] [-print_duration] [-print_rate] [-print_size]
 #include <toucanRender/FrameScheduler.h>
 #include <toucanRender/TimelineWrapper.h>
 #include <toucanRender/Util.h>
@@ -19,13 +20,14 @@ int main(int argc, char** argv)
 {
     try
     {
-        std::string input, output;
+        std::string input, output, raw;
         int gpus = 1;
         bool printStart = false, printDuration = false, printRate = false, printSize = false;
         for (int i = 1; i < argc; ++i)
         {
             const std::string a = argv[i];
             if (a == "-gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
+            else if (a == "-raw" && i + 1 < argc) raw = argv[++i];
             else if (a == "-print_start") printStart = true;
             else if (a == "-print_duration") printDuration = true;
             else if (a == "-print_rate") printRate = true;
@@ -35,7 +37,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-gpus N] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format] [-gpus N] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 
@@ -67,6 +69,10 @@ int main(int argc, char** argv)
         options.devices.clear();
         for (int i = 0; i < std::max(1, gpus); ++i) options.devices.push_back(i);
         options.pluginSearchPath = getOpenFXPluginPaths(argv[0]);
+        if (!raw.empty() && !parseRawFormat(raw, options.rawType, options.rawChannels))
+        {
+            throw std::runtime_error("Cannot find the given raw format");
+        }
         FrameScheduler scheduler(context, timelineWrapper, options);
         scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec& spec)
         {

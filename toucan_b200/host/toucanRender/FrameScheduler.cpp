@@ -10,6 +10,23 @@
 
 namespace toucan
 {
+    bool parseRawFormat(const std::string& name, int& type, int& channels)
+    {
+        static const struct { const char* name; int type; int channels; } specs[] = {
+            { "rgb24", TC_U8, 3 }, { "rgba", TC_U8, 4 }, { "rgb48", TC_U16, 3 }, { "rgba64", TC_U16, 4 },
+            { "rgbaf16", TC_F16, 4 }, { "rgbf32", TC_F32, 3 }, { "rgbaf32", TC_F32, 4 } };
+        for (const auto& spec : specs)
+        {
+            if (name == spec.name)
+            {
+                type = spec.type;
+                channels = spec.channels;
+                return true;
+            }
+        }
+        return false;
+    }
+
     std::pair<int, int> frameBlock(int first, int last, int index, int count)
     {
         const int n = last > first ? last - first : 0;
@@ -149,6 +166,15 @@ namespace toucan
                     }
                     slot.spec = slot.image.spec();
                     slot.frame = frame;
+                    void* packed = nullptr;
+                    if (_options.rawType >= 0 && slot.spec.format != _options.rawType && slot.spec.image_bytes() > 0)
+                    {
+                        // output conversion on the device: the download moves the writer's bytes
+                        const tc_image view = slot.image.view();
+                        slot.spec = ImageSpec(slot.spec.width, slot.spec.height, _options.rawChannels, _options.rawType);
+                        tcCheck(tc_malloc(&packed, slot.spec.image_bytes(), DeviceContext::stream()), "tc_malloc");
+                        tcCheck(tc_pack_raw(packed, &view, _options.rawType, _options.rawChannels, DeviceContext::stream()), "tc_pack_raw");
+                    }
                     const size_t bytes = slot.spec.image_bytes();
                     if (bytes > slot.capacity)
                     {
@@ -162,7 +188,11 @@ namespace toucan
                         // download on the copy stream so the next frame's uploads and kernels overlap it
                         tcCheck(tc_event_record(rendered, DeviceContext::stream()), "tc_event_record");
                         tcCheck(tc_stream_wait_event(copyStream, rendered), "tc_stream_wait_event");
-                        tcCheck(tc_download(slot.pinned, slot.image.data(), bytes, copyStream), "tc_download");
+                        tcCheck(tc_download(slot.pinned, packed ? packed : slot.image.data(), bytes, copyStream), "tc_download");
+                    }
+                    if (packed)
+                    {
+                        tcCheck(tc_free(packed, copyStream), "tc_free"); // stream-ordered after the download
                     }
                     tcCheck(tc_event_record(slot.done, copyStream), "tc_event_record");
                     {

@@ -22,7 +22,16 @@ namespace toucan
         std::vector<int> devices = { 0 };
         std::vector<std::filesystem::path> pluginSearchPath;
         int framesInFlight = 2; //!< pinned ring slots per GPU
+        //! Raw output format (bin/toucan-render/App.cpp:26-35 rawSpecs): when rawType >= 0 and the
+        //! frame's storage type differs from it, the frame is converted ON THE DEVICE to
+        //! rawChannels x rawType before the download (the reference converts on the host with
+        //! ImageBufAlgo::paste, and -- like here -- writes the frame as is when the types match).
+        int rawType = -1;
+        int rawChannels = 4;
     };
+
+    //! "rgb24" | "rgba" | "rgb48" | "rgba64" | "rgbaf16" | "rgbf32" | "rgbaf32" -> (tc_type, channels)
+    bool parseRawFormat(const std::string&, int& type, int& channels);
 
     //! Contiguous block of frames [first, last) owned by worker `index` of `count`.
     std::pair<int, int> frameBlock(int first, int last, int index, int count);

@@ -283,9 +283,19 @@ extern "C"
     int tr_render_range(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
                         int frames_in_flight, tr_frame_callback callback, void* user)
     {
+        return tr_render_range_raw(timeline, plugin_dir, devices, n_devices, first, last, frames_in_flight, nullptr, callback, user);
+    }
+
+    int tr_render_range_raw(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
+                            int frames_in_flight, const char* raw_format, tr_frame_callback callback, void* user)
+    {
         if (!timeline || !callback) return fail("tr_render_range: null");
         return guarded([&] {
             FrameSchedulerOptions options;
+            if (raw_format && *raw_format && !parseRawFormat(raw_format, options.rawType, options.rawChannels))
+            {
+                return fail("Cannot find the given raw format");
+            }
             options.devices.clear();
             for (int i = 0; i < n_devices; ++i) options.devices.push_back(devices ? devices[i] : i);
             if (options.devices.empty()) options.devices.push_back(0);
@@ -294,7 +304,7 @@ extern "C"
             if (frames_in_flight > 0) options.framesInFlight = frames_in_flight;
             FrameScheduler scheduler(timeline->context, timeline->wrapper, options);
             scheduler.run(first, last, [&](int frame, const void* pixels, const ImageSpec& spec) {
-                callback(user, frame, pixels, spec.width, spec.height, spec.format);
+                callback(user, frame, pixels, spec.width, spec.height, spec.format | (spec.nchannels == 3 ? 0x100 : 0));
             });
             return 0;
         });

@@ -43,6 +43,8 @@ _SIGS = {
 }
 FRAME_CALLBACK = ctypes.CFUNCTYPE(None, _VP, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int)
 _SIGS["tr_render_range"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, FRAME_CALLBACK, _VP]
+_SIGS["tr_render_range_raw"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+                                FRAME_CALLBACK, _VP]
 EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion"})
 
 
@@ -204,21 +206,24 @@ class Timeline:
                                                  ctypes.byref(t)), "tr_timeline_render_resident")
         return p.value, w.value, h.value, t.value
 
-    def render_range(self, first: int, last: int, writer, devices=(0,), frames_in_flight: int = 2, plugin_dir: str = PLUGIN_DIR):
+    def render_range(self, first: int, last: int, writer, devices=(0,), frames_in_flight: int = 2, plugin_dir: str = PLUGIN_DIR,
+                     raw_format: str | None = None):
         """toucan::FrameScheduler: frames [first, last) on `devices`, writer(frame, ndarray) called in
-        order on this thread; the array aliases pinned memory valid only during the call."""
+        order on this thread; the array aliases pinned memory valid only during the call.  raw_format:
+        device-side output conversion ("rgb24", "rgba", "rgb48", "rgba64", "rgbaf16", "rgbf32", "rgbaf32")."""
         def cb(_user, frame, pixels, w, h, t):
             if w > 0 and h > 0 and pixels:
-                dt = np.dtype(_NP_OF[t])
-                buf = (ctypes.c_char * (w * h * 4 * dt.itemsize)).from_address(pixels)
-                writer(frame, np.frombuffer(buf, dtype=dt).reshape(h, w, 4))
+                nch = 3 if t & 0x100 else 4
+                dt = np.dtype(_NP_OF[t & 0xff])
+                buf = (ctypes.c_char * (w * h * nch * dt.itemsize)).from_address(pixels)
+                writer(frame, np.frombuffer(buf, dtype=dt).reshape(h, w, nch))
             else:
                 writer(frame, np.zeros((0, 0, 4), np.uint8))
 
         c_cb = FRAME_CALLBACK(cb)
         devs = (ctypes.c_int * len(devices))(*devices)
-        _check(lib().tr_render_range(self._t, plugin_dir.encode(), devs, len(devices), int(first), int(last), int(frames_in_flight), c_cb,
-                                     None), "tr_render_range")
+        _check(lib().tr_render_range_raw(self._t, plugin_dir.encode(), devs, len(devices), int(first), int(last), int(frames_in_flight),
+                                         raw_format.encode() if raw_format else None, c_cb, None), "tr_render_range")
 
     def close(self):
         if self._t:
