@@ -158,10 +158,17 @@ struct RotParams {
 
 constexpr int ROT_MAX_TAPS = 16;
 
+// MAXT = taps per axis the footprint can span: 8 for the default lanczos3 (width 6), 16 otherwise
+template <int MAXT>
 __global__ void __launch_bounds__(256) k_rotate(const Img src, const Img dst, const __grid_constant__ RotParams P)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    constexpr int ROT_MAX_TAPS = MAXT;
+    // a warp covers an 8 x 4 pixel block, not a 32 x 1 row: under rotation a row of the output is a
+    // diagonal of the source (32 cache lines per tap), a compact block maps to a compact footprint
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int y = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
     if (x >= dst.w || y >= dst.h) return;
     const float px = __fadd_rn((float)x, 0.5f), py = __fadd_rn((float)y, 0.5f);
     const float s = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[0]), __fmul_rn(py, P.m[3])), P.m[6]);
@@ -290,7 +297,8 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
     const float mi[9] = { i00, i01, 0.0f, i10, i11, 0.0f, i20, i21, 1.0f };
     memcpy(P.m, mi, sizeof(mi));
     dim3 block(32, 8), grid((dst->w + 31) / 32, (dst->h + 7) / 8);
-    k_rotate<<<grid, block, 0, (cudaStream_t)s>>>(view(src), view(dst), P);
+    if (P.fw + 2.0f <= 8.0f) k_rotate<8><<<grid, block, 0, (cudaStream_t)s>>>(view(src), view(dst), P);
+    else k_rotate<16><<<grid, block, 0, (cudaStream_t)s>>>(view(src), view(dst), P);
     count_launch();
     return check_cuda(cudaGetLastError(), "k_rotate launch");
 }
