@@ -71,6 +71,7 @@ int tc_type_merge(int a, int b);
    lib/toucanRender/ImageEffect.cpp:93,108,126).  Memory is NOT zeroed. */
 int tc_malloc(void** out, size_t bytes, tc_stream s);
 int tc_free(void* p, tc_stream s);
+int tc_free_sync(void* p); /* cudaFree: for memory whose stream no longer exists */
 int tc_pool_trim(void);
 /* pinned host staging + copies (upload of decoded frames: Read.cpp:64-101; download
    for the writers: bin/toucan-render/App.cpp:238-262) */

@@ -49,6 +49,9 @@ int tr_timeline_media_path(const tr_timeline* timeline, const char* url, char* o
    The pixels are BORROWED: host memory is uploaded on every render that reads it, device
    memory (device != 0) is used in place.  Must be called before tr_timeline_prepare. */
 int tr_timeline_set_media(tr_timeline* timeline, const char* path, const void* pixels, int device, int width, int height, int type);
+/* Device source cache: keep up to `bytes` of uploaded host frames resident per GPU (LRU), so a still
+   is uploaded once instead of on every frame.  0 (default) = upload on every frame. */
+int tr_timeline_set_source_cache(tr_timeline* timeline, size_t bytes);
 /* Build the ImageGraph (reads the first clip's media information). */
 int tr_timeline_prepare(tr_timeline* timeline);
 /* start/rate of the first frame, number of frames (App.cpp:222-224), image size and tc_type. */

@@ -142,3 +142,26 @@ def test_builtin_png_reader_matches_harness_decode(built):
     for f in ["Counter.3.png", "Letter_A.png", "Gradient.png"]:
         p = os.path.join(TL.DATA, f)
         assert np.array_equal(render.decode_png(p), media.decode(p)), f
+
+
+def test_colour_matrices_against_published_aces_values():
+    # Published ACES conversion matrices (Bradford-adapted, D65 -> ACES white): the oracle derives its
+    # matrices from primaries + Bradford, these are the values tabulated in the ACES documentation
+    # and reproduced by OCIO's built-in config to 6 decimals.
+    srgb_to_ap1 = np.array([[0.613097, 0.339523, 0.047379], [0.070194, 0.916354, 0.013452], [0.020616, 0.109570, 0.869815]])
+    srgb_to_ap0 = np.array([[0.439633, 0.382989, 0.177378], [0.089776, 0.813439, 0.096784], [0.017541, 0.111547, 0.870912]])
+    assert np.abs(O.color_matrix("rec709", "ap1") - srgb_to_ap1).max() < 2e-5
+    assert np.abs(O.color_matrix("rec709", "ap0") - srgb_to_ap0).max() < 2e-4
+    ap0_to_ap1 = np.array([[1.4514393161, -0.2365107469, -0.2149285693], [-0.0765537734, 1.1762296998, -0.0996759264],
+                           [0.0083161484, -0.0060324498, 0.9977163014]])
+    assert np.abs(O.color_matrix("ap0", "ap1") - ap0_to_ap1).max() < 1e-5
+    # round trips are the identity
+    for a, b in [("rec709", "p3d65"), ("rec2020", "ap1")]:
+        assert np.abs(O.color_matrix(a, b).astype(np.float64) @ O.color_matrix(b, a).astype(np.float64) - np.eye(3)).max() < 1e-5
+    # ACEScct (S-2016-001): continuous at the break point, 0.18 grey -> 0.4135884
+    img = np.zeros((1, 2, 4), np.float32)
+    img[0, 0, :3] = 0.18
+    img[0, 1, :3] = 0.0078125
+    out = O.colorconvert(img, "ACEScg", "ACEScct")
+    assert abs(float(out[0, 0, 0]) - 0.4135884) < 1e-5
+    assert abs(float(out[0, 1, 0]) - (10.5402377416545 * 0.0078125 + 0.0729055341958355)) < 1e-6

@@ -266,3 +266,27 @@ def test_raw_output_formats_on_device(cuda, fmt, dtype, nch):
         assert g.dtype == want.dtype and g.shape == want.shape, (fmt, g.dtype, g.shape, want.dtype, want.shape)
         assert np.array_equal(g, want), fmt
     tl.close()
+
+
+def test_device_source_cache(host):
+    """with the source cache on, a host still is uploaded once; results are unchanged and
+    the least recently used frames are evicted beyond the budget."""
+    import ctypes
+
+    from toucan_b200 import capi
+
+    name = "CompositeTracks.otio"
+    want = {}
+    tl = TL.open_timeline(name)
+    for rec in GOLD[name]["frames"][:6]:
+        want[rec["time"]] = tl.render(host, rec["time"], max_bytes=1280 * 720 * 16)
+    tl.close()
+    tl = TL.open_timeline(name)
+    tl.set_source_cache(3 * 1280 * 720 * 4)  # room for three 720p u8 frames
+    for rep in range(2):
+        for rec in GOLD[name]["frames"][:6]:
+            got = tl.render(host, rec["time"], max_bytes=1280 * 720 * 16)
+            assert np.array_equal(got, want[rec["time"]]), (rep, rec["time"])
+            assert hashlib.sha256(got.tobytes()).hexdigest() == rec["sha256"]
+    tl.set_source_cache(0)
+    tl.close()

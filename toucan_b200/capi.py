@@ -66,6 +66,7 @@ _SIGS = {
     "tc_stream_sync": [_S],
     "tc_malloc": [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t, _S],
     "tc_free": [ctypes.c_void_p, _S],
+    "tc_free_sync": [ctypes.c_void_p],
     "tc_upload": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _S],
     "tc_download": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _S],
     "tc_host_alloc": [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t],

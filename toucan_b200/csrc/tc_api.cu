@@ -189,6 +189,12 @@ int tc_free(void* p, tc_stream s)
     TC_CUDA(cudaFreeAsync(p, (cudaStream_t)s));
     return TC_OK;
 }
+int tc_free_sync(void* p)
+{
+    if (!p) return TC_OK;
+    TC_CUDA(cudaFree(p));
+    return TC_OK;
+}
 int tc_pool_trim(void)
 {
     int dev = 0;

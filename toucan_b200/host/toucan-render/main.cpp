@@ -65,6 +65,8 @@ int main(int argc, char** argv)
         {
             throw std::runtime_error("Cannot open: " + output);
         }
+        // stills and sequence frames are decoded once and kept resident (up to 8 GiB per GPU)
+        timelineWrapper->getMediaStore()->setDeviceCacheBytes(size_t(8) << 30);
         FrameSchedulerOptions options;
         options.devices.clear();
         for (int i = 0; i < std::max(1, gpus); ++i) options.devices.push_back(i);

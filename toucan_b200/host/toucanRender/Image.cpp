@@ -82,7 +82,9 @@ namespace toucan
         tc_stream stream = nullptr;
         ~Buffer()
         {
-            if (p) tc_free(p, stream);
+            // stream-ordered release; if that stream is gone (a cached frame outliving its worker)
+            // fall back to a synchronous free
+            if (p && tc_free(p, stream) != TC_OK) tc_free_sync(p);
         }
     };
 

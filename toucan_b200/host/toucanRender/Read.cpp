@@ -37,6 +37,62 @@ namespace toucan
         _frames.clear();
     }
 
+    void MediaStore::setDeviceCacheBytes(size_t bytes)
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        _cacheLimit = bytes;
+        if (0 == bytes) _cache.clear();
+    }
+
+    size_t MediaStore::getDeviceCacheBytes() const
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        return _cacheLimit;
+    }
+
+    bool MediaStore::getCached(int device, const std::string& path, Image& out)
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        for (auto i = _cache.begin(); i != _cache.end(); ++i)
+        {
+            if (i->device == device && i->path == path)
+            {
+                out = i->image;
+                _cache.splice(_cache.begin(), _cache, i);
+                return true;
+            }
+        }
+        return false;
+    }
+
+    void MediaStore::putCached(int device, const std::string& path, const Image& image)
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        if (0 == _cacheLimit) return;
+        _cache.push_front(Cached{ device, path, image });
+        // evict the least recently used frames of this device beyond the budget
+        size_t bytes = 0;
+        for (auto i = _cache.begin(); i != _cache.end();)
+        {
+            if (i->device == device)
+            {
+                bytes += i->image.spec().image_bytes();
+                if (bytes > _cacheLimit && i != _cache.begin())
+                {
+                    i = _cache.erase(i);
+                    continue;
+                }
+            }
+            ++i;
+        }
+    }
+
+    void MediaStore::dropCached()
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        _cache.clear();
+    }
+
     const std::shared_ptr<MediaStore>& MediaStore::global()
     {
         static const std::shared_ptr<MediaStore> store = std::make_shared<MediaStore>();
@@ -70,7 +126,7 @@ namespace toucan
 
     const OTIO_NS::TimeRange& IReadNode::getTimeRange() const { return _timeRange; }
 
-    Image IReadNode::_toDevice(const MediaFrame& frame) const
+    Image IReadNode::_toDevice(const MediaFrame& frame, const std::shared_ptr<MediaStore>& store, const std::string& path) const
     {
         if (frame.nchannels != 4)
         {
@@ -81,6 +137,18 @@ namespace toucan
         if (frame.device)
         {
             return Image::wrap(frame.device, spec);
+        }
+        if (store && store->getDeviceCacheBytes() > 0)
+        {
+            const int device = DeviceContext::device();
+            Image cached;
+            if (store->getCached(device, path, cached) && cached.spec().image_bytes() == spec.image_bytes())
+            {
+                return cached;
+            }
+            cached = Image::upload(frame.host, spec);
+            store->putCached(device, path, cached);
+            return cached;
         }
         return Image::upload(frame.host, spec);
     }
@@ -117,7 +185,7 @@ namespace toucan
         {
             return Image();
         }
-        return _toDevice(frame);
+        return _toDevice(frame, _store, _path.string());
     }
 
     std::vector<std::string> ImageReadNode::getExtensions()
@@ -175,7 +243,7 @@ namespace toucan
         {
             return Image();
         }
-        return _toDevice(frame);
+        return _toDevice(frame, _store, url);
     }
 
     std::vector<std::string> SequenceReadNode::getExtensions()

@@ -10,6 +10,7 @@
 #include <toucanRender/ImageNode.h>
 
 #include <filesystem>
+#include <list>
 #include <map>
 #include <mutex>
 
@@ -39,9 +40,27 @@ namespace toucan
         //! Process-wide default store.
         static const std::shared_ptr<MediaStore>& global();
 
+        //! Device source cache: keep up to `bytes` of uploaded frames resident per
+        //! GPU so a still is uploaded once instead of on every frame (the reference re-decodes
+        //! its media on every exec(), lib/toucanRender/Read.cpp:64-101).  0 = off (the default:
+        //! host frames are uploaded on every exec()).  Least recently used frames are evicted.
+        void setDeviceCacheBytes(size_t bytes);
+        size_t getDeviceCacheBytes() const;
+        bool getCached(int device, const std::string& path, Image&);
+        void putCached(int device, const std::string& path, const Image&);
+        void dropCached();
+
     private:
-        std::mutex _mutex;
+        struct Cached
+        {
+            int device = 0;
+            std::string path;
+            Image image;
+        };
+        mutable std::mutex _mutex;
         std::map<std::string, MediaFrame> _frames;
+        size_t _cacheLimit = 0;
+        std::list<Cached> _cache; // most recently used first
     };
 
     //! Base class for read nodes.
@@ -57,7 +76,7 @@ namespace toucan
         const OTIO_NS::TimeRange& getTimeRange() const;
 
     protected:
-        Image _toDevice(const MediaFrame&) const;
+        Image _toDevice(const MediaFrame&, const std::shared_ptr<MediaStore>&, const std::string& path) const;
 
         ImageSpec _spec;
         OTIO_NS::TimeRange _timeRange;

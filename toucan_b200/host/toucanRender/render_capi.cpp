@@ -202,6 +202,13 @@ extern "C"
         return 0;
     }
 
+    int tr_timeline_set_source_cache(tr_timeline* timeline, size_t bytes)
+    {
+        if (!timeline) return fail("tr_timeline_set_source_cache: null");
+        timeline->store->setDeviceCacheBytes(bytes);
+        return 0;
+    }
+
     int tr_timeline_prepare(tr_timeline* timeline)
     {
         if (!timeline) return fail("tr_timeline_prepare: null");

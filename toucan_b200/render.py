@@ -35,6 +35,7 @@ _SIGS = {
     "tr_timeline_media_path": [_VP, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t],
     "tr_timeline_set_media": [_VP, ctypes.c_char_p, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int],
     "tr_timeline_prepare": [_VP],
+    "tr_timeline_set_source_cache": [_VP, ctypes.c_size_t],
     "tr_timeline_info": [_VP, _DP, _DP, _IP, _IP, _IP, _IP],
     "tr_timeline_describe": [_VP, _VP, ctypes.c_double, ctypes.c_char_p, ctypes.c_size_t],
     "tr_timeline_render": [_VP, _VP, ctypes.c_double, _VP, ctypes.c_size_t, _IP, _IP, _IP],
@@ -167,6 +168,10 @@ class Timeline:
             del torch
         self._keep.append(frame)
         _check(lib().tr_timeline_set_media(self._t, path.encode(), ptr, dev, frame.shape[1], frame.shape[0], t), "tr_timeline_set_media")
+
+    def set_source_cache(self, nbytes: int):
+        """Keep up to `nbytes` of uploaded host frames resident per GPU (0 = upload on every frame)."""
+        _check(lib().tr_timeline_set_source_cache(self._t, int(nbytes)), "tr_timeline_set_source_cache")
 
     def prepare(self):
         _check(lib().tr_timeline_prepare(self._t), "tr_timeline_prepare")
