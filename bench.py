@@ -151,6 +151,21 @@ def cpu_arm(cfg, frames, warmup, target_step_s=None):
     return fps, dt, cores, f"{n} frames x rows 0..{h - 1} of {cfg['height']} (1/{div} of each {cfg['width']}x{cfg['height']} frame), time scaled x{div}"
 
 
+def measured_traffic(nsrc_per_launch, tracks):
+    """DRAM bytes per launch of the fused stack kernel from the committed ncu capture, averaged over this
+    run's mix of plain (n sources = tracks) and transition (2 x tracks) frames; None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_stack_traffic.json")) as f:
+            t = json.load(f)
+        plain = sum(1 for n in nsrc_per_launch if n == tracks)
+        trans = sum(1 for n in nsrc_per_launch if n == 2 * tracks)
+        if plain + trans != len(nsrc_per_launch) or tracks != 10:
+            return None
+        return (plain * t["plain_frame_bytes"] + trans * t["transition_frame_bytes"]) / len(nsrc_per_launch)
+    except Exception:
+        return None
+
+
 def frames_for(rank, world, cfg, count):
     """Frames a rank renders, inside its own contiguous block.  The window starts in the middle of a clip
     and wraps at a multiple of half a clip, so every rank (and every multiple of 24 steps) sees the same
@@ -340,7 +355,9 @@ def run_ours(args, cfg):
                 "hbm_gbs_algorithmic": achieved * world,
                 "roofline": {"bound": "hbm", "kernel": "k_stack_f32", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
-                             "traffic": None,
+                             "traffic": measured_traffic(nsrc[args.warmup:], cfg["tracks"]) if args.scale == 1.0 else None,
+                             "traffic_source": "profiles/r01_stack_traffic.json (ncu dram__bytes_read+write per launch, plain / "
+                                               "transition frames, weighted by this run's frame mix)",
                              "algorithmic_bytes_per_launch": alg_bytes / args.steps,
                              "note": "bytes = (sources referenced + 1 output) x 530,841,600 B per frame; one launch per frame; "
                                      "rank-0-equivalent (max-over-ranks time)"},
