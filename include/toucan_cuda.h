@@ -113,6 +113,9 @@ int tc_unsharp_mask(const tc_image* dst, const tc_image* src, const char* kernel
 /* colorconvert(out, src, from, to, premult=0, key, val, cfg)   ColorPlugin.cpp:220-248.
    Baked decode-curve -> 3x3 -> encode-curve for the colour spaces of OCIO's built-in config. */
 int tc_color_convert(const tc_image* dst, const tc_image* src, const char* fromspace, const char* tospace, tc_stream s);
+/* same with OIIO's `unpremult` flag (toucan's "premult" parameter, ColorPlugin.cpp:241): pixels with
+   alpha != 0 are divided by alpha before the transform and multiplied by it afterwards */
+int tc_color_convert2(const tc_image* dst, const tc_image* src, const char* fromspace, const char* tospace, int unpremult, tc_stream s);
 int tc_color_space_known(const char* name);
 /* premult(out, src)                                       ColorPlugin.cpp:286 */
 int tc_premult(const tc_image* dst, const tc_image* src, tc_stream s);

@@ -545,7 +545,9 @@ class ImageGraph:
             if name == "toucan:Rotate":
                 return O.rotate(canvas, _dbl(meta, "angle", 0.0), _str(meta, "filter_name", ""), _dbl(meta, "filter_width", 0.0))
             if name == "toucan:ColorConvert":
-                return O.colorconvert(canvas, _str(meta, "fromspace", ""), _str(meta, "tospace", ""))
+                pm = meta.get("premult")
+                return O.colorconvert(canvas, _str(meta, "fromspace", ""), _str(meta, "tospace", ""),
+                                      unpremult=bool(pm) if isinstance(pm, bool) else False)
             if name == "toucan:Premult":
                 return O.premult(canvas)
             if name == "toucan:Unpremult":

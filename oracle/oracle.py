@@ -335,7 +335,7 @@ def color_matrix(from_prim, to_prim):
     return (np.linalg.inv(_to_ap0(to_prim)) @ _to_ap0(from_prim)).astype(np.float32)
 
 
-def colorconvert(src, fromspace, tospace):
+def colorconvert(src, fromspace, tospace, unpremult=False):
     """ColorConvertPlugin::_render -- ColorPlugin.cpp:200-250 with the effective premult flag 0
     (SURVEY 8b).  Unknown colour-space names make colorconvert() fail: the output buffer
     keeps its zero fill."""
@@ -346,6 +346,6 @@ def colorconvert(src, fromspace, tospace):
     ci, pi, fp = COLOR_SPACES[fromspace]
     co, po, tp = COLOR_SPACES[tospace]
     m = np.ascontiguousarray(color_matrix(fp, tp), dtype=np.float32)
-    lib().o_colorconvert(ctypes.byref(_img(out)), ctypes.byref(_img(src)), ci, ctypes.c_float(pi),
-                         m.ctypes.data_as(ctypes.c_void_p), co, ctypes.c_float(po))
+    lib().o_colorconvert2(ctypes.byref(_img(out)), ctypes.byref(_img(src)), ci, ctypes.c_float(pi),
+                          m.ctypes.data_as(ctypes.c_void_p), co, ctypes.c_float(po), int(bool(unpremult)))
     return out

@@ -967,6 +967,31 @@ static inline float cc_curve(int id, int encode, float p, float x)
     default: return x;
     }
 }
+/* unpremult != 0 [V: OIIO colorconvert(..., unpremult, ...)]: pixels with alpha != 0 are divided by alpha
+   before the transform and multiplied by it afterwards (toucan passes its "premult" parameter here,
+   ColorPlugin.cpp:241; its effective default is 0). */
+void o_colorconvert2(oimg* dst, const oimg* src, int curve_in, float p_in, const float* m33, int curve_out, float p_out, int unpremult)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < dst->h; ++y)
+        for (int x = 0; x < dst->w; ++x) {
+            float p[NCH], l[3], o[NCH];
+            ldpx_black(src, x, y, p);
+            const float a = p[3];
+            const int un = unpremult && a != 0.0f && a != 1.0f;
+            if (un)
+                for (int c = 0; c < 3; ++c) p[c] = p[c] / a;
+            for (int c = 0; c < 3; ++c) l[c] = cc_curve(curve_in, 0, p_in, p[c]);
+            for (int c = 0; c < 3; ++c) {
+                float v = (m33[c * 3 + 0] * l[0] + m33[c * 3 + 1] * l[1]) + m33[c * 3 + 2] * l[2];
+                o[c] = cc_curve(curve_out, 1, p_out, v);
+            }
+            if (un)
+                for (int c = 0; c < 3; ++c) o[c] = o[c] * a;
+            o[3] = a;
+            stpx(dst, x, y, o);
+        }
+}
 void o_colorconvert(oimg* dst, const oimg* src, int curve_in, float p_in, const float* m33, int curve_out, float p_out)
 {
 #pragma omp parallel for schedule(static)

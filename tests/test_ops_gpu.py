@@ -159,6 +159,9 @@ def test_pointwise_filters(T, dt, size):
     assert_close(T.colorconvert(d, "sRGB - Texture", "ACEScg"), O.colorconvert(src, "sRGB - Texture", "ACEScg"), "cc3")
     assert_close(T.colorconvert(d, "ACEScc", "Linear Rec.2020"), O.colorconvert(src, "ACEScc", "Linear Rec.2020"), "cc4", rtol=1e-6)  # ACEScc decode reaches ~220: relative bar
     assert_close(T.colorconvert(d, "nope", "ACEScg"), O.colorconvert(src, "nope", "ACEScg"), "cc unknown")
+    # OIIO's unpremult flag (toucan's "premult" parameter): divide by alpha, convert, multiply back
+    assert_close(T.colorconvert(d, "sRGB - Texture", "ACEScg", unpremult=True), O.colorconvert(src, "sRGB - Texture", "ACEScg", unpremult=True),
+                 "cc unpremult", rtol=2e-6)
 
 
 @pytest.mark.parametrize("dt", NP_TYPES)

@@ -47,6 +47,7 @@ _SIGS = {
     "tc_saturate": [_IMG, _IMG, ctypes.c_float, _S],
     "tc_unsharp_mask": [_IMG, _IMG, ctypes.c_char_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, _S],
     "tc_color_convert": [_IMG, _IMG, ctypes.c_char_p, ctypes.c_char_p, _S],
+    "tc_color_convert2": [_IMG, _IMG, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, _S],
     "tc_premult": [_IMG, _IMG, _S],
     "tc_unpremult": [_IMG, _IMG, _S],
     "tc_crop": [_IMG, _IMG, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _S],

@@ -428,9 +428,16 @@ struct ColorConvertOp {
     int curve_in, curve_out;
     float p_in, p_out;
     float m[9];
+    int unpremult;
     TC_OP_1(s)
-    __device__ __forceinline__ float4 apply(const float4 p) const
+    __device__ __forceinline__ float4 apply(float4 p) const
     {
+        const bool un = unpremult && p.w != 0.0f && p.w != 1.0f;
+        if (un) {
+            p.x = __fdiv_rn(p.x, p.w);
+            p.y = __fdiv_rn(p.y, p.w);
+            p.z = __fdiv_rn(p.z, p.w);
+        }
         const float l0 = cc_curve(curve_in, 0, p_in, p.x), l1 = cc_curve(curve_in, 0, p_in, p.y),
                     l2 = cc_curve(curve_in, 0, p_in, p.z);
         float o[3];
@@ -439,6 +446,7 @@ struct ColorConvertOp {
             const float v = __fadd_rn(__fadd_rn(__fmul_rn(m[c * 3 + 0], l0), __fmul_rn(m[c * 3 + 1], l1)),
                                       __fmul_rn(m[c * 3 + 2], l2));
             o[c] = cc_curve(curve_out, 1, p_out, v);
+            if (un) o[c] = __fmul_rn(o[c], p.w);
         }
         return make_float4(o[0], o[1], o[2], p.w);
     }
@@ -717,10 +725,15 @@ int tc_unpremult(const tc_image* dst, const tc_image* src, tc_stream s)
 }
 int tc_color_convert(const tc_image* dst, const tc_image* src, const char* fromspace, const char* tospace, tc_stream s)
 {
+    return tc_color_convert2(dst, src, fromspace, tospace, 0, s);
+}
+int tc_color_convert2(const tc_image* dst, const tc_image* src, const char* fromspace, const char* tospace, int unpremult, tc_stream s)
+{
     TC_VALIDATE(dst, "tc_color_convert dst");
     TC_VALIDATE(src, "tc_color_convert src");
     ColorConvertOp op;
     op.s = make_src(src, dst);
+    op.unpremult = unpremult ? 1 : 0;
     if (!fromspace || !tospace ||
         !color_convert_setup(fromspace, tospace, &op.curve_in, &op.p_in, op.m, &op.curve_out, &op.p_out)) {
         // OIIO colorconvert() fails on an unknown colour space; the output keeps its zero fill

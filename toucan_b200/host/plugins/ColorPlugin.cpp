@@ -16,12 +16,13 @@ namespace toucan_ofx
             const std::string contextKey = p.getString("context_key", "");
             const std::string contextValue = p.getString("context_value", "");
             const std::string colorConfig = p.getString("color_config", "");
-            if (!colorConfig.empty() || !contextKey.empty() || premult)
+            (void)contextValue;
+            if (!colorConfig.empty() || !contextKey.empty())
             {
                 // Only OCIO's built-in config, baked per (from, to) pair, is in scope.
                 return TC_ERR_UNSUPPORTED;
             }
-            return tc_color_convert(&a.output, &a.source[0], fromSpace.c_str(), toSpace.c_str(), a.stream);
+            return tc_color_convert2(&a.output, &a.source[0], fromSpace.c_str(), toSpace.c_str(), premult, a.stream);
         }
 
         int premult(const RenderArgs& a, const Params&) { return tc_premult(&a.output, &a.source[0], a.stream); }

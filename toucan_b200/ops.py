@@ -111,8 +111,8 @@ def unsharp_mask(src, kernel, width, contrast, threshold):
     return _unary(lib().tc_unsharp_mask, "tc_unsharp_mask", src, kernel.encode(), float(width), float(contrast), float(threshold))
 
 
-def colorconvert(src, fromspace, tospace):
-    return _unary(lib().tc_color_convert, "tc_color_convert", src, fromspace.encode(), tospace.encode())
+def colorconvert(src, fromspace, tospace, unpremult=False):
+    return _unary(lib().tc_color_convert2, "tc_color_convert2", src, fromspace.encode(), tospace.encode(), int(bool(unpremult)))
 
 
 # transforms -----------------------------------------------------------------------------------
