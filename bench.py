@@ -203,6 +203,27 @@ def run_reference(args, cfg):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_cpus(torch, local):
+    """Run this rank (and the threads it starts) on the CPUs NVML reports as local to its GPU, so pinned
+    staging memory is first-touched on the GPU's NUMA node.  Best effort: silently skipped if NVML is absent."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
@@ -216,6 +237,8 @@ def run_ours(args, cfg):
         raise SystemExit("bench.py: no CUDA device visible; the render path has no CPU fallback")
     torch.cuda.set_device(local)
     capi.check(capi.lib().tc_set_device(local), "tc_set_device")
+    if world > 1:
+        bind_to_gpu_cpus(torch, local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
