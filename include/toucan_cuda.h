@@ -158,6 +158,17 @@ int tc_convert(const tc_image* dst, const tc_image* src, tc_stream s);
    channels: 3 (alpha dropped) or 4. */
 int tc_pack_raw(void* dst_dev, const tc_image* src, int type, int channels, tc_stream s);
 
+/* y4m output conversion on the device                     bin/toucan-render/App.cpp:37-43,340-485
+   The reference pastes the frame into a u8/u16 RGB(A) buffer (ImageBufAlgo::paste) and runs
+   libswscale (FFmpeg 8.0, SWS_FAST_BILINEAR) RGB24->YUV422P | RGB24->YUV444P | RGBA->YUVA444P |
+   RGB48->YUV444P16, then writes the planes back to back after "FRAME\n".  tc_rgb_to_y4m writes
+   exactly those bytes (Y, U, V[, A] planes, tightly packed, little-endian for 444p16) into
+   dst_dev, which holds tc_y4m_frame_bytes(format, w, h) bytes.  Bit-exact with libswscale
+   9.1.100 on x86-64.  Even widths >= 8 only. */
+enum { TC_Y4M_422 = 0, TC_Y4M_444 = 1, TC_Y4M_444ALPHA = 2, TC_Y4M_444P16 = 3 };
+size_t tc_y4m_frame_bytes(int format, int w, int h);
+int tc_rgb_to_y4m(void* dst_dev, const tc_image* src, int format, tc_stream s);
+
 /* ---- fused track stack (cross-node fusion of the hot chain) ------------------------
  * One pass over the output for a whole stack of tracks:
  *   acc = background colour

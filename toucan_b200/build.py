@@ -36,6 +36,7 @@ CU_FILES = {
     "tc_resample.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "tc_conv.cu": [],
     "tc_stack.cu": [],
+    "tc_y4m.cu": [],
 }
 CPP_KERNEL_FILES = ["tc_tables.cpp"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"),

@@ -14,6 +14,7 @@ LIB_DIR = os.path.join(_HERE, "lib")
 CUDA_LIB = os.path.join(LIB_DIR, "libtoucan_cuda.so")
 
 U8, U16, F16, F32 = 0, 1, 2, 3
+Y4M_FORMATS = {"422": 0, "444": 1, "444alpha": 2, "444p16": 3}  # bin/toucan-render/App.cpp:37-43
 TYPE_NAMES = {U8: "u8", U16: "u16", F16: "half", F32: "float"}
 
 
@@ -61,6 +62,7 @@ _SIGS = {
     "tc_paste_on_black": [_IMG, ctypes.c_int, ctypes.c_int, _IMG, _S],
     "tc_convert": [_IMG, _IMG, _S],
     "tc_pack_raw": [ctypes.c_void_p, _IMG, ctypes.c_int, ctypes.c_int, _S],
+    "tc_rgb_to_y4m": [ctypes.c_void_p, _IMG, ctypes.c_int, _S],
     "tc_stack_f32": [_IMG, _F4, ctypes.POINTER(tc_stack_layer), ctypes.c_int, _S],
     "tc_set_device": [ctypes.c_int],
     "tc_device_count": [ctypes.POINTER(ctypes.c_int)],
@@ -83,7 +85,7 @@ _SIGS = {
 
 # every symbol include/toucan_cuda.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(set(_SIGS) | {"tc_version", "tc_last_error", "tc_stream_create", "tc_stream_destroy", "tc_type_size",
-                               "tc_image_bytes", "tc_pool_trim", "tc_memset", "tc_launch_count"})
+                               "tc_image_bytes", "tc_pool_trim", "tc_memset", "tc_launch_count", "tc_y4m_frame_bytes"})
 
 
 def lib() -> ctypes.CDLL:
@@ -101,6 +103,8 @@ def lib() -> ctypes.CDLL:
         _lib.tc_launch_count.restype = ctypes.c_ulonglong
         _lib.tc_type_size.restype = ctypes.c_size_t
         _lib.tc_image_bytes.restype = ctypes.c_size_t
+        _lib.tc_y4m_frame_bytes.restype = ctypes.c_size_t
+        _lib.tc_y4m_frame_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return _lib
 
 

@@ -175,6 +175,30 @@ def convert(src, t, size=None):
     return out
 
 
+def y4m_planes(buf, fmt, w, h):
+    """Split the bytes of one y4m frame (host or device uint8 tensor / numpy array) into its planes."""
+    cw = (w + 1) // 2 if fmt == "422" else w
+    if fmt == "444p16":
+        buf = buf.view(torch.uint16) if isinstance(buf, torch.Tensor) else buf.view("<u2")
+    shapes = [(h, w), (h, cw), (h, cw)] + ([(h, w)] if fmt == "444alpha" else [])
+    out, o = [], 0
+    for sh in shapes:
+        n = sh[0] * sh[1]
+        out.append(buf[o:o + n].reshape(sh))
+        o += n
+    return out
+
+
+def rgb_to_y4m(src, fmt):
+    """tc_rgb_to_y4m: the frame's y4m bytes (App.cpp:340-485) as a flat uint8 device tensor."""
+    h, w = src.shape[:2]
+    f = capi.Y4M_FORMATS[fmt]
+    n = int(lib().tc_y4m_frame_bytes(f, w, h))
+    out = torch.empty((n,), dtype=torch.uint8, device=src.device)
+    check(lib().tc_rgb_to_y4m(ctypes.c_void_p(out.data_ptr()), _B(img(src)), f, _stream()), "tc_rgb_to_y4m")
+    return out
+
+
 def stack_f32(w, h, background, layers, out=None):
     """layers: list of (src_a, src_b|None, radius_a, radius_b, value), bottom track first."""
     if out is None:
