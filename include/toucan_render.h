@@ -84,6 +84,15 @@ int tr_render_range(tr_timeline* timeline, const char* plugin_dir, const int* de
 int tr_render_range_raw(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
                         int frames_in_flight, const char* raw_format, tr_frame_callback callback, void* user);
 
+/* Same with the output stage of `toucan-render - -y4m <format>` (App.cpp:340-485) on the device:
+   y4m_format = "422" | "444" | "444alpha" | "444p16".  Every frame is converted to the planar YUV bytes the
+   reference writes after "FRAME\n" (Y, U, V[, A] planes back to back; tc_y4m_frame_bytes() of them) and only
+   those are downloaded; the callback's `type` is 0x200 | TC_Y4M_*. */
+int tr_render_range_y4m(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
+                        int frames_in_flight, const char* y4m_format, tr_frame_callback callback, void* user);
+/* The stream header of App.cpp:302-338, NUL-terminated, into out[capacity]. */
+int tr_y4m_header(int width, int height, double rate, const char* y4m_format, char* out, size_t capacity);
+
 /* The scheduler's partition: frames [first, last) -> the contiguous block [*lo, *hi) owned by
    worker `index` of `count` (ceil(N / G) frames per GPU). */
 void tr_frame_block(int first, int last, int index, int count, int* lo, int* hi);

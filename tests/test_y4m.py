@@ -171,3 +171,55 @@ def test_kernel_rejects():
         ops.rgb_to_y4m(torch.zeros((4, 9, 4), dtype=torch.uint8, device="cuda"), "422")
     with pytest.raises(capi.TcError):
         ops.rgb_to_y4m(torch.zeros((4, 6, 4), dtype=torch.uint8, device="cuda"), "444")
+
+
+# ---- the output stage at timeline level ------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", Y.FORMATS)
+def test_timeline_y4m_output_on_device(cuda, fmt):
+    """`toucan-render - -y4m <fmt>` (App.cpp:340-485) through toucan::FrameScheduler: the bytes handed to the writer
+    are the oracle's paste + swscale of the oracle's frame (Transition.otio is in the bit-exact class)."""
+    from oracle import graph as G
+    from tests import media
+    from tests import timelines as TL
+
+    name = "Transition.otio"
+    tl = TL.open_timeline(name)
+    otl = G.Timeline(os.path.join(TL.DATA, name))
+    og = G.ImageGraph(otl, media.decode)
+    got = {}
+    tl.render_range(2, 5, lambda f, p: got.__setitem__(f, p.tobytes()), y4m_format=fmt)
+    for i, t in enumerate(otl.frames()[2:5]):
+        assert got[2 + i] == Y.frame_bytes(og.render(t), fmt), (fmt, i)
+    tl.close()
+
+
+@pytest.mark.gpu
+def test_toucan_render_cli_y4m(cuda, tmp_path):
+    """The command line renderer's y4m stream: header, then "FRAME\\n" + planes per frame."""
+    import subprocess
+
+    from oracle import graph as G
+    from tests import media
+    from tests import timelines as TL
+    from toucan_b200 import capi, render
+
+    exe = os.path.join(capi.LIB_DIR, "toucan-render")
+    out = tmp_path / "transition2.y4m"
+    name = "Transition2.otio"  # PNG media: the command line tool decodes with its built-in reader
+    r = subprocess.run([exe, os.path.join(TL.DATA, name), str(out), "-y4m", "422"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    data = open(out, "rb").read()
+    otl = G.Timeline(os.path.join(TL.DATA, name))
+    og = G.ImageGraph(otl, media.decode)
+    header = Y.header(1280, 720, 24.0, "422")
+    assert render.y4m_header(1280, 720, 24.0, "422") == header and render.y4m_header(8, 8, 29.97, "444p16") == Y.header(8, 8, 29.97, "444p16")
+    assert data.startswith(header)
+    frames = otl.frames()
+    per = 6 + 1280 * 720 * 2
+    assert len(data) == len(header) + per * len(frames)
+    for i in (0, len(frames) // 2, len(frames) - 1):
+        chunk = data[len(header) + i * per:len(header) + (i + 1) * per]
+        assert chunk[:6] == b"FRAME\n" and chunk[6:] == Y.frame_bytes(og.render(frames[i]), "422"), i
+    bad = subprocess.run([exe, os.path.join(TL.DATA, name), "-", "-y4m", "420"], capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 1 and "Cannot find the given y4m format" in bad.stdout

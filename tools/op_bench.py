@@ -9,6 +9,7 @@ Inputs rotate over enough buffers to exceed the 126 MB L2 between iterations.
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -54,6 +55,7 @@ def main():
     ap.add_argument("--size", default="3840x2160")
     ap.add_argument("--types", default="f32,f16,u8")
     ap.add_argument("--out", default="")
+    ap.add_argument("--ops", default="", help="only ops whose name contains this substring")
     args = ap.parse_args()
     w, h = [int(v) for v in args.size.split("x")]
     capi.check(capi.lib().tc_set_device(0), "tc_set_device")
@@ -75,6 +77,11 @@ def main():
                          "frac_of_measured_peak": round(gbs / peak, 3)})
             print(f"{name:28s} {tname:4s} {ms:8.3f} ms  {gbs:8.1f} GB/s  {gbs / peak:6.1%}", flush=True)
 
+        def run(name, frames, fn, iters=20, out_bytes=None):
+            if args.ops and args.ops not in name:
+                return
+            rec(name, frames, timeit(fn, iters=iters), out_bytes)
+
         lib = capi.lib()
         B = ops._B
         S = ops._stream
@@ -82,27 +89,32 @@ def main():
         def unary(fn, *extra):
             return lambda i: capi.check(fn(B(ops.img(outs[i % n])), B(ops.img(a[i % n])), *extra, S()), "op")
 
-        rec("fill", 1, timeit(lambda i: capi.check(lib.tc_fill(B(ops.img(outs[i % n])), capi.f4([0.1, 0.2, 0.3, 1.0]), S()), "fill")))
-        rec("checkers", 1, timeit(lambda i: capi.check(lib.tc_checkers(B(ops.img(outs[i % n])), 100, 100, capi.f4([0, 0, 0, 1]), capi.f4([1, 1, 1, 1]), S()), "ck")))
-        rec("noise gaussian", 1, timeit(lambda i: capi.check(lib.tc_noise(B(ops.img(outs[i % n])), b"gaussian", 0.5, 0.1, 0, 1, S()), "noise")))
-        rec("invert", 2, timeit(unary(lib.tc_invert)))
-        rec("flip", 2, timeit(unary(lib.tc_flip)))
-        rec("flop", 2, timeit(unary(lib.tc_flop)))
-        rec("pow 2.2", 2, timeit(unary(lib.tc_pow, 2.2)))
-        rec("saturate", 2, timeit(unary(lib.tc_saturate, 0.5)))
-        rec("color_map plasma", 2, timeit(unary(lib.tc_color_map, b"plasma")))
-        rec("premult", 2, timeit(unary(lib.tc_premult)))
-        rec("colorconvert lin709->ACEScct", 2, timeit(unary(lib.tc_color_convert, b"Linear Rec.709 (sRGB)", b"ACEScct")))
-        rec("blur r10", 2, timeit(unary(lib.tc_blur, 10.0)))
-        rec("blur r20", 2, timeit(unary(lib.tc_blur, 20.0)))
-        rec("unsharp r10", 2, timeit(unary(lib.tc_unsharp_mask, b"gaussian", 10.0, 1.0, 0.0)))
-        rec("rotate 45", 2, timeit(unary(lib.tc_rotate, 0.7853982, b"", 0.0), iters=5))
+        run("fill", 1, lambda i: capi.check(lib.tc_fill(B(ops.img(outs[i % n])), capi.f4([0.1, 0.2, 0.3, 1.0]), S()), "fill"))
+        run("checkers", 1, lambda i: capi.check(lib.tc_checkers(B(ops.img(outs[i % n])), 100, 100, capi.f4([0, 0, 0, 1]), capi.f4([1, 1, 1, 1]), S()), "ck"))
+        run("noise gaussian", 1, lambda i: capi.check(lib.tc_noise(B(ops.img(outs[i % n])), b"gaussian", 0.5, 0.1, 0, 1, S()), "noise"))
+        run("invert", 2, unary(lib.tc_invert))
+        run("flip", 2, unary(lib.tc_flip))
+        run("flop", 2, unary(lib.tc_flop))
+        run("pow 2.2", 2, unary(lib.tc_pow, 2.2))
+        run("saturate", 2, unary(lib.tc_saturate, 0.5))
+        run("color_map plasma", 2, unary(lib.tc_color_map, b"plasma"))
+        run("premult", 2, unary(lib.tc_premult))
+        run("colorconvert lin709->ACEScct", 2, unary(lib.tc_color_convert, b"Linear Rec.709 (sRGB)", b"ACEScct"))
+        run("blur r10", 2, unary(lib.tc_blur, 10.0))
+        run("blur r20", 2, unary(lib.tc_blur, 20.0))
+        run("unsharp r10", 2, unary(lib.tc_unsharp_mask, b"gaussian", 10.0, 1.0, 0.0))
+        run("rotate 45", 2, unary(lib.tc_rotate, 0.7853982, b"", 0.0), iters=5)
         half = [torch.empty((h // 2, w // 2, 4), device="cuda", dtype=dt) for _ in range(n)]
-        rec("resize 1/2 (lanczos3)", 1.25, timeit(lambda i: capi.check(lib.tc_resize(B(ops.img(half[i % n])), B(ops.img(a[i % n])), b"", 0.0, S()), "rs"), iters=5))
-        rec("resize x2 (blackman-harris)", 1.25, timeit(lambda i: capi.check(lib.tc_resize(B(ops.img(outs[i % n])), B(ops.img(half[i % n])), b"", 0.0, S()), "rs"), iters=5))
-        rec("dissolve", 3, timeit(lambda i: capi.check(lib.tc_dissolve(B(ops.img(outs[i % n])), B(ops.img(a[i % n])), B(ops.img(b[i % n])), 0.3, S()), "ds")))
-        rec("wipe h", 3, timeit(lambda i: capi.check(lib.tc_wipe(B(ops.img(outs[i % n])), B(ops.img(a[i % n])), B(ops.img(b[i % n])), 0.3, 0, S()), "wp")))
-        rec("premult+over", 3, timeit(lambda i: capi.check(lib.tc_over(B(ops.img(outs[i % n])), B(ops.img(a[i % n])), B(ops.img(b[i % n])), 1, S()), "ov")))
+        run("resize 1/2 (lanczos3)", 1.25, lambda i: capi.check(lib.tc_resize(B(ops.img(half[i % n])), B(ops.img(a[i % n])), b"", 0.0, S()), "rs"), iters=5)
+        run("resize x2 (blackman-harris)", 1.25, lambda i: capi.check(lib.tc_resize(B(ops.img(outs[i % n])), B(ops.img(half[i % n])), b"", 0.0, S()), "rs"), iters=5)
+        run("dissolve", 3, lambda i: capi.check(lib.tc_dissolve(B(ops.img(outs[i % n])), B(ops.img(a[i % n])), B(ops.img(b[i % n])), 0.3, S()), "ds"))
+        run("wipe h", 3, lambda i: capi.check(lib.tc_wipe(B(ops.img(outs[i % n])), B(ops.img(a[i % n])), B(ops.img(b[i % n])), 0.3, 0, S()), "wp"))
+        run("premult+over", 3, lambda i: capi.check(lib.tc_over(B(ops.img(outs[i % n])), B(ops.img(a[i % n])), B(ops.img(b[i % n])), 1, S()), "ov"))
+        for fmt in ("422", "444", "444alpha", "444p16"):
+            ybytes = int(lib.tc_y4m_frame_bytes(capi.Y4M_FORMATS[fmt], w, h))
+            ybuf = [torch.empty((ybytes,), dtype=torch.uint8, device="cuda") for _ in range(3)]
+            run(f"y4m {fmt}", 1, lambda i, fmt=fmt, ybuf=ybuf: capi.check(lib.tc_rgb_to_y4m(
+                ctypes.c_void_p(ybuf[i % 3].data_ptr()), B(ops.img(a[i % n])), capi.Y4M_FORMATS[fmt], S()), "y4m"), out_bytes=px + ybytes)
         del a, b, outs, half
         torch.cuda.empty_cache()
     if args.out:

@@ -1,10 +1,13 @@
 // toucan-render: render a timeline to raw frames.  Mirrors bin/toucan-render/App.cpp:152-265
 // for the in-scope outputs: raw frames in the timeline's working format to a file or stdout
 // ("-").  The serial frame loop of App.cpp:222-264 is replaced by toucan::FrameScheduler:
-// frames are sharded in contiguous blocks over the GPUs and written in order.  Encoders
-// (FFmpeg, PNG, y4m) are host-side writers outside the hot path.
+// frames are sharded in contiguous blocks over the GPUs and written in order.  Both output
+// conversions of App.cpp:267-485 (-raw: paste to the raw spec; -y4m: paste + libswscale to
+// planar YUV) run on the device, so only the writer's bytes cross PCIe.  Movie and image-file
+// encoders (FFmpeg, OIIO writers) are host-side writers outside the hot path.
 //
-//   toucan-render input.otio output.raw|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32] [-gpus N]
+//   toucan-render input.otio output|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32]
+//                 [-y4m 422|444|444alpha|444p16] [-gpus N]
 //                 [-print_start] [-print_duration] [-print_rate] [-print_size]
 #include <toucanRender/FrameScheduler.h>
 #include <toucanRender/TimelineWrapper.h>
@@ -20,7 +23,7 @@ int main(int argc, char** argv)
 {
     try
     {
-        std::string input, output, raw;
+        std::string input, output, raw, y4m;
         int gpus = 1;
         bool printStart = false, printDuration = false, printRate = false, printSize = false;
         for (int i = 1; i < argc; ++i)
@@ -28,6 +31,7 @@ int main(int argc, char** argv)
             const std::string a = argv[i];
             if (a == "-gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
             else if (a == "-raw" && i + 1 < argc) raw = argv[++i];
+            else if (a == "-y4m" && i + 1 < argc) y4m = argv[++i];
             else if (a == "-print_start") printStart = true;
             else if (a == "-print_duration") printDuration = true;
             else if (a == "-print_rate") printRate = true;
@@ -37,7 +41,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format] [-gpus N] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 
@@ -75,14 +79,29 @@ int main(int argc, char** argv)
         {
             throw std::runtime_error("Cannot find the given raw format");
         }
+        if (!y4m.empty())
+        {
+            if (!parseY4mFormat(y4m, options.y4mFormat))
+            {
+                throw std::runtime_error("Cannot find the given y4m format");
+            }
+            // App.cpp:218-221: the stream header goes out before the first frame
+            ImageGraph graph(context, std::filesystem::path(input).parent_path(), timelineWrapper);
+            const std::string header = y4mHeader(graph.getImageSize().x, graph.getImageSize().y, timeRange.duration().rate(), y4m);
+            fwrite(header.c_str(), header.size(), 1, f);
+        }
         FrameScheduler scheduler(context, timelineWrapper, options);
-        scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec& spec)
+        scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec&, size_t bytes)
         {
             if (output != "-")
             {
                 std::cout << frame << "/" << frames << std::endl;
             }
-            fwrite(pixels, 1, spec.image_bytes(), f);
+            if (options.y4mFormat >= 0)
+            {
+                fwrite("FRAME\n", 6, 1, f);
+            }
+            fwrite(pixels, 1, bytes, f);
         });
         if (f != stdout) fclose(f);
     }

@@ -2,10 +2,12 @@
 
 #include "ImageEffectHost.h"
 
+#include <cmath>
 #include <condition_variable>
 #include <deque>
 #include <exception>
 #include <mutex>
+#include <sstream>
 #include <thread>
 
 namespace toucan
@@ -25,6 +27,39 @@ namespace toucan
             }
         }
         return false;
+    }
+
+    bool parseY4mFormat(const std::string& name, int& format)
+    {
+        static const struct { const char* name; int format; } specs[] = {
+            { "422", TC_Y4M_422 }, { "444", TC_Y4M_444 }, { "444alpha", TC_Y4M_444ALPHA }, { "444p16", TC_Y4M_444P16 } };
+        for (const auto& spec : specs)
+        {
+            if (name == spec.name)
+            {
+                format = spec.format;
+                return true;
+            }
+        }
+        return false;
+    }
+
+    std::string y4mHeader(int width, int height, double rate, const std::string& format)
+    {
+        // ftk::toRational (App.cpp:323): the common video rates as exact fractions, else (int(rate), 1)
+        static const std::pair<int, int> common[] = { { 24, 1 }, { 30, 1 }, { 60, 1 }, { 24000, 1001 }, { 30000, 1001 }, { 60000, 1001 } };
+        std::pair<int, int> r(static_cast<int>(rate), 1);
+        for (const auto& c : common)
+        {
+            if (std::fabs(rate - c.first / static_cast<double>(c.second)) < 0.01)
+            {
+                r = c;
+                break;
+            }
+        }
+        std::stringstream ss;
+        ss << "YUV4MPEG2 W" << width << " H" << height << " F" << r.first << ":" << r.second << " C" << format << "\n";
+        return ss.str();
     }
 
     std::pair<int, int> frameBlock(int first, int last, int index, int count)
@@ -82,6 +117,7 @@ namespace toucan
             tc_event done = nullptr;
             Image image; // keeps the device frame alive until its download has been consumed
             ImageSpec spec;
+            size_t bytes = 0;
             int frame = -1;
         };
 
@@ -167,15 +203,27 @@ namespace toucan
                     slot.spec = slot.image.spec();
                     slot.frame = frame;
                     void* packed = nullptr;
-                    if (_options.rawType >= 0 && slot.spec.format != _options.rawType && slot.spec.image_bytes() > 0)
+                    size_t bytes = slot.spec.image_bytes();
+                    if (_options.y4mFormat >= 0 && bytes > 0)
+                    {
+                        // paste + swscale of App.cpp:340-412 as one kernel; the download moves the planar bytes
+                        const tc_image view = slot.image.view();
+                        bytes = tc_y4m_frame_bytes(_options.y4mFormat, slot.spec.width, slot.spec.height);
+                        slot.spec = ImageSpec(slot.spec.width, slot.spec.height, TC_Y4M_444ALPHA == _options.y4mFormat ? 4 : 3,
+                            TC_Y4M_444P16 == _options.y4mFormat ? TC_U16 : TC_U8);
+                        tcCheck(tc_malloc(&packed, bytes, DeviceContext::stream()), "tc_malloc");
+                        tcCheck(tc_rgb_to_y4m(packed, &view, _options.y4mFormat, DeviceContext::stream()), "tc_rgb_to_y4m");
+                    }
+                    else if (_options.rawType >= 0 && slot.spec.format != _options.rawType && bytes > 0)
                     {
                         // output conversion on the device: the download moves the writer's bytes
                         const tc_image view = slot.image.view();
                         slot.spec = ImageSpec(slot.spec.width, slot.spec.height, _options.rawChannels, _options.rawType);
-                        tcCheck(tc_malloc(&packed, slot.spec.image_bytes(), DeviceContext::stream()), "tc_malloc");
+                        bytes = slot.spec.image_bytes();
+                        tcCheck(tc_malloc(&packed, bytes, DeviceContext::stream()), "tc_malloc");
                         tcCheck(tc_pack_raw(packed, &view, _options.rawType, _options.rawChannels, DeviceContext::stream()), "tc_pack_raw");
                     }
-                    const size_t bytes = slot.spec.image_bytes();
+                    slot.bytes = bytes;
                     if (bytes > slot.capacity)
                     {
                         pinnedPool.release(slot.pinned, slot.capacity);
@@ -255,7 +303,7 @@ namespace toucan
                 try
                 {
                     tcCheck(tc_event_sync(slot.done), "tc_event_sync");
-                    writer(slot.frame, slot.pinned, slot.spec);
+                    writer(slot.frame, slot.pinned, slot.spec, slot.bytes);
                 }
                 catch (...)
                 {

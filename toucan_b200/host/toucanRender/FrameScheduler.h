@@ -28,10 +28,20 @@ namespace toucan
         //! ImageBufAlgo::paste, and -- like here -- writes the frame as is when the types match).
         int rawType = -1;
         int rawChannels = 4;
+        //! y4m output format (bin/toucan-render/App.cpp:37-43 y4mSpecs; TC_Y4M_*), -1 = off.  Every frame is
+        //! converted ON THE DEVICE to the planar YUV bytes the reference's paste + libswscale chain
+        //! (App.cpp:340-485) writes after "FRAME\n"; only those bytes are downloaded.
+        int y4mFormat = -1;
     };
 
     //! "rgb24" | "rgba" | "rgb48" | "rgba64" | "rgbaf16" | "rgbf32" | "rgbaf32" -> (tc_type, channels)
     bool parseRawFormat(const std::string&, int& type, int& channels);
+
+    //! "422" | "444" | "444alpha" | "444p16" -> TC_Y4M_*
+    bool parseY4mFormat(const std::string&, int& format);
+
+    //! The stream header of App.cpp:302-338: "YUV4MPEG2 W<w> H<h> F<num>:<den> C<format>\n".
+    std::string y4mHeader(int width, int height, double rate, const std::string& format);
 
     //! Contiguous block of frames [first, last) owned by worker `index` of `count`.
     std::pair<int, int> frameBlock(int first, int last, int index, int count);
@@ -39,7 +49,9 @@ namespace toucan
     class FrameScheduler
     {
     public:
-        using Writer = std::function<void(int frame, const void* pixels, const ImageSpec&)>;
+        //! `bytes` is the size of `pixels`: spec.image_bytes() for interleaved frames, the planar frame size in y4m mode
+        //! (where spec carries the frame size and the sample type only).
+        using Writer = std::function<void(int frame, const void* pixels, const ImageSpec&, size_t bytes)>;
 
         FrameScheduler(
             const std::shared_ptr<ftk::Context>&,

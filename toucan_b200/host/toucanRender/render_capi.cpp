@@ -310,9 +310,45 @@ extern "C"
             else options.pluginSearchPath = getOpenFXPluginPaths(libraryDirectory() / "toucan-render");
             if (frames_in_flight > 0) options.framesInFlight = frames_in_flight;
             FrameScheduler scheduler(timeline->context, timeline->wrapper, options);
-            scheduler.run(first, last, [&](int frame, const void* pixels, const ImageSpec& spec) {
+            scheduler.run(first, last, [&](int frame, const void* pixels, const ImageSpec& spec, size_t) {
                 callback(user, frame, pixels, spec.width, spec.height, spec.format | (spec.nchannels == 3 ? 0x100 : 0));
             });
+            return 0;
+        });
+    }
+
+    int tr_render_range_y4m(tr_timeline* timeline, const char* plugin_dir, const int* devices, int n_devices, int first, int last,
+                            int frames_in_flight, const char* y4m_format, tr_frame_callback callback, void* user)
+    {
+        if (!timeline || !callback || !y4m_format) return fail("tr_render_range_y4m: null");
+        return guarded([&] {
+            FrameSchedulerOptions options;
+            if (!parseY4mFormat(y4m_format, options.y4mFormat))
+            {
+                return fail("Cannot find the given y4m format");
+            }
+            options.devices.clear();
+            for (int i = 0; i < n_devices; ++i) options.devices.push_back(devices ? devices[i] : i);
+            if (options.devices.empty()) options.devices.push_back(0);
+            if (plugin_dir && *plugin_dir) options.pluginSearchPath.push_back(plugin_dir);
+            else options.pluginSearchPath = getOpenFXPluginPaths(libraryDirectory() / "toucan-render");
+            if (frames_in_flight > 0) options.framesInFlight = frames_in_flight;
+            const int format = options.y4mFormat;
+            FrameScheduler scheduler(timeline->context, timeline->wrapper, options);
+            scheduler.run(first, last, [&](int frame, const void* pixels, const ImageSpec& spec, size_t) {
+                callback(user, frame, pixels, spec.width, spec.height, 0x200 | format);
+            });
+            return 0;
+        });
+    }
+
+    int tr_y4m_header(int width, int height, double rate, const char* y4m_format, char* out, size_t capacity)
+    {
+        if (!y4m_format || !out) return fail("tr_y4m_header: null");
+        return guarded([&] {
+            const std::string header = y4mHeader(width, height, rate, y4m_format);
+            if (header.size() + 1 > capacity) return fail("tr_y4m_header: buffer too small");
+            memcpy(out, header.c_str(), header.size() + 1);
             return 0;
         });
     }

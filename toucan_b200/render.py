@@ -46,6 +46,8 @@ FRAME_CALLBACK = ctypes.CFUNCTYPE(None, _VP, ctypes.c_int, _VP, ctypes.c_int, ct
 _SIGS["tr_render_range"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, FRAME_CALLBACK, _VP]
 _SIGS["tr_render_range_raw"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
                                 FRAME_CALLBACK, _VP]
+_SIGS["tr_render_range_y4m"] = _SIGS["tr_render_range_raw"]
+_SIGS["tr_y4m_header"] = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
 EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion"})
 
 
@@ -92,6 +94,13 @@ def sync():
 
 def set_fusion(enabled: bool):
     lib().tr_set_fusion(1 if enabled else 0)
+
+
+def y4m_header(width: int, height: int, rate: float, y4m_format: str) -> bytes:
+    """The y4m stream header toucan-render writes before the first frame (App.cpp:302-338)."""
+    buf = ctypes.create_string_buffer(256)
+    _check(lib().tr_y4m_header(int(width), int(height), float(rate), y4m_format.encode(), buf, 256), "tr_y4m_header")
+    return buf.value
 
 
 def frame_block(first: int, last: int, index: int, count: int):
@@ -212,12 +221,17 @@ class Timeline:
         return p.value, w.value, h.value, t.value
 
     def render_range(self, first: int, last: int, writer, devices=(0,), frames_in_flight: int = 2, plugin_dir: str = PLUGIN_DIR,
-                     raw_format: str | None = None):
+                     raw_format: str | None = None, y4m_format: str | None = None):
         """toucan::FrameScheduler: frames [first, last) on `devices`, writer(frame, ndarray) called in
         order on this thread; the array aliases pinned memory valid only during the call.  raw_format:
-        device-side output conversion ("rgb24", "rgba", "rgb48", "rgba64", "rgbaf16", "rgbf32", "rgbaf32")."""
+        device-side output conversion ("rgb24", "rgba", "rgb48", "rgba64", "rgbaf16", "rgbf32", "rgbaf32").
+        y4m_format ("422", "444", "444alpha", "444p16"): device-side conversion to the planar YUV bytes of
+        `toucan-render -y4m`; the writer then receives a flat uint8 array (split it with ops.y4m_planes)."""
         def cb(_user, frame, pixels, w, h, t):
-            if w > 0 and h > 0 and pixels:
+            if t & 0x200 and w > 0 and h > 0 and pixels:
+                n = int(capi.lib().tc_y4m_frame_bytes(t & 0xf, w, h))
+                writer(frame, np.frombuffer((ctypes.c_char * n).from_address(pixels), dtype=np.uint8))
+            elif w > 0 and h > 0 and pixels:
                 nch = 3 if t & 0x100 else 4
                 dt = np.dtype(_NP_OF[t & 0xff])
                 buf = (ctypes.c_char * (w * h * nch * dt.itemsize)).from_address(pixels)
@@ -227,6 +241,10 @@ class Timeline:
 
         c_cb = FRAME_CALLBACK(cb)
         devs = (ctypes.c_int * len(devices))(*devices)
+        if y4m_format:
+            _check(lib().tr_render_range_y4m(self._t, plugin_dir.encode(), devs, len(devices), int(first), int(last), int(frames_in_flight),
+                                             y4m_format.encode(), c_cb, None), "tr_render_range_y4m")
+            return
         _check(lib().tr_render_range_raw(self._t, plugin_dir.encode(), devs, len(devices), int(first), int(last), int(frames_in_flight),
                                          raw_format.encode() if raw_format else None, c_cb, None), "tr_render_range")
 
