@@ -101,6 +101,10 @@ void tr_frame_block(int first, int last, int index, int count, int* lo, int* hi)
    A = 1 appended to RGB, alpha associated on read like OIIO's reader).  out may be NULL to
    query the size. */
 int tr_decode_png(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
+/* The built-in JPEG reader (baseline / extended / progressive Huffman, 8-bit YCbCr or RGB, 1x-2x sampling):
+   libjpeg's defaults -- islow IDCT, fancy upsampling, integer colour tables -- bit for bit, RGBA out with
+   A = 255 (Read.cpp:86-94).  Same calling convention as tr_decode_png. */
+int tr_decode_jpeg(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
 
 /* Cross-node fusion of the track stack (default on). */
 void tr_set_fusion(int enabled);

@@ -1,0 +1,252 @@
+"""Ingest (lib/toucanRender/Read.cpp:34-216): the C++ host's built-in readers.
+
+The reference reads stills through OpenImageIO, i.e. libjpeg(-turbo) / libpng with their defaults.  Pillow
+links the same libjpeg-turbo, so comparing the built-in JPEG reader with Pillow's decode pins it to the real
+library: every pixel must match (islow IDCT, fancy upsampling, integer colour tables are all exact integer
+algorithms).  These tests run on the CPU -- decode is host code -- except the last, which renders a JPEG-backed
+fixture through the command line tool.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from tests import media
+from tests import timelines as TL
+
+Image = pytest.importorskip("PIL.Image")
+
+
+def pil_rgb(path):
+    return np.asarray(Image.open(path).convert("RGB"))
+
+
+def synth(w, h, kind, seed=0):
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    a = np.stack([xx * 255 // max(w - 1, 1), yy * 255 // max(h - 1, 1), ((xx + yy) * 7) % 256], -1).astype(np.uint8)
+    a[h // 3:h // 2, w // 4:w // 2] = (255, 0, 0)  # a saturated edge: exercises the range limits
+    return a
+
+
+def test_reference_fixture_jpeg(built):
+    """data/Charlie.jpg is a progressive 4:4:4 JPEG (spectral selection + successive approximation)."""
+    from toucan_b200 import render
+
+    path = os.path.join(TL.DATA, "Charlie.jpg")
+    got = render.decode_jpeg(path)
+    assert got.shape == (720, 1280, 4) and got.dtype == np.uint8
+    assert np.array_equal(got[..., :3], pil_rgb(path)) and (got[..., 3] == 255).all()  # Read.cpp:86-94: A = 1
+    assert np.array_equal(got, media.decode(path))  # what the parity tests feed the oracle
+
+
+@pytest.mark.parametrize("size", [(1, 1), (2, 2), (3, 5), (8, 8), (17, 9), (33, 31), (100, 75), (257, 129)])
+@pytest.mark.parametrize("subsampling", [0, 1, 2])  # 4:4:4, 4:2:2 (h2v1), 4:2:0 (h2v2)
+def test_jpeg_matches_libjpeg_turbo(built, tmp_path, size, subsampling):
+    from toucan_b200 import render
+
+    w, h = size
+    n = 0
+    for kind in ("noise", "ramp"):
+        for progressive in (False, True):
+            for extra in ({"quality": 30}, {"quality": 92, "optimize": True}, {"quality": 75, "restart_marker_blocks": 3}):
+                path = str(tmp_path / f"{kind}_{int(progressive)}_{n}.jpg")
+                Image.fromarray(synth(w, h, kind, n)).save(path, subsampling=subsampling, progressive=progressive, **extra)
+                assert np.array_equal(render.decode_jpeg(path)[..., :3], pil_rgb(path)), (size, subsampling, kind, progressive, extra)
+                n += 1
+
+
+def test_jpeg_rgb_colourspace_and_errors(built, tmp_path):
+    from toucan_b200 import capi, render
+
+    path = str(tmp_path / "rgb.jpg")
+    Image.fromarray(synth(37, 21, "noise")).save(path, quality=85, keep_rgb=True)  # Adobe-less RGB components 'R','G','B'
+    assert np.array_equal(render.decode_jpeg(path)[..., :3], pil_rgb(path))
+    Image.fromarray(synth(9, 9, "noise")[..., 0]).save(path)
+    with pytest.raises(capi.TcError, match="grayscale"):
+        render.decode_jpeg(path)
+    for junk in (b"\xff\xd8\xff\xd9", b"not a jpeg", b""):
+        with open(path, "wb") as f:
+            f.write(junk)
+        with pytest.raises(capi.TcError):
+            render.decode_jpeg(path)
+    # a truncated stream keeps what was decoded (zero coefficients for the rest), like libjpeg's premature-EOF path
+    Image.fromarray(synth(64, 64, "ramp")).save(path, quality=80)
+    data = open(path, "rb").read()
+    with open(path, "wb") as f:
+        f.write(data[:len(data) * 2 // 3])
+    assert render.decode_jpeg(path).shape == (64, 64, 4)
+
+
+@pytest.mark.gpu
+def test_cli_reads_jpeg_media_itself(cuda, tmp_path):
+    """toucan-render on a fixture backed by Charlie.jpg with NO pre-decoded media: the read node decodes the file
+    with the built-in reader and the frames equal the golden ones (which were rendered from Pillow's decode)."""
+    import subprocess
+
+    from toucan_b200 import capi
+
+    gold = TL.golden()["TransitionWipe.otio"]["frames"]
+    exe = os.path.join(capi.LIB_DIR, "toucan-render")
+    out = tmp_path / "wipe.raw"
+    r = subprocess.run([exe, os.path.join(TL.DATA, "TransitionWipe.otio"), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out, np.uint8).reshape(len(gold), 720, 1280, 4)
+    for i, rec in enumerate(gold):
+        assert hashlib.sha256(raw[i].tobytes()).hexdigest() == rec["sha256"], f"frame {i}"
+
+
+# ---- bundles and "open a file as a timeline" (TimelineWrapper.cpp:68-306) ------------------------
+def _bundle_doc(name):
+    """The fixture with its media moved under media/, the layout OTIO's otioz / otiod adapters write."""
+    import json
+
+    doc = json.load(open(os.path.join(TL.DATA, name)))
+    files = set()
+
+    def walk(o):
+        if isinstance(o, dict):
+            schema = o.get("OTIO_SCHEMA", "")
+            if schema.startswith("ExternalReference"):
+                files.add(o["target_url"])
+                o["target_url"] = "media/" + o["target_url"]
+            elif schema.startswith("ImageSequenceReference"):
+                n0 = int(o["available_range"]["start_time"]["value"])
+                for i in range(n0, n0 + int(o["available_range"]["duration"]["value"])):
+                    files.add(f"{o['name_prefix']}{i:0{o['frame_zero_padding']}d}{o['name_suffix']}")
+                o["target_url_base"] = "media/"
+            for v in o.values():
+                walk(v)
+        elif isinstance(o, list):
+            for v in o:
+                walk(v)
+
+    walk(doc)
+    return json.dumps(doc), sorted(files)
+
+
+def make_otioz(path, name, media_compression=None):
+    import zipfile
+
+    text, files = _bundle_doc(name)
+    with zipfile.ZipFile(path, "w") as z:
+        z.writestr("content.otio", text, compress_type=zipfile.ZIP_DEFLATED)  # the adapter deflates the timeline ...
+        for f in files:
+            z.write(os.path.join(TL.DATA, f), "media/" + f, compress_type=media_compression or zipfile.ZIP_STORED)  # ... and stores media
+
+
+def make_otiod(path, name):
+    import shutil
+
+    text, files = _bundle_doc(name)
+    os.makedirs(os.path.join(path, "media"))
+    with open(os.path.join(path, "content.otio"), "w") as f:
+        f.write(text)
+    for f in files:
+        shutil.copyfile(os.path.join(TL.DATA, f), os.path.join(path, "media", f))
+
+
+def test_bundle_errors(built, tmp_path):
+    """Open-time errors of the archive front-end, with the reference's messages (TimelineWrapper.cpp:150-211)."""
+    import zipfile
+
+    from toucan_b200 import capi, render
+
+    bad = str(tmp_path / "compressed.otioz")
+    make_otioz(bad, "Transition.otio", media_compression=zipfile.ZIP_DEFLATED)
+    with pytest.raises(capi.TcError, match="Media is not uncompressed: media/Counter.0.png"):
+        render.Timeline(bad)
+    missing = str(tmp_path / "missing.otioz")
+    text, _ = _bundle_doc("Transition.otio")
+    with zipfile.ZipFile(missing, "w") as z:
+        z.writestr("content.otio", text)
+    with pytest.raises(capi.TcError, match="Cannot locate: media/"):
+        render.Timeline(missing)
+    empty = str(tmp_path / "empty.otioz")
+    with zipfile.ZipFile(empty, "w") as z:
+        z.writestr("readme.txt", "no timeline here")
+    with pytest.raises(capi.TcError, match="Cannot locate: content.otio"):
+        render.Timeline(empty)
+    with open(str(tmp_path / "junk.otioz"), "wb") as f:
+        f.write(b"this is not a zip archive at all")
+    with pytest.raises(capi.TcError, match="Cannot open zip file"):
+        render.Timeline(str(tmp_path / "junk.otioz"))
+    with pytest.raises(capi.TcError, match="Unrecognized file"):
+        render.Timeline(str(tmp_path / "movie.mov"))
+
+
+def _render_all(tl, n):
+    got = {}
+    tl.render_range(0, n, lambda f, p: got.__setitem__(f, hashlib.sha256(p.tobytes()).hexdigest()))
+    return [got[i] for i in range(n)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["Transition.otio", "TransitionWipe.otio", "CompositeTracks.otio"])
+def test_otioz_and_otiod_render_like_the_plain_timeline(cuda, tmp_path, name):
+    """PNG sequences and a JPEG still read in place from the memory-mapped archive (and from the unpacked
+    bundle): every frame equals the golden frame of the plain .otio fixture."""
+    from toucan_b200 import render
+
+    gold = [r["sha256"] for r in TL.golden()[name]["frames"]]
+    z = str(tmp_path / "bundle.otioz")
+    make_otioz(z, name)
+    tl = render.Timeline(z)
+    tl.prepare()
+    assert _render_all(tl, len(gold)) == gold
+    tl.close()
+    d = str(tmp_path / "bundle.otiod")
+    make_otiod(d, name)
+    tl = render.Timeline(d)
+    tl.prepare()
+    assert _render_all(tl, len(gold)) == gold
+    tl.close()
+
+
+@pytest.mark.gpu
+def test_image_and_sequence_open_as_timelines(cuda, tmp_path):
+    """TimelineWrapper.cpp:262-306: a still becomes a one-frame timeline at 24 fps, a numbered file the sequence it
+    belongs to (ordered by number, same prefix / padding / extension)."""
+    import shutil
+
+    from toucan_b200 import render
+
+    still = os.path.join(TL.DATA, "Charlie.jpg")
+    tl = render.Timeline(still)
+    tl.prepare()
+    info = tl.info()
+    assert (info["frames"], info["rate"], info["width"], info["height"]) == (1, 24.0, 1280, 720)
+    out = []
+    tl.render_range(0, 1, lambda f, p: out.append(p.copy()))
+    assert np.array_equal(out[0], media.decode(still))
+    tl.close()
+    for i in (3, 4, 5, 7):  # a sequence with a hole and a decoy of another padding
+        shutil.copyfile(os.path.join(TL.DATA, f"Counter.{i}.png"), str(tmp_path / f"shot.{i:04d}.png"))
+    shutil.copyfile(os.path.join(TL.DATA, "Counter.9.png"), str(tmp_path / "shot.9.png"))
+    tl = render.Timeline(str(tmp_path / "shot.0004.png"))
+    tl.prepare()
+    info = tl.info()
+    assert (info["frames"], info["start"]) == (4, 0.0)  # 4 files found -> duration 4 from frame 3 (files 3, 4, 5, 6)
+    frames = {}
+    tl.render_range(0, 4, lambda f, p: frames.__setitem__(f, p.copy()))
+    tl.close()
+    # the same one-clip timeline spelled out for the oracle
+    from oracle import graph as G
+
+    def rt(v):
+        return {"OTIO_SCHEMA": "RationalTime.1", "rate": 24.0, "value": float(v)}
+
+    doc = {"OTIO_SCHEMA": "Timeline.1", "name": "", "tracks": {"OTIO_SCHEMA": "Stack.1", "name": "tracks", "children": [
+        {"OTIO_SCHEMA": "Track.1", "name": "Video", "kind": "Video", "children": [
+            {"OTIO_SCHEMA": "Clip.1", "name": "", "source_range": {"OTIO_SCHEMA": "TimeRange.1", "start_time": rt(3), "duration": rt(4)},
+             "media_reference": {"OTIO_SCHEMA": "ImageSequenceReference.1", "target_url_base": str(tmp_path), "name_prefix": "shot.",
+                                 "name_suffix": ".png", "start_frame": 3, "frame_step": 1, "rate": 24.0, "frame_zero_padding": 4,
+                                 "available_range": None}}]}]}}
+    otl = G.Timeline(doc)
+    otl.dir = str(tmp_path)
+    og = G.ImageGraph(otl, media.decode)
+    for f, t in enumerate(otl.frames()):
+        assert np.array_equal(frames[f], og.render(t)), f  # frame 3 names file 0006, which does not exist: background only

@@ -42,6 +42,21 @@ namespace toucan
         size_t n;
         while ((n = fread(buf, 1, sizeof(buf), f)) > 0) file.insert(file.end(), buf, buf + n);
         fclose(f);
+        return readPngMemory(file.data(), file.size(), out);
+    }
+
+    bool readPngMemory(const unsigned char* bytes, size_t size, MediaFrame& out)
+    {
+        // the chunk walk below indexes `file`
+        struct View
+        {
+            const unsigned char* p;
+            size_t n;
+            const unsigned char* data() const { return p; }
+            size_t size() const { return n; }
+            const unsigned char& operator[](size_t i) const { return p[i]; }
+        };
+        const View file{ bytes, size };
         static const unsigned char sig[8] = { 0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a };
         if (file.size() < 33 || memcmp(file.data(), sig, 8) != 0) return false;
 

@@ -11,6 +11,7 @@
 namespace toucan
 {
     bool readPng(const std::string& path, MediaFrame& out);
+    bool readPngMemory(const unsigned char* data, size_t size, MediaFrame& out);
 
     //! Write 8-bit RGBA (alpha dropped when `rgb` is true).
     bool writePng(const std::string& path, const unsigned char* rgba, int width, int height, bool rgb = false);

@@ -1,5 +1,6 @@
 #include "Read.h"
 
+#include "JpegRead.h"
 #include "PngRead.h"
 #include "Util.h"
 
@@ -99,20 +100,35 @@ namespace toucan
         return store;
     }
 
-    bool readMedia(const std::shared_ptr<MediaStore>& store, const std::string& path, MediaFrame& out)
+    bool readMedia(const std::shared_ptr<MediaStore>& store, const std::string& path, MediaFrame& out, const MemoryReference& memory)
     {
         if (store && store->get(path, out))
         {
             return true;
         }
-        // Built-in reader: PNG only (zlib).  The decoded frame is parked in the store so a
+        // Built-in readers: PNG (zlib) and JPEG.  The decoded frame is parked in the store so a
         // still is decoded once; it is still uploaded on every exec().
-        if (toLower(std::filesystem::path(path).extension().string()) == ".png" && readPng(path, out))
+        const std::string extension = toLower(std::filesystem::path(path).extension().string());
+        bool read = false;
+        const bool inMemory = memory.isValid();
+        try
         {
-            if (store) store->set(path, out);
-            return true;
+            if (".png" == extension)
+            {
+                read = inMemory ? readPngMemory(memory.data, memory.size, out) : readPng(path, out);
+            }
+            else if (".jpg" == extension || ".jpeg" == extension)
+            {
+                read = inMemory ? readJpegMemory(memory.data, memory.size, out) : readJpeg(path, out);
+            }
         }
-        return false;
+        catch (const std::exception&)
+        {
+            // OIIO::ImageInput::open returns null for a file it cannot decode (Read.cpp:40-46)
+            read = false;
+        }
+        if (read && store) store->set(path, out);
+        return read;
     }
 
     IReadNode::IReadNode(const std::string& name) :
@@ -155,13 +171,15 @@ namespace toucan
 
     ImageReadNode::ImageReadNode(
         const std::filesystem::path& path,
-        const std::shared_ptr<MediaStore>& store) :
+        const std::shared_ptr<MediaStore>& store,
+        const MemoryReference& memory) :
         IReadNode("ImageRead"),
         _path(path),
-        _store(store)
+        _store(store),
+        _memory(memory)
     {
         MediaFrame frame;
-        if (!readMedia(_store, _path.string(), frame))
+        if (!readMedia(_store, _path.string(), frame, _memory))
         {
             std::stringstream ss;
             ss << "Cannot open file: " << _path.string();
@@ -181,7 +199,7 @@ namespace toucan
     Image ImageReadNode::exec()
     {
         MediaFrame frame;
-        if (!readMedia(_store, _path.string(), frame))
+        if (!readMedia(_store, _path.string(), frame, _memory))
         {
             return Image();
         }
@@ -201,7 +219,8 @@ namespace toucan
         int frameStep,
         double rate,
         int frameZeroPadding,
-        const std::shared_ptr<MediaStore>& store) :
+        const std::shared_ptr<MediaStore>& store,
+        const MemoryReferences& memoryReferences) :
         IReadNode("SequenceRead"),
         _base(base),
         _namePrefix(namePrefix),
@@ -210,12 +229,15 @@ namespace toucan
         _frameStep(frameStep),
         _rate(rate),
         _frameZeroPadding(frameZeroPadding),
-        _store(store)
+        _store(store),
+        _memoryReferences(memoryReferences)
     {
         // Image information comes from the first frame; a missing first frame leaves an
         // empty spec instead of throwing (Read.cpp:138-150).
         MediaFrame frame;
-        if (readMedia(_store, getSequenceFrame(_base, _namePrefix, _startFrame, _frameZeroPadding, _nameSuffix), frame))
+        const std::string first = getSequenceFrame(_base, _namePrefix, _startFrame, _frameZeroPadding, _nameSuffix);
+        const auto memory = _memoryReferences.find(first);
+        if (readMedia(_store, first, frame, memory != _memoryReferences.end() ? memory->second : MemoryReference()))
         {
             _spec = ImageSpec(frame.width, frame.height, frame.nchannels, frame.format);
         }
@@ -239,7 +261,8 @@ namespace toucan
         // The clip-local time IS the file number (Read.cpp:169-174).
         const std::string url = getSequenceFrame(_base, _namePrefix, _time.to_frames(), _frameZeroPadding, _nameSuffix);
         MediaFrame frame;
-        if (!readMedia(_store, url, frame))
+        const auto memory = _memoryReferences.find(url);
+        if (!readMedia(_store, url, frame, memory != _memoryReferences.end() ? memory->second : MemoryReference()))
         {
             return Image();
         }
@@ -253,9 +276,10 @@ namespace toucan
 
     std::shared_ptr<IReadNode> createReadNode(
         const std::filesystem::path& path,
-        const std::shared_ptr<MediaStore>& store)
+        const std::shared_ptr<MediaStore>& store,
+        const MemoryReference& memory)
     {
-        return std::make_shared<ImageReadNode>(path, store);
+        return std::make_shared<ImageReadNode>(path, store, memory);
     }
 
     std::shared_ptr<IReadNode> createReadNode(
@@ -266,9 +290,10 @@ namespace toucan
         int frameStep,
         double rate,
         int frameZeroPadding,
-        const std::shared_ptr<MediaStore>& store)
+        const std::shared_ptr<MediaStore>& store,
+        const MemoryReferences& memoryReferences)
     {
         return std::make_shared<SequenceReadNode>(
-            base, namePrefix, nameSuffix, startFrame, frameStep, rate, frameZeroPadding, store);
+            base, namePrefix, nameSuffix, startFrame, frameStep, rate, frameZeroPadding, store, memoryReferences);
     }
 }

@@ -28,6 +28,18 @@ namespace toucan
         std::shared_ptr<std::vector<unsigned char> > owned; // storage for frames decoded by the built-in reader
     };
 
+    //! A file held in memory (lib/toucanRender/MemoryMap.h: MemoryReference): an entry of a mapped .otioz.
+    struct MemoryReference
+    {
+        std::shared_ptr<const void> owner; //!< keeps the mapping alive
+        const unsigned char* data = nullptr;
+        size_t size = 0;
+        bool isValid() const { return data != nullptr && size > 0; }
+    };
+
+    //! In-memory files by URL (TimelineWrapper.cpp:196-246: the media of an .otioz archive).
+    typedef std::map<std::string, MemoryReference> MemoryReferences;
+
     //! Registry path -> decoded frame, shared by all read nodes of a timeline.
     class MediaStore
     {
@@ -88,7 +100,8 @@ namespace toucan
     public:
         ImageReadNode(
             const std::filesystem::path&,
-            const std::shared_ptr<MediaStore>& = MediaStore::global());
+            const std::shared_ptr<MediaStore>& = MediaStore::global(),
+            const MemoryReference& = MemoryReference());
 
         virtual ~ImageReadNode();
 
@@ -101,6 +114,7 @@ namespace toucan
     private:
         std::filesystem::path _path;
         std::shared_ptr<MediaStore> _store;
+        MemoryReference _memory;
     };
 
     //! Image sequence read node.
@@ -115,7 +129,8 @@ namespace toucan
             int frameStep,
             double rate,
             int frameZeroPadding,
-            const std::shared_ptr<MediaStore>& = MediaStore::global());
+            const std::shared_ptr<MediaStore>& = MediaStore::global(),
+            const MemoryReferences& = MemoryReferences());
 
         virtual ~SequenceReadNode();
 
@@ -134,16 +149,18 @@ namespace toucan
         double _rate = 1.0;
         int _frameZeroPadding = 0;
         std::shared_ptr<MediaStore> _store;
+        MemoryReferences _memoryReferences;
     };
 
     //! Look a frame up in the store, falling back to the built-in file readers.
-    bool readMedia(const std::shared_ptr<MediaStore>&, const std::string& path, MediaFrame&);
+    bool readMedia(const std::shared_ptr<MediaStore>&, const std::string& path, MediaFrame&, const MemoryReference& = MemoryReference());
 
     //! Create a read node for a single image.  Throws std::runtime_error if the media cannot
     //! be opened (the caller logs it and the clip yields no node, ImageGraph.cpp:355-367).
     std::shared_ptr<IReadNode> createReadNode(
         const std::filesystem::path&,
-        const std::shared_ptr<MediaStore>& = MediaStore::global());
+        const std::shared_ptr<MediaStore>& = MediaStore::global(),
+        const MemoryReference& = MemoryReference());
 
     //! Create a read node for an image sequence.
     std::shared_ptr<IReadNode> createReadNode(
@@ -154,5 +171,6 @@ namespace toucan
         int frameStep,
         double rate,
         int frameZeroPadding,
-        const std::shared_ptr<MediaStore>& = MediaStore::global());
+        const std::shared_ptr<MediaStore>& = MediaStore::global(),
+        const MemoryReferences& = MemoryReferences());
 }

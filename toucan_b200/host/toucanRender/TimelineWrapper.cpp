@@ -4,21 +4,132 @@
 
 namespace toucan
 {
+    namespace
+    {
+        OTIO_NS::SerializableObject::Retainer<OTIO_NS::Timeline> timelineFromFile(const std::filesystem::path& path)
+        {
+            OTIO_NS::ErrorStatus errorStatus;
+            OTIO_NS::SerializableObject::Retainer<OTIO_NS::Timeline> out(
+                dynamic_cast<OTIO_NS::Timeline*>(OTIO_NS::Timeline::from_json_file(path.string(), &errorStatus)));
+            if (!out)
+            {
+                throw std::runtime_error(errorStatus.full_description);
+            }
+            return out;
+        }
+    }
+
     TimelineWrapper::TimelineWrapper(const std::filesystem::path& path) :
         _path(path),
         _store(MediaStore::global())
     {
         const std::string extension = toLower(_path.extension().string());
-        if (".otio" != extension)
+        if (".otio" == extension)
         {
-            throw std::runtime_error("Unrecognized file");
+            _timeline = timelineFromFile(_path);
         }
-        OTIO_NS::ErrorStatus errorStatus;
-        _timeline = OTIO_NS::SerializableObject::Retainer<OTIO_NS::Timeline>(
-            dynamic_cast<OTIO_NS::Timeline*>(OTIO_NS::Timeline::from_json_file(_path.string(), &errorStatus)));
-        if (!_timeline)
+        else if (".otiod" == extension)
         {
-            throw std::runtime_error(errorStatus.full_description);
+            // an unpacked bundle: content.otio + media/ inside the directory (TimelineWrapper.cpp:84-95)
+            _path = _path / "content.otio";
+            _timeline = timelineFromFile(_path);
+        }
+        else if (".otioz" == extension)
+        {
+            // TimelineWrapper.cpp:146-246: map the archive, inflate content.otio, reference the stored media in place
+            _archive = std::make_shared<ZipArchive>(path);
+            const ZipArchive::Entry* content = _archive->find("content.otio");
+            if (!content)
+            {
+                throw std::runtime_error("Cannot locate: content.otio");
+            }
+            const std::vector<unsigned char> json = _archive->read(*content);
+            OTIO_NS::ErrorStatus errorStatus;
+            _timeline = OTIO_NS::SerializableObject::Retainer<OTIO_NS::Timeline>(dynamic_cast<OTIO_NS::Timeline*>(
+                OTIO_NS::Timeline::from_json_string(std::string(json.begin(), json.end()), &errorStatus)));
+            if (!_timeline)
+            {
+                throw std::runtime_error(errorStatus.full_description);
+            }
+            // URLs inside an archive are only meaningful for this timeline: a private store
+            _store = std::make_shared<MediaStore>();
+            auto reference = [this](const std::string& url)
+            {
+                const std::string name = splitURLProtocol(url).second;
+                const ZipArchive::Entry* entry = _archive->find(name);
+                if (!entry)
+                {
+                    throw std::runtime_error("Cannot locate: " + name);
+                }
+                if (entry->method != 0)
+                {
+                    throw std::runtime_error("Media is not uncompressed: " + name);
+                }
+                MemoryReference memory;
+                memory.owner = _archive;
+                memory.data = _archive->data() + entry->dataOffset;
+                memory.size = entry->size;
+                _memoryReferences[url] = memory;
+            };
+            for (const auto& clip : _timeline->find_clips())
+            {
+                if (auto externalRef = dynamic_cast<OTIO_NS::ExternalReference*>(clip->media_reference()))
+                {
+                    reference(externalRef->target_url());
+                }
+                else if (auto sequenceRef = dynamic_cast<OTIO_NS::ImageSequenceReference*>(clip->media_reference()))
+                {
+                    const OTIO_NS::TimeRange timeRange = clip->available_range();
+                    for (int64_t frame = static_cast<int64_t>(timeRange.start_time().value());
+                        frame <= static_cast<int64_t>(timeRange.end_time_inclusive().value());
+                        ++frame)
+                    {
+                        reference(getSequenceFrame(
+                            sequenceRef->target_url_base(),
+                            sequenceRef->name_prefix(),
+                            static_cast<int>(frame),
+                            sequenceRef->frame_zero_padding(),
+                            sequenceRef->name_suffix()));
+                    }
+                }
+            }
+        }
+        else if (hasExtension(extension, ImageReadNode::getExtensions()))
+        {
+            // an image or a numbered image sequence opened as a one-clip timeline (TimelineWrapper.cpp:262-306)
+            const auto sequence = getSequence(path);
+            const auto split = splitFileNameNumber(sequence.front().stem().string());
+            _timeline = OTIO_NS::SerializableObject::Retainer<OTIO_NS::Timeline>(new OTIO_NS::Timeline);
+            OTIO_NS::SerializableObject::Retainer<OTIO_NS::Track> track(new OTIO_NS::Track);
+            _timeline->tracks()->append_child(OTIO_NS::SerializableObject::Retainer<OTIO_NS::Composable>(track.value));
+            OTIO_NS::SerializableObject::Retainer<OTIO_NS::Clip> clip(new OTIO_NS::Clip);
+            track->append_child(OTIO_NS::SerializableObject::Retainer<OTIO_NS::Composable>(clip.value));
+            if (split.second.empty())
+            {
+                clip->set_media_reference(new OTIO_NS::ExternalReference(path.string()));
+                clip->set_source_range(OTIO_NS::TimeRange(OTIO_NS::RationalTime(0.0, 24.0), OTIO_NS::RationalTime(1.0, 24.0)));
+            }
+            else
+            {
+                const int start = std::atoi(split.second.c_str());
+                const double rate = 24.0;
+                clip->set_media_reference(new OTIO_NS::ImageSequenceReference(
+                    sequence.front().parent_path().string(),
+                    split.first,
+                    sequence.front().extension().string(),
+                    start,
+                    1,
+                    rate,
+                    static_cast<int>(getNumberPadding(split.second))));
+                clip->set_source_range(OTIO_NS::TimeRange(
+                    OTIO_NS::RationalTime(start, rate),
+                    OTIO_NS::RationalTime(static_cast<double>(sequence.size()), rate)));
+            }
+        }
+        else
+        {
+            // movie and SVG front-ends need FFmpeg / lunasvg decoders: outside this path
+            throw std::runtime_error("Unrecognized file");
         }
         _init();
     }
@@ -59,6 +170,10 @@ namespace toucan
 
     std::string TimelineWrapper::getMediaPath(const std::string& url) const
     {
+        if (_archive)
+        {
+            return url; // in-memory media are keyed by their URL (TimelineWrapper.cpp:339-342)
+        }
         std::filesystem::path path = splitURLProtocol(url).second;
         if (!path.is_absolute())
         {
@@ -72,7 +187,11 @@ namespace toucan
         std::shared_ptr<IReadNode> out;
         if (auto externalRef = dynamic_cast<const OTIO_NS::ExternalReference*>(ref))
         {
-            out = toucan::createReadNode(getMediaPath(externalRef->target_url()), _store);
+            const auto memory = _memoryReferences.find(externalRef->target_url());
+            out = toucan::createReadNode(
+                getMediaPath(externalRef->target_url()),
+                _store,
+                memory != _memoryReferences.end() ? memory->second : MemoryReference());
         }
         else if (auto sequenceRef = dynamic_cast<const OTIO_NS::ImageSequenceReference*>(ref))
         {
@@ -84,7 +203,8 @@ namespace toucan
                 sequenceRef->frame_step(),
                 sequenceRef->rate(),
                 sequenceRef->frame_zero_padding(),
-                _store);
+                _store,
+                _memoryReferences);
         }
         return out;
     }

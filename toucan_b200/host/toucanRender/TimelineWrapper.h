@@ -1,10 +1,12 @@
 // Opens a timeline and resolves its media.  Interface parity:
-// lib/toucanRender/TimelineWrapper.h:21-52.  In scope: .otio files (and, as an extension for
-// tests and synthetic workloads, a timeline given as a JSON string).  The .otiod/.otioz
-// archive front-ends and the movie/image "open as timeline" conveniences are outside the hot
-// path and throw "Unrecognized file".
+// lib/toucanRender/TimelineWrapper.h:21-52.  Opens .otio files, .otiod directories, .otioz
+// archives (media referenced in place inside the memory-mapped ZIP), single images and
+// numbered image sequences (as one-clip timelines) and, as an extension for tests and
+// synthetic workloads, a timeline given as a JSON string.  Movie and SVG files need the
+// FFmpeg / lunasvg decoders and throw "Unrecognized file".
 #pragma once
 
+#include <toucanRender/Archive.h>
 #include <toucanRender/Read.h>
 
 #include <opentimelineio/otio.h>
@@ -45,6 +47,8 @@ namespace toucan
         OTIO_NS::SerializableObject::Retainer<OTIO_NS::Timeline> _timeline;
         OTIO_NS::TimeRange _timeRange;
         std::shared_ptr<MediaStore> _store;
+        std::shared_ptr<ZipArchive> _archive;
+        MemoryReferences _memoryReferences;
     };
 
     //! Get the video clips of a timeline, track by track (lib/toucanRender/TimelineAlgo.cpp:10-26).

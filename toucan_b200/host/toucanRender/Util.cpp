@@ -1,5 +1,7 @@
 #include "Util.h"
 
+#include <map>
+
 #include <algorithm>
 #include <cctype>
 #include <cstdlib>
@@ -56,6 +58,33 @@ namespace toucan
     size_t getNumberPadding(const std::string& value)
     {
         return (!value.empty() && '0' == value[0]) ? value.size() : 0;
+    }
+
+    std::vector<std::filesystem::path> getSequence(const std::filesystem::path& path)
+    {
+        // Util.cpp:88-121: same prefix, same zero padding, same extension; ordered by number
+        const auto split = splitFileNameNumber(path.stem().string());
+        if (split.second.empty())
+        {
+            return { path };
+        }
+        std::map<int64_t, std::filesystem::path> byNumber;
+        const size_t padding = getNumberPadding(split.second);
+        const std::filesystem::path directory = path.parent_path().empty() ? std::filesystem::path(".") : path.parent_path();
+        for (const auto& entry : std::filesystem::directory_iterator(directory))
+        {
+            if (!entry.is_regular_file()) continue;
+            const auto other = splitFileNameNumber(entry.path().stem().string());
+            if (other.first == split.first && !other.second.empty() && getNumberPadding(other.second) == padding &&
+                entry.path().extension() == path.extension())
+            {
+                byNumber[std::atoi(other.second.c_str())] = entry.path();
+            }
+        }
+        std::vector<std::filesystem::path> out;
+        for (const auto& i : byNumber) out.push_back(i.second);
+        if (out.empty()) out.push_back(path);
+        return out;
     }
 
     IMATH_NAMESPACE::Box2i fit(const IMATH_NAMESPACE::V2i& a, const IMATH_NAMESPACE::V2i& b)

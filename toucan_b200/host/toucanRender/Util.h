@@ -29,6 +29,9 @@ namespace toucan
     std::pair<std::string, std::string> splitFileNameNumber(const std::string&);
     size_t getNumberPadding(const std::string&);
 
+    //! The files of the numbered sequence `path` belongs to, in frame order (the path alone if its stem has no number).
+    std::vector<std::filesystem::path> getSequence(const std::filesystem::path&);
+
     //! Fit box b inside a (aspect preserved, integer truncation, centred).
     IMATH_NAMESPACE::Box2i fit(const IMATH_NAMESPACE::V2i& a, const IMATH_NAMESPACE::V2i& b);
 

@@ -4,6 +4,7 @@
 #include "ImageEffectHost.h"
 #include "FrameScheduler.h"
 #include "ImageGraph.h"
+#include "JpegRead.h"
 #include "PngRead.h"
 #include "StackFusion.h"
 #include "TimelineWrapper.h"
@@ -373,6 +374,25 @@ extern "C"
             if (out)
             {
                 if (bytes > capacity) return fail("tr_decode_png: output buffer too small");
+                memcpy(out, frame.host, bytes);
+            }
+            return 0;
+        });
+    }
+
+    int tr_decode_jpeg(const char* path, void* out, size_t capacity, int* width, int* height, int* type)
+    {
+        if (!path) return fail("tr_decode_jpeg: null");
+        return guarded([&] {
+            MediaFrame frame;
+            if (!readJpeg(path, frame)) return fail(std::string("tr_decode_jpeg: cannot read ") + path);
+            if (width) *width = frame.width;
+            if (height) *height = frame.height;
+            if (type) *type = frame.format;
+            const size_t bytes = tc_image_bytes(frame.width, frame.height, frame.format);
+            if (out)
+            {
+                if (bytes > capacity) return fail("tr_decode_jpeg: output buffer too small");
                 memcpy(out, frame.host, bytes);
             }
             return 0;

@@ -40,6 +40,7 @@ _SIGS = {
     "tr_timeline_describe": [_VP, _VP, ctypes.c_double, ctypes.c_char_p, ctypes.c_size_t],
     "tr_timeline_render": [_VP, _VP, ctypes.c_double, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_decode_png": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
+    "tr_decode_jpeg": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_timeline_render_resident": [_VP, _VP, ctypes.c_double, ctypes.POINTER(_VP), _IP, _IP, _IP],
 }
 FRAME_CALLBACK = ctypes.CFUNCTYPE(None, _VP, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int)
@@ -119,6 +120,15 @@ def decode_png(path: str) -> np.ndarray:
     _check(lib().tr_decode_png(path.encode(), None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_png")
     out = np.empty((h.value, w.value, 4), _NP_OF[t.value])
     _check(lib().tr_decode_png(path.encode(), out.ctypes.data, out.nbytes, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_png")
+    return out
+
+
+def decode_jpeg(path: str) -> np.ndarray:
+    """The C++ host's built-in JPEG reader (RGBA u8, A = 255; libjpeg's default decode, bit for bit)."""
+    w, h, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _check(lib().tr_decode_jpeg(path.encode(), None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_jpeg")
+    out = np.empty((h.value, w.value, 4), _NP_OF[t.value])
+    _check(lib().tr_decode_jpeg(path.encode(), out.ctypes.data, out.nbytes, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_jpeg")
     return out
 
 
