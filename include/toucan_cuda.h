@@ -158,6 +158,15 @@ int tc_convert(const tc_image* dst, const tc_image* src, tc_stream s);
    channels: 3 (alpha dropped) or 4. */
 int tc_pack_raw(void* dst_dev, const tc_image* src, int type, int channels, tc_stream s);
 
+/* ---- draw (plugins/DrawPlugin.cpp) ---------------------------------------------------
+   copy(src -> dst) + ImageBufAlgo::render_box / render_line: "colour over pixel"
+   r[c] = color[c] + r[c] * (1 - color[3]) (plain store when color[3] == 1), clipped to the image.
+   Box: corners inclusive; filled, or four skip-first lines; a single point when the corners coincide.
+   Line: integer Bresenham walk from (x1, y1) to (x2, y2).  DrawPlugin.cpp:198-233, :306-341 */
+int tc_draw_box(const tc_image* dst, const tc_image* src, int x1, int y1, int x2, int y2, const float color[4], int fill, tc_stream s);
+int tc_draw_line(const tc_image* dst, const tc_image* src, int x1, int y1, int x2, int y2, const float color[4], int skip_first_point,
+                 tc_stream s);
+
 /* y4m output conversion on the device                     bin/toucan-render/App.cpp:37-43,340-485
    The reference pastes the frame into a u8/u16 RGB(A) buffer (ImageBufAlgo::paste) and runs
    libswscale (FFmpeg 8.0, SWS_FAST_BILINEAR) RGB24->YUV422P | RGB24->YUV444P | RGBA->YUVA444P |

@@ -278,6 +278,16 @@ def _int2(meta, key):
     return [0, 0]
 
 
+def _bool_as_int(meta, key, local):
+    """`int x = local; paramGetValue(h, &x)`: a bool is written into the low byte, an integer into the whole int."""
+    v = meta.get(key)
+    if isinstance(v, bool):
+        return (local & ~0xff) | int(v)
+    if _is_int(v):
+        return v & 0xffffffff
+    return local
+
+
 def _dbl(meta, key, described, local=None):
     v = meta.get(key)
     if v is None:
@@ -293,7 +303,8 @@ def _str(meta, key, described):
 GENERATORS = {"toucan:Fill", "toucan:Checkers", "toucan:Gradient", "toucan:Noise"}
 FILTERS = {"toucan:Blur", "toucan:ColorMap", "toucan:Invert", "toucan:Pow", "toucan:Saturate",
            "toucan:UnsharpMask", "toucan:Crop", "toucan:Flip", "toucan:Flop", "toucan:Resize",
-           "toucan:Rotate", "toucan:ColorConvert", "toucan:Premult", "toucan:Unpremult"}
+           "toucan:Rotate", "toucan:ColorConvert", "toucan:Premult", "toucan:Unpremult",
+           "toucan:Box", "toucan:Line", "toucan:Text"}
 TRANSITIONS = {"toucan:Dissolve", "toucan:HorizontalWipe", "toucan:VerticalWipe"}
 KNOWN = GENERATORS | FILTERS | TRANSITIONS
 
@@ -548,6 +559,15 @@ class ImageGraph:
                 pm = meta.get("premult")
                 return O.colorconvert(canvas, _str(meta, "fromspace", ""), _str(meta, "tospace", ""),
                                       unpremult=bool(pm) if isinstance(pm, bool) else False)
+            if name == "toucan:Box":
+                return O.draw_box(canvas, _int2(meta, "pos1"), _int2(meta, "pos2"), _rgba(meta, "color", 1.0), _bool_as_int(meta, "fill", 0))
+            if name == "toucan:Line":
+                return O.draw_line(canvas, _int2(meta, "pos1"), _int2(meta, "pos2"), _rgba(meta, "color", 1.0),
+                                   _bool_as_int(meta, "skip_first_point", 0))
+            if name == "toucan:Text":
+                # render_text needs FreeType and a font file; without a font it draws nothing and the plug-in
+                # ignores the failure (DrawPlugin.cpp:436-452): the output is the copy of the source
+                return np.ascontiguousarray(canvas.copy())
             if name == "toucan:Premult":
                 return O.premult(canvas)
             if name == "toucan:Unpremult":

@@ -160,6 +160,17 @@ def gauss_kernel(width):
     return k
 
 
+# --- draw (DrawPlugin.cpp) --------------------------------------------------------------
+def draw_box(src, pos1, pos2, color, fill=True):
+    c = (ctypes.c_float * 4)(*[float(v) for v in color])
+    return _unary(lib().o_draw_box, src, int(pos1[0]), int(pos1[1]), int(pos2[0]), int(pos2[1]), c, 1 if fill else 0)
+
+
+def draw_line(src, pos1, pos2, color, skip_first_point=False):
+    c = (ctypes.c_float * 4)(*[float(v) for v in color])
+    return _unary(lib().o_draw_line, src, int(pos1[0]), int(pos1[1]), int(pos2[0]), int(pos2[1]), c, 1 if skip_first_point else 0)
+
+
 # --- transforms (TransformPlugin.cpp) --------------------------------------------------
 def crop(src, pos, size):
     return _unary(lib().o_crop, src, int(pos[0]), int(pos[1]), int(size[0]), int(size[1]), size=size)

@@ -588,6 +588,86 @@ int o_unsharp(oimg* dst, const oimg* src, float width, float contrast, float thr
 }
 
 /* ------------------------------------------------------------------------- */
+
+/* 9.x draw -- plugins/DrawPlugin.cpp:198-233 (Box), :306-341 (Line): copy(out, src) then
+   ImageBufAlgo::render_box / render_line [V: OIIO 3.0 imagebufalgo_draw.cpp].  A drawn pixel is
+   "colour over pixel": r[c] = color[c] + r[c] * (1 - alpha), alpha = color[3]; a plain store when
+   alpha == 1.  Everything is clipped to the image. */
+static void draw_point(oimg* im, int x, int y, const float* color)
+{
+    if (x < 0 || y < 0 || x >= im->w || y >= im->h) return;
+    float p[NCH];
+    ldpx(im, x, y, p);
+    const float alpha = color[3];
+    if (alpha == 1.0f) {
+        for (int c = 0; c < NCH; ++c) p[c] = color[c];
+    } else {
+        const float oma = 1.0f - alpha;
+        for (int c = 0; c < NCH; ++c) p[c] = color[c] + p[c] * oma;
+    }
+    stpx(im, x, y, p);
+}
+static void copy_into(oimg* dst, const oimg* src)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < dst->h; ++y)
+        for (int x = 0; x < dst->w; ++x) {
+            float p[NCH];
+            ldpx_black(src, x, y, p);
+            stpx(dst, x, y, p);
+        }
+}
+/* the integer Bresenham walk of OIIO's bresenham2d, first point optionally skipped */
+static void draw_line(oimg* im, int x1, int y1, int x2, int y2, const float* color, int skip_first)
+{
+    int dx = abs(x2 - x1), dy = abs(y2 - y1);
+    const int xinc = x1 > x2 ? -1 : 1, yinc = y1 > y2 ? -1 : 1;
+    if (dx >= dy) {
+        const int dpr = dy << 1, dpru = dpr - (dx << 1);
+        int delta = dpr - dx;
+        for (; dx >= 0; --dx) {
+            if (skip_first) skip_first = 0;
+            else draw_point(im, x1, y1, color);
+            x1 += xinc;
+            if (delta > 0) { y1 += yinc; delta += dpru; }
+            else delta += dpr;
+        }
+    } else {
+        const int dpr = dx << 1, dpru = dpr - (dy << 1);
+        int delta = dpr - dy;
+        for (; dy >= 0; --dy) {
+            if (skip_first) skip_first = 0;
+            else draw_point(im, x1, y1, color);
+            y1 += yinc;
+            if (delta > 0) { x1 += xinc; delta += dpru; }
+            else delta += dpr;
+        }
+    }
+}
+void o_draw_line(oimg* dst, const oimg* src, int x1, int y1, int x2, int y2, const float* color, int skip_first)
+{
+    copy_into(dst, src);
+    draw_line(dst, x1, y1, x2, y2, color, skip_first);
+}
+void o_draw_box(oimg* dst, const oimg* src, int x1, int y1, int x2, int y2, const float* color, int fill)
+{
+    copy_into(dst, src);
+    if (x1 == x2 && y1 == y2) {
+        draw_point(dst, x1, y1, color);
+        return;
+    }
+    if (fill) {
+        /* roi_intersection(image, ROI(x1, x2 + 1, y1, y2 + 1)) */
+        for (int y = y1 > 0 ? y1 : 0; y < (y2 + 1 < dst->h ? y2 + 1 : dst->h); ++y)
+            for (int x = x1 > 0 ? x1 : 0; x < (x2 + 1 < dst->w ? x2 + 1 : dst->w); ++x) draw_point(dst, x, y, color);
+        return;
+    }
+    draw_line(dst, x1, y1, x2, y1, color, 1);
+    draw_line(dst, x2, y1, x2, y2, color, 1);
+    draw_line(dst, x2, y2, x1, y2, color, 1);
+    draw_line(dst, x1, y2, x1, y1, color, 1);
+}
+
 /* 9.5 geometry */
 
 /* cut + copy -- TransformPlugin.cpp:197-200: out(x,y) = src(pos+x, pos+y), 0 outside src */

@@ -25,7 +25,7 @@ REF = "/root/reference/data"
 from oracle import graph as G  # noqa: E402
 from tests import media  # noqa: E402
 
-SKIP = {"Draw.otio"}  # toucan:Box / Line / Text are out of scope
+SKIP = set()  # Draw.otio: Box and Line are drawn; Text copies its source (no FreeType / font: what render_text leaves when it finds no font)
 
 
 def main():

@@ -16,6 +16,7 @@ IDENTIFIERS = {
     "toucan:Crop", "toucan:Flip", "toucan:Flop", "toucan:Resize", "toucan:Rotate",
     "toucan:Dissolve", "toucan:HorizontalWipe", "toucan:VerticalWipe",
     "toucan:ColorConvert", "toucan:Premult", "toucan:Unpremult",
+    "toucan:Box", "toucan:Line", "toucan:Text",  # SURVEY 8 row f3 (Text copies its source: no FreeType / font here)
 }
 
 
@@ -42,7 +43,7 @@ def test_render_abi_exports(built):
 
 
 def test_host_loads_all_effects(host):
-    # the 21 in-scope plug-in identifiers of SURVEY 8b, served by 5 *.ofx modules
+    # the 21 in-scope plug-in identifiers of SURVEY 8b plus the three Draw effects, served by 6 *.ofx modules
     assert set(host.identifiers()) == IDENTIFIERS
 
 
@@ -53,7 +54,7 @@ def test_ofx_modules_export_entry_points(built):
 
     capi.lib()
     mods = sorted(f for f in os.listdir(render.PLUGIN_DIR) if f.endswith(".ofx"))
-    assert len(mods) == 5
+    assert len(mods) == 6
     total = 0
     for m in mods:
         so = ctypes.CDLL(os.path.join(render.PLUGIN_DIR, m))
@@ -61,7 +62,7 @@ def test_ofx_modules_export_entry_points(built):
         n = so.OfxGetNumberOfPlugins()
         assert n >= 3 and hasattr(so, "OfxGetPlugin")
         total += n
-    assert total == 21
+    assert total == 24
 
 
 @pytest.mark.parametrize("name", sorted(GOLD))

@@ -310,3 +310,55 @@ def test_stack_rejects_what_it_cannot_fuse(T):
         T.stack_f32(64, 48, [0, 0, 0, 1], [(a, b, 10.0, 4.0, 0.5)])
     with pytest.raises(capi.TcError):  # radius beyond the fused kernel's range
         T.stack_f32(64, 48, [0, 0, 0, 1], [(a, None, 60.0, 0.0, 0.0)])
+
+
+# ---- draw (plugins/DrawPlugin.cpp) -------------------------------------------------
+@pytest.mark.parametrize("dt", NP_TYPES)
+def test_draw_box_bit_exact(dt):
+    from toucan_b200 import ops
+
+    w, h = 97, 61
+    src = rand_img(w, h, dt, 40)
+    cases = [((10, 8), (60, 40), (0.8, 0.0, 0.3, 1.0), True),       # opaque fill
+             ((10, 8), (60, 40), (0.4, 0.1, 0.3, 0.5), True),       # "over" with alpha < 1
+             ((-20, -5), (30, 200), (0.2, 0.9, 0.3, 0.25), True),   # clipped on three sides
+             ((60, 40), (10, 8), (1.0, 1.0, 1.0, 1.0), True),       # corners out of order: empty ROI
+             ((5, 5), (90, 55), (0.9, 0.5, 0.1, 0.7), False),       # outline = four skip-first lines
+             ((-3, 20), (120, 70), (0.9, 0.5, 0.1, 1.0), False),    # outline partly outside
+             ((33, 12), (33, 12), (0.1, 0.2, 0.3, 0.4), True),      # degenerate: one point
+             ((200, 200), (200, 200), (0.1, 0.2, 0.3, 0.4), False)]  # a point outside the image
+    for p1, p2, color, fill in cases:
+        assert_exact(ops.draw_box(to_dev(src), p1, p2, color, fill), O.draw_box(src, p1, p2, color, fill), f"box {p1} {p2} {color} {fill}")
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.float32])
+def test_draw_line_matches_the_sequential_bresenham_walk(dt):
+    """Every step of the line is an independent thread (closed-form minor-axis advance); the oracle walks OIIO's
+    sequential Bresenham loop.  All octants, degenerate and clipped lines, with and without the first point."""
+    from toucan_b200 import ops
+
+    w, h = 83, 59
+    src = rand_img(w, h, dt, 41)
+    rng = np.random.default_rng(42)
+    lines = [((0, 0), (82, 58)), ((82, 58), (0, 0)), ((0, 58), (82, 0)), ((10, 5), (10, 50)), ((70, 30), (3, 30)), ((4, 4), (4, 4)),
+             ((-30, 10), (120, 44)), ((40, -20), (45, 90)), ((0, 0), (82, 1)), ((0, 0), (1, 58)), ((5, 7), (6, 8)), ((20, 20), (21, 20))]
+    lines += [(tuple(rng.integers(-20, 110, 2).tolist()), tuple(rng.integers(-20, 90, 2).tolist())) for _ in range(60)]
+    for i, (p1, p2) in enumerate(lines):
+        color = (0.9, 0.5, 0.1, 1.0) if i % 2 else (0.3, 0.2, 0.1, 0.6)
+        for skip in (False, True):
+            assert_exact(ops.draw_line(to_dev(src), p1, p2, color, skip), O.draw_line(src, p1, p2, color, skip), f"line {p1} {p2} skip={skip}")
+
+
+def test_draw_long_lines_at_8k():
+    """BASELINE size: a diagonal across a 7680x4320 frame (7680 threads), checked through its drawn pixels only."""
+    from toucan_b200 import ops
+
+    w, h = 7680, 4320
+    src = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    out = ops.draw_line(src, (0, 0), (w - 1, h - 1), (1.0, 1.0, 1.0, 1.0))
+    ys, xs = torch.nonzero(out[..., 0], as_tuple=True)
+    assert xs.numel() == w and torch.equal(torch.sort(xs).values, torch.arange(w, device="cuda"))  # one pixel per column
+    want = O.draw_line(np.zeros((64, 114, 4), np.uint8), (0, 0), (113, 63), (1.0, 1.0, 1.0, 1.0))  # same slope class, small
+    small = ops.draw_line(torch.zeros((64, 114, 4), dtype=torch.uint8, device="cuda"), (0, 0), (113, 63), (1.0, 1.0, 1.0, 1.0))
+    assert np.array_equal(small.cpu().numpy(), want)
+    assert int(ys.max()) == h - 1 and int(ys.min()) == 0

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 GOLD = TL.golden()
 # timelines whose every node is in the bit-exact class
 EXACT = {"Transition.otio", "Transition2.otio", "TransitionWipe.otio", "CompositeTracks.otio", "Gap.otio", "Generator.otio",
-         "LinearTimeWarp.otio", "Markers.otio", "MissingMedia.otio", "MissingMedia2.otio"}
+         "LinearTimeWarp.otio", "Markers.otio", "MissingMedia.otio", "MissingMedia2.otio", "Draw.otio"}
 TOLERANT = {"Filter.otio", "MultipleEffects.otio", "Transform.otio", "ColorSpace.otio"}
 
 

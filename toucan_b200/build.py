@@ -37,6 +37,7 @@ CU_FILES = {
     "tc_conv.cu": [],
     "tc_stack.cu": [],
     "tc_y4m.cu": [],
+    "tc_draw.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
 }
 CPP_KERNEL_FILES = ["tc_tables.cpp"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"),
@@ -103,6 +104,7 @@ PLUGIN_MODULES = {
     "toucanTransformPlugin.ofx": ["TransformPlugin.cpp"],
     "toucanTransitionPlugin.ofx": ["TransitionPlugin.cpp"],
     "toucanColorPlugin.ofx": ["ColorPlugin.cpp"],
+    "toucanDrawPlugin.ofx": ["DrawPlugin.cpp"],
 }
 
 

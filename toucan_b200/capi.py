@@ -63,6 +63,8 @@ _SIGS = {
     "tc_convert": [_IMG, _IMG, _S],
     "tc_pack_raw": [ctypes.c_void_p, _IMG, ctypes.c_int, ctypes.c_int, _S],
     "tc_rgb_to_y4m": [ctypes.c_void_p, _IMG, ctypes.c_int, _S],
+    "tc_draw_box": [_IMG, _IMG, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F4, ctypes.c_int, _S],
+    "tc_draw_line": [_IMG, _IMG, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F4, ctypes.c_int, _S],
     "tc_stack_f32": [_IMG, _F4, ctypes.POINTER(tc_stack_layer), ctypes.c_int, _S],
     "tc_set_device": [ctypes.c_int],
     "tc_device_count": [ctypes.POINTER(ctypes.c_int)],

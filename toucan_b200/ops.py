@@ -175,6 +175,15 @@ def convert(src, t, size=None):
     return out
 
 
+def draw_box(src, pos1, pos2, color, fill=True):
+    return _unary(lib().tc_draw_box, "tc_draw_box", src, int(pos1[0]), int(pos1[1]), int(pos2[0]), int(pos2[1]), f4(color), 1 if fill else 0)
+
+
+def draw_line(src, pos1, pos2, color, skip_first_point=False):
+    return _unary(lib().tc_draw_line, "tc_draw_line", src, int(pos1[0]), int(pos1[1]), int(pos2[0]), int(pos2[1]), f4(color),
+                  1 if skip_first_point else 0)
+
+
 def y4m_planes(buf, fmt, w, h):
     """Split the bytes of one y4m frame (host or device uint8 tensor / numpy array) into its planes."""
     cw = (w + 1) // 2 if fmt == "422" else w
