@@ -14,8 +14,12 @@
 // sinpif -- the difference is far above the 1e-5 tolerance.
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "tc_common.cuh"
+#include "tc_tile.cuh"
 
 namespace tc {
 
@@ -149,6 +153,130 @@ __global__ void __launch_bounds__(256) k_resize_cols(const float4* __restrict__ 
     store_px(dst.p, dst.type, (size_t)y * dst.w + x, pel);
 }
 
+// The same two passes fused through shared memory (the north-star layout for Resize: a filtered-resample
+// gather through a shared-memory tile).  A CTA owns a 32 x th block of the destination (th chosen so the
+// block's source footprint is at most 32 rows): it stages the footprint once (clamped, converted to float),
+// runs the row pass into a second, transposed shared tile and the column pass from there -- same weights,
+// same accumulation order as the two kernels above, so the results are identical to theirs; the float
+// scratch image and its HBM round trip are gone.
+//   row pass:    lane = source row, warp = destination column.  Row strides are odd multiples of 16 bytes,
+//                so the 32 rows of one column are bank-conflict free whatever the resize ratio, and the
+//                column's weights are warp-uniform (a zero weight -- which the reference skips -- is a
+//                uniform branch, not a per-lane select);
+//   column pass: lane = destination column, warp = destination row; again uniform weights.
+constexpr int RT_W = 32, RT_ROWS = 32, RT_MH = 33, RT_MAXT = 16, RT_THREADS = 512, RT_MAXH = 32;
+
+struct ResizeTile {
+    int sw;       // shared source tile columns (allocation)
+    int th;       // destination rows per CTA
+    int xtaps, ytaps;
+};
+
+static size_t resize_tile_smem(int sw)
+{
+    return ((size_t)RT_ROWS * (sw | 1) + (size_t)RT_W * RT_MH) * sizeof(float4) + ((size_t)RT_W * RT_MAXT + (size_t)RT_MAXH * RT_MAXT) * sizeof(float) +
+           (RT_W + RT_MAXH) * sizeof(int);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(RT_THREADS) k_resize_tile(const Img src_, const Img dst, const int* __restrict__ xf, const float* __restrict__ xw,
+                                                             const float* __restrict__ xt, const int* __restrict__ yf,
+                                                             const float* __restrict__ yw, const float* __restrict__ yt, const ResizeTile T)
+{
+    extern __shared__ float4 rt_smem[];
+    const Img src { src_.p, src_.w, src_.h, TYPE }; // storage type known at compile time: one load path
+    const int swp = T.sw | 1;
+    float4* S = rt_smem;                                 // [RT_ROWS][swp]
+    float4* Mt = S + (size_t)RT_ROWS * swp;              // [RT_W][RT_MH]: row-pass results, transposed
+    float* wxs = reinterpret_cast<float*>(Mt + RT_W * RT_MH); // [RT_W][RT_MAXT]
+    float* wys = wxs + RT_W * RT_MAXT;                   // [RT_MAXH][RT_MAXT]
+    int* fxs = reinterpret_cast<int*>(wys + RT_MAXH * RT_MAXT); // [RT_W]  first tap, relative to the tile
+    int* fys = fxs + RT_W;                               // [RT_MAXH]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * T.th;
+    const int nx = min(RT_W, dst.w - x0), ny = min(T.th, dst.h - y0);
+    const int fx0 = xf[x0], fy0 = yf[y0];
+    const int cols = min(xf[x0 + nx - 1] + T.xtaps - fx0, T.sw);
+    const int rows = min(yf[y0 + ny - 1] + T.ytaps - fy0, RT_ROWS);
+    // stage the footprint: a warp per source row (coalesced along the row), edge-clamped like the per-tap clamp of
+    // the two-pass kernels.  Every load of the thread (32 / warps rows x 3 spans cover 32 rows x 96 columns) is issued before
+    // anything waits on one, and the weight tables are fetched while those loads are in flight.
+    constexpr int WARPS = RT_THREADS / 32;
+    constexpr int KR = RT_ROWS / WARPS, KT = RT_W * RT_MAXT / RT_THREADS;
+    float4 v[KR][3];
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+        const size_t rbase = (size_t)min(max(fy0 + min(warp + k * WARPS, rows - 1), 0), src.h - 1) * src.w;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int sx = min(max(fx0 + min(q * 32 + lane, cols - 1), 0), src.w - 1);
+            v[k][q] = load_px(src.p, TYPE, rbase + sx);
+        }
+    }
+    // per-axis tables of this block; a column / row whose weights do not sum (zero total) produces 0
+    float wv[KT], hv[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const int i = tid + k * RT_THREADS;
+        const int x = i / RT_MAXT, t = i - x * RT_MAXT; // also the (row, tap) split of the y table
+        wv[k] = (t < T.xtaps && x < nx && xt[(x0 + x) * 2 + 1] != 0.0f) ? xw[(size_t)(x0 + x) * T.xtaps + t] : 0.0f;
+        hv[k] = (t < T.ytaps && x < ny && yt[(y0 + x) * 2 + 0] != 0.0f) ? yw[(size_t)(y0 + x) * T.ytaps + t] : 0.0f;
+    }
+    int first = 0;
+    if (tid < RT_W) first = min(xf[min(x0 + tid, dst.w - 1)] - fx0, T.sw - T.xtaps);
+    else if (tid < RT_W + RT_MAXH) first = min(yf[min(y0 + tid - RT_W, dst.h - 1)] - fy0, RT_ROWS - T.ytaps);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        wxs[tid + k * RT_THREADS] = wv[k];
+        wys[tid + k * RT_THREADS] = hv[k];
+    }
+    if (tid < RT_W + RT_MAXH) fxs[tid] = first; // fys follows fxs
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+        const int r = warp + k * WARPS;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int c = q * 32 + lane;
+            if (r < rows && c < cols) S[(size_t)r * swp + c] = v[k][q];
+        }
+    }
+    // wider footprints (a resize ratio above ~2.5 along x): the remaining columns, one span at a time
+    for (int c = 96 + lane; c < cols; c += 32) {
+        const int sx = min(max(fx0 + c, 0), src.w - 1);
+        for (int r = warp; r < rows; r += WARPS) S[(size_t)r * swp + c] = load_px(src.p, TYPE, (size_t)min(max(fy0 + r, 0), src.h - 1) * src.w + sx);
+    }
+    __syncthreads();
+    // row pass: Mt(x, r) = sum_i wx_i(x) * S(r, fx(x) + i)
+    {
+        const float4* row = S + (size_t)min(lane, rows - 1) * swp;
+        for (int x = warp; x < RT_W; x += WARPS) {
+            const float4* p = row + fxs[x];
+            const float* w = wxs + x * RT_MAXT;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int t = 0; t < T.xtaps; ++t) {
+                const float wt = w[t];
+                if (wt != 0.0f) acc = fma4p(wt, p[t], acc);
+            }
+            Mt[x * RT_MH + lane] = acc;
+        }
+    }
+    __syncthreads();
+    // column pass: dst(x, y) = sum_j wy_j(y) * Mt(x, fy(y) + j)
+    for (int y = warp; y < ny; y += WARPS) {
+        const float4* p = Mt + lane * RT_MH + fys[y];
+        const float* w = wys + y * RT_MAXT;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int t = 0; t < T.ytaps; ++t) {
+            const float wt = w[t];
+            if (wt != 0.0f) acc = fma4p(wt, p[t], acc);
+        }
+        if (lane < nx) store_px(dst.p, dst.type, (size_t)(y0 + y) * dst.w + x0 + lane, acc);
+    }
+}
+
 struct RotParams {
     float m[9];  // inverse matrix, row-vector convention
     int id;      // filter id
@@ -229,6 +357,44 @@ static int filter_id(const char* name)
     return -2;
 }
 
+// Per-axis tap tables are a function of the geometry and the filter only: built once per (device, axis
+// parameters) and kept, so a resize is one launch.  The first use synchronises its stream, so later uses
+// from any stream see a finished table.
+struct AxisTable { int* first = nullptr; float* wts = nullptr; float* total = nullptr; };
+
+static int axis_table(const AxisParams& A, cudaStream_t st, AxisTable& out)
+{
+    static std::mutex mutex;
+    static std::map<std::tuple<int, int, int, int, uint32_t, uint32_t, int>, AxisTable> cache;
+    int device = 0;
+    TC_CUDA(cudaGetDevice(&device));
+    uint32_t sb, rb;
+    memcpy(&sb, &A.scale, 4);
+    memcpy(&rb, &A.ratio, 4);
+    const auto key = std::make_tuple(device, A.dn, A.sn, A.id, sb, rb, A.taps);
+    std::lock_guard<std::mutex> lock(mutex);
+    const auto it = cache.find(key);
+    if (it != cache.end()) {
+        out = it->second;
+        return TC_OK;
+    }
+    if (cache.size() >= 512) return TC_ERR_UNSUPPORTED; // caller builds the tables in its scratch instead
+    AxisTable t;
+    const size_t bytes = ((size_t)A.dn * (3 + A.taps)) * 4;
+    void* p = nullptr;
+    TC_CUDA(cudaMalloc(&p, bytes));
+    t.first = (int*)p;
+    t.total = (float*)p + A.dn;
+    t.wts = t.total + 2 * (size_t)A.dn;
+    k_resize_axis<<<(A.dn + 127) / 128, 128, 0, st>>>(A, t.first, t.wts, t.total);
+    count_launch();
+    TC_CUDA(cudaGetLastError());
+    TC_CUDA(cudaStreamSynchronize(st));
+    cache[key] = t;
+    out = t;
+    return TC_OK;
+}
+
 } // namespace tc
 
 using namespace tc;
@@ -257,13 +423,26 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
     if (ax.taps > 4096 || ay.taps > 4096) return fail(TC_ERR_UNSUPPORTED, "tc_resize: %d x %d taps", ax.taps, ay.taps);
 
     cudaStream_t st = (cudaStream_t)s;
-    // scratch: [tmp (dw x sh float4) | xf | yf | xtot | ytot | xw | yw]
-    const size_t n_tmp = (size_t)dst->w * src->h * 4;
-    const size_t n_int = (size_t)dst->w + dst->h;
-    const size_t n_tot = 2 * ((size_t)dst->w + dst->h);
-    const size_t n_w = (size_t)dst->w * ax.taps + (size_t)dst->h * ay.taps;
+    // shared-memory tile path: taps fit the unrolled loops and some block height keeps the footprint within 32 rows
+    ResizeTile T;
+    T.xtaps = ax.taps;
+    T.ytaps = ay.taps;
+    T.sw = (int)ceilf((float)(RT_W - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
+    T.th = 0;
+    for (int th = RT_MAXH; th >= 4 && !T.th; --th)
+        if ((int)ceilf((float)(th - 1) * (float)src->h / (float)dst->h) + ay.taps + 1 <= RT_ROWS) T.th = th;
+    const size_t tile_smem = resize_tile_smem(T.sw);
+    const bool tiled = T.th > 0 && ax.taps <= RT_MAXT && ay.taps <= RT_MAXT && tile_smem <= 100 * 1024;
+    // per-axis tables: cached per geometry; built in the call's scratch only if the cache is full
+    AxisTable tx, ty;
+    const bool cached = axis_table(ax, st, tx) == TC_OK && axis_table(ay, st, ty) == TC_OK;
+    // scratch: [tmp (dw x sh float4, two-pass path only) | xf | yf | xtot | ytot | xw | yw (uncached tables only)]
+    const size_t n_tmp = tiled ? 0 : (size_t)dst->w * src->h * 4;
+    const size_t n_int = cached ? 0 : (size_t)dst->w + dst->h;
+    const size_t n_tot = cached ? 0 : 2 * ((size_t)dst->w + dst->h);
+    const size_t n_w = cached ? 0 : (size_t)dst->w * ax.taps + (size_t)dst->h * ay.taps;
     void* scratch = nullptr;
-    TC_CUDA(cudaMallocAsync(&scratch, (n_tmp + n_int + n_tot + n_w) * 4, st));
+    if (n_tmp + n_int + n_tot + n_w) TC_CUDA(cudaMallocAsync(&scratch, (n_tmp + n_int + n_tot + n_w) * 4, st));
     float4* tmp = (float4*)scratch;
     int* xf = (int*)((float*)scratch + n_tmp);
     int* yf = xf + dst->w;
@@ -271,14 +450,42 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
     float* yt = xt + 2 * (size_t)dst->w;
     float* xw = yt + 2 * (size_t)dst->h;
     float* yw = xw + (size_t)dst->w * ax.taps;
-    k_resize_axis<<<(dst->w + 127) / 128, 128, 0, st>>>(ax, xf, xw, xt);
-    k_resize_axis<<<(dst->h + 127) / 128, 128, 0, st>>>(ay, yf, yw, yt);
-    dim3 block(32, 8);
-    k_resize_rows<<<dim3((dst->w + 31) / 32, (src->h + 7) / 8), block, 0, st>>>(view(src), tmp, dst->w, xf, xw, xt, ax.taps);
-    k_resize_cols<<<dim3((dst->w + 31) / 32, (dst->h + 7) / 8), block, 0, st>>>(tmp, src->h, view(dst), yf, yw, yt, ay.taps);
-    count_launch(4);
+    if (cached) {
+        xf = tx.first, xw = tx.wts, xt = tx.total;
+        yf = ty.first, yw = ty.wts, yt = ty.total;
+    } else {
+        k_resize_axis<<<(dst->w + 127) / 128, 128, 0, st>>>(ax, xf, xw, xt);
+        k_resize_axis<<<(dst->h + 127) / 128, 128, 0, st>>>(ay, yf, yw, yt);
+        count_launch(2);
+    }
+    if (tiled) {
+        const dim3 grid((dst->w + RT_W - 1) / RT_W, (dst->h + T.th - 1) / T.th);
+        int e = TC_OK;
+#define TC_RT(TY)                                                                                                                  \
+    case TY:                                                                                                                       \
+        e = ensure_dynamic_smem((const void*)k_resize_tile<TY>, tile_smem);                                                        \
+        if (e == TC_OK) k_resize_tile<TY><<<grid, RT_THREADS, tile_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, T);   \
+        break;
+        switch (src->type) {
+            TC_RT(TC_U8)
+            TC_RT(TC_U16)
+            TC_RT(TC_F16)
+            TC_RT(TC_F32)
+        }
+#undef TC_RT
+        if (e != TC_OK) {
+            if (scratch) cudaFreeAsync(scratch, st);
+            return e;
+        }
+        count_launch(1);
+    } else {
+        dim3 block(32, 8);
+        k_resize_rows<<<dim3((dst->w + 31) / 32, (src->h + 7) / 8), block, 0, st>>>(view(src), tmp, dst->w, xf, xw, xt, ax.taps);
+        k_resize_cols<<<dim3((dst->w + 31) / 32, (dst->h + 7) / 8), block, 0, st>>>(tmp, src->h, view(dst), yf, yw, yt, ay.taps);
+        count_launch(2);
+    }
     int st_launch = check_cuda(cudaGetLastError(), "k_resize launch");
-    cudaFreeAsync(scratch, st);
+    if (scratch) cudaFreeAsync(scratch, st);
     return st_launch;
 }
 
