@@ -349,6 +349,78 @@ __global__ void __launch_bounds__(256) k_rotate(const Img src_, const Img dst, c
     store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
 }
 
+// The same gather through a shared-memory tile (the north-star layout for Rotate).  A CTA owns a 16 x 16 block
+// of the destination; the inverse map is affine, so the block's source footprint is the bounding box of its
+// four corner footprints.  The box is staged once with black outside the source -- which also removes the
+// per-tap bounds test -- and every pixel then filters out of shared memory: 4 source pixels loaded per
+// destination pixel instead of 49-64 L1 gathers.  Same weights, same accumulation order as k_rotate.
+constexpr int RTT = 16; // destination block edge
+
+struct RotTile { int cols, rows, pitch; }; // allocation of the shared source tile; row pitch in pixels
+
+template <int MAXT, int FILT, int TYPE>
+__global__ void __launch_bounds__(RTT * RTT) k_rotate_tile(const Img src_, const Img dst, const __grid_constant__ RotParams P, const RotTile T)
+{
+    extern __shared__ float4 rot_smem[];
+    const Img src { src_.p, src_.w, src_.h, TYPE };
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * RTT, y0 = blockIdx.y * RTT;
+    const float ds = fmaxf(1.0f, fmaxf(fabsf(P.m[0]), fabsf(P.m[3])));
+    const float dt = fmaxf(1.0f, fmaxf(fabsf(P.m[1]), fabsf(P.m[4])));
+    const float rs = __fmul_rn(__fmul_rn(0.5f, ds), P.fw), rt = __fmul_rn(__fmul_rn(0.5f, dt), P.fw);
+    // footprint of the block: extremes of the affine map are at its corner pixels (one pixel of slack for rounding)
+    float smn = 3.0e38f, smx = -3.0e38f, tmn = 3.0e38f, tmx = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float px = __fadd_rn((float)(x0 + (k & 1) * (RTT - 1)), 0.5f), py = __fadd_rn((float)(y0 + (k >> 1) * (RTT - 1)), 0.5f);
+        const float s = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[0]), __fmul_rn(py, P.m[3])), P.m[6]);
+        const float t = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[1]), __fmul_rn(py, P.m[4])), P.m[7]);
+        smn = fminf(smn, s), smx = fmaxf(smx, s), tmn = fminf(tmn, t), tmx = fmaxf(tmx, t);
+    }
+    const int s0 = (int)floorf(smn - rs) - 1, t0 = (int)floorf(tmn - rt) - 1;
+    const int cols = min((int)ceilf(smx + rs) + 1 - s0, T.cols), rows = min((int)ceilf(tmx + rt) + 1 - t0, T.rows);
+    const int pitch = T.pitch;
+    // stage: a warp per source row, black outside the source
+    for (int r = tid >> 5; r < rows; r += RTT * RTT / 32)
+        for (int c = tid & 31; c < cols; c += 32) rot_smem[r * pitch + c] = load_black(src, s0 + c, t0 + r);
+    __syncthreads();
+
+    const int x = x0 + (tid & (RTT - 1)), y = y0 + tid / RTT;
+    if (x >= dst.w || y >= dst.h) return;
+    const float px = __fadd_rn((float)x, 0.5f), py = __fadd_rn((float)y, 0.5f);
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[0]), __fmul_rn(py, P.m[3])), P.m[6]);
+    const float t = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[1]), __fmul_rn(py, P.m[4])), P.m[7]);
+    const float ds_inv = __fdiv_rn(1.0f, ds), dt_inv = __fdiv_rn(1.0f, dt);
+    const int smin = (int)floorf(__fsub_rn(s, rs)), smax = (int)ceilf(__fadd_rn(s, rs));
+    const int tmin = (int)floorf(__fsub_rn(t, rt)), tmax = (int)ceilf(__fadd_rn(t, rt));
+    const int ns = min(smax - smin, MAXT), nt = min(tmax - tmin, MAXT);
+    float wx[MAXT];
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i)
+        wx[i] = i < ns ? rot_filt<FILT>(P.fscale, __fmul_rn(ds_inv, __fsub_rn(__fadd_rn((float)(smin + i), 0.5f), s))) : 0.0f;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float total = 0.0f;
+    // indices stay inside the staged box by construction; the clamps only guard the allocation
+    const int cbase = min(max(smin - s0, 0), max(cols - ns, 0));
+#pragma unroll 1
+    for (int j = 0; j < nt; ++j) {
+        const float wy = rot_filt<FILT>(P.fscale, __fmul_rn(dt_inv, __fsub_rn(__fadd_rn((float)(tmin + j), 0.5f), t)));
+        const float4* row = rot_smem + min(max(tmin + j - t0, 0), rows - 1) * pitch + cbase;
+#pragma unroll
+        for (int i = 0; i < MAXT; ++i) {
+            if (i < ns) {
+                const float w = __fmul_rn(wx[i], wy);
+                sum = fma4p(w, row[i], sum);
+                total = __fadd_rn(total, w);
+            }
+        }
+    }
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (total > 0.0f)
+        o = make_float4(__fdiv_rn(sum.x, total), __fdiv_rn(sum.y, total), __fdiv_rn(sum.z, total), __fdiv_rn(sum.w, total));
+    store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
+}
+
 static int filter_id(const char* name)
 {
     if (!name || !*name) return -1;
@@ -521,6 +593,61 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
     const bool narrow = P.fw + 2.0f <= 8.0f;
     const Img vs = view(src), vd = view(dst);
     cudaStream_t st = (cudaStream_t)s;
+    // shared-memory tile path: default-width filters whose block footprint fits 64 KB
+    {
+        const float ds = fmaxf(1.0f, fmaxf(fabsf(P.m[0]), fabsf(P.m[3]))), dt = fmaxf(1.0f, fmaxf(fabsf(P.m[1]), fabsf(P.m[4])));
+        RotTile T;
+        T.cols = (int)ceilf((RTT - 1) * (fabsf(P.m[0]) + fabsf(P.m[3])) + ds * P.fw) + 5;
+        T.rows = (int)ceilf((RTT - 1) * (fabsf(P.m[1]) + fabsf(P.m[4])) + dt * P.fw) + 5;
+        // Row pitch: 8 consecutive destination pixels (a quarter warp, one 128-bit shared-memory phase) step through the
+        // source by (m0, m1) each; pick the pitch whose 16-byte slots collide least for that step over a few phases
+        // (at 45 degrees the step is about (+1 row, +1 column), so pitch + 1 must not be a multiple of 8).
+        int best = 1 << 30;
+        T.pitch = T.cols;
+        for (int pitch = T.cols; pitch < T.cols + 8; ++pitch) {
+            int cost = 0;
+            for (int ph = 0; ph < 16; ++ph) {
+                const float sf = 0.25f * (float)(ph & 3), tf = 0.25f * (float)(ph >> 2);
+                int hits[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                for (int k = 0; k < 8; ++k) {
+                    const int slot = (int)floorf(tf + 64.0f + (float)k * P.m[1]) * pitch + (int)floorf(sf + 64.0f + (float)k * P.m[0]);
+                    ++hits[slot & 7];
+                }
+                int worst = 0;
+                for (int k = 0; k < 8; ++k) worst = hits[k] > worst ? hits[k] : worst;
+                cost += worst;
+            }
+            if (cost < best) {
+                best = cost;
+                T.pitch = pitch;
+            }
+        }
+        const size_t smem = (size_t)T.rows * T.pitch * sizeof(float4);
+        if (narrow && smem <= 64 * 1024) {
+            const dim3 tgrid((dst->w + RTT - 1) / RTT, (dst->h + RTT - 1) / RTT);
+            int e = TC_OK;
+#define TC_ROTT(TY)                                                                                                     \
+    case TY:                                                                                                            \
+        if (id == 0) {                                                                                                  \
+            e = ensure_dynamic_smem((const void*)k_rotate_tile<8, 0, TY>, smem);                                        \
+            if (e == TC_OK) k_rotate_tile<8, 0, TY><<<tgrid, RTT * RTT, smem, st>>>(vs, vd, P, T);                      \
+        } else {                                                                                                        \
+            e = ensure_dynamic_smem((const void*)k_rotate_tile<8, 1, TY>, smem);                                        \
+            if (e == TC_OK) k_rotate_tile<8, 1, TY><<<tgrid, RTT * RTT, smem, st>>>(vs, vd, P, T);                      \
+        }                                                                                                               \
+        break;
+            switch (src->type) {
+                TC_ROTT(TC_U8)
+                TC_ROTT(TC_U16)
+                TC_ROTT(TC_F16)
+                TC_ROTT(TC_F32)
+            }
+#undef TC_ROTT
+            if (e != TC_OK) return e;
+            count_launch();
+            return check_cuda(cudaGetLastError(), "k_rotate_tile launch");
+        }
+    }
 #define TC_ROT(T)                                                                         \
     case T:                                                                               \
         if (id == 0) {                                                                    \
