@@ -158,6 +158,31 @@ int tc_convert(const tc_image* dst, const tc_image* src, tc_stream s);
    channels: 3 (alpha dropped) or 4. */
 int tc_pack_raw(void* dst_dev, const tc_image* src, int type, int channels, tc_stream s);
 
+/* ---- pointwise chain (cross-node fusion of consecutive pointwise effects) --------------
+ * One pass for a chain of 2..TC_CHAIN_MAX pointwise effect nodes (Invert, Pow, Saturate, ColorMap, Premult,
+ * Unpremult, ColorConvert) applied bottom to top: ops[0] runs first.  Between two steps the value goes through
+ * the storage type of the images (the reference materialises a typed buffer at every node boundary), so the
+ * result is bit-identical to running the per-node kernels one after the other -- minus 2(n-1) frame passes.
+ * name_a / name_b: ColorMap map name; ColorConvert from / to colour space.  flag: ColorConvert's unpremult.
+ * An op the per-node call would refuse (unknown colour space) yields zeros, like its per-node kernel. */
+enum { TC_CHAIN_INVERT = 0, TC_CHAIN_POW, TC_CHAIN_SATURATE, TC_CHAIN_COLOR_MAP, TC_CHAIN_PREMULT, TC_CHAIN_UNPREMULT, TC_CHAIN_COLOR_CONVERT,
+       TC_CHAIN_ZERO };
+#define TC_CHAIN_MAX 8
+typedef struct tc_chain_op {
+    int kind;
+    float value;
+    int flag;
+    char name_a[96];
+    char name_b[96];
+} tc_chain_op;
+/* what a plug-in appends to when the host asks it to describe its pixel operation instead of launching it
+   (render-argument property "ToucanPropPointwiseChain") */
+typedef struct tc_chain {
+    int n;
+    tc_chain_op ops[TC_CHAIN_MAX];
+} tc_chain;
+int tc_pointwise_chain(const tc_image* dst, const tc_image* src, const tc_chain_op* ops, int n, tc_stream s);
+
 /* ---- draw (plugins/DrawPlugin.cpp) ---------------------------------------------------
    copy(src -> dst) + ImageBufAlgo::render_box / render_line: "colour over pixel"
    r[c] = color[c] + r[c] * (1 - color[3]) (plain store when color[3] == 1), clipped to the image.

@@ -119,3 +119,44 @@ def test_c4_transform_and_colorspace_4k_float(host):
 
     run(host, "Transform.otio", media, [0, 2, 4, 6, 8], check)
     run(host, "ColorSpace.otio", media, [0, 3, 6], close_f32)
+
+
+def test_c2_chained_filters_fuse_into_fewer_launches(cuda):
+    """SURVEY 8d config 2, chained variant: one clip carrying ColorMap -> Invert -> Pow -> Saturate -> Blur -> UnsharpMask
+    at 1920x1080 float32.  The four leading pointwise nodes run as ONE kernel (the plug-ins describe their operation
+    to the host, which launches tc_pointwise_chain); frames are bit-identical to the node-by-node path and within
+    1e-5 of the oracle."""
+    import torch
+
+    from oracle import graph as G
+    from toucan_b200 import capi, render, workloads
+
+    w, h = 1920, 1080
+    rng = np.random.default_rng(1001)
+    src = rng.random((h, w, 4), dtype=np.float32)
+    src[..., 3] = 1.0
+    doc = workloads.filter_chain_timeline(frames=6)
+    render.bind_device(0)
+    host = render.Host()
+    tl = render.Timeline(json_doc=doc, directory="/synthetic")
+    path = tl.media_path("synthetic://chain/source.exr")
+    tl.set_media(path, src)
+    tl.prepare()
+    n0 = capi.launch_count()
+    fused = tl.render(host, 2.0)
+    fused_launches = capi.launch_count() - n0
+    render.set_fusion(False)
+    try:
+        n0 = capi.launch_count()
+        plain = tl.render(host, 2.0)
+        plain_launches = capi.launch_count() - n0
+    finally:
+        render.set_fusion(True)
+    assert fused.dtype == np.float32 and np.array_equal(fused, plain)
+    assert plain_launches - fused_launches == 3, (plain_launches, fused_launches)  # 4 pointwise launches became 1
+    otl = G.Timeline(doc)
+    otl.dir = "/synthetic"
+    want = G.ImageGraph(otl, lambda p: src if p == path else None).render(G.RT(2.0, 24.0))
+    assert float(np.abs(fused - want).max()) <= 1e-5
+    tl.close()
+    del torch

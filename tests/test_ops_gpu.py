@@ -362,3 +362,47 @@ def test_draw_long_lines_at_8k():
     small = ops.draw_line(torch.zeros((64, 114, 4), dtype=torch.uint8, device="cuda"), (0, 0), (113, 63), (1.0, 1.0, 1.0, 1.0))
     assert np.array_equal(small.cpu().numpy(), want)
     assert int(ys.max()) == h - 1 and int(ys.min()) == 0
+
+
+# ---- chain of pointwise effects in one pass (cross-node fusion) ---------------------------------------
+CHAINS = [
+    [("color_map", "plasma"), ("invert",), ("pow", 2.0), ("saturate", 0.0)],                 # SURVEY 8d config 2, chained
+    [("unpremult",), ("color_convert", "Linear Rec.709 (sRGB)", "ACEScct", False), ("premult",)],
+    [("pow", 2.2), ("color_convert", "sRGB - Texture", "no such space", False), ("invert",)],   # failed convert: zeros, then invert
+    [("saturate", 1.5), ("color_map", "no such map"), ("invert",), ("pow", 3.0), ("premult",), ("unpremult",), ("invert",), ("saturate", 0.25)],
+]
+
+
+def _single(ops_mod, t, st):
+    return {"invert": lambda: ops_mod.invert(t), "pow": lambda: ops_mod.pow_(t, st[1]), "saturate": lambda: ops_mod.saturate(t, st[1]),
+            "color_map": lambda: ops_mod.color_map(t, st[1]), "premult": lambda: ops_mod.premult(t), "unpremult": lambda: ops_mod.unpremult(t),
+            "color_convert": lambda: ops_mod.colorconvert(t, st[1], st[2], unpremult=st[3])}[st[0]]()
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+@pytest.mark.parametrize("chain", range(len(CHAINS)))
+def test_pointwise_chain_equals_the_nodes_one_by_one(dt, chain):
+    """Bit-identical to the per-node kernels run in sequence (the storage round trip of every node boundary is
+    replayed in registers), for every storage type; and within tolerance of the oracle's node-by-node evaluation."""
+    from toucan_b200 import ops
+
+    steps = CHAINS[chain]
+    src = rand_img(171, 93, dt, 50 + chain, alpha="mixed")
+    got = ops.pointwise_chain(to_dev(src), steps)
+    seq = to_dev(src)
+    ref = src
+    for st in steps:
+        seq = _single(ops, seq, st)
+        ref = _single(O, ref, st)
+    assert_exact(got, to_host(seq), f"chain {chain} vs per-node kernels")
+    assert_close(got, ref, f"chain {chain} vs oracle", tol=2e-5, lsb=2)
+
+
+def test_pointwise_chain_rejects():
+    from toucan_b200 import capi, ops
+
+    t = to_dev(rand_img(16, 8, np.float32, 1))
+    with pytest.raises(capi.TcError):
+        ops.pointwise_chain(t, [("invert",)] * 9)
+    with pytest.raises(capi.TcError):
+        ops.pointwise_chain(t, [])

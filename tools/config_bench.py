@@ -49,11 +49,12 @@ def resized(doc, size):
     return doc
 
 
-def bench_timeline(host, label, name, frames_by_file, size=None, cpu_frames=2):
-    doc = json.load(open(os.path.join(TL.DATA, name)))
+def bench_timeline(host, label, name, frames_by_file, size=None, cpu_frames=2, doc=None):
+    if doc is None:
+        doc = json.load(open(os.path.join(TL.DATA, name)))
     if size:
         doc = resized(doc, size)
-    by_path = {os.path.join(TL.DATA, f): a for f, a in frames_by_file.items()}
+    by_path = {(f if os.path.isabs(f) else os.path.join(TL.DATA, f)): a for f, a in frames_by_file.items()}
     # --- GPU, media resident ---
     tl = render.Timeline(json_doc=doc, directory=TL.DATA)
     dev = {}
@@ -142,6 +143,11 @@ def main():
         rows.append(bench_timeline(host, "C1/fixtures 1280x720 u8", name, shipped))
     charlie = {"Charlie.jpg": synth(1920, 1080, np.float32, 1001)}
     rows.append(bench_timeline(host, "C2 1920x1080 f32", "Filter.otio", charlie))
+    from toucan_b200 import workloads  # noqa: E402
+
+    rows.append(bench_timeline(host, "C2 1920x1080 f32", "six filters chained on one clip (240 frames)",
+                               {os.path.join(TL.DATA, "source.exr"): charlie["Charlie.jpg"]},
+                               doc=workloads.filter_chain_timeline(frames=240, url="source.exr")))
     c3 = {"Charlie.jpg": synth(3840, 2160, np.float16, 1002)}
     rows.append(bench_timeline(host, "C3 3840x2160 half", "MultipleEffects.otio", c3))
     seq = {f"Counter.{i}.png": synth(3840, 2160, np.float16, 1100 + i, disc=True) for i in range(10)}

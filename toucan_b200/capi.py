@@ -26,6 +26,14 @@ class tc_image(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("w", ctypes.c_int), ("h", ctypes.c_int), ("type", ctypes.c_int)]
 
 
+class tc_chain_op(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("value", ctypes.c_float), ("flag", ctypes.c_int), ("name_a", ctypes.c_char * 96),
+                ("name_b", ctypes.c_char * 96)]
+
+
+CHAIN_KINDS = {"invert": 0, "pow": 1, "saturate": 2, "color_map": 3, "premult": 4, "unpremult": 5, "color_convert": 6}
+
+
 class tc_stack_layer(ctypes.Structure):
     _fields_ = [("src_a", ctypes.c_void_p), ("src_b", ctypes.c_void_p), ("radius_a", ctypes.c_float),
                 ("radius_b", ctypes.c_float), ("value", ctypes.c_double)]
@@ -63,6 +71,7 @@ _SIGS = {
     "tc_convert": [_IMG, _IMG, _S],
     "tc_pack_raw": [ctypes.c_void_p, _IMG, ctypes.c_int, ctypes.c_int, _S],
     "tc_rgb_to_y4m": [ctypes.c_void_p, _IMG, ctypes.c_int, _S],
+    "tc_pointwise_chain": [_IMG, _IMG, ctypes.POINTER(tc_chain_op), ctypes.c_int, _S],
     "tc_draw_box": [_IMG, _IMG, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F4, ctypes.c_int, _S],
     "tc_draw_line": [_IMG, _IMG, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _F4, ctypes.c_int, _S],
     "tc_stack_f32": [_IMG, _F4, ctypes.POINTER(tc_stack_layer), ctypes.c_int, _S],

@@ -452,6 +452,67 @@ struct ColorConvertOp {
     }
 };
 
+// ---- chain of pointwise effects in one pass -----------------------------------------------
+// Each step is the per-node functor above, applied in registers; between steps the value takes the
+// round trip through the images' storage type that the node boundary would have applied.
+struct ChainStep {
+    int kind;
+    float v;          // Pow / Saturate value
+    int n;            // ColorMap knots
+    const float* k;   // ColorMap knot table (device)
+    int curve_in, curve_out, unpremult;
+    float p_in, p_out;
+    float m[9];
+};
+struct ChainOp {
+    Src s;
+    int n, type;
+    ChainStep step[TC_CHAIN_MAX];
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const
+    {
+        for (int i = 0; i < n; ++i) {
+            const ChainStep& st = step[i];
+            switch (st.kind) {
+            case TC_CHAIN_INVERT: p = InvertOp().apply(p); break;
+            case TC_CHAIN_POW: {
+                PowOp o;
+                o.v = st.v;
+                p = o.apply(p);
+                break;
+            }
+            case TC_CHAIN_SATURATE: {
+                SaturateOp o;
+                o.v = st.v;
+                p = o.apply(p);
+                break;
+            }
+            case TC_CHAIN_COLOR_MAP: {
+                ColorMapOp o;
+                o.n = st.n;
+                o.k = st.k;
+                p = o.apply(p);
+                break;
+            }
+            case TC_CHAIN_PREMULT: p = PremultOp().apply(p); break;
+            case TC_CHAIN_UNPREMULT: p = UnpremultOp().apply(p); break;
+            case TC_CHAIN_COLOR_CONVERT: {
+                ColorConvertOp o;
+                o.curve_in = st.curve_in, o.curve_out = st.curve_out, o.unpremult = st.unpremult;
+                o.p_in = st.p_in, o.p_out = st.p_out;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) o.m[c] = st.m[c];
+                p = o.apply(p);
+                break;
+            }
+            default: p = make_float4(0.f, 0.f, 0.f, 0.f); break;
+            }
+            if (i + 1 < n) p = quant4(p, type);
+        }
+        return p;
+    }
+};
+
 // ---- address-only transforms ---------------------------------------------------------
 struct CropOp {
     TC_OP_0()
@@ -739,6 +800,48 @@ int tc_color_convert2(const tc_image* dst, const tc_image* src, const char* from
         // OIIO colorconvert() fails on an unknown colour space; the output keeps its zero fill
         const float z[4] = { 0.f, 0.f, 0.f, 0.f };
         return launch(FillOp { f4(z) }, dst, s);
+    }
+    return launch(op, dst, s);
+}
+
+int tc_pointwise_chain(const tc_image* dst, const tc_image* src, const tc_chain_op* ops, int n, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_pointwise_chain dst");
+    TC_VALIDATE(src, "tc_pointwise_chain src");
+    if (!ops || n < 1 || n > TC_CHAIN_MAX) return fail(TC_ERR_INVALID, "tc_pointwise_chain: %d ops (1..%d)", n, TC_CHAIN_MAX);
+    if (dst->type != src->type) return fail(TC_ERR_INVALID, "tc_pointwise_chain: source and destination storage types differ");
+    ChainOp op;
+    memset(&op, 0, sizeof(op));
+    op.s = make_src(src, dst);
+    op.n = n;
+    op.type = dst->type;
+    for (int i = 0; i < n; ++i) {
+        ChainStep& st = op.step[i];
+        st.kind = ops[i].kind;
+        st.v = ops[i].value;
+        switch (ops[i].kind) {
+        case TC_CHAIN_INVERT:
+        case TC_CHAIN_POW:
+        case TC_CHAIN_SATURATE:
+        case TC_CHAIN_PREMULT:
+        case TC_CHAIN_UNPREMULT:
+        case TC_CHAIN_ZERO: break;
+        case TC_CHAIN_COLOR_MAP: {
+            const float* knots = nullptr;
+            st.n = color_map_knots(ops[i].name_a, &knots);
+            if (st.n) {
+                int e = device_knots(knots, st.n, s, &st.k);
+                if (e != TC_OK) return e;
+            }
+            break;
+        }
+        case TC_CHAIN_COLOR_CONVERT:
+            st.unpremult = ops[i].flag ? 1 : 0;
+            if (!color_convert_setup(ops[i].name_a, ops[i].name_b, &st.curve_in, &st.p_in, st.m, &st.curve_out, &st.p_out))
+                st.kind = TC_CHAIN_ZERO; // colorconvert() fails: the node's output keeps its zero fill
+            break;
+        default: return fail(TC_ERR_INVALID, "tc_pointwise_chain: unknown op kind %d", ops[i].kind);
+        }
     }
     return launch(op, dst, s);
 }

@@ -160,6 +160,29 @@ namespace toucan_ofx
             suites.prop.propGetPointer(inArgs, kOfxImageEffectPropCudaStream, 0, &stream);
             args.stream = stream;
 
+            // Describe-only pass of the host's pointwise-chain fusion: no images, nothing is launched.
+            void* chain = nullptr;
+            if (kOfxStatOK == suites.prop.propGetPointer(inArgs, kToucanPropPointwiseChain, 0, &chain) && chain)
+            {
+                if (!fx.pointwise)
+                {
+                    return kOfxStatReplyDefault;
+                }
+                args.chain = static_cast<tc_chain*>(chain);
+                OfxParamSetHandle paramSet = nullptr;
+                suites.effect.getParamSet(handle, &paramSet);
+                const int st = fx.render(args, Params(suites.param, paramSet));
+                if (TC_ERR_UNSUPPORTED == st || TC_ERR_INVALID == st)
+                {
+                    // the per-node path clears the output for such arguments
+                    tc_chain_op zero;
+                    memset(&zero, 0, sizeof(zero));
+                    zero.kind = TC_CHAIN_ZERO;
+                    return TC_OK == chainAppend(args, zero) ? kOfxStatOK : kOfxStatReplyDefault;
+                }
+                return TC_OK == st ? kOfxStatOK : kOfxStatReplyDefault;
+            }
+
             OfxPropertySetHandle images[3] = { nullptr, nullptr, nullptr };
             bool ok = clipImage(handle, "Output", args.time, images[0], args.output);
             if (Context::Filter == fx.context)
@@ -246,6 +269,16 @@ namespace toucan_ofx
             static std::vector<OfxPlugin> p = makePlugins(std::make_index_sequence<maxEffects>());
             return p;
         }
+    }
+
+    int chainAppend(const RenderArgs& a, const tc_chain_op& op)
+    {
+        if (!a.chain || a.chain->n >= TC_CHAIN_MAX)
+        {
+            return TC_ERR_CUDA;
+        }
+        a.chain->ops[a.chain->n++] = op;
+        return TC_OK;
     }
 
     // ---- Params ---------------------------------------------------------------------------

@@ -70,7 +70,26 @@ namespace toucan_ofx
         OfxTime time;
         OfxRectI window;
         tc_stream stream;
+        //! Non-null when the host asked the effect to DESCRIBE its pixel operation instead of launching it
+        //! (render-argument property kToucanPropPointwiseChain): the body appends one tc_chain_op and returns.
+        //! Only effects flagged `pointwise` are ever called this way; they have no images then.
+        tc_chain* chain;
     };
+
+    //! Render-argument property (pointer to a tc_chain): the host collects consecutive pointwise effects of a
+    //! graph into one kernel launch.  An effect that is not pointwise answers kOfxStatReplyDefault.
+    constexpr const char* kToucanPropPointwiseChain = "ToucanPropPointwiseChain";
+
+    //! Append `op` to the chain being recorded.
+    int chainAppend(const RenderArgs&, const tc_chain_op&);
+
+    inline tc_chain_op chainOp(int kind, float value = 0.F)
+    {
+        tc_chain_op op = {};
+        op.kind = kind;
+        op.value = value;
+        return op;
+    }
 
     using RenderFn = int (*)(const RenderArgs&, const Params&); // returns a tc_status
 
@@ -81,6 +100,7 @@ namespace toucan_ofx
         Context context;
         std::vector<ParamDef> params;
         RenderFn render;
+        bool pointwise = false; //!< the render body honours RenderArgs::chain
     };
 
     //! The effect table of this module (defined once per .ofx).

@@ -1,5 +1,7 @@
 #include "ImageEffect.h"
 
+#include "StackFusion.h"
+
 #include <toucanRender/Util.h>
 
 #include <algorithm>
@@ -109,6 +111,85 @@ namespace toucan
         return ss.str();
     }
 
+    bool ImageEffectNode::describePointwise(tc_chain& chain) const
+    {
+        char* context = nullptr;
+        _plugin.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
+        if (!context || 0 != strcmp(context, kOfxImageEffectContextFilter) || _inputs.size() != 1 || !_inputs[0])
+        {
+            return false;
+        }
+        const auto sizeIt = _metaData.find("size");
+        if (sizeIt != _metaData.end() && sizeIt->second.has_value())
+        {
+            return false; // an output-size override is not a same-position operation
+        }
+        const int before = chain.n;
+        if (before >= TC_CHAIN_MAX)
+        {
+            return false;
+        }
+        // The plug-in resolves its parameters exactly as in a real render (same getters, same local initialisers)
+        // and appends one tc_chain_op; effects that are not pointwise answer kOfxStatReplyDefault.
+        PropertySet args;
+        args.setDouble(kOfxPropTime, 0, _time.value());
+        const int window[4] = { 0, 0, 0, 0 };
+        args.setIntN(kOfxImageEffectPropRenderWindow, 4, window);
+        args.setInt(kOfxImageEffectPropCudaEnabled, 0, 1);
+        args.setPointer(kOfxImageEffectPropCudaStream, 0, DeviceContext::stream());
+        args.setPointer("ToucanPropPointwiseChain", 0, &chain);
+        _instance->images.clear();
+        const OfxStatus status = _plugin.ofxPlugin->mainEntry(
+            kOfxImageEffectActionRender,
+            &_handle,
+            reinterpret_cast<OfxPropertySetHandle>(&args),
+            nullptr);
+        if (status != kOfxStatOK || chain.n != before + 1)
+        {
+            chain.n = before;
+            return false;
+        }
+        return true;
+    }
+
+    bool ImageEffectNode::_tryPointwiseChain(Image& out)
+    {
+        if (!getStackFusionEnabled())
+        {
+            return false;
+        }
+        // Walk down while the nodes are pointwise effects; ops are recorded top first.
+        tc_chain chain;
+        memset(&chain, 0, sizeof(chain));
+        const ImageEffectNode* node = this;
+        std::shared_ptr<IImageNode> base;
+        while (node && node->describePointwise(chain))
+        {
+            base = node->_inputs[0];
+            node = dynamic_cast<const ImageEffectNode*>(base.get());
+        }
+        if (chain.n < 2)
+        {
+            return false; // a single effect takes the ordinary per-node path
+        }
+        const Image source = base->exec();
+        const ImageSpec& spec = source.spec();
+        if (spec.width <= 0 || spec.height <= 0)
+        {
+            out = Image(); // what a chain of filters over a missing image yields node by node
+            return true;
+        }
+        tc_chain_op ops[TC_CHAIN_MAX];
+        for (int i = 0; i < chain.n; ++i)
+        {
+            ops[i] = chain.ops[chain.n - 1 - i];
+        }
+        out = Image(spec);
+        const tc_image src = source.view(), dst = out.view();
+        tcCheck(tc_pointwise_chain(&dst, &src, ops, chain.n, DeviceContext::stream()), "tc_pointwise_chain");
+        return true;
+    }
+
     Image ImageEffectNode::exec()
     {
         // Evaluate the inputs the effect's context consumes, then render.
@@ -117,6 +198,11 @@ namespace toucan
         std::vector<Image> inputs;
         if (context && 0 == strcmp(context, kOfxImageEffectContextFilter))
         {
+            Image fused;
+            if (_tryPointwiseChain(fused))
+            {
+                return fused;
+            }
             if (!_inputs.empty() && _inputs[0]) inputs.push_back(_inputs[0]->exec());
         }
         else if (context && 0 == strcmp(context, kOfxImageEffectContextTransition))

@@ -62,7 +62,14 @@ namespace toucan
         //! Render into `out` from already evaluated inputs (the per-node OpenFX path).
         Image render(const std::vector<Image>& inputs);
 
+        //! Cross-node fusion of pointwise effects: ask the plug-in to append its pixel operation (with the
+        //! parameters as IT resolves them) to `chain` instead of launching it.  False if the effect is not a
+        //! same-size, single-input pointwise effect, or the plug-in does not take part.
+        bool describePointwise(tc_chain& chain) const;
+
     private:
+        bool _tryPointwiseChain(Image& out);
+
         ImageEffectPlugin& _plugin;
         std::unique_ptr<ImageEffectInstance> _instance;
         ImageEffectHandle _handle;

@@ -175,6 +175,22 @@ def convert(src, t, size=None):
     return out
 
 
+def pointwise_chain(src, steps):
+    """tc_pointwise_chain: steps = [("invert",), ("pow", 2.0), ("saturate", 0.5), ("color_map", "plasma"), ("premult",),
+    ("unpremult",), ("color_convert", from, to, unpremult)], first step first."""
+    arr = (capi.tc_chain_op * len(steps))()
+    for i, st in enumerate(steps):
+        arr[i].kind = capi.CHAIN_KINDS[st[0]]
+        if st[0] in ("pow", "saturate"):
+            arr[i].value = float(st[1])
+        elif st[0] == "color_map":
+            arr[i].name_a = st[1].encode()
+        elif st[0] == "color_convert":
+            arr[i].name_a, arr[i].name_b = st[1].encode(), st[2].encode()
+            arr[i].flag = 1 if (len(st) > 3 and st[3]) else 0
+    return _unary(lib().tc_pointwise_chain, "tc_pointwise_chain", src, arr, len(steps))
+
+
 def draw_box(src, pos1, pos2, color, fill=True):
     return _unary(lib().tc_draw_box, "tc_draw_box", src, int(pos1[0]), int(pos1[1]), int(pos2[0]), int(pos2[1]), f4(color), 1 if fill else 0)
 

@@ -59,6 +59,24 @@ def stack_timeline(tracks=10, frames=1000, rate=24.0, clip_frames=48, offset=12,
             "tracks": {"OTIO_SCHEMA": "Stack.1", "name": "tracks", "metadata": {}, "effects": [], "children": track_nodes}}
 
 
+# SURVEY 8d config 2, chained variant: ONE clip carrying the six filters of data/Filter.otio in this order
+FILTER_CHAIN = [("toucan:ColorMap", {"map_name": "plasma"}), ("toucan:Invert", {}), ("toucan:Pow", {"value": 2.0}),
+                ("toucan:Saturate", {"value": 0.0}), ("toucan:Blur", {"radius": 10.0}),
+                ("toucan:UnsharpMask", {"kernel": "gaussian", "width": 10.0, "contrast": 1.0, "threshold": 0.0})]
+
+
+def filter_chain_timeline(frames=240, rate=24.0, effects=None, url="synthetic://chain/source.exr"):
+    """A single-track timeline whose only clip (a still held for `frames` frames) carries `effects` (default: FILTER_CHAIN)."""
+    fx = [{"OTIO_SCHEMA": "Effect.1", "name": n.split(":")[1], "effect_name": n, "metadata": dict(m)} for n, m in (effects or FILTER_CHAIN)]
+    clip = {"OTIO_SCHEMA": "Clip.2", "name": "chain", "metadata": {}, "source_range": _tr(0, frames, rate), "effects": fx,
+            "media_references": {"DEFAULT_MEDIA": {"OTIO_SCHEMA": "ExternalReference.1", "name": "", "metadata": {},
+                                                   "available_range": _tr(0, frames, rate), "target_url": url}},
+            "active_media_reference_key": "DEFAULT_MEDIA"}
+    track = {"OTIO_SCHEMA": "Track.1", "name": "V1", "kind": "Video", "metadata": {}, "effects": [], "children": [clip]}
+    return {"OTIO_SCHEMA": "Timeline.1", "name": "filter-chain", "metadata": {},
+            "tracks": {"OTIO_SCHEMA": "Stack.1", "name": "tracks", "metadata": {}, "effects": [], "children": [track]}}
+
+
 def stack_layers(frame: int, tracks=10, frames=1000, clip_frames=48, offset=12, blur_radius=10.0, **_):
     """What ImageGraph::_track yields for `frame` of stack_timeline(), bottom track first:
     a list of (still_a, still_b | None, radius_a, radius_b, value) with still = (track, k).
