@@ -146,6 +146,10 @@ int tc_wipe(const tc_image* dst, const tc_image* from, const tc_image* to, doubl
 /* ---- compositing: lib/toucanRender/Comp.cpp --------------------------------------- */
 /* premult (Comp.cpp:41, optional) + over (Comp.cpp:72) in ONE pass; fg, bg, dst same size */
 int tc_over(const tc_image* dst, const tc_image* fg, const tc_image* bg, int premult_fg, tc_stream s);
+/* the same over a CONSTANT background: the Fill generator at the bottom of a track stack (ImageGraph.cpp:165-171,
+   GeneratorPlugin.cpp:283-306) as a colour instead of a frame.  `color` is the fill colour, `bg_type` the storage type
+   the generator would have produced (its values are quantised to it); dst has fg's size. */
+int tc_over_fill(const tc_image* dst, const tc_image* fg, const float color[4], int bg_type, int premult_fg, tc_stream s);
 /* paste(dst, ox, oy, src) into a ZEROED dst of another size/type   Comp.cpp:56-67.
    Writes every dst pixel (0 outside the pasted rectangle). */
 int tc_paste_on_black(const tc_image* dst, int ox, int oy, const tc_image* src, tc_stream s);

@@ -406,3 +406,18 @@ def test_pointwise_chain_rejects():
         ops.pointwise_chain(t, [("invert",)] * 9)
     with pytest.raises(capi.TcError):
         ops.pointwise_chain(t, [])
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+@pytest.mark.parametrize("premult", [False, True])
+def test_over_constant_background_equals_over_a_filled_frame(dt, premult):
+    """tc_over_fill: the Fill generator under a track stack as a colour.  Bit-identical to rendering the u8 Fill frame and
+    compositing over it (the colour takes the generator's u8 quantisation)."""
+    from toucan_b200 import ops
+
+    w, h = 203, 77
+    fg = rand_img(w, h, dt, 60, alpha="mixed")
+    for color in ([0.0, 0.0, 0.0, 1.0], [0.3, 0.7, 0.123, 0.5], [1.0, 1.0, 1.0, 0.0]):
+        frame = ops.over(to_dev(fg), ops.fill(w, h, color), premult_fg=premult)
+        assert_exact(ops.over_fill(to_dev(fg), color, premult_fg=premult), to_host(frame), f"over_fill {color}")
+        assert_exact(frame, O.comp(fg, O.fill(w, h, color, O.U8), premult), "over vs oracle")

@@ -67,6 +67,7 @@ _SIGS = {
     "tc_dissolve": [_IMG, _IMG, _IMG, ctypes.c_double, _S],
     "tc_wipe": [_IMG, _IMG, _IMG, ctypes.c_double, ctypes.c_int, _S],
     "tc_over": [_IMG, _IMG, _IMG, ctypes.c_int, _S],
+    "tc_over_fill": [_IMG, _IMG, _F4, ctypes.c_int, ctypes.c_int, _S],
     "tc_paste_on_black": [_IMG, ctypes.c_int, ctypes.c_int, _IMG, _S],
     "tc_convert": [_IMG, _IMG, _S],
     "tc_pack_raw": [ctypes.c_void_p, _IMG, ctypes.c_int, ctypes.c_int, _S],

@@ -611,6 +611,30 @@ struct OverOp {
                            __fadd_rn(a.z, __fmul_rn(oma, b.z)), __fadd_rn(a.w, __fmul_rn(oma, b.w)));
     }
 };
+// over a constant background: the Fill generator at the bottom of every track stack (ImageGraph.cpp:165-171)
+// never needs to exist as a frame -- same arithmetic as OverOp with b = the fill colour as the Fill
+// generator's storage type holds it
+struct OverFillOp {
+    Src fg;
+    float4 b;
+    int premult;
+    TC_OP_1(fg)
+    __device__ __forceinline__ float4 apply(float4 a) const
+    {
+        if (premult) {
+            if (a.w != 1.0f) {
+                a.x = __fmul_rn(a.x, a.w);
+                a.y = __fmul_rn(a.y, a.w);
+                a.z = __fmul_rn(a.z, a.w);
+            }
+            a = quant4(a, fg.im.type);
+        }
+        const float alpha = fminf(fmaxf(a.w, 0.0f), 1.0f);
+        const float oma = __fsub_rn(1.0f, alpha);
+        return make_float4(__fadd_rn(a.x, __fmul_rn(oma, b.x)), __fadd_rn(a.y, __fmul_rn(oma, b.y)),
+                           __fadd_rn(a.z, __fmul_rn(oma, b.z)), __fadd_rn(a.w, __fmul_rn(oma, b.w)));
+    }
+};
 
 // colour-map knot tables (tc_tables.cpp)
 int color_map_knots(const char* name, const float** knots);
@@ -916,6 +940,19 @@ int tc_over(const tc_image* dst, const tc_image* fg, const tc_image* bg, int pre
     TC_VALIDATE(fg, "tc_over fg");
     TC_VALIDATE(bg, "tc_over bg");
     return launch(OverOp { make_src(fg, dst), make_src(bg, dst), premult_fg ? 1 : 0 }, dst, s);
+}
+int tc_over_fill(const tc_image* dst, const tc_image* fg, const float color[4], int bg_type, int premult_fg, tc_stream s)
+{
+    TC_VALIDATE(dst, "tc_over_fill dst");
+    TC_VALIDATE(fg, "tc_over_fill fg");
+    if (!color || bg_type < TC_U8 || bg_type > TC_F32) return fail(TC_ERR_INVALID, "tc_over_fill: bad background");
+    if (fg->w != dst->w || fg->h != dst->h) return fail(TC_ERR_INVALID, "tc_over_fill: foreground and destination sizes differ");
+    float4 b;
+    b.x = quant_host(color[0], bg_type);
+    b.y = quant_host(color[1], bg_type);
+    b.z = quant_host(color[2], bg_type);
+    b.w = quant_host(color[3], bg_type);
+    return launch(OverFillOp { make_src(fg, dst), b, premult_fg ? 1 : 0 }, dst, s);
 }
 
 } // extern "C"

@@ -90,6 +90,20 @@ namespace toucan
                 return buf;
             }
             const Image fg = _inputs[0]->exec();
+            // The bottom of a track stack is a Fill generator (ImageGraph.cpp:165-171): composite over its colour
+            // instead of rendering, writing and re-reading a constant frame.
+            IMATH_NAMESPACE::V2i fillSize(0, 0);
+            float fillColor[4];
+            const ImageSpec& fgSpec = fg.spec();
+            if (getStackFusionEnabled() && fgSpec.width > 0 && fgSpec.height > 0 && matchFillBackground(_inputs[1], fillSize, fillColor) &&
+                fillSize.x == fgSpec.width && fillSize.y == fgSpec.height)
+            {
+                // generators render 4-channel UINT8 (ImageEffect.cpp:93)
+                buf = Image(ImageSpec(fgSpec.width, fgSpec.height, 4, tc_type_merge(fgSpec.format, TC_U8)));
+                const tc_image f = fg.view(), o = buf.view();
+                tcCheck(tc_over_fill(&o, &f, fillColor, TC_U8, _premult ? 1 : 0, DeviceContext::stream()), "tc_over_fill");
+                return buf;
+            }
             const Image bg = _inputs[1]->exec();
             buf = composite(fg, bg);
         }

@@ -115,6 +115,52 @@ namespace toucan
         return v != 0;
     }
 
+    bool matchFillBackground(const std::shared_ptr<IImageNode>& node, IMATH_NAMESPACE::V2i& size, float color[4])
+    {
+        const ImageEffectNode* fill = asEffect(node, "toucan:Fill");
+        if (!fill || !fill->getInputs().empty())
+        {
+            return false;
+        }
+        const auto& metaData = fill->getMetaData();
+        const auto sizeIt = metaData.find("size");
+        if (sizeIt == metaData.end() || !sizeIt->second.has_value())
+        {
+            return false;
+        }
+        anyToVec(std::any_cast<OTIO_NS::AnyVector>(sizeIt->second), size);
+        if (size.x <= 0 || size.y <= 0)
+        {
+            return false;
+        }
+        // what Fill's render body receives: a vector of doubles from the metadata, else only element 0 of the
+        // described default (= 0)
+        for (int c = 0; c < 4; ++c) color[c] = 0.F;
+        const auto& params = fill->getParams();
+        const auto i = params.find("color");
+        if (i != params.end())
+        {
+            if (auto v = std::any_cast<OTIO_NS::AnyVector>(&i->second))
+            {
+                for (size_t c = 0; c < v->size() && c < 4; ++c)
+                {
+                    auto d = std::any_cast<double>(&(*v)[c]);
+                    if (!d) return false;
+                    color[c] = static_cast<float>(*d);
+                }
+            }
+            else if (auto d = std::any_cast<double>(&i->second))
+            {
+                color[0] = static_cast<float>(*d);
+            }
+            else
+            {
+                return false;
+            }
+        }
+        return true;
+    }
+
     bool tryFusedStack(const CompNode& top, Image& out)
     {
         if (!getStackFusionEnabled())
@@ -126,6 +172,7 @@ namespace toucan
         std::vector<Layer> layers; // top first
         const IImageNode* node = &top;
         const ImageEffectNode* background = nullptr;
+        std::shared_ptr<IImageNode> backgroundNode;
         while (true)
         {
             auto comp = dynamic_cast<const CompNode*>(node);
@@ -142,6 +189,7 @@ namespace toucan
             const auto& below = comp->getInputs()[1];
             if ((background = asEffect(below, "toucan:Fill")))
             {
+                backgroundNode = below;
                 break;
             }
             node = below.get();
@@ -153,47 +201,12 @@ namespace toucan
 
         // Background: a Fill generator of the output size.
         IMATH_NAMESPACE::V2i size(0, 0);
-        {
-            const auto& metaData = background->getMetaData();
-            const auto i = metaData.find("size");
-            if (i == metaData.end() || !i->second.has_value())
-            {
-                return false;
-            }
-            anyToVec(std::any_cast<OTIO_NS::AnyVector>(i->second), size);
-        }
-        if (size.x <= 0 || size.y <= 0)
+        float color[4] = { 0.F, 0.F, 0.F, 0.F };
+        if (!matchFillBackground(backgroundNode, size, color))
         {
             return false;
         }
-        float color[4] = { 0.F, 0.F, 0.F, 0.F };
-        {
-            // what Fill's render body receives: a vector of doubles from the metadata, else
-            // only element 0 of the described default (= 0)
-            const auto& params = background->getParams();
-            const auto i = params.find("color");
-            if (i != params.end())
-            {
-                if (auto v = std::any_cast<OTIO_NS::AnyVector>(&i->second))
-                {
-                    for (size_t c = 0; c < v->size() && c < 4; ++c)
-                    {
-                        auto d = std::any_cast<double>(&(*v)[c]);
-                        if (!d) return false;
-                        color[c] = static_cast<float>(*d);
-                    }
-                }
-                else if (auto d = std::any_cast<double>(&i->second))
-                {
-                    color[0] = static_cast<float>(*d);
-                }
-                else
-                {
-                    return false;
-                }
-            }
-            for (float& c : color) c = quantU8(c);
-        }
+        for (float& c : color) c = quantU8(c);
 
         // All sources must be float32 RGBA frames of the output size (checked on the read
         // nodes' specs before anything is evaluated, and again on the evaluated frames).

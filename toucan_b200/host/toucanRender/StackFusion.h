@@ -9,6 +9,9 @@
 #pragma once
 
 #include <toucanRender/Image.h>
+#include <toucanRender/ImageNode.h>
+
+#include <Imath/ImathVec.h>
 
 namespace toucan
 {
@@ -17,6 +20,10 @@ namespace toucan
     //! Evaluate the chain rooted at `top` in one pass if it matches; false = not fusable
     //! (the caller then evaluates node by node).
     bool tryFusedStack(const CompNode& top, Image& out);
+
+    //! Is `node` the Fill generator a track stack stands on?  Yields its size and the colour its render body would
+    //! receive (unquantised).  Used to composite over a constant instead of materialising the background frame.
+    bool matchFillBackground(const std::shared_ptr<IImageNode>& node, IMATH_NAMESPACE::V2i& size, float color[4]);
 
     //! Enable / disable the fusion pass for the calling process (default: enabled; the
     //! environment variable TOUCAN_NO_FUSION=1 disables it at start-up).

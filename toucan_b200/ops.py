@@ -160,6 +160,11 @@ def over(fg, bg, premult_fg=False, out=None):
     return out
 
 
+def over_fill(fg, color, bg_type=U8, premult_fg=False):
+    out_t = capi.lib().tc_type_merge(tcode(fg), bg_type)
+    return _unary(lib().tc_over_fill, "tc_over_fill", fg, f4(color), bg_type, 1 if premult_fg else 0, out_type=TORCH_OF[out_t])
+
+
 def paste_on_black(src, size, ox, oy, t):
     out = new(size[0], size[1], t)
     check(lib().tc_paste_on_black(_B(img(out)), int(ox), int(oy), _B(img(src)), _stream()), "tc_paste_on_black")
