@@ -82,6 +82,8 @@ int tc_download(void* dst_host, const void* src_dev, size_t bytes, tc_stream s);
 int tc_memset(void* dst_dev, int value, size_t bytes, tc_stream s);
 /* count of kernels launched by this library in the calling process (bench evidence) */
 unsigned long long tc_launch_count(void);
+/* diagnostics: calls into tc_malloc / tc_free so far and the host time spent inside them */
+void tc_alloc_stats(unsigned long long* calls, unsigned long long* nanoseconds);
 
 /* ---- generators: plugins/GeneratorPlugin.cpp -------------------------------------- */
 /* ImageBufAlgo::fill(out, color)                          GeneratorPlugin.cpp:296-303 */

@@ -49,7 +49,17 @@ def resized(doc, size):
     return doc
 
 
+ONLY = ""
+
+
 def bench_timeline(host, label, name, frames_by_file, size=None, cpu_frames=2, doc=None):
+    if ONLY and not any(o in f"{label} {name}" for o in ONLY.split(",")):
+        return None
+    # every row starts from an empty stream-ordered pool, like a fresh toucan-render process: blocks cached for the
+    # previous timeline's frame sizes otherwise make the allocator split and re-map on every frame
+    torch.cuda.synchronize()
+    capi.check(capi.lib().tc_pool_trim(), "tc_pool_trim")
+    torch.cuda.empty_cache()
     if doc is None:
         doc = json.load(open(os.path.join(TL.DATA, name)))
     if size:
@@ -77,11 +87,16 @@ def bench_timeline(host, label, name, frames_by_file, size=None, cpu_frames=2, d
     torch.cuda.synchronize()
     l0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0 = capi.alloc_stats()
+    h0 = time.perf_counter()
     e0.record()
     for _ in range(reps):
         for t in times:
             tl.render_resident(host, t)
     e1.record()
+    host_ms = (time.perf_counter() - h0) * 1e3 / (reps * n)  # time the host needed to ENQUEUE a frame
+    a1 = capi.alloc_stats()
+    alloc_ms = (a1[1] - a0[1]) * 1e3 / (reps * n)
     torch.cuda.synchronize()
     gpu_ms = e0.elapsed_time(e1) / (reps * n)
     launches = (capi.launch_count() - l0) / (reps * n)
@@ -121,7 +136,7 @@ def bench_timeline(host, label, name, frames_by_file, size=None, cpu_frames=2, d
     fbytes = first.nbytes
     obytes = out.nbytes if out is not None else 0
     row = {"config": label, "timeline": name, "frames": n, "size": f"{info['width']}x{info['height']}", "type": str(first.dtype),
-           "gpu_ms_per_frame": round(gpu_ms, 4), "gpu_frames_per_s": round(1e3 / gpu_ms, 1), "kernel_launches_per_frame": round(launches, 1),
+           "gpu_ms_per_frame": round(gpu_ms, 4), "host_enqueue_ms_per_frame": round(host_ms, 4), "allocator_ms_per_frame": round(alloc_ms, 4), "gpu_frames_per_s": round(1e3 / gpu_ms, 1), "kernel_launches_per_frame": round(launches, 1),
            "alg_bytes_per_frame": fbytes + obytes, "alg_GBs": round((fbytes + obytes) / (gpu_ms * 1e-3) / 1e9, 1),
            "e2e_frames_per_s": round(e2e_fps, 1), "cpu_oracle_ms_per_frame": round(cpu_ms, 2), "cpu_cores": os.cpu_count(),
            "gpu_over_cpu": round(cpu_ms / gpu_ms, 1)}
@@ -132,7 +147,10 @@ def bench_timeline(host, label, name, frames_by_file, size=None, cpu_frames=2, d
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="", help="only rows whose 'config timeline' label contains this substring")
     args = ap.parse_args()
+    global ONLY
+    ONLY = args.only
     capi.check(capi.lib().tc_set_device(0), "tc_set_device")
     render.bind_device(0)
     host = render.Host()
@@ -155,6 +173,7 @@ def main():
     c4 = {"Charlie.jpg": synth(3840, 2160, np.float32, 1003)}
     rows.append(bench_timeline(host, "C4 3840x2160 f32", "Transform.otio", c4))
     rows.append(bench_timeline(host, "C4 3840x2160 f32", "ColorSpace.otio", c4))
+    rows = [r for r in rows if r]
     if args.out:
         with open(os.path.join(ROOT, args.out), "w") as f:
             json.dump(rows, f, indent=1)

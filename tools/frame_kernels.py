@@ -28,6 +28,11 @@ def main():
         doc = json.load(open(os.path.join(TL.DATA, "MultipleEffects.otio")))
         media = {os.path.join(TL.DATA, "Charlie.jpg"): synth(3840, 2160, np.float16, 1002)}
         frame = 3.0
+    elif which == "C3c":
+        from tools.config_bench import resized as _rs
+        doc = _rs(json.load(open(os.path.join(TL.DATA, "CompositeTracks.otio"))), (3840, 2160))
+        media = {os.path.join(TL.DATA, f"Counter.{i}.png"): synth(3840, 2160, np.float16, 1100 + i, disc=True) for i in range(10)}
+        frame = 3.0
     elif which == "C4":
         doc = json.load(open(os.path.join(TL.DATA, "Transform.otio")))
         media = {os.path.join(TL.DATA, "Charlie.jpg"): synth(3840, 2160, np.float32, 1003)}

@@ -97,7 +97,7 @@ _SIGS = {
 
 # every symbol include/toucan_cuda.h declares (checked by tests/test_abi.py)
 EXPORTS = sorted(set(_SIGS) | {"tc_version", "tc_last_error", "tc_stream_create", "tc_stream_destroy", "tc_type_size",
-                               "tc_image_bytes", "tc_pool_trim", "tc_memset", "tc_launch_count", "tc_y4m_frame_bytes"})
+                               "tc_image_bytes", "tc_pool_trim", "tc_memset", "tc_launch_count", "tc_y4m_frame_bytes", "tc_alloc_stats"})
 
 
 def lib() -> ctypes.CDLL:
@@ -127,6 +127,13 @@ def check(status: int, what: str = ""):
 
 def f4(c):
     return (ctypes.c_float * 4)(*[float(v) for v in c])
+
+
+def alloc_stats():
+    """(calls, seconds) spent in the stream-ordered allocator so far."""
+    c, ns = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    lib().tc_alloc_stats(ctypes.byref(c), ctypes.byref(ns))
+    return c.value, ns.value * 1e-9
 
 
 def launch_count() -> int:

@@ -1,11 +1,14 @@
 // tc_api.cu -- runtime part of the C ABI: errors, device/stream management, the
 // stream-ordered frame pool and pinned staging.  See include/toucan_cuda.h.
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -175,23 +178,157 @@ int tc_type_merge(int a, int b)
     return TC_F32;
 }
 
+// host time spent inside the allocator (diagnostics: tc_alloc_stats)
+static std::atomic<unsigned long long> g_alloc_calls{ 0 }, g_alloc_ns{ 0 };
+struct AllocTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~AllocTimer()
+    {
+        g_alloc_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        ++g_alloc_calls;
+    }
+};
+
+// ---- frame-buffer cache -----------------------------------------------------------------
+// A render allocates the same handful of buffer sizes for every frame.  The CUDA stream-ordered pool
+// serves them from its free list most of the time, but with several frame sizes in flight it can fall into
+// re-mapping physical memory on every request (measured: 0.27 ms of host time per frame for a 3-launch 4K
+// frame, ten times the cost of building and launching the frame).  So freed buffers are kept here by exact
+// size, per device: a free records an event on the freeing stream, the next allocation of that size makes
+// its stream wait for that event and takes the buffer -- no call into the pool in steady state.  The cache
+// is bounded (TOUCAN_CACHE_BYTES, default 64 GiB of the 180 GB); beyond the bound buffers go back to the pool.
+namespace {
+struct CachedBlock { void* p; cudaEvent_t ev; };
+struct DeviceCache {
+    std::mutex m;
+    std::map<size_t, std::vector<CachedBlock>> free_;
+    std::map<void*, size_t> live;     // buffers handed out by tc_malloc
+    std::vector<cudaEvent_t> events;  // recycled events
+    size_t cached = 0;
+};
+constexpr int kMaxDevices = 64;
+DeviceCache g_cache[kMaxDevices];
+
+size_t cache_limit()
+{
+    static const size_t limit = [] {
+        const char* env = getenv("TOUCAN_CACHE_BYTES");
+        return env && *env ? (size_t)strtoull(env, nullptr, 10) : ((size_t)64 << 30);
+    }();
+    return limit;
+}
+
+DeviceCache* current_cache()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    return &g_cache[dev];
+}
+
+// give every cached buffer back to the stream-ordered pool (caller holds no lock)
+void cache_flush(DeviceCache& c)
+{
+    std::lock_guard<std::mutex> lock(c.m);
+    for (auto& kv : c.free_)
+        for (CachedBlock& b : kv.second) {
+            cudaEventSynchronize(b.ev);
+            cudaFreeAsync(b.p, (cudaStream_t)0);
+            c.events.push_back(b.ev);
+        }
+    c.free_.clear();
+    c.cached = 0;
+}
+} // namespace
+
 int tc_malloc(void** out, size_t bytes, tc_stream s)
 {
     if (!out) return fail(TC_ERR_INVALID, "tc_malloc: null");
     *out = nullptr;
     if (bytes == 0) return TC_OK;
+    AllocTimer timer;
+    DeviceCache* c = current_cache();
+    if (c) {
+        CachedBlock b { nullptr, nullptr };
+        {
+            std::lock_guard<std::mutex> lock(c->m);
+            const auto it = c->free_.find(bytes);
+            if (it != c->free_.end() && !it->second.empty()) {
+                b = it->second.back();
+                it->second.pop_back();
+                c->cached -= bytes;
+                c->live[b.p] = bytes;
+            }
+        }
+        if (b.p) {
+            // everything the previous owner enqueued before freeing the buffer finishes first
+            const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)s, b.ev, 0);
+            {
+                std::lock_guard<std::mutex> lock(c->m);
+                c->events.push_back(b.ev);
+            }
+            TC_CUDA(e);
+            *out = b.p;
+            return TC_OK;
+        }
+    }
     TC_CUDA(cudaMallocAsync(out, bytes, (cudaStream_t)s));
+    if (c) {
+        std::lock_guard<std::mutex> lock(c->m);
+        c->live[*out] = bytes;
+    }
     return TC_OK;
 }
 int tc_free(void* p, tc_stream s)
 {
     if (!p) return TC_OK;
+    AllocTimer timer;
+    DeviceCache* c = current_cache();
+    size_t bytes = 0;
+    cudaEvent_t ev = nullptr;
+    if (c) {
+        std::lock_guard<std::mutex> lock(c->m);
+        const auto it = c->live.find(p);
+        if (it != c->live.end()) {
+            bytes = it->second;
+            c->live.erase(it);
+            if (c->cached + bytes <= cache_limit()) {
+                if (!c->events.empty()) {
+                    ev = c->events.back();
+                    c->events.pop_back();
+                }
+            } else {
+                bytes = 0; // over the bound: straight back to the pool
+            }
+        }
+    }
+    if (bytes) {
+        if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+        if (ev && cudaEventRecord(ev, (cudaStream_t)s) == cudaSuccess) {
+            std::lock_guard<std::mutex> lock(c->m);
+            c->free_[bytes].push_back(CachedBlock { p, ev });
+            c->cached += bytes;
+            return TC_OK;
+        }
+        if (ev) {
+            std::lock_guard<std::mutex> lock(c->m);
+            c->events.push_back(ev);
+        }
+    }
     TC_CUDA(cudaFreeAsync(p, (cudaStream_t)s));
     return TC_OK;
+}
+void tc_alloc_stats(unsigned long long* calls, unsigned long long* nanoseconds)
+{
+    if (calls) *calls = g_alloc_calls.load();
+    if (nanoseconds) *nanoseconds = g_alloc_ns.load();
 }
 int tc_free_sync(void* p)
 {
     if (!p) return TC_OK;
+    if (DeviceCache* c = current_cache()) {
+        std::lock_guard<std::mutex> lock(c->m);
+        c->live.erase(p);
+    }
     TC_CUDA(cudaFree(p));
     return TC_OK;
 }
@@ -201,6 +338,8 @@ int tc_pool_trim(void)
     TC_CUDA(cudaGetDevice(&dev));
     cudaMemPool_t pool;
     TC_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    TC_CUDA(cudaDeviceSynchronize());
+    if (dev >= 0 && dev < kMaxDevices) cache_flush(g_cache[dev]);
     TC_CUDA(cudaDeviceSynchronize());
     TC_CUDA(cudaMemPoolTrimTo(pool, 0));
     return TC_OK;
