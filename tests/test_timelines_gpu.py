@@ -181,6 +181,11 @@ def test_toucan_render_cli(cuda, tmp_path):
     raw = raw.reshape(len(frames), 720, 1280, 4)
     for i, rec in enumerate(frames):
         assert hashlib.sha256(raw[i].tobytes()).hexdigest() == rec["sha256"], f"frame {i}"
+    # several render threads per GPU (-workers): same frames, same order
+    out3 = tmp_path / "transition_w3.raw"
+    r = subprocess.run([exe, os.path.join(TL.DATA, "Transition.otio"), str(out3), "-workers", "3"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out3, "rb").read() == open(out, "rb").read()
 
 
 @pytest.mark.parametrize("devices", [[0], [0, 0, 0]])

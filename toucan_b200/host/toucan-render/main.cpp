@@ -7,7 +7,7 @@
 // encoders (FFmpeg, OIIO writers) are host-side writers outside the hot path.
 //
 //   toucan-render input.otio output|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32]
-//                 [-y4m 422|444|444alpha|444p16] [-gpus N]
+//                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K]
 //                 [-print_start] [-print_duration] [-print_rate] [-print_size]
 #include <toucanRender/FrameScheduler.h>
 #include <toucanRender/TimelineWrapper.h>
@@ -25,11 +25,13 @@ int main(int argc, char** argv)
     {
         std::string input, output, raw, y4m;
         int gpus = 1;
+        int workers = 1; // render threads per GPU: small frames are bound by the host-side graph build, which overlaps across workers
         bool printStart = false, printDuration = false, printRate = false, printSize = false;
         for (int i = 1; i < argc; ++i)
         {
             const std::string a = argv[i];
             if (a == "-gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
+            else if (a == "-workers" && i + 1 < argc) workers = std::atoi(argv[++i]);
             else if (a == "-raw" && i + 1 < argc) raw = argv[++i];
             else if (a == "-y4m" && i + 1 < argc) y4m = argv[++i];
             else if (a == "-print_start") printStart = true;
@@ -41,7 +43,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 
@@ -73,7 +75,10 @@ int main(int argc, char** argv)
         timelineWrapper->getMediaStore()->setDeviceCacheBytes(size_t(8) << 30);
         FrameSchedulerOptions options;
         options.devices.clear();
-        for (int i = 0; i < std::max(1, gpus); ++i) options.devices.push_back(i);
+        for (int i = 0; i < std::max(1, gpus); ++i)
+        {
+            for (int k = 0; k < std::max(1, workers); ++k) options.devices.push_back(i);
+        }
         options.pluginSearchPath = getOpenFXPluginPaths(argv[0]);
         if (!raw.empty() && !parseRawFormat(raw, options.rawType, options.rawChannels))
         {
