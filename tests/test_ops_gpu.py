@@ -421,3 +421,48 @@ def test_over_constant_background_equals_over_a_filled_frame(dt, premult):
         frame = ops.over(to_dev(fg), ops.fill(w, h, color), premult_fg=premult)
         assert_exact(ops.over_fill(to_dev(fg), color, premult_fg=premult), to_host(frame), f"over_fill {color}")
         assert_exact(frame, O.comp(fg, O.fill(w, h, color, O.U8), premult), "over vs oracle")
+
+
+def test_frame_buffer_cache_reuses_across_streams_in_order():
+    """tc_free keeps the buffer by exact size with an event on the freeing stream; tc_malloc on ANOTHER stream takes it
+    over after waiting for that event, so work queued before the free still completes first."""
+    import ctypes
+
+    from toucan_b200 import capi
+
+    lib = capi.lib()
+    w, h = 2048, 1024
+    nbytes = w * h * 4 * 4
+    s1, s2 = ctypes.c_void_p(), ctypes.c_void_p()
+    capi.check(lib.tc_stream_create(ctypes.byref(s1)), "stream")
+    capi.check(lib.tc_stream_create(ctypes.byref(s2)), "stream")
+    p1 = ctypes.c_void_p()
+    capi.check(lib.tc_malloc(ctypes.byref(p1), nbytes, s1), "tc_malloc")
+    img = capi.tc_image(p1.value, w, h, capi.F32)
+    big = torch.rand((h, w, 4), device="cuda")
+    torch.cuda.synchronize()
+    # a long chain of work on stream 1 writing the buffer, then the free
+    src = capi.tc_image(big.data_ptr(), w, h, capi.F32)
+    for _ in range(20):
+        capi.check(lib.tc_blur(ctypes.byref(img), ctypes.byref(src), ctypes.c_float(20.0), s1), "tc_blur")
+    capi.check(lib.tc_free(p1, s1), "tc_free")
+    p2 = ctypes.c_void_p()
+    capi.check(lib.tc_malloc(ctypes.byref(p2), nbytes, s2), "tc_malloc")
+    assert p2.value == p1.value  # same size: the cached buffer, not a new allocation
+    img2 = capi.tc_image(p2.value, w, h, capi.F32)
+    capi.check(lib.tc_fill(ctypes.byref(img2), capi.f4([0.25, 0.5, 0.75, 1.0]), s2), "tc_fill")
+    out = torch.empty((h, w, 4), pin_memory=True)
+    capi.check(lib.tc_download(ctypes.c_void_p(out.data_ptr()), p2, nbytes, s2), "tc_download")
+    capi.check(lib.tc_stream_sync(s2), "sync")
+    capi.check(lib.tc_stream_sync(s1), "sync")
+    want = torch.tensor([0.25, 0.5, 0.75, 1.0]).expand(h, w, 4)
+    assert torch.equal(out, want)  # the fill on stream 2 ran after stream 1's blurs, not under them
+    capi.check(lib.tc_free(p2, s2), "tc_free")
+    # another size does not match the cached buffer
+    p3 = ctypes.c_void_p()
+    capi.check(lib.tc_malloc(ctypes.byref(p3), nbytes // 2, s2), "tc_malloc")
+    assert p3.value != p2.value
+    capi.check(lib.tc_free(p3, s2), "tc_free")
+    capi.check(lib.tc_pool_trim(), "tc_pool_trim")
+    lib.tc_stream_destroy(s1)
+    lib.tc_stream_destroy(s2)
