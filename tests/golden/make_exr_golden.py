@@ -1,0 +1,48 @@
+"""OpenEXR fixtures for the built-in EXR reader, written by the REAL OpenEXR library (through OpenCV).
+
+Run in the authoring container:
+    python tests/golden/make_exr_golden.py
+
+Writes tests/golden/exr/*.exr (seeded 37x21 frames: half / float samples, RGB / RGBA, compression NONE / RLE / ZIPS / ZIP)
+and tests/golden/exr/expected.npz with the pixels OpenCV's OpenEXR reader returns for each file (RGBA order, float32).
+"""
+import os
+
+os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+
+import cv2  # noqa: E402
+import numpy as np  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "exr")
+TYPES = {"half": cv2.IMWRITE_EXR_TYPE_HALF, "float": cv2.IMWRITE_EXR_TYPE_FLOAT}
+COMPRESSIONS = {"none": cv2.IMWRITE_EXR_COMPRESSION_NO, "rle": cv2.IMWRITE_EXR_COMPRESSION_RLE, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
+                "zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(77)
+    w, h = 37, 21  # more than one 16-line ZIP chunk, odd sizes
+    expected = {}
+    for tname, t in TYPES.items():
+        for cname, c in COMPRESSIONS.items():
+            for nch in (3, 4):
+                a = (rng.random((h, w, nch), dtype=np.float32) * 3.0 - 1.0).astype(np.float32)  # negative and > 1 values
+                a[:4, :6] = 0.25  # a flat patch: runs for the RLE coder
+                name = f"{tname}_{cname}_{'rgba' if nch == 4 else 'rgb'}.exr"
+                bgr = a[..., [2, 1, 0, 3]] if nch == 4 else a[..., ::-1]
+                assert cv2.imwrite(os.path.join(OUT, name), np.ascontiguousarray(bgr), [cv2.IMWRITE_EXR_TYPE, t, cv2.IMWRITE_EXR_COMPRESSION, c])
+                b = cv2.imread(os.path.join(OUT, name), cv2.IMREAD_UNCHANGED)
+                rgba = b[..., [2, 1, 0, 3]] if nch == 4 else np.concatenate([b[..., ::-1], np.ones((h, w, 1), np.float32)], -1)
+                expected[name] = np.ascontiguousarray(rgba.astype(np.float32))
+    # a PIZ file: a compression the reader must refuse
+    a = rng.random((h, w, 3), dtype=np.float32)
+    assert cv2.imwrite(os.path.join(OUT, "half_piz_rgb.exr"), a, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION,
+                                                                   cv2.IMWRITE_EXR_COMPRESSION_PIZ])
+    np.savez_compressed(os.path.join(OUT, "expected.npz"), **expected)
+    print(len(expected), "files,", sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

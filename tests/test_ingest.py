@@ -250,3 +250,62 @@ def test_image_and_sequence_open_as_timelines(cuda, tmp_path):
     og = G.ImageGraph(otl, media.decode)
     for f, t in enumerate(otl.frames()):
         assert np.array_equal(frames[f], og.render(t)), f  # frame 3 names file 0006, which does not exist: background only
+
+
+# ---- OpenEXR stills (half / float media) -------------------------------------------------------------------------
+EXR_DIR = os.path.join(TL.GOLDEN, "exr")
+
+
+def _exr_cases():
+    return sorted(f for f in os.listdir(EXR_DIR) if f.endswith(".exr") and "piz" not in f)
+
+
+@pytest.mark.parametrize("name", _exr_cases())
+def test_exr_reader_matches_openexr(built, name):
+    """Files written by the real OpenEXR library (tests/golden/make_exr_golden.py): every sample equals what OpenEXR's own
+    reader returns; the frame's type is the file's sample type; RGB files get A = 1 (Read.cpp:86-94)."""
+    from toucan_b200 import render
+
+    want = np.load(os.path.join(EXR_DIR, "expected.npz"))[name]
+    got = render.decode_exr(os.path.join(EXR_DIR, name))
+    assert got.dtype == (np.float16 if name.startswith("half") else np.float32) and got.shape == want.shape
+    assert np.array_equal(got.astype(np.float32), want)
+    if name.endswith("_rgb.exr"):
+        assert (got[..., 3] == 1).all()
+
+
+def test_exr_reader_refuses_what_it_does_not_decode(built, tmp_path):
+    from toucan_b200 import capi, render
+
+    with pytest.raises(capi.TcError, match="PIZ"):
+        render.decode_exr(os.path.join(EXR_DIR, "half_piz_rgb.exr"))
+    data = open(os.path.join(EXR_DIR, "float_zip_rgba.exr"), "rb").read()
+    bad = str(tmp_path / "cut.exr")
+    with open(bad, "wb") as f:
+        f.write(data[:len(data) // 2])
+    with pytest.raises(capi.TcError):
+        render.decode_exr(bad)
+    with open(bad, "wb") as f:
+        f.write(b"\x00" * 64)
+    with pytest.raises(capi.TcError, match="not an OpenEXR"):
+        render.decode_exr(bad)
+
+
+@pytest.mark.gpu
+def test_exr_still_renders_as_a_timeline(cuda):
+    """A half-float EXR opened as a one-frame timeline: decoded by the read node, composited over the black background
+    in half precision -- equal to the oracle's evaluation of the same decoded frame."""
+    from oracle import oracle as O
+    from toucan_b200 import render
+
+    path = os.path.join(EXR_DIR, "half_zip_rgba.exr")
+    tl = render.Timeline(path)
+    tl.prepare()
+    info = tl.info()
+    assert (info["frames"], info["width"], info["height"]) == (1, 37, 21)
+    out = []
+    tl.render_range(0, 1, lambda f, p: out.append(p.copy()))
+    src = render.decode_exr(path)
+    want = O.comp(src, O.fill(37, 21, [0.0, 0.0, 0.0, 1.0], O.U8), True)
+    assert out[0].dtype == np.float16 and np.array_equal(out[0].view(np.uint16), want.view(np.uint16))
+    tl.close()

@@ -1,5 +1,6 @@
 #include "Read.h"
 
+#include "ExrRead.h"
 #include "JpegRead.h"
 #include "PngRead.h"
 #include "Util.h"
@@ -106,7 +107,7 @@ namespace toucan
         {
             return true;
         }
-        // Built-in readers: PNG (zlib) and JPEG.  The decoded frame is parked in the store so a
+        // Built-in readers: PNG (zlib), JPEG and scanline OpenEXR.  The decoded frame is parked in the store so a
         // still is decoded once; it is still uploaded on every exec().
         const std::string extension = toLower(std::filesystem::path(path).extension().string());
         bool read = false;
@@ -120,6 +121,10 @@ namespace toucan
             else if (".jpg" == extension || ".jpeg" == extension)
             {
                 read = inMemory ? readJpegMemory(memory.data, memory.size, out) : readJpeg(path, out);
+            }
+            else if (".exr" == extension)
+            {
+                read = inMemory ? readExrMemory(memory.data, memory.size, out) : readExr(path, out);
             }
         }
         catch (const std::exception&)

@@ -4,6 +4,7 @@
 #include "ImageEffectHost.h"
 #include "FrameScheduler.h"
 #include "ImageGraph.h"
+#include "ExrRead.h"
 #include "JpegRead.h"
 #include "PngRead.h"
 #include "StackFusion.h"
@@ -393,6 +394,25 @@ extern "C"
             if (out)
             {
                 if (bytes > capacity) return fail("tr_decode_jpeg: output buffer too small");
+                memcpy(out, frame.host, bytes);
+            }
+            return 0;
+        });
+    }
+
+    int tr_decode_exr(const char* path, void* out, size_t capacity, int* width, int* height, int* type)
+    {
+        if (!path) return fail("tr_decode_exr: null");
+        return guarded([&] {
+            MediaFrame frame;
+            if (!readExr(path, frame)) return fail(std::string("tr_decode_exr: cannot read ") + path);
+            if (width) *width = frame.width;
+            if (height) *height = frame.height;
+            if (type) *type = frame.format;
+            const size_t bytes = tc_image_bytes(frame.width, frame.height, frame.format);
+            if (out)
+            {
+                if (bytes > capacity) return fail("tr_decode_exr: output buffer too small");
                 memcpy(out, frame.host, bytes);
             }
             return 0;
