@@ -309,3 +309,47 @@ def test_exr_still_renders_as_a_timeline(cuda):
     want = O.comp(src, O.fill(37, 21, [0.0, 0.0, 0.0, 1.0], O.U8), True)
     assert out[0].dtype == np.float16 and np.array_equal(out[0].view(np.uint16), want.view(np.uint16))
     tl.close()
+
+
+# ---- image-sequence outputs of the command line tool (App.cpp:243-252) -----------------------------------------------
+@pytest.mark.gpu
+def test_cli_writes_png_and_exr_sequences(cuda, tmp_path):
+    import json
+    import subprocess
+
+    from oracle import graph as G
+    from toucan_b200 import capi, render, workloads
+
+    exe = os.path.join(capi.LIB_DIR, "toucan-render")
+    # u8 timeline -> 8-bit PNG sequence numbered from the output name's number; opaque frames read back unchanged
+    gold = TL.golden()["Transition.otio"]["frames"]
+    r = subprocess.run([exe, os.path.join(TL.DATA, "Transition.otio"), str(tmp_path / "out.0100.png")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    names = sorted(f for f in os.listdir(tmp_path) if f.endswith(".png"))
+    assert names == [f"out.{100 + i:04d}.png" for i in range(len(gold))]
+    for i in (0, 4, len(gold) - 1):
+        im = np.asarray(Image.open(str(tmp_path / names[i])))
+        assert im.shape == (720, 1280, 4) and hashlib.sha256(im.tobytes()).hexdigest() == gold[i]["sha256"], i
+    # float EXR still + Invert -> float EXR sequence, every sample as rendered
+    doc = workloads.filter_chain_timeline(frames=3, effects=[("toucan:Invert", {})], url="exr/float_zip_rgba.exr")
+    otio = tmp_path / "invert.otio"
+    otio.write_text(json.dumps(doc))
+    os.symlink(EXR_DIR, str(tmp_path / "exr"))
+    r = subprocess.run([exe, str(otio), str(tmp_path / "inv.exr")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    src = render.decode_exr(os.path.join(EXR_DIR, "float_zip_rgba.exr"))
+    otl = G.Timeline(doc)
+    otl.dir = str(tmp_path)
+    want = G.ImageGraph(otl, lambda p: src if p.endswith("float_zip_rgba.exr") else None).render(G.RT(1.0, 24.0))
+    for i in range(3):
+        got = render.decode_exr(str(tmp_path / f"inv{i}.exr"))
+        assert got.dtype == np.float32 and np.array_equal(got, want), i
+    # the half variant is written as half; an 8-bit timeline asked for .exr is converted to half on the device
+    r = subprocess.run([exe, os.path.join(TL.DATA, "Transition.otio"), str(tmp_path / "t.00.exr")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = render.decode_exr(str(tmp_path / "t.03.exr"))
+    u8 = np.asarray(Image.open(str(tmp_path / names[3])))
+    assert got.dtype == np.float16 and np.array_equal(got, (u8.astype(np.float32) * np.float32(1.0 / 255.0)).astype(np.float16))
+    # encoders that are not built in are refused, not silently written as raw
+    r = subprocess.run([exe, os.path.join(TL.DATA, "Transition.otio"), str(tmp_path / "out.mov")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Unsupported output" in r.stdout

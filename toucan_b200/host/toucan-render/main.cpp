@@ -3,13 +3,18 @@
 // ("-").  The serial frame loop of App.cpp:222-264 is replaced by toucan::FrameScheduler:
 // frames are sharded in contiguous blocks over the GPUs and written in order.  Both output
 // conversions of App.cpp:267-485 (-raw: paste to the raw spec; -y4m: paste + libswscale to
-// planar YUV) run on the device, so only the writer's bytes cross PCIe.  Movie and image-file
-// encoders (FFmpeg, OIIO writers) are host-side writers outside the hot path.
+// planar YUV) run on the device, so only the writer's bytes cross PCIe.  An output name ending in
+// .png or .exr writes a numbered image sequence like App.cpp:243-252 (getSequenceFrame of the
+// name's prefix, start number and padding): .png from 8/16-bit frames (wider frames are converted to
+// 16 bit on the device), .exr from half / float frames (8/16-bit frames are converted to half).
+// Movie encoders and the other OIIO writers are outside the hot path ("Unsupported output").
 //
 //   toucan-render input.otio output|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32]
 //                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K]
 //                 [-print_start] [-print_duration] [-print_rate] [-print_size]
+#include <toucanRender/ExrRead.h>
 #include <toucanRender/FrameScheduler.h>
+#include <toucanRender/PngRead.h>
 #include <toucanRender/TimelineWrapper.h>
 #include <toucanRender/Util.h>
 
@@ -66,10 +71,29 @@ int main(int argc, char** argv)
         int frames = 0;
         for (OTIO_NS::RationalTime time = timeRange.start_time(); time <= timeRange.end_time_inclusive(); time += timeInc) ++frames;
 
-        FILE* f = output == "-" ? stdout : fopen(output.c_str(), "wb");
-        if (!f)
+        // output kind: "-" / anything else = raw stream, *.png / *.exr = numbered image sequence
+        const std::filesystem::path outputPath(output);
+        const std::string outputExtension = toLower(outputPath.extension().string());
+        const bool stream = "-" == output || !raw.empty() || !y4m.empty(); // -raw / -y4m: a byte stream whatever the name
+        const bool toPng = !stream && ".png" == outputExtension;
+        const bool toExr = !stream && ".exr" == outputExtension;
+        const bool toSequence = toPng || toExr;
+        if (output != "-" && !toSequence && raw.empty() && y4m.empty() &&
+            (hasExtension(outputExtension, { ".mov", ".mp4", ".m4v", ".y4m", ".jpg", ".jpeg", ".tif", ".tiff" })))
         {
-            throw std::runtime_error("Cannot open: " + output);
+            throw std::runtime_error("Unsupported output (raw stream, -raw, -y4m, .png and .exr sequences are built in): " + output);
+        }
+        const auto outputSplit = splitFileNameNumber(outputPath.stem().string());
+        const int outputStartFrame = std::atoi(outputSplit.second.c_str());
+        const int outputNumberPadding = static_cast<int>(getNumberPadding(outputSplit.second));
+        FILE* f = nullptr;
+        if (!toSequence)
+        {
+            f = output == "-" ? stdout : fopen(output.c_str(), "wb");
+            if (!f)
+            {
+                throw std::runtime_error("Cannot open: " + output);
+            }
         }
         // stills and sequence frames are decoded once and kept resident (up to 8 GiB per GPU)
         timelineWrapper->getMediaStore()->setDeviceCacheBytes(size_t(8) << 30);
@@ -84,6 +108,15 @@ int main(int argc, char** argv)
         {
             throw std::runtime_error("Cannot find the given raw format");
         }
+        if (toSequence)
+        {
+            // the file format decides the sample type; frames of another type are converted on the device
+            ImageGraph graph(context, std::filesystem::path(input).parent_path(), timelineWrapper);
+            const std::string type = graph.getImageDataType();
+            options.rawChannels = 4;
+            if (toPng) options.rawType = ("u8" == type) ? TC_U8 : TC_U16;
+            else options.rawType = ("float" == type) ? TC_F32 : TC_F16;
+        }
         if (!y4m.empty())
         {
             if (!parseY4mFormat(y4m, options.y4mFormat))
@@ -96,11 +129,30 @@ int main(int argc, char** argv)
             fwrite(header.c_str(), header.size(), 1, f);
         }
         FrameScheduler scheduler(context, timelineWrapper, options);
-        scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec&, size_t bytes)
+        scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec& spec, size_t bytes)
         {
             if (output != "-")
             {
                 std::cout << frame << "/" << frames << std::endl;
+            }
+            if (toSequence && (spec.width <= 0 || spec.height <= 0))
+            {
+                return; // no image at this time: nothing to write
+            }
+            if (toSequence)
+            {
+                // App.cpp:243-252: prefix + (start number + frame number of the absolute time) + extension
+                const int number = outputStartFrame + static_cast<int>(timeRange.start_time().value()) + frame;
+                const std::string fileName = getSequenceFrame(
+                    outputPath.parent_path().string(), outputSplit.first, number, outputNumberPadding, outputPath.extension().string());
+                const bool ok = toPng ?
+                    writePngFrame(fileName, pixels, spec.width, spec.height, TC_U8 == spec.format ? 8 : 16, false, true) :
+                    writeExr(fileName, pixels, spec.width, spec.height, spec.format);
+                if (!ok)
+                {
+                    throw std::runtime_error("Cannot write: " + fileName);
+                }
+                return;
             }
             if (options.y4mFormat >= 0)
             {
@@ -108,7 +160,7 @@ int main(int argc, char** argv)
             }
             fwrite(pixels, 1, bytes, f);
         });
-        if (f != stdout) fclose(f);
+        if (f && f != stdout) fclose(f);
     }
     catch (const std::exception& e)
     {

@@ -315,6 +315,108 @@ namespace toucan
         return true;
     }
 
+    bool writeExr(const std::string& path, const void* pixels, int width, int height, int type)
+    {
+        if ((type != TC_F16 && type != TC_F32) || width <= 0 || height <= 0) return false;
+        const size_t bps = TC_F16 == type ? 2 : 4;
+        std::vector<unsigned char> file;
+        auto put32 = [&file](uint32_t v) { for (int i = 0; i < 4; ++i) file.push_back(static_cast<unsigned char>(v >> (8 * i))); };
+        auto putStr = [&file](const char* s) { file.insert(file.end(), s, s + strlen(s) + 1); };
+        auto attr = [&](const char* name, const char* typeName, uint32_t len) { putStr(name); putStr(typeName); put32(len); };
+        put32(20000630u);
+        put32(2);
+        attr("channels", "chlist", 4 * 18 + 1);
+        for (const char* ch : { "A", "B", "G", "R" })
+        {
+            putStr(ch);
+            put32(TC_F16 == type ? 1u : 2u);
+            put32(0); // pLinear + reserved
+            put32(1);
+            put32(1);
+        }
+        file.push_back(0);
+        attr("compression", "compression", 1);
+        file.push_back(3); // ZIP
+        for (const char* name : { "dataWindow", "displayWindow" })
+        {
+            attr(name, "box2i", 16);
+            put32(0);
+            put32(0);
+            put32(static_cast<uint32_t>(width - 1));
+            put32(static_cast<uint32_t>(height - 1));
+        }
+        attr("lineOrder", "lineOrder", 1);
+        file.push_back(0);
+        const float one = 1.F, zero = 0.F;
+        uint32_t oneBits, zeroBits;
+        memcpy(&oneBits, &one, 4);
+        memcpy(&zeroBits, &zero, 4);
+        attr("pixelAspectRatio", "float", 4);
+        put32(oneBits);
+        attr("screenWindowCenter", "v2f", 8);
+        put32(zeroBits);
+        put32(zeroBits);
+        attr("screenWindowWidth", "float", 4);
+        put32(oneBits);
+        file.push_back(0);
+
+        const int chunks = (height + 15) / 16;
+        const size_t tableAt = file.size();
+        file.resize(tableAt + static_cast<size_t>(chunks) * 8);
+        const size_t lineBytes = static_cast<size_t>(width) * 4 * bps;
+        std::vector<unsigned char> raw, split, packed;
+        static const int order[4] = { 3, 2, 1, 0 }; // file order A, B, G, R
+        for (int k = 0; k < chunks; ++k)
+        {
+            const int y0 = k * 16, lines = std::min(16, height - y0);
+            raw.resize(lineBytes * static_cast<size_t>(lines));
+            for (int l = 0; l < lines; ++l)
+            {
+                const unsigned char* src = static_cast<const unsigned char*>(pixels) + static_cast<size_t>(y0 + l) * lineBytes;
+                unsigned char* dst = raw.data() + static_cast<size_t>(l) * lineBytes;
+                for (int c = 0; c < 4; ++c)
+                {
+                    for (int x = 0; x < width; ++x)
+                    {
+                        memcpy(dst + (static_cast<size_t>(c) * width + x) * bps, src + (static_cast<size_t>(x) * 4 + order[c]) * bps, bps);
+                    }
+                }
+            }
+            // even / odd byte split, then the byte predictor (ImfZip.cpp)
+            const size_t n = raw.size();
+            split.resize(n);
+            {
+                size_t a = 0, b = (n + 1) / 2;
+                for (size_t i = 0; i < n;)
+                {
+                    split[a++] = raw[i++];
+                    if (i < n) split[b++] = raw[i++];
+                }
+                int prev = split[0];
+                for (size_t i = 1; i < n; ++i)
+                {
+                    const int cur = split[i];
+                    split[i] = static_cast<unsigned char>(cur - prev + 128);
+                    prev = cur;
+                }
+            }
+            uLongf zlen = compressBound(static_cast<uLong>(n));
+            packed.resize(zlen);
+            if (compress2(packed.data(), &zlen, split.data(), static_cast<uLong>(n), 4) != Z_OK) return false;
+            const bool stored = zlen >= n;
+            const uint64_t at = file.size();
+            for (int i = 0; i < 8; ++i) file[tableAt + static_cast<size_t>(k) * 8 + static_cast<size_t>(i)] = static_cast<unsigned char>(at >> (8 * i));
+            put32(static_cast<uint32_t>(y0));
+            put32(static_cast<uint32_t>(stored ? n : zlen));
+            if (stored) file.insert(file.end(), raw.begin(), raw.end());
+            else file.insert(file.end(), packed.begin(), packed.begin() + static_cast<long>(zlen));
+        }
+        std::ofstream f(path, std::ios::binary);
+        if (!f) return false;
+        f.write(reinterpret_cast<const char*>(file.data()), static_cast<std::streamsize>(file.size()));
+        return static_cast<bool>(f);
+    }
+
     bool readExr(const std::string& path, MediaFrame& out)
     {
         std::ifstream f(path, std::ios::binary);

@@ -194,14 +194,52 @@ namespace toucan
 
     bool writePng(const std::string& path, const unsigned char* rgba, int width, int height, bool rgb)
     {
+        return writePngFrame(path, rgba, width, height, 8, rgb, false);
+    }
+
+    bool writePngFrame(const std::string& path, const void* pixels, int width, int height, int depth, bool rgb, bool unassociate)
+    {
+        if (depth != 8 && depth != 16) return false;
         const int ch = rgb ? 3 : 4;
-        std::vector<unsigned char> raw((static_cast<size_t>(width) * ch + 1) * height);
+        const size_t bps = static_cast<size_t>(depth / 8);
+        const size_t stride = static_cast<size_t>(width) * ch * bps + 1;
+        const unsigned maxv = 16 == depth ? 65535u : 255u;
+        std::vector<unsigned char> raw(stride * height);
         for (int y = 0; y < height; ++y)
         {
-            unsigned char* row = &raw[(static_cast<size_t>(width) * ch + 1) * y];
+            unsigned char* row = &raw[stride * y];
             row[0] = 0;
             for (int x = 0; x < width; ++x)
-                for (int c = 0; c < ch; ++c) row[1 + x * ch + c] = rgba[(static_cast<size_t>(y) * width + x) * 4 + c];
+            {
+                unsigned v[4];
+                const size_t at = (static_cast<size_t>(y) * width + x) * 4;
+                for (int c = 0; c < 4; ++c)
+                {
+                    v[c] = 16 == depth ? static_cast<const uint16_t*>(pixels)[at + c] : static_cast<const unsigned char*>(pixels)[at + c];
+                }
+                if (unassociate && !rgb && v[3] != 0 && v[3] != maxv)
+                {
+                    // PNG stores unassociated alpha: colour * max / alpha, clamped (OIIO's png writer does the same on write)
+                    for (int c = 0; c < 3; ++c)
+                    {
+                        const unsigned long long f = static_cast<unsigned long long>(v[c]) * maxv / v[3];
+                        v[c] = f > maxv ? maxv : static_cast<unsigned>(f);
+                    }
+                }
+                for (int c = 0; c < ch; ++c)
+                {
+                    unsigned char* o = row + 1 + (static_cast<size_t>(x) * ch + c) * bps;
+                    if (16 == depth)
+                    {
+                        o[0] = static_cast<unsigned char>(v[c] >> 8); // PNG samples are big-endian
+                        o[1] = static_cast<unsigned char>(v[c]);
+                    }
+                    else
+                    {
+                        o[0] = static_cast<unsigned char>(v[c]);
+                    }
+                }
+            }
         }
         uLongf zlen = compressBound(static_cast<uLong>(raw.size()));
         std::vector<unsigned char> z(zlen);
@@ -227,7 +265,7 @@ namespace toucan
                                    static_cast<unsigned char>(width >> 8), static_cast<unsigned char>(width),
                                    static_cast<unsigned char>(height >> 24), static_cast<unsigned char>(height >> 16),
                                    static_cast<unsigned char>(height >> 8), static_cast<unsigned char>(height),
-                                   8, static_cast<unsigned char>(rgb ? 2 : 6), 0, 0, 0 };
+                                   static_cast<unsigned char>(depth), static_cast<unsigned char>(rgb ? 2 : 6), 0, 0, 0 };
         chunk("IHDR", ihdr, 13);
         chunk("IDAT", z.data(), static_cast<uint32_t>(zlen));
         chunk("IEND", nullptr, 0);

@@ -15,4 +15,8 @@ namespace toucan
 
     //! Write 8-bit RGBA (alpha dropped when `rgb` is true).
     bool writePng(const std::string& path, const unsigned char* rgba, int width, int height, bool rgb = false);
+
+    //! Write an RGBA frame of 8- or 16-bit samples (host byte order in memory).  With `unassociate`, premultiplied
+    //! colour is divided by alpha on the way out, as PNG stores unassociated alpha.
+    bool writePngFrame(const std::string& path, const void* pixels, int width, int height, int depth, bool rgb, bool unassociate);
 }
