@@ -400,6 +400,15 @@ extern "C"
         });
     }
 
+    int tr_write_exr(const char* path, const void* pixels, int width, int height, int type)
+    {
+        if (!path || !pixels) return fail("tr_write_exr: null");
+        return guarded([&] {
+            if (!writeExr(path, pixels, width, height, type)) return fail(std::string("tr_write_exr: cannot write ") + path);
+            return 0;
+        });
+    }
+
     int tr_decode_exr(const char* path, void* out, size_t capacity, int* width, int* height, int* type)
     {
         if (!path) return fail("tr_decode_exr: null");
