@@ -109,9 +109,9 @@ int tr_decode_jpeg(const char* path, void* out, size_t capacity, int* width, int
    RGBA out in the widest channel type (*type = TC_F16 or TC_F32), A = 1 when the file has no alpha.  Same calling
    convention as tr_decode_png. */
 int tr_decode_exr(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
-/* The writer behind `toucan-render out.####.exr`: an RGBA half (TC_F16) or float (TC_F32) host frame as a scanline,
-   ZIP-compressed OpenEXR file. */
-int tr_write_exr(const char* path, const void* pixels, int width, int height, int type);
+/* The writer behind `toucan-render out.####.exr`: an RGBA half (TC_F16) or float (TC_F32) host frame as a scanline
+   OpenEXR file, ZIP-compressed (zip != 0, what the command line tool writes) or uncompressed. */
+int tr_write_exr(const char* path, const void* pixels, int width, int height, int type, int zip);
 
 /* Cross-node fusion of the track stack (default on). */
 void tr_set_fusion(int enabled);

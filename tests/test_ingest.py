@@ -365,6 +365,8 @@ def test_exr_writer_round_trips_and_is_valid_openexr(built, tmp_path):
         a = (rng.random((45, 83, 4), dtype=np.float32) * 4.0 - 1.5).astype(dtype)
         a[:20, :30] = dtype(0.5)
         path = str(tmp_path / f"w_{np.dtype(dtype).name}.exr")
+        render.write_exr(str(tmp_path / "raw.exr"), a, zip=False)
+        assert np.array_equal(render.decode_exr(str(tmp_path / "raw.exr")).view(np.uint8), a.view(np.uint8))
         render.write_exr(path, a)
         back = render.decode_exr(path)
         assert back.dtype == dtype and np.array_equal(back.view(np.uint16 if dtype == np.float16 else np.uint32),

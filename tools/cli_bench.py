@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Wall-clock throughput of the command line tool itself on the config-5 structure, from files on disk:
+
+    toucan-render stack.otio - -y4m 422 -gpus N  >  /dev/null
+
+float32 OpenEXR stills (uncompressed, written once into a scratch directory) -> read nodes (decoded once per still and kept in
+the 8 GiB device source cache) -> fused stack kernel -> y4m conversion on the device -> ordered download -> stdout.  This is the
+product as a user runs it; bench.py's e2e instead re-uploads every source on every frame as the measurement contract requires.
+
+  python tools/cli_bench.py [--size 3840x2160] [--tracks 10] [--frames 240] [--gpus 1] [--format 422] [--out profiles/xxx.json]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from toucan_b200 import capi, render, workloads  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", default="3840x2160")
+    ap.add_argument("--tracks", type=int, default=10)
+    ap.add_argument("--frames", type=int, default=240)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--format", default="422", help="y4m format, or raw:<fmt> for -raw")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    w, h = [int(v) for v in args.size.split("x")]
+    scratch = tempfile.mkdtemp(prefix="toucan_cli_bench_")
+    os.makedirs(os.path.join(scratch, "stills"))
+    text = json.dumps(workloads.stack_timeline(tracks=args.tracks, frames=args.frames))
+    rng = np.random.default_rng(5)
+    t0 = time.perf_counter()
+    for t in range(args.tracks):
+        for k in range(2):
+            a = rng.random((h, w, 4), dtype=np.float32)
+            rel = f"stills/t{t}_k{k}.exr"
+            render.write_exr(os.path.join(scratch, rel), a, zip=False)
+            text = text.replace(workloads.still_url(t, k), rel)
+    with open(os.path.join(scratch, "stack.otio"), "w") as f:
+        f.write(text)
+    prep = time.perf_counter() - t0
+    exe = os.path.join(capi.LIB_DIR, "toucan-render")
+    fmt = ["-raw", args.format[4:]] if args.format.startswith("raw:") else ["-y4m", args.format]
+    rows = []
+    # the first run is a throw-away (the stills were just written: page cache and write-back settle); then both timed
+    # runs touch every still and their difference is steady-state rendering
+    for frames in (args.frames, args.frames, 2 * args.frames):
+        s = json.dumps(workloads.stack_timeline(tracks=args.tracks, frames=frames))
+        for t in range(args.tracks):
+            for k in range(2):
+                s = s.replace(workloads.still_url(t, k), f"stills/t{t}_k{k}.exr")
+        otio = os.path.join(scratch, f"stack_{frames}.otio")
+        with open(otio, "w") as f:
+            f.write(s)
+        cmd = [exe, otio, "-"] + fmt + ["-gpus", str(args.gpus)]
+        t0 = time.perf_counter()
+        with open(os.devnull, "wb") as null:
+            r = subprocess.run(cmd, stdout=null, stderr=subprocess.PIPE, timeout=3000)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise SystemExit(r.stderr.decode()[-2000:])
+        rows.append((frames, dt))
+    (f0, t0_), (f1, t1_) = rows[1:]
+    steady = (f1 - f0) / (t1_ - t0_)
+    out = {"tool": "toucan-render", "workload": f"config-5 structure, {args.tracks} tracks, {w}x{h} float32 EXR stills, {fmt[0]} {fmt[1]} to /dev/null",
+           "gpus": args.gpus, "frames": f0, "wall_s": round(t0_, 3), "frames_per_s_whole_run": round(f0 / t0_, 1),
+           "frames_2x": f1, "wall_s_2x": round(t1_, 3), "startup_s_estimate": round(t0_ - f0 / steady, 3),
+           "frames_per_s_steady": round(steady, 1), "stills_written_s": round(prep, 1)}
+    print(json.dumps(out))
+    if args.out:
+        with open(os.path.join(ROOT, args.out), "w") as f:
+            json.dump(out, f, indent=1)
+    subprocess.run(["rm", "-rf", scratch])
+
+
+if __name__ == "__main__":
+    main()

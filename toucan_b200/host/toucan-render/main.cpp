@@ -10,7 +10,7 @@
 // Movie encoders and the other OIIO writers are outside the hot path ("Unsupported output").
 //
 //   toucan-render input.otio output|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32]
-//                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K]
+//                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K] [-cache GiB] [-v]
 //                 [-print_start] [-print_duration] [-print_rate] [-print_size]
 #include <toucanRender/ExrRead.h>
 #include <toucanRender/FrameScheduler.h>
@@ -18,6 +18,7 @@
 #include <toucanRender/TimelineWrapper.h>
 #include <toucanRender/Util.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -30,15 +31,18 @@ int main(int argc, char** argv)
     {
         std::string input, output, raw, y4m;
         int gpus = 1;
+        double cacheGiB = 64.0; // device source cache per GPU (a B200 has 180 GB): stills and sequence frames are uploaded once
         int workers = 1; // render threads per GPU: small frames are bound by the host-side graph build, which overlaps across workers
-        bool printStart = false, printDuration = false, printRate = false, printSize = false;
+        bool printStart = false, printDuration = false, printRate = false, printSize = false, verbose = false;
         for (int i = 1; i < argc; ++i)
         {
             const std::string a = argv[i];
             if (a == "-gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
             else if (a == "-workers" && i + 1 < argc) workers = std::atoi(argv[++i]);
+            else if (a == "-cache" && i + 1 < argc) cacheGiB = std::atof(argv[++i]);
             else if (a == "-raw" && i + 1 < argc) raw = argv[++i];
             else if (a == "-y4m" && i + 1 < argc) y4m = argv[++i];
+            else if (a == "-v") verbose = true;
             else if (a == "-print_start") printStart = true;
             else if (a == "-print_duration") printDuration = true;
             else if (a == "-print_rate") printRate = true;
@@ -48,7 +52,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-cache GiB] [-v] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 
@@ -95,8 +99,8 @@ int main(int argc, char** argv)
                 throw std::runtime_error("Cannot open: " + output);
             }
         }
-        // stills and sequence frames are decoded once and kept resident (up to 8 GiB per GPU)
-        timelineWrapper->getMediaStore()->setDeviceCacheBytes(size_t(8) << 30);
+        // stills and sequence frames are decoded once and kept resident (-cache GiB per GPU, least recently used out first)
+        timelineWrapper->getMediaStore()->setDeviceCacheBytes(static_cast<size_t>(std::max(0.0, cacheGiB) * 1073741824.0));
         FrameSchedulerOptions options;
         options.devices.clear();
         for (int i = 0; i < std::max(1, gpus); ++i)
@@ -128,6 +132,9 @@ int main(int argc, char** argv)
             const std::string header = y4mHeader(graph.getImageSize().x, graph.getImageSize().y, timeRange.duration().rate(), y4m);
             fwrite(header.c_str(), header.size(), 1, f);
         }
+        const auto wallStart = std::chrono::steady_clock::now();
+        // decode the timeline's stills in the background, in clip order, while the first frames render
+        MediaPrefetch prefetch(timelineWrapper->getMediaStore(), timelineWrapper->getStillMedia(), 2);
         FrameScheduler scheduler(context, timelineWrapper, options);
         scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec& spec, size_t bytes)
         {
@@ -161,6 +168,17 @@ int main(int argc, char** argv)
             fwrite(pixels, 1, bytes, f);
         });
         if (f && f != stdout) fclose(f);
+        if (verbose)
+        {
+            // -v (App.cpp:98-100): run statistics on stderr, so they never mix with a stream on stdout
+            const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wallStart).count();
+            unsigned long long allocCalls = 0, allocNs = 0;
+            tc_alloc_stats(&allocCalls, &allocNs);
+            std::cerr << "frames: " << frames << "  seconds: " << seconds << "  frames/s: " << (seconds > 0.0 ? frames / seconds : 0.0)
+                      << "  kernel launches: " << tc_launch_count() << "  allocator calls: " << allocCalls << " (" << allocNs * 1e-9 << " s)"
+                      << "  source uploads: " << timelineWrapper->getMediaStore()->getUploadCount() << " ("
+                      << timelineWrapper->getMediaStore()->getUploadBytes() / 1.0e9 << " GB)" << std::endl;
+        }
     }
     catch (const std::exception& e)
     {

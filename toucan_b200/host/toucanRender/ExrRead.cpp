@@ -2,10 +2,19 @@
 
 #include <zlib.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <stdexcept>
+#include <thread>
 
 namespace toucan
 {
@@ -225,84 +234,132 @@ namespace toucan
         for (uint64_t& o : offsets) o = r.u64();
 
         const size_t pixelBytes = asFloat ? 16 : 8;
-        auto pixels = std::make_shared<std::vector<unsigned char> >(static_cast<size_t>(width) * height * pixelBytes);
-        std::vector<unsigned char> tmp, raw;
-        for (int k = 0; k < chunks; ++k)
+        // uninitialised storage: value-initialising (and page-faulting) half a gigabyte twice is most of a naive decode
+        std::shared_ptr<unsigned char> pixels(new unsigned char[static_cast<size_t>(width) * height * pixelBytes], std::default_delete<unsigned char[]>());
+
+        // one planar scanline -> interleaved RGBA; typed loops the compiler can keep in registers
+        auto interleave = [&](const unsigned char* line, unsigned char* dst)
         {
-            Reader c{ data, size, static_cast<size_t>(offsets[static_cast<size_t>(k)]) };
-            const int y0 = c.i32() - dw[1];
-            const uint32_t packed = c.u32();
-            c.need(packed);
-            if (y0 < 0 || y0 >= height) bad("bad chunk");
-            const int lines = std::min(linesPerChunk, height - y0);
-            const size_t expected = lineBytes * static_cast<size_t>(lines);
-            const unsigned char* src = data + c.pos;
-            if (packed < expected)
+            for (int ch = 0; ch < 4; ++ch)
             {
-                if (1 == compression)
+                const Channel* cn = rgba[ch];
+                if (asFloat)
                 {
-                    unrle(src, packed, tmp, expected);
-                }
-                else if (compression >= 2)
-                {
-                    tmp.resize(expected);
-                    uLongf n = static_cast<uLongf>(expected);
-                    if (uncompress(tmp.data(), &n, src, packed) != Z_OK || n != expected) bad("bad zlib data");
+                    float* o = reinterpret_cast<float*>(dst) + ch;
+                    if (!cn)
+                    {
+                        for (int x = 0; x < width; ++x) o[static_cast<size_t>(x) * 4] = 1.F; // Read.cpp:86-94: A = 1
+                    }
+                    else if (2 == cn->type)
+                    {
+                        const unsigned char* in = line + cn->offset;
+                        for (int x = 0; x < width; ++x)
+                        {
+                            float v;
+                            memcpy(&v, in + static_cast<size_t>(x) * 4, 4);
+                            o[static_cast<size_t>(x) * 4] = v;
+                        }
+                    }
+                    else
+                    {
+                        const unsigned char* in = line + cn->offset;
+                        for (int x = 0; x < width; ++x)
+                        {
+                            uint16_t hv;
+                            memcpy(&hv, in + static_cast<size_t>(x) * 2, 2);
+                            o[static_cast<size_t>(x) * 4] = halfToFloat(hv);
+                        }
+                    }
                 }
                 else
                 {
-                    bad("bad chunk size");
-                }
-                unpredict(tmp, raw);
-                src = raw.data();
-            }
-            else if (packed != expected)
-            {
-                bad("bad chunk size");
-            }
-            // a chunk that did not shrink is stored as it is
-            for (int l = 0; l < lines; ++l)
-            {
-                const unsigned char* line = src + lineBytes * static_cast<size_t>(l);
-                unsigned char* dst = pixels->data() + (static_cast<size_t>(y0 + l) * width) * pixelBytes;
-                for (int ch = 0; ch < 4; ++ch)
-                {
-                    const Channel* cn = rgba[ch];
-                    for (int x = 0; x < width; ++x)
+                    uint16_t* o = reinterpret_cast<uint16_t*>(dst) + ch;
+                    if (!cn)
                     {
-                        unsigned char* o = dst + static_cast<size_t>(x) * pixelBytes + static_cast<size_t>(ch) * (asFloat ? 4 : 2);
-                        if (!cn)
-                        {
-                            // no alpha channel: Read.cpp:86-94 appends A = 1
-                            if (asFloat)
-                            {
-                                const float one = 1.F;
-                                memcpy(o, &one, 4);
-                            }
-                            else
-                            {
-                                const uint16_t one = 0x3c00;
-                                memcpy(o, &one, 2);
-                            }
-                        }
-                        else if (2 == cn->type)
-                        {
-                            memcpy(o, line + cn->offset + static_cast<size_t>(x) * 4, 4);
-                        }
-                        else if (asFloat)
+                        for (int x = 0; x < width; ++x) o[static_cast<size_t>(x) * 4] = 0x3c00; // half 1.0
+                    }
+                    else
+                    {
+                        const unsigned char* in = line + cn->offset;
+                        for (int x = 0; x < width; ++x)
                         {
                             uint16_t hv;
-                            memcpy(&hv, line + cn->offset + static_cast<size_t>(x) * 2, 2);
-                            const float f = halfToFloat(hv);
-                            memcpy(o, &f, 4);
-                        }
-                        else
-                        {
-                            memcpy(o, line + cn->offset + static_cast<size_t>(x) * 2, 2);
+                            memcpy(&hv, in + static_cast<size_t>(x) * 2, 2);
+                            o[static_cast<size_t>(x) * 4] = hv;
                         }
                     }
                 }
             }
+        };
+
+        // chunks are independent: decode them on several threads (a 4K float frame is 133 MB, an 8K one 531 MB)
+        auto decodeChunks = [&](int first, int step, std::string& error)
+        {
+            std::vector<unsigned char> tmp, raw;
+            try
+            {
+                for (int k = first; k < chunks; k += step)
+                {
+                    Reader c{ data, size, static_cast<size_t>(offsets[static_cast<size_t>(k)]) };
+                    const int y0 = c.i32() - dw[1];
+                    const uint32_t packed = c.u32();
+                    c.need(packed);
+                    if (y0 < 0 || y0 >= height) bad("bad chunk");
+                    const int lines = std::min(linesPerChunk, height - y0);
+                    const size_t expected = lineBytes * static_cast<size_t>(lines);
+                    const unsigned char* src = data + c.pos;
+                    if (packed < expected)
+                    {
+                        if (1 == compression)
+                        {
+                            unrle(src, packed, tmp, expected);
+                        }
+                        else if (compression >= 2)
+                        {
+                            tmp.resize(expected);
+                            uLongf n = static_cast<uLongf>(expected);
+                            if (uncompress(tmp.data(), &n, src, packed) != Z_OK || n != expected) bad("bad zlib data");
+                        }
+                        else
+                        {
+                            bad("bad chunk size");
+                        }
+                        unpredict(tmp, raw);
+                        src = raw.data();
+                    }
+                    else if (packed != expected)
+                    {
+                        bad("bad chunk size");
+                    }
+                    // (a chunk that did not shrink is stored as it is)
+                    for (int l = 0; l < lines; ++l)
+                    {
+                        interleave(src + lineBytes * static_cast<size_t>(l), pixels.get() + (static_cast<size_t>(y0 + l) * width) * pixelBytes);
+                    }
+                }
+            }
+            catch (const std::exception& e)
+            {
+                error = e.what();
+            }
+        };
+        const size_t totalBytes = static_cast<size_t>(width) * height * pixelBytes;
+        const int threads = static_cast<int>(std::max<size_t>(1, std::min<size_t>({ 8, std::thread::hardware_concurrency() / 2, totalBytes >> 22,
+                                                                                    static_cast<size_t>(chunks) })));
+        std::vector<std::string> errors(static_cast<size_t>(threads));
+        if (1 == threads)
+        {
+            decodeChunks(0, 1, errors[0]);
+        }
+        else
+        {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; ++t) pool.emplace_back(decodeChunks, t, threads, std::ref(errors[static_cast<size_t>(t)]));
+            for (auto& t : pool) t.join();
+        }
+        for (const std::string& e : errors)
+        {
+            if (!e.empty()) throw std::runtime_error(e);
         }
 
         out = MediaFrame();
@@ -310,12 +367,12 @@ namespace toucan
         out.height = height;
         out.nchannels = 4;
         out.format = asFloat ? TC_F32 : TC_F16;
-        out.owned = pixels;
-        out.host = pixels->data();
+        out.storage = pixels;
+        out.host = pixels.get();
         return true;
     }
 
-    bool writeExr(const std::string& path, const void* pixels, int width, int height, int type)
+    bool writeExr(const std::string& path, const void* pixels, int width, int height, int type, bool zip)
     {
         if ((type != TC_F16 && type != TC_F32) || width <= 0 || height <= 0) return false;
         const size_t bps = TC_F16 == type ? 2 : 4;
@@ -336,7 +393,7 @@ namespace toucan
         }
         file.push_back(0);
         attr("compression", "compression", 1);
-        file.push_back(3); // ZIP
+        file.push_back(zip ? 3 : 0); // ZIP (blocks of 16 lines) or NONE (one line per chunk)
         for (const char* name : { "dataWindow", "displayWindow" })
         {
             attr(name, "box2i", 16);
@@ -360,7 +417,8 @@ namespace toucan
         put32(oneBits);
         file.push_back(0);
 
-        const int chunks = (height + 15) / 16;
+        const int linesPerChunk = zip ? 16 : 1;
+        const int chunks = (height + linesPerChunk - 1) / linesPerChunk;
         const size_t tableAt = file.size();
         file.resize(tableAt + static_cast<size_t>(chunks) * 8);
         const size_t lineBytes = static_cast<size_t>(width) * 4 * bps;
@@ -368,7 +426,7 @@ namespace toucan
         static const int order[4] = { 3, 2, 1, 0 }; // file order A, B, G, R
         for (int k = 0; k < chunks; ++k)
         {
-            const int y0 = k * 16, lines = std::min(16, height - y0);
+            const int y0 = k * linesPerChunk, lines = std::min(linesPerChunk, height - y0);
             raw.resize(lineBytes * static_cast<size_t>(lines));
             for (int l = 0; l < lines; ++l)
             {
@@ -382,8 +440,17 @@ namespace toucan
                     }
                 }
             }
-            // even / odd byte split, then the byte predictor (ImfZip.cpp)
             const size_t n = raw.size();
+            if (!zip)
+            {
+                const uint64_t at = file.size();
+                for (int i = 0; i < 8; ++i) file[tableAt + static_cast<size_t>(k) * 8 + static_cast<size_t>(i)] = static_cast<unsigned char>(at >> (8 * i));
+                put32(static_cast<uint32_t>(y0));
+                put32(static_cast<uint32_t>(n));
+                file.insert(file.end(), raw.begin(), raw.end());
+                continue;
+            }
+            // even / odd byte split, then the byte predictor (ImfZip.cpp)
             split.resize(n);
             {
                 size_t a = 0, b = (n + 1) / 2;
@@ -419,9 +486,30 @@ namespace toucan
 
     bool readExr(const std::string& path, MediaFrame& out)
     {
-        std::ifstream f(path, std::ios::binary);
-        if (!f) return false;
-        const std::vector<unsigned char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-        return readExrMemory(bytes.data(), bytes.size(), out);
+        // map the file: the decoder reads every byte once
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || st.st_size <= 0)
+        {
+            close(fd);
+            return false;
+        }
+        const size_t size = static_cast<size_t>(st.st_size);
+        void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        if (MAP_FAILED == map) return false;
+        madvise(map, size, MADV_SEQUENTIAL);
+        try
+        {
+            const bool ok = readExrMemory(static_cast<const unsigned char*>(map), size, out);
+            munmap(map, size);
+            return ok;
+        }
+        catch (...)
+        {
+            munmap(map, size);
+            throw;
+        }
     }
 }

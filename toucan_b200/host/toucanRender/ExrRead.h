@@ -18,7 +18,7 @@ namespace toucan
     bool readExr(const std::string& path, MediaFrame& out);
     bool readExrMemory(const unsigned char* data, size_t size, MediaFrame& out);
 
-    //! Write an RGBA half (TC_F16) or float (TC_F32) frame as a scanline OpenEXR file, ZIP-compressed in blocks of 16
-    //! lines (OpenImageIO's default for .exr output).
-    bool writeExr(const std::string& path, const void* pixels, int width, int height, int type);
+    //! Write an RGBA half (TC_F16) or float (TC_F32) frame as a scanline OpenEXR file: ZIP-compressed in blocks of 16
+    //! lines (OpenImageIO's default for .exr output), or uncompressed.
+    bool writeExr(const std::string& path, const void* pixels, int width, int height, int type, bool zip = true);
 }

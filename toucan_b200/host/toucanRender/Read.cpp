@@ -5,7 +5,9 @@
 #include "PngRead.h"
 #include "Util.h"
 
+#include <atomic>
 #include <sstream>
+#include <thread>
 
 namespace toucan
 {
@@ -89,6 +91,45 @@ namespace toucan
         }
     }
 
+    bool MediaStore::beginLoad(const std::string& path)
+    {
+        std::unique_lock<std::mutex> lock(_mutex);
+        if (_loading.insert(path).second)
+        {
+            return true;
+        }
+        _loaded.wait(lock, [this, &path] { return 0 == _loading.count(path); });
+        return false;
+    }
+
+    void MediaStore::endLoad(const std::string& path)
+    {
+        {
+            std::lock_guard<std::mutex> lock(_mutex);
+            _loading.erase(path);
+        }
+        _loaded.notify_all();
+    }
+
+    void MediaStore::countUpload(size_t bytes)
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        ++_uploads;
+        _uploadBytes += bytes;
+    }
+
+    size_t MediaStore::getUploadCount() const
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        return _uploads;
+    }
+
+    size_t MediaStore::getUploadBytes() const
+    {
+        std::lock_guard<std::mutex> lock(_mutex);
+        return _uploadBytes;
+    }
+
     void MediaStore::dropCached()
     {
         std::lock_guard<std::mutex> lock(_mutex);
@@ -101,39 +142,108 @@ namespace toucan
         return store;
     }
 
-    bool readMedia(const std::shared_ptr<MediaStore>& store, const std::string& path, MediaFrame& out, const MemoryReference& memory)
+    namespace
+    {
+        bool decodeMedia(const std::string& path, MediaFrame& out, const MemoryReference& memory)
+        {
+            // Built-in readers: PNG (zlib), JPEG and scanline OpenEXR.
+            const std::string extension = toLower(std::filesystem::path(path).extension().string());
+            const bool inMemory = memory.isValid();
+            try
+            {
+                if (".png" == extension)
+                {
+                    return inMemory ? readPngMemory(memory.data, memory.size, out) : readPng(path, out);
+                }
+                if (".jpg" == extension || ".jpeg" == extension)
+                {
+                    return inMemory ? readJpegMemory(memory.data, memory.size, out) : readJpeg(path, out);
+                }
+                if (".exr" == extension)
+                {
+                    return inMemory ? readExrMemory(memory.data, memory.size, out) : readExr(path, out);
+                }
+            }
+            catch (const std::exception&)
+            {
+                // OIIO::ImageInput::open returns null for a file it cannot decode (Read.cpp:40-46)
+            }
+            return false;
+        }
+    }
+
+    bool readMedia(const std::shared_ptr<MediaStore>& store, const std::string& path, MediaFrame& out, const MemoryReference& memory, bool park)
     {
         if (store && store->get(path, out))
         {
             return true;
         }
-        // Built-in readers: PNG (zlib), JPEG and scanline OpenEXR.  The decoded frame is parked in the store so a
-        // still is decoded once; it is still uploaded on every exec().
-        const std::string extension = toLower(std::filesystem::path(path).extension().string());
+        if (!store || !park)
+        {
+            return decodeMedia(path, out, memory);
+        }
+        // The decoded frame is parked in the store so a still is decoded once (it is still uploaded on every exec()
+        // unless the device source cache is on).  One thread decodes a given file; a concurrent caller -- a render
+        // thread catching up with the prefetcher, or the other way round -- waits for it instead of decoding again.
+        if (!store->beginLoad(path))
+        {
+            return store->get(path, out);
+        }
         bool read = false;
-        const bool inMemory = memory.isValid();
         try
         {
-            if (".png" == extension)
-            {
-                read = inMemory ? readPngMemory(memory.data, memory.size, out) : readPng(path, out);
-            }
-            else if (".jpg" == extension || ".jpeg" == extension)
-            {
-                read = inMemory ? readJpegMemory(memory.data, memory.size, out) : readJpeg(path, out);
-            }
-            else if (".exr" == extension)
-            {
-                read = inMemory ? readExrMemory(memory.data, memory.size, out) : readExr(path, out);
-            }
+            read = decodeMedia(path, out, memory);
+            if (read) store->set(path, out);
         }
-        catch (const std::exception&)
+        catch (...)
         {
-            // OIIO::ImageInput::open returns null for a file it cannot decode (Read.cpp:40-46)
-            read = false;
+            store->endLoad(path);
+            throw;
         }
-        if (read && store) store->set(path, out);
+        store->endLoad(path);
         return read;
+    }
+
+    struct MediaPrefetch::State
+    {
+        std::shared_ptr<MediaStore> store;
+        std::vector<std::pair<std::string, MemoryReference> > media;
+        std::atomic<size_t> next{ 0 };
+        std::atomic<bool> stop{ false };
+        std::vector<std::thread> threads;
+    };
+
+    MediaPrefetch::MediaPrefetch(
+        const std::shared_ptr<MediaStore>& store,
+        const std::vector<std::pair<std::string, MemoryReference> >& media,
+        int threads) :
+        _state(std::make_shared<State>())
+    {
+        _state->store = store;
+        _state->media = media;
+        State* state = _state.get();
+        for (int t = 0; t < std::max(1, threads); ++t)
+        {
+            _state->threads.emplace_back([state]
+            {
+                for (;;)
+                {
+                    const size_t i = state->next++;
+                    if (i >= state->media.size() || state->stop) return;
+                    MediaFrame frame;
+                    readMedia(state->store, state->media[i].first, frame, state->media[i].second);
+                }
+            });
+        }
+    }
+
+    MediaPrefetch::~MediaPrefetch()
+    {
+        _state->stop = true;
+        for (auto& t : _state->threads)
+        {
+            if (t.joinable()) t.join();
+        }
     }
 
     IReadNode::IReadNode(const std::string& name) :
@@ -168,9 +278,11 @@ namespace toucan
                 return cached;
             }
             cached = Image::upload(frame.host, spec);
+            store->countUpload(spec.image_bytes());
             store->putCached(device, path, cached);
             return cached;
         }
+        if (store) store->countUpload(spec.image_bytes());
         return Image::upload(frame.host, spec);
     }
 
@@ -242,7 +354,7 @@ namespace toucan
         MediaFrame frame;
         const std::string first = getSequenceFrame(_base, _namePrefix, _startFrame, _frameZeroPadding, _nameSuffix);
         const auto memory = _memoryReferences.find(first);
-        if (readMedia(_store, first, frame, memory != _memoryReferences.end() ? memory->second : MemoryReference()))
+        if (readMedia(_store, first, frame, memory != _memoryReferences.end() ? memory->second : MemoryReference(), false))
         {
             _spec = ImageSpec(frame.width, frame.height, frame.nchannels, frame.format);
         }
@@ -267,7 +379,7 @@ namespace toucan
         const std::string url = getSequenceFrame(_base, _namePrefix, _time.to_frames(), _frameZeroPadding, _nameSuffix);
         MediaFrame frame;
         const auto memory = _memoryReferences.find(url);
-        if (!readMedia(_store, url, frame, memory != _memoryReferences.end() ? memory->second : MemoryReference()))
+        if (!readMedia(_store, url, frame, memory != _memoryReferences.end() ? memory->second : MemoryReference(), false))
         {
             return Image();
         }

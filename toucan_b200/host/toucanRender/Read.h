@@ -10,9 +10,11 @@
 #include <toucanRender/ImageNode.h>
 
 #include <filesystem>
+#include <condition_variable>
 #include <list>
 #include <map>
 #include <mutex>
+#include <set>
 
 namespace toucan
 {
@@ -25,7 +27,8 @@ namespace toucan
         int height = 0;
         int nchannels = 4;
         int format = TC_U8;
-        std::shared_ptr<std::vector<unsigned char> > owned; // storage for frames decoded by the built-in reader
+        std::shared_ptr<std::vector<unsigned char> > owned; // storage for frames decoded by the built-in readers
+        std::shared_ptr<unsigned char> storage;               // ... or a plain (uninitialised) array for the large ones
     };
 
     //! A file held in memory (lib/toucanRender/MemoryMap.h: MemoryReference): an entry of a mapped .otioz.
@@ -62,6 +65,15 @@ namespace toucan
         void putCached(int device, const std::string& path, const Image&);
         void dropCached();
 
+        //! Decode coordination: the first caller for a path gets true and must call endLoad(); others block until it has.
+        bool beginLoad(const std::string& path);
+        void endLoad(const std::string& path);
+
+        //! Host -> device uploads of source frames so far (diagnostics).
+        void countUpload(size_t bytes);
+        size_t getUploadCount() const;
+        size_t getUploadBytes() const;
+
     private:
         struct Cached
         {
@@ -72,6 +84,9 @@ namespace toucan
         mutable std::mutex _mutex;
         std::map<std::string, MediaFrame> _frames;
         size_t _cacheLimit = 0;
+        size_t _uploads = 0, _uploadBytes = 0;
+        std::set<std::string> _loading;
+        std::condition_variable _loaded;
         std::list<Cached> _cache; // most recently used first
     };
 
@@ -152,8 +167,23 @@ namespace toucan
         MemoryReferences _memoryReferences;
     };
 
+    //! Decode, in the background, the stills and sequence frames a timeline references (in timeline order) and park them
+    //! in the store, so the render threads find them decoded.  Returns immediately; the returned handle joins on destruction.
+    class MediaPrefetch
+    {
+    public:
+        MediaPrefetch(const std::shared_ptr<MediaStore>&, const std::vector<std::pair<std::string, MemoryReference> >& media, int threads = 2);
+        ~MediaPrefetch();
+
+    private:
+        struct State;
+        std::shared_ptr<State> _state;
+    };
+
     //! Look a frame up in the store, falling back to the built-in file readers.
-    bool readMedia(const std::shared_ptr<MediaStore>&, const std::string& path, MediaFrame&, const MemoryReference& = MemoryReference());
+    //! `park`: keep the decoded frame in the store (stills, decoded once); sequence frames are used once and are not kept.
+    bool readMedia(const std::shared_ptr<MediaStore>&, const std::string& path, MediaFrame&, const MemoryReference& = MemoryReference(),
+        bool park = true);
 
     //! Create a read node for a single image.  Throws std::runtime_error if the media cannot
     //! be opened (the caller logs it and the clip yields no node, ImageGraph.cpp:355-367).

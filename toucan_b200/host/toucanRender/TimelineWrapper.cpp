@@ -2,6 +2,8 @@
 
 #include "Util.h"
 
+#include <set>
+
 namespace toucan
 {
     namespace
@@ -205,6 +207,27 @@ namespace toucan
                 sequenceRef->frame_zero_padding(),
                 _store,
                 _memoryReferences);
+        }
+        return out;
+    }
+
+    std::vector<std::pair<std::string, MemoryReference> > TimelineWrapper::getStillMedia() const
+    {
+        std::vector<std::pair<std::string, MemoryReference> > out;
+        std::set<std::string> seen;
+        for (const auto& clip : _timeline->find_clips())
+        {
+            if (auto externalRef = dynamic_cast<OTIO_NS::ExternalReference*>(clip->media_reference()))
+            {
+                const std::string path = getMediaPath(externalRef->target_url());
+                if (!hasExtension(toLower(std::filesystem::path(path).extension().string()), ImageReadNode::getExtensions()) ||
+                    !seen.insert(path).second)
+                {
+                    continue;
+                }
+                const auto memory = _memoryReferences.find(externalRef->target_url());
+                out.emplace_back(path, memory != _memoryReferences.end() ? memory->second : MemoryReference());
+            }
         }
         return out;
     }

@@ -36,6 +36,10 @@ namespace toucan
 
         std::shared_ptr<IReadNode> createReadNode(const OTIO_NS::MediaReference*);
 
+        //! The stills (single-file media) the timeline's clips reference, in clip order, without duplicates: what a
+        //! background prefetch decodes ahead of the render threads.  Sequence frames are not listed (they stream).
+        std::vector<std::pair<std::string, MemoryReference> > getStillMedia() const;
+
         //! Decoded frames the read nodes draw from (defaults to the process-wide store).
         void setMediaStore(const std::shared_ptr<MediaStore>&);
         const std::shared_ptr<MediaStore>& getMediaStore() const;

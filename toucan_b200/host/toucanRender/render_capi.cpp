@@ -400,11 +400,11 @@ extern "C"
         });
     }
 
-    int tr_write_exr(const char* path, const void* pixels, int width, int height, int type)
+    int tr_write_exr(const char* path, const void* pixels, int width, int height, int type, int zip)
     {
         if (!path || !pixels) return fail("tr_write_exr: null");
         return guarded([&] {
-            if (!writeExr(path, pixels, width, height, type)) return fail(std::string("tr_write_exr: cannot write ") + path);
+            if (!writeExr(path, pixels, width, height, type, zip != 0)) return fail(std::string("tr_write_exr: cannot write ") + path);
             return 0;
         });
     }

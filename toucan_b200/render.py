@@ -42,7 +42,7 @@ _SIGS = {
     "tr_decode_png": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_decode_jpeg": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_decode_exr": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
-    "tr_write_exr": [ctypes.c_char_p, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int],
+    "tr_write_exr": [ctypes.c_char_p, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int],
     "tr_timeline_render_resident": [_VP, _VP, ctypes.c_double, ctypes.POINTER(_VP), _IP, _IP, _IP],
 }
 FRAME_CALLBACK = ctypes.CFUNCTYPE(None, _VP, ctypes.c_int, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int)
@@ -143,10 +143,10 @@ def decode_exr(path: str) -> np.ndarray:
     return out
 
 
-def write_exr(path: str, frame: np.ndarray):
-    """Write an (h, w, 4) float16 / float32 array as a ZIP-compressed scanline OpenEXR file."""
+def write_exr(path: str, frame: np.ndarray, zip: bool = True):
+    """Write an (h, w, 4) float16 / float32 array as a scanline OpenEXR file (ZIP-compressed or uncompressed)."""
     assert frame.ndim == 3 and frame.shape[2] == 4 and frame.flags.c_contiguous and frame.dtype in (np.float16, np.float32)
-    _check(lib().tr_write_exr(path.encode(), frame.ctypes.data, frame.shape[1], frame.shape[0], _T_OF[frame.dtype]), "tr_write_exr")
+    _check(lib().tr_write_exr(path.encode(), frame.ctypes.data, frame.shape[1], frame.shape[0], _T_OF[frame.dtype], 1 if zip else 0), "tr_write_exr")
 
 
 class Host:
