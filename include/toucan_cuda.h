@@ -75,6 +75,9 @@ int tc_free_sync(void* p); /* cudaFree: for memory whose stream no longer exists
 int tc_pool_trim(void);
 /* pinned host staging + copies (upload of decoded frames: Read.cpp:64-101; download
    for the writers: bin/toucan-render/App.cpp:238-262) */
+/* page-lock / unlock memory the caller owns (decoded source frames), so uploads run at PCIe speed from every GPU */
+int tc_host_register(void* p, size_t bytes);
+int tc_host_unregister(void* p);
 int tc_host_alloc(void** out, size_t bytes);
 int tc_host_free(void* p);
 int tc_upload(void* dst_dev, const void* src_host, size_t bytes, tc_stream s);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tools/cli_probe.sh WxH frames  -- writes stills, runs the CLI with -v in a few configurations
+# usage: tools/cli_probe.sh WxH frames  -- writes stills once, runs the CLI with -v in a few configurations
 set -e
 python - "$1" "$2" <<'PY'
 import json, os, sys
@@ -9,17 +9,21 @@ from toucan_b200 import render, workloads
 w, h = [int(v) for v in sys.argv[1].split("x")]
 frames = int(sys.argv[2])
 d = "/tmp/cli_probe"; os.makedirs(d + "/stills", exist_ok=True)
-text = json.dumps(workloads.stack_timeline(tracks=10, frames=frames))
 rng = np.random.default_rng(5)
 for t in range(10):
     for k in range(2):
-        rel = f"stills/t{t}_k{k}.exr"
-        render.write_exr(os.path.join(d, rel), rng.random((h, w, 4), dtype=np.float32), zip=False)
-        text = text.replace(workloads.still_url(t, k), rel)
-open(d + "/stack.otio", "w").write(text)
+        render.write_exr(os.path.join(d, f"stills/t{t}_k{k}.exr"), rng.random((h, w, 4), dtype=np.float32), zip=False)
+for n in (frames, 2 * frames):
+    text = json.dumps(workloads.stack_timeline(tracks=10, frames=n))
+    for t in range(10):
+        for k in range(2):
+            text = text.replace(workloads.still_url(t, k), f"stills/t{t}_k{k}.exr")
+    open(d + f"/stack_{n}.otio", "w").write(text)
 PY
 EXE=toucan_b200/lib/toucan-render
-echo "== y4m 422"; $EXE /tmp/cli_probe/stack.otio - -y4m 422 -v > /dev/null
-echo "== raw"; $EXE /tmp/cli_probe/stack.otio - -v > /dev/null
-echo "== no fusion"; TOUCAN_NO_FUSION=1 $EXE /tmp/cli_probe/stack.otio - -y4m 422 -v > /dev/null
+F=$2
+echo "== warm"; $EXE /tmp/cli_probe/stack_$F.otio - -y4m 422 -v > /dev/null
+echo "== N"; $EXE /tmp/cli_probe/stack_$F.otio - -y4m 422 -v > /dev/null
+echo "== 2N"; $EXE /tmp/cli_probe/stack_$((2*F)).otio - -y4m 422 -v > /dev/null
+echo "== 2N again"; $EXE /tmp/cli_probe/stack_$((2*F)).otio - -y4m 422 -v > /dev/null
 rm -rf /tmp/cli_probe

@@ -86,6 +86,8 @@ _SIGS = {
     "tc_download": [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, _S],
     "tc_host_alloc": [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t],
     "tc_host_free": [ctypes.c_void_p],
+    "tc_host_register": [ctypes.c_void_p, ctypes.c_size_t],
+    "tc_host_unregister": [ctypes.c_void_p],
     "tc_type_merge": [ctypes.c_int, ctypes.c_int],
     "tc_event_create": [ctypes.POINTER(ctypes.c_void_p)],
     "tc_event_destroy": [ctypes.c_void_p],

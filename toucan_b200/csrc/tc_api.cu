@@ -344,6 +344,18 @@ int tc_pool_trim(void)
     TC_CUDA(cudaMemPoolTrimTo(pool, 0));
     return TC_OK;
 }
+int tc_host_register(void* p, size_t bytes)
+{
+    if (!p || !bytes) return fail(TC_ERR_INVALID, "tc_host_register: null");
+    TC_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return TC_OK;
+}
+int tc_host_unregister(void* p)
+{
+    if (!p) return TC_OK;
+    TC_CUDA(cudaHostUnregister(p));
+    return TC_OK;
+}
 int tc_host_alloc(void** out, size_t bytes)
 {
     if (!out) return fail(TC_ERR_INVALID, "tc_host_alloc: null");

@@ -136,8 +136,15 @@ int main(int argc, char** argv)
         // decode the timeline's stills in the background, in clip order, while the first frames render
         MediaPrefetch prefetch(timelineWrapper->getMediaStore(), timelineWrapper->getStillMedia(), 2);
         FrameScheduler scheduler(context, timelineWrapper, options);
+        double firstFrameSeconds = 0.0, halfWaySeconds = 0.0;
         scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec& spec, size_t bytes)
         {
+            if (verbose && (0 == frame || frames / 2 == frame))
+            {
+                const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - wallStart).count();
+                if (0 == frame) firstFrameSeconds = t;
+                if (frames / 2 == frame) halfWaySeconds = t;
+            }
             if (output != "-")
             {
                 std::cout << frame << "/" << frames << std::endl;
@@ -174,7 +181,10 @@ int main(int argc, char** argv)
             const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wallStart).count();
             unsigned long long allocCalls = 0, allocNs = 0;
             tc_alloc_stats(&allocCalls, &allocNs);
+            const double secondHalf = seconds - halfWaySeconds;
             std::cerr << "frames: " << frames << "  seconds: " << seconds << "  frames/s: " << (seconds > 0.0 ? frames / seconds : 0.0)
+                      << "  first frame after: " << firstFrameSeconds << " s  second half: "
+                      << (secondHalf > 0.0 ? (frames - frames / 2) / secondHalf : 0.0) << " frames/s"
                       << "  kernel launches: " << tc_launch_count() << "  allocator calls: " << allocCalls << " (" << allocNs * 1e-9 << " s)"
                       << "  source uploads: " << timelineWrapper->getMediaStore()->getUploadCount() << " ("
                       << timelineWrapper->getMediaStore()->getUploadBytes() / 1.0e9 << " GB)" << std::endl;

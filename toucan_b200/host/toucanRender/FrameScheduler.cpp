@@ -124,7 +124,7 @@ namespace toucan
         struct Worker
         {
             int device = 0;
-            int first = 0, last = 0;
+            int first = 0, last = 0, step = 1;
             std::vector<Slot> slots;
             std::mutex mutex;
             std::condition_variable cv;
@@ -158,9 +158,20 @@ namespace toucan
         {
             auto w = std::make_unique<Worker>();
             w->device = _options.devices[static_cast<size_t>(i)];
-            const auto block = frameBlock(first, last, i, count);
-            w->first = block.first;
-            w->last = block.second;
+            if (_options.interleave)
+            {
+                // frame f belongs to worker (f - first) % count: the ordered writer visits the workers round-robin, so
+                // every GPU renders all the time with a ring of only framesInFlight slots
+                w->first = first + i;
+                w->last = last;
+                w->step = count;
+            }
+            else
+            {
+                const auto block = frameBlock(first, last, i, count);
+                w->first = block.first;
+                w->last = block.second;
+            }
             w->slots.resize(static_cast<size_t>(_options.framesInFlight));
             for (int s = 0; s < _options.framesInFlight; ++s) w->free_.push_back(s);
             workers.push_back(std::move(w));
@@ -184,7 +195,7 @@ namespace toucan
                     host = std::make_shared<ImageEffectHost>(_context, _options.pluginSearchPath);
                 }
                 auto graph = std::make_shared<ImageGraph>(_context, _timelineWrapper->getPath().parent_path(), _timelineWrapper);
-                for (int frame = w.first; frame < w.last; ++frame)
+                for (int frame = w.first; frame < w.last; frame += w.step)
                 {
                     int index = -1;
                     {
@@ -284,37 +295,52 @@ namespace toucan
             wp->thread = std::thread([body, wp] { body(*wp); });
         }
 
-        // The writer: frames in order, each from the worker that owns its block.
+        // The writer: frames in timeline order, each from the worker that owns it.
         std::exception_ptr error;
-        for (auto& w : workers)
+        auto owner = [&](int frame) -> Worker*
         {
-            for (int frame = w->first; frame < w->last && !error; ++frame)
+            if (_options.interleave)
             {
-                int index = -1;
-                {
-                    std::unique_lock<std::mutex> lock(w->mutex);
-                    w->cv.wait(lock, [&w] { return !w->ready.empty() || w->error || w->finished; });
-                    if (w->error) { error = w->error; break; }
-                    if (w->ready.empty()) { error = std::make_exception_ptr(std::runtime_error("frame scheduler: worker ended early")); break; }
-                    index = w->ready.front();
-                    w->ready.pop_front();
-                }
-                Slot& slot = w->slots[static_cast<size_t>(index)];
-                try
-                {
-                    tcCheck(tc_event_sync(slot.done), "tc_event_sync");
-                    writer(slot.frame, slot.pinned, slot.spec, slot.bytes);
-                }
-                catch (...)
-                {
-                    error = std::current_exception();
-                }
-                {
-                    std::lock_guard<std::mutex> lock(w->mutex);
-                    w->free_.push_back(index);
-                }
-                w->cv.notify_all();
+                return workers[static_cast<size_t>((frame - first) % count)].get();
             }
+            for (auto& w : workers)
+            {
+                if (frame >= w->first && frame < w->last) return w.get();
+            }
+            return nullptr;
+        };
+        for (int frame = first; frame < last && !error; ++frame)
+        {
+            Worker* w = owner(frame);
+            if (!w)
+            {
+                error = std::make_exception_ptr(std::runtime_error("frame scheduler: frame without a worker"));
+                break;
+            }
+            int index = -1;
+            {
+                std::unique_lock<std::mutex> lock(w->mutex);
+                w->cv.wait(lock, [w] { return !w->ready.empty() || w->error || w->finished; });
+                if (w->error) { error = w->error; break; }
+                if (w->ready.empty()) { error = std::make_exception_ptr(std::runtime_error("frame scheduler: worker ended early")); break; }
+                index = w->ready.front();
+                w->ready.pop_front();
+            }
+            Slot& slot = w->slots[static_cast<size_t>(index)];
+            try
+            {
+                tcCheck(tc_event_sync(slot.done), "tc_event_sync");
+                writer(slot.frame, slot.pinned, slot.spec, slot.bytes);
+            }
+            catch (...)
+            {
+                error = std::current_exception();
+            }
+            {
+                std::lock_guard<std::mutex> lock(w->mutex);
+                w->free_.push_back(index);
+            }
+            w->cv.notify_all();
         }
         if (error)
         {

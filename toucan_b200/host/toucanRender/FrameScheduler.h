@@ -4,7 +4,8 @@
 // Replaces the serial loop of bin/toucan-render/App.cpp:222-264 (one frame in flight, one
 // node at a time, the writer blocking the renderer).  Frames are independent
 // (lib/toucanRender/ImageGraph.cpp:144-215 builds a fresh tree per time), so:
-//   * the range is cut into contiguous blocks, one per GPU -- no collective;
+//   * frames are dealt to the GPUs round-robin (or in contiguous blocks, SURVEY 8e, for writers that do not need
+//     timeline order across GPUs) -- no collective;
 //   * each GPU has a worker thread with its own device binding, ImageEffectHost and
 //     ImageGraph (ImageGraph::exec is not re-entrant), a render stream and a copy stream;
 //   * a finished frame is downloaded on the copy stream into a pinned ring slot while the
@@ -22,6 +23,11 @@ namespace toucan
         std::vector<int> devices = { 0 };
         std::vector<std::filesystem::path> pluginSearchPath;
         int framesInFlight = 2; //!< pinned ring slots per GPU
+        //! Frame -> worker assignment.  Interleaved (frame f to worker f % G): the ordered writer drains the workers
+        //! round-robin, so all GPUs render concurrently with small rings.  Contiguous blocks (frameBlock) keep each
+        //! worker on consecutive frames -- what separate processes use (bench.py, one rank per GPU, no shared writer) --
+        //! but behind ONE ordered writer a worker can only run framesInFlight frames ahead of its turn.
+        bool interleave = true;
         //! Raw output format (bin/toucan-render/App.cpp:26-35 rawSpecs): when rawType >= 0 and the
         //! frame's storage type differs from it, the frame is converted ON THE DEVICE to
         //! rawChannels x rawType before the download (the reference converts on the host with

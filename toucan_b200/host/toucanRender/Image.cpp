@@ -80,6 +80,7 @@ namespace toucan
     {
         void* p = nullptr;
         tc_stream stream = nullptr;
+        std::shared_ptr<const void> hostSource; // page-locked host memory an asynchronous upload is still reading
         ~Buffer()
         {
             // stream-ordered release; if that stream is gone (a cached frame outliving its worker)
@@ -120,6 +121,11 @@ namespace toucan
             tcCheck(tc_upload(out._data, hostPixels, spec.image_bytes(), DeviceContext::stream()), "tc_upload");
         }
         return out;
+    }
+
+    void Image::keepAlive(const std::shared_ptr<const void>& hostSource)
+    {
+        if (_buffer) _buffer->hostSource = hostSource;
     }
 
     void Image::download(void* hostPixels) const

@@ -56,6 +56,10 @@ namespace toucan
         //! Upload host pixels (tightly packed) on the calling thread's stream.
         static Image upload(const void* hostPixels, const ImageSpec&);
 
+        //! Tie the lifetime of the host memory an upload reads to this image: uploads from page-locked memory are
+        //! asynchronous, so the source must outlive the copy (it is released with the device buffer).
+        void keepAlive(const std::shared_ptr<const void>& hostSource);
+
         const ImageSpec& spec() const { return _spec; }
         bool initialized() const { return _data != nullptr; }
         void* data() const { return _data; }

@@ -193,7 +193,24 @@ namespace toucan
         try
         {
             read = decodeMedia(path, out, memory);
-            if (read) store->set(path, out);
+            if (read)
+            {
+                // A parked still lives as long as the store: page-lock the large ones (when there is a CUDA device to
+                // upload to), so every GPU's upload runs at PCIe speed.  Frames that are not parked stay pageable --
+                // an asynchronous copy from locked memory could outlive them.
+                const size_t bytes = tc_image_bytes(out.width, out.height, out.format);
+                void* p = const_cast<void*>(out.host);
+                if (bytes >= (size_t(32) << 20) && p && TC_OK == tc_host_register(p, bytes))
+                {
+                    const auto innerStorage = out.storage;
+                    const auto innerOwned = out.owned;
+                    out.storage = std::shared_ptr<unsigned char>(static_cast<unsigned char*>(p), [innerStorage, innerOwned](unsigned char* q)
+                    {
+                        tc_host_unregister(q); // before the captured owners free the memory
+                    });
+                }
+                store->set(path, out);
+            }
         }
         catch (...)
         {
@@ -278,12 +295,15 @@ namespace toucan
                 return cached;
             }
             cached = Image::upload(frame.host, spec);
+            cached.keepAlive(frame.storage ? std::shared_ptr<const void>(frame.storage) : std::shared_ptr<const void>(frame.owned));
             store->countUpload(spec.image_bytes());
             store->putCached(device, path, cached);
             return cached;
         }
         if (store) store->countUpload(spec.image_bytes());
-        return Image::upload(frame.host, spec);
+        Image uploaded = Image::upload(frame.host, spec);
+        uploaded.keepAlive(frame.storage ? std::shared_ptr<const void>(frame.storage) : std::shared_ptr<const void>(frame.owned));
+        return uploaded;
     }
 
     ImageReadNode::ImageReadNode(
