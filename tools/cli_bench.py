@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--frames", type=int, default=240)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--format", default="422", help="y4m format, or raw:<fmt> for -raw")
+    ap.add_argument("--inflight", type=int, default=0)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     w, h = [int(v) for v in args.size.split("x")]
@@ -58,7 +59,7 @@ def main():
     otio = os.path.join(scratch, "stack.otio")
     with open(otio, "w") as f:
         f.write(s)
-    cmd = [exe, otio, "-"] + fmt + ["-gpus", str(args.gpus), "-v"]
+    cmd = [exe, otio, "-"] + fmt + ["-gpus", str(args.gpus), "-v"] + (["-inflight", str(args.inflight)] if args.inflight else [])
     runs = []
     for _ in range(3):  # the first run is a throw-away (the stills were just written: page cache and write-back settle)
         t0 = time.perf_counter()

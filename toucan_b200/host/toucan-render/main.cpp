@@ -10,7 +10,7 @@
 // Movie encoders and the other OIIO writers are outside the hot path ("Unsupported output").
 //
 //   toucan-render input.otio output|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32]
-//                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K] [-cache GiB] [-v]
+//                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K] [-cache GiB] [-inflight N] [-v]
 //                 [-print_start] [-print_duration] [-print_rate] [-print_size]
 #include <toucanRender/ExrRead.h>
 #include <toucanRender/FrameScheduler.h>
@@ -32,6 +32,7 @@ int main(int argc, char** argv)
         std::string input, output, raw, y4m;
         int gpus = 1;
         double cacheGiB = 64.0; // device source cache per GPU (a B200 has 180 GB): stills and sequence frames are uploaded once
+        int inflight = 0; // pinned ring slots per worker (0 = the scheduler's default)
         int workers = 1; // render threads per GPU: small frames are bound by the host-side graph build, which overlaps across workers
         bool printStart = false, printDuration = false, printRate = false, printSize = false, verbose = false;
         for (int i = 1; i < argc; ++i)
@@ -40,6 +41,7 @@ int main(int argc, char** argv)
             if (a == "-gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
             else if (a == "-workers" && i + 1 < argc) workers = std::atoi(argv[++i]);
             else if (a == "-cache" && i + 1 < argc) cacheGiB = std::atof(argv[++i]);
+            else if (a == "-inflight" && i + 1 < argc) inflight = std::atoi(argv[++i]);
             else if (a == "-raw" && i + 1 < argc) raw = argv[++i];
             else if (a == "-y4m" && i + 1 < argc) y4m = argv[++i];
             else if (a == "-v") verbose = true;
@@ -108,6 +110,7 @@ int main(int argc, char** argv)
             for (int k = 0; k < std::max(1, workers); ++k) options.devices.push_back(i);
         }
         options.pluginSearchPath = getOpenFXPluginPaths(argv[0]);
+        if (inflight > 0) options.framesInFlight = inflight;
         if (!raw.empty() && !parseRawFormat(raw, options.rawType, options.rawChannels))
         {
             throw std::runtime_error("Cannot find the given raw format");

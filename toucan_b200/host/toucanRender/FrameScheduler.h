@@ -22,7 +22,7 @@ namespace toucan
     {
         std::vector<int> devices = { 0 };
         std::vector<std::filesystem::path> pluginSearchPath;
-        int framesInFlight = 2; //!< pinned ring slots per GPU
+        int framesInFlight = 4; //!< pinned ring slots per GPU (behind one ordered writer, two slots leave ~30 % of four GPUs idle)
         //! Frame -> worker assignment.  Interleaved (frame f to worker f % G): the ordered writer drains the workers
         //! round-robin, so all GPUs render concurrently with small rings.  Contiguous blocks (frameBlock) keep each
         //! worker on consecutive frames -- what separate processes use (bench.py, one rank per GPU, no shared writer) --
