@@ -109,6 +109,10 @@ int tr_decode_jpeg(const char* path, void* out, size_t capacity, int* width, int
    RGBA out in the widest channel type (*type = TC_F16 or TC_F32), A = 1 when the file has no alpha.  Same calling
    convention as tr_decode_png. */
 int tr_decode_exr(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
+/* The built-in TIFF reader (classic, stripped, chunky RGB / RGBA; 8/16-bit unsigned or 32-bit float; uncompressed, LZW,
+   deflate, PackBits; predictor 1 or 2): RGBA out in the file's sample type, A = 1 for RGB, unassociated alpha associated
+   on read.  Same calling convention as tr_decode_png. */
+int tr_decode_tiff(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
 /* The writer behind `toucan-render out.####.exr`: an RGBA half (TC_F16) or float (TC_F32) host frame as a scanline
    OpenEXR file, ZIP-compressed (zip != 0, what the command line tool writes) or uncompressed. */
 int tr_write_exr(const char* path, const void* pixels, int width, int height, int type, int zip);

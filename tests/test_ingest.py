@@ -420,3 +420,66 @@ def test_cli_renders_the_stack_workload_from_exr_stills(cuda, tmp_path):
     for i in (0, 24, 40, 47, 60, 79):  # plain frames and frames inside dissolves
         want = og.render(times[i])
         assert float(np.abs(frames[i] - want).max()) <= 1e-5, i
+
+
+# ---- TIFF stills -------------------------------------------------------------------------------------------------
+def _associate_u8(rgba):
+    """OIIO associates unassociated alpha on read (what Pillow writes for RGBA): v' = store_u8(alpha * v) in float."""
+    f = rgba.astype(np.float32) * np.float32(1.0 / 255.0)
+    al = f[..., 3:4]
+    rgb = np.where(al != 1.0, al * f[..., :3], f[..., :3]).astype(np.float32)
+    q = np.clip(rgb * np.float32(255.0) + np.float32(0.5), 0, 255).astype(np.uint8)
+    return np.concatenate([q, rgba[..., 3:4]], -1)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (64, 33), (301, 77)])
+@pytest.mark.parametrize("channels", [3, 4])
+def test_tiff_reader_matches_libtiff(built, tmp_path, size, channels):
+    """8-bit files written by Pillow (libtiff): uncompressed, LZW, deflate and PackBits strips, with and without the
+    horizontal-differencing predictor -- every sample as Pillow decodes it."""
+    from toucan_b200 import render
+
+    w, h = size
+    rng = np.random.default_rng(3)
+    for kind in ("noise", "ramp"):
+        a = rng.integers(0, 256, (h, w, channels), dtype=np.uint8) if kind == "noise" else \
+            np.ascontiguousarray(np.broadcast_to((np.arange(w)[None, :, None] * 5 + np.arange(h)[:, None, None] * 3) % 256, (h, w, channels)).astype(np.uint8))
+        for compression in (None, "tiff_lzw", "tiff_adobe_deflate", "packbits"):
+            for predictor in (None, 2):
+                if predictor and compression not in ("tiff_lzw", "tiff_adobe_deflate"):
+                    continue
+                path = str(tmp_path / "t.tif")
+                kw = {}
+                if compression:
+                    kw["compression"] = compression
+                if predictor:
+                    kw["tiffinfo"] = {317: 2}
+                Image.fromarray(a).save(path, **kw)
+                want = np.asarray(Image.open(path))
+                want = np.concatenate([want, np.full((h, w, 1), 255, np.uint8)], -1) if channels == 3 else _associate_u8(want)
+                got = render.decode_tiff(path)
+                assert got.dtype == np.uint8 and np.array_equal(got, want), (size, channels, kind, compression, predictor)
+
+
+def test_tiff_reader_16_bit_and_float(built, tmp_path):
+    """16-bit (LZW + predictor, what OpenCV's libtiff writes) and 32-bit float files against OpenCV's decode."""
+    cv2 = pytest.importorskip("cv2")
+    from toucan_b200 import capi, render
+
+    rng = np.random.default_rng(4)
+    for dtype, scale in ((np.uint16, 65535.0), (np.float32, 2.0)):
+        for ch in (3, 4):
+            a = (rng.random((45, 83, ch)) * scale).astype(dtype)
+            path = str(tmp_path / "c.tif")
+            assert cv2.imwrite(path, a)
+            b = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+            want = b[..., [2, 1, 0, 3]] if ch == 4 else np.concatenate([b[..., ::-1], np.full((45, 83, 1), dtype(scale if dtype == np.uint16 else 1.0), dtype)], -1)
+            got = render.decode_tiff(path)
+            assert got.dtype == dtype and np.array_equal(got, want), (dtype, ch)
+    with open(str(tmp_path / "junk.tif"), "wb") as f:
+        f.write(b"II*\x00" + b"\x00" * 20)
+    with pytest.raises(capi.TcError):
+        render.decode_tiff(str(tmp_path / "junk.tif"))
+    Image.fromarray(rng.integers(0, 256, (9, 9), dtype=np.uint8)).save(str(tmp_path / "gray.tif"))
+    with pytest.raises(capi.TcError, match="RGB"):
+        render.decode_tiff(str(tmp_path / "gray.tif"))

@@ -97,7 +97,7 @@ def build_cuda(verbose=False, force=False):
 
 
 HOST_LIB_SOURCES = ["otio.cpp", "PropertySet.cpp", "Plugin.cpp", "Util.cpp", "Image.cpp", "ImageNode.cpp", "ImageEffect.cpp",
-                    "ImageEffectHost.cpp", "Comp.cpp", "StackFusion.cpp", "Read.cpp", "PngRead.cpp", "JpegRead.cpp", "ExrRead.cpp", "Archive.cpp", "TimelineWrapper.cpp", "ImageGraph.cpp", "FrameScheduler.cpp", "render_capi.cpp"]
+                    "ImageEffectHost.cpp", "Comp.cpp", "StackFusion.cpp", "Read.cpp", "PngRead.cpp", "JpegRead.cpp", "ExrRead.cpp", "TiffRead.cpp", "Archive.cpp", "TimelineWrapper.cpp", "ImageGraph.cpp", "FrameScheduler.cpp", "render_capi.cpp"]
 PLUGIN_MODULES = {
     "toucanGeneratorPlugin.ofx": ["GeneratorPlugin.cpp"],
     "toucanFilterPlugin.ofx": ["FilterPlugin.cpp"],

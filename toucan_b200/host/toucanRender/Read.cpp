@@ -3,6 +3,7 @@
 #include "ExrRead.h"
 #include "JpegRead.h"
 #include "PngRead.h"
+#include "TiffRead.h"
 #include "Util.h"
 
 #include <atomic>
@@ -146,7 +147,7 @@ namespace toucan
     {
         bool decodeMedia(const std::string& path, MediaFrame& out, const MemoryReference& memory)
         {
-            // Built-in readers: PNG (zlib), JPEG and scanline OpenEXR.
+            // Built-in readers: PNG (zlib), JPEG, scanline OpenEXR and stripped TIFF.
             const std::string extension = toLower(std::filesystem::path(path).extension().string());
             const bool inMemory = memory.isValid();
             try
@@ -162,6 +163,10 @@ namespace toucan
                 if (".exr" == extension)
                 {
                     return inMemory ? readExrMemory(memory.data, memory.size, out) : readExr(path, out);
+                }
+                if (".tif" == extension || ".tiff" == extension)
+                {
+                    return inMemory ? readTiffMemory(memory.data, memory.size, out) : readTiff(path, out);
                 }
             }
             catch (const std::exception&)

@@ -7,6 +7,7 @@
 #include "ExrRead.h"
 #include "JpegRead.h"
 #include "PngRead.h"
+#include "TiffRead.h"
 #include "StackFusion.h"
 #include "TimelineWrapper.h"
 #include "Util.h"
@@ -394,6 +395,25 @@ extern "C"
             if (out)
             {
                 if (bytes > capacity) return fail("tr_decode_jpeg: output buffer too small");
+                memcpy(out, frame.host, bytes);
+            }
+            return 0;
+        });
+    }
+
+    int tr_decode_tiff(const char* path, void* out, size_t capacity, int* width, int* height, int* type)
+    {
+        if (!path) return fail("tr_decode_tiff: null");
+        return guarded([&] {
+            MediaFrame frame;
+            if (!readTiff(path, frame)) return fail(std::string("tr_decode_tiff: cannot read ") + path);
+            if (width) *width = frame.width;
+            if (height) *height = frame.height;
+            if (type) *type = frame.format;
+            const size_t bytes = tc_image_bytes(frame.width, frame.height, frame.format);
+            if (out)
+            {
+                if (bytes > capacity) return fail("tr_decode_tiff: output buffer too small");
                 memcpy(out, frame.host, bytes);
             }
             return 0;

@@ -42,6 +42,7 @@ _SIGS = {
     "tr_decode_png": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_decode_jpeg": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_decode_exr": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
+    "tr_decode_tiff": [ctypes.c_char_p, _VP, ctypes.c_size_t, _IP, _IP, _IP],
     "tr_write_exr": [ctypes.c_char_p, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int],
     "tr_timeline_render_resident": [_VP, _VP, ctypes.c_double, ctypes.POINTER(_VP), _IP, _IP, _IP],
 }
@@ -140,6 +141,15 @@ def decode_exr(path: str) -> np.ndarray:
     _check(lib().tr_decode_exr(path.encode(), None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_exr")
     out = np.empty((h.value, w.value, 4), _NP_OF[t.value])
     _check(lib().tr_decode_exr(path.encode(), out.ctypes.data, out.nbytes, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_exr")
+    return out
+
+
+def decode_tiff(path: str) -> np.ndarray:
+    """The C++ host's built-in TIFF reader (RGBA u8 / u16 / float32)."""
+    w, h, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _check(lib().tr_decode_tiff(path.encode(), None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_tiff")
+    out = np.empty((h.value, w.value, 4), _NP_OF[t.value])
+    _check(lib().tr_decode_tiff(path.encode(), out.ctypes.data, out.nbytes, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_tiff")
     return out
 
 
