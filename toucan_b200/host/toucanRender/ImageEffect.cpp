@@ -57,27 +57,32 @@ namespace toucan
         // (it matches bool / int64_t / double / string / AnyVector) -- so Integer,
         // Integer2D and Boolean defaults silently fall back to the plug-in's local
         // initialisers.  Kept on purpose: it defines the effective parameter defaults.
-        for (const auto& def : _plugin.paramDefs)
+        if (!_plugin.defaultsHarvested)
         {
-            if (hasProperty(def.second.getStringProperties(), kOfxParamPropDefault))
+            for (const auto& def : _plugin.paramDefs)
             {
-                char* s = nullptr;
-                def.second.getString(kOfxParamPropDefault, 0, &s);
-                if (s) _instance->params[def.first] = std::string(s);
+                if (hasProperty(def.second.getStringProperties(), kOfxParamPropDefault))
+                {
+                    char* s = nullptr;
+                    def.second.getString(kOfxParamPropDefault, 0, &s);
+                    if (s) _plugin.harvestedDefaults[def.first] = std::string(s);
+                }
+                if (hasProperty(def.second.getDoubleProperties(), kOfxParamPropDefault))
+                {
+                    double d = 0.0;
+                    def.second.getDouble(kOfxParamPropDefault, 0, &d);
+                    _plugin.harvestedDefaults[def.first] = d;
+                }
+                if (hasProperty(def.second.getIntProperties(), kOfxParamPropDefault))
+                {
+                    int i = 0;
+                    def.second.getInt(kOfxParamPropDefault, 0, &i);
+                    _plugin.harvestedDefaults[def.first] = i;
+                }
             }
-            if (hasProperty(def.second.getDoubleProperties(), kOfxParamPropDefault))
-            {
-                double d = 0.0;
-                def.second.getDouble(kOfxParamPropDefault, 0, &d);
-                _instance->params[def.first] = d;
-            }
-            if (hasProperty(def.second.getIntProperties(), kOfxParamPropDefault))
-            {
-                int i = 0;
-                def.second.getInt(kOfxParamPropDefault, 0, &i);
-                _instance->params[def.first] = i;
-            }
+            _plugin.defaultsHarvested = true;
         }
+        _instance->params = _plugin.harvestedDefaults;
         for (const auto& kv : metaData)
         {
             _instance->params[kv.first] = kv.second;

@@ -22,6 +22,10 @@ namespace toucan
         std::map<std::string, PropertySet> clipPropSets;
         std::map<std::string, std::string> paramTypes;
         std::map<std::string, PropertySet> paramDefs;
+        //! The described defaults as the node constructor harvests them (computed once, on first use; a host and its
+        //! plug-in records belong to one thread).
+        std::map<std::string, std::any> harvestedDefaults;
+        bool defaultsHarvested = false;
     };
 
     //! Image effect instance.
