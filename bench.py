@@ -374,7 +374,7 @@ def run_ours(args, cfg):
         line = {"metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_json(cfg, world),
-                "api": "toucan::ImageGraph::exec + IImageNode::exec through libtoucan_render.so (OpenFX host + 5 .ofx modules)",
+                "api": "toucan::ImageGraph::exec + IImageNode::exec through libtoucan_render.so (OpenFX host + 6 .ofx modules)",
                 "hbm_gbs_algorithmic": achieved * world,
                 "roofline": {"bound": "hbm", "kernel": "k_stack_f32", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
