@@ -105,7 +105,7 @@ int tr_decode_png(const char* path, void* out, size_t capacity, int* width, int*
    libjpeg's defaults -- islow IDCT, fancy upsampling, integer colour tables -- bit for bit, RGBA out with
    A = 255 (Read.cpp:86-94).  Same calling convention as tr_decode_png. */
 int tr_decode_jpeg(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
-/* The built-in OpenEXR reader (scanline, single-part, R/G/B[/A] HALF or FLOAT, compression NONE / RLE / ZIPS / ZIP):
+/* The built-in OpenEXR reader (scanline, single-part, R/G/B[/A] HALF or FLOAT, compression NONE / RLE / ZIPS / ZIP / PIZ):
    RGBA out in the widest channel type (*type = TC_F16 or TC_F32), A = 1 when the file has no alpha.  Same calling
    convention as tr_decode_png. */
 int tr_decode_exr(const char* path, void* out, size_t capacity, int* width, int* height, int* type);

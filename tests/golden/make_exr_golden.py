@@ -3,7 +3,7 @@
 Run in the authoring container:
     python tests/golden/make_exr_golden.py
 
-Writes tests/golden/exr/*.exr (seeded 37x21 frames: half / float samples, RGB / RGBA, compression NONE / RLE / ZIPS / ZIP)
+Writes tests/golden/exr/*.exr (seeded 37x37 frames: half / float samples, RGB / RGBA, compression NONE / RLE / ZIPS / ZIP / PIZ)
 and tests/golden/exr/expected.npz with the pixels OpenCV's OpenEXR reader returns for each file (RGBA order, float32).
 """
 import os
@@ -17,13 +17,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "exr")
 TYPES = {"half": cv2.IMWRITE_EXR_TYPE_HALF, "float": cv2.IMWRITE_EXR_TYPE_FLOAT}
 COMPRESSIONS = {"none": cv2.IMWRITE_EXR_COMPRESSION_NO, "rle": cv2.IMWRITE_EXR_COMPRESSION_RLE, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
-                "zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP}
+                "zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "piz": cv2.IMWRITE_EXR_COMPRESSION_PIZ}
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     rng = np.random.default_rng(77)
-    w, h = 37, 21  # more than one 16-line ZIP chunk, odd sizes
+    w, h = 37, 37  # more than one 16-line ZIP chunk and more than one 32-line PIZ chunk, odd sizes
     expected = {}
     for tname, t in TYPES.items():
         for cname, c in COMPRESSIONS.items():
@@ -36,10 +36,10 @@ def main():
                 b = cv2.imread(os.path.join(OUT, name), cv2.IMREAD_UNCHANGED)
                 rgba = b[..., [2, 1, 0, 3]] if nch == 4 else np.concatenate([b[..., ::-1], np.ones((h, w, 1), np.float32)], -1)
                 expected[name] = np.ascontiguousarray(rgba.astype(np.float32))
-    # a PIZ file: a compression the reader must refuse
+    # a lossy DWAA file: a compression the reader must refuse
     a = rng.random((h, w, 3), dtype=np.float32)
-    assert cv2.imwrite(os.path.join(OUT, "half_piz_rgb.exr"), a, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION,
-                                                                   cv2.IMWRITE_EXR_COMPRESSION_PIZ])
+    assert cv2.imwrite(os.path.join(OUT, "refused_dwaa_rgb.exr"), a, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION,
+                                                                      cv2.IMWRITE_EXR_COMPRESSION_DWAA])
     np.savez_compressed(os.path.join(OUT, "expected.npz"), **expected)
     print(len(expected), "files,", sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)), "bytes")
 

@@ -110,6 +110,311 @@ namespace toucan
             if (out.size() != expected) bad("bad RLE data");
         }
 
+
+        // ---- PIZ: range table + Huffman + 2-D wavelet (OpenEXR ImfPizCompressor / ImfHuf / ImfWav) ----
+        constexpr int HUF_ENCBITS = 16, HUF_DECBITS = 14;
+        constexpr int HUF_ENCSIZE = (1 << HUF_ENCBITS) + 1, HUF_DECSIZE = 1 << HUF_DECBITS, HUF_DECMASK = HUF_DECSIZE - 1;
+        constexpr int SHORT_ZEROCODE_RUN = 59, LONG_ZEROCODE_RUN = 63, SHORTEST_LONG_RUN = 2 + LONG_ZEROCODE_RUN - SHORT_ZEROCODE_RUN;
+
+        struct HufDec
+        {
+            int len = 0;              // short code: its length
+            int lit = 0;              // short code: the symbol; long codes: how many share this prefix
+            std::vector<int> longs;   // symbols whose codes are longer than HUF_DECBITS and start with this prefix
+        };
+
+        struct BitIn
+        {
+            const unsigned char* p;
+            const unsigned char* end;
+            uint64_t c = 0;
+            int lc = 0;
+            void byte()
+            {
+                if (p >= end) bad("truncated PIZ data");
+                c = (c << 8) | *p++;
+                lc += 8;
+            }
+            uint64_t bits(int n)
+            {
+                while (lc < n) byte();
+                lc -= n;
+                return (c >> lc) & ((uint64_t(1) << n) - 1);
+            }
+        };
+
+        void hufUncompress(const unsigned char* in, size_t inSize, uint16_t* out, size_t count)
+        {
+            if (0 == inSize)
+            {
+                if (count) bad("bad PIZ data");
+                return;
+            }
+            if (inSize < 20) bad("truncated PIZ data");
+            auto u32 = [in](size_t at) { return uint32_t(in[at]) | uint32_t(in[at + 1]) << 8 | uint32_t(in[at + 2]) << 16 | uint32_t(in[at + 3]) << 24; };
+            const uint32_t im = u32(0), iM = u32(4), nBits = u32(12);
+            if (im >= uint32_t(HUF_ENCSIZE) || iM >= uint32_t(HUF_ENCSIZE)) bad("bad PIZ Huffman table");
+            // code lengths, run-length packed in 6-bit fields
+            std::vector<uint64_t> code(HUF_ENCSIZE, 0);
+            BitIn table{ in + 20, in + inSize };
+            for (uint32_t i = im; i <= iM; ++i)
+            {
+                const uint64_t l = code[i] = table.bits(6);
+                if (LONG_ZEROCODE_RUN == l || l >= uint64_t(SHORT_ZEROCODE_RUN))
+                {
+                    uint64_t run = LONG_ZEROCODE_RUN == l ? table.bits(8) + SHORTEST_LONG_RUN : l - SHORT_ZEROCODE_RUN + 2;
+                    if (i + run > uint64_t(iM) + 1) bad("bad PIZ Huffman table");
+                    while (run--) code[i++] = 0;
+                    --i;
+                }
+            }
+            const unsigned char* data = table.p;
+            if (nBits > 8 * uint64_t(in + inSize - data)) bad("bad PIZ data");
+            // canonical codes from the lengths: code[i] = length | code << 6
+            {
+                uint64_t n[59] = {};
+                for (int i = 0; i < HUF_ENCSIZE; ++i) n[code[size_t(i)]] += 1;
+                uint64_t c = 0;
+                for (int i = 58; i > 0; --i)
+                {
+                    const uint64_t nc = (c + n[i]) >> 1;
+                    n[i] = c;
+                    c = nc;
+                }
+                for (int i = 0; i < HUF_ENCSIZE; ++i)
+                {
+                    const uint64_t l = code[size_t(i)];
+                    if (l > 0) code[size_t(i)] = l | (n[l]++ << 6);
+                }
+            }
+            // decoding table: HUF_DECBITS-bit prefixes
+            std::vector<HufDec> dec(HUF_DECSIZE);
+            for (uint32_t i = im; i <= iM; ++i)
+            {
+                const uint64_t c = code[i] >> 6;
+                const int l = int(code[i] & 63);
+                if (c >> l) bad("bad PIZ Huffman table");
+                if (l > HUF_DECBITS)
+                {
+                    HufDec& d = dec[size_t(c >> (l - HUF_DECBITS))];
+                    if (d.len) bad("bad PIZ Huffman table");
+                    d.lit++;
+                    d.longs.push_back(int(i));
+                }
+                else if (l)
+                {
+                    HufDec* d = &dec[size_t(c << (HUF_DECBITS - l))];
+                    for (uint64_t k = uint64_t(1) << (HUF_DECBITS - l); k > 0; --k, ++d)
+                    {
+                        if (d->len || !d->longs.empty()) bad("bad PIZ Huffman table");
+                        d->len = l;
+                        d->lit = int(i);
+                    }
+                }
+            }
+            // decode; symbol iM is the run-length escape (repeat the previous output `next byte` times)
+            const unsigned char* p = data;
+            const unsigned char* pe = data + (nBits + 7) / 8;
+            uint64_t c = 0;
+            int lc = 0;
+            size_t o = 0;
+            auto emit = [&](int symbol)
+            {
+                if (uint32_t(symbol) == iM)
+                {
+                    if (lc < 8)
+                    {
+                        if (p >= in + inSize) bad("truncated PIZ data");
+                        c = (c << 8) | *p++;
+                        lc += 8;
+                    }
+                    lc -= 8;
+                    size_t run = size_t((c >> lc) & 0xff);
+                    if (o + run > count || 0 == o) bad("bad PIZ run");
+                    const uint16_t v = out[o - 1];
+                    while (run--) out[o++] = v;
+                }
+                else
+                {
+                    if (o >= count) bad("bad PIZ data");
+                    out[o++] = uint16_t(symbol);
+                }
+            };
+            while (p < pe)
+            {
+                c = (c << 8) | *p++;
+                lc += 8;
+                while (lc >= HUF_DECBITS)
+                {
+                    const HufDec& d = dec[size_t((c >> (lc - HUF_DECBITS)) & HUF_DECMASK)];
+                    if (d.len)
+                    {
+                        lc -= d.len;
+                        emit(d.lit);
+                    }
+                    else
+                    {
+                        if (d.longs.empty()) bad("bad PIZ code");
+                        size_t j = 0;
+                        for (; j < d.longs.size(); ++j)
+                        {
+                            const int l = int(code[size_t(d.longs[j])] & 63);
+                            while (lc < l && p < pe)
+                            {
+                                c = (c << 8) | *p++;
+                                lc += 8;
+                            }
+                            if (lc >= l && (code[size_t(d.longs[j])] >> 6) == ((c >> (lc - l)) & ((uint64_t(1) << l) - 1)))
+                            {
+                                lc -= l;
+                                emit(d.longs[j]);
+                                break;
+                            }
+                        }
+                        if (j == d.longs.size()) bad("bad PIZ code");
+                    }
+                }
+            }
+            const int pad = int((8 - nBits) & 7);
+            c >>= pad;
+            lc -= pad;
+            while (lc > 0)
+            {
+                const HufDec& d = dec[size_t((c << (HUF_DECBITS - lc)) & HUF_DECMASK)];
+                if (!d.len) bad("bad PIZ code");
+                lc -= d.len;
+                emit(d.lit);
+            }
+            if (o != count) bad("bad PIZ data");
+        }
+
+        inline void wdec14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b)
+        {
+            const int ls = int16_t(l), hi = int16_t(h);
+            const int ai = ls + (hi & 1) + (hi >> 1);
+            a = uint16_t(int16_t(ai));
+            b = uint16_t(int16_t(ai - hi));
+        }
+
+        inline void wdec16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b)
+        {
+            const int m = l, d = h;
+            const int bb = (m - (d >> 1)) & 0xffff;
+            a = uint16_t((d + bb - 0x8000) & 0xffff);
+            b = uint16_t(bb);
+        }
+
+        void wav2Decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx)
+        {
+            const bool w14 = mx < (1 << 14);
+            const int n = nx > ny ? ny : nx;
+            int p = 1;
+            while (p <= n) p <<= 1;
+            p >>= 1;
+            int p2 = p;
+            p >>= 1;
+            auto dec = [w14](uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) { if (w14) wdec14(l, h, a, b); else wdec16(l, h, a, b); };
+            while (p >= 1)
+            {
+                uint16_t* py = in;
+                uint16_t* const ey = in + ptrdiff_t(oy) * (ny - p2);
+                const ptrdiff_t oy1 = ptrdiff_t(oy) * p, oy2 = ptrdiff_t(oy) * p2, ox1 = ptrdiff_t(ox) * p, ox2 = ptrdiff_t(ox) * p2;
+                uint16_t i00, i01, i10, i11;
+                for (; py <= ey; py += oy2)
+                {
+                    uint16_t* px = py;
+                    uint16_t* const ex = py + ptrdiff_t(ox) * (nx - p2);
+                    for (; px <= ex; px += ox2)
+                    {
+                        uint16_t* p01 = px + ox1;
+                        uint16_t* p10 = px + oy1;
+                        uint16_t* p11 = p10 + ox1;
+                        dec(*px, *p10, i00, i10);
+                        dec(*p01, *p11, i01, i11);
+                        dec(i00, i01, *px, *p01);
+                        dec(i10, i11, *p10, *p11);
+                    }
+                    if (nx & p)
+                    {
+                        uint16_t* p10 = px + oy1;
+                        dec(*px, *p10, i00, *p10);
+                        *px = i00;
+                    }
+                }
+                if (ny & p)
+                {
+                    uint16_t* px = py;
+                    uint16_t* const ex = py + ptrdiff_t(ox) * (nx - p2);
+                    for (; px <= ex; px += ox2)
+                    {
+                        uint16_t* p01 = px + ox1;
+                        dec(*px, *p01, i00, *p01);
+                        *px = i00;
+                    }
+                }
+                p2 = p;
+                p >>= 1;
+            }
+        }
+
+        // One PIZ chunk -> the uncompressed scanline layout (per line: each channel's samples, little-endian)
+        void unpiz(const unsigned char* in, size_t inSize, const std::vector<Channel>& channels, int width, int lines, std::vector<unsigned char>& out)
+        {
+            size_t total = 0; // in 16-bit units
+            for (const Channel& c : channels) total += size_t(width) * lines * (1 == c.type ? 1 : 2);
+            std::vector<uint16_t> tmp(total);
+            if (inSize < 4) bad("truncated PIZ data");
+            const int minNonZero = in[0] | in[1] << 8, maxNonZero = in[2] | in[3] << 8;
+            size_t at = 4;
+            std::vector<unsigned char> bitmap(8192, 0);
+            if (maxNonZero >= 8192) bad("bad PIZ bitmap");
+            if (minNonZero <= maxNonZero)
+            {
+                const size_t n = size_t(maxNonZero - minNonZero + 1);
+                if (at + n > inSize) bad("truncated PIZ data");
+                memcpy(&bitmap[size_t(minNonZero)], in + at, n);
+                at += n;
+            }
+            std::vector<uint16_t> lut(65536, 0);
+            int k = 0;
+            for (int i = 0; i < 65536; ++i)
+            {
+                if (0 == i || (bitmap[size_t(i >> 3)] & (1 << (i & 7)))) lut[size_t(k++)] = uint16_t(i);
+            }
+            const uint16_t maxValue = uint16_t(k - 1);
+            if (at + 4 > inSize) bad("truncated PIZ data");
+            const uint32_t length = uint32_t(in[at]) | uint32_t(in[at + 1]) << 8 | uint32_t(in[at + 2]) << 16 | uint32_t(in[at + 3]) << 24;
+            at += 4;
+            if (at + length > inSize) bad("truncated PIZ data");
+            hufUncompress(in + at, length, tmp.data(), total);
+            // wavelet: every channel is a (lines x width) plane of `size` interleaved 16-bit words
+            std::vector<size_t> start(channels.size());
+            size_t offset = 0;
+            for (size_t c = 0; c < channels.size(); ++c)
+            {
+                const int size = 1 == channels[c].type ? 1 : 2;
+                start[c] = offset;
+                for (int j = 0; j < size; ++j) wav2Decode(tmp.data() + offset + j, width, size, lines, width * size, maxValue);
+                offset += size_t(width) * lines * size;
+            }
+            for (uint16_t& v : tmp) v = lut[v];
+            out.resize(total * 2);
+            unsigned char* o = out.data();
+            for (int y = 0; y < lines; ++y)
+            {
+                for (size_t c = 0; c < channels.size(); ++c)
+                {
+                    const size_t n = size_t(width) * (1 == channels[c].type ? 1 : 2);
+                    const uint16_t* src = tmp.data() + start[c] + size_t(y) * n;
+                    for (size_t i = 0; i < n; ++i)
+                    {
+                        *o++ = static_cast<unsigned char>(src[i]);
+                        *o++ = static_cast<unsigned char>(src[i] >> 8);
+                    }
+                }
+            }
+        }
+
         float halfToFloat(uint16_t h)
         {
             const uint32_t sign = static_cast<uint32_t>(h & 0x8000u) << 16;
@@ -205,7 +510,8 @@ namespace toucan
         {
         case 0: case 1: case 2: linesPerChunk = 1; break; // none, RLE, ZIPS
         case 3: linesPerChunk = 16; break;                 // ZIP
-        default: bad("only uncompressed, RLE, ZIPS and ZIP files are supported (PIZ, PXR24, B44, DWA are not)");
+        case 4: linesPerChunk = 32; break;                 // PIZ
+        default: bad("only uncompressed, RLE, ZIPS, ZIP and PIZ files are supported (PXR24, B44, DWA are not)");
         }
 
         // scanline layout: channels in file (alphabetical) order, each `width` samples
@@ -310,7 +616,13 @@ namespace toucan
                     const unsigned char* src = data + c.pos;
                     if (packed < expected)
                     {
-                        if (1 == compression)
+                        if (4 == compression)
+                        {
+                            unpiz(src, packed, channels, width, lines, raw);
+                            if (raw.size() != expected) bad("bad PIZ chunk");
+                            src = raw.data();
+                        }
+                        else if (1 == compression)
                         {
                             unrle(src, packed, tmp, expected);
                         }
@@ -324,8 +636,11 @@ namespace toucan
                         {
                             bad("bad chunk size");
                         }
-                        unpredict(tmp, raw);
-                        src = raw.data();
+                        if (compression != 4)
+                        {
+                            unpredict(tmp, raw);
+                            src = raw.data();
+                        }
                     }
                     else if (packed != expected)
                     {
