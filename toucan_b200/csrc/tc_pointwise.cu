@@ -7,6 +7,7 @@
 // Kernel shape: grid-stride over pixels, one RGBA pixel per thread-iteration (128-bit
 // load/store for float, 64-bit for half/u16, 32-bit for u8), 4 independent pixels in
 // flight per thread, grid sized as a multiple of the SM count.
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
