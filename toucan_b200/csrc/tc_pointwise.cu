@@ -188,7 +188,13 @@ struct CheckerOp {
     TC_OP_0()
     float4 c1, c2;
     int cw, ch;
-    __device__ float4 operator()(int x, int y, unsigned) const { return ((x / cw + y / ch) & 1) ? c2 : c1; }
+    unsigned mx, my; // floor(2^32 / c) + 1: x / c == umulhi(x, m) exactly while x * c < 2^32 (0 = divide)
+    __device__ float4 operator()(int x, int y, unsigned) const
+    {
+        const unsigned tx = mx ? __umulhi((unsigned)x, mx) : (unsigned)(x / cw);
+        const unsigned ty = my ? __umulhi((unsigned)y, my) : (unsigned)(y / ch);
+        return ((tx + ty) & 1) ? c2 : c1;
+    }
 };
 struct GradientOp {
     TC_OP_0()
@@ -736,7 +742,12 @@ int tc_checkers(const tc_image* dst, int cw, int ch, const float c1[4], const fl
     TC_VALIDATE(dst, "tc_checkers dst");
     if (!c1 || !c2) return fail(TC_ERR_INVALID, "tc_checkers: null color");
     if (cw <= 0 || ch <= 0) return fail(TC_ERR_INVALID, "tc_checkers: checker size %dx%d (the reference divides by zero here)", cw, ch);
-    return launch(CheckerOp { f4(c1), f4(c2), cw, ch }, dst, s);
+    // exact division by multiplication: valid when (extent - 1) * checker < 2^32 and the checker is at least 2
+    auto magic = [](int c, int extent) -> unsigned {
+        if (c < 2 || (unsigned long long)(extent > 0 ? extent - 1 : 0) * (unsigned long long)c >= (1ull << 32)) return 0u;
+        return (unsigned)((1ull << 32) / (unsigned)c) + 1u;
+    };
+    return launch(CheckerOp { f4(c1), f4(c2), cw, ch, magic(cw, dst->w), magic(ch, dst->h) }, dst, s);
 }
 
 int tc_gradient(const tc_image* dst, const float c1[4], const float c2[4], int vertical, tc_stream s)
