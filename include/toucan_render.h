@@ -120,6 +120,10 @@ int tr_write_exr(const char* path, const void* pixels, int width, int height, in
 /* Cross-node fusion of the track stack (default on). */
 void tr_set_fusion(int enabled);
 
+/* Frame -> worker assignment of tr_render_range*: round-robin (default; all GPUs busy behind the one ordered writer) or
+   contiguous blocks (tr_frame_block: consecutive frames per worker). */
+void tr_set_interleave(int enabled);
+
 #ifdef __cplusplus
 }
 #endif

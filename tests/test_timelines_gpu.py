@@ -188,11 +188,14 @@ def test_toucan_render_cli(cuda, tmp_path):
     assert open(out3, "rb").read() == open(out, "rb").read()
 
 
+@pytest.mark.parametrize("interleave", [True, False])
 @pytest.mark.parametrize("devices", [[0], [0, 0, 0]])
-def test_frame_scheduler_ordered_output(cuda, devices):
-    """toucan::FrameScheduler: contiguous frame blocks per worker, frames handed to the writer in
-    timeline order, equal to the golden frames (three workers share GPU 0 here; on a multi-GPU box the
+def test_frame_scheduler_ordered_output(cuda, devices, interleave):
+    """toucan::FrameScheduler: frames dealt to the workers round-robin or in contiguous blocks, handed to the writer
+    in timeline order either way, equal to the golden frames (three workers share GPU 0 here; on a multi-GPU box the
     same code takes one device per worker)."""
+    from toucan_b200 import render
+
     name = "Transition2.otio"
     tl = TL.open_timeline(name)
     got = []
@@ -201,7 +204,11 @@ def test_frame_scheduler_ordered_output(cuda, devices):
         got.append((frame, hashlib.sha256(pixels.tobytes()).hexdigest(), pixels.shape))
 
     frames = GOLD[name]["frames"]
-    tl.render_range(0, len(frames), writer, devices=devices, frames_in_flight=2)
+    render.set_interleave(interleave)
+    try:
+        tl.render_range(0, len(frames), writer, devices=devices, frames_in_flight=2)
+    finally:
+        render.set_interleave(True)
     assert [g[0] for g in got] == list(range(len(frames)))
     assert [g[1] for g in got] == [r["sha256"] for r in frames]
     tl.close()

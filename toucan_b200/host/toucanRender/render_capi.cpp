@@ -14,6 +14,7 @@
 
 #include <dlfcn.h>
 
+#include <atomic>
 #include <cstring>
 #include <sstream>
 
@@ -37,6 +38,7 @@ struct tr_timeline
 
 namespace
 {
+    std::atomic<bool> interleaveFrames{ true };
     thread_local std::string lastError;
 
     int fail(const std::string& what)
@@ -312,6 +314,7 @@ extern "C"
             if (plugin_dir && *plugin_dir) options.pluginSearchPath.push_back(plugin_dir);
             else options.pluginSearchPath = getOpenFXPluginPaths(libraryDirectory() / "toucan-render");
             if (frames_in_flight > 0) options.framesInFlight = frames_in_flight;
+            options.interleave = interleaveFrames;
             FrameScheduler scheduler(timeline->context, timeline->wrapper, options);
             scheduler.run(first, last, [&](int frame, const void* pixels, const ImageSpec& spec, size_t) {
                 callback(user, frame, pixels, spec.width, spec.height, spec.format | (spec.nchannels == 3 ? 0x100 : 0));
@@ -336,6 +339,7 @@ extern "C"
             if (plugin_dir && *plugin_dir) options.pluginSearchPath.push_back(plugin_dir);
             else options.pluginSearchPath = getOpenFXPluginPaths(libraryDirectory() / "toucan-render");
             if (frames_in_flight > 0) options.framesInFlight = frames_in_flight;
+            options.interleave = interleaveFrames;
             const int format = options.y4mFormat;
             FrameScheduler scheduler(timeline->context, timeline->wrapper, options);
             scheduler.run(first, last, [&](int frame, const void* pixels, const ImageSpec& spec, size_t) {
@@ -449,4 +453,6 @@ extern "C"
     }
 
     void tr_set_fusion(int enabled) { setStackFusionEnabled(enabled != 0); }
+
+    void tr_set_interleave(int enabled) { interleaveFrames = enabled != 0; }
 }

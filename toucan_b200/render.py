@@ -52,7 +52,7 @@ _SIGS["tr_render_range_raw"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.
                                 FRAME_CALLBACK, _VP]
 _SIGS["tr_render_range_y4m"] = _SIGS["tr_render_range_raw"]
 _SIGS["tr_y4m_header"] = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
-EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion"})
+EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion", "tr_set_interleave"})
 
 
 def lib() -> ctypes.CDLL:
@@ -75,6 +75,8 @@ def lib() -> ctypes.CDLL:
         _lib.tr_host_plugin_identifier.restype = ctypes.c_char_p
         _lib.tr_set_fusion.argtypes = [ctypes.c_int]
         _lib.tr_set_fusion.restype = None
+        _lib.tr_set_interleave.argtypes = [ctypes.c_int]
+        _lib.tr_set_interleave.restype = None
     return _lib
 
 
@@ -98,6 +100,11 @@ def sync():
 
 def set_fusion(enabled: bool):
     lib().tr_set_fusion(1 if enabled else 0)
+
+
+def set_interleave(enabled: bool):
+    """Round-robin (default) or contiguous-block assignment of frames to the scheduler's workers."""
+    lib().tr_set_interleave(1 if enabled else 0)
 
 
 def y4m_header(width: int, height: int, rate: float, y4m_format: str) -> bytes:
