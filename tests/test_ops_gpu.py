@@ -202,8 +202,9 @@ def test_rotate(T, dt, angle):
 
 @pytest.mark.parametrize("dta", NP_TYPES)
 @pytest.mark.parametrize("dtb", NP_TYPES)
-def test_transitions_and_over(T, dta, dtb):
-    w, h = 333, 217
+@pytest.mark.parametrize("size", [(333, 217), (64, 48)])  # odd pixel count: scalar path; multiple of 4: the 128-bit groups, mixed types included
+def test_transitions_and_over(T, dta, dtb, size):
+    w, h = size
     a, b = rand_img(w, h, dta, 6), rand_img(w, h, dtb, 7)
     da, db = to_dev(a), to_dev(b)
     exact_ok = True

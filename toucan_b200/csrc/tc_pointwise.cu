@@ -108,7 +108,7 @@ static int launch(const Op& op, const tc_image* dst, tc_stream s)
 {
     const size_t total = (size_t)dst->w * dst->h;
     if (total >= (1ull << 31)) return fail(TC_ERR_UNSUPPORTED, "image too large (%d x %d)", dst->w, dst->h);
-    // 128-bit groups need every same-sized source in the destination's storage type
+    // 128-bit groups of the destination's pixels; sources of any storage type (Src::preload)
     const int vec = dst->type == TC_F32 ? 1 : (dst->type == TC_U8 ? 4 : 2);
     if (vec > 1 && total % vec == 0 && op.vec_ok(dst->type)) {
         if (vec == 4) return launch_vec<Op, 4>(op, dst, s);
@@ -117,27 +117,45 @@ static int launch(const Op& op, const tc_image* dst, tc_stream s)
     return launch_vec<Op, 1>(op, dst, s);
 }
 
-// A source image read at the destination's pixel position (0 outside).
+// A source image read at the destination's pixel position (0 outside).  In the vectorised kernels a thread owns a
+// group of VEC consecutive pixels (VEC comes from the DESTINATION's storage type); a same-sized source supplies those
+// pixels as one 32/64/128-bit word when VEC of ITS pixels fit in 16 bytes -- whatever its own type, so a half frame
+// over a u8 frame is vectorised too -- and as per-pixel loads (each at least 64 bits wide) otherwise.
+__host__ __device__ __forceinline__ int px_bytes(int type) { return type == TC_U8 ? 4 : (type == TC_F32 ? 16 : 8); }
+
 struct Src {
     Img im;
     int same; // same dimensions as the destination -> linear index can be reused
-    bool vec_ok(int t) const { return !same || im.type == t; }
+    bool vec_ok(int) const { return true; }
     template <int VEC>
     __device__ __forceinline__ void preload(uint4& c, unsigned idx0) const
     {
-        if (VEC > 1 && same) c = __ldg(reinterpret_cast<const uint4*>(im.p) + idx0 / VEC);
+        if (VEC > 1 && same) {
+            const int bytes = VEC * px_bytes(im.type);
+            const char* p = reinterpret_cast<const char*>(im.p) + (size_t)idx0 * px_bytes(im.type);
+            if (bytes == 16) {
+                c = __ldg(reinterpret_cast<const uint4*>(p));
+            } else if (bytes == 8) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+                c.x = v.x;
+                c.y = v.y;
+            } else if (bytes == 4) {
+                c.x = __ldg(reinterpret_cast<const unsigned*>(p));
+            }
+        }
     }
     template <int VEC>
     __device__ __forceinline__ float4 at(const uint4& c, int x, int y, unsigned idx, int j) const
     {
         if (VEC == 1) return same ? load_px(im.p, im.type, idx) : load_black(im, x, y);
         if (!same) return load_black(im, x, y);
+        if (VEC * px_bytes(im.type) > 16) return load_px(im.p, im.type, idx);
         const unsigned* w = &c.x;
-        if (VEC == 4) {
+        if (im.type == TC_U8) {
             const unsigned v = w[j];
             return make_float4(u8_to_f(v & 0xffu), u8_to_f((v >> 8) & 0xffu), u8_to_f((v >> 16) & 0xffu), u8_to_f(v >> 24));
         }
-        const unsigned lo = w[2 * j], hi = w[2 * j + 1];
+        const unsigned lo = w[(2 * j) & 3], hi = w[(2 * j + 1) & 3]; // two 16-bit pixels per word pair (VEC <= 2 here)
         if (im.type == TC_U16) return make_float4(u16_to_f(lo & 0xffffu), u16_to_f(lo >> 16), u16_to_f(hi & 0xffffu), u16_to_f(hi >> 16));
         const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&lo)), fb = __half22float2(*reinterpret_cast<const __half2*>(&hi));
         return make_float4(fa.x, fa.y, fb.x, fb.y);
