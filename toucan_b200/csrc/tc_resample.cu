@@ -277,6 +277,72 @@ __global__ void __launch_bounds__(RT_THREADS) k_resize_tile(const Img src_, cons
     }
 }
 
+// Row pass of the two-pass path through the same kind of shared tile, for footprints the fused kernel cannot hold (more
+// than 16 taps per axis: reductions below ~0.4).  A CTA owns 32 source rows x `xw` destination columns; the rows' common
+// source span is staged once (coalesced), then lane = row, warp = destination column, weights warp-uniform -- instead of
+// every thread gathering its `taps` source pixels with a stride of 1/ratio pixels through L1.
+constexpr int RR_ROWS = 32, RR_THREADS = 256;
+
+struct RowsTile { int cols; int xw; int xtaps; }; // staged columns (allocation), destination columns per CTA
+
+template <int TYPE>
+__global__ void __launch_bounds__(RR_THREADS) k_resize_rows_tile(const Img src_, float4* __restrict__ tmp, int dw, const int* __restrict__ xf,
+                                                                  const float* __restrict__ xw, const float* __restrict__ xt, const RowsTile T)
+{
+    extern __shared__ float4 rr_smem[];
+    const Img src { src_.p, src_.w, src_.h, TYPE };
+    const int pitch = T.cols | 1;
+    float4* S = rr_smem;                                              // [RR_ROWS][pitch]
+    float* ws = reinterpret_cast<float*>(S + (size_t)RR_ROWS * pitch); // [xw][xtaps]
+    int* fs = reinterpret_cast<int*>(ws + T.xw * T.xtaps);            // [xw]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int WARPS = RR_THREADS / 32;
+    const int x0 = blockIdx.x * T.xw, y0 = blockIdx.y * RR_ROWS;
+    const int nx = min(T.xw, dw - x0), ny = min(RR_ROWS, src.h - y0);
+    const int fx0 = xf[x0];
+    const int cols = min(xf[x0 + nx - 1] + T.xtaps - fx0, T.cols);
+    for (int i = tid; i < nx * T.xtaps; i += RR_THREADS) {
+        const int x = i / T.xtaps, t = i - x * T.xtaps;
+        ws[i] = xt[(x0 + x) * 2 + 1] != 0.0f ? xw[(size_t)(x0 + x) * T.xtaps + t] : 0.0f;
+    }
+    if (tid < nx) fs[tid] = min(xf[x0 + tid] - fx0, T.cols - T.xtaps);
+    // stage: a warp per source row, eight loads in flight per thread
+    for (int r = warp; r < ny; r += 2 * WARPS) {
+        const int rb = min(r + WARPS, ny - 1);
+        const size_t ra = (size_t)(y0 + r) * src.w, rbase = (size_t)(y0 + rb) * src.w;
+        for (int c0 = 0; c0 < cols; c0 += 128) {
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int sx = min(max(fx0 + min(c0 + k * 32 + lane, cols - 1), 0), src.w - 1);
+                va[k] = load_px(src.p, TYPE, ra + sx);
+                vb[k] = load_px(src.p, TYPE, rbase + sx);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k * 32 + lane;
+                if (c < cols) {
+                    S[(size_t)r * pitch + c] = va[k];
+                    S[(size_t)rb * pitch + c] = vb[k];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const float4* row = S + (size_t)min(lane, ny - 1) * pitch;
+    for (int x = warp; x < nx; x += WARPS) {
+        const float4* p = row + fs[x];
+        const float* w = ws + x * T.xtaps;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int t = 0; t < T.xtaps; ++t) {
+            const float wt = w[t];
+            if (wt != 0.0f) acc = fma4p(wt, p[t], acc);
+        }
+        if (lane < ny) tmp[(size_t)(y0 + lane) * dw + x0 + x] = acc;
+    }
+}
+
 struct RotParams {
     float m[9];  // inverse matrix, row-vector convention
     int id;      // filter id
@@ -552,6 +618,33 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
         count_launch(1);
     } else {
         dim3 block(32, 8);
+        // row pass: staged tile when a useful number of destination columns fits next to their footprint, else the gather
+        RowsTile R;
+        R.xtaps = ax.taps;
+        R.cols = 127;
+        R.xw = (int)floorf((float)(R.cols - ax.taps - 1) * (float)dst->w / (float)src->w) + 1;
+        if (R.xw > 64) R.xw = 64;
+        const size_t rows_smem = (size_t)RR_ROWS * (R.cols | 1) * sizeof(float4) + ((size_t)R.xw * ax.taps + R.xw) * sizeof(float);
+        if (R.xw >= 4 && ax.taps + 2 <= R.cols && rows_smem <= 72 * 1024) {
+            const dim3 rgrid((dst->w + R.xw - 1) / R.xw, (src->h + RR_ROWS - 1) / RR_ROWS);
+            int e = TC_OK;
+#define TC_RR(TY)                                                                                                              \
+    case TY:                                                                                                                   \
+        e = ensure_dynamic_smem((const void*)k_resize_rows_tile<TY>, rows_smem);                                               \
+        if (e == TC_OK) k_resize_rows_tile<TY><<<rgrid, RR_THREADS, rows_smem, st>>>(view(src), tmp, dst->w, xf, xw, xt, R);   \
+        break;
+            switch (src->type) {
+                TC_RR(TC_U8)
+                TC_RR(TC_U16)
+                TC_RR(TC_F16)
+                TC_RR(TC_F32)
+            }
+#undef TC_RR
+            if (e != TC_OK) {
+                if (scratch) cudaFreeAsync(scratch, st);
+                return e;
+            }
+        } else
         k_resize_rows<<<dim3((dst->w + 31) / 32, (src->h + 7) / 8), block, 0, st>>>(view(src), tmp, dst->w, xf, xw, xt, ax.taps);
         k_resize_cols<<<dim3((dst->w + 31) / 32, (dst->h + 7) / 8), block, 0, st>>>(tmp, src->h, view(dst), yf, yw, yt, ay.taps);
         count_launch(2);
