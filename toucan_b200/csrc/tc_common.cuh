@@ -129,4 +129,18 @@ __device__ __forceinline__ float4 load_clamp(const Img& im, int x, int y)
     return load_px(im.p, im.type, (size_t)y * im.w + x);
 }
 
+// Approximate SFU operations for the tolerance paths (1-2 ulp; inputs in the normal range)
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 } // namespace tc

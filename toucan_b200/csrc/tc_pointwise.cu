@@ -343,6 +343,43 @@ struct InvertOp {
         return p;
     }
 };
+// powf for the tolerance path.  CUDA's powf is ~95 instructions (double-float log2 and a tree of special
+// cases); this one is ~40 and good to ~4 ulp at any magnitude for exponents of a few units (the error is
+// that of log2 of the mantissa times v, independent of the base's exponent):
+//   x = m 2^e with m in [sqrt(1/2), sqrt(2));  log2 m = (2 / ln 2) atanh((m - 1) / (m + 1)), odd series to s^9
+//   (|s| <= 0.172, truncation 2e-9 relative);  v e is split exactly (product + FMA residual), so the integer
+//   part of v log2 x never costs mantissa bits;  2^fraction on the SFU, 2^integer exact.
+// Zero, denormals, infinity and NaN take exp2f(v log2f(x)), which has powf's limits for them.  A negative
+// base follows powf's rule in pow_fast (integer exponent: sign by parity, otherwise NaN).
+__device__ __forceinline__ float pow_pos(float x, float v)
+{
+    const int bits = __float_as_int(x);
+    if ((unsigned)(bits - 0x00800000) >= 0x7f000000u) return exp2f(__fmul_rn(v, log2f(x)));
+    const int e = (bits - 0x3f3504f3) >> 23;
+    const float m = __int_as_float(bits - (e << 23)), fe = (float)e;
+    const float num = __fsub_rn(m, 1.0f), den = __fadd_rn(m, 1.0f);
+    const float r = rcp_approx(den);
+    float s = __fmul_rn(num, r);
+    s = fmaf(r, fmaf(-s, den, num), s); // one Newton step: the quotient to ~0.5 ulp
+    const float z = __fmul_rn(s, s);
+    float p = fmaf(z, 1.0f / 9.0f, 1.0f / 7.0f);
+    p = fmaf(p, z, 1.0f / 5.0f);
+    p = fmaf(p, z, 1.0f / 3.0f);
+    p = __fmul_rn(p, z);
+    const float u = __fmul_rn(s, 2.8853900817779268f);
+    const float lm = fmaf(u, p, u); // log2(m)
+    const float a = __fmul_rn(v, fe);
+    const float b = fmaf(lm, v, fmaf(fe, v, -a));
+    const float n = rintf(__fadd_rn(a, b));
+    const float f = __fadd_rn(__fsub_rn(a, n), b);
+    return __fmul_rn(ex2_approx(f), exp2f(n));
+}
+__device__ __forceinline__ float pow_fast(float x, float v, bool v_int, bool v_odd)
+{
+    const float r = pow_pos(fabsf(x), v);
+    if (x < 0.0f) return v_int ? (v_odd ? -r : r) : __int_as_float(0x7fffffff);
+    return r;
+}
 struct PowOp {
     Src s;
     float v;
@@ -352,7 +389,11 @@ struct PowOp {
         // small integer exponents (the fixtures use 2 and 3) as products: within 1 ulp of powf
         if (v == 2.0f) return make_float4(p.x * p.x, p.y * p.y, p.z * p.z, p.w * p.w);
         if (v == 3.0f) return make_float4(p.x * p.x * p.x, p.y * p.y * p.y, p.z * p.z * p.z, p.w * p.w * p.w);
-        return make_float4(powf(p.x, v), powf(p.y, v), powf(p.z, v), powf(p.w, v));
+        if (v == 0.0f) return make_float4(1.f, 1.f, 1.f, 1.f);
+        // any other exponent: exp2(v * log2|x|) with powf's sign rules (pow_fast, tolerance path)
+        const bool v_int = truncf(v) == v, v_odd = v_int && fabsf(v) < 16777216.0f && ((long long)v & 1);
+        return make_float4(pow_fast(p.x, v, v_int, v_odd), pow_fast(p.y, v, v_int, v_odd), pow_fast(p.z, v, v_int, v_odd),
+                           pow_fast(p.w, v, v_int, v_odd));
     }
 };
 struct SaturateOp {
@@ -425,10 +466,10 @@ __device__ __forceinline__ float cc_curve(int id, int encode, float p, float x)
     switch (id) {
     case 1:
         if (x <= 0.0f) return x;
-        return powf(x, encode ? __fdiv_rn(1.0f, p) : p);
+        return pow_pos(x, encode ? __fdiv_rn(1.0f, p) : p);
     case 2:
-        if (!encode) return x <= 0.04045f ? __fdiv_rn(x, 12.92f) : powf(__fdiv_rn(__fadd_rn(x, 0.055f), 1.055f), 2.4f);
-        return x <= 0.0031308f ? __fmul_rn(x, 12.92f) : __fsub_rn(__fmul_rn(1.055f, powf(x, 1.0f / 2.4f)), 0.055f);
+        if (!encode) return x <= 0.04045f ? __fdiv_rn(x, 12.92f) : pow_pos(__fdiv_rn(__fadd_rn(x, 0.055f), 1.055f), 2.4f);
+        return x <= 0.0031308f ? __fmul_rn(x, 12.92f) : __fsub_rn(__fmul_rn(1.055f, pow_pos(x, 1.0f / 2.4f)), 0.055f);
     case 3:
         if (encode)
             return x <= 0.0078125f ? __fadd_rn(__fmul_rn(10.5402377416545f, x), 0.0729055341958355f)
@@ -476,6 +517,39 @@ struct ColorConvertOp {
         return make_float4(o[0], o[1], o[2], p.w);
     }
 };
+
+// The same conversion with both curves fixed at compile time (the per-node kernel).  With run-time curve
+// ids every pixel of the unrolled loop carries all five curves twice over and the kernel outgrows the
+// instruction cache; a (decode, encode) pair is a few hundred instructions.  The chain kernel keeps the
+// run-time form above.
+template <int CIN, int COUT>
+struct ColorConvertOpT {
+    Src s;
+    float p_in, p_out;
+    float m[9];
+    int unpremult;
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const
+    {
+        const bool un = unpremult && p.w != 0.0f && p.w != 1.0f;
+        if (un) {
+            p.x = __fdiv_rn(p.x, p.w);
+            p.y = __fdiv_rn(p.y, p.w);
+            p.z = __fdiv_rn(p.z, p.w);
+        }
+        const float l0 = cc_curve(CIN, 0, p_in, p.x), l1 = cc_curve(CIN, 0, p_in, p.y), l2 = cc_curve(CIN, 0, p_in, p.z);
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __fadd_rn(__fadd_rn(__fmul_rn(m[c * 3 + 0], l0), __fmul_rn(m[c * 3 + 1], l1)),
+                                      __fmul_rn(m[c * 3 + 2], l2));
+            o[c] = cc_curve(COUT, 1, p_out, v);
+            if (un) o[c] = __fmul_rn(o[c], p.w);
+        }
+        return make_float4(o[0], o[1], o[2], p.w);
+    }
+};
+constexpr int CC_CURVES = 5; // linear, gamma, sRGB, ACEScct, ACEScc (cc_curve)
 
 // ---- chain of pointwise effects in one pass -----------------------------------------------
 // Each step is the per-node functor above, applied in registers; between steps the value takes the
@@ -855,7 +929,21 @@ int tc_color_convert2(const tc_image* dst, const tc_image* src, const char* from
         const float z[4] = { 0.f, 0.f, 0.f, 0.f };
         return launch(FillOp { f4(z) }, dst, s);
     }
-    return launch(op, dst, s);
+    if (op.curve_in < 0 || op.curve_in >= CC_CURVES || op.curve_out < 0 || op.curve_out >= CC_CURVES) return launch(op, dst, s);
+    switch (op.curve_in * CC_CURVES + op.curve_out) {
+#define TC_CC(I, O)                                                    \
+    case I * CC_CURVES + O: {                                          \
+        ColorConvertOpT<I, O> t;                                       \
+        t.s = op.s, t.p_in = op.p_in, t.p_out = op.p_out, t.unpremult = op.unpremult; \
+        memcpy(t.m, op.m, sizeof(t.m));                                \
+        return launch(t, dst, s);                                      \
+    }
+#define TC_CC_ROW(I) TC_CC(I, 0) TC_CC(I, 1) TC_CC(I, 2) TC_CC(I, 3) TC_CC(I, 4)
+        TC_CC_ROW(0) TC_CC_ROW(1) TC_CC_ROW(2) TC_CC_ROW(3) TC_CC_ROW(4)
+#undef TC_CC_ROW
+#undef TC_CC
+    default: return launch(op, dst, s);
+    }
 }
 
 int tc_pointwise_chain(const tc_image* dst, const tc_image* src, const tc_chain_op* ops, int n, tc_stream s)
