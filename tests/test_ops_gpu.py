@@ -164,6 +164,33 @@ def test_pointwise_filters(T, dt, size):
                  "cc unpremult", rtol=2e-6)
 
 
+@pytest.mark.parametrize("value", [2.2, 0.4545, -1.5, 4.0, 5.0, -3.0, 0.0, 1.0, 7.25])
+def test_pow_special_values(T, value):
+    """toucan:Pow is powf per channel (FilterPlugin.cpp:420-441): negative bases (NaN unless the exponent is an integer,
+    then signed by parity), zeros, denormals, infinities, NaN, and magnitudes from 1e-30 to 1e30 -- relative bar 1e-6
+    (exponents of a few units: the error of the split-log2 evaluation grows with |value|)."""
+    rng = np.random.default_rng(11)
+    mags = np.float32(10.0) ** rng.uniform(-30, 30, size=(64, 64, 4)).astype(np.float32)
+    src = (mags * np.where(rng.random((64, 64, 4)) < 0.3, -1, 1)).astype(np.float32)
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-40, -1e-40, 1.17549435e-38, 3.4028235e38, 0.5, 2.0],
+                       dtype=np.float32)
+    src.reshape(-1)[:special.size] = special
+    with np.errstate(all="ignore"):
+        want = O.pow_(src, value)
+    got = to_host(T.pow_(to_dev(src), value))
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern"
+    inf = np.isinf(want)
+    big = np.abs(want) > 1e37  # within a few ulp of overflow either side may round to infinity
+    assert np.array_equal(got[inf & ~big], want[inf & ~big]) and np.array_equal(np.isinf(got) & ~big, inf & ~big), "infinities"
+    fin = np.isfinite(want) & np.isfinite(got) & ~big
+    tiny = np.abs(want) < 1e-37  # denormal results: absolute bar
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    assert (d[fin & tiny] <= 1e-37).all()
+    rel = d[fin & ~tiny] / np.abs(want[fin & ~tiny].astype(np.float64))
+    assert rel.max() <= 1e-6, f"pow {value}: max relative error {rel.max():.3e}"
+    assert np.array_equal(np.signbit(got[fin & ~tiny]), np.signbit(want[fin & ~tiny])), "sign"
+
+
 @pytest.mark.parametrize("dt", NP_TYPES)
 @pytest.mark.parametrize("radius", [10.0, 20.0, 3.0, 1.0, 7.5])
 def test_blur_unsharp(T, dt, radius):

@@ -349,14 +349,10 @@ struct InvertOp {
 //   x = m 2^e with m in [sqrt(1/2), sqrt(2));  log2 m = (2 / ln 2) atanh((m - 1) / (m + 1)), odd series to s^9
 //   (|s| <= 0.172, truncation 2e-9 relative);  v e is split exactly (product + FMA residual), so the integer
 //   part of v log2 x never costs mantissa bits;  2^fraction on the SFU, 2^integer exact.
-// Zero, denormals, infinity and NaN take exp2f(v log2f(x)), which has powf's limits for them.  A negative
-// base follows powf's rule in pow_fast (integer exponent: sign by parity, otherwise NaN).
-__device__ __forceinline__ float pow_pos(float x, float v)
+__device__ __forceinline__ float pow_core(int bits, int e0, float v)
 {
-    const int bits = __float_as_int(x);
-    if ((unsigned)(bits - 0x00800000) >= 0x7f000000u) return exp2f(__fmul_rn(v, log2f(x)));
     const int e = (bits - 0x3f3504f3) >> 23;
-    const float m = __int_as_float(bits - (e << 23)), fe = (float)e;
+    const float m = __int_as_float(bits - (e << 23)), fe = (float)(e + e0);
     const float num = __fsub_rn(m, 1.0f), den = __fadd_rn(m, 1.0f);
     const float r = rcp_approx(den);
     float s = __fmul_rn(num, r);
@@ -370,15 +366,46 @@ __device__ __forceinline__ float pow_pos(float x, float v)
     const float lm = fmaf(u, p, u); // log2(m)
     const float a = __fmul_rn(v, fe);
     const float b = fmaf(lm, v, fmaf(fe, v, -a));
-    const float n = rintf(__fadd_rn(a, b));
+    // nearest integer by the 1.5 * 2^23 trick (|v log2 x| < 2^22 or the result is 0 / infinity anyway)
+    const float t = fminf(fmaxf(__fadd_rn(a, b), -1000.0f), 1000.0f);
+    const float n = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
     const float f = __fadd_rn(__fsub_rn(a, n), b);
-    return __fmul_rn(ex2_approx(f), exp2f(n));
+    // 2^n on the SFU: exact for integers; below 2^-126 it flushes to zero (1e-38 absolute)
+    return __fmul_rn(ex2_approx(f), ex2_approx(n));
 }
-__device__ __forceinline__ float pow_fast(float x, float v, bool v_int, bool v_odd)
+// the rare bases: denormals are renormalised; zero, infinity and NaN take exp2f(v log2f(x))
+__device__ __noinline__ float pow_rare(float x, float v)
 {
-    const float r = pow_pos(fabsf(x), v);
-    if (x < 0.0f) return v_int ? (v_odd ? -r : r) : __int_as_float(0x7fffffff);
+    const int bits = __float_as_int(x);
+    if (bits > 0 && bits < 0x00800000) return pow_core(__float_as_int(__fmul_rn(x, 16777216.0f)), -24, v);
+    return exp2f(__fmul_rn(v, log2f(x)));
+}
+// x >= 0 (the colour curves)
+__device__ __forceinline__ float pow_pos(float x, float v)
+{
+    const int bits = __float_as_int(x);
+    if ((unsigned)(bits - 0x00800000) >= 0x7f000000u) return pow_rare(x, v);
+    return pow_core(bits, 0, v);
+}
+// Everything that is not a positive normal number, with powf's rules for the sign bit: an odd integer
+// exponent keeps it; a non-integer exponent of a negative finite non-zero base is NaN; -0 and -infinity
+// behave as their magnitudes otherwise.  flags: bit 0 = v is an integer, bit 1 = v is an odd integer.
+__device__ __noinline__ float pow_signed_rare(float x, float v, int flags)
+{
+    const float ax = fabsf(x);
+    const float r = pow_pos(ax, v);
+    if (__float_as_int(x) < 0) {
+        if (flags & 2) return -r;
+        if (!(flags & 1) && ax != 0.0f && ax <= 3.4028234664e38f) return __int_as_float(0x7fffffff);
+    }
     return r;
+}
+// any base: one test sends positive normal numbers (every pixel of an ordinary image) to the core
+__device__ __forceinline__ float pow_fast(float x, float v, int flags)
+{
+    const int bits = __float_as_int(x);
+    if ((unsigned)(bits - 0x00800000) >= 0x7f000000u) return pow_signed_rare(x, v, flags);
+    return pow_core(bits, 0, v);
 }
 struct PowOp {
     Src s;
@@ -392,8 +419,8 @@ struct PowOp {
         if (v == 0.0f) return make_float4(1.f, 1.f, 1.f, 1.f);
         // any other exponent: exp2(v * log2|x|) with powf's sign rules (pow_fast, tolerance path)
         const bool v_int = truncf(v) == v, v_odd = v_int && fabsf(v) < 16777216.0f && ((long long)v & 1);
-        return make_float4(pow_fast(p.x, v, v_int, v_odd), pow_fast(p.y, v, v_int, v_odd), pow_fast(p.z, v, v_int, v_odd),
-                           pow_fast(p.w, v, v_int, v_odd));
+        const int flags = (v_int ? 1 : 0) | (v_odd ? 2 : 0);
+        return make_float4(pow_fast(p.x, v, flags), pow_fast(p.y, v, flags), pow_fast(p.z, v, flags), pow_fast(p.w, v, flags));
     }
 };
 struct SaturateOp {

@@ -54,6 +54,7 @@ struct StUnit {
 };
 struct StParams {
     int w, h, n_units, first_staged;
+    int tiles_x, tiles_y, band; // CTA order: bands of `band` tile rows, column-major inside a band
     float4 background;
     StKernel k[ST_MAX_KERNELS];
     StUnit unit[ST_MAX_UNITS];
@@ -113,7 +114,16 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restric
     constexpr int ST_PX = T::PX;
     extern __shared__ float4 smem[];
     float4* mid = smem + NBUF * T::IN_ELEMS;
-    const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * TH;
+    // CTA -> tile: the CTAs resident at one time (2-3 per SM, ~300-450) walk every source at about the same
+    // pace, so a halo row or column shared by two of them is read from HBM once and from L2 the second time
+    // -- if both are resident together.  In row-major order a wave is 2-4 full rows of tiles and the halo
+    // rows towards the next wave have left L2 (20 sources x 300 tiles x 37 KB = 220 MB) before it starts;
+    // bands of `band` tile rows walked column by column keep most vertical neighbours in the same wave.
+    const int per_band = P.band * P.tiles_x;
+    const int band = blockIdx.x / per_band, within = blockIdx.x - band * per_band;
+    const int bh = min(P.band, P.tiles_y - band * P.band);
+    const int tx = within / bh, ty = band * P.band + (within - tx * bh);
+    const int x0 = tx * ST_TW, y0 = ty * TH;
     const int col = threadIdx.x % ST_TW, seg = threadIdx.x / ST_TW;
     const int x = x0 + col, y = y0 + seg * ST_PX;
 
@@ -246,15 +256,27 @@ static int st_build_kernel(float width, StKernel* K)
 template <int R, int TH, int NBUF>
 constexpr int st_occ() { return StTile<R, TH, NBUF>::SMEM <= 74 * 1024 ? 3 : (StTile<R, TH, NBUF>::SMEM <= 112 * 1024 ? 2 : 1); }
 
+static int st_band()
+{
+    static const int band = [] {
+        const char* e = getenv("TOUCAN_STACK_BAND");
+        const int v = e ? atoi(e) : 0;
+        return v > 0 ? v : 8;
+    }();
+    return band;
+}
+
 template <int R, int TH, int NBUF, int OCC = st_occ<R, TH, NBUF>()>
-static int launch_stack(const tc_image* dst, const StParams& P, cudaStream_t st)
+static int launch_stack(const tc_image* dst, StParams& P, cudaStream_t st)
 {
     using T = StTile<R, TH, NBUF>;
     static_assert(T::SMEM <= 227 * 1024, "tile does not fit in shared memory");
     int st_attr = ensure_dynamic_smem((const void*)k_stack_f32<R, TH, NBUF, OCC>, T::SMEM);
     if (st_attr != TC_OK) return st_attr;
-    dim3 grid((dst->w + ST_TW - 1) / ST_TW, (dst->h + TH - 1) / TH);
-    k_stack_f32<R, TH, NBUF, OCC><<<grid, ST_THREADS, T::SMEM, st>>>((float4*)dst->data, P);
+    P.tiles_x = (dst->w + ST_TW - 1) / ST_TW;
+    P.tiles_y = (dst->h + TH - 1) / TH;
+    P.band = min(st_band(), P.tiles_y);
+    k_stack_f32<R, TH, NBUF, OCC><<<P.tiles_x * P.tiles_y, ST_THREADS, T::SMEM, st>>>((float4*)dst->data, P);
     count_launch();
     return check_cuda(cudaGetLastError(), "k_stack_f32 launch");
 }
