@@ -310,9 +310,9 @@ def test_blur_wide_kernel_fallback(T, radius):
     assert_close(T.unsharp_mask(to_dev(src), "gaussian", radius, 0.5, 0.0), O.unsharp_mask(src, "gaussian", radius, 0.5, 0.0), "unsharp wide")
 
 
-@pytest.mark.parametrize("radius", [3.0, 14.0, 20.0, 26.0])
+@pytest.mark.parametrize("radius", [3.0, 7.0, 10.0, 14.0, 20.0, 26.0])
 def test_stack_other_radii_and_mixed_layers(T, radius):
-    # template instantiations R = 2, 6, 9, 12; blurred, unblurred and dissolve layers in one stack;
+    # template instantiations R = 2, 4, 6, 9, 12; blurred, unblurred and dissolve layers in one stack;
     # odd frame size (partial tiles on both axes)
     w, h = 203, 77
     a = [rand_img(w, h, np.float32, 300 + i) for i in range(6)]
