@@ -38,13 +38,12 @@ void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxe
 
 int num_sms()
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaDeviceProp p;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) sms = p.multiProcessorCount;
-        if (sms <= 0) sms = 148;
-    }
+    // one GPU model per box: the first caller's device answers for all (initialisation is thread-safe)
+    static const int sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        return n;
+    }();
     return sms;
 }
 
