@@ -200,7 +200,7 @@ __device__ __forceinline__ unsigned filt(const unsigned short* s, Tap t, int bas
     return min((v15 + 64) >> 7, 255u);
 }
 
-template <int FORMAT>
+template <int FORMAT, int TYPE>
 __global__ void __launch_bounds__(Y4M_THREADS) k_rgb_to_y4m(void* __restrict__ dst, const Img src, const Y4mParams P)
 {
     constexpr bool P16 = FORMAT == TC_Y4M_444P16;
@@ -223,11 +223,27 @@ __global__ void __launch_bounds__(Y4M_THREADS) k_rgb_to_y4m(void* __restrict__ d
     const size_t row = (size_t)y * w;
 
     // stage A: packed RGBA (any storage type) -> quantised RGB(A) -> integer Y / pair-sum U, V
-    for (int k = threadIdx.x; k < pairs; k += Y4M_THREADS) {
-        const int x0 = lo + 2 * k;
-        // a row of odd width ends in half a pair; its partner reads as the last pixel again
-        const int x1 = min(x0 + 1, w - 1);
-        const float4 p0 = load_px(src.p, src.type, row + x0), p1 = load_px(src.p, src.type, row + x1);
+    // The source's storage type is a template parameter and all of the thread's pixel pairs are loaded before the first
+    // is converted: with a run-time type switch per load each conversion waited for its own load (four to six exposed
+    // latencies per thread).
+    constexpr int PAIR_ITERS = (N / 2 + Y4M_THREADS - 1) / Y4M_THREADS;
+    float4 q0[PAIR_ITERS], q1[PAIR_ITERS];
+#pragma unroll
+    for (int i = 0; i < PAIR_ITERS; ++i) {
+        const int k = threadIdx.x + i * Y4M_THREADS;
+        if (k < pairs) {
+            const int x0 = lo + 2 * k;
+            // a row of odd width ends in half a pair; its partner reads as the last pixel again
+            const int x1 = min(x0 + 1, w - 1);
+            q0[i] = load_px(src.p, TYPE, row + x0);
+            q1[i] = load_px(src.p, TYPE, row + x1);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PAIR_ITERS; ++i) {
+        const int k = threadIdx.x + i * Y4M_THREADS;
+        if (k >= pairs) continue;
+        const float4 p0 = q0[i], p1 = q1[i];
         if (P16) {
             const unsigned r0 = f_to_u16(p0.x), g0 = f_to_u16(p0.y), b0 = f_to_u16(p0.z);
             const unsigned r1 = f_to_u16(p1.x), g1 = f_to_u16(p1.y), b1 = f_to_u16(p1.z);
@@ -308,12 +324,20 @@ int tc_rgb_to_y4m(void* dst_dev, const tc_image* src, int format, tc_stream s)
     const Y4mParams P { t.dev, t.dev + src->w, t.cw_src, t.cw_dst };
     const dim3 grid((unsigned)((src->w + Y4M_SEG - 1) / Y4M_SEG), (unsigned)src->h);
     cudaStream_t st = (cudaStream_t)s;
-    switch (format) {
-    case TC_Y4M_422: k_rgb_to_y4m<TC_Y4M_422><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;
-    case TC_Y4M_444: k_rgb_to_y4m<TC_Y4M_444><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;
-    case TC_Y4M_444ALPHA: k_rgb_to_y4m<TC_Y4M_444ALPHA><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;
-    default: k_rgb_to_y4m<TC_Y4M_444P16><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;
+#define TC_Y4M_LAUNCH(F)                                                                                  \
+    switch (src->type) {                                                                                  \
+    case TC_U8: k_rgb_to_y4m<F, TC_U8><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;       \
+    case TC_U16: k_rgb_to_y4m<F, TC_U16><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;     \
+    case TC_F16: k_rgb_to_y4m<F, TC_F16><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;     \
+    default: k_rgb_to_y4m<F, TC_F32><<<grid, Y4M_THREADS, 0, st>>>(dst_dev, view(src), P); break;         \
     }
+    switch (format) {
+    case TC_Y4M_422: TC_Y4M_LAUNCH(TC_Y4M_422) break;
+    case TC_Y4M_444: TC_Y4M_LAUNCH(TC_Y4M_444) break;
+    case TC_Y4M_444ALPHA: TC_Y4M_LAUNCH(TC_Y4M_444ALPHA) break;
+    default: TC_Y4M_LAUNCH(TC_Y4M_444P16) break;
+    }
+#undef TC_Y4M_LAUNCH
     count_launch();
     return check_cuda(cudaGetLastError(), "k_rgb_to_y4m launch");
 }
