@@ -97,6 +97,11 @@ int tr_y4m_header(int width, int height, double rate, const char* y4m_format, ch
    worker `index` of `count` (ceil(N / G) frames per GPU). */
 void tr_frame_block(int first, int last, int index, int count, int* lo, int* hi);
 
+/* toucan::fit (lib/toucanRender/Util.cpp:123-147): the box, inside a frame of aw x ah, that a bw x bh image is fitted
+   into (aspect preserved, centred).  out = { min x, min y, width, height }.  CompNode and the Dissolve / Wipe effects
+   place a differently sized input with it. */
+void tr_fit(int aw, int ah, int bw, int bh, int out[4]);
+
 /* The built-in PNG reader used when no decoded frame was registered for a path (RGBA out,
    A = 1 appended to RGB, alpha associated on read like OIIO's reader).  out may be NULL to
    query the size. */

@@ -95,3 +95,21 @@ def test_unknown_effect_is_skipped_and_unknown_transition_dissolves(host):
     tree = tl.describe(host, 40.0)
     assert "toucan:Dissolve {value=0.16666666666666666}" in tree
     assert "nonesuch" not in tree and tree.count("toucan:Blur") == 2
+
+
+def test_host_fit_matches_oracle():
+    """toucan::fit of the C++ host against the oracle's restatement of Util.cpp:123-147 (the box decides which pixels
+    a fit-resize writes, so it must agree to the pixel): config sizes, odd sizes, degenerate boxes, 2000 random pairs."""
+    import numpy as np
+
+    from oracle import oracle as O
+    from toucan_b200 import render
+
+    cases = [((1280, 720), (1280, 720)), ((3840, 2160), (1920, 1080)), ((1280, 720), (720, 1280)), ((128, 72), (64, 36)),
+             ((1920, 1080), (1000, 1000)), ((7, 5), (3, 11)), ((1, 1), (1, 1)), ((100, 100), (1, 0)), ((100, 0), (10, 10)),
+             ((33, 77), (1280, 720)), ((7680, 4320), (1281, 719))]
+    rng = np.random.default_rng(4)
+    cases += [((int(a), int(b)), (int(c), int(d))) for a, b, c, d in rng.integers(1, 5000, size=(2000, 4))]
+    for a, b in cases:
+        assert render.fit(a, b) == tuple(O.fit(a, b)), (a, b)
+

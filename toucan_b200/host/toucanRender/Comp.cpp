@@ -12,9 +12,9 @@ namespace toucan
     CompNode::~CompNode()
     {}
 
-    void CompNode::setPremult(bool premult) { _premult = premult; }
+    void CompNode::setPremult(bool premult) { _premultiply = premult; }
 
-    void CompNode::setResize(bool resize) { _resize = resize; }
+    void CompNode::setResize(bool resize) { _fit = resize; }
 
     Image CompNode::composite(const Image& fgIn, const Image& bg) const
     {
@@ -32,7 +32,7 @@ namespace toucan
             // Slow path (Comp.cpp:37-68): premult -> resize into the fitted box -> paste on a
             // transparent buffer of the background's size and type -> over.
             Image fg = fgIn;
-            if (_premult)
+            if (_premultiply)
             {
                 Image pm(fgSpec);
                 const tc_image s = fgIn.view(), d = pm.view();
@@ -64,7 +64,7 @@ namespace toucan
         if (!bgValid)
         {
             // over() with an empty background: the foreground alone
-            if (!_premult) return fgIn;
+            if (!_premultiply) return fgIn;
             Image pm(fgSpec);
             const tc_image s = fgIn.view(), d = pm.view();
             tcCheck(tc_premult(&d, &s, stream), "tc_premult");
@@ -73,7 +73,7 @@ namespace toucan
         // Fast path: premult + over fused into one pass.
         Image out(ImageSpec(bgSpec.width, bgSpec.height, 4, tc_type_merge(fgSpec.format, bgSpec.format)));
         const tc_image f = fgIn.view(), b = bg.view(), o = out.view();
-        tcCheck(tc_over(&o, &f, &b, _premult ? 1 : 0, stream), "tc_over");
+        tcCheck(tc_over(&o, &f, &b, _premultiply ? 1 : 0, stream), "tc_over");
         return out;
     }
 
@@ -85,7 +85,7 @@ namespace toucan
             // Cross-node fusion: a chain of CompNodes over [Dissolve of] [Blur of] float
             // sources collapses into one pass (StackFusion.h).  Falls through when the
             // pattern does not match.
-            if (_premult && tryFusedStack(*this, buf))
+            if (_premultiply && tryFusedStack(*this, buf))
             {
                 return buf;
             }
@@ -101,7 +101,7 @@ namespace toucan
                 // generators render 4-channel UINT8 (ImageEffect.cpp:93)
                 buf = Image(ImageSpec(fgSpec.width, fgSpec.height, 4, tc_type_merge(fgSpec.format, TC_U8)));
                 const tc_image f = fg.view(), o = buf.view();
-                tcCheck(tc_over_fill(&o, &f, fillColor, TC_U8, _premult ? 1 : 0, DeviceContext::stream()), "tc_over_fill");
+                tcCheck(tc_over_fill(&o, &f, fillColor, TC_U8, _premultiply ? 1 : 0, DeviceContext::stream()), "tc_over_fill");
                 return buf;
             }
             const Image bg = _inputs[1]->exec();
@@ -110,7 +110,7 @@ namespace toucan
         else if (1 == _inputs.size() && _inputs[0])
         {
             buf = _inputs[0]->exec();
-            if (_premult && buf.spec().width > 0 && buf.spec().height > 0)
+            if (_premultiply && buf.spec().width > 0 && buf.spec().height > 0)
             {
                 Image pm(buf.spec());
                 const tc_image s = buf.view(), d = pm.view();

@@ -1,34 +1,34 @@
-// Track/stack compositing node.  Interface parity: lib/toucanRender/Comp.h:11-29.
+// Track / stack compositing: the node ImageGraph puts between every video track and what lies below it.
+// Same public interface as lib/toucanRender/Comp.h:11-29 (inputs {foreground, background}, setPremult, setResize).
 #pragma once
 
 #include <toucanRender/ImageNode.h>
 
 namespace toucan
 {
-    //! Compositing node: premultiply the foreground, fit it to the background if the
-    //! sizes differ, then Porter-Duff "over".
+    //! foreground over background: premultiply the foreground (if asked), fit it into the background's frame when
+    //! the sizes differ, then Porter-Duff "over".  One fused kernel when the sizes agree.
     class CompNode : public IImageNode
     {
     public:
-        CompNode(const std::vector<std::shared_ptr<IImageNode> >& = {});
-
+        CompNode(const ImageNodeList& inputs = {});
         virtual ~CompNode();
 
-        //! Set whether images are pre-multiplied before compositing.
+        //! Multiply the foreground's colour by its alpha before compositing (ImageGraph always sets this).
         void setPremult(bool);
-        bool getPremult() const { return _premult; }
+        bool getPremult() const { return _premultiply; }
 
-        //! Set whether images are resized before compositing (stored, never consulted:
-        //! same as the reference, Comp.cpp:24-27 vs :29-84).
+        //! Accepted and stored for interface parity; like the reference (Comp.cpp:24-27 against :29-84) nothing
+        //! reads it: a foreground of another size is always fitted.
         void setResize(bool);
 
         Image exec() override;
 
-        //! Composite already evaluated images (used by exec and by the fusion pass).
+        //! Composite two already evaluated images (exec, and the fusion pass for layers it cannot fuse).
         Image composite(const Image& fg, const Image& bg) const;
 
     private:
-        bool _premult = false;
-        bool _resize = true;
+        bool _premultiply = false;
+        bool _fit = true;
     };
 }

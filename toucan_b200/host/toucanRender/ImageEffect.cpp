@@ -46,10 +46,10 @@ namespace toucan
         const std::string& name,
         const std::vector<std::shared_ptr<IImageNode> >& inputs) :
         IImageNode(name, inputs),
-        _plugin(plugin),
-        _instance(new ImageEffectInstance),
-        _handle{ &plugin, _instance.get() },
-        _metaData(metaData)
+        _effect(plugin),
+        _settings(metaData),
+        _live(new ImageEffectInstance),
+        _self{ &plugin, _live.get() }
     {
         // Harvest described defaults the way the reference does (ImageEffect.cpp:21-51):
         // only element 0 of OfxParamPropDefault, typed by the property table it sits in.
@@ -57,55 +57,55 @@ namespace toucan
         // (it matches bool / int64_t / double / string / AnyVector) -- so Integer,
         // Integer2D and Boolean defaults silently fall back to the plug-in's local
         // initialisers.  Kept on purpose: it defines the effective parameter defaults.
-        if (!_plugin.defaultsHarvested)
+        if (!_effect.defaultsHarvested)
         {
-            for (const auto& def : _plugin.paramDefs)
+            for (const auto& def : _effect.paramDefs)
             {
                 if (hasProperty(def.second.getStringProperties(), kOfxParamPropDefault))
                 {
                     char* s = nullptr;
                     def.second.getString(kOfxParamPropDefault, 0, &s);
-                    if (s) _plugin.harvestedDefaults[def.first] = std::string(s);
+                    if (s) _effect.harvestedDefaults[def.first] = std::string(s);
                 }
                 if (hasProperty(def.second.getDoubleProperties(), kOfxParamPropDefault))
                 {
                     double d = 0.0;
                     def.second.getDouble(kOfxParamPropDefault, 0, &d);
-                    _plugin.harvestedDefaults[def.first] = d;
+                    _effect.harvestedDefaults[def.first] = d;
                 }
                 if (hasProperty(def.second.getIntProperties(), kOfxParamPropDefault))
                 {
                     int i = 0;
                     def.second.getInt(kOfxParamPropDefault, 0, &i);
-                    _plugin.harvestedDefaults[def.first] = i;
+                    _effect.harvestedDefaults[def.first] = i;
                 }
             }
-            _plugin.defaultsHarvested = true;
+            _effect.defaultsHarvested = true;
         }
-        _instance->params = _plugin.harvestedDefaults;
+        _live->params = _effect.harvestedDefaults;
         for (const auto& kv : metaData)
         {
-            _instance->params[kv.first] = kv.second;
+            _live->params[kv.first] = kv.second;
         }
 
-        _plugin.ofxPlugin->mainEntry(kOfxActionCreateInstance, &_handle, nullptr, nullptr);
+        _effect.ofxPlugin->mainEntry(kOfxActionCreateInstance, &_self, nullptr, nullptr);
     }
 
     ImageEffectNode::~ImageEffectNode()
     {
-        _plugin.ofxPlugin->mainEntry(kOfxActionDestroyInstance, &_handle, nullptr, nullptr);
+        _effect.ofxPlugin->mainEntry(kOfxActionDestroyInstance, &_self, nullptr, nullptr);
     }
 
-    const std::map<std::string, std::any>& ImageEffectNode::getParams() const { return _instance->params; }
+    const std::map<std::string, std::any>& ImageEffectNode::getParams() const { return _live->params; }
 
-    const OTIO_NS::AnyDictionary& ImageEffectNode::getMetaData() const { return _metaData; }
+    const OTIO_NS::AnyDictionary& ImageEffectNode::getMetaData() const { return _settings; }
 
     std::string ImageEffectNode::describe() const
     {
         std::stringstream ss;
         ss << _name << " {";
         bool first = true;
-        for (const auto& kv : _metaData)
+        for (const auto& kv : _settings)
         {
             if (!first) ss << ", ";
             first = false;
@@ -119,13 +119,13 @@ namespace toucan
     bool ImageEffectNode::describePointwise(tc_chain& chain) const
     {
         char* context = nullptr;
-        _plugin.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
+        _effect.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
         if (!context || 0 != strcmp(context, kOfxImageEffectContextFilter) || _inputs.size() != 1 || !_inputs[0])
         {
             return false;
         }
-        const auto sizeIt = _metaData.find("size");
-        if (sizeIt != _metaData.end() && sizeIt->second.has_value())
+        const auto sizeIt = _settings.find("size");
+        if (sizeIt != _settings.end() && sizeIt->second.has_value())
         {
             return false; // an output-size override is not a same-position operation
         }
@@ -143,10 +143,10 @@ namespace toucan
         args.setInt(kOfxImageEffectPropCudaEnabled, 0, 1);
         args.setPointer(kOfxImageEffectPropCudaStream, 0, DeviceContext::stream());
         args.setPointer("ToucanPropPointwiseChain", 0, &chain);
-        _instance->images.clear();
-        const OfxStatus status = _plugin.ofxPlugin->mainEntry(
+        _live->images.clear();
+        const OfxStatus status = _effect.ofxPlugin->mainEntry(
             kOfxImageEffectActionRender,
-            &_handle,
+            &_self,
             reinterpret_cast<OfxPropertySetHandle>(&args),
             nullptr);
         if (status != kOfxStatOK || chain.n != before + 1)
@@ -199,7 +199,7 @@ namespace toucan
     {
         // Evaluate the inputs the effect's context consumes, then render.
         char* context = nullptr;
-        _plugin.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
+        _effect.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
         std::vector<Image> inputs;
         if (context && 0 == strcmp(context, kOfxImageEffectContextFilter))
         {
@@ -227,24 +227,24 @@ namespace toucan
 
         // Output size override: read straight from the node metadata (ImageEffect.cpp:84-88).
         IMATH_NAMESPACE::V2i size(0, 0);
-        const auto sizeIt = _metaData.find("size");
-        if (sizeIt != _metaData.end() && sizeIt->second.has_value())
+        const auto sizeIt = _settings.find("size");
+        if (sizeIt != _settings.end() && sizeIt->second.has_value())
         {
             anyToVec(std::any_cast<OTIO_NS::AnyVector>(sizeIt->second), size);
         }
 
         char* context = nullptr;
-        _plugin.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
+        _effect.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
         if (!context)
         {
             return out;
         }
-        _instance->images.clear();
+        _live->images.clear();
         if (0 == strcmp(context, kOfxImageEffectContextGenerator))
         {
             // generators are hard-wired to 4-channel UINT8 (ImageEffect.cpp:93)
             out = Image(ImageSpec(size.x, size.y, 4));
-            _instance->images["Output"] = bufToPropSet(out);
+            _live->images["Output"] = bufToPropSet(out);
         }
         else if (0 == strcmp(context, kOfxImageEffectContextFilter) && inputs.size() >= 1)
         {
@@ -255,8 +255,8 @@ namespace toucan
                 spec.height = size.y;
             }
             out = Image(spec);
-            _instance->images["Source"] = bufToPropSet(inputs[0]);
-            _instance->images["Output"] = bufToPropSet(out);
+            _live->images["Source"] = bufToPropSet(inputs[0]);
+            _live->images["Output"] = bufToPropSet(out);
         }
         else if (0 == strcmp(context, kOfxImageEffectContextTransition) && inputs.size() >= 2)
         {
@@ -267,9 +267,9 @@ namespace toucan
                 spec.height = size.y;
             }
             out = Image(spec);
-            _instance->images["SourceFrom"] = bufToPropSet(inputs[0]);
-            _instance->images["SourceTo"] = bufToPropSet(inputs[1]);
-            _instance->images["Output"] = bufToPropSet(out);
+            _live->images["SourceFrom"] = bufToPropSet(inputs[0]);
+            _live->images["SourceTo"] = bufToPropSet(inputs[1]);
+            _live->images["Output"] = bufToPropSet(out);
         }
 
         const ImageSpec& spec = out.spec();
@@ -283,9 +283,9 @@ namespace toucan
             args.setInt(kOfxImageEffectPropCudaEnabled, 0, 1);
             args.setPointer(kOfxImageEffectPropCudaStream, 0, DeviceContext::stream());
 
-            const OfxStatus status = _plugin.ofxPlugin->mainEntry(
+            const OfxStatus status = _effect.ofxPlugin->mainEntry(
                 kOfxImageEffectActionRender,
-                &_handle,
+                &_self,
                 reinterpret_cast<OfxPropertySetHandle>(&args),
                 nullptr);
             // The reference ignores the render status (ImageEffect.cpp:145); a device

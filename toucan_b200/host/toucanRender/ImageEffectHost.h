@@ -1,7 +1,8 @@
-// The OpenFX host: finds and loads the *.ofx modules, drives Load / Describe /
-// DescribeInContext, serves the property / parameter / image-effect suites and creates
-// effect nodes by plug-in identifier.
-// Interface parity: lib/toucanRender/ImageEffectHost.h:17-54.
+// The OpenFX host: finds and loads the *.ofx modules under a search path, drives Load / Describe /
+// DescribeInContext on every image-effect plug-in in them, serves the property / parameter / image-effect
+// suites, and creates effect nodes by plug-in identifier.
+// The public interface is the reference's (lib/toucanRender/ImageEffectHost.h:17-30): same constructor,
+// same createNode; everything else lives in the implementation file.
 #pragma once
 
 #include <toucanRender/ImageEffect.h>
@@ -9,50 +10,35 @@
 #include <ftk/Core/Context.h>
 
 #include <filesystem>
+#include <memory>
+#include <string>
+#include <vector>
 
 namespace toucan
 {
-    //! Image effect host.
     class ImageEffectHost : public std::enable_shared_from_this<ImageEffectHost>
     {
     public:
         ImageEffectHost(
             const std::shared_ptr<ftk::Context>&,
             const std::vector<std::filesystem::path>& searchPath);
-
         ~ImageEffectHost();
 
-        //! Create an image node. Returns nullptr for an unknown effect name.
+        ImageEffectHost(const ImageEffectHost&) = delete;
+        ImageEffectHost& operator=(const ImageEffectHost&) = delete;
+
+        //! A node running the effect `name` (a plug-in identifier such as "toucan:Blur") with the parameters in
+        //! `metaData` on `inputs`; nullptr when no loaded plug-in has that identifier.
         std::shared_ptr<IImageNode> createNode(
-            const OTIO_NS::AnyDictionary&,
+            const OTIO_NS::AnyDictionary& metaData,
             const std::string& name,
-            const std::vector<std::shared_ptr<IImageNode> >& = {});
+            const std::vector<std::shared_ptr<IImageNode> >& inputs = {});
 
         //! Identifiers of the loaded effects, in load order.
         std::vector<std::string> getPluginIdentifiers() const;
 
     private:
-        void _suiteInit();
-        void _pluginInit(const std::vector<std::filesystem::path>& searchPath);
-
-        static const void* _fetchSuite(OfxPropertySetHandle, const char* suiteName, int suiteVersion);
-        static OfxStatus _getPropertySet(OfxImageEffectHandle, OfxPropertySetHandle*);
-        static OfxStatus _getParamSet(OfxImageEffectHandle, OfxParamSetHandle*);
-        static OfxStatus _paramDefine(OfxParamSetHandle, const char* paramType, const char* name, OfxPropertySetHandle*);
-        static OfxStatus _paramGetHandle(OfxParamSetHandle, const char* name, OfxParamHandle*, OfxPropertySetHandle*);
-        static OfxStatus _paramGetValue(OfxParamHandle, ...);
-        static OfxStatus _clipDefine(OfxImageEffectHandle, const char* name, OfxPropertySetHandle*);
-        static OfxStatus _clipGetHandle(OfxImageEffectHandle, const char* name, OfxImageClipHandle*, OfxPropertySetHandle*);
-        static OfxStatus _clipGetImage(OfxImageClipHandle, OfxTime, const OfxRectD*, OfxPropertySetHandle*);
-        static OfxStatus _clipReleaseImage(OfxPropertySetHandle);
-
-        std::weak_ptr<ftk::Context> _context;
-        PropertySet _propSet;
-        OfxHost _host;
-        OfxPropertySuiteV1 _propertySuite;
-        OfxParameterSuiteV1 _parameterSuite;
-        OfxImageEffectSuiteV1 _effectSuite;
-        // std::deque-like stability is required: nodes keep ImageEffectPlugin& references
-        std::vector<std::unique_ptr<ImageEffectPlugin> > _plugins;
+        struct State;
+        std::unique_ptr<State> _state;
     };
 }

@@ -12,21 +12,69 @@ namespace toucan
         const std::string logPrefix = "toucan::ImageGraph";
     }
 
+    // What the constructor learns about the timeline, and the read-node cache shared by every frame.
+    struct ImageGraph::Data
+    {
+        std::weak_ptr<ftk::Context> context;
+        std::filesystem::path path;
+        std::shared_ptr<TimelineWrapper> timelineWrapper;
+        OTIO_NS::TimeRange timeRange;
+        IMATH_NAMESPACE::V2i imageSize = IMATH_NAMESPACE::V2i(0, 0);
+        int imageChannels = 0;
+        std::string imageDataType;
+        ftk::LRUCache<const OTIO_NS::MediaReference*, std::shared_ptr<IReadNode> > readCache;
+
+        std::shared_ptr<IReadNode> read(const OTIO_NS::MediaReference*, bool cache);
+        void imageInfo(const std::shared_ptr<IReadNode>&);
+    };
+
+    // Builder of ONE frame's node tree: the state the reference keeps in ImageGraph members for the duration of
+    // exec() (ImageGraph.h:74-77) lives here, on exec()'s stack.
+    class ImageGraph::Frame
+    {
+    public:
+        using EffectList = std::vector<OTIO_NS::SerializableObject::Retainer<OTIO_NS::Effect> >;
+
+        Frame(Data& data, const std::shared_ptr<ImageEffectHost>& h, const OTIO_NS::Item* solo) : d(data), host(h), soloItem(solo) {}
+
+        std::shared_ptr<IImageNode> buildTrack(
+            const OTIO_NS::RationalTime&,
+            const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Track>&);
+        std::shared_ptr<IImageNode> buildItem(
+            const OTIO_NS::RationalTime&,
+            const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Item>&);
+        std::shared_ptr<IImageNode> buildTransition(
+            const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Transition>&,
+            const OTIO_NS::TimeRange&,
+            const OTIO_NS::RationalTime&,
+            const std::shared_ptr<IImageNode>& from,
+            const std::shared_ptr<IImageNode>& to);
+        OTIO_NS::RationalTime warpTime(const OTIO_NS::RationalTime&, const OTIO_NS::TimeRange&, const EffectList&);
+        std::shared_ptr<IImageNode> applyEffects(const OTIO_NS::RationalTime&, const EffectList&, const std::shared_ptr<IImageNode>&);
+
+        Data& d;
+        std::shared_ptr<ImageEffectHost> host;
+        const OTIO_NS::Item* soloItem = nullptr;   // exec()'s optional item: its output replaces the stack's
+        std::shared_ptr<IImageNode> soloNode;
+    };
+
     ImageGraph::ImageGraph(
         const std::shared_ptr<ftk::Context>& context,
         const std::filesystem::path& path,
         const std::shared_ptr<TimelineWrapper>& timelineWrapper) :
-        _context(context),
-        _path(path),
-        _timelineWrapper(timelineWrapper),
-        _timeRange(timelineWrapper->getTimeRange())
+        _d(new Data)
     {
-        _readCache.setMax(20);
+        Data& d = *_d;
+        d.context = context;
+        d.path = path;
+        d.timelineWrapper = timelineWrapper;
+        d.timeRange = timelineWrapper->getTimeRange();
+        d.readCache.setMax(20);
 
         // The timeline's image size / channels / type come from the first video clip that
         // yields them: readable media, or a generator with a "size" parameter (generators
         // are hard-wired to 4 x UINT8).  ImageGraph.cpp:53-123.
-        for (const auto& clip : getVideoClips(_timelineWrapper->getTimeline()))
+        for (const auto& clip : getVideoClips(d.timelineWrapper->getTimeline()))
         {
             OTIO_NS::MediaReference* ref = clip->media_reference();
             if (auto generatorRef = dynamic_cast<OTIO_NS::GeneratorReference*>(ref))
@@ -35,17 +83,17 @@ namespace toucan
                 const auto i = parameters.find("size");
                 if (i != parameters.end() && i->second.has_value())
                 {
-                    anyToVec(std::any_cast<OTIO_NS::AnyVector>(i->second), _imageSize);
-                    _imageChannels = 4;
-                    _imageDataType = toImageDataType(TC_U8);
+                    anyToVec(std::any_cast<OTIO_NS::AnyVector>(i->second), d.imageSize);
+                    d.imageChannels = 4;
+                    d.imageDataType = toImageDataType(TC_U8);
                     break;
                 }
             }
-            else if (auto read = _read(ref, false))
+            else if (auto read = d.read(ref, false))
             {
                 if (read->getSpec().width > 0)
                 {
-                    _imageInfo(read);
+                    d.imageInfo(read);
                     break;
                 }
             }
@@ -55,22 +103,22 @@ namespace toucan
     ImageGraph::~ImageGraph()
     {}
 
-    const IMATH_NAMESPACE::V2i& ImageGraph::getImageSize() const { return _imageSize; }
+    const IMATH_NAMESPACE::V2i& ImageGraph::getImageSize() const { return _d->imageSize; }
 
-    int ImageGraph::getImageChannels() const { return _imageChannels; }
+    int ImageGraph::getImageChannels() const { return _d->imageChannels; }
 
-    const std::string& ImageGraph::getImageDataType() const { return _imageDataType; }
+    const std::string& ImageGraph::getImageDataType() const { return _d->imageDataType; }
 
-    void ImageGraph::_imageInfo(const std::shared_ptr<IReadNode>& read)
+    void ImageGraph::Data::imageInfo(const std::shared_ptr<IReadNode>& read)
     {
         const ImageSpec& spec = read->getSpec();
-        _imageSize.x = spec.width;
-        _imageSize.y = spec.height;
-        _imageChannels = spec.nchannels;
-        _imageDataType = toImageDataType(spec.format);
+        imageSize.x = spec.width;
+        imageSize.y = spec.height;
+        imageChannels = spec.nchannels;
+        imageDataType = toImageDataType(spec.format);
     }
 
-    std::shared_ptr<IReadNode> ImageGraph::_read(const OTIO_NS::MediaReference* ref, bool cache)
+    std::shared_ptr<IReadNode> ImageGraph::Data::read(const OTIO_NS::MediaReference* ref, bool cache)
     {
         // External and image-sequence references become read nodes; a reader that cannot be
         // opened is logged and yields no node (the clip then contributes nothing).
@@ -80,23 +128,23 @@ namespace toucan
         {
             return read;
         }
-        if (cache && _readCache.get(ref, read))
+        if (cache && readCache.get(ref, read))
         {
             return read;
         }
         try
         {
-            read = _timelineWrapper->createReadNode(ref);
+            read = timelineWrapper->createReadNode(ref);
             if (cache)
             {
-                _readCache.add(ref, read);
+                readCache.add(ref, read);
             }
         }
         catch (const std::exception& e)
         {
-            if (auto context = _context.lock())
+            if (auto ctx = context.lock())
             {
-                context->getSystem<ftk::LogSystem>()->print(logPrefix, e.what(), ftk::LogType::Error);
+                ctx->getSystem<ftk::LogSystem>()->print(logPrefix, e.what(), ftk::LogType::Error);
             }
         }
         return read;
@@ -107,19 +155,19 @@ namespace toucan
         const OTIO_NS::RationalTime& time,
         const OTIO_NS::Item* itemNode)
     {
-        _host = host;
-        _itemNode = itemNode;
+        Data& d = *_d;
+        Frame frame(d, host, itemNode);
 
         // Background: opaque black at the timeline's size.
         OTIO_NS::AnyDictionary metaData;
-        metaData["size"] = vecToAny(_imageSize);
+        metaData["size"] = vecToAny(d.imageSize);
         metaData["color"] = vecToAny(IMATH_NAMESPACE::V4f(0.F, 0.F, 0.F, 1.F));
         std::shared_ptr<IImageNode> node = host->createNode(metaData, "toucan:Fill");
 
-        auto stack = _timelineWrapper->getTimeline()->tracks();
-        const EffectList& stackEffects = stack->effects();
-        OTIO_NS::RationalTime t = time - _timeRange.start_time();
-        t = _timeWarps(t, stack->available_range(), stackEffects);
+        auto stack = d.timelineWrapper->getTimeline()->tracks();
+        const Frame::EffectList& stackEffects = stack->effects();
+        OTIO_NS::RationalTime t = time - d.timeRange.start_time();
+        t = frame.warpTime(t, stack->available_range(), stackEffects);
 
         // Bottom track first; each video track with clips is composited over what is below.
         for (const auto& child : stack->children())
@@ -129,13 +177,13 @@ namespace toucan
             {
                 continue;
             }
-            const EffectList& trackEffects = track->effects();
+            const Frame::EffectList& trackEffects = track->effects();
             OTIO_NS::RationalTime t2 = t;
             if (!trackEffects.empty())
             {
-                t2 = _timeWarps(t2, track->available_range(), trackEffects);
+                t2 = frame.warpTime(t2, track->available_range(), trackEffects);
             }
-            auto trackNode = _effects(t2, trackEffects, _track(t2, track));
+            auto trackNode = frame.applyEffects(t2, trackEffects, frame.buildTrack(t2, track));
 
             std::vector<std::shared_ptr<IImageNode> > nodes;
             if (trackNode) nodes.push_back(trackNode);
@@ -145,19 +193,13 @@ namespace toucan
             node = comp;
         }
 
-        node = _effects(t, stackEffects, node);
+        node = frame.applyEffects(t, stackEffects, node);
 
-        _host.reset();
-        _itemNode = nullptr;
-        if (_outNode)
-        {
-            node = _outNode;
-        }
-        _outNode.reset();
-        return node;
+        // a caller that asked for one item's output gets that node instead of the stack's
+        return frame.soloNode ? frame.soloNode : node;
     }
 
-    std::shared_ptr<IImageNode> ImageGraph::_transition(
+    std::shared_ptr<IImageNode> ImageGraph::Frame::buildTransition(
         const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Transition>& transition,
         const OTIO_NS::TimeRange& range,
         const OTIO_NS::RationalTime& time,
@@ -168,16 +210,16 @@ namespace toucan
         const double value = (time - range.start_time()).value() / range.duration().value();
         OTIO_NS::AnyDictionary metaData = transition->metadata();
         metaData["value"] = value;
-        auto node = _host->createNode(metaData, transition->transition_type(), { from, to });
+        auto node = host->createNode(metaData, transition->transition_type(), { from, to });
         if (!node)
         {
             // unknown transition types fall back to a dissolve
-            node = _host->createNode(metaData, "toucan:Dissolve", { from, to });
+            node = host->createNode(metaData, "toucan:Dissolve", { from, to });
         }
         return node;
     }
 
-    std::shared_ptr<IImageNode> ImageGraph::_track(
+    std::shared_ptr<IImageNode> ImageGraph::Frame::buildTrack(
         const OTIO_NS::RationalTime& time,
         const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Track>& track)
     {
@@ -198,7 +240,7 @@ namespace toucan
             const auto range = item->trimmed_range_in_parent();
             if (range.has_value() && range.value().contains(time))
             {
-                out = _item(track->transformed_time(time, item), item);
+                out = buildItem(track->transformed_time(time, item), item);
                 index = i;
                 break;
             }
@@ -234,31 +276,31 @@ namespace toucan
             {
                 continue;
             }
-            auto otherNode = _item(track->transformed_time(time, other), other);
+            auto otherNode = buildItem(track->transformed_time(time, other), other);
             out = side < 0 ?
-                _transition(transition, range.value(), time, otherNode, out) :
-                _transition(transition, range.value(), time, out, otherNode);
+                buildTransition(transition, range.value(), time, otherNode, out) :
+                buildTransition(transition, range.value(), time, out, otherNode);
         }
         return out;
     }
 
-    std::shared_ptr<IImageNode> ImageGraph::_item(
+    std::shared_ptr<IImageNode> ImageGraph::Frame::buildItem(
         const OTIO_NS::RationalTime& time,
         const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Item>& item)
     {
         std::shared_ptr<IImageNode> out;
 
         const EffectList& effects = item->effects();
-        OTIO_NS::RationalTime t = _timeWarps(time, item->available_range(), effects);
+        OTIO_NS::RationalTime t = warpTime(time, item->available_range(), effects);
 
         if (auto clip = OTIO_NS::dynamic_retainer_cast<OTIO_NS::Clip>(item))
         {
             OTIO_NS::MediaReference* ref = clip->media_reference();
             if (auto generatorRef = dynamic_cast<OTIO_NS::GeneratorReference*>(ref))
             {
-                out = _host->createNode(generatorRef->parameters(), generatorRef->generator_kind());
+                out = host->createNode(generatorRef->parameters(), generatorRef->generator_kind());
             }
-            else if (auto read = _read(ref, true))
+            else if (auto read = d.read(ref, true))
             {
                 if (dynamic_cast<OTIO_NS::ExternalReference*>(ref) &&
                     clip->available_range().start_time() != read->getTimeRange().start_time())
@@ -274,20 +316,20 @@ namespace toucan
         {
             // a gap is a transparent frame
             OTIO_NS::AnyDictionary metaData;
-            metaData["size"] = vecToAny(_imageSize);
-            out = _host->createNode(metaData, "toucan:Fill");
+            metaData["size"] = vecToAny(d.imageSize);
+            out = host->createNode(metaData, "toucan:Fill");
         }
 
-        out = _effects(t, effects, out);
+        out = applyEffects(t, effects, out);
 
-        if (item.value == _itemNode)
+        if (item.value == soloItem)
         {
-            _outNode = out;
+            soloNode = out;
         }
         return out;
     }
 
-    OTIO_NS::RationalTime ImageGraph::_timeWarps(
+    OTIO_NS::RationalTime ImageGraph::Frame::warpTime(
         const OTIO_NS::RationalTime& time,
         const OTIO_NS::TimeRange& timeRange,
         const EffectList& effects)
@@ -305,7 +347,7 @@ namespace toucan
         return out;
     }
 
-    std::shared_ptr<IImageNode> ImageGraph::_effects(
+    std::shared_ptr<IImageNode> ImageGraph::Frame::applyEffects(
         const OTIO_NS::RationalTime&,
         const EffectList& effects,
         const std::shared_ptr<IImageNode>& input)
@@ -314,7 +356,7 @@ namespace toucan
         for (const auto& effect : effects)
         {
             // effects the host does not know (including "" of a LinearTimeWarp) are skipped
-            if (auto node = _host->createNode(effect->metadata(), effect->effect_name(), { out }))
+            if (auto node = host->createNode(effect->metadata(), effect->effect_name(), { out }))
             {
                 out = node;
             }

@@ -1,6 +1,8 @@
-// Builds the per-frame image graph of a timeline.  Interface parity:
-// lib/toucanRender/ImageGraph.h:21-78 (same public methods; exec() is not re-entrant, use one
-// ImageGraph per render thread).
+// The per-frame image graph of a timeline: exec() turns (timeline, time) into a tree of image nodes whose root
+// renders the frame.  The public interface is the reference's (lib/toucanRender/ImageGraph.h:21-44: same
+// constructor, the three image-info getters, exec with an optional item).  Unlike the reference, exec() keeps its
+// working state on its own stack (ImageGraph.cpp: Frame), so only the read-node cache is shared between calls;
+// use one ImageGraph per render thread all the same.
 #pragma once
 
 #include <toucanRender/ImageNode.h>
@@ -12,80 +14,43 @@
 
 #include <filesystem>
 #include <memory>
+#include <string>
 
 namespace toucan
 {
     class ImageEffectHost;
 
-    //! Create image graphs from a timeline.
     class ImageGraph : public std::enable_shared_from_this<ImageGraph>
     {
     public:
+        //! Reads the first video clip that yields an image description (readable media, or a generator with a
+        //! "size" parameter) to learn the timeline's frame size, channel count and storage type.
         ImageGraph(
             const std::shared_ptr<ftk::Context>&,
             const std::filesystem::path&,
             const std::shared_ptr<TimelineWrapper>&);
-
         ~ImageGraph();
 
-        //! Get the timeline image size.
+        ImageGraph(const ImageGraph&) = delete;
+        ImageGraph& operator=(const ImageGraph&) = delete;
+
+        //! Frame size of the timeline in pixels.
         const IMATH_NAMESPACE::V2i& getImageSize() const;
-
-        //! Get the timeline image channels.
+        //! Channels per pixel of the timeline's frames.
         int getImageChannels() const;
-
-        //! Get the timeline image data type ("u8", "u16", "half", "float").
+        //! Storage type of the timeline's frames: "u8", "u16", "half" or "float".
         const std::string& getImageDataType() const;
 
-        //! Get an image graph for the given time.
+        //! The node tree of the frame at `time`.  With `item`, the returned root is that item's output (after its
+        //! own effects) instead of the composited stack.
         std::shared_ptr<IImageNode> exec(
             const std::shared_ptr<ImageEffectHost>&,
-            const OTIO_NS::RationalTime&,
-            const OTIO_NS::Item* = nullptr);
+            const OTIO_NS::RationalTime& time,
+            const OTIO_NS::Item* item = nullptr);
 
     private:
-        using EffectList = std::vector<OTIO_NS::SerializableObject::Retainer<OTIO_NS::Effect> >;
-
-        std::shared_ptr<IReadNode> _read(const OTIO_NS::MediaReference*, bool cache);
-        void _imageInfo(const std::shared_ptr<IReadNode>&);
-
-        std::shared_ptr<IImageNode> _track(
-            const OTIO_NS::RationalTime&,
-            const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Track>&);
-
-        std::shared_ptr<IImageNode> _item(
-            const OTIO_NS::RationalTime&,
-            const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Item>&);
-
-        std::shared_ptr<IImageNode> _transition(
-            const OTIO_NS::SerializableObject::Retainer<OTIO_NS::Transition>&,
-            const OTIO_NS::TimeRange&,
-            const OTIO_NS::RationalTime&,
-            const std::shared_ptr<IImageNode>& from,
-            const std::shared_ptr<IImageNode>& to);
-
-        OTIO_NS::RationalTime _timeWarps(
-            const OTIO_NS::RationalTime&,
-            const OTIO_NS::TimeRange&,
-            const EffectList&);
-
-        std::shared_ptr<IImageNode> _effects(
-            const OTIO_NS::RationalTime&,
-            const EffectList&,
-            const std::shared_ptr<IImageNode>&);
-
-        std::weak_ptr<ftk::Context> _context;
-        std::filesystem::path _path;
-        std::shared_ptr<TimelineWrapper> _timelineWrapper;
-        OTIO_NS::TimeRange _timeRange;
-        IMATH_NAMESPACE::V2i _imageSize = IMATH_NAMESPACE::V2i(0, 0);
-        int _imageChannels = 0;
-        std::string _imageDataType;
-        ftk::LRUCache<const OTIO_NS::MediaReference*, std::shared_ptr<IReadNode> > _readCache;
-
-        // Temporary variables available during execution.
-        std::shared_ptr<ImageEffectHost> _host;
-        const OTIO_NS::Item* _itemNode = nullptr;
-        std::shared_ptr<IImageNode> _outNode;
+        struct Data;   // timeline facts and the read-node cache
+        class Frame;   // builder of one frame's tree
+        std::unique_ptr<Data> _d;
     };
 }

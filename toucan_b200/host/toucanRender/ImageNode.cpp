@@ -4,9 +4,7 @@
 
 namespace toucan
 {
-    IImageNode::IImageNode(
-        const std::string& name,
-        const std::vector<std::shared_ptr<IImageNode> >& inputs) :
+    IImageNode::IImageNode(const std::string& name, const ImageNodeList& inputs) :
         _name(name),
         _inputs(inputs)
     {}
@@ -18,42 +16,47 @@ namespace toucan
 
     std::string IImageNode::getLabel() const { return _name; }
 
-    const std::vector<std::shared_ptr<IImageNode> >& IImageNode::getInputs() const { return _inputs; }
+    const ImageNodeList& IImageNode::getInputs() const { return _inputs; }
 
-    void IImageNode::setInputs(const std::vector<std::shared_ptr<IImageNode> >& value) { _inputs = value; }
+    void IImageNode::setInputs(const ImageNodeList& value) { _inputs = value; }
 
     void IImageNode::setTime(const OTIO_NS::RationalTime& value) { _time = value; }
 
     const OTIO_NS::RationalTime& IImageNode::getTime() const { return _time; }
+
+    namespace
+    {
+        // Graphviz identifier of a node: its name made unique by its address
+        std::string dotId(const IImageNode& node)
+        {
+            std::stringstream ss;
+            ss << node.getName() << "_" << static_cast<const void*>(&node);
+            return ss.str();
+        }
+
+        // depth-first: a node's own line, then each input's subtree followed by the edge into the node
+        void dotLines(const IImageNode& node, std::vector<std::string>& out)
+        {
+            out.push_back("    " + dotId(node) + " [label=\"" + node.getLabel() + "\"];");
+            for (const auto& input : node.getInputs())
+            {
+                if (input)
+                {
+                    dotLines(*input, out);
+                    out.push_back("    " + dotId(*input) + " -> " + dotId(node) + ";");
+                }
+            }
+        }
+    }
 
     std::vector<std::string> IImageNode::graph(const std::string& name)
     {
         std::vector<std::string> out;
         out.push_back("digraph " + name + " {");
         out.push_back("    node [shape=box, fontsize=12, margin=0.05, width=0, height=0];");
-        _graph(shared_from_this(), out);
+        dotLines(*this, out);
         out.push_back("}");
         return out;
-    }
-
-    void IImageNode::_graph(const std::shared_ptr<IImageNode>& node, std::vector<std::string>& out)
-    {
-        out.push_back("    " + node->_getGraphName() + " [label=\"" + node->getLabel() + "\"];");
-        for (const auto& input : node->_inputs)
-        {
-            if (input)
-            {
-                _graph(input, out);
-                out.push_back("    " + input->_getGraphName() + " -> " + node->_getGraphName() + ";");
-            }
-        }
-    }
-
-    std::string IImageNode::_getGraphName() const
-    {
-        std::stringstream ss;
-        ss << _name << "_" << static_cast<const void*>(this);
-        return ss.str();
     }
 
     std::string IImageNode::describe() const { return getLabel(); }

@@ -1,6 +1,7 @@
-// Base class of the per-frame image graph.  Interface parity: lib/toucanRender/ImageNode.h:18-57
-// -- identical except that exec() returns a device-resident toucan::Image instead of an
-// OIIO::ImageBuf (frames stay in HBM across the whole graph).
+// A node of the per-frame image graph.  The public interface is the reference's IImageNode
+// (lib/toucanRender/ImageNode.h:18-57: name, label, inputs, time, exec, graph) with one change of type:
+// exec() returns a device-resident toucan::Image instead of an OIIO::ImageBuf, so frames stay in HBM
+// across the whole graph and only the writer downloads.
 #pragma once
 
 #include <toucanRender/Image.h>
@@ -14,37 +15,32 @@
 namespace toucan
 {
     class ImageEffectHost;
+    class IImageNode;
 
-    //! Base class for image nodes.
+    using ImageNodeList = std::vector<std::shared_ptr<IImageNode> >;
+
     class IImageNode : public std::enable_shared_from_this<IImageNode>
     {
     public:
-        IImageNode(
-            const std::string& name,
-            const std::vector<std::shared_ptr<IImageNode> >& = {});
-
+        IImageNode(const std::string& name, const ImageNodeList& inputs = {});
         virtual ~IImageNode() = 0;
 
-        //! Get the name.
+        // ---- identity and wiring ----
         const std::string& getName() const;
-
-        //! Get the label.
+        //! What graph() and describe() print for this node; the name unless a subclass adds detail.
         virtual std::string getLabel() const;
+        const ImageNodeList& getInputs() const;
+        void setInputs(const ImageNodeList&);
 
-        //! Get the inputs.
-        const std::vector<std::shared_ptr<IImageNode> >& getInputs() const;
-
-        //! Set the inputs.
-        void setInputs(const std::vector<std::shared_ptr<IImageNode> >&);
-
-        //! Set the time.
+        // ---- the time the node is evaluated at (read nodes pick their frame from it) ----
         void setTime(const OTIO_NS::RationalTime&);
         const OTIO_NS::RationalTime& getTime() const;
 
-        //! Execute the image operation (enqueues kernels on the thread's stream).
+        //! Evaluate the inputs, then this node: enqueues kernels on the calling thread's stream and returns the
+        //! node's output without waiting for them.
         virtual Image exec() = 0;
 
-        //! Generate a Graphviz graph.
+        //! The tree under this node as Graphviz source, one line per element.
         std::vector<std::string> graph(const std::string& name);
 
         //! One line per node, children indented: a stable text form of the tree used by the
@@ -53,11 +49,8 @@ namespace toucan
         void describeTree(std::vector<std::string>&, int depth = 0) const;
 
     protected:
-        void _graph(const std::shared_ptr<IImageNode>&, std::vector<std::string>&);
-        std::string _getGraphName() const;
-
         std::string _name;
-        std::vector<std::shared_ptr<IImageNode> > _inputs;
+        ImageNodeList _inputs;
         OTIO_NS::RationalTime _time;
     };
 }

@@ -162,26 +162,47 @@ namespace toucan
     std::vector<std::string> PropertySet::getDoubleProperties() const { return names(_doubles); }
     std::vector<std::string> PropertySet::getIntProperties() const { return names(_ints); }
 
-#define TOUCAN_PS(handle) reinterpret_cast<PropertySet*>(handle)
-    OfxStatus PropertySet::setPointer(OfxPropertySetHandle h, const char* p, int i, void* v) { return TOUCAN_PS(h)->setPointer(p, i, v); }
-    OfxStatus PropertySet::setString(OfxPropertySetHandle h, const char* p, int i, const char* v) { return TOUCAN_PS(h)->setString(p, i, v); }
-    OfxStatus PropertySet::setDouble(OfxPropertySetHandle h, const char* p, int i, double v) { return TOUCAN_PS(h)->setDouble(p, i, v); }
-    OfxStatus PropertySet::setInt(OfxPropertySetHandle h, const char* p, int i, int v) { return TOUCAN_PS(h)->setInt(p, i, v); }
-    OfxStatus PropertySet::setPointerN(OfxPropertySetHandle h, const char* p, int n, void* const* v) { return TOUCAN_PS(h)->setPointerN(p, n, v); }
-    OfxStatus PropertySet::setStringN(OfxPropertySetHandle h, const char* p, int n, const char* const* v) { return TOUCAN_PS(h)->setStringN(p, n, v); }
-    OfxStatus PropertySet::setDoubleN(OfxPropertySetHandle h, const char* p, int n, const double* v) { return TOUCAN_PS(h)->setDoubleN(p, n, v); }
-    OfxStatus PropertySet::setIntN(OfxPropertySetHandle h, const char* p, int n, const int* v) { return TOUCAN_PS(h)->setIntN(p, n, v); }
-    OfxStatus PropertySet::getPointer(OfxPropertySetHandle h, const char* p, int i, void** v) { return TOUCAN_PS(h)->getPointer(p, i, v); }
-    OfxStatus PropertySet::getString(OfxPropertySetHandle h, const char* p, int i, char** v) { return TOUCAN_PS(h)->getString(p, i, v); }
-    OfxStatus PropertySet::getDouble(OfxPropertySetHandle h, const char* p, int i, double* v) { return TOUCAN_PS(h)->getDouble(p, i, v); }
-    OfxStatus PropertySet::getInt(OfxPropertySetHandle h, const char* p, int i, int* v) { return TOUCAN_PS(h)->getInt(p, i, v); }
-    OfxStatus PropertySet::getPointerN(OfxPropertySetHandle h, const char* p, int n, void** v) { return TOUCAN_PS(h)->getPointerN(p, n, v); }
-    OfxStatus PropertySet::getStringN(OfxPropertySetHandle h, const char* p, int n, char** v) { return TOUCAN_PS(h)->getStringN(p, n, v); }
-    OfxStatus PropertySet::getDoubleN(OfxPropertySetHandle h, const char* p, int n, double* v) { return TOUCAN_PS(h)->getDoubleN(p, n, v); }
-    OfxStatus PropertySet::getIntN(OfxPropertySetHandle h, const char* p, int n, int* v) { return TOUCAN_PS(h)->getIntN(p, n, v); }
-    OfxStatus PropertySet::reset(OfxPropertySetHandle h, const char* p) { return TOUCAN_PS(h)->reset(p); }
-    OfxStatus PropertySet::getDimension(OfxPropertySetHandle h, const char* p, int* n) { return TOUCAN_PS(h)->getDimension(p, n); }
-#undef TOUCAN_PS
+    // The property suite handed to plug-ins: every slot is a thin adaptor from the opaque handle (a PropertySet*) to
+    // the typed tables above.  Eighteen functions, all live (ImageEffectHost.cpp:67-84 of the reference fills the same slots).
+    void fillPropertySuite(OfxPropertySuiteV1& suite)
+    {
+        suite.propSetPointer = [](OfxPropertySetHandle h, const char* name, int index, void* value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setPointer(name, index, value); };
+        suite.propSetString = [](OfxPropertySetHandle h, const char* name, int index, const char* value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setString(name, index, value); };
+        suite.propSetDouble = [](OfxPropertySetHandle h, const char* name, int index, double value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setDouble(name, index, value); };
+        suite.propSetInt = [](OfxPropertySetHandle h, const char* name, int index, int value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setInt(name, index, value); };
+        suite.propSetPointerN = [](OfxPropertySetHandle h, const char* name, int count, void* const* values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setPointerN(name, count, values); };
+        suite.propSetStringN = [](OfxPropertySetHandle h, const char* name, int count, const char* const* values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setStringN(name, count, values); };
+        suite.propSetDoubleN = [](OfxPropertySetHandle h, const char* name, int count, const double* values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setDoubleN(name, count, values); };
+        suite.propSetIntN = [](OfxPropertySetHandle h, const char* name, int count, const int* values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->setIntN(name, count, values); };
+        suite.propGetPointer = [](OfxPropertySetHandle h, const char* name, int index, void** value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getPointer(name, index, value); };
+        suite.propGetString = [](OfxPropertySetHandle h, const char* name, int index, char** value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getString(name, index, value); };
+        suite.propGetDouble = [](OfxPropertySetHandle h, const char* name, int index, double* value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getDouble(name, index, value); };
+        suite.propGetInt = [](OfxPropertySetHandle h, const char* name, int index, int* value) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getInt(name, index, value); };
+        suite.propGetPointerN = [](OfxPropertySetHandle h, const char* name, int count, void** values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getPointerN(name, count, values); };
+        suite.propGetStringN = [](OfxPropertySetHandle h, const char* name, int count, char** values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getStringN(name, count, values); };
+        suite.propGetDoubleN = [](OfxPropertySetHandle h, const char* name, int count, double* values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getDoubleN(name, count, values); };
+        suite.propGetIntN = [](OfxPropertySetHandle h, const char* name, int count, int* values) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getIntN(name, count, values); };
+        suite.propReset = [](OfxPropertySetHandle h, const char* name) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->reset(name); };
+        suite.propGetDimension = [](OfxPropertySetHandle h, const char* name, int* count) -> OfxStatus {
+            return reinterpret_cast<PropertySet*>(h)->getDimension(name, count); };
+    }
 
     PropertySet bufToPropSet(const Image& image)
     {

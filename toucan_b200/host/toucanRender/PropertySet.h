@@ -1,7 +1,8 @@
-// OpenFX property-set storage served to plug-ins through OfxPropertySuiteV1, plus the
-// image -> property-set marshalling of the render call.
-// Interface parity: lib/toucanRender/PropertySet.h:16-72 (same member and static suite
-// functions, same statuses); bufToPropSet: PropertySet.cpp:431-471.
+// OpenFX property storage.  Plug-ins never see this class: they reach it through the C property suite
+// (fillPropertySuite), with a PropertySet* travelling as the opaque OfxPropertySetHandle.  The host side uses the
+// typed accessors directly.  Method names and statuses follow the reference's class of the same name
+// (lib/toucanRender/PropertySet.h:16-72) so host code reads the same; the image marshalling is
+// PropertySet.cpp:431-471 of the reference restated for device images.
 #pragma once
 
 #include <toucanRender/Image.h>
@@ -14,52 +15,39 @@
 
 namespace toucan
 {
-    //! OpenFX properties.
     class PropertySet
     {
     public:
-        OfxStatus setPointer(const char* property, int index, void* value);
-        OfxStatus setString(const char* property, int index, const char* value);
-        OfxStatus setDouble(const char* property, int index, double value);
+        // ---- one value of a property (the array grows to hold `index`) ----
         OfxStatus setInt(const char* property, int index, int value);
-        OfxStatus setPointerN(const char* property, int count, void* const* value);
-        OfxStatus setStringN(const char* property, int count, const char* const* value);
-        OfxStatus setDoubleN(const char* property, int count, const double* value);
-        OfxStatus setIntN(const char* property, int count, const int* value);
-        OfxStatus getPointer(const char* property, int index, void** value) const;
-        OfxStatus getString(const char* property, int index, char** value) const;
-        OfxStatus getDouble(const char* property, int index, double* value) const;
+        OfxStatus setDouble(const char* property, int index, double value);
+        OfxStatus setString(const char* property, int index, const char* value);
+        OfxStatus setPointer(const char* property, int index, void* value);
         OfxStatus getInt(const char* property, int index, int* value) const;
-        OfxStatus getPointerN(const char* property, int count, void** value) const;
-        OfxStatus getStringN(const char* property, int count, char** value) const;
-        OfxStatus getDoubleN(const char* property, int count, double* value) const;
+        OfxStatus getDouble(const char* property, int index, double* value) const;
+        // the returned characters belong to the set and stay valid until the property is written again
+        OfxStatus getString(const char* property, int index, char** value) const;
+        OfxStatus getPointer(const char* property, int index, void** value) const;
+
+        // ---- the first `count` values of a property ----
+        OfxStatus setIntN(const char* property, int count, const int* value);
+        OfxStatus setDoubleN(const char* property, int count, const double* value);
+        OfxStatus setStringN(const char* property, int count, const char* const* value);
+        OfxStatus setPointerN(const char* property, int count, void* const* value);
         OfxStatus getIntN(const char* property, int count, int* value) const;
-        OfxStatus reset(const char* property);
+        OfxStatus getDoubleN(const char* property, int count, double* value) const;
+        OfxStatus getStringN(const char* property, int count, char** value) const;
+        OfxStatus getPointerN(const char* property, int count, void** value) const;
+
+        // ---- whole properties ----
         OfxStatus getDimension(const char* property, int* count) const;
+        OfxStatus reset(const char* property);
 
-        std::vector<std::string> getPointerProperties() const;
-        std::vector<std::string> getStringProperties() const;
-        std::vector<std::string> getDoubleProperties() const;
+        // names present in each typed table (diagnostics, parameter harvesting)
         std::vector<std::string> getIntProperties() const;
-
-        static OfxStatus setPointer(OfxPropertySetHandle, const char* property, int index, void* value);
-        static OfxStatus setString(OfxPropertySetHandle, const char* property, int index, const char* value);
-        static OfxStatus setDouble(OfxPropertySetHandle, const char* property, int index, double value);
-        static OfxStatus setInt(OfxPropertySetHandle, const char* property, int index, int value);
-        static OfxStatus setPointerN(OfxPropertySetHandle, const char* property, int count, void* const* value);
-        static OfxStatus setStringN(OfxPropertySetHandle, const char* property, int count, const char* const* value);
-        static OfxStatus setDoubleN(OfxPropertySetHandle, const char* property, int count, const double* value);
-        static OfxStatus setIntN(OfxPropertySetHandle, const char* property, int count, const int* value);
-        static OfxStatus getPointer(OfxPropertySetHandle, const char* property, int index, void** value);
-        static OfxStatus getString(OfxPropertySetHandle, const char* property, int index, char** value);
-        static OfxStatus getDouble(OfxPropertySetHandle, const char* property, int index, double* value);
-        static OfxStatus getInt(OfxPropertySetHandle, const char* property, int index, int* value);
-        static OfxStatus getPointerN(OfxPropertySetHandle, const char* property, int count, void** value);
-        static OfxStatus getStringN(OfxPropertySetHandle, const char* property, int count, char** value);
-        static OfxStatus getDoubleN(OfxPropertySetHandle, const char* property, int count, double* value);
-        static OfxStatus getIntN(OfxPropertySetHandle, const char* property, int count, int* value);
-        static OfxStatus reset(OfxPropertySetHandle, const char* property);
-        static OfxStatus getDimension(OfxPropertySetHandle, const char* property, int* count);
+        std::vector<std::string> getDoubleProperties() const;
+        std::vector<std::string> getStringProperties() const;
+        std::vector<std::string> getPointerProperties() const;
 
     private:
         template <class T>
@@ -69,6 +57,9 @@ namespace toucan
         Table<double> _doubles;
         Table<int> _ints;
     };
+
+    //! Fill every slot of the OpenFX property suite with adaptors from the opaque handle to PropertySet.
+    void fillPropertySuite(OfxPropertySuiteV1&);
 
     //! Describe a device image to a plug-in: bounds, components, depth, row bytes and the
     //! DEVICE pointer in OfxImagePropData (OpenFX CUDA render convention).

@@ -89,60 +89,62 @@ namespace toucan
 
     IMATH_NAMESPACE::Box2i fit(const IMATH_NAMESPACE::V2i& a, const IMATH_NAMESPACE::V2i& b)
     {
-        // Same arithmetic as the reference (Util.cpp:123-147): double aspect ratios and
-        // truncation to int, because the box decides which pixels the resize writes.
-        const double aAspect = a.y > 0 ? (a.x / static_cast<double>(a.y)) : 1.0;
-        const double bAspect = b.y > 0 ? (b.x / static_cast<double>(b.y)) : 1.0;
-        int w = 0;
-        int h = 0;
-        if (bAspect > aAspect)
+        // The box decides which pixels the fit-resize writes, so the arithmetic is the reference's to the last
+        // truncation (Util.cpp:123-147): width / height ratios in double (1 for an empty box), the side that
+        // touches the frame copied, the other one scaled and truncated toward zero, halves taken before subtracting.
+        auto aspect = [](const IMATH_NAMESPACE::V2i& v) { return v.y > 0 ? v.x / static_cast<double>(v.y) : 1.0; };
+        const double target = aspect(b);
+        const bool fullWidth = target > aspect(a);
+        const int w = fullWidth ? a.x : static_cast<int>(a.y * target);
+        const int h = fullWidth ? static_cast<int>(a.x / target) : a.y;
+        const IMATH_NAMESPACE::V2i origin(a.x / 2 - w / 2, a.y / 2 - h / 2);
+        IMATH_NAMESPACE::Box2i box;
+        box.min = origin;
+        box.max = IMATH_NAMESPACE::V2i(origin.x + w - 1, origin.y + h - 1);
+        return box;
+    }
+
+    namespace
+    {
+        // OTIO stores numbers as int64_t or double and nothing else; any_cast is strict (a JSON real where an
+        // integer is expected throws bad_any_cast, as in the reference)
+        template <class Stored, class Component, int N>
+        OTIO_NS::AnyVector pack(const Component (&c)[N])
         {
-            w = a.x;
-            h = static_cast<int>(w / bAspect);
+            OTIO_NS::AnyVector out;
+            for (const Component& v : c) out.push_back(static_cast<Stored>(v));
+            return out;
         }
-        else
+        template <class Stored, class Component, int N>
+        void unpack(const OTIO_NS::AnyVector& any, Component* const (&c)[N])
         {
-            h = a.y;
-            w = static_cast<int>(h * bAspect);
+            if (any.size() != static_cast<size_t>(N)) return; // any other length leaves the vector as it was
+            for (int i = 0; i < N; ++i) *c[i] = static_cast<Component>(std::any_cast<Stored>(any[static_cast<size_t>(i)]));
         }
-        IMATH_NAMESPACE::Box2i out;
-        out.min.x = a.x / 2 - w / 2;
-        out.min.y = a.y / 2 - h / 2;
-        out.max.x = out.min.x + w - 1;
-        out.max.y = out.min.y + h - 1;
-        return out;
     }
 
     OTIO_NS::AnyVector vecToAny(const IMATH_NAMESPACE::V2i& vec)
     {
-        return OTIO_NS::AnyVector{ static_cast<int64_t>(vec.x), static_cast<int64_t>(vec.y) };
+        const int c[2] = { vec.x, vec.y };
+        return pack<int64_t>(c);
     }
 
     OTIO_NS::AnyVector vecToAny(const IMATH_NAMESPACE::V4f& vec)
     {
-        return OTIO_NS::AnyVector{
-            static_cast<double>(vec.x), static_cast<double>(vec.y), static_cast<double>(vec.z), static_cast<double>(vec.w) };
+        const float c[4] = { vec.x, vec.y, vec.z, vec.w };
+        return pack<double>(c);
     }
 
     void anyToVec(const OTIO_NS::AnyVector& any, IMATH_NAMESPACE::V2i& out)
     {
-        // strict any_cast like the reference: a JSON real in "size" throws bad_any_cast
-        if (2 == any.size())
-        {
-            out.x = static_cast<int>(std::any_cast<int64_t>(any[0]));
-            out.y = static_cast<int>(std::any_cast<int64_t>(any[1]));
-        }
+        int* const c[2] = { &out.x, &out.y };
+        unpack<int64_t>(any, c);
     }
 
     void anyToVec(const OTIO_NS::AnyVector& any, IMATH_NAMESPACE::V4f& out)
     {
-        if (4 == any.size())
-        {
-            out.x = static_cast<float>(std::any_cast<double>(any[0]));
-            out.y = static_cast<float>(std::any_cast<double>(any[1]));
-            out.z = static_cast<float>(std::any_cast<double>(any[2]));
-            out.w = static_cast<float>(std::any_cast<double>(any[3]));
-        }
+        float* const c[4] = { &out.x, &out.y, &out.z, &out.w };
+        unpack<double>(any, c);
     }
 
     std::vector<std::filesystem::path> getOpenFXPluginPaths(const std::filesystem::path& executablePath)

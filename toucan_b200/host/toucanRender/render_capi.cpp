@@ -360,6 +360,15 @@ extern "C"
         });
     }
 
+    void tr_fit(int aw, int ah, int bw, int bh, int out[4])
+    {
+        const IMATH_NAMESPACE::Box2i box = toucan::fit(IMATH_NAMESPACE::V2i(aw, ah), IMATH_NAMESPACE::V2i(bw, bh));
+        out[0] = box.min.x;
+        out[1] = box.min.y;
+        out[2] = box.max.x - box.min.x + 1;
+        out[3] = box.max.y - box.min.y + 1;
+    }
+
     void tr_frame_block(int first, int last, int index, int count, int* lo, int* hi)
     {
         const auto block = frameBlock(first, last, index, count);

@@ -52,7 +52,7 @@ _SIGS["tr_render_range_raw"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.
                                 FRAME_CALLBACK, _VP]
 _SIGS["tr_render_range_y4m"] = _SIGS["tr_render_range_raw"]
 _SIGS["tr_y4m_header"] = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
-EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion", "tr_set_interleave"})
+EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_fit", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion", "tr_set_interleave"})
 
 
 def lib() -> ctypes.CDLL:
@@ -122,6 +122,16 @@ def frame_block(first: int, last: int, index: int, count: int):
     f.restype = None
     f(first, last, index, count, ctypes.byref(lo), ctypes.byref(hi))
     return lo.value, hi.value
+
+
+def fit(a, b):
+    """toucan::fit -- (min x, min y, width, height) of the box a (bw, bh) image is fitted into inside an (aw, ah) frame."""
+    out = (ctypes.c_int * 4)()
+    f = lib().tr_fit
+    f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_int * 4]
+    f.restype = None
+    f(int(a[0]), int(a[1]), int(b[0]), int(b[1]), out)
+    return tuple(out)
 
 
 def decode_png(path: str) -> np.ndarray:
