@@ -113,3 +113,32 @@ def test_host_fit_matches_oracle():
     for a, b in cases:
         assert render.fit(a, b) == tuple(O.fit(a, b)), (a, b)
 
+
+def test_plugins_resolve_parameters_through_the_host_suites(tmp_path):
+    """tests/cpp/chain_probe.cpp: effect nodes created like ImageGraph creates them, then the Render action in
+    pointwise-chain mode -- the plug-ins read their parameters through the host's parameter suite exactly as in a real
+    render (double, string and boolean values, described and effective defaults: SURVEY 8b), no kernel launched."""
+    import subprocess
+
+    from toucan_b200 import build as B
+
+    B.build_all()
+    exe = str(tmp_path / "chain_probe")
+    subprocess.run([B.CXX, "-O1", "-std=c++17", "-I", os.path.join(B.ROOT, "include"), "-I", B.HOST, os.path.join(B.ROOT, "tests", "cpp", "chain_probe.cpp"),
+                    "-o", exe, "-L", B.LIB, "-ltoucan_render", "-ltoucan_cuda", f"-Wl,-rpath,{B.LIB}"], check=True, capture_output=True)
+    out = subprocess.run([exe, os.path.join(B.LIB, "plugins")], check=True, capture_output=True, text=True).stdout
+    lines = [l for l in out.splitlines() if l.startswith("toucan:")]
+    assert lines == [
+        "toucan:Invert 1 1 0 0 0 [] []",
+        "toucan:Pow 1 1 1 2.20000005 0 [] []",
+        "toucan:Pow 1 1 1 1 0 [] []",                                   # described default of "value"
+        "toucan:Saturate 1 1 2 0.25 0 [] []",
+        "toucan:ColorMap 1 1 3 0 0 [plasma] []",
+        "toucan:ColorConvert 1 1 6 0 1 [sRGB - Texture] [ACEScg]",
+        "toucan:ColorConvert 1 1 6 0 0 [] []",                          # effective default of "premult" is 0
+        "toucan:Premult 1 1 4 0 0 [] []",
+        "toucan:Unpremult 1 1 5 0 0 [] []",
+        "toucan:Blur 0 0 -1 0 0 [] []",                                 # not a pointwise effect
+        "toucan:Pow 0 0 -1 0 0 [] []",                                  # output-size override
+    ], out
+

@@ -141,7 +141,8 @@ namespace toucan
         const int window[4] = { 0, 0, 0, 0 };
         args.setIntN(kOfxImageEffectPropRenderWindow, 4, window);
         args.setInt(kOfxImageEffectPropCudaEnabled, 0, 1);
-        args.setPointer(kOfxImageEffectPropCudaStream, 0, DeviceContext::stream());
+        // no kernel is launched in this mode: the stream is passed along if the thread has one, never created for it
+        args.setPointer(kOfxImageEffectPropCudaStream, 0, DeviceContext::isBound() ? DeviceContext::stream() : nullptr);
         args.setPointer("ToucanPropPointwiseChain", 0, &chain);
         _live->images.clear();
         const OfxStatus status = _effect.ofxPlugin->mainEntry(
