@@ -483,3 +483,92 @@ def test_tiff_reader_16_bit_and_float(built, tmp_path):
     Image.fromarray(rng.integers(0, 256, (9, 9), dtype=np.uint8)).save(str(tmp_path / "gray.tif"))
     with pytest.raises(capi.TcError, match="RGB"):
         render.decode_tiff(str(tmp_path / "gray.tif"))
+
+
+def _write_tiled_tiff(path, a, tile, deflate=False, predictor=False):
+    """A minimal little-endian TILED TIFF (Pillow and OpenCV only write strips): RGB / RGBA, 8- or 16-bit unsigned,
+    tiles padded to full size by repeating the edge, optional deflate and horizontal differencing."""
+    import struct
+    import zlib
+
+    h, w, ch = a.shape
+    tw, th = tile
+    bps = a.dtype.itemsize
+    across, down = (w + tw - 1) // tw, (h + th - 1) // th
+    blocks = []
+    for ty in range(down):
+        for tx in range(across):
+            t = a[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw]
+            t = np.pad(t, ((0, th - t.shape[0]), (0, tw - t.shape[1]), (0, 0)), mode="edge")
+            if predictor:
+                d = t.astype(np.int64)
+                d[:, 1:] -= t[:, :-1].astype(np.int64)
+                t = (d % (1 << (8 * bps))).astype(a.dtype)
+            raw = t.astype("<u%d" % bps).tobytes()
+            blocks.append(zlib.compress(raw) if deflate else raw)
+    entries = [(256, 4, [w]), (257, 4, [h]), (258, 3, [8 * bps] * ch), (259, 3, [8 if deflate else 1]), (262, 3, [2]), (277, 3, [ch]),
+               (284, 3, [1]), (317, 3, [2 if predictor else 1]), (322, 4, [tw]), (323, 4, [th]), (324, 4, None), (325, 4, [len(b) for b in blocks]),
+               (339, 3, [1] * ch)]
+    if ch == 4:
+        entries.append((338, 3, [2]))  # unassociated alpha, what Pillow writes for RGBA
+    entries.sort()
+    size = {3: 2, 4: 4}
+    ifd_at = 8
+    extra_at = ifd_at + 2 + 12 * len(entries) + 4
+    extra = b""
+    slots = {}
+    for tag, typ, vals in entries:
+        n = len(blocks) if vals is None else len(vals)
+        if n * size[typ] > 4:
+            slots[tag] = extra_at + len(extra)
+            extra += b"\0" * (n * size[typ] + (n * size[typ]) % 2)
+    data_at = extra_at + len(extra)
+    offsets, at = [], data_at
+    for b in blocks:
+        offsets.append(at)
+        at += len(b) + len(b) % 2
+    out = bytearray(b"II*\0" + struct.pack("<I", ifd_at) + struct.pack("<H", len(entries)))
+    extra = bytearray(extra)
+    for tag, typ, vals in entries:
+        vals = offsets if vals is None else vals
+        packed = b"".join(struct.pack("<H" if typ == 3 else "<I", v) for v in vals)
+        if tag in slots:
+            o = slots[tag] - extra_at
+            extra[o:o + len(packed)] = packed
+            field = struct.pack("<I", slots[tag])
+        else:
+            field = packed.ljust(4, b"\0")
+        out += struct.pack("<HHI", tag, typ, len(vals)) + field
+    out += struct.pack("<I", 0) + extra
+    for b in blocks:
+        out += b + b"\0" * (len(b) % 2)
+    with open(path, "wb") as f:
+        f.write(bytes(out))
+
+
+@pytest.mark.parametrize("size,tile", [((101, 77), (64, 64)), ((64, 64), (64, 64)), ((33, 130), (16, 32)), ((5, 3), (16, 16)), ((300, 40), (128, 16))])
+def test_tiff_reader_tiled(built, tmp_path, size, tile):
+    """Tiled files (TileWidth / TileLength / TileOffsets): uncompressed and deflate tiles, with and without the predictor,
+    8-bit RGB / RGBA and 16-bit RGB, edge tiles padded.  The fixture is checked against Pillow's (libtiff's) decode first."""
+    from toucan_b200 import render
+
+    w, h = size
+    rng = np.random.default_rng(8)
+    for dtype, ch in ((np.uint8, 3), (np.uint8, 4), (np.uint16, 3)):
+        a = rng.integers(0, 256 if dtype == np.uint8 else 65536, (h, w, ch)).astype(dtype)
+        for deflate in (False, True):
+            for predictor in ((False, True) if deflate else (False,)):  # libtiff applies the predictor inside LZW / deflate only
+                path = str(tmp_path / "tiled.tif")
+                _write_tiled_tiff(path, a, tile, deflate, predictor)
+                if dtype == np.uint8:  # Pillow has no 16-bit RGB mode: OpenCV's libtiff checks those
+                    assert np.array_equal(np.asarray(Image.open(path)), a), ("fixture", size, tile, ch, deflate, predictor)
+                else:
+                    cv2 = pytest.importorskip("cv2")
+                    assert np.array_equal(cv2.imread(path, cv2.IMREAD_UNCHANGED)[..., ::-1], a), ("fixture", size, tile, ch, deflate, predictor)
+                if ch == 3:
+                    want = np.concatenate([a, np.full((h, w, 1), np.iinfo(dtype).max, dtype)], -1)
+                else:
+                    want = _associate_u8(a)
+                got = render.decode_tiff(path)
+                assert got.dtype == dtype and np.array_equal(got, want), (size, tile, dtype, ch, deflate, predictor)
+

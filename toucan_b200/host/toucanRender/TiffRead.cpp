@@ -201,7 +201,6 @@ namespace toucan
         const int predictor = static_cast<int>(get(317, 1));
         const int sampleFormat = static_cast<int>(get(339, 1));
         if (width <= 0 || height <= 0 || width > 65536 || height > 65536) bad("bad image size");
-        if (tags.count(322)) bad("tiled files are not supported");
         if (photometric != 2 || (samples != 3 && samples != 4)) bad("only RGB / RGBA images are supported (the effects take RGBA)");
         for (int c = 1; c < samples; ++c)
         {
@@ -216,69 +215,106 @@ namespace toucan
 
         const size_t bps = static_cast<size_t>(bits / 8);
         const size_t lineBytes = static_cast<size_t>(width) * samples * bps;
-        const uint32_t rowsPerStrip = std::min<uint32_t>(get(278, static_cast<uint32_t>(height)), static_cast<uint32_t>(height));
-        const auto offsets = tags.find(273), counts = tags.find(279);
-        if (offsets == tags.end() || counts == tags.end() || 0 == rowsPerStrip) bad("missing strips");
-        const uint32_t strips = (static_cast<uint32_t>(height) + rowsPerStrip - 1) / rowsPerStrip;
-        if (offsets->second.count < strips || counts->second.count < strips) bad("missing strips");
-
         std::vector<unsigned char> pix(lineBytes * static_cast<size_t>(height));
         std::vector<unsigned char> tmp;
-        for (uint32_t s = 0; s < strips; ++s)
+        // one compressed block (a strip or a tile) -> `expected` bytes at dst
+        auto decode = [&](size_t at, size_t len, unsigned char* dst, size_t expected)
         {
-            const size_t at = value(f, offsets->second, s), len = value(f, counts->second, s);
             f.need(at, len);
-            const size_t row0 = static_cast<size_t>(s) * rowsPerStrip;
-            const size_t rows = std::min<size_t>(rowsPerStrip, static_cast<size_t>(height) - row0);
-            const size_t expected = rows * lineBytes;
-            unsigned char* dst = &pix[row0 * lineBytes];
             switch (compression)
             {
             case 1:
-                if (len < expected) bad("short strip");
+                if (len < expected) bad("short block");
                 memcpy(dst, data + at, expected);
                 break;
             case 5:
                 lzw(data + at, len, tmp, expected);
-                if (tmp.size() < expected) bad("short LZW strip");
+                if (tmp.size() < expected) bad("short LZW block");
                 memcpy(dst, tmp.data(), expected);
                 break;
             case 8: case 32946:
             {
                 uLongf got = static_cast<uLongf>(expected);
-                if (uncompress(dst, &got, data + at, static_cast<uLong>(len)) != Z_OK || got != expected) bad("bad deflate strip");
+                if (uncompress(dst, &got, data + at, static_cast<uLong>(len)) != Z_OK || got != expected) bad("bad deflate block");
                 break;
             }
             case 32773:
                 packBits(data + at, len, tmp, expected);
-                if (tmp.size() < expected) bad("short PackBits strip");
+                if (tmp.size() < expected) bad("short PackBits block");
                 memcpy(dst, tmp.data(), expected);
                 break;
             default: bad("only uncompressed, LZW, deflate and PackBits files are supported");
             }
-            // horizontal differencing: per row, per sample, in the file's byte order
-            if (2 == predictor)
+        };
+        // horizontal differencing: per row of the block, per sample, in the file's byte order
+        auto undoPredictor = [&](unsigned char* block, size_t rows, size_t rowPixels)
+        {
+            // libtiff runs the predictor inside its LZW and deflate codecs only: with any other scheme the tag is inert
+            if (predictor != 2 || !(5 == compression || 8 == compression || 32946 == compression)) return;
+            const size_t rowBytes = rowPixels * samples * bps;
+            for (size_t r = 0; r < rows; ++r)
             {
-                for (size_t r = 0; r < rows; ++r)
+                unsigned char* line = block + r * rowBytes;
+                if (8 == bits)
                 {
-                    unsigned char* line = dst + r * lineBytes;
-                    if (8 == bits)
+                    for (size_t i = static_cast<size_t>(samples); i < rowBytes; ++i) line[i] = static_cast<unsigned char>(line[i] + line[i - samples]);
+                }
+                else
+                {
+                    for (size_t i = static_cast<size_t>(samples); i < rowPixels * samples; ++i)
                     {
-                        for (size_t i = static_cast<size_t>(samples); i < lineBytes; ++i) line[i] = static_cast<unsigned char>(line[i] + line[i - samples]);
-                    }
-                    else
-                    {
-                        for (size_t i = static_cast<size_t>(samples); i < static_cast<size_t>(width) * samples; ++i)
-                        {
-                            unsigned char* a = line + i * 2;
-                            const unsigned char* b = line + (i - samples) * 2;
-                            const unsigned va = f.big ? (a[0] << 8 | a[1]) : (a[0] | a[1] << 8), vb = f.big ? (b[0] << 8 | b[1]) : (b[0] | b[1] << 8);
-                            const unsigned v = (va + vb) & 0xffffu;
-                            if (f.big) { a[0] = static_cast<unsigned char>(v >> 8); a[1] = static_cast<unsigned char>(v); }
-                            else { a[0] = static_cast<unsigned char>(v); a[1] = static_cast<unsigned char>(v >> 8); }
-                        }
+                        unsigned char* a = line + i * 2;
+                        const unsigned char* b = line + (i - samples) * 2;
+                        const unsigned va = f.big ? (a[0] << 8 | a[1]) : (a[0] | a[1] << 8), vb = f.big ? (b[0] << 8 | b[1]) : (b[0] | b[1] << 8);
+                        const unsigned v = (va + vb) & 0xffffu;
+                        if (f.big) { a[0] = static_cast<unsigned char>(v >> 8); a[1] = static_cast<unsigned char>(v); }
+                        else { a[0] = static_cast<unsigned char>(v); a[1] = static_cast<unsigned char>(v >> 8); }
                     }
                 }
+            }
+        };
+
+        if (tags.count(322))
+        {
+            // Tiles: TileWidth x TileLength blocks in row-major order, every one stored at full size (the right and bottom
+            // edges are padded); the predictor runs along a tile's own rows.
+            const uint32_t tw = get(322, 0), th = get(323, 0);
+            const auto offsets = tags.find(324), counts = tags.find(325);
+            if (0 == tw || 0 == th || tw > 65536 || th > 65536 || offsets == tags.end() || counts == tags.end()) bad("missing tiles");
+            const uint32_t across = (static_cast<uint32_t>(width) + tw - 1) / tw, down = (static_cast<uint32_t>(height) + th - 1) / th;
+            if (offsets->second.count < across * down || counts->second.count < across * down) bad("missing tiles");
+            const size_t tileRowBytes = static_cast<size_t>(tw) * samples * bps;
+            std::vector<unsigned char> tile(tileRowBytes * th);
+            for (uint32_t ty = 0; ty < down; ++ty)
+            {
+                for (uint32_t tx = 0; tx < across; ++tx)
+                {
+                    const uint32_t t = ty * across + tx;
+                    decode(value(f, offsets->second, t), value(f, counts->second, t), tile.data(), tile.size());
+                    undoPredictor(tile.data(), th, tw);
+                    const size_t x0 = static_cast<size_t>(tx) * tw, y0 = static_cast<size_t>(ty) * th;
+                    const size_t cols = std::min<size_t>(tw, static_cast<size_t>(width) - x0), rows = std::min<size_t>(th, static_cast<size_t>(height) - y0);
+                    for (size_t r = 0; r < rows; ++r)
+                    {
+                        memcpy(&pix[(y0 + r) * lineBytes + x0 * samples * bps], &tile[r * tileRowBytes], cols * samples * bps);
+                    }
+                }
+            }
+        }
+        else
+        {
+            const uint32_t rowsPerStrip = std::min<uint32_t>(get(278, static_cast<uint32_t>(height)), static_cast<uint32_t>(height));
+            const auto offsets = tags.find(273), counts = tags.find(279);
+            if (offsets == tags.end() || counts == tags.end() || 0 == rowsPerStrip) bad("missing strips");
+            const uint32_t strips = (static_cast<uint32_t>(height) + rowsPerStrip - 1) / rowsPerStrip;
+            if (offsets->second.count < strips || counts->second.count < strips) bad("missing strips");
+            for (uint32_t s = 0; s < strips; ++s)
+            {
+                const size_t row0 = static_cast<size_t>(s) * rowsPerStrip;
+                const size_t rows = std::min<size_t>(rowsPerStrip, static_cast<size_t>(height) - row0);
+                unsigned char* dst = &pix[row0 * lineBytes];
+                decode(value(f, offsets->second, s), value(f, counts->second, s), dst, rows * lineBytes);
+                undoPredictor(dst, rows, static_cast<size_t>(width));
             }
         }
 
