@@ -3,7 +3,7 @@
 Run in the authoring container:
     python tests/golden/make_exr_golden.py
 
-Writes tests/golden/exr/*.exr (seeded 37x37 frames: half / float samples, RGB / RGBA, compression NONE / RLE / ZIPS / ZIP / PIZ)
+Writes tests/golden/exr/*.exr (seeded 37x37 frames: half / float samples, RGB / RGBA, compression NONE / RLE / ZIPS / ZIP / PIZ / PXR24)
 and tests/golden/exr/expected.npz with the pixels OpenCV's OpenEXR reader returns for each file (RGBA order, float32).
 """
 import os
@@ -36,6 +36,20 @@ def main():
                 b = cv2.imread(os.path.join(OUT, name), cv2.IMREAD_UNCHANGED)
                 rgba = b[..., [2, 1, 0, 3]] if nch == 4 else np.concatenate([b[..., ::-1], np.ones((h, w, 1), np.float32)], -1)
                 expected[name] = np.ascontiguousarray(rgba.astype(np.float32))
+    # PXR24 (zlib over byte planes of per-channel differences; float samples keep 24 bits, half samples are exact): its own
+    # generator so the files above stay what they were
+    rng24 = np.random.default_rng(78)
+    for tname, t in TYPES.items():
+        for nch in (3, 4):
+            a = (rng24.random((h, w, nch), dtype=np.float32) * 3.0 - 1.0).astype(np.float32)
+            a[:4, :6] = 0.25
+            name = f"{tname}_pxr24_{'rgba' if nch == 4 else 'rgb'}.exr"
+            bgr = a[..., [2, 1, 0, 3]] if nch == 4 else a[..., ::-1]
+            assert cv2.imwrite(os.path.join(OUT, name), np.ascontiguousarray(bgr), [cv2.IMWRITE_EXR_TYPE, t, cv2.IMWRITE_EXR_COMPRESSION,
+                                                                                     cv2.IMWRITE_EXR_COMPRESSION_PXR24])
+            b = cv2.imread(os.path.join(OUT, name), cv2.IMREAD_UNCHANGED)
+            rgba = b[..., [2, 1, 0, 3]] if nch == 4 else np.concatenate([b[..., ::-1], np.ones((h, w, 1), np.float32)], -1)
+            expected[name] = np.ascontiguousarray(rgba.astype(np.float32))
     # a lossy DWAA file: a compression the reader must refuse
     a = rng.random((h, w, 3), dtype=np.float32)
     assert cv2.imwrite(os.path.join(OUT, "refused_dwaa_rgb.exr"), a, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF, cv2.IMWRITE_EXR_COMPRESSION,

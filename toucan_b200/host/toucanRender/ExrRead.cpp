@@ -357,6 +357,60 @@ namespace toucan
             }
         }
 
+        // One PXR24 chunk -> the uncompressed scanline layout.  The chunk is a zlib stream of byte PLANES: for every line and
+        // channel, the most significant bytes of all samples, then the next bytes, ...; a sample is the running sum of the
+        // differences those bytes spell (OpenEXR ImfPxr24Compressor).  HALF samples are whole (2 planes), FLOAT samples were
+        // rounded to 24 bits by the writer (3 planes, low byte zero), UINT samples have 4 planes.
+        void unpxr24(const unsigned char* in, size_t inSize, const std::vector<Channel>& channels, int width, int lines, std::vector<unsigned char>& planes,
+                     std::vector<unsigned char>& out)
+        {
+            size_t planeBytes = 0, outBytes = 0;
+            for (const Channel& c : channels)
+            {
+                planeBytes += size_t(width) * (1 == c.type ? 2 : (2 == c.type ? 3 : 4));
+                outBytes += size_t(width) * (1 == c.type ? 2 : 4);
+            }
+            planeBytes *= size_t(lines);
+            planes.resize(planeBytes);
+            uLongf n = static_cast<uLongf>(planeBytes);
+            if (uncompress(planes.data(), &n, in, static_cast<uLong>(inSize)) != Z_OK || n != planeBytes) bad("bad PXR24 data");
+            out.resize(outBytes * size_t(lines));
+            const unsigned char* p = planes.data();
+            unsigned char* w = out.data();
+            for (int l = 0; l < lines; ++l)
+            {
+                for (const Channel& c : channels)
+                {
+                    const size_t count = size_t(width);
+                    uint32_t value = 0;
+                    if (1 == c.type)
+                    {
+                        for (size_t j = 0; j < count; ++j)
+                        {
+                            value += (uint32_t(p[j]) << 8) | uint32_t(p[count + j]);
+                            w[0] = static_cast<unsigned char>(value);
+                            w[1] = static_cast<unsigned char>(value >> 8);
+                            w += 2;
+                        }
+                        p += 2 * count;
+                    }
+                    else
+                    {
+                        const int nPlanes = 2 == c.type ? 3 : 4;
+                        for (size_t j = 0; j < count; ++j)
+                        {
+                            uint32_t diff = (uint32_t(p[j]) << 24) | (uint32_t(p[count + j]) << 16) | (uint32_t(p[2 * count + j]) << 8);
+                            if (4 == nPlanes) diff |= uint32_t(p[3 * count + j]);
+                            value += diff;
+                            for (int k = 0; k < 4; ++k) w[k] = static_cast<unsigned char>(value >> (8 * k));
+                            w += 4;
+                        }
+                        p += size_t(nPlanes) * count;
+                    }
+                }
+            }
+        }
+
         // One PIZ chunk -> the uncompressed scanline layout (per line: each channel's samples, little-endian)
         void unpiz(const unsigned char* in, size_t inSize, const std::vector<Channel>& channels, int width, int lines, std::vector<unsigned char>& out)
         {
@@ -511,7 +565,8 @@ namespace toucan
         case 0: case 1: case 2: linesPerChunk = 1; break; // none, RLE, ZIPS
         case 3: linesPerChunk = 16; break;                 // ZIP
         case 4: linesPerChunk = 32; break;                 // PIZ
-        default: bad("only uncompressed, RLE, ZIPS, ZIP and PIZ files are supported (PXR24, B44, DWA are not)");
+        case 5: linesPerChunk = 16; break;                 // PXR24
+        default: bad("only uncompressed, RLE, ZIPS, ZIP, PIZ and PXR24 files are supported (B44, DWA are not)");
         }
 
         // scanline layout: channels in file (alphabetical) order, each `width` samples
@@ -622,6 +677,12 @@ namespace toucan
                             if (raw.size() != expected) bad("bad PIZ chunk");
                             src = raw.data();
                         }
+                        else if (5 == compression)
+                        {
+                            unpxr24(src, packed, channels, width, lines, tmp, raw);
+                            if (raw.size() != expected) bad("bad PXR24 chunk");
+                            src = raw.data();
+                        }
                         else if (1 == compression)
                         {
                             unrle(src, packed, tmp, expected);
@@ -636,7 +697,7 @@ namespace toucan
                         {
                             bad("bad chunk size");
                         }
-                        if (compression != 4)
+                        if (compression != 4 && compression != 5)
                         {
                             unpredict(tmp, raw);
                             src = raw.data();

@@ -1,7 +1,7 @@
 // OpenEXR reader for the read nodes (ingest): the half / float stills and sequences a
 // VFX timeline is made of.  The reference reads them through OpenImageIO -> OpenEXR
 // (lib/toucanRender/Read.cpp:34-101,164-216); this reader covers the common scanline case --
-// single-part, R/G/B[/A] channels of type HALF or FLOAT, compression NONE, RLE, ZIPS, ZIP or PIZ -- and
+// single-part, R/G/B[/A] channels of type HALF or FLOAT, compression NONE, RLE, ZIPS, ZIP, PIZ or PXR24 -- and
 // yields what OIIO's read_image yields for it: the data window, RGBA order, the widest channel type as
 // the frame's type, A = 1 when the file has no alpha (Read.cpp:86-94).  Lossless formats: every sample
 // is the file's sample (pinned against OpenEXR through OpenCV in tests/test_ingest.py).  Tiled, deep,
