@@ -572,3 +572,82 @@ def test_tiff_reader_tiled(built, tmp_path, size, tile):
                 got = render.decode_tiff(path)
                 assert got.dtype == dtype and np.array_equal(got, want), (size, tile, dtype, ch, deflate, predictor)
 
+
+def _write_tiled_exr(path, rgba, tile, dtype, zip_tiles, mode=0):
+    """A minimal single-part TILED OpenEXR file (OpenCV only writes scanline files): channels A, B, G, R of type HALF or
+    FLOAT, level mode ONE_LEVEL (0) or MIPMAP_LEVELS (1: only the full-resolution level is stored first, which is all a
+    level-0 reader needs -- OpenEXR itself wants the other levels, so that variant is not shown to it), tiles clipped at
+    the right / bottom edge, stored raw or ZIP-compressed (byte split + predictor + zlib, kept only when smaller)."""
+    import struct
+    import zlib
+
+    h, w, nch = rgba.shape
+    tw, th = tile
+    names = ["A", "B", "G", "R"] if nch == 4 else ["B", "G", "R"]
+    plane = {"R": 0, "G": 1, "B": 2, "A": 3}
+    px = 1 if dtype == np.float16 else 2
+
+    def attr(name, typ, payload):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<I", len(payload)) + payload
+
+    chlist = b"".join(n.encode() + b"\0" + struct.pack("<iBBBBii", px, 0, 0, 0, 0, 1, 1) for n in names) + b"\0"
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    header = struct.pack("<II", 20000630, 2 | 0x200)
+    header += attr("channels", "chlist", chlist) + attr("compression", "compression", bytes([3 if zip_tiles else 0]))
+    header += attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0")
+    header += attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + attr("screenWindowCenter", "v2f", struct.pack("<ff", 0.0, 0.0))
+    header += attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + attr("tiles", "tiledesc", struct.pack("<IIB", tw, th, mode)) + b"\0"
+    nx, ny = (w + tw - 1) // tw, (h + th - 1) // th
+    chunks = []
+    for ty in range(ny):
+        for tx in range(nx):
+            t = rgba[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw]
+            raw = b"".join(np.ascontiguousarray(t[l, :, plane[n]]).astype(dtype).tobytes() for l in range(t.shape[0]) for n in names)
+            data = raw
+            if zip_tiles:
+                b = np.frombuffer(raw, np.uint8)
+                split = np.concatenate([b[0::2], b[1::2]]).astype(np.int32)
+                pred = split.copy()
+                pred[1:] = (split[1:] - split[:-1] + 128 + 256) % 256
+                z = zlib.compress(pred.astype(np.uint8).tobytes())
+                data = z if len(z) < len(raw) else raw
+            chunks.append(struct.pack("<iiiii", tx, ty, 0, 0, len(data)) + data)
+    table_at = len(header)
+    at = table_at + 8 * len(chunks)
+    table = b""
+    for c in chunks:
+        table += struct.pack("<Q", at)
+        at += len(c)
+    with open(path, "wb") as f:
+        f.write(header + table + b"".join(chunks))
+
+
+@pytest.mark.parametrize("size,tile", [((37, 37), (16, 16)), ((64, 32), (64, 32)), ((70, 9), (32, 32)), ((5, 50), (8, 16))])
+def test_exr_reader_tiled(built, tmp_path, size, tile):
+    """Tiled single-part files: half / float, RGB / RGBA, raw and ZIP tiles, edge tiles clipped; the ONE_LEVEL fixtures are
+    shown to the OpenEXR library (through OpenCV) first, and a MIPMAP_LEVELS file is read at its full-resolution level."""
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    cv2 = pytest.importorskip("cv2")
+    from toucan_b200 import render
+
+    w, h = size
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    for dtype in (np.float16, np.float32):
+        for nch in (3, 4):
+            # smooth ramps with a flat patch (so that ZIP tiles really shrink) plus negative and > 1 values
+            a = np.stack([xx / w * 2.5 - 0.5, yy / h, (xx + yy) / (w + h) * 1.5, np.clip(xx / w, 0, 1)][:nch], -1).astype(np.float32)
+            a[: h // 2, : w // 2] = 0.25
+            a = a.astype(dtype).astype(np.float32)  # what the file will hold
+            for zip_tiles in (False, True):
+                path = str(tmp_path / "tiled.exr")
+                _write_tiled_exr(path, a, tile, dtype, zip_tiles)
+                ref = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+                if ref is not None:  # OpenCV built with its OpenEXR codec
+                    ref = ref[..., [2, 1, 0, 3]] if nch == 4 else ref[..., ::-1]
+                    assert np.array_equal(ref.astype(np.float32), a), ("fixture", size, tile, dtype, nch, zip_tiles)
+                want = a if nch == 4 else np.concatenate([a, np.ones((h, w, 1), np.float32)], -1)
+                got = render.decode_exr(path)
+                assert got.dtype == dtype and np.array_equal(got.astype(np.float32), want), (size, tile, dtype, nch, zip_tiles)
+                _write_tiled_exr(path, a, tile, dtype, zip_tiles, mode=1)
+                assert np.array_equal(render.decode_exr(path).astype(np.float32), want), ("mipmap level 0", size, tile, dtype, nch, zip_tiles)
+

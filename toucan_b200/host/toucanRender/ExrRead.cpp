@@ -513,11 +513,13 @@ namespace toucan
         if (r.u32() != 20000630u) bad("not an OpenEXR file");
         const uint32_t version = r.u32();
         if ((version & 0xffu) != 2) bad("unsupported file version");
-        if (version & 0x1a00u) bad("tiled, deep and multi-part files are not supported"); // 0x200 tiled, 0x800 deep, 0x1000 multipart
+        if (version & 0x1800u) bad("deep and multi-part files are not supported"); // 0x800 deep, 0x1000 multipart
+        const bool tiled = (version & 0x200u) != 0;
 
         std::vector<Channel> channels;
         int compression = 0;
         int dw[4] = { 0, 0, -1, -1 };
+        uint32_t tileW = 0, tileH = 0;
         bool haveChannels = false, haveWindow = false;
         for (;;)
         {
@@ -548,6 +550,13 @@ namespace toucan
             else if ("compression" == name)
             {
                 compression = data[r.pos];
+            }
+            else if ("tiles" == name && "tiledesc" == type)
+            {
+                // x size, y size, then level mode | rounding mode << 4: every mode stores the full-resolution level first,
+                // which is the only one read here
+                tileW = r.u32();
+                tileH = r.u32();
             }
             else if ("dataWindow" == name && "box2i" == type)
             {
@@ -590,7 +599,11 @@ namespace toucan
             if (c && 2 == c->type) asFloat = true;
         }
 
-        const int chunks = (height + linesPerChunk - 1) / linesPerChunk;
+        if (tiled && (0 == tileW || 0 == tileH || tileW > 65536 || tileH > 65536)) bad("missing tile description");
+        const int tilesX = tiled ? (width + static_cast<int>(tileW) - 1) / static_cast<int>(tileW) : 1;
+        const int tilesY = tiled ? (height + static_cast<int>(tileH) - 1) / static_cast<int>(tileH) : 1;
+        // scanline files: blocks of linesPerChunk lines; tiled files: the tiles of level 0 (first in the offset table)
+        const int chunks = tiled ? tilesX * tilesY : (height + linesPerChunk - 1) / linesPerChunk;
         std::vector<uint64_t> offsets(static_cast<size_t>(chunks));
         for (uint64_t& o : offsets) o = r.u64();
 
@@ -599,7 +612,8 @@ namespace toucan
         std::shared_ptr<unsigned char> pixels(new unsigned char[static_cast<size_t>(width) * height * pixelBytes], std::default_delete<unsigned char[]>());
 
         // one planar scanline -> interleaved RGBA; typed loops the compiler can keep in registers
-        auto interleave = [&](const unsigned char* line, unsigned char* dst)
+        // (`width` below is the number of samples per channel in this line: the frame's width, or a tile's)
+        auto interleave = [&, frameWidth = width](const unsigned char* line, unsigned char* dst, int width)
         {
             for (int ch = 0; ch < 4; ++ch)
             {
@@ -613,7 +627,7 @@ namespace toucan
                     }
                     else if (2 == cn->type)
                     {
-                        const unsigned char* in = line + cn->offset;
+                        const unsigned char* in = line + cn->offset / static_cast<size_t>(frameWidth) * static_cast<size_t>(width);
                         for (int x = 0; x < width; ++x)
                         {
                             float v;
@@ -623,7 +637,7 @@ namespace toucan
                     }
                     else
                     {
-                        const unsigned char* in = line + cn->offset;
+                        const unsigned char* in = line + cn->offset / static_cast<size_t>(frameWidth) * static_cast<size_t>(width);
                         for (int x = 0; x < width; ++x)
                         {
                             uint16_t hv;
@@ -641,7 +655,7 @@ namespace toucan
                     }
                     else
                     {
-                        const unsigned char* in = line + cn->offset;
+                        const unsigned char* in = line + cn->offset / static_cast<size_t>(frameWidth) * static_cast<size_t>(width);
                         for (int x = 0; x < width; ++x)
                         {
                             uint16_t hv;
@@ -662,24 +676,38 @@ namespace toucan
                 for (int k = first; k < chunks; k += step)
                 {
                     Reader c{ data, size, static_cast<size_t>(offsets[static_cast<size_t>(k)]) };
-                    const int y0 = c.i32() - dw[1];
+                    int x0 = 0, y0 = 0, cols = width, lines = 0;
+                    if (tiled)
+                    {
+                        const int tx = c.i32(), ty = c.i32(), lx = c.i32(), ly = c.i32();
+                        if (tx < 0 || tx >= tilesX || ty < 0 || ty >= tilesY || lx != 0 || ly != 0) bad("bad tile");
+                        x0 = tx * static_cast<int>(tileW);
+                        y0 = ty * static_cast<int>(tileH);
+                        cols = std::min(static_cast<int>(tileW), width - x0); // edge tiles are clipped, not padded
+                        lines = std::min(static_cast<int>(tileH), height - y0);
+                    }
+                    else
+                    {
+                        y0 = c.i32() - dw[1];
+                        if (y0 < 0 || y0 >= height) bad("bad chunk");
+                        lines = std::min(linesPerChunk, height - y0);
+                    }
                     const uint32_t packed = c.u32();
                     c.need(packed);
-                    if (y0 < 0 || y0 >= height) bad("bad chunk");
-                    const int lines = std::min(linesPerChunk, height - y0);
-                    const size_t expected = lineBytes * static_cast<size_t>(lines);
+                    const size_t blockLineBytes = lineBytes / static_cast<size_t>(width) * static_cast<size_t>(cols);
+                    const size_t expected = blockLineBytes * static_cast<size_t>(lines);
                     const unsigned char* src = data + c.pos;
                     if (packed < expected)
                     {
                         if (4 == compression)
                         {
-                            unpiz(src, packed, channels, width, lines, raw);
+                            unpiz(src, packed, channels, cols, lines, raw);
                             if (raw.size() != expected) bad("bad PIZ chunk");
                             src = raw.data();
                         }
                         else if (5 == compression)
                         {
-                            unpxr24(src, packed, channels, width, lines, tmp, raw);
+                            unpxr24(src, packed, channels, cols, lines, tmp, raw);
                             if (raw.size() != expected) bad("bad PXR24 chunk");
                             src = raw.data();
                         }
@@ -710,7 +738,8 @@ namespace toucan
                     // (a chunk that did not shrink is stored as it is)
                     for (int l = 0; l < lines; ++l)
                     {
-                        interleave(src + lineBytes * static_cast<size_t>(l), pixels.get() + (static_cast<size_t>(y0 + l) * width) * pixelBytes);
+                        interleave(src + blockLineBytes * static_cast<size_t>(l),
+                                   pixels.get() + (static_cast<size_t>(y0 + l) * width + static_cast<size_t>(x0)) * pixelBytes, cols);
                     }
                 }
             }

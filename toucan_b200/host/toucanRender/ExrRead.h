@@ -1,11 +1,11 @@
 // OpenEXR reader for the read nodes (ingest): the half / float stills and sequences a
 // VFX timeline is made of.  The reference reads them through OpenImageIO -> OpenEXR
-// (lib/toucanRender/Read.cpp:34-101,164-216); this reader covers the common scanline case --
-// single-part, R/G/B[/A] channels of type HALF or FLOAT, compression NONE, RLE, ZIPS, ZIP, PIZ or PXR24 -- and
-// yields what OIIO's read_image yields for it: the data window, RGBA order, the widest channel type as
-// the frame's type, A = 1 when the file has no alpha (Read.cpp:86-94).  Lossless formats: every sample
-// is the file's sample (pinned against OpenEXR through OpenCV in tests/test_ingest.py).  Tiled, deep,
-// multi-part and PXR24 / B44 / DWA files throw (the read node then yields no image, like a
+// (lib/toucanRender/Read.cpp:34-101,164-216); this reader covers single-part scanline files and the
+// full-resolution level of single-part tiled files -- R/G/B[/A] channels of type HALF or FLOAT, compression NONE,
+// RLE, ZIPS, ZIP, PIZ or PXR24 -- and yields what OIIO's read_image yields for them: the data window, RGBA order, the
+// widest channel type as the frame's type, A = 1 when the file has no alpha (Read.cpp:86-94).  Every sample is the
+// file's sample (pinned against OpenEXR through OpenCV in tests/test_ingest.py; PXR24 keeps 24 bits of a float
+// sample by design).  Deep, multi-part and B44 / DWA files throw (the read node then yields no image, like a
 // file OIIO cannot open).
 #pragma once
 
