@@ -651,3 +651,68 @@ def test_exr_reader_tiled(built, tmp_path, size, tile):
                 _write_tiled_exr(path, a, tile, dtype, zip_tiles, mode=1)
                 assert np.array_equal(render.decode_exr(path).astype(np.float32), want), ("mipmap level 0", size, tile, dtype, nch, zip_tiles)
 
+
+def _write_png(path, a, interlaced, filter_type=0):
+    """A PNG written by hand (Pillow and OpenCV do not write Adam7): 8- or 16-bit RGB / RGBA, every row with the given
+    filter type (0 None, 1 Sub, 2 Up), optionally Adam7-interlaced (seven separately filtered sub-images)."""
+    import struct
+    import zlib
+
+    h, w, ch = a.shape
+    depth = 8 * a.dtype.itemsize
+    big = a.astype(">u%d" % a.dtype.itemsize)
+
+    def rows(img):
+        out = b""
+        prev = np.zeros(img.shape[1] * ch * a.dtype.itemsize, np.uint8)
+        bpp = ch * a.dtype.itemsize
+        for r in img:
+            cur = np.frombuffer(r.tobytes(), np.uint8)
+            if filter_type == 1:
+                left = np.concatenate([np.zeros(bpp, np.uint8), cur[:-bpp]])
+                enc = (cur.astype(np.int32) - left) % 256
+            elif filter_type == 2:
+                enc = (cur.astype(np.int32) - prev) % 256
+            else:
+                enc = cur
+            out += bytes([filter_type]) + enc.astype(np.uint8).tobytes()
+            prev = cur
+        return out
+
+    if interlaced:
+        passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]
+        raw = b"".join(rows(big[y0::dy, x0::dx]) for x0, y0, dx, dy in passes if big[y0::dy, x0::dx].size)
+    else:
+        raw = rows(big)
+
+    def chunk(kind, payload):
+        return struct.pack(">I", len(payload)) + kind + payload + struct.pack(">I", zlib.crc32(kind + payload))
+
+    ihdr = struct.pack(">IIBBBBB", w, h, depth, 6 if ch == 4 else 2, 0, 0, 1 if interlaced else 0)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+@pytest.mark.parametrize("size", [(1, 1), (3, 2), (8, 8), (9, 17), (67, 41)])
+def test_png_reader_interlaced_and_filters(built, tmp_path, size):
+    """Adam7-interlaced and plain files, filter types None / Sub / Up, 8-bit RGB / RGBA (checked against Pillow's decode
+    of the same file, alpha associated like OIIO's reader) and 16-bit RGB."""
+    from tests import media
+    from toucan_b200 import render
+
+    w, h = size
+    rng = np.random.default_rng(12)
+    for dtype, ch in ((np.uint8, 3), (np.uint8, 4), (np.uint16, 3)):
+        a = rng.integers(0, 256 if dtype == np.uint8 else 65536, (h, w, ch)).astype(dtype)
+        for interlaced in (False, True):
+            for ft in (0, 1, 2):
+                path = str(tmp_path / f"p_{np.dtype(dtype).name}_{ch}_{int(interlaced)}_{ft}.png")
+                _write_png(path, a, interlaced, ft)
+                if dtype == np.uint8:
+                    assert np.array_equal(np.asarray(Image.open(path)), a), ("fixture", size, ch, interlaced, ft)
+                    want = media.decode(path)
+                else:
+                    want = np.concatenate([a, np.full((h, w, 1), 65535, np.uint16)], -1)
+                got = render.decode_png(path)
+                assert got.dtype == dtype and np.array_equal(got, want), (size, dtype, ch, interlaced, ft)
+

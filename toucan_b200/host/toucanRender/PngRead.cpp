@@ -84,7 +84,7 @@ namespace toucan
             else if (!memcmp(type, "IEND", 4)) break;
             pos += 12 + len;
         }
-        if (!width || !height || interlace != 0) return false;
+        if (!width || !height || interlace > 1) return false;
         int channels = 0;
         switch (colorType)
         {
@@ -96,34 +96,74 @@ namespace toucan
         if (!(depth == 8 || (depth == 16 && colorType != 3))) return false;
         const size_t bpp = static_cast<size_t>(channels) * depth / 8;
         const size_t stride = bpp * width;
-        std::vector<unsigned char> raw((stride + 1) * height);
+
+        // The image is one filtered sub-image, or -- Adam7 interlace -- seven of them, each covering the pixels
+        // (x0 + i dx, y0 + j dy) and filtered on its own; empty passes (narrow images) are not stored at all.
+        struct Pass { uint32_t x0, y0, dx, dy; };
+        static const Pass adam7[7] = { { 0, 0, 8, 8 }, { 4, 0, 8, 8 }, { 0, 4, 4, 8 }, { 2, 0, 4, 4 }, { 0, 2, 2, 4 }, { 1, 0, 2, 2 }, { 0, 1, 1, 2 } };
+        static const Pass whole = { 0, 0, 1, 1 };
+        const Pass* passes = interlace ? adam7 : &whole;
+        const int nPasses = interlace ? 7 : 1;
+        size_t rawBytes = 0;
+        for (int k = 0; k < nPasses; ++k)
+        {
+            const Pass& ps = passes[k];
+            const size_t pw = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0, ph = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
+            if (pw && ph) rawBytes += (pw * bpp + 1) * ph;
+        }
+        std::vector<unsigned char> raw(rawBytes);
         uLongf rawLen = static_cast<uLongf>(raw.size());
         if (uncompress(raw.data(), &rawLen, idat.data(), static_cast<uLong>(idat.size())) != Z_OK || rawLen != raw.size()) return false;
 
-        // undo the scanline filters in place
         std::vector<unsigned char> pix(stride * height);
-        for (uint32_t y = 0; y < height; ++y)
+        std::vector<unsigned char> sub; // a pass's unfiltered rows (interlaced files only)
+        const unsigned char* in = raw.data();
+        for (int k = 0; k < nPasses; ++k)
         {
-            const unsigned char* in = &raw[(stride + 1) * y];
-            const int ft = in[0];
-            ++in;
-            unsigned char* cur = &pix[stride * y];
-            const unsigned char* up = y ? &pix[stride * (y - 1)] : nullptr;
-            for (size_t i = 0; i < stride; ++i)
+            const Pass& ps = passes[k];
+            const size_t pw = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0, ph = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
+            if (!pw || !ph) continue;
+            const size_t pstride = pw * bpp;
+            unsigned char* rows = pix.data();
+            if (interlace)
             {
-                const int a = i >= bpp ? cur[i - bpp] : 0;
-                const int b = up ? up[i] : 0;
-                const int c = (up && i >= bpp) ? up[i - bpp] : 0;
-                int v = in[i];
-                switch (ft)
+                sub.resize(pstride * ph);
+                rows = sub.data();
+            }
+            // undo the scanline filters
+            for (size_t y = 0; y < ph; ++y)
+            {
+                const int ft = in[0];
+                ++in;
+                unsigned char* cur = rows + pstride * y;
+                const unsigned char* up = y ? rows + pstride * (y - 1) : nullptr;
+                for (size_t i = 0; i < pstride; ++i)
                 {
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) / 2; break;
-                case 4: v += paeth(a, b, c); break;
-                default: break;
+                    const int a = i >= bpp ? cur[i - bpp] : 0;
+                    const int b = up ? up[i] : 0;
+                    const int c = (up && i >= bpp) ? up[i - bpp] : 0;
+                    int v = in[i];
+                    switch (ft)
+                    {
+                    case 1: v += a; break;
+                    case 2: v += b; break;
+                    case 3: v += (a + b) / 2; break;
+                    case 4: v += paeth(a, b, c); break;
+                    default: break;
+                    }
+                    cur[i] = static_cast<unsigned char>(v);
                 }
-                cur[i] = static_cast<unsigned char>(v);
+                in += pstride;
+            }
+            if (interlace)
+            {
+                for (size_t y = 0; y < ph; ++y)
+                {
+                    for (size_t x = 0; x < pw; ++x)
+                    {
+                        memcpy(&pix[(ps.y0 + y * ps.dy) * stride + (ps.x0 + x * ps.dx) * bpp], &sub[y * pstride + x * bpp], bpp);
+                    }
+                }
             }
         }
 
