@@ -65,6 +65,7 @@ namespace toucan
         {
             std::string name;
             int type = 1; // 0 uint, 1 half, 2 float
+            bool pLinear = false; // "perceptually linear" hint: B44 then codes the samples through a log table
             size_t offset = 0; // byte offset of this channel's samples inside one scanline
         };
 
@@ -411,6 +412,96 @@ namespace toucan
             }
         }
 
+        // One B44 / B44A chunk -> the uncompressed scanline layout.  HALF channels are coded in 4 x 4 blocks of 14 bytes
+        // (the first sample, then 6-bit differences down the first column and along the rows, all shifted by a common
+        // amount) or, B44A only, 3 bytes for a block of one value; FLOAT and UINT channels are stored as they are.  The
+        // chunk holds one channel after the other, each as a plane of `lines` rows (OpenEXR ImfB44Compressor).  Fixed
+        // rate and lossy at the writer; decoding is exact.
+        void unb44(const unsigned char* in, size_t inSize, const std::vector<Channel>& channels, int width, int lines, std::vector<unsigned char>& out)
+        {
+            const size_t nx = size_t(width), ny = size_t(lines);
+            std::vector<std::vector<uint16_t> > planes(channels.size());
+            const unsigned char* p = in;
+            const unsigned char* const end = in + inSize;
+            auto ordered = [](uint16_t v) -> uint16_t { return (v & 0x8000u) ? uint16_t(v & 0x7fffu) : uint16_t(~v); };
+            for (size_t ci = 0; ci < channels.size(); ++ci)
+            {
+                const Channel& c = channels[ci];
+                std::vector<uint16_t>& plane = planes[ci];
+                if (c.type != 1)
+                {
+                    const size_t bytes = nx * ny * 4;
+                    if (size_t(end - p) < bytes) bad("truncated B44 data");
+                    plane.resize(nx * ny * 2);
+                    memcpy(plane.data(), p, bytes);
+                    p += bytes;
+                    continue;
+                }
+                if (c.pLinear) bad("B44 channels flagged perceptually linear are not supported");
+                plane.resize(nx * ny);
+                for (size_t y = 0; y < ny; y += 4)
+                {
+                    for (size_t x = 0; x < nx; x += 4)
+                    {
+                        uint16_t s[16];
+                        if (end - p < 3) bad("truncated B44 data");
+                        if (0xfc == p[2])
+                        {
+                            const uint16_t v = ordered(uint16_t((p[0] << 8) | p[1]));
+                            for (uint16_t& e : s) e = v;
+                            p += 3;
+                        }
+                        else
+                        {
+                            if (end - p < 14) bad("truncated B44 data");
+                            const unsigned shift = p[2] >> 2;
+                            const unsigned bias = 0x20u << shift;
+                            // six-bit fields, most significant bit first, starting at bit 6 of byte 2
+                            auto field = [&](int k) -> unsigned
+                            {
+                                const int bit = 22 + 6 * k; // bit offset from the start of the block
+                                const int at = bit >> 3; // a field spans at most two of the block's 14 bytes
+                                const unsigned w16 = (unsigned(p[at]) << 8) | unsigned(at + 1 < 14 ? p[at + 1] : 0);
+                                return (w16 >> (10 - (bit & 7))) & 0x3fu;
+                            };
+                            uint16_t t[16];
+                            t[0] = uint16_t((p[0] << 8) | p[1]);
+                            // column 0 downwards (fields 0-2), then each further column from the one on its left
+                            t[4] = uint16_t(t[0] + (field(0) << shift) - bias);
+                            t[8] = uint16_t(t[4] + (field(1) << shift) - bias);
+                            t[12] = uint16_t(t[8] + (field(2) << shift) - bias);
+                            for (int col = 1; col < 4; ++col)
+                            {
+                                for (int row = 0; row < 4; ++row)
+                                {
+                                    t[row * 4 + col] = uint16_t(t[row * 4 + col - 1] + (field(3 + (col - 1) * 4 + row) << shift) - bias);
+                                }
+                            }
+                            for (int i = 0; i < 16; ++i) s[i] = ordered(t[i]);
+                            p += 14;
+                        }
+                        for (size_t j = 0; j < 4 && y + j < ny; ++j)
+                        {
+                            for (size_t i = 0; i < 4 && x + i < nx; ++i) plane[(y + j) * nx + x + i] = s[j * 4 + i];
+                        }
+                    }
+                }
+            }
+            size_t lineBytes = 0;
+            for (const Channel& c : channels) lineBytes += nx * (1 == c.type ? 2 : 4);
+            out.resize(lineBytes * ny);
+            unsigned char* w = out.data();
+            for (size_t y = 0; y < ny; ++y)
+            {
+                for (size_t ci = 0; ci < channels.size(); ++ci)
+                {
+                    const size_t halves = nx * (1 == channels[ci].type ? 1 : 2);
+                    memcpy(w, planes[ci].data() + y * halves, halves * 2);
+                    w += halves * 2;
+                }
+            }
+        }
+
         // One PIZ chunk -> the uncompressed scanline layout (per line: each channel's samples, little-endian)
         void unpiz(const unsigned char* in, size_t inSize, const std::vector<Channel>& channels, int width, int lines, std::vector<unsigned char>& out)
         {
@@ -539,6 +630,7 @@ namespace toucan
                     c.name = ch;
                     c.type = r.i32();
                     r.need(4);
+                    c.pLinear = data[r.pos] != 0;
                     r.pos += 4; // pLinear + reserved
                     const int xs = r.i32(), ys = r.i32();
                     if (xs != 1 || ys != 1) bad("sub-sampled channels are not supported");
@@ -575,7 +667,8 @@ namespace toucan
         case 3: linesPerChunk = 16; break;                 // ZIP
         case 4: linesPerChunk = 32; break;                 // PIZ
         case 5: linesPerChunk = 16; break;                 // PXR24
-        default: bad("only uncompressed, RLE, ZIPS, ZIP, PIZ and PXR24 files are supported (B44, DWA are not)");
+        case 6: case 7: linesPerChunk = 32; break;         // B44, B44A
+        default: bad("only uncompressed, RLE, ZIPS, ZIP, PIZ, PXR24 and B44 files are supported (DWA is not)");
         }
 
         // scanline layout: channels in file (alphabetical) order, each `width` samples
@@ -705,6 +798,12 @@ namespace toucan
                             if (raw.size() != expected) bad("bad PIZ chunk");
                             src = raw.data();
                         }
+                        else if (6 == compression || 7 == compression)
+                        {
+                            unb44(src, packed, channels, cols, lines, raw);
+                            if (raw.size() != expected) bad("bad B44 chunk");
+                            src = raw.data();
+                        }
                         else if (5 == compression)
                         {
                             unpxr24(src, packed, channels, cols, lines, tmp, raw);
@@ -725,7 +824,7 @@ namespace toucan
                         {
                             bad("bad chunk size");
                         }
-                        if (compression != 4 && compression != 5)
+                        if (compression < 4)
                         {
                             unpredict(tmp, raw);
                             src = raw.data();
