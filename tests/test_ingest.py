@@ -716,3 +716,28 @@ def test_png_reader_interlaced_and_filters(built, tmp_path, size):
                 got = render.decode_png(path)
                 assert got.dtype == dtype and np.array_equal(got, want), (size, dtype, ch, interlaced, ft)
 
+
+@pytest.mark.parametrize("colors,bits", [(2, 1), (4, 2), (16, 4), (200, 8)])
+def test_png_reader_palette_depths(built, tmp_path, colors, bits):
+    """Palette files with 1, 2, 4 and 8 bits per index (Pillow writes them), with and without a tRNS chunk, at widths that
+    do not fill the last byte of a row -- against Pillow's decode with OIIO's alpha association."""
+    from tests import media
+    from toucan_b200 import render
+
+    rng = np.random.default_rng(13)
+    for w, h in ((1, 1), (7, 5), (33, 9)):
+        idx = rng.integers(0, colors, (h, w)).astype(np.uint8)
+        pal = rng.integers(0, 256, (colors, 3)).astype(np.uint8)
+        for transparent in (False, True):
+            im = Image.fromarray(idx, mode="P")
+            im.putpalette(pal.reshape(-1).tolist())
+            path = str(tmp_path / f"pal_{w}_{int(transparent)}.png")
+            kw = {"bits": bits}
+            if transparent:
+                kw["transparency"] = bytes(rng.integers(0, 256, colors).astype(np.uint8))
+            im.save(path, **kw)
+            chk = Image.open(path)
+            assert chk.mode == "P"
+            got = render.decode_png(path)
+            assert got.dtype == np.uint8 and np.array_equal(got, media.decode(path)), (colors, bits, w, h, transparent)
+

@@ -93,9 +93,11 @@ namespace toucan
         case 3: channels = 1; break;
         default: return false; // grey images are 1-channel in the reference: outside the RGBA path
         }
-        if (!(depth == 8 || (depth == 16 && colorType != 3))) return false;
-        const size_t bpp = static_cast<size_t>(channels) * depth / 8;
+        const bool packed = 3 == colorType && (1 == depth || 2 == depth || 4 == depth); // several palette indices per byte
+        if (!(depth == 8 || (depth == 16 && colorType != 3) || packed)) return false;
+        const size_t bpp = packed ? 1 : static_cast<size_t>(channels) * depth / 8; // bytes per pixel in `pix`, and the filters' pixel distance
         const size_t stride = bpp * width;
+        auto rowBytes = [&](size_t pixels) { return packed ? (pixels * static_cast<size_t>(depth) + 7) / 8 : pixels * bpp; };
 
         // The image is one filtered sub-image, or -- Adam7 interlace -- seven of them, each covering the pixels
         // (x0 + i dx, y0 + j dy) and filtered on its own; empty passes (narrow images) are not stored at all.
@@ -109,7 +111,7 @@ namespace toucan
         {
             const Pass& ps = passes[k];
             const size_t pw = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0, ph = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
-            if (pw && ph) rawBytes += (pw * bpp + 1) * ph;
+            if (pw && ph) rawBytes += (rowBytes(pw) + 1) * ph;
         }
         std::vector<unsigned char> raw(rawBytes);
         uLongf rawLen = static_cast<uLongf>(raw.size());
@@ -123,9 +125,10 @@ namespace toucan
             const Pass& ps = passes[k];
             const size_t pw = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0, ph = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
             if (!pw || !ph) continue;
-            const size_t pstride = pw * bpp;
+            const size_t pstride = rowBytes(pw);
             unsigned char* rows = pix.data();
-            if (interlace)
+            const bool scatter = interlace || packed; // the pass is unfiltered on its own, then its pixels are placed
+            if (scatter)
             {
                 sub.resize(pstride * ph);
                 rows = sub.data();
@@ -155,13 +158,23 @@ namespace toucan
                 }
                 in += pstride;
             }
-            if (interlace)
+            if (scatter)
             {
                 for (size_t y = 0; y < ph; ++y)
                 {
                     for (size_t x = 0; x < pw; ++x)
                     {
-                        memcpy(&pix[(ps.y0 + y * ps.dy) * stride + (ps.x0 + x * ps.dx) * bpp], &sub[y * pstride + x * bpp], bpp);
+                        unsigned char* dst = &pix[(ps.y0 + y * ps.dy) * stride + (ps.x0 + x * ps.dx) * bpp];
+                        if (packed)
+                        {
+                            // indices are packed most significant bits first
+                            const size_t bit = x * static_cast<size_t>(depth);
+                            *dst = static_cast<unsigned char>((sub[y * pstride + (bit >> 3)] >> (8 - depth - static_cast<int>(bit & 7))) & ((1 << depth) - 1));
+                        }
+                        else
+                        {
+                            memcpy(dst, &sub[y * pstride + x * bpp], bpp);
+                        }
                     }
                 }
             }
@@ -172,7 +185,7 @@ namespace toucan
         out.width = static_cast<int>(width);
         out.height = static_cast<int>(height);
         out.nchannels = 4;
-        if (depth == 8)
+        if (depth <= 8)
         {
             out.format = TC_U8;
             out.owned = std::make_shared<std::vector<unsigned char> >(count * 4);
