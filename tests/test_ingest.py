@@ -741,3 +741,37 @@ def test_png_reader_palette_depths(built, tmp_path, colors, bits):
             got = render.decode_png(path)
             assert got.dtype == np.uint8 and np.array_equal(got, media.decode(path)), (colors, bits, w, h, transparent)
 
+
+def test_readers_survive_damaged_files(built, tmp_path):
+    """tests/cpp/reader_fuzz.cpp under AddressSanitizer + UBSan: every EXR / PNG / JPEG fixture plus tiled, interlaced and
+    palette files written here, each decoded whole, truncated and with random bytes flipped.  A reader may refuse a damaged
+    file (false / an exception); it may not read or write out of bounds, overflow or allocate what a header merely claims."""
+    import glob
+    import subprocess
+
+    from toucan_b200 import build as B
+
+    rng = np.random.default_rng(0)
+    u8 = rng.integers(0, 256, (37, 41, 3)).astype(np.uint8)
+    f32 = rng.random((37, 41, 4)).astype(np.float32)
+    files = sorted(glob.glob(os.path.join(EXR_DIR, "*.exr"))) + sorted(glob.glob(os.path.join(TL.DATA, "*.png"))) + sorted(glob.glob(os.path.join(TL.DATA, "*.jpg")))
+    for dt, z in ((np.float16, False), (np.float32, True)):
+        files.append(str(tmp_path / f"tiled_{np.dtype(dt).name}.exr"))
+        _write_tiled_exr(files[-1], f32.astype(dt).astype(np.float32), (16, 16), dt, z)
+    for deflate, predictor in ((False, False), (True, True)):
+        files.append(str(tmp_path / f"tiled_{int(deflate)}.tif"))
+        _write_tiled_tiff(files[-1], u8, (16, 16), deflate, predictor)
+    files.append(str(tmp_path / "lzw.tif"))
+    Image.fromarray(u8).save(files[-1], compression="tiff_lzw", tiffinfo={317: 2})
+    files.append(str(tmp_path / "adam7.png"))
+    _write_png(files[-1], u8, True, 1)
+    exe = str(tmp_path / "reader_fuzz")
+    src = [os.path.join(B.ROOT, "tests", "cpp", "reader_fuzz.cpp")] + [os.path.join(B.HOST, "toucanRender", f) for f in
+                                                                        ("ExrRead.cpp", "TiffRead.cpp", "PngRead.cpp", "JpegRead.cpp")]
+    r = subprocess.run([B.CXX, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-I", os.path.join(B.ROOT, "include"),
+                        "-I", B.HOST] + src + ["-o", exe, "-lz", "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no sanitizer runtime for " + B.CXX)
+    r = subprocess.run([exe, "60"] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "decoded" in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+

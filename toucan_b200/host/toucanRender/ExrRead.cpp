@@ -454,8 +454,10 @@ namespace toucan
                         else
                         {
                             if (end - p < 14) bad("truncated B44 data");
+                            // (a damaged block can name a shift of up to 62: 64-bit arithmetic keeps that defined, the
+                            // 16-bit results wrap exactly as they would for a valid one)
                             const unsigned shift = p[2] >> 2;
-                            const unsigned bias = 0x20u << shift;
+                            const uint64_t bias = uint64_t(0x20) << shift;
                             // six-bit fields, most significant bit first, starting at bit 6 of byte 2
                             auto field = [&](int k) -> unsigned
                             {
@@ -467,14 +469,14 @@ namespace toucan
                             uint16_t t[16];
                             t[0] = uint16_t((p[0] << 8) | p[1]);
                             // column 0 downwards (fields 0-2), then each further column from the one on its left
-                            t[4] = uint16_t(t[0] + (field(0) << shift) - bias);
-                            t[8] = uint16_t(t[4] + (field(1) << shift) - bias);
-                            t[12] = uint16_t(t[8] + (field(2) << shift) - bias);
+                            t[4] = uint16_t(t[0] + (uint64_t(field(0)) << shift) - bias);
+                            t[8] = uint16_t(t[4] + (uint64_t(field(1)) << shift) - bias);
+                            t[12] = uint16_t(t[8] + (uint64_t(field(2)) << shift) - bias);
                             for (int col = 1; col < 4; ++col)
                             {
                                 for (int row = 0; row < 4; ++row)
                                 {
-                                    t[row * 4 + col] = uint16_t(t[row * 4 + col - 1] + (field(3 + (col - 1) * 4 + row) << shift) - bias);
+                                    t[row * 4 + col] = uint16_t(t[row * 4 + col - 1] + (uint64_t(field(3 + (col - 1) * 4 + row)) << shift) - bias);
                                 }
                             }
                             for (int i = 0; i < 16; ++i) s[i] = ordered(t[i]);

@@ -84,7 +84,7 @@ namespace toucan
             else if (!memcmp(type, "IEND", 4)) break;
             pos += 12 + len;
         }
-        if (!width || !height || interlace > 1) return false;
+        if (!width || !height || width > 65536 || height > 65536 || interlace > 1) return false;
         int channels = 0;
         switch (colorType)
         {
@@ -113,6 +113,8 @@ namespace toucan
             const size_t pw = width > ps.x0 ? (width - ps.x0 + ps.dx - 1) / ps.dx : 0, ph = height > ps.y0 ? (height - ps.y0 + ps.dy - 1) / ps.dy : 0;
             if (pw && ph) rawBytes += (rowBytes(pw) + 1) * ph;
         }
+        // deflate cannot expand by more than ~1032:1: a header that promises more than the data can hold is damaged
+        if (rawBytes / 1032 > idat.size() + 1) return false;
         std::vector<unsigned char> raw(rawBytes);
         uLongf rawLen = static_cast<uLongf>(raw.size());
         if (uncompress(raw.data(), &rawLen, idat.data(), static_cast<uLong>(idat.size())) != Z_OK || rawLen != raw.size()) return false;
