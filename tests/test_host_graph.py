@@ -142,3 +142,35 @@ def test_plugins_resolve_parameters_through_the_host_suites(tmp_path):
         "toucan:Pow 0 0 -1 0 0 [] []",                                  # output-size override
     ], out
 
+
+def test_timeline_documents_survive_damage(tmp_path):
+    """tests/cpp/otio_fuzz.cpp under AddressSanitizer + UBSan: every fixture timeline (and a .otioz bundle) parsed whole,
+    truncated and with random bytes flipped, plus documents nested 300 000 levels deep -- refused, never a crash."""
+    import glob
+    import subprocess
+
+    from tests.test_ingest import make_otioz
+    from toucan_b200 import build as B
+
+    files = sorted(glob.glob(os.path.join(TL.DATA, "*.otio")))
+    bundle = str(tmp_path / "t.otioz")
+    make_otioz(bundle, "Transition.otio")
+    deep = [str(tmp_path / "deep_array.otio"), str(tmp_path / "deep_object.otio")]
+    with open(deep[0], "w") as f:
+        f.write("[" * 300000)
+    with open(deep[1], "w") as f:
+        f.write('{"a":' * 200000)
+    exe = str(tmp_path / "otio_fuzz")
+    src = [os.path.join(B.ROOT, "tests", "cpp", "otio_fuzz.cpp"), os.path.join(B.HOST, "toucanRender", "otio.cpp"), os.path.join(B.HOST, "toucanRender", "Archive.cpp")]
+    r = subprocess.run([B.CXX, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-I", os.path.join(B.ROOT, "include"),
+                        "-I", B.HOST] + src + ["-o", exe, "-lz", "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no sanitizer runtime for " + B.CXX)
+    r = subprocess.run([exe, "300", str(tmp_path / "mutated.otioz")] + files + [bundle] + deep, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "parsed" in r.stdout, (r.stdout[-300:], r.stderr[-3000:])
+    # and through the public API: a hopeless document is an error, not a crash
+    from toucan_b200 import capi, render
+
+    with pytest.raises(capi.TcError):
+        render.Timeline(json_doc=None, path=deep[0])
+

@@ -18,6 +18,8 @@ struct Parser {
     const char* p;
     const char* end;
     std::string err;
+    int depth = 0; // containers open at the cursor: bounded, because the parser recurses once per level
+    static constexpr int maxDepth = 512;
 
     void ws()
     {
@@ -33,8 +35,14 @@ struct Parser {
         ws();
         if (p >= end) return fail("unexpected end of input");
         switch (*p) {
-        case '{': return object(out);
-        case '[': return array(out);
+        case '{':
+        case '[': {
+            if (depth >= maxDepth) return fail("nesting deeper than 512 levels");
+            ++depth;
+            const bool ok = '{' == *p ? object(out) : array(out);
+            --depth;
+            return ok;
+        }
         case '"': {
             std::string s;
             if (!string(s)) return false;
