@@ -106,6 +106,12 @@ void tr_fit(int aw, int ah, int bw, int bh, int out[4]);
    A = 1 appended to RGB, alpha associated on read like OIIO's reader).  out may be NULL to
    query the size. */
 int tr_decode_png(const char* path, void* out, size_t capacity, int* width, int* height, int* type);
+/* Reader option = OpenImageIO's "oiio:UnassociatedAlpha" open hint: keep != 0 leaves the unassociated alpha of PNG / TIFF
+   files as stored; 0 (the default, what the reference gets by opening its media with no hints, Read.cpp:39) multiplies colour
+   by alpha on read.  The reference's own film strips of the transition timelines were rendered with unassociated frames
+   (INTEGRATION.md "PNG alpha").  Process-wide; also TOUCAN_UNASSOCIATED_ALPHA=1 and `toucan-render -unassociated_alpha`. */
+void tr_set_unassociated_alpha(int keep);
+int tr_get_unassociated_alpha(void);
 /* The built-in JPEG reader (baseline / extended / progressive Huffman, 8-bit YCbCr or RGB, 1x-2x sampling):
    libjpeg's defaults -- islow IDCT, fancy upsampling, integer colour tables -- bit for bit, RGBA out with
    A = 255 (Read.cpp:86-94).  Same calling convention as tr_decode_png. */

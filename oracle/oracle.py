@@ -31,7 +31,8 @@ class _OImg(ctypes.Structure):
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "toucan_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    inc = os.path.join(_HERE, "colormap_tables.inc")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(inc)):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 

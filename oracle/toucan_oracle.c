@@ -346,52 +346,11 @@ void o_saturate(oimg* dst, const oimg* src, float scale)
         }
 }
 
-/* Colour-map knot tables [V: OIIO imagebufalgo_pixelmath.cpp color_map].  Restated
-   from the published tables (samples of the matplotlib maps, 6 decimals). */
-static const float k_magma[] = {
-    0.001462f, 0.000466f, 0.013866f, 0.039608f, 0.031090f, 0.133515f, 0.113094f, 0.065492f, 0.276784f,
-    0.211718f, 0.061992f, 0.418647f, 0.316654f, 0.071690f, 0.485380f, 0.414709f, 0.110431f, 0.504662f,
-    0.512831f, 0.148179f, 0.507648f, 0.613617f, 0.181811f, 0.498536f, 0.716387f, 0.214982f, 0.475290f,
-    0.816914f, 0.255895f, 0.436461f, 0.904281f, 0.319610f, 0.388137f, 0.960949f, 0.418323f, 0.359630f,
-    0.986700f, 0.535582f, 0.382210f, 0.996096f, 0.653659f, 0.446213f, 0.996898f, 0.769591f, 0.534892f,
-    0.992440f, 0.884330f, 0.640099f, 0.987053f, 0.991438f, 0.749504f
-};
-static const float k_inferno[] = {
-    0.001462f, 0.000466f, 0.013866f, 0.046915f, 0.030324f, 0.150164f, 0.142378f, 0.046242f, 0.308553f,
-    0.258234f, 0.038571f, 0.406485f, 0.366529f, 0.071579f, 0.431994f, 0.472328f, 0.110547f, 0.428334f,
-    0.578304f, 0.148039f, 0.404411f, 0.682656f, 0.189501f, 0.360757f, 0.780517f, 0.243327f, 0.299523f,
-    0.865006f, 0.316822f, 0.226055f, 0.929644f, 0.411479f, 0.145367f, 0.970919f, 0.522853f, 0.058367f,
-    0.987622f, 0.645320f, 0.039886f, 0.978806f, 0.774545f, 0.176037f, 0.950018f, 0.903409f, 0.380271f,
-    0.988362f, 0.998364f, 0.644924f
-};
-static const float k_plasma[] = {
-    0.050383f, 0.029803f, 0.527975f, 0.186213f, 0.018803f, 0.587228f, 0.287076f, 0.010855f, 0.627295f,
-    0.381047f, 0.001814f, 0.653068f, 0.471457f, 0.005678f, 0.659897f, 0.557243f, 0.047331f, 0.643443f,
-    0.636008f, 0.112092f, 0.605205f, 0.706178f, 0.178437f, 0.553657f, 0.768090f, 0.244817f, 0.498465f,
-    0.823132f, 0.311261f, 0.444806f, 0.872303f, 0.378774f, 0.393355f, 0.915471f, 0.448807f, 0.342890f,
-    0.951344f, 0.522850f, 0.292275f, 0.977856f, 0.602051f, 0.241387f, 0.992541f, 0.687030f, 0.192170f,
-    0.992505f, 0.777967f, 0.152855f, 0.940015f, 0.975158f, 0.131326f
-};
-static const float k_viridis[] = {
-    0.267004f, 0.004874f, 0.329415f, 0.282656f, 0.100196f, 0.422160f, 0.277134f, 0.185228f, 0.489898f,
-    0.253935f, 0.265254f, 0.529983f, 0.221989f, 0.339161f, 0.548752f, 0.190631f, 0.407061f, 0.556089f,
-    0.163625f, 0.471133f, 0.558148f, 0.139147f, 0.533812f, 0.555298f, 0.120565f, 0.596422f, 0.543611f,
-    0.134692f, 0.658636f, 0.517649f, 0.208030f, 0.718701f, 0.472873f, 0.327796f, 0.773980f, 0.406640f,
-    0.477504f, 0.821444f, 0.318195f, 0.647257f, 0.858400f, 0.209861f, 0.824940f, 0.884720f, 0.106217f,
-    0.993248f, 0.906157f, 0.143936f
-};
-/* turbo: 8-bit-precision samples (index 0,16,...,240,255) -- the 6-decimal table could
-   not be restated with confidence. [V-approx] */
-static const float k_turbo[] = {
-    48 / 255.f, 18 / 255.f, 59 / 255.f, 65 / 255.f, 69 / 255.f, 171 / 255.f, 70 / 255.f, 117 / 255.f, 237 / 255.f,
-    57 / 255.f, 162 / 255.f, 252 / 255.f, 27 / 255.f, 207 / 255.f, 212 / 255.f, 36 / 255.f, 236 / 255.f, 166 / 255.f,
-    97 / 255.f, 252 / 255.f, 108 / 255.f, 164 / 255.f, 252 / 255.f, 59 / 255.f, 209 / 255.f, 232 / 255.f, 52 / 255.f,
-    243 / 255.f, 198 / 255.f, 58 / 255.f, 254 / 255.f, 155 / 255.f, 45 / 255.f, 243 / 255.f, 99 / 255.f, 21 / 255.f,
-    217 / 255.f, 56 / 255.f, 6 / 255.f, 177 / 255.f, 25 / 255.f, 1 / 255.f, 122 / 255.f, 4 / 255.f, 2 / 255.f
-};
-static const float k_bluered[] = { 0.0f, 0.0f, 1.0f, 1.0f, 0.0f, 0.0f };
-static const float k_spectrum[] = { 0, 0, 0.05f, 0, 0, 0.75f, 0, 0.5f, 0, 0.5f, 0.5f, 0, 1, 0, 0 };
-static const float k_heat[] = { 0, 0, 0, 0.05f, 0, 0, 0.25f, 0, 0, 0.75f, 0.75f, 0, 1, 1, 1 };
+/* Colour-map knot tables [V: OIIO imagebufalgo_pixelmath.cpp color_map]: 17 knots per matplotlib map / turbo in
+   LINEAR light (the published sRGB-encoded map at indices 0,16,...,240,255, linearised).  Generated by
+   tools/make_colormaps.py; pinned at thumbnail scale by the reference's own render images/Filter.png
+   (tests/test_reference_filmstrips.py: 0.24/255 mean with these knots, 34.5/255 with round 1's sRGB-encoded ones). */
+#include "colormap_tables.inc"
 
 /* returns number of knots and pointer, or 0 for an unknown name */
 int o_color_map_knots(const char* name, const float** knots)

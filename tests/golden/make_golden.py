@@ -5,6 +5,8 @@ Run in the authoring container (needs /root/reference):
 
   tests/golden/data/       the reference's data/*.otio timelines and raster media, copied verbatim
                            (inputs that define the workloads; /root/reference does not exist on the GPU box)
+  tests/golden/ref_images/ the reference's film strips images/*.png, copied verbatim: pixels the REFERENCE rendered
+                           (tests/test_reference_filmstrips.py pins the oracle to them at thumbnail scale)
   tests/golden/frames.json per timeline and frame: the node tree ImageGraph::exec builds (text form) and the
                            sha256 + shape + dtype of the frame the CPU oracle renders from the decoded media
 The reference's own tests hold no golden pixels (tests/toucanRenderTest/ImageGraphTest.cpp:62-74 only
@@ -34,6 +36,12 @@ def main():
     for f in sorted(os.listdir(REF)):
         if f.endswith((".otio", ".png", ".jpg")):
             shutil.copyfile(os.path.join(REF, f), os.path.join(dst, f))
+    # the reference's own renders: README film strips made by bin/toucan-filmstrip (120x67 tiles at a 140 px stride)
+    strips = os.path.join(HERE, "ref_images")
+    os.makedirs(strips, exist_ok=True)
+    for f in sorted(os.listdir("/root/reference/images")):
+        if f.endswith(".png") and not f.startswith("toucan-view"):
+            shutil.copyfile(os.path.join("/root/reference/images", f), os.path.join(strips, f))
     out = {}
     for f in sorted(os.listdir(dst)):
         if not f.endswith(".otio") or f in SKIP:

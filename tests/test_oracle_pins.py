@@ -1,7 +1,7 @@
 """CPU: what pins the oracle.
 
-The reference's own tests hold no golden pixels and OpenImageIO is not available, so parity is
-UNPINNED against a real toucan-render.  What can be pinned here:
+The reference's own tests hold no golden pixels and OpenImageIO is not available; what pins the oracle to the reference's
+output is tests/test_reference_filmstrips.py (the reference's own rendered film strips, thumbnail scale).  Pinned here:
   * regression: the oracle renders every frame of every fixture timeline to the committed
     sha256 (tests/golden/frames.json, made by tests/golden/make_golden.py);
   * closed-form known answers of SURVEY 8c (identities, constant images, wipe/dissolve endpoints);
@@ -94,8 +94,9 @@ def test_known_answers():
     assert np.array_equal(O.over(clear, f), f)                    # alpha = 0 fg shows bg
     black = np.zeros((4, 4, 4), np.float32)
     white = np.ones((4, 4, 4), np.float32)
-    assert np.allclose(O.color_map(black, "plasma")[0, 0, :3], [0.050383, 0.029803, 0.527975])
-    assert np.allclose(O.color_map(white, "plasma")[0, 0, :3], [0.940015, 0.975158, 0.131326])
+    # first / last knot: matplotlib plasma's ends (0.050383, 0.029803, 0.527975) / (0.940015, 0.975158, 0.131326), linearised
+    assert np.allclose(O.color_map(black, "plasma")[0, 0, :3], _srgb_to_linear([0.050383, 0.029803, 0.527975]), atol=1e-6)
+    assert np.allclose(O.color_map(white, "plasma")[0, 0, :3], _srgb_to_linear([0.940015, 0.975158, 0.131326]), atol=1e-6)
     assert O.fit((1280, 720), (640, 360)) == (0, 0, 1280, 720)
     assert O.fit((1280, 720), (100, 100)) == (280, 0, 720, 720)
     # wipes at the ends: value 0 -> the 200 px ramp starts at 0; far right is all `from`
@@ -113,25 +114,44 @@ def test_fast_sinpi_error_bound():
     assert 0.0008 < err < 0.00093, err
 
 
-def test_colour_map_knots_against_opencv():
-    # The knot tables are restated from OIIO's published color_map tables [V].  What can be checked
-    # without OIIO: every knot is a genuine sample of the matplotlib map (OpenCV ships the same
-    # 256-entry tables at 8-bit precision), the samples run in increasing order, and the first and
-    # last knots are the ends of the map.
+def _srgb_to_linear(v):
+    v = np.asarray(v, np.float64)
+    return np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+
+
+def test_colour_map_knots_are_linearised_samples_at_the_17_knot_indices():
+    # OIIO's color_map tables [V], pinned by the reference's render of data/Filter.otio (test_reference_filmstrips.py): 17 knots per
+    # map = the published (sRGB-encoded) map at indices 0,16,...,240,255 converted to LINEAR light.  OpenCV ships the same 256-entry
+    # tables at 8-bit precision, so every knot, re-encoded, must sit within half an 8-bit step (+ the de-quantisation's slack) of
+    # that entry -- which fixes the colour space, the knot count and the spacing (round 1's sRGB-encoded knots at 0,15,...,225,255
+    # fail all three).
     cv2 = pytest.importorskip("cv2")
     import ctypes
 
+    index = list(range(0, 241, 16)) + [255]
     for name, code in [("plasma", cv2.COLORMAP_PLASMA), ("inferno", cv2.COLORMAP_INFERNO), ("magma", cv2.COLORMAP_MAGMA),
                        ("viridis", cv2.COLORMAP_VIRIDIS), ("turbo", cv2.COLORMAP_TURBO)]:
         lut = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(1, 256), code)[0, :, ::-1].astype(np.float64) / 255.0
         p = ctypes.POINTER(ctypes.c_float)()
         n = O.lib().o_color_map_knots(name.encode(), ctypes.byref(p))
-        assert 15 <= n <= 17
-        knots = np.array([p[i] for i in range(3 * n)]).reshape(n, 3)
-        best = [int(np.argmin(np.abs(lut - k).sum(1))) for k in knots]
-        assert best[0] == 0 and best[-1] == 255, (name, best)
-        assert all(b > a for a, b in zip(best, best[1:])), (name, best)
-        assert max(float(np.abs(lut[b] - k).max()) for b, k in zip(best, knots)) < 1.0 / 255 + 1e-3, name
+        assert n == 17, (name, n)
+        knots = np.array([p[i] for i in range(3 * n)], np.float64).reshape(n, 3)
+        want = _srgb_to_linear(lut[index])
+        # half an 8-bit step in the encoded value, through the slope of the decode curve (<= 2.3), plus the table's 6 decimals
+        slope = np.maximum(1.0 / 12.92, 2.4 / 1.055 * ((lut[index] + 0.055) / 1.055) ** 1.4)
+        assert np.all(np.abs(knots - want) <= (1.0 / 255) * slope + 2e-6), (name, np.abs(knots - want).max())
+    # magma's knots are the six-decimal matplotlib values: OIIO's published table starts 0.000113, 0.000036, 0.001073, 0.003066, ...
+    p = ctypes.POINTER(ctypes.c_float)()
+    O.lib().o_color_map_knots(b"magma", ctypes.byref(p))
+    assert [round(p[i], 6) for i in range(6)] == [0.000113, 0.000036, 0.001073, 0.003066, 0.002406, 0.016033]
+
+
+def test_kernel_and_oracle_colour_map_tables_are_the_same_numbers():
+    # both generated by tools/make_colormaps.py; the product never reads oracle/, so the numbers exist twice
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = open(os.path.join(root, "oracle", "colormap_tables.inc")).read().replace("k_", "X")
+    b = open(os.path.join(root, "toucan_b200", "csrc", "tc_colormap_tables.inc")).read().replace("kMap_", "X")
+    assert a == b and a.count("static const float") == 8
 
 
 def test_builtin_png_reader_matches_harness_decode(built):
@@ -142,6 +162,17 @@ def test_builtin_png_reader_matches_harness_decode(built):
     for f in ["Counter.3.png", "Letter_A.png", "Gradient.png"]:
         p = os.path.join(TL.DATA, f)
         assert np.array_equal(render.decode_png(p), media.decode(p)), f
+    # ... and the "oiio:UnassociatedAlpha" switch leaves the file's values alone in both
+    render.set_unassociated_alpha(True)
+    try:
+        for f in ["Counter.3.png", "Letter_A.png"]:
+            p = os.path.join(TL.DATA, f)
+            got = render.decode_png(p)
+            assert np.array_equal(got, media.decode_unassociated(p)), f
+            assert not np.array_equal(got, media.decode(p)), f
+        assert tuple(render.decode_png(os.path.join(TL.DATA, "Counter.3.png"))[0, 0]) == (255, 255, 255, 0)  # transparent white
+    finally:
+        render.set_unassociated_alpha(False)
 
 
 def test_colour_matrices_against_published_aces_values():

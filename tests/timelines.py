@@ -10,6 +10,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DATA = os.path.join(GOLDEN, "data")
 
 
+SVG_STAND_INS = ("Letter_A.svg", "Letter_B.svg", "Letter_C.svg")
+
+
 def golden():
     with open(os.path.join(GOLDEN, "frames.json")) as f:
         return json.load(f)
@@ -27,5 +30,9 @@ def open_timeline(name):
             frame = media.decode(os.path.join(DATA, f))
             if frame is not None:
                 tl.set_media(os.path.join(DATA, f), frame)
+    for name in SVG_STAND_INS:  # the .svg media of Gap.otio: the PNG export stands in (tests/media.py)
+        frame = media.decode(os.path.join(DATA, name))
+        if frame is not None:
+            tl.set_media(os.path.join(DATA, name), frame)
     tl.prepare()
     return tl

@@ -65,7 +65,7 @@ def _run(cmd, verbose):
 def _headers(d):
     out = []
     for base, _, files in os.walk(d):
-        out += [os.path.join(base, f) for f in files if f.endswith((".h", ".cuh", ".hpp"))]
+        out += [os.path.join(base, f) for f in files if f.endswith((".h", ".cuh", ".hpp", ".inc"))]
     return out
 
 

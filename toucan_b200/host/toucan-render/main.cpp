@@ -10,7 +10,7 @@
 // Movie encoders and the other OIIO writers are outside the hot path ("Unsupported output").
 //
 //   toucan-render input.otio output|- [-raw rgb24|rgba|rgb48|rgba64|rgbaf16|rgbf32|rgbaf32]
-//                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K] [-cache GiB] [-inflight N] [-v]
+//                 [-y4m 422|444|444alpha|444p16] [-gpus N] [-workers K] [-cache GiB] [-inflight N] [-v] [-unassociated_alpha]
 //                 [-print_start] [-print_duration] [-print_rate] [-print_size]
 #include <toucanRender/ExrRead.h>
 #include <toucanRender/FrameScheduler.h>
@@ -45,6 +45,8 @@ int main(int argc, char** argv)
             else if (a == "-raw" && i + 1 < argc) raw = argv[++i];
             else if (a == "-y4m" && i + 1 < argc) y4m = argv[++i];
             else if (a == "-v") verbose = true;
+            else if (a == "-unassociated_alpha") setKeepUnassociatedAlpha(true); // OIIO's "oiio:UnassociatedAlpha" reader hint
+
             else if (a == "-print_start") printStart = true;
             else if (a == "-print_duration") printDuration = true;
             else if (a == "-print_rate") printRate = true;
@@ -54,7 +56,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-cache GiB] [-v] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-cache GiB] [-v] [-unassociated_alpha] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 

@@ -183,6 +183,7 @@ namespace toucan
         }
 
         const size_t count = static_cast<size_t>(width) * height;
+        const bool associate = !getKeepUnassociatedAlpha(); // OIIO's pnginput associates unless "oiio:UnassociatedAlpha" is set
         out = MediaFrame();
         out.width = static_cast<int>(width);
         out.height = static_cast<int>(height);
@@ -212,7 +213,7 @@ namespace toucan
                     b = p[2];
                     if (channels == 4) a = p[3];
                 }
-                if (a != 255)
+                if (a != 255 && associate)
                 {
                     const float af = a * (1.0f / 255.0f);
                     r = toUnsigned<unsigned char>(af * (r * (1.0f / 255.0f)), 255.f);
@@ -235,7 +236,7 @@ namespace toucan
                 const unsigned char* p = &pix[i * channels * 2];
                 uint16_t v[4] = { 0, 0, 0, 65535 };
                 for (int c = 0; c < channels; ++c) v[c] = static_cast<uint16_t>((p[c * 2] << 8) | p[c * 2 + 1]);
-                if (v[3] != 65535)
+                if (v[3] != 65535 && associate)
                 {
                     const float af = v[3] * (1.0f / 65535.0f);
                     for (int c = 0; c < 3; ++c) v[c] = toUnsigned<uint16_t>(af * (v[c] * (1.0f / 65535.0f)), 65535.f);

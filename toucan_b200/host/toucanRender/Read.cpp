@@ -7,11 +7,27 @@
 #include "Util.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <sstream>
 #include <thread>
 
 namespace toucan
 {
+    namespace
+    {
+        std::atomic<bool>& keepUnassociatedAlpha()
+        {
+            static std::atomic<bool> value([] {
+                const char* e = getenv("TOUCAN_UNASSOCIATED_ALPHA");
+                return e && *e && *e != '0';
+            }());
+            return value;
+        }
+    }
+
+    void setKeepUnassociatedAlpha(bool value) { keepUnassociatedAlpha() = value; }
+    bool getKeepUnassociatedAlpha() { return keepUnassociatedAlpha(); }
+
     void MediaStore::set(const std::string& path, const MediaFrame& frame)
     {
         std::lock_guard<std::mutex> lock(_mutex);

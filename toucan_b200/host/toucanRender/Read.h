@@ -31,6 +31,15 @@ namespace toucan
         std::shared_ptr<unsigned char> storage;               // ... or a plain (uninitialised) array for the large ones
     };
 
+    //! Reader option, the counterpart of OpenImageIO's "oiio:UnassociatedAlpha" open-time hint: PNG (and TIFF ExtraSamples = 2)
+    //! files store UNassociated alpha; OIIO's readers multiply colour by alpha on read unless that hint is set, and the
+    //! reference opens its media with no hints (lib/toucanRender/Read.cpp:39) -- so the default here is to associate.  The
+    //! reference's own rendered film strips (images/Transition*.png) show UNassociated Counter frames entering the Dissolve, i.e.
+    //! they were made by a build whose read path kept the file's values; `true` reproduces those renders
+    //! (tests/test_reference_filmstrips.py runs both).  Process-wide; initial value from TOUCAN_UNASSOCIATED_ALPHA=1.
+    void setKeepUnassociatedAlpha(bool);
+    bool getKeepUnassociatedAlpha();
+
     //! A file held in memory (lib/toucanRender/MemoryMap.h: MemoryReference): an entry of a mapped .otioz.
     struct MemoryReference
     {

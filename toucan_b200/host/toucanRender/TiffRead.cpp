@@ -211,7 +211,7 @@ namespace toucan
         if (planar != 1) bad("planar files are not supported");
         if (predictor != 1 && !(2 == predictor && !isFloat)) bad("unsupported predictor");
         // ExtraSamples: 1 = associated alpha, 2 = unassociated (associated on read, like OIIO's reader), 0 / absent = unspecified
-        const int extra = 4 == samples ? static_cast<int>(get(338, 1)) : 0;
+        const int extra = (4 == samples && !getKeepUnassociatedAlpha()) ? static_cast<int>(get(338, 1)) : 0;
 
         const size_t bps = static_cast<size_t>(bits / 8);
         const size_t lineBytes = static_cast<size_t>(width) * samples * bps;

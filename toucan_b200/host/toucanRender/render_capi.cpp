@@ -376,6 +376,9 @@ extern "C"
         if (hi) *hi = block.second;
     }
 
+    void tr_set_unassociated_alpha(int keep) { setKeepUnassociatedAlpha(keep != 0); }
+    int tr_get_unassociated_alpha(void) { return getKeepUnassociatedAlpha() ? 1 : 0; }
+
     int tr_decode_png(const char* path, void* out, size_t capacity, int* width, int* height, int* type)
     {
         if (!path) return fail("tr_decode_png: null");

@@ -52,7 +52,8 @@ _SIGS["tr_render_range_raw"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.
                                 FRAME_CALLBACK, _VP]
 _SIGS["tr_render_range_y4m"] = _SIGS["tr_render_range_raw"]
 _SIGS["tr_y4m_header"] = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
-EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_fit", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion", "tr_set_interleave"})
+EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_fit", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion", "tr_set_interleave",
+                                  "tr_set_unassociated_alpha", "tr_get_unassociated_alpha"})
 
 
 def lib() -> ctypes.CDLL:
@@ -134,8 +135,16 @@ def fit(a, b):
     return tuple(out)
 
 
+def set_unassociated_alpha(keep: bool) -> None:
+    """OIIO's "oiio:UnassociatedAlpha" reader hint for the built-in PNG / TIFF readers (default off = associate on read)."""
+    f = lib().tr_set_unassociated_alpha
+    f.argtypes = [ctypes.c_int]
+    f.restype = None
+    f(1 if keep else 0)
+
+
 def decode_png(path: str) -> np.ndarray:
-    """The C++ host's built-in PNG reader (RGBA, alpha associated like OIIO's reader)."""
+    """The C++ host's built-in PNG reader (RGBA; alpha associated like OIIO's reader unless set_unassociated_alpha(True))."""
     w, h, t = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     _check(lib().tr_decode_png(path.encode(), None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(t)), "tr_decode_png")
     out = np.empty((h.value, w.value, 4), _NP_OF[t.value])
