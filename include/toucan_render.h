@@ -52,6 +52,10 @@ int tr_timeline_set_media(tr_timeline* timeline, const char* path, const void* p
 /* Device source cache: keep up to `bytes` of uploaded host frames resident per GPU (LRU), so a still
    is uploaded once instead of on every frame.  0 (default) = upload on every frame. */
 int tr_timeline_set_source_cache(tr_timeline* timeline, size_t bytes);
+/* Host -> device source uploads so far (count, bytes): what the device source cache saved shows up here. */
+int tr_timeline_upload_stats(const tr_timeline* timeline, unsigned long long* uploads, unsigned long long* bytes);
+/* Empty the device source cache (the next frame uploads what it reads again). */
+int tr_timeline_drop_source_cache(tr_timeline* timeline);
 /* Build the ImageGraph (reads the first clip's media information). */
 int tr_timeline_prepare(tr_timeline* timeline);
 /* start/rate of the first frame, number of frames (App.cpp:222-224), image size and tc_type. */

@@ -1,6 +1,6 @@
 """Python restatement of toucan's per-frame graph builder and its evaluation on the CPU oracle.
 
-TEST INFRASTRUCTURE ONLY (see oracle/toucan_oracle.c).  PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY (see oracle/toucan_oracle.c).  Parity: coarsely pinned (tests/test_reference_filmstrips.py).
 
 Follows, in this order of authority:
   * lib/toucanRender/ImageGraph.cpp:42-466 (constructor, exec, _track, _item, _timeWarps, _effects)

@@ -1,8 +1,8 @@
 """ctypes front-end of the CPU oracle (oracle/toucan_oracle.c).
 
 TEST INFRASTRUCTURE ONLY -- see the header of toucan_oracle.c.  Nothing under
-toucan_b200/ may import this module.  PARITY UNPINNED (no OIIO here, no golden pixels
-in the reference's tests).
+toucan_b200/ may import this module.  Parity: coarsely pinned by the reference's own film strips
+(tests/test_reference_filmstrips.py); [V] below thumbnail resolution.
 
 Images are numpy arrays of shape (h, w, 4) and dtype uint8 / uint16 / float16 / float32.
 Every function returns a new array and cites the reference call site it restates.

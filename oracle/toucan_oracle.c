@@ -5,17 +5,20 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this library.  The
  * product path (toucan_b200/) never links, loads or calls it.
  *
- * PARITY UNPINNED.  The pixel arithmetic of the reference lives in OpenImageIO
+ * PARITY: COARSELY PINNED.  The pixel arithmetic of the reference lives in OpenImageIO
  * v3.0.10.0 (cmake/SuperBuild/BuildOpenImageIO.cmake:4) and OpenColorIO v2.4.2
  * (BuildOpenColorIO.cmake:4), neither of which is vendored under /root/reference nor
  * installed here, and the reference's own tests hold no golden pixels
  * (tests/toucanRenderTest/ImageGraphTest.cpp:62-74 only writes PNGs).  Each function
  * below restates the published OIIO algorithm that the cited toucan call site invokes.
- * Items restated from the third-party library are tagged [V] (to verify against a real
- * OIIO build when one is available).  Two constants tables could be cross-checked
+ * What pins the restatement to the reference's output: the film strips the reference
+ * rendered itself (the images/ PNG strips), matched per frame at thumbnail scale to <= 1/255 mean
+ * by tests/test_reference_filmstrips.py (every effect of the fixtures except toucan:Text).
+ * Below that resolution the items restated from the third-party libraries stay [V] (to
+ * verify against a real OIIO build when one is available).  Constants cross-checked
  * here: fast_sinpi (max abs error 0.000918958 measured vs 0.000918954611 documented)
- * and the colour-map knots (within 8-bit precision of OpenCV's copy of the matplotlib
- * tables); see tests/test_oracle_pins.py.
+ * and the colour-map knots (OpenCV's copy of the matplotlib tables, linearised);
+ * see tests/test_oracle_pins.py.
  *
  * Conventions: every image is interleaved RGBA (4 channels), row-major, top row
  * first, no row padding (PropertySet.cpp:467, Read.cpp:79-84).  All arithmetic is
@@ -23,6 +26,7 @@
  * -ffp-contract=off: OIIO is built for baseline x86-64 (no FMA).
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -36,6 +40,19 @@ typedef struct {
 } oimg;
 
 #define NCH 4
+
+/* bench.py's CPU arms: the OpenMP team size, set explicitly (torchrun exports OMP_NUM_THREADS=1 to its ranks) */
+void o_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int o_get_threads(void)
+{
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
+}
 
 /* ------------------------------------------------------------------------- */
 /* 9.1 storage conversion  [V: OIIO fmath.h convert_type / scaled_conversion] */

@@ -4,6 +4,7 @@
 #include <opentimelineio/otio.h>
 #include <toucanRender/Archive.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -36,6 +37,21 @@ int main(int argc, char** argv)
                     if (zip && (rng() & 1)) at = mut.size() - 1 - rng() % std::min<size_t>(mut.size(), 400); // the central directory
                     mut[at] = char(rng());
                 }
+                if (zip && (m % 7 == 3 || m % 7 == 5))
+                {
+                    // crafted central-directory records: a stored entry that claims more bytes than it holds, sizes / offsets
+                    // at the 32-bit sentinel (ZIP64 lookups) and offsets near 2^32 (sums that would wrap)
+                    mut = bytes;
+                    for (size_t at = 0; at + 46 < mut.size(); ++at)
+                    {
+                        if (mut[at] == 'P' && mut[at + 1] == 'K' && mut[at + 2] == 1 && mut[at + 3] == 2 && (rng() & 1))
+                        {
+                            const uint32_t v = m % 7 == 3 ? (rng() | 0x40000000u) : (0xfffffff0u + rng() % 16);
+                            const size_t field = m % 7 == 3 ? (rng() & 1 ? 24 : 20) : 42;
+                            for (int b = 0; b < 4; ++b) mut[at + field + b] = char(v >> (8 * b));
+                        }
+                    }
+                }
             }
             try
             {
@@ -45,6 +61,13 @@ int main(int argc, char** argv)
                     std::ofstream(tmp, std::ios::binary).write(mut.data(), std::streamsize(mut.size()));
                     toucan::ZipArchive archive(tmp);
                     (void)archive.find("content.otio");
+                    // every entry the directory accepted can be read without leaving the mapping
+                    for (const auto& e : archive.entries())
+                    {
+                        if (e.second.size > (size_t(1) << 28)) continue;
+                        try { (void)archive.read(e.second); } catch (const std::exception&) {}
+                        if (0 == e.second.method && (e.second.dataOffset > archive.size() || archive.size() - e.second.dataOffset < e.second.size)) std::abort();
+                    }
                     ++ok;
                 }
                 else

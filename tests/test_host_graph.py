@@ -164,8 +164,9 @@ def test_timeline_documents_survive_damage(tmp_path):
     src = [os.path.join(B.ROOT, "tests", "cpp", "otio_fuzz.cpp"), os.path.join(B.HOST, "toucanRender", "otio.cpp"), os.path.join(B.HOST, "toucanRender", "Archive.cpp")]
     r = subprocess.run([B.CXX, "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-I", os.path.join(B.ROOT, "include"),
                         "-I", B.HOST] + src + ["-o", exe, "-lz", "-lpthread"], capture_output=True, text=True)
-    if r.returncode != 0:
+    if r.returncode != 0 and ("asan" in r.stderr.lower() or "ubsan" in r.stderr.lower() or "fsanitize" in r.stderr):
         pytest.skip("no sanitizer runtime for " + B.CXX)
+    assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe, "300", str(tmp_path / "mutated.otioz")] + files + [bundle] + deep, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "parsed" in r.stdout, (r.stdout[-300:], r.stderr[-3000:])
     # and through the public API: a hopeless document is an error, not a crash

@@ -210,9 +210,16 @@ DeviceCache g_cache[kMaxDevices];
 
 size_t cache_limit()
 {
+    // TOUCAN_CACHE_BYTES, else a third of the device's memory (60 GB of a B200's 180): the bound scales with the part
     static const size_t limit = [] {
         const char* env = getenv("TOUCAN_CACHE_BYTES");
-        return env && *env ? (size_t)strtoull(env, nullptr, 10) : ((size_t)64 << 30);
+        if (env && *env) return (size_t)strtoull(env, nullptr, 10);
+        size_t free_b = 0, total = 0;
+        if (cudaMemGetInfo(&free_b, &total) != cudaSuccess || !total) {
+            cudaGetLastError();
+            return (size_t)64 << 30;
+        }
+        return total / 3;
     }();
     return limit;
 }
@@ -222,6 +229,15 @@ DeviceCache* current_cache()
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
     return &g_cache[dev];
+}
+
+// the device a pointer was allocated on (a buffer may be released by a thread bound to another GPU)
+int owner_device(const void* p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeDevice) return attr.device;
+    cudaGetLastError();
+    return -1;
 }
 
 // give every cached buffer back to the stream-ordered pool (caller holds no lock)
@@ -270,7 +286,16 @@ int tc_malloc(void** out, size_t bytes, tc_stream s)
             return TC_OK;
         }
     }
-    TC_CUDA(cudaMallocAsync(out, bytes, (cudaStream_t)s));
+    cudaError_t e = cudaMallocAsync(out, bytes, (cudaStream_t)s);
+    if (cudaErrorMemoryAllocation == e && c) {
+        // out of memory while buffers of other sizes sit idle in the cache: give them back to the pool and retry once
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        cache_flush(*c);
+        cudaDeviceSynchronize();
+        e = cudaMallocAsync(out, bytes, (cudaStream_t)s);
+    }
+    TC_CUDA(e);
     if (c) {
         std::lock_guard<std::mutex> lock(c->m);
         c->live[*out] = bytes;
@@ -282,6 +307,19 @@ int tc_free(void* p, tc_stream s)
     if (!p) return TC_OK;
     AllocTimer timer;
     DeviceCache* c = current_cache();
+    if (c) {
+        bool mine;
+        {
+            std::lock_guard<std::mutex> lock(c->m);
+            mine = c->live.count(p) != 0;
+        }
+        if (!mine) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            const int owner = owner_device(p);
+            if (owner >= 0 && owner != cur) return fail(TC_ERR_INVALID, "tc_free: the buffer belongs to another device (use tc_free_sync)");
+        }
+    }
     size_t bytes = 0;
     cudaEvent_t ev = nullptr;
     if (c) {
@@ -324,11 +362,21 @@ void tc_alloc_stats(unsigned long long* calls, unsigned long long* nanoseconds)
 int tc_free_sync(void* p)
 {
     if (!p) return TC_OK;
-    if (DeviceCache* c = current_cache()) {
-        std::lock_guard<std::mutex> lock(c->m);
-        c->live.erase(p);
+    // look the buffer up in the cache of the device that owns it, not the calling thread's current device
+    int cur = 0;
+    cudaGetDevice(&cur);
+    const int owner = owner_device(p);
+    if (owner >= 0 && owner != cur) cudaSetDevice(owner);
+    const int dev = owner >= 0 ? owner : cur;
+    if (dev >= 0 && dev < kMaxDevices) {
+        DeviceCache& c = g_cache[dev];
+        std::lock_guard<std::mutex> lock(c.m);
+        c.live.erase(p);
     }
-    TC_CUDA(cudaFree(p));
+    // cudaFree waits for all work on the device: safe for a buffer several streams have read
+    const cudaError_t e = cudaFree(p);
+    if (owner >= 0 && owner != cur) cudaSetDevice(cur);
+    TC_CUDA(e);
     return TC_OK;
 }
 int tc_pool_trim(void)

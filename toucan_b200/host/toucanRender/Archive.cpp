@@ -1,5 +1,6 @@
 #include "Archive.h"
 
+#include <algorithm>
 #include <zlib.h>
 
 #include <fcntl.h>
@@ -62,7 +63,7 @@ namespace toucan
         {
             // ZIP64: the locator points at the 64-bit end-of-central-directory record
             const uint64_t eocd64 = le64(_data + eocd - 20 + 8);
-            if (eocd64 + 56 <= _size && 0x06064b50 == le32(_data + eocd64))
+            if (eocd64 <= _size && _size - eocd64 >= 56 && 0x06064b50 == le32(_data + eocd64))
             {
                 count = le64(_data + eocd64 + 32);
                 cdOffset = le64(_data + eocd64 + 48);
@@ -71,7 +72,9 @@ namespace toucan
         uint64_t p = cdOffset;
         for (uint64_t i = 0; i < count; ++i)
         {
-            if (p + 46 > _size || le32(_data + p) != 0x02014b50)
+            // every bound below is written as "offset <= size && size - offset >= need": the 64-bit ZIP64 fields of a crafted
+            // archive must not wrap the sum
+            if (p > _size || _size - p < 46 || le32(_data + p) != 0x02014b50)
             {
                 throw std::runtime_error("Corrupt zip central directory: " + path.string());
             }
@@ -81,7 +84,7 @@ namespace toucan
             e.size = le32(_data + p + 24);
             const size_t nameLen = le16(_data + p + 28), extraLen = le16(_data + p + 30), commentLen = le16(_data + p + 32);
             uint64_t local = le32(_data + p + 42);
-            if (p + 46 + nameLen + extraLen > _size)
+            if (_size - p - 46 < nameLen + extraLen)
             {
                 throw std::runtime_error("Corrupt zip central directory: " + path.string());
             }
@@ -90,7 +93,8 @@ namespace toucan
             for (size_t x = 0; x + 4 <= extraLen;)
             {
                 const unsigned char* f = _data + p + 46 + nameLen + x;
-                const size_t id = le16(f), len = le16(f + 2);
+                const size_t id = le16(f);
+                const size_t len = std::min<size_t>(le16(f + 2), extraLen - x - 4); // a field cannot reach past the extra area
                 if (0x0001 == id)
                 {
                     size_t o = 4;
@@ -100,13 +104,19 @@ namespace toucan
                 }
                 x += 4 + len;
             }
-            if (local + 30 > _size || le32(_data + local) != 0x04034b50)
+            if (local > _size || _size - local < 30 || le32(_data + local) != 0x04034b50)
             {
                 throw std::runtime_error("Corrupt zip local header: " + name);
             }
             // TimelineWrapper.cpp:205-211: 30 bytes + file name + extra field of the LOCAL header
             e.dataOffset = local + 30 + le16(_data + local + 26) + le16(_data + local + 28);
-            if (e.dataOffset + e.compressedSize > _size)
+            if (e.dataOffset > _size || _size - e.dataOffset < e.compressedSize)
+            {
+                throw std::runtime_error("Corrupt zip entry: " + name);
+            }
+            // a stored entry IS its data: a size other than the stored size would read past the entry (media of an
+            // .otioz are referenced in place with this size, TimelineWrapper.cpp); deflate cannot expand beyond 1032:1
+            if ((0 == e.method && e.size != e.compressedSize) || (8 == e.method && e.size / 1032 > e.compressedSize + 1))
             {
                 throw std::runtime_error("Corrupt zip entry: " + name);
             }

@@ -31,6 +31,7 @@ namespace toucan
         ZipArchive& operator=(const ZipArchive&) = delete;
 
         const Entry* find(const std::string& name) const;
+        const std::map<std::string, Entry>& entries() const { return _entries; }
 
         //! The entry's contents (inflated when needed).
         std::vector<unsigned char> read(const Entry&) const;

@@ -1,5 +1,7 @@
 #include "FrameScheduler.h"
 
+#include <atomic>
+
 #include "ImageEffectHost.h"
 
 #include <cmath>
@@ -132,6 +134,7 @@ namespace toucan
             std::deque<int> free_;  // slot indices the writer has released
             std::exception_ptr error;
             bool finished = false;
+            bool writerDone = false; // the writer will not touch this worker's slots again
             std::thread thread;
         };
     }
@@ -177,7 +180,10 @@ namespace toucan
             workers.push_back(std::move(w));
         }
 
-        auto body = [this, rate, &timeRange](Worker& w)
+        // set on any error, in a worker or in the writer: every worker stops at its next frame
+        std::atomic<bool> cancel{ false };
+
+        auto body = [this, rate, &timeRange, &cancel](Worker& w)
         {
             tc_stream copyStream = nullptr;
             tc_event rendered = nullptr;
@@ -195,12 +201,13 @@ namespace toucan
                     host = std::make_shared<ImageEffectHost>(_context, _options.pluginSearchPath);
                 }
                 auto graph = std::make_shared<ImageGraph>(_context, _timelineWrapper->getPath().parent_path(), _timelineWrapper);
-                for (int frame = w.first; frame < w.last; frame += w.step)
+                for (int frame = w.first; frame < w.last && !cancel; frame += w.step)
                 {
                     int index = -1;
                     {
                         std::unique_lock<std::mutex> lock(w.mutex);
-                        w.cv.wait(lock, [&w] { return !w.free_.empty(); });
+                        w.cv.wait(lock, [&w, &cancel] { return !w.free_.empty() || cancel; });
+                        if (cancel) break;
                         index = w.free_.front();
                         w.free_.pop_front();
                     }
@@ -260,18 +267,23 @@ namespace toucan
                     }
                     w.cv.notify_all();
                 }
-                // drain: every handed-out slot comes back before the device objects go away
-                {
-                    std::unique_lock<std::mutex> lock(w.mutex);
-                    w.cv.wait(lock, [&w] { return w.free_.size() == w.slots.size(); });
-                }
-                DeviceContext::synchronize();
             }
             catch (...)
             {
+                cancel = true;
                 std::lock_guard<std::mutex> lock(w.mutex);
                 w.error = std::current_exception();
             }
+            w.cv.notify_all();
+            // Drain before anything is released: every handed-out slot comes back, or -- after an error anywhere -- the
+            // writer has declared it will not touch this worker's slots again; then both streams are idle (no copy is
+            // still writing a pinned buffer that goes back to the process-wide pool).
+            {
+                std::unique_lock<std::mutex> lock(w.mutex);
+                w.cv.wait(lock, [&w] { return w.free_.size() == w.slots.size() || w.writerDone; });
+            }
+            if (copyStream) tc_stream_sync(copyStream);
+            if (DeviceContext::isBound()) tc_stream_sync(DeviceContext::stream());
             for (Slot& slot : w.slots)
             {
                 slot.image = Image();
@@ -282,6 +294,7 @@ namespace toucan
             }
             if (rendered) tc_event_destroy(rendered);
             if (copyStream) tc_stream_destroy(copyStream);
+            DeviceContext::unbind(); // the thread's own stream goes with the thread
             {
                 std::lock_guard<std::mutex> lock(w.mutex);
                 w.finished = true;
@@ -309,7 +322,8 @@ namespace toucan
             }
             return nullptr;
         };
-        for (int frame = first; frame < last && !error; ++frame)
+        bool stopped = false;
+        for (int frame = first; frame < last && !error && !stopped; ++frame)
         {
             Worker* w = owner(frame);
             if (!w)
@@ -320,8 +334,10 @@ namespace toucan
             int index = -1;
             {
                 std::unique_lock<std::mutex> lock(w->mutex);
-                w->cv.wait(lock, [w] { return !w->ready.empty() || w->error || w->finished; });
+                // another worker's failure sets `cancel` without signalling this worker's condition: poll for it
+                while (!w->cv.wait_for(lock, std::chrono::milliseconds(20), [w] { return !w->ready.empty() || w->error || w->finished; }) && !cancel) {}
                 if (w->error) { error = w->error; break; }
+                if (w->ready.empty() && cancel) { stopped = true; break; } // the failing worker's exception is collected after the join
                 if (w->ready.empty()) { error = std::make_exception_ptr(std::runtime_error("frame scheduler: worker ended early")); break; }
                 index = w->ready.front();
                 w->ready.pop_front();
@@ -342,19 +358,15 @@ namespace toucan
             }
             w->cv.notify_all();
         }
-        if (error)
+        if (error) cancel = true; // a failed writer (a closed pipe): the workers stop instead of rendering the rest
+        for (auto& w : workers)
         {
-            // unblock workers waiting for a slot: release everything they may have queued
-            for (auto& w : workers)
+            // the writer is done with every slot: workers waiting for one (or draining) may tear down
             {
-                std::unique_lock<std::mutex> lock(w->mutex);
-                while (!w->finished)
-                {
-                    while (!w->ready.empty()) { w->free_.push_back(w->ready.front()); w->ready.pop_front(); }
-                    w->cv.notify_all();
-                    w->cv.wait_for(lock, std::chrono::milliseconds(10));
-                }
+                std::lock_guard<std::mutex> lock(w->mutex);
+                w->writerDone = true;
             }
+            w->cv.notify_all();
         }
         for (auto& w : workers)
         {

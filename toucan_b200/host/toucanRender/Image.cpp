@@ -1,5 +1,6 @@
 #include "Image.h"
 
+#include <atomic>
 #include <sstream>
 
 namespace toucan
@@ -44,6 +45,16 @@ namespace toucan
         binding.bound = true;
     }
 
+    void DeviceContext::unbind()
+    {
+        if (binding.bound && binding.stream)
+        {
+            tc_stream_sync(binding.stream);
+            if (binding.ownStream) tc_stream_destroy(binding.stream);
+        }
+        binding = Binding();
+    }
+
     bool DeviceContext::isBound() { return binding.bound; }
 
     int DeviceContext::device()
@@ -81,11 +92,15 @@ namespace toucan
         void* p = nullptr;
         tc_stream stream = nullptr;
         std::shared_ptr<const void> hostSource; // page-locked host memory an asynchronous upload is still reading
+        tc_event ready = nullptr;               // publish(): the contents are complete on `stream` at this point
+        std::atomic<bool> shared{ false };      // acquire()d from another stream: readers are not ordered by `stream`
         ~Buffer()
         {
-            // stream-ordered release; if that stream is gone (a cached frame outliving its worker)
-            // fall back to a synchronous free
-            if (p && tc_free(p, stream) != TC_OK) tc_free_sync(p);
+            // Stream-ordered release when only the allocating stream ever touched the buffer.  A buffer other streams
+            // have read (cached sources), or whose stream / device binding is gone (a cached frame outliving its
+            // worker), is released with cudaFree, which waits for all work on the device.
+            if (p && (shared.load() || tc_free(p, stream) != TC_OK)) tc_free_sync(p);
+            if (ready) tc_event_destroy(ready);
         }
     };
 
@@ -126,6 +141,22 @@ namespace toucan
     void Image::keepAlive(const std::shared_ptr<const void>& hostSource)
     {
         if (_buffer) _buffer->hostSource = hostSource;
+    }
+
+    void Image::publish()
+    {
+        if (!_buffer) return;
+        if (!_buffer->ready) tcCheck(tc_event_create(&_buffer->ready), "tc_event_create");
+        tcCheck(tc_event_record(_buffer->ready, DeviceContext::stream()), "tc_event_record");
+    }
+
+    void Image::acquire() const
+    {
+        if (!_buffer || !_buffer->ready) return;
+        const tc_stream mine = DeviceContext::stream();
+        if (mine == _buffer->stream) return; // same stream: already ordered
+        _buffer->shared = true;
+        tcCheck(tc_stream_wait_event(mine, _buffer->ready), "tc_stream_wait_event");
     }
 
     void Image::download(void* hostPixels) const

@@ -22,6 +22,8 @@ namespace toucan
     public:
         //! Bind the calling thread to a device. stream == nullptr creates one.
         static void bind(int device, tc_stream stream = nullptr);
+        //! Wait for the thread's stream and destroy it if bind() created it (end of a worker thread).
+        static void unbind();
         static bool isBound();
         static int device();
         static tc_stream stream();
@@ -59,6 +61,14 @@ namespace toucan
         //! Tie the lifetime of the host memory an upload reads to this image: uploads from page-locked memory are
         //! asynchronous, so the source must outlive the copy (it is released with the device buffer).
         void keepAlive(const std::shared_ptr<const void>& hostSource);
+
+        //! Sharing one image between render threads (the device source cache): every thread has its own stream.
+        //! publish(): record "contents complete" on the calling thread's stream -- call after the work that fills the
+        //! image was enqueued, before other threads can see it.  acquire(): make the calling thread's stream wait for
+        //! that point; a buffer acquired from a second stream is released with a device-wide wait instead of a
+        //! stream-ordered free, because its readers are no longer ordered by the allocating stream alone.
+        void publish();
+        void acquire() const;
 
         const ImageSpec& spec() const { return _spec; }
         bool initialized() const { return _data != nullptr; }

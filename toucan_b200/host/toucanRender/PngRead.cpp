@@ -1,5 +1,7 @@
 #include "PngRead.h"
 
+#include <atomic>
+#include <cstdlib>
 #include <zlib.h>
 
 #include <cstdint>
@@ -10,6 +12,22 @@
 
 namespace toucan
 {
+    // the reader option declared in Read.h (lives here so the readers link on their own, e.g. in tests/cpp/reader_fuzz.cpp)
+    namespace
+    {
+        std::atomic<bool>& keepUnassociatedAlpha()
+        {
+            static std::atomic<bool> value([] {
+                const char* e = getenv("TOUCAN_UNASSOCIATED_ALPHA");
+                return e && *e && *e != '0';
+            }());
+            return value;
+        }
+    }
+
+    void setKeepUnassociatedAlpha(bool value) { keepUnassociatedAlpha() = value; }
+    bool getKeepUnassociatedAlpha() { return keepUnassociatedAlpha(); }
+
     namespace
     {
         uint32_t be32(const unsigned char* p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | p[3]; }

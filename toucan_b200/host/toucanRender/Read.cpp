@@ -13,21 +13,6 @@
 
 namespace toucan
 {
-    namespace
-    {
-        std::atomic<bool>& keepUnassociatedAlpha()
-        {
-            static std::atomic<bool> value([] {
-                const char* e = getenv("TOUCAN_UNASSOCIATED_ALPHA");
-                return e && *e && *e != '0';
-            }());
-            return value;
-        }
-    }
-
-    void setKeepUnassociatedAlpha(bool value) { keepUnassociatedAlpha() = value; }
-    bool getKeepUnassociatedAlpha() { return keepUnassociatedAlpha(); }
-
     void MediaStore::set(const std::string& path, const MediaFrame& frame)
     {
         std::lock_guard<std::mutex> lock(_mutex);
@@ -313,10 +298,13 @@ namespace toucan
             Image cached;
             if (store->getCached(device, path, cached) && cached.spec().image_bytes() == spec.image_bytes())
             {
+                // another worker of this GPU may have uploaded it on its own stream: wait for that copy
+                cached.acquire();
                 return cached;
             }
             cached = Image::upload(frame.host, spec);
             cached.keepAlive(frame.storage ? std::shared_ptr<const void>(frame.storage) : std::shared_ptr<const void>(frame.owned));
+            cached.publish(); // before any other thread can find it in the cache
             store->countUpload(spec.image_bytes());
             store->putCached(device, path, cached);
             return cached;

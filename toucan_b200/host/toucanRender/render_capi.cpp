@@ -214,6 +214,20 @@ extern "C"
         return 0;
     }
 
+    int tr_timeline_upload_stats(const tr_timeline* timeline, unsigned long long* uploads, unsigned long long* bytes)
+    {
+        if (!timeline) return fail("tr_timeline_upload_stats: null");
+        if (uploads) *uploads = timeline->store->getUploadCount();
+        if (bytes) *bytes = timeline->store->getUploadBytes();
+        return 0;
+    }
+
+    int tr_timeline_drop_source_cache(tr_timeline* timeline)
+    {
+        if (!timeline) return fail("tr_timeline_drop_source_cache: null");
+        return guarded([&] { timeline->store->dropCached(); return 0; });
+    }
+
     int tr_timeline_prepare(tr_timeline* timeline)
     {
         if (!timeline) return fail("tr_timeline_prepare: null");

@@ -36,6 +36,8 @@ _SIGS = {
     "tr_timeline_set_media": [_VP, ctypes.c_char_p, _VP, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int],
     "tr_timeline_prepare": [_VP],
     "tr_timeline_set_source_cache": [_VP, ctypes.c_size_t],
+    "tr_timeline_upload_stats": [_VP, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)],
+    "tr_timeline_drop_source_cache": [_VP],
     "tr_timeline_info": [_VP, _DP, _DP, _IP, _IP, _IP, _IP],
     "tr_timeline_describe": [_VP, _VP, ctypes.c_double, ctypes.c_char_p, ctypes.c_size_t],
     "tr_timeline_render": [_VP, _VP, ctypes.c_double, _VP, ctypes.c_size_t, _IP, _IP, _IP],
@@ -244,6 +246,15 @@ class Timeline:
     def set_source_cache(self, nbytes: int):
         """Keep up to `nbytes` of uploaded host frames resident per GPU (0 = upload on every frame)."""
         _check(lib().tr_timeline_set_source_cache(self._t, int(nbytes)), "tr_timeline_set_source_cache")
+
+    def upload_stats(self):
+        """(uploads, bytes) of source frames copied host -> device so far."""
+        n, b = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        _check(lib().tr_timeline_upload_stats(self._t, ctypes.byref(n), ctypes.byref(b)), "tr_timeline_upload_stats")
+        return n.value, b.value
+
+    def drop_source_cache(self):
+        _check(lib().tr_timeline_drop_source_cache(self._t), "tr_timeline_drop_source_cache")
 
     def prepare(self):
         _check(lib().tr_timeline_prepare(self._t), "tr_timeline_prepare")
