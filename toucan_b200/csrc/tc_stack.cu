@@ -23,7 +23,12 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
+
+#include <cuda.h> // CUtensorMap (types only: the encoder is looked up through cudaGetDriverEntryPoint)
 
 #include "tc_tile.cuh"
 
@@ -51,6 +56,7 @@ struct StUnit {
     short kernel;
     short flags;
     int next_staged;    // index of the next staged unit (prefetch target), or -1
+    short map, map2;    // k_stack_tma: tensor maps of src / src2
 };
 struct StParams {
     int w, h, n_units, first_staged;
@@ -201,6 +207,253 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_stack_f32(float4* __restric
     }
 }
 
+
+// =====================================================================================================
+// k_stack_tma: the same chain with the source tiles moved by the TMA engine and no CTA-wide barrier.
+//
+//   * One CUtensorMap per source frame (2-D: 2W x H elements of 8 bytes, so a pixel is two elements and the
+//     box may be IWP = 64 + 2R + 1 pixels wide -- the odd row pitch the row pass wants -- without exceeding
+//     the 256-element box limit).  ONE cp.async.bulk.tensor.2d moves a (64+2R+1) x (24+2R) tile; its completion
+//     is counted on an mbarrier ("full").  There is no producer warp (a ninth warp would cost every warp 16
+//     registers: the register file is split over four schedulers): a staging buffer is handed back through a
+//     shared-memory counter, and the lane whose warp hands it back LAST issues the copy of the tile after next
+//     into it -- nobody ever blocks on "empty".  The 8 warps never touch global memory for staged layers.
+//   * TMA fills out-of-frame cells with zeros, OIIO's convolve clamps: the ~3 % of tiles that touch the frame
+//     border patch those cells from the clamped in-frame cell of the same tile after it lands (the only place a
+//     consumer-wide named barrier is used).
+//   * The row-pass result is warp-private: warp w filters the 8-column strip w of the tile (lane = source row),
+//     writes its own 9-pixel-pitch strip of `mid`, and runs the column pass on the same strip (lane = column x
+//     4 row segments of 6), so row -> column needs __syncwarp only.  Warps drift apart and the shared-memory
+//     heavy row pass of one overlaps the FMA heavy column pass of another.
+template <int R, int TH>
+struct StTma {
+    static constexpr int PX = 6;                       // rows per lane in the column pass (4 segments x 6 = TH)
+    static constexpr int IW = ST_TW + 2 * R, IH = TH + 2 * R, IWP = IW | 1;
+    static constexpr int IN_BYTES = ((IH * IWP * 16) + 127) / 128 * 128;
+    static constexpr int MP = ST_HB + 1;               // strip pitch (pixels): odd, row-per-lane stores conflict-free
+    static constexpr int MID_BYTES = 8 * IH * MP * 16; // 8 warps
+    static constexpr int BAR_BYTES = 64; // full[2], (unused) empty[2], released[2]
+    static constexpr size_t SMEM = 2 * IN_BYTES + MID_BYTES + BAR_BYTES;
+    static_assert(TH == 4 * PX, "column pass: 4 segments of 6 rows");
+};
+constexpr int ST_MAX_MAPS = 2 * ST_MAX_LAYERS;
+constexpr int ST_TMA_THREADS = ST_THREADS;
+
+struct StTmaParams {
+    StParams p;
+    int n_tiles;                    // staged tiles per CTA, in consumption order
+    short tile_map[ST_MAX_MAPS];    // tile -> tensor map
+    alignas(64) CUtensorMap maps[ST_MAX_MAPS];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
+                     smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(ST_THREADS) : "memory"); }
+
+// cells of a landed tile that lie outside the frame <- the clamped in-frame cell of the same tile
+template <int R, int TH>
+__device__ __forceinline__ void tile_clamp_patch(float4* in, int w, int h, int x0, int y0)
+{
+    using T = StTma<R, TH>;
+    for (int i = threadIdx.x; i < T::IH * T::IW; i += ST_THREADS) {
+        const int r = i / T::IW, c = i - r * T::IW;
+        const int sx = x0 - R + c, sy = y0 - R + r;
+        const int cx = min(max(sx, 0), w - 1), cy = min(max(sy, 0), h - 1);
+        if (cx != sx || cy != sy) in[r * T::IWP + c] = in[(cy - (y0 - R)) * T::IWP + (cx - (x0 - R))];
+    }
+}
+
+template <int R, int TH, bool MIX>
+__device__ __forceinline__ void strip_rows(const float4* ina, const float4* inb, float wa, float wb, float4* strip, int xb, int lane,
+                                           const float (&g)[2 * R + 1])
+{
+    using T = StTma<R, TH>;
+    for (int row = lane; row < T::IH; row += 32) {
+        const int base = row * T::IWP + xb * ST_HB;
+        float4* m = strip + row * T::MP;
+        float4 o[ST_HB];
+#pragma unroll
+        for (int j = 0; j < ST_HB + 2 * R; ++j) {
+            float4 q = ina[base + j];
+            if (MIX) q = fma4p(wa, q, mul4p(wb, inb[base + j]));
+#pragma unroll
+            for (int k = 0; k < ST_HB; ++k) {
+                const int t = j - k;
+                if (t == 0) o[k] = mul4p(g[0], q);
+                else if (t > 0 && t <= 2 * R) o[k] = fma4p(g[t], q, o[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ST_HB; ++k) m[k] = o[k];
+    }
+}
+
+template <int R, int TH>
+__device__ __forceinline__ void strip_cols(const float4* strip, int lane, const float (&g)[2 * R + 1], float4 (&out)[StTma<R, TH>::PX])
+{
+    using T = StTma<R, TH>;
+    const int col = lane % ST_HB, seg = lane / ST_HB;
+    const float4* p = strip + (seg * T::PX) * T::MP + col;
+#pragma unroll
+    for (int j = 0; j < T::PX + 2 * R; ++j) {
+        const float4 q = p[j * T::MP];
+#pragma unroll
+        for (int k = 0; k < T::PX; ++k) {
+            const int t = j - k;
+            if (t == 0) out[k] = mul4p(g[0], q);
+            else if (t > 0 && t <= 2 * R) out[k] = fma4p(g[t], q, out[k]);
+        }
+    }
+}
+
+template <int R, int TH, int OCC>
+__global__ void __launch_bounds__(ST_TMA_THREADS, OCC) k_stack_tma(float4* __restrict__ dst, const __grid_constant__ StTmaParams Q)
+{
+    using T = StTma<R, TH>;
+    constexpr int PX = T::PX;
+    const StParams& P = Q.p;
+    extern __shared__ __align__(128) unsigned char smem_raw[]; // (no pointer arithmetic through integers: keeps LDS / STS)
+    unsigned char* base = smem_raw;
+    float4* buf0 = (float4*)base;
+    float4* buf1 = (float4*)(base + T::IN_BYTES);
+    float4* mid = (float4*)(base + 2 * T::IN_BYTES);
+    uint64_t* full = (uint64_t*)(base + 2 * T::IN_BYTES + T::MID_BYTES); // [2]
+    uint64_t* empty = full + 2;                                          // [2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_band = P.band * P.tiles_x;
+    const int band = blockIdx.x / per_band, within = blockIdx.x - band * per_band;
+    const int bh = min(P.band, P.tiles_y - band * P.band);
+    const int tx = within / bh, ty = band * P.band + (within - tx * bh);
+    const int x0 = tx * ST_TW, y0 = ty * TH;
+
+    int* released = (int*)(empty + 2); // [2] warps that have handed the buffer back
+    (void)empty;
+    constexpr unsigned TILE_BYTES = (unsigned)(T::IH * T::IWP * 16);
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        released[0] = released[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        // the first two tiles
+        for (int t = 0; t < 2 && t < Q.n_tiles; ++t) {
+            mbar_expect_tx(&full[t], TILE_BYTES);
+            tma_load_tile(t ? buf1 : buf0, &Q.maps[Q.tile_map[t]], 2 * (x0 - R), y0 - R, &full[t]);
+        }
+    }
+    __syncthreads();
+    // hand staging buffer s (it held tile `tile`) back; the last warp to do so starts the copy of tile + 2 into it
+    auto release = [&](int s, int tile) {
+        int prev;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;\n" : "=r"(prev) : "r"(smem_u32(&released[s])) : "memory");
+        if (prev == ST_THREADS / 32 - 1) {
+            released[s] = 0;
+            if (tile + 2 < Q.n_tiles) {
+                // the warps' generic-proxy reads (and border patches) of this buffer are ordered before the copy's async-proxy writes
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_expect_tx(&full[s], TILE_BYTES);
+                tma_load_tile(s ? buf1 : buf0, &Q.maps[Q.tile_map[tile + 2]], 2 * (x0 - R), y0 - R, &full[s]);
+            }
+        }
+    };
+
+    // ===== consumers =====
+    const int xb = warp;                                 // this warp's 8-column strip
+    float4* strip = mid + warp * (T::IH * T::MP);
+    const int col = lane % ST_HB, seg = lane / ST_HB;
+    const int x = x0 + xb * ST_HB + col, y = y0 + seg * PX;
+    const bool border = x0 - R < 0 || y0 - R < 0 || x0 + ST_TW + R > P.w || y0 + TH + R > P.h;
+
+    float4 acc[PX];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) acc[k] = P.background;
+
+    int seq = 0;
+    for (int u = 0; u < P.n_units; ++u) {
+        const StUnit& U = P.unit[u];
+        float4 f[PX];
+        if (U.flags & ST_DIRECT) {
+            tile_load<PX>(U.src, P.w, P.h, x, y, f);
+            if (U.src2) {
+                float4 fb[PX];
+                tile_load<PX>(U.src2, P.w, P.h, x, y, fb);
+#pragma unroll
+                for (int k = 0; k < PX; ++k) f[k] = mix4(f[k], fb[k], U.w, U.w2);
+            }
+        } else {
+            const StKernel& K = P.k[U.kernel];
+            float g[2 * R + 1];
+#pragma unroll
+            for (int t = 0; t <= 2 * R; ++t) {
+                const int sft = t - R + K.R;
+                g[t] = (sft >= 0 && sft <= 2 * K.R) ? K.g[sft] : 0.0f;
+            }
+            const bool mix = (U.flags & ST_MIX) != 0;
+            const int s = seq & 1;
+            float4* ina = s ? buf1 : buf0;
+            float4* inb = s ? buf0 : buf1;
+            mbar_wait(&full[s], (seq >> 1) & 1);
+            if (mix) mbar_wait(&full[s ^ 1], ((seq + 1) >> 1) & 1);
+            if (border) {
+                tile_clamp_patch<R, TH>(ina, P.w, P.h, x0, y0);
+                if (mix) tile_clamp_patch<R, TH>(inb, P.w, P.h, x0, y0);
+                consumer_sync();
+            }
+            __syncwarp(); // the previous layer's column pass has left this warp's strip
+            if (mix) strip_rows<R, TH, true>(ina, inb, U.w, U.w2, strip, xb, lane, g);
+            else strip_rows<R, TH, false>(ina, ina, 1.0f, 0.0f, strip, xb, lane, g);
+            __syncwarp();
+            if (lane == 0) {
+                release(s, seq); // this warp is done with the staged tile(s)
+                if (mix) release(s ^ 1, seq + 1);
+            }
+            seq += mix ? 2 : 1;
+            strip_cols<R, TH>(strip, lane, g, f);
+        }
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            float4 p = f[k];
+            const float a = p.w;
+            const float pm = a != 1.0f ? a : 1.0f;
+            p.x *= pm;
+            p.y *= pm;
+            p.z *= pm;
+            const float oma = 1.0f - fminf(fmaxf(a, 0.0f), 1.0f);
+            acc[k] = fma4p(oma, acc[k], p);
+        }
+    }
+    if (x < P.w) {
+#pragma unroll
+        for (int k = 0; k < PX; ++k)
+            if (y + k < P.h) __stcs(dst + (size_t)(y + k) * P.w + x, acc[k]);
+    }
+}
+
 // same construction as tc_conv.cu build_params (OIIO make_kernel + convolve normalisation)
 static float st_fast_exp(float xin)
 {
@@ -281,6 +534,100 @@ static int launch_stack(const tc_image* dst, StParams& P, cudaStream_t st)
     return check_cuda(cudaGetLastError(), "k_stack_f32 launch");
 }
 
+// ---- tensor maps -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// (pointer, frame size, box) -> descriptor; a render reads the same stills frame after frame
+static int tensor_map_for(const void* ptr, int w, int h, int box_px, int box_rows, CUtensorMap* out)
+{
+    typedef std::tuple<const void*, int, int, int, int> Key;
+    static std::mutex m;
+    static std::map<Key, CUtensorMap> cache;
+    const Key key(ptr, w, h, box_px, box_rows);
+    {
+        std::lock_guard<std::mutex> lock(m);
+        const auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return TC_OK;
+        }
+    }
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: cuTensorMapEncodeTiled is not available");
+    // a pixel (16 bytes) = two 8-byte elements, so an odd pixel count per box row is expressible
+    const cuuint64_t dims[2] = { (cuuint64_t)w * 2, (cuuint64_t)h };
+    const cuuint64_t strides[1] = { (cuuint64_t)w * 16 };
+    const cuuint32_t box[2] = { (cuuint32_t)box_px * 2, (cuuint32_t)box_rows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    CUtensorMap tm;
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: cuTensorMapEncodeTiled failed (%d) for a %d x %d frame", (int)r, w, h);
+    std::lock_guard<std::mutex> lock(m);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = tm;
+    *out = tm;
+    return TC_OK;
+}
+
+static bool st_use_tma()
+{
+    static const bool on = [] {
+        const char* e = getenv("TOUCAN_STACK_TMA");
+        return !(e && *e == '0');
+    }();
+    return on;
+}
+
+template <int R, int TH>
+static int launch_stack_tma(const tc_image* dst, StParams& P, cudaStream_t st)
+{
+    using T = StTma<R, TH>;
+    static_assert(T::SMEM <= 227 * 1024, "tile does not fit in shared memory");
+    constexpr int OCC = T::SMEM <= 113 * 1024 ? 2 : 1;
+    StTmaParams Q;
+    int n_maps = 0;
+    for (int u = 0; u < P.n_units; ++u) {
+        StUnit& U = P.unit[u];
+        U.map = U.map2 = -1;
+        if (U.flags & ST_DIRECT) continue;
+        if (n_maps + 2 > ST_MAX_MAPS) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: too many staged sources");
+        int e = tensor_map_for(U.src, P.w, P.h, T::IWP, T::IH, &Q.maps[n_maps]);
+        if (e != TC_OK) return e;
+        Q.tile_map[n_maps] = (short)n_maps;
+        U.map = (short)n_maps++;
+        if (U.flags & ST_MIX) {
+            e = tensor_map_for(U.src2, P.w, P.h, T::IWP, T::IH, &Q.maps[n_maps]);
+            if (e != TC_OK) return e;
+            Q.tile_map[n_maps] = (short)n_maps;
+            U.map2 = (short)n_maps++;
+        }
+    }
+    int st_attr = ensure_dynamic_smem((const void*)k_stack_tma<R, TH, OCC>, T::SMEM);
+    if (st_attr != TC_OK) return st_attr;
+    P.tiles_x = (dst->w + ST_TW - 1) / ST_TW;
+    P.tiles_y = (dst->h + TH - 1) / TH;
+    P.band = min(st_band(), P.tiles_y);
+    Q.p = P;
+    Q.n_tiles = n_maps;
+    k_stack_tma<R, TH, OCC><<<P.tiles_x * P.tiles_y, ST_TMA_THREADS, T::SMEM, st>>>((float4*)dst->data, Q);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_stack_tma launch");
+}
+
 } // namespace tc
 
 using namespace tc;
@@ -347,6 +694,17 @@ extern "C" int tc_stack_f32(const tc_image* dst, const float background[4], cons
     }
     P.n_units = nu;
     cudaStream_t st = (cudaStream_t)s;
+    // the TMA kernel: frames at least one tile large whose rows are 16-byte multiples (always) and whose base is 16-byte aligned
+    bool tma = st_use_tma() && encode_tiled() != nullptr && dst->w >= ST_TW && dst->h >= 24;
+    for (int u = 0; u < nu && tma; ++u)
+        if (((uintptr_t)P.unit[u].src | (uintptr_t)P.unit[u].src2) & 15) tma = false;
+    if (tma) {
+        if (maxR <= 2) return launch_stack_tma<2, 24>(dst, P, st);
+        if (maxR <= 4) return launch_stack_tma<4, 24>(dst, P, st);
+        if (maxR <= 6) return launch_stack_tma<6, 24>(dst, P, st);
+        if (maxR <= 9) return launch_stack_tma<9, 24>(dst, P, st);
+        return launch_stack_tma<12, 24>(dst, P, st);
+    }
     if (maxR <= 2) return launch_stack<2, 24, 2>(dst, P, st);
     if (maxR <= 4) return launch_stack<4, 24, 2>(dst, P, st);
     if (maxR <= 6) return launch_stack<6, 24, 2>(dst, P, st);

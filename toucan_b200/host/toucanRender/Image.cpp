@@ -1,6 +1,8 @@
 #include "Image.h"
 
 #include <atomic>
+#include <mutex>
+#include <set>
 #include <sstream>
 
 namespace toucan
@@ -15,6 +17,27 @@ namespace toucan
             bool ownStream = false;
         };
         thread_local Binding binding;
+
+        // Streams created by bind() that are still alive.  A buffer can outlive the worker thread that allocated it (a cached
+        // source frame): its release must not touch a destroyed stream handle.
+        std::mutex ownedStreamsMutex;
+        std::set<tc_stream> ownedStreams;
+
+        bool streamIsGone(tc_stream stream, bool owned)
+        {
+            if (!owned) return false; // a caller-provided stream (tr_bind_stream): the caller keeps it alive
+            std::lock_guard<std::mutex> lock(ownedStreamsMutex);
+            return 0 == ownedStreams.count(stream);
+        }
+
+        void destroyOwnedStream(tc_stream stream)
+        {
+            {
+                std::lock_guard<std::mutex> lock(ownedStreamsMutex);
+                ownedStreams.erase(stream);
+            }
+            tc_stream_destroy(stream);
+        }
     }
 
     void tcCheck(int status, const char* what)
@@ -32,7 +55,8 @@ namespace toucan
         tcCheck(tc_set_device(device), "tc_set_device");
         if (binding.bound && binding.ownStream && binding.stream)
         {
-            tc_stream_destroy(binding.stream);
+            tc_stream_sync(binding.stream);
+            destroyOwnedStream(binding.stream);
         }
         binding.device = device;
         binding.ownStream = false;
@@ -41,6 +65,8 @@ namespace toucan
         {
             tcCheck(tc_stream_create(&binding.stream), "tc_stream_create");
             binding.ownStream = true;
+            std::lock_guard<std::mutex> lock(ownedStreamsMutex);
+            ownedStreams.insert(binding.stream);
         }
         binding.bound = true;
     }
@@ -50,7 +76,7 @@ namespace toucan
         if (binding.bound && binding.stream)
         {
             tc_stream_sync(binding.stream);
-            if (binding.ownStream) tc_stream_destroy(binding.stream);
+            if (binding.ownStream) destroyOwnedStream(binding.stream);
         }
         binding = Binding();
     }
@@ -67,6 +93,11 @@ namespace toucan
     {
         if (!binding.bound) bind(0);
         return binding.stream;
+    }
+
+    bool DeviceContext::streamIsOwned()
+    {
+        return binding.bound && binding.ownStream;
     }
 
     void DeviceContext::synchronize()
@@ -91,6 +122,7 @@ namespace toucan
     {
         void* p = nullptr;
         tc_stream stream = nullptr;
+        bool streamOwned = false;               // `stream` was created by DeviceContext::bind (it ends with its thread)
         std::shared_ptr<const void> hostSource; // page-locked host memory an asynchronous upload is still reading
         tc_event ready = nullptr;               // publish(): the contents are complete on `stream` at this point
         std::atomic<bool> shared{ false };      // acquire()d from another stream: readers are not ordered by `stream`
@@ -99,7 +131,7 @@ namespace toucan
             // Stream-ordered release when only the allocating stream ever touched the buffer.  A buffer other streams
             // have read (cached sources), or whose stream / device binding is gone (a cached frame outliving its
             // worker), is released with cudaFree, which waits for all work on the device.
-            if (p && (shared.load() || tc_free(p, stream) != TC_OK)) tc_free_sync(p);
+            if (p && (shared.load() || streamIsGone(stream, streamOwned) || tc_free(p, stream) != TC_OK)) tc_free_sync(p);
             if (ready) tc_event_destroy(ready);
         }
     };
@@ -115,6 +147,7 @@ namespace toucan
             }
             _buffer = std::make_shared<Buffer>();
             _buffer->stream = DeviceContext::stream();
+            _buffer->streamOwned = DeviceContext::streamIsOwned();
             tcCheck(tc_malloc(&_buffer->p, bytes, _buffer->stream), "tc_malloc");
             _data = _buffer->p;
         }

@@ -27,6 +27,8 @@ namespace toucan
         static bool isBound();
         static int device();
         static tc_stream stream();
+        //! Whether bind() created the thread's stream (it is destroyed with the binding) or the caller provided it.
+        static bool streamIsOwned();
         static void synchronize();
     };
 
