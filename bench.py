@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- frames/s and HBM GB/s of the toucan render hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|c2|c3|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c5|s4k|c2|c3|c4]
 
 Workloads (BASELINE.json `configs`; a "step" is one timeline frame):
   c5 (default, configs[4], the configuration the 1/2/4/8-GPU metric is quoted on): synthetic 1000-frame, 10-track
       7680x4320 RGBA float32 timeline, toucan:Blur radius 10 on every clip, toucan:Dissolve between clips, tracks
       composited premult+over on black.  Timed steps alternate plain (10 sources) and mid-transition (20 sources) frames.
+  s4k the c5 timeline at 3840x2160: north_star's "synthetic 4K RGBA-float multi-effect timeline" (target >= 60 % of the HBM roofline)
   c2  configs[1]: the six filters of data/Filter.otio chained on one clip, 1920x1080 RGBA float32
   c3  configs[2]: data/MultipleEffects.otio's structure at 3840x2160 RGBA half
   c4  configs[3]: data/Transform.otio's structure at 3840x2160 RGBA float32
@@ -210,12 +211,18 @@ def c5_e2e_window(rank, world, cfg, steps):
 
 
 def c5_config_json(cfg, world):
-    return {"workload": "c5: synthetic 1000-frame 10-track 7680x4320 RGBA float32 timeline, blur(radius 10)+dissolve per track, "
-                        "premult+over stack (BASELINE.json configs[4])",
+    if (cfg["width"], cfg["height"]) == (3840, 2160):
+        label = ("s4k: the c5 timeline at 3840x2160 -- north_star's \"synthetic 4K RGBA-float multi-effect timeline\": 1000 frames, 10 tracks, "
+                 "blur(radius 10)+dissolve per track, premult+over stack, RGBA float32")
+    else:
+        label = ("c5: synthetic 1000-frame 10-track 7680x4320 RGBA float32 timeline, blur(radius 10)+dissolve per track, "
+                 "premult+over stack (BASELINE.json configs[4])")
+    mb = cfg["width"] * cfg["height"] * 16 / 1e6
+    return {"workload": label,
             "width": cfg["width"], "height": cfg["height"], "tracks": cfg["tracks"], "frames": cfg["frames"],
             "frame_mix": "timed steps alternate plain (10 sources) and mid-transition (20 sources) frames: 50:50",
             "sharding": f"contiguous frame blocks over {world} GPU(s), no collective",
-            "l2": "inputs larger than L2 (each source frame 531 MB, 10-20 per step)"}
+            "l2": f"inputs larger than L2 (each source frame {mb:.0f} MB, 10-20 per step)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -287,7 +294,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     world = max(1, args.gpus)
-    if args.workload == "c5":
+    if args.workload in ("c5", "s4k"):
         full = args.steps + args.warmup <= FULL_FRAME_STEPS
         frames = c5_frames(0, world, cfg, args.steps + args.warmup)
         info = c5_cpu_arm(cfg, c5_sources_numpy(cfg), frames, args.warmup, full)
@@ -528,7 +535,7 @@ def run_c5(args, cfg):
                "h2d_GBs_aggregate": h2d_total / dt / 1e9, "d2h_GBs_aggregate": world * e2e_steps * F / dt / 1e9,
                "note": "toucan::FrameScheduler through the C API: source stills in pinned host memory, device source cache EMPTY at the "
                        "start of the timed region, each still uploaded the first time a frame reads it (de-duplicated by media path: "
-                       f"{int(up_n)} uploads of 531 MB on this rank), {e2e_steps} consecutive frames (half before, half inside a "
+                       f"{int(up_n)} uploads of {F / 1e6:.0f} MB on this rank), {e2e_steps} consecutive frames (half before, half inside a "
                        "transition) rendered and every finished float32 frame downloaded into a pinned ring for the ordered writer; "
                        "wall clock, max over ranks"}
         if os.environ.get("TOUCAN_BENCH_REUPLOAD", "1") != "0":
@@ -574,7 +581,7 @@ def run_c5(args, cfg):
                              "traffic_source": "profiles/ stack traffic json (ncu dram__bytes_read+write per launch, plain / "
                                                "transition frames, weighted by this run's frame mix)",
                              "algorithmic_bytes_per_launch": alg_bytes / args.steps,
-                             "note": "bytes = (sources referenced + 1 output) x 530,841,600 B per frame; one launch per frame; "
+                             "note": f"bytes = (sources referenced + 1 output) x {F:,} B per frame; one launch per frame; "
                                      "rank-0-equivalent (max-over-ranks time)"},
                 "cpu_baseline": cpu, "e2e": e2e, "e2e_reupload_every_frame": e2e_reupload, "gpu_launches": int(launches), "clocks": clk,
                 "checksum": checksum}
@@ -705,16 +712,18 @@ def main():
     ap.add_argument("--steps", type=int, default=240)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "s4k", "c2", "c3", "c4"])
     ap.add_argument("--scale", type=float, default=1.0, help="debug: shrink the c5 frame (NOT a valid bench number)")
     args = ap.parse_args()
     cfg = dict(workloads.C5)
     if args.scale != 1.0:
         cfg["width"] = max(64, int(cfg["width"] * args.scale))
         cfg["height"] = max(64, int(cfg["height"] * args.scale) // BAND_DIV * BAND_DIV)
+    if args.workload == "s4k":
+        cfg.update(width=3840, height=2160)
     if args.impl == "reference":
         run_reference(args, cfg)
-    elif args.workload == "c5":
+    elif args.workload in ("c5", "s4k"):
         run_c5(args, cfg)
     else:
         run_small(args)

@@ -503,3 +503,71 @@ def test_frame_buffer_cache_reuses_across_streams_in_order():
     capi.check(lib.tc_pool_trim(), "tc_pool_trim")
     lib.tc_stream_destroy(s1)
     lib.tc_stream_destroy(s2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# compute-sanitizer is closed on this GPU pool (profiles/r02_compute_sanitizer_refused.txt), so the tiled kernels are
+# checked the way the pool asks for: outputs inside guard bands that must stay untouched (an out-of-bounds store shows),
+# sources followed by poisoned memory (an out-of-bounds load that reaches the result shows), and the same launch repeated
+# many times with bit-identical results (a race between the asynchronous tile copies and the warps that read them would
+# not reproduce).  Sizes are chosen to have partial tiles and border tiles on every side.
+def _guarded(w, h, dt=torch.float32, fill=float("nan")):
+    pad = 4096
+    flat = torch.full((pad + h * w * 4 + pad,), fill, dtype=dt, device="cuda")
+    return flat, flat[pad:pad + h * w * 4].view(h, w, 4)
+
+
+@pytest.mark.parametrize("w,h,radius", [(203, 77, 10.0), (64, 24, 10.0), (129, 49, 20.0), (517, 263, 10.0)])
+def test_stack_kernel_stays_inside_its_buffers_and_is_deterministic(T, w, h, radius):
+    srcs = []
+    for i in range(6):
+        flat, view = _guarded(w, h)
+        view.copy_(to_dev(rand_img(w, h, np.float32, 900 + i)))
+        srcs.append((flat, view))
+    d = [v for _, v in srcs]
+    layers = [(d[0], None, radius, 0.0, 0.0), (d[1], d[2], radius, radius, 0.3), (d[3], None, 0.0, 0.0, 0.0), (d[4], d[5], radius, radius, 0.75)]
+    flat, out = _guarded(w, h, fill=123.0)
+    first = None
+    for rep in range(25):
+        out.fill_(-7.0)
+        T.stack_f32(w, h, [0.1, 0.2, 0.3, 1.0], layers, out=out)
+        torch.cuda.synchronize()
+        assert bool((flat[:4096] == 123.0).all()) and bool((flat[-4096:] == 123.0).all()), "store outside the output frame"
+        assert bool(torch.isfinite(out).all()), "a poisoned (out-of-frame) source value reached the result"
+        if first is None:
+            first = out.clone()
+        else:
+            assert torch.equal(first, out), f"run {rep} differs from run 0"
+    a = [to_host(v) for v in d]
+    acc = O.fill(w, h, [0.1, 0.2, 0.3, 1.0], O.F32)
+    for sa, sb, ra, rb, v in [(a[0], None, radius, 0.0, 0.0), (a[1], a[2], radius, radius, 0.3), (a[3], None, 0.0, 0.0, 0.0), (a[4], a[5], radius, radius, 0.75)]:
+        x = O.blur(sa, ra) if ra > 0 else sa
+        if sb is not None:
+            x = O.dissolve(x, O.blur(sb, rb) if rb > 0 else sb, v)
+        acc = O.comp(x, acc, True)
+    assert_close(first, acc, "guarded stack vs oracle")
+
+
+@pytest.mark.parametrize("op", ["blur", "unsharp", "resize_down", "resize_up", "rotate"])
+def test_tiled_filters_are_deterministic_with_poisoned_surroundings(T, op):
+    w, h = 333, 217
+    flat, src = _guarded(w, h)
+    src.copy_(to_dev(rand_img(w, h, np.float32, 950)))
+    first = None
+    for rep in range(10):
+        if op == "blur":
+            got = T.blur(src, 10.0)
+        elif op == "unsharp":
+            got = T.unsharp_mask(src, "gaussian", 10.0, 1.0, 0.0)
+        elif op == "resize_down":
+            got = T.resize(src, (160, 101))
+        elif op == "resize_up":
+            got = T.resize(src, (700, 450))
+        else:
+            got = T.rotate(src, 33.0)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(got).all()), op
+        if first is None:
+            first = got.clone()
+        else:
+            assert torch.equal(first, got), f"{op}: run {rep} differs from run 0"

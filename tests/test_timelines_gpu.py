@@ -16,6 +16,7 @@ from oracle import graph as G
 from oracle import oracle as O
 from tests import media
 from tests import timelines as TL
+from tests.envelope import assert_within_envelope, envelope
 
 pytestmark = pytest.mark.gpu
 
@@ -56,11 +57,14 @@ def test_fixture_timeline_matches_oracle(host, name):
             diff = np.abs(got.astype(np.int64) - want.astype(np.int64))
             d = int(diff.max())
             worst = max(worst, d)
-            # +-1 LSB per filtering op.  MultipleEffects applies Pow 3.0 to the whole stack AFTER the
-            # blur (ImageGraph.cpp:203): a +-1 LSB flip at the blur's u8 boundary is amplified by
-            # d(x^3)/dx <= 3, so the chain's bound is 3 LSB, on the (rare) flipped values only.
-            bound = 3 if name == "MultipleEffects.otio" else 1
-            assert d <= bound, f"{name} @ {t.value}: max LSB diff {d}"
+            if name == "MultipleEffects.otio":
+                # Blur -> Invert -> over -> Pow 3: ops downstream of the Blur's u8 store see a +-1 LSB flip of it (about one
+                # store in 10^4) and Pow amplifies it.  The exact bar (tests/envelope.py): the frame lies between the
+                # oracle's frames with the tolerant ops' stores moved by -1 / 0 / +1 code, +-1 LSB for the last op.
+                lo, hi, _ = envelope(otl, media.decode, t, alpha_varies=False)
+                assert_within_envelope(got, lo, hi, f"{name} @ {t.value}")
+            else:
+                assert d <= 1, f"{name} @ {t.value}: max LSB diff {d}"
             assert float((diff > 1).mean()) < 1e-3, f"{name} @ {t.value}: {int((diff > 1).sum())} values off by more than 1 LSB"
     tl.close()
 
@@ -189,11 +193,14 @@ def test_stack_timeline_other_types_take_the_node_path(host, dtype):
         want = og.render(G.RT(float(f), 24.0))
         got = tl.render(host, float(f))
         assert got.dtype == want.dtype and got.shape == want.shape
-        if dtype == np.float16:
-            d = np.abs(got.astype(np.float32) - want.astype(np.float32)).max()
-            assert d <= 2e-3, d  # +-1 half LSB at values near 1, through 2 node chains
-        else:
-            assert int(np.abs(got.astype(np.int64) - want.astype(np.int64)).max()) <= 1
+        # Blur stores may flip by one code; Dissolve and premult + over downstream of them are exact (tests/envelope.py)
+        lo, hi, base = envelope(otl, lambda p: frames.get(p), G.RT(float(f), 24.0))
+        assert np.array_equal(base, want)
+        assert_within_envelope(got, lo, hi, f"{np.dtype(dtype).name} frame {f}", slack=0)
+        # ... and flips are rare: all but a few values are the oracle's own codes
+        from tests.envelope import ordered
+
+        assert float((np.abs(ordered(got) - ordered(want)) > 1).mean()) < 2e-3
     tl.close()
 
 
