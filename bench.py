@@ -538,7 +538,54 @@ def run_c5(args, cfg):
                        f"{int(up_n)} uploads of {F / 1e6:.0f} MB on this rank), {e2e_steps} consecutive frames (half before, half inside a "
                        "transition) rendered and every finished float32 frame downloaded into a pinned ring for the ordered writer; "
                        "wall clock, max over ranks"}
-        if os.environ.get("TOUCAN_BENCH_REUPLOAD", "1") != "0":
+        if world > 1 and os.environ.get("TOUCAN_BENCH_FANOUT", "1") != "0":
+            # N GPUs of one box read the SAME stills: instead of every rank pulling all 20 through the one PCIe root they share
+            # (N x 10.6 GB), each still crosses PCIe ONCE -- uploaded by the rank that owns it (index % N) -- and is fanned out to the
+            # other GPUs over NVLink (NCCL broadcast: the one real exchange step of the sharded job).  All of it inside the timed region.
+            tl2.close()
+            keys = sorted(host_src)
+            dev_buf = {k: torch.zeros((h, w, 4), dtype=torch.float32, device=dev) for k in keys}
+            tl3 = render.Timeline(json_doc=doc, directory="/synthetic")
+            for k in keys:
+                tl3.set_media(tl3.media_path(workloads.still_url(*k)), dev_buf[k])  # device media: the scheduler uploads nothing
+            tl3.prepare()
+            sink = {"n": 0}
+
+            def writer(frame, pixels):
+                sink["n"] += 1
+
+            tl3.render_range(first + e2e_steps // 2, first + e2e_steps // 2 + 2, writer, devices=[local])  # warm-up
+            for i, k in enumerate(keys):  # NCCL warm-up (communicator channels) on a small slice
+                D.dist.broadcast(dev_buf[k][:8], src=i % world)
+            D.barrier()
+            t0 = time.perf_counter()
+            own = 0
+            for i, k in enumerate(keys):
+                if i % world == rank:
+                    dev_buf[k].copy_(host_src[k], non_blocking=True)
+                    own += 1
+                D.dist.broadcast(dev_buf[k], src=i % world)
+            torch.cuda.synchronize()
+            t_dist = time.perf_counter() - t0
+            tl3.render_range(first, first + e2e_steps, writer, devices=[local])
+            dt3 = time.perf_counter() - t0
+            D.barrier()
+            dt3 = D.max(dt3)
+            assert sink["n"] == e2e_steps + 2
+            e2e_independent = dict(e2e, note="informational: every rank uploads all the stills it reads itself (no exchange between GPUs); " + e2e["note"])
+            h2d3 = D.sum(float(own * F))
+            e2e = {"value": world * e2e_steps / dt3, "unit": "frames/s", "h2d_bytes_per_step": int(h2d3 / (world * e2e_steps)),
+                   "d2h_bytes_per_step": F, "steps": e2e_steps, "source_uploads_per_rank": own, "source_distribution_s": D.max(t_dist),
+                   "h2d_GBs_aggregate": h2d3 / dt3 / 1e9, "d2h_GBs_aggregate": world * e2e_steps * F / dt3 / 1e9,
+                   "independent_uploads": e2e_independent,
+                   "note": f"source stills in pinned host memory, each uploaded ONCE per job by the rank that owns it ({own} of {len(keys)} on this "
+                           "rank) and broadcast to the other GPUs over NVLink (NCCL), then toucan::FrameScheduler renders "
+                           f"{e2e_steps} consecutive frames per rank and downloads every finished float32 frame to the ordered writer; upload, "
+                           "broadcast, render and download all inside the timed region; wall clock, max over ranks"}
+            tl3.close()
+            dev_buf.clear()
+            tl2 = None
+        if tl2 is not None and os.environ.get("TOUCAN_BENCH_REUPLOAD", "1") != "0":
             # (informational) round 1's arrangement: no source cache, every frame re-uploads every still it reads
             tl2.set_source_cache(0)
             n_re = min(e2e_steps, 8)
@@ -547,7 +594,8 @@ def run_c5(args, cfg):
                             "d2h_bytes_per_step": F, "steps": n_re,
                             "note": "informational: source cache off, every frame uploads all 10-20 stills it reads (the reference re-reads "
                                     "its media every frame); PCIe-bound by construction"}
-        tl2.close()
+        if tl2 is not None:
+            tl2.close()
 
     cpu = None
     if rank == 0 and world == 1 and os.environ.get("TOUCAN_BENCH_CPU", "1") != "0":

@@ -196,7 +196,9 @@ def test_pow_special_values(T, value):
 @pytest.mark.parametrize("dt", NP_TYPES)
 @pytest.mark.parametrize("radius", [10.0, 20.0, 3.0, 1.0, 7.5, 13.0, 25.0])  # tile templates R = 4, 9, 2, 2, 4, 6, 12
 def test_blur_unsharp(T, dt, radius):
-    for (w, h) in [(333, 217), (40, 30)]:
+    # 332 x 217: rows are 16-byte multiples for every type -> the TMA kernel (k_gauss_tma), partial tiles on both axes;
+    # 333 x 217: odd 8/16-bit row pitches -> the cp-free typed-load kernel (k_gauss_tile); 40 x 30: smaller than a tile
+    for (w, h) in [(332, 217), (333, 217), (40, 30)]:
         src = rand_img(w, h, dt, 3)
         d = to_dev(src)
         assert_close(T.blur(d, radius), O.blur(src, radius), f"blur {radius}")

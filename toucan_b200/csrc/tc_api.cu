@@ -1,5 +1,6 @@
 // tc_api.cu -- runtime part of the C ABI: errors, device/stream management, the
 // stream-ordered frame pool and pinned staging.  See include/toucan_cuda.h.
+#include <tuple>
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -10,6 +11,7 @@
 #include <mutex>
 #include <vector>
 
+#include "tc_tma.cuh"
 #include "tc_common.cuh"
 
 namespace tc {
@@ -76,6 +78,64 @@ int validate(const tc_image* im, const char* name)
 } // namespace tc
 
 using namespace tc;
+
+
+// ---- tensor maps (tc_tma.cuh) ------------------------------------------------------------------------
+namespace tc {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+bool tma_available() { return encode_tiled() != nullptr; }
+
+// a render reads the same stills frame after frame: descriptors are cached by every argument
+int tensor_map_2d(const void* base, int elem_bytes, unsigned long long dim0, unsigned long long dim1, unsigned long long pitch_bytes,
+                  unsigned box0, unsigned box1, CUtensorMap* out)
+{
+    typedef std::tuple<const void*, int, unsigned long long, unsigned long long, unsigned long long, unsigned, unsigned> Key;
+    static std::mutex m;
+    static std::map<Key, CUtensorMap> cache;
+    const Key key(base, elem_bytes, dim0, dim1, pitch_bytes, box0, box1);
+    {
+        std::lock_guard<std::mutex> lock(m);
+        const auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return TC_OK;
+        }
+    }
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail(TC_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+    if (((uintptr_t)base & 15) || (pitch_bytes & 15) || box0 > 256 || box1 > 256 || ((unsigned long long)box0 * elem_bytes & 15))
+        return fail(TC_ERR_INVALID, "tensor map: base, pitch and box row must be 16-byte multiples, box <= 256 elements per side");
+    const cuuint64_t dims[2] = { dim0, dim1 };
+    const cuuint64_t strides[1] = { pitch_bytes };
+    const cuuint32_t box[2] = { box0, box1 };
+    const cuuint32_t estr[2] = { 1, 1 };
+    // plain copies: the element type only sets the element size (and zero as the out-of-bounds fill)
+    const CUtensorMapDataType dt = elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    CUtensorMap tm;
+    const CUresult r = enc(&tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TC_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    std::lock_guard<std::mutex> lock(m);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = tm;
+    *out = tm;
+    return TC_OK;
+}
+} // namespace tc
 
 extern "C" {
 

@@ -6,10 +6,12 @@
 //
 // Tolerance op (<= 1e-5 abs / +-1 LSB), so FMA contraction is allowed in this file.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "tc_tile.cuh"
+#include "tc_tma.cuh"
 
 namespace tc {
 
@@ -128,6 +130,223 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tile(const Img src, c
     }
 }
 
+
+// =====================================================================================================
+// k_gauss_tma: Blur / UnsharpMask with the tile moved by the TMA engine IN ITS STORAGE TYPE (a u8 tile is a
+// quarter of the float one: a quarter of the shared-memory bytes on the way in and out of the row pass, and a
+// quarter of the LDS instructions -- one 16-byte read is four pixels), persistent CTAs that filter tile i while
+// tiles i+1 / i+2 are in flight, warp-private strips between the two passes (no CTA-wide barrier; see tc_stack.cu
+// for the scheme).  The box is the smallest width >= 56 + (pixels one row item reads) whose row pitch is an odd
+// multiple of 16 bytes, so the row-per-lane 16-byte reads are bank-conflict free for every type.
+// 8/16-bit sources: the 1/255 (1/65535) of OIIO's load conversion is folded into the row-pass weights (the taps see
+// integers); the unsharp epilogue converts its centre pixel exactly.
+template <int R, int TYPE>
+struct GtTile {
+    static constexpr int TH = 24, PX = 6;
+    static constexpr int B = TYPE == TC_U8 ? 4 : (TYPE == TC_F32 ? 16 : 8); // bytes per pixel
+    static constexpr int VPX = 16 / B;                                      // pixels per 16-byte vector
+    // TMA wants the first byte of a box row 16-byte aligned: the box starts RA >= R pixels left of the tile, RA a multiple of
+    // the pixels per 16 bytes (found the hard way: an unaligned start is an "illegal instruction" at the copy)
+    static constexpr int RA = (R + VPX - 1) / VPX * VPX;
+    static constexpr int D = RA - R;                                        // tap t of output k reads window pixel k + t + D
+    static constexpr int NPX = (ST_HB + 2 * R + D + VPX - 1) / VPX * VPX;   // pixels one row item reads
+    static constexpr int NV = NPX / VPX;
+    static constexpr int IH = TH + 2 * R;
+    static constexpr int MINW = ST_TW - ST_HB + NPX;
+    static constexpr int box_width()
+    {
+        int w = MINW;
+        while ((w * B) % 32 != 16) ++w;
+        return w;
+    }
+    static constexpr int BW = box_width();
+    static constexpr int PITCH = BW * B;
+    static constexpr int IN_BYTES = (IH * PITCH + 127) / 128 * 128;
+    static constexpr int MP = ST_HB + 1;
+    static constexpr int MID_BYTES = 8 * IH * MP * 16;
+    static constexpr size_t SMEM = 2 * IN_BYTES + MID_BYTES + 64;
+    static constexpr int ELEM = B == 4 ? 4 : 8; // tensor-map element size
+    static constexpr unsigned TILE_BYTES = (unsigned)(IH * PITCH);
+};
+
+template <int TYPE>
+__device__ __forceinline__ void unpack_vec(uint4 v, float4* px)
+{
+    if (TYPE == TC_F32) {
+        px[0] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+    } else if (TYPE == TC_F16) {
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&v.x)), b = __half22float2(*reinterpret_cast<__half2*>(&v.y));
+        const float2 c = __half22float2(*reinterpret_cast<__half2*>(&v.z)), d = __half22float2(*reinterpret_cast<__half2*>(&v.w));
+        px[0] = make_float4(a.x, a.y, b.x, b.y);
+        px[1] = make_float4(c.x, c.y, d.x, d.y);
+    } else if (TYPE == TC_U16) {
+        px[0] = make_float4((float)(v.x & 0xffffu), (float)(v.x >> 16), (float)(v.y & 0xffffu), (float)(v.y >> 16));
+        px[1] = make_float4((float)(v.z & 0xffffu), (float)(v.z >> 16), (float)(v.w & 0xffffu), (float)(v.w >> 16));
+    } else {
+        const unsigned w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            px[i] = make_float4((float)(w[i] & 0xffu), (float)((w[i] >> 8) & 0xffu), (float)((w[i] >> 16) & 0xffu), (float)(w[i] >> 24));
+    }
+}
+// one pixel of the staged tile, converted exactly like a load from global memory
+template <int TYPE>
+__device__ __forceinline__ float4 staged_px(const unsigned char* tile, int byte_offset)
+{
+    if (TYPE == TC_F32) return *reinterpret_cast<const float4*>(tile + byte_offset);
+    if (TYPE == TC_U8) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(tile + byte_offset);
+        return make_float4(u8_to_f(v.x), u8_to_f(v.y), u8_to_f(v.z), u8_to_f(v.w));
+    }
+    const uint2 raw = *reinterpret_cast<const uint2*>(tile + byte_offset);
+    if (TYPE == TC_U16) return make_float4(u16_to_f(raw.x & 0xffffu), u16_to_f(raw.x >> 16), u16_to_f(raw.y & 0xffffu), u16_to_f(raw.y >> 16));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+struct GtParams {
+    int w, h, tiles_x, n_tiles;
+    ConvParams c;
+    alignas(64) CUtensorMap map;
+};
+
+template <int R, int TYPE, bool UNSHARP, int OCC>
+__global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict__ dstp, const __grid_constant__ GtParams Q)
+{
+    using T = GtTile<R, TYPE>;
+    constexpr int PX = T::PX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* buf0 = smem_raw;
+    unsigned char* buf1 = smem_raw + T::IN_BYTES;
+    float4* mid = (float4*)(smem_raw + 2 * T::IN_BYTES);
+    uint64_t* full = (uint64_t*)(smem_raw + 2 * T::IN_BYTES + T::MID_BYTES); // [2]
+    int* released = (int*)(full + 2);                                        // [2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stride = gridDim.x;
+
+    auto issue = [&](int s, int tile) {
+        const int tx = tile % Q.tiles_x, ty = tile / Q.tiles_x;
+        mbar_expect_tx(&full[s], T::TILE_BYTES);
+        tma_load_tile(s ? buf1 : buf0, &Q.map, (tx * ST_TW - T::RA) * (T::B / T::ELEM), ty * T::TH - R, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        released[0] = released[1] = 0;
+        mbar_init_fence();
+        if ((int)blockIdx.x < Q.n_tiles) issue(0, blockIdx.x);
+        if ((int)blockIdx.x + stride < Q.n_tiles) issue(1, blockIdx.x + stride);
+    }
+    __syncthreads();
+
+    // taps centred on R; the row pass carries the load conversion's scale for integer storage
+    float g[2 * R + 1], gr[2 * R + 1];
+    const float in_scale = TYPE == TC_U8 ? 1.0f / 255.0f : (TYPE == TC_U16 ? 1.0f / 65535.0f : 1.0f);
+#pragma unroll
+    for (int t = 0; t <= 2 * R; ++t) {
+        const int sft = t - R + Q.c.R;
+        g[t] = (sft >= 0 && sft <= 2 * Q.c.R) ? Q.c.g[sft] : 0.0f;
+        gr[t] = g[t] * in_scale;
+    }
+    const int xb = warp;
+    float4* strip = mid + warp * (T::IH * T::MP);
+    const int col = lane % ST_HB, seg = lane / ST_HB;
+
+    int i = 0;
+    for (int tile = blockIdx.x; tile < Q.n_tiles; tile += stride, ++i) {
+        const int s = i & 1;
+        unsigned char* in = s ? buf1 : buf0;
+        const int tx = tile % Q.tiles_x, ty = tile / Q.tiles_x;
+        const int x0 = tx * ST_TW, y0 = ty * T::TH;
+        mbar_wait(&full[s], (i >> 1) & 1);
+        const bool border = x0 - T::RA < 0 || y0 - R < 0 || x0 - T::RA + T::BW > Q.w || y0 + T::TH + R > Q.h;
+        if (border) {
+            // cells outside the frame <- the clamped in-frame cell of the same tile (TMA filled them with zeros)
+            for (int c = threadIdx.x; c < T::IH * T::BW; c += ST_THREADS) {
+                const int r = c / T::BW, cc = c - r * T::BW;
+                const int sx = x0 - T::RA + cc, sy = y0 - R + r;
+                const int cx = min(max(sx, 0), Q.w - 1), cy = min(max(sy, 0), Q.h - 1);
+                if (cx != sx || cy != sy) {
+                    const unsigned char* from = in + (cy - (y0 - R)) * T::PITCH + (cx - (x0 - T::RA)) * T::B;
+                    unsigned char* to = in + r * T::PITCH + cc * T::B;
+                    if (T::B == 16) *reinterpret_cast<uint4*>(to) = *reinterpret_cast<const uint4*>(from);
+                    else if (T::B == 8) *reinterpret_cast<uint2*>(to) = *reinterpret_cast<const uint2*>(from);
+                    else *reinterpret_cast<unsigned*>(to) = *reinterpret_cast<const unsigned*>(from);
+                }
+            }
+            __syncthreads();
+        }
+        __syncwarp();
+        // ---- rows: lane = source row, 8 outputs from NV 16-byte reads ----
+        // (every lane runs every iteration on a clamped row and only the store is predicated: a partially active warp costs
+        // the same issue slots, and the loop body stays free of divergence)
+        for (int row0 = 0; row0 < T::IH; row0 += 32) {
+            const int row = min(row0 + lane, T::IH - 1);
+            const uint4* p = reinterpret_cast<const uint4*>(in + row * T::PITCH + xb * ST_HB * T::B);
+            float4 o[ST_HB];
+#pragma unroll
+            for (int v = 0; v < T::NV; ++v) {
+                float4 px[T::VPX];
+                unpack_vec<TYPE>(p[v], px);
+#pragma unroll
+                for (int e = 0; e < T::VPX; ++e) {
+                    const int j = v * T::VPX + e;
+#pragma unroll
+                    for (int k = 0; k < ST_HB; ++k) {
+                        const int t = j - k - T::D;
+                        if (t == 0) o[k] = mul4p(gr[0], px[e]);
+                        else if (t > 0 && t <= 2 * R) o[k] = fma4p(gr[t], px[e], o[k]);
+                    }
+                }
+            }
+            if (row0 + lane < T::IH) {
+                float4* m = strip + row * T::MP;
+#pragma unroll
+                for (int k = 0; k < ST_HB; ++k) m[k] = o[k];
+            }
+        }
+        __syncwarp();
+        auto release = [&]() {
+            if (lane == 0 && release_count(&released[s]) == ST_THREADS / 32 - 1) {
+                released[s] = 0;
+                if (tile + 2 * stride < Q.n_tiles) {
+                    fence_proxy_async();
+                    issue(s, tile + 2 * stride);
+                }
+            }
+        };
+        if (!UNSHARP) release();
+        // ---- columns: lane = column x 4 segments of 6 rows ----
+        float4 f[PX];
+        {
+            const float4* p = strip + (seg * PX) * T::MP + col;
+#pragma unroll
+            for (int j = 0; j < PX + 2 * R; ++j) {
+                const float4 q = p[j * T::MP];
+#pragma unroll
+                for (int k = 0; k < PX; ++k) {
+                    const int t = j - k;
+                    if (t == 0) f[k] = mul4p(g[0], q);
+                    else if (t > 0 && t <= 2 * R) f[k] = fma4p(g[t], q, f[k]);
+                }
+            }
+        }
+        const int x = x0 + xb * ST_HB + col, y = y0 + seg * PX;
+        if (UNSHARP) {
+#pragma unroll
+            for (int k = 0; k < PX; ++k)
+                f[k] = unsharp_px(staged_px<TYPE>(in, (seg * PX + k + R) * T::PITCH + (xb * ST_HB + col + T::RA) * T::B), f[k], Q.c.contrast, Q.c.threshold);
+            __syncwarp();
+            release();
+        }
+        if (x < Q.w) {
+#pragma unroll
+            for (int k = 0; k < PX; ++k)
+                if (y + k < Q.h) store_px(dstp, TYPE, (size_t)(y + k) * Q.w + x, f[k]);
+        }
+    }
+}
+
 // Generic fallback for very wide kernels (R > 12): 32 x 32 tiles, one tap per shared-memory read.
 template <bool UNSHARP>
 __global__ void __launch_bounds__(CONV_THREADS) k_gauss_wide(const Img src, const Img dst, const __grid_constant__ ConvParams P)
@@ -241,9 +460,74 @@ static int launch_tile(const tc_image* dst, const tc_image* src, const ConvParam
     return check_cuda(cudaGetLastError(), "k_gauss_tile launch");
 }
 
+
+static bool gt_use_tma()
+{
+    static const bool on = [] {
+        const char* e = getenv("TOUCAN_CONV_TMA");
+        return !(e && *e == '0');
+    }();
+    return on;
+}
+
+template <int R, int TYPE, bool UNSHARP>
+static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
+{
+    using T = GtTile<R, TYPE>;
+    static_assert(T::SMEM <= 227 * 1024, "tile does not fit in shared memory");
+    constexpr int OCC = T::SMEM <= 75 * 1024 ? 3 : (T::SMEM <= 113 * 1024 ? 2 : 1);
+    GtParams Q;
+    Q.w = dst->w;
+    Q.h = dst->h;
+    Q.tiles_x = (dst->w + ST_TW - 1) / ST_TW;
+    Q.n_tiles = Q.tiles_x * ((dst->h + T::TH - 1) / T::TH);
+    Q.c = P;
+    const unsigned long long pitch = (unsigned long long)src->w * T::B;
+    int e = tensor_map_2d(src->data, T::ELEM, pitch / T::ELEM, (unsigned long long)src->h, pitch, (unsigned)(T::BW * T::B / T::ELEM), (unsigned)T::IH, &Q.map);
+    if (e != TC_OK) return e;
+    e = ensure_dynamic_smem((const void*)k_gauss_tma<R, TYPE, UNSHARP, OCC>, T::SMEM);
+    if (e != TC_OK) return e;
+    const int grid = min(Q.n_tiles, num_sms() * OCC);
+    k_gauss_tma<R, TYPE, UNSHARP, OCC><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_gauss_tma launch");
+}
+
+template <int R, bool UNSHARP>
+static int launch_gauss_tma_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
+{
+    switch (src->type) {
+    case TC_U8: return launch_gauss_tma<R, TC_U8, UNSHARP>(dst, src, P, st);
+    case TC_U16: return launch_gauss_tma<R, TC_U16, UNSHARP>(dst, src, P, st);
+    case TC_F16: return launch_gauss_tma<R, TC_F16, UNSHARP>(dst, src, P, st);
+    default: return launch_gauss_tma<R, TC_F32, UNSHARP>(dst, src, P, st);
+    }
+}
+
+// the TMA kernel's preconditions: same-sized, same-typed frames of at least one tile, 16-byte aligned rows
+static bool gauss_tma_ok(const tc_image* dst, const tc_image* src)
+{
+    if (!gt_use_tma() || !tma_available()) return false;
+    if (src->w != dst->w || src->h != dst->h || src->type != dst->type || dst->w < ST_TW || dst->h < 24) return false;
+    const size_t pitch = (size_t)src->w * 4 * tc_type_size(src->type);
+    return !(pitch & 15) && !((uintptr_t)src->data & 15);
+}
+// Which kernel for which case (4K, one B200, profiles/r02_op_bench_blur.md): float frames take the TMA kernel at every radius
+// (r = 10: 0.078 -> 0.047 ms, r = 20: 0.126 -> 0.094 ms); 8/16-bit and half frames are bound by the conversions and the
+// FMA pipe, not by bytes: the TMA kernel converts a staged pixel once per warp that reads it (2-3x per pixel), the typed-load
+// kernel once at staging, which wins from R = 6 up (u8 r = 20: 0.099 vs 0.114 ms).
+static bool gauss_tma_pays(int R, int type) { return type == TC_F32 || R <= 4; }
+
 template <bool UNSHARP>
 static int launch_conv_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
 {
+    if (P.R <= 12 && gauss_tma_ok(dst, src) && gauss_tma_pays(P.R, src->type)) {
+        if (P.R <= 2) return launch_gauss_tma_t<2, UNSHARP>(dst, src, P, st);
+        if (P.R <= 4) return launch_gauss_tma_t<4, UNSHARP>(dst, src, P, st);
+        if (P.R <= 6) return launch_gauss_tma_t<6, UNSHARP>(dst, src, P, st);
+        if (P.R <= 9) return launch_gauss_tma_t<9, UNSHARP>(dst, src, P, st);
+        return launch_gauss_tma_t<12, UNSHARP>(dst, src, P, st);
+    }
     if (P.R <= 2) return launch_tile<2, UNSHARP>(dst, src, P, st);
     if (P.R <= 4) return launch_tile<4, UNSHARP>(dst, src, P, st);
     if (P.R <= 6) return launch_tile<6, UNSHARP>(dst, src, P, st);

@@ -23,14 +23,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <map>
-#include <mutex>
-#include <tuple>
 #include <vector>
 
-#include <cuda.h> // CUtensorMap (types only: the encoder is looked up through cudaGetDriverEntryPoint)
-
 #include "tc_tile.cuh"
+#include "tc_tma.cuh"
 
 namespace tc {
 
@@ -246,33 +242,6 @@ struct StTmaParams {
     alignas(64) CUtensorMap maps[ST_MAX_MAPS];
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
-                     smem_u32(bar)),
-                 "r"(parity)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(ST_THREADS) : "memory"); }
 
 // cells of a landed tile that lie outside the frame <- the clamped in-frame cell of the same tile
@@ -359,7 +328,7 @@ __global__ void __launch_bounds__(ST_TMA_THREADS, OCC) k_stack_tma(float4* __res
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         released[0] = released[1] = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        mbar_init_fence();
         // the first two tiles
         for (int t = 0; t < 2 && t < Q.n_tiles; ++t) {
             mbar_expect_tx(&full[t], TILE_BYTES);
@@ -369,13 +338,11 @@ __global__ void __launch_bounds__(ST_TMA_THREADS, OCC) k_stack_tma(float4* __res
     __syncthreads();
     // hand staging buffer s (it held tile `tile`) back; the last warp to do so starts the copy of tile + 2 into it
     auto release = [&](int s, int tile) {
-        int prev;
-        asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;\n" : "=r"(prev) : "r"(smem_u32(&released[s])) : "memory");
-        if (prev == ST_THREADS / 32 - 1) {
+        if (release_count(&released[s]) == ST_THREADS / 32 - 1) {
             released[s] = 0;
             if (tile + 2 < Q.n_tiles) {
                 // the warps' generic-proxy reads (and border patches) of this buffer are ordered before the copy's async-proxy writes
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                fence_proxy_async();
                 mbar_expect_tx(&full[s], TILE_BYTES);
                 tma_load_tile(s ? buf1 : buf0, &Q.maps[Q.tile_map[tile + 2]], 2 * (x0 - R), y0 - R, &full[s]);
             }
@@ -534,55 +501,6 @@ static int launch_stack(const tc_image* dst, StParams& P, cudaStream_t st)
     return check_cuda(cudaGetLastError(), "k_stack_f32 launch");
 }
 
-// ---- tensor maps -------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled()
-{
-    static const EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            p = nullptr;
-        }
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
-// (pointer, frame size, box) -> descriptor; a render reads the same stills frame after frame
-static int tensor_map_for(const void* ptr, int w, int h, int box_px, int box_rows, CUtensorMap* out)
-{
-    typedef std::tuple<const void*, int, int, int, int> Key;
-    static std::mutex m;
-    static std::map<Key, CUtensorMap> cache;
-    const Key key(ptr, w, h, box_px, box_rows);
-    {
-        std::lock_guard<std::mutex> lock(m);
-        const auto it = cache.find(key);
-        if (it != cache.end()) {
-            *out = it->second;
-            return TC_OK;
-        }
-    }
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: cuTensorMapEncodeTiled is not available");
-    // a pixel (16 bytes) = two 8-byte elements, so an odd pixel count per box row is expressible
-    const cuuint64_t dims[2] = { (cuuint64_t)w * 2, (cuuint64_t)h };
-    const cuuint64_t strides[1] = { (cuuint64_t)w * 16 };
-    const cuuint32_t box[2] = { (cuuint32_t)box_px * 2, (cuuint32_t)box_rows };
-    const cuuint32_t estr[2] = { 1, 1 };
-    CUtensorMap tm;
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: cuTensorMapEncodeTiled failed (%d) for a %d x %d frame", (int)r, w, h);
-    std::lock_guard<std::mutex> lock(m);
-    if (cache.size() > 4096) cache.clear();
-    cache[key] = tm;
-    *out = tm;
-    return TC_OK;
-}
-
 static bool st_use_tma()
 {
     static const bool on = [] {
@@ -605,12 +523,12 @@ static int launch_stack_tma(const tc_image* dst, StParams& P, cudaStream_t st)
         U.map = U.map2 = -1;
         if (U.flags & ST_DIRECT) continue;
         if (n_maps + 2 > ST_MAX_MAPS) return fail(TC_ERR_UNSUPPORTED, "tc_stack_f32: too many staged sources");
-        int e = tensor_map_for(U.src, P.w, P.h, T::IWP, T::IH, &Q.maps[n_maps]);
+        int e = tensor_map_2d(U.src, 8, 2ull * P.w, (unsigned long long)P.h, 16ull * P.w, 2u * T::IWP, (unsigned)T::IH, &Q.maps[n_maps]);
         if (e != TC_OK) return e;
         Q.tile_map[n_maps] = (short)n_maps;
         U.map = (short)n_maps++;
         if (U.flags & ST_MIX) {
-            e = tensor_map_for(U.src2, P.w, P.h, T::IWP, T::IH, &Q.maps[n_maps]);
+            e = tensor_map_2d(U.src2, 8, 2ull * P.w, (unsigned long long)P.h, 16ull * P.w, 2u * T::IWP, (unsigned)T::IH, &Q.maps[n_maps]);
             if (e != TC_OK) return e;
             Q.tile_map[n_maps] = (short)n_maps;
             U.map2 = (short)n_maps++;
@@ -695,7 +613,7 @@ extern "C" int tc_stack_f32(const tc_image* dst, const float background[4], cons
     P.n_units = nu;
     cudaStream_t st = (cudaStream_t)s;
     // the TMA kernel: frames at least one tile large whose rows are 16-byte multiples (always) and whose base is 16-byte aligned
-    bool tma = st_use_tma() && encode_tiled() != nullptr && dst->w >= ST_TW && dst->h >= 24;
+    bool tma = st_use_tma() && tma_available() && dst->w >= ST_TW && dst->h >= 24;
     for (int u = 0; u < nu && tma; ++u)
         if (((uintptr_t)P.unit[u].src | (uintptr_t)P.unit[u].src2) & 15) tma = false;
     if (tma) {
