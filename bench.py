@@ -414,10 +414,11 @@ def timed_loop(D, step, items, warm):
 def e2e_run(D, tl, first, steps, warm_first):
     """toucan::FrameScheduler through the C API from host media with a COLD device source cache: every still is uploaded
     inside the timed region the first time a frame reads it.  Wall clock around the whole call, max over ranks."""
-    sink = {"n": 0, "acc": 0.0}
+    sink = {"n": 0, "acc": 0.0, "t": []}
 
     def writer(frame, pixels):
         sink["n"] += 1
+        sink["t"].append(time.perf_counter())
         if pixels.size:
             sink["acc"] += float(pixels.reshape(-1)[0])  # the writer's read of the finished frame
 
@@ -432,6 +433,8 @@ def e2e_run(D, tl, first, steps, warm_first):
     D.barrier()
     n1, b1 = tl.upload_stats()
     assert sink["n"] == steps + 2
+    if os.environ.get("TOUCAN_BENCH_TRACE"):
+        sys.stderr.write("e2e frame arrival ms: " + " ".join(f"{(t - t0) * 1e3:.0f}" for t in sink["t"][2:]) + "\n")
     return D.max(dt), dt, b1 - b0, n1 - n0
 
 
@@ -560,10 +563,11 @@ def run_c5(args, cfg):
             D.barrier()
             t0 = time.perf_counter()
             own = 0
-            for i, k in enumerate(keys):
+            for i, k in enumerate(keys):  # every rank uploads its own share at the same time ...
                 if i % world == rank:
                     dev_buf[k].copy_(host_src[k], non_blocking=True)
                     own += 1
+            for i, k in enumerate(keys):  # ... then the shares are exchanged over NVLink
                 D.dist.broadcast(dev_buf[k], src=i % world)
             torch.cuda.synchronize()
             t_dist = time.perf_counter() - t0

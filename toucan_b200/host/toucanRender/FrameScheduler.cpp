@@ -4,11 +4,14 @@
 
 #include "ImageEffectHost.h"
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <condition_variable>
 #include <deque>
 #include <exception>
 #include <mutex>
+#include <set>
 #include <sstream>
 #include <thread>
 
@@ -302,6 +305,44 @@ namespace toucan
             w.cv.notify_all();
         };
 
+        // Upload ahead: with the device source cache on, one thread per GPU copies the timeline's stills to the device in the order
+        // the frames first touch them, on its own stream -- the frame that needs a still finds it cached (or waits for the copy's event
+        // on the GPU, never on the host), and the host -> device copies of later clips overlap the device -> host copies of finished
+        // frames (PCIe is full duplex; uploading at first use serialised the two directions).
+        std::vector<std::thread> uploaders;
+        const auto store = _timelineWrapper->getMediaStore();
+        if (_options.uploadAhead && store && store->getDeviceCacheBytes() > 0)
+        {
+            std::set<int> devices(_options.devices.begin(), _options.devices.end());
+            const auto stills = _timelineWrapper->getStillMediaByFirstUse(OTIO_NS::RationalTime(first, rate));
+            for (const int device : devices)
+            {
+                uploaders.emplace_back([device, stills, store, &cancel]
+                {
+                    try
+                    {
+                        DeviceContext::bind(device);
+                        size_t budget = store->getDeviceCacheBytes();
+                        for (const auto& still : stills)
+                        {
+                            if (cancel) break;
+                            MediaFrame frame;
+                            if (!readMedia(store, still.first, frame, still.second) || frame.device || !frame.host || 4 != frame.nchannels) continue;
+                            const size_t bytes = tc_image_bytes(frame.width, frame.height, frame.format);
+                            if (bytes > budget) break; // the cache is full: what is needed now must not be evicted for what is needed later
+                            budget -= bytes;
+                            uploadToCache(frame, store, device, still.first);
+                        }
+                    }
+                    catch (...)
+                    {
+                        // best effort: a still that cannot be read here fails where the frame that needs it is rendered
+                    }
+                    DeviceContext::unbind();
+                });
+            }
+        }
+
         for (auto& w : workers)
         {
             Worker* wp = w.get();
@@ -372,6 +413,10 @@ namespace toucan
         {
             if (w->thread.joinable()) w->thread.join();
             if (!error && w->error) error = w->error;
+        }
+        for (auto& u : uploaders)
+        {
+            if (u.joinable()) u.join();
         }
         if (error)
         {

@@ -12,6 +12,7 @@
 //     next frame renders; the calling thread is the writer and receives frames in order.
 #pragma once
 
+#include <cstdlib>
 #include <toucanRender/ImageGraph.h>
 
 #include <functional>
@@ -38,6 +39,9 @@ namespace toucan
         //! converted ON THE DEVICE to the planar YUV bytes the reference's paste + libswscale chain
         //! (App.cpp:340-485) writes after "FRAME\n"; only those bytes are downloaded.
         int y4mFormat = -1;
+        //! With the device source cache on, copy the timeline's stills to each GPU ahead of the frames that read them (one
+        //! thread and stream per GPU, first-use order).  TOUCAN_NO_UPLOAD_AHEAD=1 turns it off.
+        bool uploadAhead = getenv("TOUCAN_NO_UPLOAD_AHEAD") == nullptr;
     };
 
     //! "rgb24" | "rgba" | "rgb48" | "rgba64" | "rgbaf16" | "rgbf32" | "rgbaf32" -> (tc_type, channels)

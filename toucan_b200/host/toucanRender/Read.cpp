@@ -113,6 +113,27 @@ namespace toucan
         _loaded.notify_all();
     }
 
+    bool MediaStore::beginUpload(int device, const std::string& path)
+    {
+        std::unique_lock<std::mutex> lock(_mutex);
+        const auto key = std::make_pair(device, path);
+        if (_uploading.insert(key).second)
+        {
+            return true;
+        }
+        _loaded.wait(lock, [this, &key] { return 0 == _uploading.count(key); });
+        return false;
+    }
+
+    void MediaStore::endUpload(int device, const std::string& path)
+    {
+        {
+            std::lock_guard<std::mutex> lock(_mutex);
+            _uploading.erase(std::make_pair(device, path));
+        }
+        _loaded.notify_all();
+    }
+
     void MediaStore::countUpload(size_t bytes)
     {
         std::lock_guard<std::mutex> lock(_mutex);
@@ -280,6 +301,38 @@ namespace toucan
 
     const OTIO_NS::TimeRange& IReadNode::getTimeRange() const { return _timeRange; }
 
+    Image uploadToCache(const MediaFrame& frame, const std::shared_ptr<MediaStore>& store, int device, const std::string& path)
+    {
+        const ImageSpec spec(frame.width, frame.height, 4, frame.format);
+        Image cached;
+        for (;;)
+        {
+            if (store->getCached(device, path, cached) && cached.spec().image_bytes() == spec.image_bytes())
+            {
+                // another thread of this GPU (a second worker, or the scheduler's upload-ahead thread) may have uploaded it
+                // on its own stream: wait for that copy on ours
+                cached.acquire();
+                return cached;
+            }
+            if (store->beginUpload(device, path)) break; // ours to upload; otherwise someone just finished: look again
+        }
+        try
+        {
+            cached = Image::upload(frame.host, spec);
+            cached.keepAlive(frame.storage ? std::shared_ptr<const void>(frame.storage) : std::shared_ptr<const void>(frame.owned));
+            cached.publish(); // before any other thread can find it in the cache
+            store->countUpload(spec.image_bytes());
+            store->putCached(device, path, cached);
+        }
+        catch (...)
+        {
+            store->endUpload(device, path);
+            throw;
+        }
+        store->endUpload(device, path);
+        return cached;
+    }
+
     Image IReadNode::_toDevice(const MediaFrame& frame, const std::shared_ptr<MediaStore>& store, const std::string& path) const
     {
         if (frame.nchannels != 4)
@@ -294,20 +347,7 @@ namespace toucan
         }
         if (store && store->getDeviceCacheBytes() > 0)
         {
-            const int device = DeviceContext::device();
-            Image cached;
-            if (store->getCached(device, path, cached) && cached.spec().image_bytes() == spec.image_bytes())
-            {
-                // another worker of this GPU may have uploaded it on its own stream: wait for that copy
-                cached.acquire();
-                return cached;
-            }
-            cached = Image::upload(frame.host, spec);
-            cached.keepAlive(frame.storage ? std::shared_ptr<const void>(frame.storage) : std::shared_ptr<const void>(frame.owned));
-            cached.publish(); // before any other thread can find it in the cache
-            store->countUpload(spec.image_bytes());
-            store->putCached(device, path, cached);
-            return cached;
+            return uploadToCache(frame, store, DeviceContext::device(), path);
         }
         if (store) store->countUpload(spec.image_bytes());
         Image uploaded = Image::upload(frame.host, spec);

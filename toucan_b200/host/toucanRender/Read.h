@@ -78,6 +78,11 @@ namespace toucan
         bool beginLoad(const std::string& path);
         void endLoad(const std::string& path);
 
+        //! Upload coordination for the device cache: the first caller for (device, path) gets true, uploads, puts the frame in
+        //! the cache and calls endUpload(); a concurrent caller blocks until then and gets false (the frame is cached by then).
+        bool beginUpload(int device, const std::string& path);
+        void endUpload(int device, const std::string& path);
+
         //! Host -> device uploads of source frames so far (diagnostics).
         void countUpload(size_t bytes);
         size_t getUploadCount() const;
@@ -95,6 +100,7 @@ namespace toucan
         size_t _cacheLimit = 0;
         size_t _uploads = 0, _uploadBytes = 0;
         std::set<std::string> _loading;
+        std::set<std::pair<int, std::string> > _uploading;
         std::condition_variable _loaded;
         std::list<Cached> _cache; // most recently used first
     };
@@ -188,6 +194,10 @@ namespace toucan
         struct State;
         std::shared_ptr<State> _state;
     };
+
+    //! Upload a host frame into the store's device cache for `device` on the calling thread's stream (or find it there):
+    //! one upload per (device, path) however many threads ask.
+    Image uploadToCache(const MediaFrame&, const std::shared_ptr<MediaStore>&, int device, const std::string& path);
 
     //! Look a frame up in the store, falling back to the built-in file readers.
     //! `park`: keep the decoded frame in the store (stills, decoded once); sequence frames are used once and are not kept.

@@ -2,6 +2,7 @@
 
 #include "Util.h"
 
+#include <algorithm>
 #include <set>
 
 namespace toucan
@@ -228,6 +229,52 @@ namespace toucan
                 const auto memory = _memoryReferences.find(externalRef->target_url());
                 out.emplace_back(path, memory != _memoryReferences.end() ? memory->second : MemoryReference());
             }
+        }
+        return out;
+    }
+
+    std::vector<std::pair<std::string, MemoryReference> > TimelineWrapper::getStillMediaByFirstUse(const OTIO_NS::RationalTime& from) const
+    {
+        // The order a render starting at `from` (a time in the tracks' coordinates) first touches the stills: the clips under
+        // `from`, then the later ones by their start, then the ones already over (a transition's out-going clip is still read a
+        // little past its end: it is under `from` or uploaded at first use, which the cache handles either way).
+        struct Entry
+        {
+            double key0, key1;
+            std::pair<std::string, MemoryReference> media;
+        };
+        std::vector<Entry> entries;
+        const double t0 = from.to_seconds();
+        for (const auto& child : _timeline->tracks()->children())
+        {
+            auto track = dynamic_cast<OTIO_NS::Track*>(child.value);
+            if (!track) continue;
+            for (const auto& clip : track->find_clips())
+            {
+                auto externalRef = dynamic_cast<OTIO_NS::ExternalReference*>(clip->media_reference());
+                if (!externalRef) continue;
+                const std::string path = getMediaPath(externalRef->target_url());
+                if (!hasExtension(toLower(std::filesystem::path(path).extension().string()), ImageReadNode::getExtensions())) continue;
+                double start = 0.0, end = 0.0;
+                if (const auto range = clip->trimmed_range_in_parent())
+                {
+                    start = range->start_time().to_seconds();
+                    end = range->end_time_exclusive().to_seconds();
+                }
+                const auto memory = _memoryReferences.find(externalRef->target_url());
+                entries.push_back({ end > t0 ? 0.0 : 1.0, std::max(0.0, start - t0),
+                    std::make_pair(path, memory != _memoryReferences.end() ? memory->second : MemoryReference()) });
+            }
+        }
+        std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b)
+        {
+            return a.key0 != b.key0 ? a.key0 < b.key0 : a.key1 < b.key1;
+        });
+        std::vector<std::pair<std::string, MemoryReference> > out;
+        std::set<std::string> seen;
+        for (const auto& e : entries)
+        {
+            if (seen.insert(e.media.first).second) out.push_back(e.media);
         }
         return out;
     }

@@ -39,6 +39,8 @@ namespace toucan
         //! The stills (single-file media) the timeline's clips reference, in clip order, without duplicates: what a
         //! background prefetch decodes ahead of the render threads.  Sequence frames are not listed (they stream).
         std::vector<std::pair<std::string, MemoryReference> > getStillMedia() const;
+        //! The same stills in the order a render starting at `from` (a time in the tracks' coordinates) first touches them.
+        std::vector<std::pair<std::string, MemoryReference> > getStillMediaByFirstUse(const OTIO_NS::RationalTime& from) const;
 
         //! Decoded frames the read nodes draw from (defaults to the process-wide store).
         void setMediaStore(const std::shared_ptr<MediaStore>&);
