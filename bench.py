@@ -411,7 +411,7 @@ def timed_loop(D, step, items, warm):
     return D.max(e0.elapsed_time(e1)), last
 
 
-def e2e_run(D, tl, first, steps, warm_first):
+def e2e_run(D, tl, first, steps, warm_first, y4m_format=None):
     """toucan::FrameScheduler through the C API from host media with a COLD device source cache: every still is uploaded
     inside the timed region the first time a frame reads it.  Wall clock around the whole call, max over ranks."""
     sink = {"n": 0, "acc": 0.0, "t": []}
@@ -422,13 +422,13 @@ def e2e_run(D, tl, first, steps, warm_first):
         if pixels.size:
             sink["acc"] += float(pixels.reshape(-1)[0])  # the writer's read of the finished frame
 
-    tl.render_range(warm_first, warm_first + 2, writer, devices=[D.local])  # pool growth, pinned ring, plug-in load
+    tl.render_range(warm_first, warm_first + 2, writer, devices=[D.local], y4m_format=y4m_format)  # pool growth, pinned ring, plug-in load
     tl.drop_source_cache()  # ... and forget the uploads: the timed region starts with nothing resident
     D.torch.cuda.synchronize()
     n0, b0 = tl.upload_stats()
     D.barrier()
     t0 = time.perf_counter()
-    tl.render_range(first, first + steps, writer, devices=[D.local])
+    tl.render_range(first, first + steps, writer, devices=[D.local], y4m_format=y4m_format)
     dt = time.perf_counter() - t0
     D.barrier()
     n1, b1 = tl.upload_stats()
@@ -516,6 +516,7 @@ def run_c5(args, cfg):
 
     # ---- end to end: host buffers in, host buffers out, every copy inside the timed region ----
     e2e = None
+    e2e_y4m = None
     e2e_reupload = None
     host_src = None
     e2e_steps = int(os.environ.get("TOUCAN_BENCH_E2E_STEPS", str(min(args.steps, 24))))
@@ -541,6 +542,14 @@ def run_c5(args, cfg):
                        f"{int(up_n)} uploads of {F / 1e6:.0f} MB on this rank), {e2e_steps} consecutive frames (half before, half inside a "
                        "transition) rendered and every finished float32 frame downloaded into a pinned ring for the ordered writer; "
                        "wall clock, max over ranks"}
+        if os.environ.get("TOUCAN_BENCH_Y4M", "1") != "0":
+            # (informational) the same run with the reference README's pipe-to-ffmpeg output, `toucan-render timeline.otio - -y4m 444`:
+            # the RGB -> planar YUV conversion of App.cpp:340-485 runs on the device, so 3 bytes per pixel cross PCIe instead of 16
+            dty, _, upy, _ = e2e_run(D, tl2, first, e2e_steps, first + e2e_steps // 2, y4m_format="444")
+            e2e_y4m = {"value": world * e2e_steps / dty, "unit": "frames/s", "h2d_bytes_per_step": int(D.sum(float(upy)) / (world * e2e_steps)),
+                       "d2h_bytes_per_step": 3 * w * h, "steps": e2e_steps,
+                       "note": "informational: as `e2e` (cold source cache, every still uploaded inside the timed region) but the finished frame is "
+                               "converted to y4m 4:4:4 on the device and those bytes are downloaded"}
         if world > 1 and os.environ.get("TOUCAN_BENCH_FANOUT", "1") != "0":
             # N GPUs of one box read the SAME stills: instead of every rank pulling all 20 through the one PCIe root they share
             # (N x 10.6 GB), each still crosses PCIe ONCE -- uploaded by the rank that owns it (index % N) -- and is fanned out to the
@@ -635,7 +644,7 @@ def run_c5(args, cfg):
                              "algorithmic_bytes_per_launch": alg_bytes / args.steps,
                              "note": f"bytes = (sources referenced + 1 output) x {F:,} B per frame; one launch per frame; "
                                      "rank-0-equivalent (max-over-ranks time)"},
-                "cpu_baseline": cpu, "e2e": e2e, "e2e_reupload_every_frame": e2e_reupload, "gpu_launches": int(launches), "clocks": clk,
+                "cpu_baseline": cpu, "e2e": e2e, "e2e_y4m444": e2e_y4m, "e2e_reupload_every_frame": e2e_reupload, "gpu_launches": int(launches), "clocks": clk,
                 "checksum": checksum}
         if args.scale != 1.0:
             line["INVALID"] = "debug run at reduced frame size (--scale)"
