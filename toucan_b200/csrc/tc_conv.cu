@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tile(const Img src, c
 // multiple of 16 bytes, so the row-per-lane 16-byte reads are bank-conflict free for every type.
 // 8/16-bit sources: the 1/255 (1/65535) of OIIO's load conversion is folded into the row-pass weights (the taps see
 // integers); the unsharp epilogue converts its centre pixel exactly.
-template <int R, int TYPE>
+template <int R, int TYPE, int NBUF = 2>
 struct GtTile {
     static constexpr int TH = 24, PX = 6;
     static constexpr int B = TYPE == TC_U8 ? 4 : (TYPE == TC_F32 ? 16 : 8); // bytes per pixel
@@ -164,7 +164,7 @@ struct GtTile {
     static constexpr int IN_BYTES = (IH * PITCH + 127) / 128 * 128;
     static constexpr int MP = ST_HB + 1;
     static constexpr int MID_BYTES = 8 * IH * MP * 16;
-    static constexpr size_t SMEM = 2 * IN_BYTES + MID_BYTES + 64;
+    static constexpr size_t SMEM = NBUF * IN_BYTES + MID_BYTES + 64;
     static constexpr int ELEM = B == 4 ? 4 : 8; // tensor-map element size
     static constexpr unsigned TILE_BYTES = (unsigned)(IH * PITCH);
 };
@@ -210,17 +210,17 @@ struct GtParams {
     alignas(64) CUtensorMap map;
 };
 
-template <int R, int TYPE, bool UNSHARP, int OCC>
+template <int R, int TYPE, bool UNSHARP, int NBUF, int OCC>
 __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict__ dstp, const __grid_constant__ GtParams Q)
 {
-    using T = GtTile<R, TYPE>;
+    using T = GtTile<R, TYPE, NBUF>;
     constexpr int PX = T::PX;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* buf0 = smem_raw;
-    unsigned char* buf1 = smem_raw + T::IN_BYTES;
-    float4* mid = (float4*)(smem_raw + 2 * T::IN_BYTES);
-    uint64_t* full = (uint64_t*)(smem_raw + 2 * T::IN_BYTES + T::MID_BYTES); // [2]
-    int* released = (int*)(full + 2);                                        // [2]
+    unsigned char* buf1 = smem_raw + (NBUF - 1) * T::IN_BYTES; // (== buf0 with one staging buffer)
+    float4* mid = (float4*)(smem_raw + NBUF * T::IN_BYTES);
+    uint64_t* full = (uint64_t*)(smem_raw + NBUF * T::IN_BYTES + T::MID_BYTES); // [2]
+    int* released = (int*)(full + 2);                                           // [2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stride = gridDim.x;
 
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict_
         released[0] = released[1] = 0;
         mbar_init_fence();
         if ((int)blockIdx.x < Q.n_tiles) issue(0, blockIdx.x);
-        if ((int)blockIdx.x + stride < Q.n_tiles) issue(1, blockIdx.x + stride);
+        if (NBUF > 1 && (int)blockIdx.x + stride < Q.n_tiles) issue(1, blockIdx.x + stride);
     }
     __syncthreads();
 
@@ -254,11 +254,11 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict_
 
     int i = 0;
     for (int tile = blockIdx.x; tile < Q.n_tiles; tile += stride, ++i) {
-        const int s = i & 1;
+        const int s = NBUF > 1 ? (i & 1) : 0;
         unsigned char* in = s ? buf1 : buf0;
         const int tx = tile % Q.tiles_x, ty = tile / Q.tiles_x;
         const int x0 = tx * ST_TW, y0 = ty * T::TH;
-        mbar_wait(&full[s], (i >> 1) & 1);
+        mbar_wait(&full[s], (NBUF > 1 ? (i >> 1) : i) & 1);
         const bool border = x0 - T::RA < 0 || y0 - R < 0 || x0 - T::RA + T::BW > Q.w || y0 + T::TH + R > Q.h;
         if (border) {
             // cells outside the frame <- the clamped in-frame cell of the same tile (TMA filled them with zeros)
@@ -278,40 +278,46 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict_
         }
         __syncwarp();
         // ---- rows: lane = source row, 8 outputs from NV 16-byte reads ----
-        // (every lane runs every iteration on a clamped row and only the store is predicated: a partially active warp costs
-        // the same issue slots, and the loop body stays free of divergence)
-        for (int row0 = 0; row0 < T::IH; row0 += 32) {
-            const int row = min(row0 + lane, T::IH - 1);
-            const uint4* p = reinterpret_cast<const uint4*>(in + row * T::PITCH + xb * ST_HB * T::B);
-            float4 o[ST_HB];
+        // Up to 32 staged rows: one lane per row, 8 outputs each.  More rows (R >= 6): a lane per HALF row (4 outputs), so that
+        // 2 IH items fill the warp's iterations (IH = 42: 3 iterations of 4 outputs instead of 2 of 8, a quarter fewer FMA slots).
+        // Every lane runs every iteration on a clamped item and only the store is predicated: a partially active warp costs the
+        // same issue slots.  Lanes on consecutive rows with a 16 (mod 128)-byte pitch: conflict-free either way.
+        constexpr int HO = T::IH <= 32 ? ST_HB : ST_HB / 2;   // outputs per item
+        constexpr int ITEMS = T::IH * (ST_HB / HO);
+        constexpr int NVI = ((HO + 2 * R + T::D + T::VPX - 1) / T::VPX);  // 16-byte reads per item
+        for (int i0 = 0; i0 < ITEMS; i0 += 32) {
+            const int item = min(i0 + lane, ITEMS - 1);
+            const int half = item / T::IH, row = item - half * T::IH;
+            const uint4* p = reinterpret_cast<const uint4*>(in + row * T::PITCH + (xb * ST_HB + half * HO) * T::B);
+            float4 o[HO];
 #pragma unroll
-            for (int v = 0; v < T::NV; ++v) {
+            for (int v = 0; v < NVI; ++v) {
                 float4 px[T::VPX];
                 unpack_vec<TYPE>(p[v], px);
 #pragma unroll
                 for (int e = 0; e < T::VPX; ++e) {
                     const int j = v * T::VPX + e;
 #pragma unroll
-                    for (int k = 0; k < ST_HB; ++k) {
+                    for (int k = 0; k < HO; ++k) {
                         const int t = j - k - T::D;
                         if (t == 0) o[k] = mul4p(gr[0], px[e]);
                         else if (t > 0 && t <= 2 * R) o[k] = fma4p(gr[t], px[e], o[k]);
                     }
                 }
             }
-            if (row0 + lane < T::IH) {
-                float4* m = strip + row * T::MP;
+            if (i0 + lane < ITEMS) {
+                float4* m = strip + row * T::MP + half * HO;
 #pragma unroll
-                for (int k = 0; k < ST_HB; ++k) m[k] = o[k];
+                for (int k = 0; k < HO; ++k) m[k] = o[k];
             }
         }
         __syncwarp();
         auto release = [&]() {
             if (lane == 0 && release_count(&released[s]) == ST_THREADS / 32 - 1) {
                 released[s] = 0;
-                if (tile + 2 * stride < Q.n_tiles) {
+                if (tile + NBUF * stride < Q.n_tiles) {
                     fence_proxy_async();
-                    issue(s, tile + 2 * stride);
+                    issue(s, tile + NBUF * stride);
                 }
             }
         };
@@ -473,7 +479,10 @@ static bool gt_use_tma()
 template <int R, int TYPE, bool UNSHARP>
 static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
 {
-    using T = GtTile<R, TYPE>;
+    // two staging buffers per CTA unless that leaves one CTA (8 warps) per SM: then one buffer and two CTAs, which cover each
+    // other's copy latency (float frames from R = 6 up)
+    constexpr int NBUF = GtTile<R, TYPE, 2>::SMEM <= 113 * 1024 ? 2 : (GtTile<R, TYPE, 1>::SMEM <= 113 * 1024 ? 1 : 2);
+    using T = GtTile<R, TYPE, NBUF>;
     static_assert(T::SMEM <= 227 * 1024, "tile does not fit in shared memory");
     constexpr int OCC = T::SMEM <= 75 * 1024 ? 3 : (T::SMEM <= 113 * 1024 ? 2 : 1);
     GtParams Q;
@@ -485,10 +494,10 @@ static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const Conv
     const unsigned long long pitch = (unsigned long long)src->w * T::B;
     int e = tensor_map_2d(src->data, T::ELEM, pitch / T::ELEM, (unsigned long long)src->h, pitch, (unsigned)(T::BW * T::B / T::ELEM), (unsigned)T::IH, &Q.map);
     if (e != TC_OK) return e;
-    e = ensure_dynamic_smem((const void*)k_gauss_tma<R, TYPE, UNSHARP, OCC>, T::SMEM);
+    e = ensure_dynamic_smem((const void*)k_gauss_tma<R, TYPE, UNSHARP, NBUF, OCC>, T::SMEM);
     if (e != TC_OK) return e;
     const int grid = min(Q.n_tiles, num_sms() * OCC);
-    k_gauss_tma<R, TYPE, UNSHARP, OCC><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
+    k_gauss_tma<R, TYPE, UNSHARP, NBUF, OCC><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
     count_launch();
     return check_cuda(cudaGetLastError(), "k_gauss_tma launch");
 }
