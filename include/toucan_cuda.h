@@ -168,14 +168,18 @@ int tc_convert(const tc_image* dst, const tc_image* src, tc_stream s);
 int tc_pack_raw(void* dst_dev, const tc_image* src, int type, int channels, tc_stream s);
 
 /* ---- pointwise chain (cross-node fusion of consecutive pointwise effects) --------------
- * One pass for a chain of 2..TC_CHAIN_MAX pointwise effect nodes (Invert, Pow, Saturate, ColorMap, Premult,
- * Unpremult, ColorConvert) applied bottom to top: ops[0] runs first.  Between two steps the value goes through
+ * One pass for a chain of 2..TC_CHAIN_MAX pointwise graph nodes (Invert, Pow, Saturate, ColorMap, Premult,
+ * Unpremult, ColorConvert; Flip / Flop, which only change where the source pixel is read and commute with every pointwise op;
+ * CompNode's premult + over onto the Fill generator's colour, TC_CHAIN_OVER_FILL) applied bottom to top: ops[0] runs first.  Between two steps the value goes through
  * the storage type of the images (the reference materialises a typed buffer at every node boundary), so the
  * result is bit-identical to running the per-node kernels one after the other -- minus 2(n-1) frame passes.
  * name_a / name_b: ColorMap map name; ColorConvert from / to colour space.  flag: ColorConvert's unpremult.
  * An op the per-node call would refuse (unknown colour space) yields zeros, like its per-node kernel. */
 enum { TC_CHAIN_INVERT = 0, TC_CHAIN_POW, TC_CHAIN_SATURATE, TC_CHAIN_COLOR_MAP, TC_CHAIN_PREMULT, TC_CHAIN_UNPREMULT, TC_CHAIN_COLOR_CONVERT,
-       TC_CHAIN_ZERO };
+       TC_CHAIN_ZERO,
+       TC_CHAIN_OVER_FILL, /* lib/toucanRender/Comp.cpp:29-84 over the Fill generator's frame: color = the fill colour, flag = premult */
+       TC_CHAIN_FLIP,      /* plugins/TransformPlugin.cpp:232-248 */
+       TC_CHAIN_FLOP };    /* :277-293 */
 #define TC_CHAIN_MAX 8
 typedef struct tc_chain_op {
     int kind;
@@ -183,6 +187,8 @@ typedef struct tc_chain_op {
     int flag;
     char name_a[96];
     char name_b[96];
+    float color[4]; /* TC_CHAIN_OVER_FILL */
+    int w, h;       /* TC_CHAIN_OVER_FILL: the Fill frame's size (the chain's frames must have it) */
 } tc_chain_op;
 /* what a plug-in appends to when the host asks it to describe its pixel operation instead of launching it
    (render-argument property "ToucanPropPointwiseChain") */

@@ -409,13 +409,28 @@ CHAINS = [
     [("unpremult",), ("color_convert", "Linear Rec.709 (sRGB)", "ACEScct", False), ("premult",)],
     [("pow", 2.2), ("color_convert", "sRGB - Texture", "no such space", False), ("invert",)],   # failed convert: zeros, then invert
     [("saturate", 1.5), ("color_map", "no such map"), ("invert",), ("pow", 3.0), ("premult",), ("unpremult",), ("invert",), ("saturate", 0.25)],
+    # data/MultipleEffects.otio's second clip through the whole graph: Flop, ColorMap (clip), Invert (track), CompNode over the
+    # Fill frame (premult + over), Pow 3 (stack) -- five graph nodes, one launch
+    [("flop",), ("color_map", "plasma"), ("invert",), ("over_fill", (0.0, 0.0, 0.0, 1.0), True), ("pow", 3.0)],
+    [("invert",), ("flip",), ("saturate", 0.3), ("flop",), ("over_fill", (0.25, 0.5, 0.125, 0.75), True)],
+    [("flip",), ("flip",), ("flop",), ("over_fill", (1.0, 0.0, 0.0, 0.5), False)],
 ]
 
 
 def _single(ops_mod, t, st):
     return {"invert": lambda: ops_mod.invert(t), "pow": lambda: ops_mod.pow_(t, st[1]), "saturate": lambda: ops_mod.saturate(t, st[1]),
             "color_map": lambda: ops_mod.color_map(t, st[1]), "premult": lambda: ops_mod.premult(t), "unpremult": lambda: ops_mod.unpremult(t),
-            "color_convert": lambda: ops_mod.colorconvert(t, st[1], st[2], unpremult=st[3])}[st[0]]()
+            "color_convert": lambda: ops_mod.colorconvert(t, st[1], st[2], unpremult=st[3]),
+            "flip": lambda: ops_mod.flip(t), "flop": lambda: ops_mod.flop(t),
+            "over_fill": lambda: _over_fill(ops_mod, t, st[1], st[2])}[st[0]]()
+
+
+def _over_fill(ops_mod, t, color, premult):
+    """CompNode over the Fill generator's UINT8 frame, node by node: fill, then premult + over."""
+    h, w = t.shape[0], t.shape[1]
+    if ops_mod is O:
+        return O.comp(t, O.fill(w, h, list(color)), premult)
+    return ops_mod.over(t, ops_mod.fill(w, h, list(color)), premult_fg=premult)
 
 
 @pytest.mark.parametrize("dt", NP_TYPES)

@@ -374,3 +374,33 @@ def test_device_source_cache(host):
             assert hashlib.sha256(got.tobytes()).hexdigest() == rec["sha256"]
     tl.set_source_cache(0)
     tl.close()
+
+
+@pytest.mark.parametrize("name", ["MultipleEffects.otio", "CompositeTracks.otio", "Transform.otio", "Filter.otio", "Gap.otio", "ColorSpace.otio"])
+def test_node_chains_through_comp_and_flips_are_bit_identical_to_the_node_path(host, name):
+    """Cross-node fusion of same-position nodes now runs through CompNode (premult + over onto the Fill generator's colour is one
+    more chain step) and Flip / Flop (which only move the source read): every frame must equal the node-by-node frame bit for
+    bit, and data/MultipleEffects.otio's second clip (Flop, ColorMap, track Invert, CompNode, stack Pow 3) must be ONE launch."""
+    from toucan_b200 import capi, render
+
+    tl = TL.open_timeline(name)
+    info = tl.info()
+    try:
+        for f in range(info["frames"]):
+            t = info["start"] + f
+            render.set_fusion(True)
+            n0 = capi.launch_count()
+            fused = tl.render(host, t, max_bytes=1280 * 720 * 16)
+            n_fused = capi.launch_count() - n0
+            render.set_fusion(False)
+            n0 = capi.launch_count()
+            plain = tl.render(host, t, max_bytes=1280 * 720 * 16)
+            n_plain = capi.launch_count() - n0
+            assert fused.shape == plain.shape and fused.dtype == plain.dtype
+            assert np.array_equal(fused, plain), f"{name} frame {f}: {int((fused != plain).sum())} values differ"
+            assert n_fused <= n_plain
+            if name == "MultipleEffects.otio" and f >= 5:
+                assert n_fused == 1 and n_plain >= 6, (n_fused, n_plain)
+    finally:
+        render.set_fusion(True)
+        tl.close()

@@ -28,10 +28,11 @@ class tc_image(ctypes.Structure):
 
 class tc_chain_op(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("value", ctypes.c_float), ("flag", ctypes.c_int), ("name_a", ctypes.c_char * 96),
-                ("name_b", ctypes.c_char * 96)]
+                ("name_b", ctypes.c_char * 96), ("color", ctypes.c_float * 4), ("w", ctypes.c_int), ("h", ctypes.c_int)]
 
 
-CHAIN_KINDS = {"invert": 0, "pow": 1, "saturate": 2, "color_map": 3, "premult": 4, "unpremult": 5, "color_convert": 6}
+CHAIN_KINDS = {"invert": 0, "pow": 1, "saturate": 2, "color_map": 3, "premult": 4, "unpremult": 5, "color_convert": 6,
+               "over_fill": 8, "flip": 9, "flop": 10}
 
 
 class tc_stack_layer(ctypes.Structure):

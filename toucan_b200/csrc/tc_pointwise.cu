@@ -592,11 +592,10 @@ struct ChainStep {
     float p_in, p_out;
     float m[9];
 };
-struct ChainOp {
-    Src s;
+// The steps of a chain applied to one pixel (shared by the plain and the flipped-source kernels).
+struct ChainSteps {
     int n, type;
     ChainStep step[TC_CHAIN_MAX];
-    TC_OP_1(s)
     __device__ __forceinline__ float4 apply(float4 p) const
     {
         for (int i = 0; i < n; ++i) {
@@ -633,11 +632,229 @@ struct ChainOp {
                 p = o.apply(p);
                 break;
             }
+            case TC_CHAIN_OVER_FILL: {
+                // CompNode: premult(fg) [a typed buffer in the reference], then over the Fill frame's colour (m[0..3])
+                if (st.unpremult) { // (the step's flag: premultiply first)
+                    if (p.w != 1.0f) {
+                        p.x = __fmul_rn(p.x, p.w);
+                        p.y = __fmul_rn(p.y, p.w);
+                        p.z = __fmul_rn(p.z, p.w);
+                    }
+                    p = quant4(p, type);
+                }
+                const float alpha = fminf(fmaxf(p.w, 0.0f), 1.0f);
+                const float oma = __fsub_rn(1.0f, alpha);
+                p = make_float4(__fadd_rn(p.x, __fmul_rn(oma, st.m[0])), __fadd_rn(p.y, __fmul_rn(oma, st.m[1])),
+                                __fadd_rn(p.z, __fmul_rn(oma, st.m[2])), __fadd_rn(p.w, __fmul_rn(oma, st.m[3])));
+                break;
+            }
             default: p = make_float4(0.f, 0.f, 0.f, 0.f); break;
             }
             if (i + 1 < n) p = quant4(p, type);
         }
         return p;
+    }
+};
+// The fast chain kernel: the step loop runs OUTSIDE the pixel loop -- a thread owns 4 (float / half) or 8 (8-bit) pixels and every
+// step is dispatched once for all of them -- and the storage type is a template parameter, so the node-boundary quantisation is
+// straight-line code.  (The generic k_pointwise<ChainOp> dispatches per pixel: 216 instructions per pixel for a three-step chain
+// on half frames, half of them branches and constant loads; profiles/r02_chain_kernel.md.)  Same functors, same arithmetic, same
+// quantisation points: bit-identical results.  Flip / Flop nodes read the mirrored 16-byte group and reverse it in registers.
+template <int TYPE>
+struct ChainGeom {
+    static constexpr int VEC = TYPE == TC_F32 ? 1 : (TYPE == TC_U8 ? 4 : 2); // pixels per 16 bytes
+    static constexpr int NG = TYPE == TC_F32 ? 4 : 2;                        // 16-byte groups per thread-iteration
+    static constexpr int NP = VEC * NG;
+};
+template <int TYPE>
+__device__ __forceinline__ void chain_unpack(const uint4 v, float4* px, bool reverse)
+{
+    constexpr int VEC = ChainGeom<TYPE>::VEC;
+    float4 t[VEC];
+    if (TYPE == TC_F32) {
+        t[0] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+    } else if (TYPE == TC_U8) {
+        const unsigned w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = make_float4(u8_to_f(w[j] & 0xffu), u8_to_f((w[j] >> 8) & 0xffu), u8_to_f((w[j] >> 16) & 0xffu), u8_to_f(w[j] >> 24));
+    } else if (TYPE == TC_U16) {
+        t[0] = make_float4(u16_to_f(v.x & 0xffffu), u16_to_f(v.x >> 16), u16_to_f(v.y & 0xffffu), u16_to_f(v.y >> 16));
+        t[VEC - 1] = make_float4(u16_to_f(v.z & 0xffffu), u16_to_f(v.z >> 16), u16_to_f(v.w & 0xffffu), u16_to_f(v.w >> 16));
+    } else {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+        t[0] = make_float4(a.x, a.y, b.x, b.y);
+        t[VEC - 1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) px[j] = reverse ? t[VEC - 1 - j] : t[j];
+}
+
+// the two long bodies as calls (one copy of the code, the pixel array stays in registers: a rolled loop would index it dynamically)
+__device__ __noinline__ float4 chain_pow_general(float v, float4 p)
+{
+    PowOp o;
+    o.v = v;
+    return o.apply(p);
+}
+__device__ __noinline__ float4 chain_color_convert(const ChainStep& st, float4 p)
+{
+    ColorConvertOp o;
+    o.curve_in = st.curve_in, o.curve_out = st.curve_out, o.unpremult = st.unpremult;
+    o.p_in = st.p_in, o.p_out = st.p_out;
+#pragma unroll
+    for (int m = 0; m < 9; ++m) o.m[m] = st.m[m];
+    return o.apply(p);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(PW_THREADS) k_chain(const __grid_constant__ ChainSteps c, const Img src, const Img dst, const int flipx, const int flipy)
+{
+    using G = ChainGeom<TYPE>;
+    constexpr int VEC = G::VEC, NG = G::NG, NP = G::NP;
+    const unsigned groups = ((unsigned)dst.w * (unsigned)dst.h) / VEC;
+    const unsigned gw = (unsigned)dst.w / VEC; // groups per row (flips only: the width is a multiple of VEC then)
+    const unsigned stride = gridDim.x * blockDim.x;
+    const uint4* __restrict__ in = reinterpret_cast<const uint4*>(src.p);
+    for (unsigned base = blockIdx.x * blockDim.x + threadIdx.x; base < groups; base += NG * stride) {
+        uint4 raw[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const unsigned g = base + k * stride;
+            if (g < groups) {
+                unsigned sg = g;
+                if (flipx | flipy) {
+                    const unsigned y = g / gw, xg = g - y * gw;
+                    sg = (flipy ? (unsigned)dst.h - 1 - y : y) * gw + (flipx ? gw - 1 - xg : xg);
+                }
+                raw[k] = __ldg(in + sg);
+            } else {
+                raw[k] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        float4 px[NP];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) chain_unpack<TYPE>(raw[k], px + k * VEC, flipx != 0);
+        for (int i = 0; i < c.n; ++i) {
+            const ChainStep& st = c.step[i];
+            switch (st.kind) {
+            case TC_CHAIN_INVERT:
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = InvertOp().apply(px[q]);
+                break;
+            case TC_CHAIN_POW: {
+                // (the exponent classes of PowOp::apply, decided once per step instead of once per pixel)
+                if (st.v == 2.0f) {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) px[q] = make_float4(px[q].x * px[q].x, px[q].y * px[q].y, px[q].z * px[q].z, px[q].w * px[q].w);
+                } else if (st.v == 3.0f) {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q)
+                        px[q] = make_float4(px[q].x * px[q].x * px[q].x, px[q].y * px[q].y * px[q].y, px[q].z * px[q].z * px[q].z, px[q].w * px[q].w * px[q].w);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) px[q] = chain_pow_general(st.v, px[q]);
+                }
+                break;
+            }
+            case TC_CHAIN_SATURATE: {
+                SaturateOp o;
+                o.v = st.v;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = o.apply(px[q]);
+                break;
+            }
+            case TC_CHAIN_COLOR_MAP: {
+                ColorMapOp o;
+                o.n = st.n;
+                o.k = st.k;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = o.apply(px[q]);
+                break;
+            }
+            case TC_CHAIN_PREMULT:
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = PremultOp().apply(px[q]);
+                break;
+            case TC_CHAIN_UNPREMULT:
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = UnpremultOp().apply(px[q]);
+                break;
+            case TC_CHAIN_COLOR_CONVERT:
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = chain_color_convert(st, px[q]);
+                break;
+            case TC_CHAIN_OVER_FILL: {
+                const float4 b = make_float4(st.m[0], st.m[1], st.m[2], st.m[3]);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    float4 p = px[q];
+                    if (st.unpremult) { // (the step's flag: premultiply first, into a typed buffer)
+                        if (p.w != 1.0f) {
+                            p.x = __fmul_rn(p.x, p.w);
+                            p.y = __fmul_rn(p.y, p.w);
+                            p.z = __fmul_rn(p.z, p.w);
+                        }
+                        p = quant4(p, TYPE);
+                    }
+                    const float oma = __fsub_rn(1.0f, fminf(fmaxf(p.w, 0.0f), 1.0f));
+                    px[q] = make_float4(__fadd_rn(p.x, __fmul_rn(oma, b.x)), __fadd_rn(p.y, __fmul_rn(oma, b.y)), __fadd_rn(p.z, __fmul_rn(oma, b.z)),
+                                        __fadd_rn(p.w, __fmul_rn(oma, b.w)));
+                }
+                break;
+            }
+            default:
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                break;
+            }
+            if (i + 1 < c.n && TYPE != TC_F32) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) px[q] = quant4(px[q], TYPE);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const unsigned g = base + k * stride;
+            if (g < groups) {
+                float4 v[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) v[j] = px[k * VEC + j];
+                store_vec<VEC>(dst.p, TYPE, g * VEC, v);
+            }
+        }
+    }
+}
+
+template <int TYPE>
+static int launch_chain(const ChainSteps& c, const tc_image* dst, const tc_image* src, int flipx, int flipy, tc_stream s)
+{
+    using G = ChainGeom<TYPE>;
+    const size_t groups = (size_t)dst->w * dst->h / G::VEC;
+    const size_t per_block = (size_t)PW_THREADS * G::NG;
+    size_t blocks = (groups + per_block - 1) / per_block;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    k_chain<TYPE><<<(unsigned)blocks, PW_THREADS, 0, (cudaStream_t)s>>>(c, view(src), view(dst), flipx, flipy);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_chain launch");
+}
+
+struct ChainOp {
+    Src s;
+    ChainSteps c;
+    TC_OP_1(s)
+    __device__ __forceinline__ float4 apply(float4 p) const { return c.apply(p); }
+};
+// ... with Flip / Flop nodes in the chain: they commute with every pointwise step, so their net effect is where the source is read
+struct ChainFlipOp {
+    TC_OP_0()
+    Img src;
+    int flipx, flipy;
+    ChainSteps c;
+    __device__ float4 operator()(int x, int y, unsigned) const
+    {
+        return c.apply(load_black(src, flipx ? src.w - 1 - x : x, flipy ? src.h - 1 - y : y));
     }
 };
 
@@ -981,16 +1198,27 @@ int tc_pointwise_chain(const tc_image* dst, const tc_image* src, const tc_chain_
     TC_VALIDATE(src, "tc_pointwise_chain src");
     if (!ops || n < 1 || n > TC_CHAIN_MAX) return fail(TC_ERR_INVALID, "tc_pointwise_chain: %d ops (1..%d)", n, TC_CHAIN_MAX);
     if (dst->type != src->type) return fail(TC_ERR_INVALID, "tc_pointwise_chain: source and destination storage types differ");
-    ChainOp op;
-    memset(&op, 0, sizeof(op));
-    op.s = make_src(src, dst);
-    op.n = n;
-    op.type = dst->type;
+    ChainSteps steps;
+    memset(&steps, 0, sizeof(steps));
+    steps.type = dst->type;
+    int flipx = 0, flipy = 0;
     for (int i = 0; i < n; ++i) {
-        ChainStep& st = op.step[i];
+        if (TC_CHAIN_FLIP == ops[i].kind || TC_CHAIN_FLOP == ops[i].kind) {
+            // position-only nodes: their typed output equals their input, so no step (and no quantisation) remains of them
+            if (src->w != dst->w || src->h != dst->h) return fail(TC_ERR_INVALID, "tc_pointwise_chain: Flip / Flop need same-sized frames");
+            (TC_CHAIN_FLIP == ops[i].kind ? flipy : flipx) ^= 1;
+            continue;
+        }
+        ChainStep& st = steps.step[steps.n++];
         st.kind = ops[i].kind;
         st.v = ops[i].value;
         switch (ops[i].kind) {
+        case TC_CHAIN_OVER_FILL:
+            if (ops[i].w != dst->w || ops[i].h != dst->h) return fail(TC_ERR_INVALID, "tc_pointwise_chain: the Fill frame's size differs from the chain's");
+            st.unpremult = ops[i].flag ? 1 : 0;
+            // the colour as the Fill generator's UINT8 frame holds it (ImageEffect.cpp:93)
+            for (int c = 0; c < 4; ++c) st.m[c] = quant_host(ops[i].color[c], TC_U8);
+            break;
         case TC_CHAIN_INVERT:
         case TC_CHAIN_POW:
         case TC_CHAIN_SATURATE:
@@ -1014,6 +1242,35 @@ int tc_pointwise_chain(const tc_image* dst, const tc_image* src, const tc_chain_
         default: return fail(TC_ERR_INVALID, "tc_pointwise_chain: unknown op kind %d", ops[i].kind);
         }
     }
+    // the fast kernel: whole 16-byte groups of same-sized, 16-byte aligned frames (a flip also needs whole groups per row)
+    {
+        const int vec = dst->type == TC_F32 ? 1 : (dst->type == TC_U8 ? 4 : 2);
+        const size_t total = (size_t)dst->w * dst->h;
+        if (steps.n > 0 && src->w == dst->w && src->h == dst->h && total < (1ull << 31) && total % vec == 0 && !(((uintptr_t)src->data | (uintptr_t)dst->data) & 15) &&
+            (!(flipx || flipy) || dst->w % vec == 0)) {
+            switch (dst->type) {
+            case TC_U8: return launch_chain<TC_U8>(steps, dst, src, flipx, flipy, s);
+            case TC_U16: return launch_chain<TC_U16>(steps, dst, src, flipx, flipy, s);
+            case TC_F16: return launch_chain<TC_F16>(steps, dst, src, flipx, flipy, s);
+            default: return launch_chain<TC_F32>(steps, dst, src, flipx, flipy, s);
+            }
+        }
+    }
+    if (flipx || flipy) {
+        ChainFlipOp op;
+        memset(&op, 0, sizeof(op));
+        op.src = view(src);
+        op.flipx = flipx;
+        op.flipy = flipy;
+        op.c = steps;
+        if (0 == steps.n) return flipx && flipy ? fail(TC_ERR_UNSUPPORTED, "tc_pointwise_chain: a chain of flips only") : (flipy ? tc_flip(dst, src, s) : tc_flop(dst, src, s));
+        return launch(op, dst, s);
+    }
+    if (0 == steps.n) return fail(TC_ERR_INVALID, "tc_pointwise_chain: empty chain");
+    ChainOp op;
+    memset(&op, 0, sizeof(op));
+    op.s = make_src(src, dst);
+    op.c = steps;
     return launch(op, dst, s);
 }
 

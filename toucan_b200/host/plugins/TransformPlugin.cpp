@@ -20,9 +20,18 @@ namespace toucan_ofx
                            static_cast<int>(size[1]), a.stream);
         }
 
-        int flip(const RenderArgs& a, const Params&) { return tc_flip(&a.output, &a.source[0], a.stream); }
+        // Flip / Flop only change where the source pixel is read: in the host's chain fusion they are position ops
+        int flip(const RenderArgs& a, const Params&)
+        {
+            if (a.chain) return chainAppend(a, chainOp(TC_CHAIN_FLIP));
+            return tc_flip(&a.output, &a.source[0], a.stream);
+        }
 
-        int flop(const RenderArgs& a, const Params&) { return tc_flop(&a.output, &a.source[0], a.stream); }
+        int flop(const RenderArgs& a, const Params&)
+        {
+            if (a.chain) return chainAppend(a, chainOp(TC_CHAIN_FLOP));
+            return tc_flop(&a.output, &a.source[0], a.stream);
+        }
 
         int resize(const RenderArgs& a, const Params& p)
         {
@@ -53,8 +62,8 @@ namespace toucan_ofx
     {
         static const std::vector<EffectDef> table = {
             { "toucan:Crop", "Crop", Context::Filter, { paramInt2("pos", "Position", 0, 0), paramInt2("size", "Size", 0, 0) }, &crop },
-            { "toucan:Flip", "Flip", Context::Filter, {}, &flip },
-            { "toucan:Flop", "Flop", Context::Filter, {}, &flop },
+            { "toucan:Flip", "Flip", Context::Filter, {}, &flip, true },
+            { "toucan:Flop", "Flop", Context::Filter, {}, &flop, true },
             { "toucan:Resize", "Resize", Context::Filter,
               { paramInt2("size", "Size", 0, 0), paramString("filter_name", "Filter name", ""), paramDouble("filter_width", "Filter width", 0.0) },
               &resize },

@@ -3,6 +3,8 @@
 #include "StackFusion.h"
 #include "Util.h"
 
+#include <cstring>
+
 namespace toucan
 {
     CompNode::CompNode(const std::vector<std::shared_ptr<IImageNode> >& inputs) :
@@ -77,6 +79,38 @@ namespace toucan
         return out;
     }
 
+    bool CompNode::describeChain(tc_chain& chain, std::shared_ptr<IImageNode>& input) const
+    {
+        if (_inputs.size() < 2 || !_inputs[0] || !_inputs[1] || chain.n >= TC_CHAIN_MAX)
+        {
+            return false;
+        }
+        IMATH_NAMESPACE::V2i fillSize(0, 0);
+        float fillColor[4];
+        int w = 0, h = 0;
+        if (!matchFillBackground(_inputs[1], fillSize, fillColor) || !_inputs[0]->sizeHint(w, h) || w != fillSize.x || h != fillSize.y)
+        {
+            return false;
+        }
+        tc_chain_op& op = chain.ops[chain.n++];
+        memset(&op, 0, sizeof(op));
+        op.kind = TC_CHAIN_OVER_FILL;
+        op.flag = _premultiply ? 1 : 0;
+        for (int c = 0; c < 4; ++c) op.color[c] = fillColor[c];
+        op.w = fillSize.x;
+        op.h = fillSize.y;
+        input = _inputs[0];
+        return true;
+    }
+
+    bool CompNode::sizeHint(int& width, int& height) const
+    {
+        // the composite has the background's size (a foreground of another size is fitted into it)
+        if (_inputs.size() > 1 && _inputs[1]) return _inputs[1]->sizeHint(width, height);
+        if (1 == _inputs.size() && _inputs[0]) return _inputs[0]->sizeHint(width, height);
+        return false;
+    }
+
     Image CompNode::exec()
     {
         Image buf;
@@ -86,6 +120,11 @@ namespace toucan
             // sources collapses into one pass (StackFusion.h).  Falls through when the
             // pattern does not match.
             if (_premultiply && tryFusedStack(*this, buf))
+            {
+                return buf;
+            }
+            // ... and over the Fill's colour the node is one more step of the foreground's chain of same-position operations
+            if (tryNodeChain(*this, buf))
             {
                 return buf;
             }

@@ -24,6 +24,11 @@ namespace toucan
 
         Image exec() override;
 
+        //! Over the Fill generator at the bottom of a track stack, with a foreground known to have the Fill's size, the
+        //! node is a same-position operation on its foreground (TC_CHAIN_OVER_FILL).
+        bool describeChain(tc_chain& chain, std::shared_ptr<IImageNode>& input) const override;
+        bool sizeHint(int& width, int& height) const override;
+
         //! Composite two already evaluated images (exec, and the fusion pass for layers it cannot fuse).
         Image composite(const Image& fg, const Image& bg) const;
 

@@ -158,42 +158,41 @@ namespace toucan
         return true;
     }
 
-    bool ImageEffectNode::_tryPointwiseChain(Image& out)
+    bool ImageEffectNode::describeChain(tc_chain& chain, std::shared_ptr<IImageNode>& input) const
     {
-        if (!getStackFusionEnabled())
+        if (!describePointwise(chain))
         {
             return false;
         }
-        // Walk down while the nodes are pointwise effects; ops are recorded top first.
-        tc_chain chain;
-        memset(&chain, 0, sizeof(chain));
-        const ImageEffectNode* node = this;
-        std::shared_ptr<IImageNode> base;
-        while (node && node->describePointwise(chain))
-        {
-            base = node->_inputs[0];
-            node = dynamic_cast<const ImageEffectNode*>(base.get());
-        }
-        if (chain.n < 2)
-        {
-            return false; // a single effect takes the ordinary per-node path
-        }
-        const Image source = base->exec();
-        const ImageSpec& spec = source.spec();
-        if (spec.width <= 0 || spec.height <= 0)
-        {
-            out = Image(); // what a chain of filters over a missing image yields node by node
-            return true;
-        }
-        tc_chain_op ops[TC_CHAIN_MAX];
-        for (int i = 0; i < chain.n; ++i)
-        {
-            ops[i] = chain.ops[chain.n - 1 - i];
-        }
-        out = Image(spec);
-        const tc_image src = source.view(), dst = out.view();
-        tcCheck(tc_pointwise_chain(&dst, &src, ops, chain.n, DeviceContext::stream()), "tc_pointwise_chain");
+        input = _inputs[0];
         return true;
+    }
+
+    bool ImageEffectNode::sizeHint(int& width, int& height) const
+    {
+        const auto sizeIt = _settings.find("size");
+        if (sizeIt != _settings.end() && sizeIt->second.has_value())
+        {
+            IMATH_NAMESPACE::V2i size(0, 0);
+            try
+            {
+                anyToVec(std::any_cast<OTIO_NS::AnyVector>(sizeIt->second), size);
+            }
+            catch (const std::exception&)
+            {
+                return false;
+            }
+            width = size.x;
+            height = size.y;
+            return size.x > 0 && size.y > 0;
+        }
+        char* context = nullptr;
+        _effect.propSet.getString(kOfxImageEffectPropSupportedContexts, 0, &context);
+        if (context && 0 != strcmp(context, kOfxImageEffectContextGenerator) && !_inputs.empty() && _inputs[0])
+        {
+            return _inputs[0]->sizeHint(width, height); // filters and transitions render at their (first) input's size
+        }
+        return false;
     }
 
     Image ImageEffectNode::exec()
@@ -205,7 +204,7 @@ namespace toucan
         if (context && 0 == strcmp(context, kOfxImageEffectContextFilter))
         {
             Image fused;
-            if (_tryPointwiseChain(fused))
+            if (tryNodeChain(*this, fused))
             {
                 return fused;
             }

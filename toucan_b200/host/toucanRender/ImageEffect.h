@@ -76,9 +76,10 @@ namespace toucan
         //! parameters as IT resolves them) to `chain` instead of launching it.  False if the effect is not a
         //! same-size, single-input pointwise effect, or the plug-in does not take part.
         bool describePointwise(tc_chain& chain) const;
+        bool describeChain(tc_chain& chain, std::shared_ptr<IImageNode>& input) const override;
+        bool sizeHint(int& width, int& height) const override;
 
     private:
-        bool _tryPointwiseChain(Image& out);
 
         ImageEffectPlugin& _effect;                  // the loaded effect this node instantiates
         OTIO_NS::AnyDictionary _settings;            // the metadata the node was created with

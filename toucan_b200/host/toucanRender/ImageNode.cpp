@@ -1,5 +1,8 @@
 #include "ImageNode.h"
 
+#include "StackFusion.h"
+
+#include <cstring>
 #include <sstream>
 
 namespace toucan
@@ -23,6 +26,58 @@ namespace toucan
     void IImageNode::setTime(const OTIO_NS::RationalTime& value) { _time = value; }
 
     const OTIO_NS::RationalTime& IImageNode::getTime() const { return _time; }
+
+    bool IImageNode::describeChain(tc_chain&, std::shared_ptr<IImageNode>&) const { return false; }
+
+    bool IImageNode::sizeHint(int&, int&) const { return false; }
+
+    bool tryNodeChain(const IImageNode& top, Image& out)
+    {
+        if (!getStackFusionEnabled())
+        {
+            return false;
+        }
+        // Walk down while the nodes are same-position operations; ops are recorded top first.
+        tc_chain chain;
+        memset(&chain, 0, sizeof(chain));
+        const IImageNode* node = &top;
+        std::shared_ptr<IImageNode> base, next;
+        while (node && node->describeChain(chain, next))
+        {
+            base = next;
+            node = base.get();
+        }
+        if (chain.n < 2 || !base)
+        {
+            return false; // a single operation takes the ordinary per-node path
+        }
+        const Image source = base->exec();
+        const ImageSpec& spec = source.spec();
+        if (spec.width <= 0 || spec.height <= 0)
+        {
+            bool comp = false;
+            for (int i = 0; i < chain.n; ++i) comp = comp || TC_CHAIN_OVER_FILL == chain.ops[i].kind;
+            if (comp)
+            {
+                return false; // an empty foreground leaves the background: the per-node path renders it (rare: missing media)
+            }
+            out = Image(); // what a chain of filters over a missing image yields node by node
+            return true;
+        }
+        tc_chain_op ops[TC_CHAIN_MAX];
+        for (int i = 0; i < chain.n; ++i)
+        {
+            ops[i] = chain.ops[chain.n - 1 - i];
+            if (TC_CHAIN_OVER_FILL == ops[i].kind && (ops[i].w != spec.width || ops[i].h != spec.height))
+            {
+                return false; // (sizeHint said otherwise: fall back; the source is evaluated again by the per-node path)
+            }
+        }
+        out = Image(spec);
+        const tc_image src = source.view(), dst = out.view();
+        tcCheck(tc_pointwise_chain(&dst, &src, ops, chain.n, DeviceContext::stream()), "tc_pointwise_chain");
+        return true;
+    }
 
     namespace
     {

@@ -40,6 +40,12 @@ namespace toucan
         //! node's output without waiting for them.
         virtual Image exec() = 0;
 
+        //! Cross-node fusion of same-position operations (tc_pointwise_chain): a node that is such an operation on ONE input
+        //! appends its tc_chain_op, names that input and returns true; anything else returns false and ends the chain.
+        virtual bool describeChain(tc_chain& chain, std::shared_ptr<IImageNode>& input) const;
+        //! The size of the frame exec() will return, when it is known without evaluating anything (false otherwise).
+        virtual bool sizeHint(int& width, int& height) const;
+
         //! The tree under this node as Graphviz source, one line per element.
         std::vector<std::string> graph(const std::string& name);
 
@@ -53,4 +59,7 @@ namespace toucan
         ImageNodeList _inputs;
         OTIO_NS::RationalTime _time;
     };
+    //! Evaluate the chain of same-position nodes that starts at `top` (two or more of them) as ONE kernel over the chain's
+    //! source; false when `top` does not start such a chain (nothing has been evaluated then).
+    bool tryNodeChain(const IImageNode& top, Image& out);
 }

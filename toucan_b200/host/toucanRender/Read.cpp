@@ -299,6 +299,13 @@ namespace toucan
 
     const ImageSpec& IReadNode::getSpec() const { return _spec; }
 
+    bool IReadNode::sizeHint(int& width, int& height) const
+    {
+        width = _spec.width;
+        height = _spec.height;
+        return width > 0 && height > 0;
+    }
+
     const OTIO_NS::TimeRange& IReadNode::getTimeRange() const { return _timeRange; }
 
     Image uploadToCache(const MediaFrame& frame, const std::shared_ptr<MediaStore>& store, int device, const std::string& path)

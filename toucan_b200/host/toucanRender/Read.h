@@ -114,6 +114,7 @@ namespace toucan
         virtual ~IReadNode() = 0;
 
         const ImageSpec& getSpec() const;
+        bool sizeHint(int& width, int& height) const override;
 
         const OTIO_NS::TimeRange& getTimeRange() const;
 

@@ -193,6 +193,11 @@ def pointwise_chain(src, steps):
         elif st[0] == "color_convert":
             arr[i].name_a, arr[i].name_b = st[1].encode(), st[2].encode()
             arr[i].flag = 1 if (len(st) > 3 and st[3]) else 0
+        elif st[0] == "over_fill":  # ("over_fill", colour, premult): CompNode over the Fill generator's frame
+            for c in range(4):
+                arr[i].color[c] = float(st[1][c])
+            arr[i].flag = 1 if st[2] else 0
+            arr[i].w, arr[i].h = int(src.shape[1]), int(src.shape[0])
     return _unary(lib().tc_pointwise_chain, "tc_pointwise_chain", src, arr, len(steps))
 
 
