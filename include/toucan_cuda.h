@@ -179,7 +179,11 @@ enum { TC_CHAIN_INVERT = 0, TC_CHAIN_POW, TC_CHAIN_SATURATE, TC_CHAIN_COLOR_MAP,
        TC_CHAIN_ZERO,
        TC_CHAIN_OVER_FILL, /* lib/toucanRender/Comp.cpp:29-84 over the Fill generator's frame: color = the fill colour, flag = premult */
        TC_CHAIN_FLIP,      /* plugins/TransformPlugin.cpp:232-248 */
-       TC_CHAIN_FLOP };    /* :277-293 */
+       TC_CHAIN_FLOP,      /* :277-293 */
+       /* A chain may START with one convolution node (ops[0] only): the remaining ops run as the Blur / UnsharpMask kernel's
+          epilogue when they are simple (Invert, Premult, Pow 2 / 3, over-Fill), else as a second launch over a temporary. */
+       TC_CHAIN_BLUR,      /* plugins/FilterPlugin.cpp:178-205: value = radius */
+       TC_CHAIN_UNSHARP }; /* :590-621: name_a = kernel, value = width, color[0] = contrast, color[1] = threshold */
 #define TC_CHAIN_MAX 8
 typedef struct tc_chain_op {
     int kind;

@@ -49,7 +49,7 @@ int main(int argc, char** argv)
     probe(host, "toucan:ColorConvert", none); // effective defaults (premult -> 0)
     probe(host, "toucan:Premult", none);
     probe(host, "toucan:Unpremult", none);
-    probe(host, "toucan:Blur", blur);         // not pointwise: refuses
+    probe(host, "toucan:Blur", blur);         // a convolution node describes itself as the head of a chain
     probe(host, "toucan:Pow", sized);         // output-size override: refuses
     return 0;
 }

@@ -164,8 +164,9 @@ def test_c2_chained_filters_fuse_into_fewer_launches(cuda):
     finally:
         render.set_fusion(True)
     assert fused.dtype == np.float32 and np.array_equal(fused, plain)
-    # 4 pointwise launches became 1, and the Fill background is composited as a colour instead of a rendered frame
-    assert plain_launches - fused_launches == 4, (plain_launches, fused_launches)
+    # 4 pointwise launches became 1, the Fill background is composited as a colour instead of a rendered frame, and that
+    # composite is the UnsharpMask kernel's epilogue: 8 launches -> 3 (chain, Blur, UnsharpMask + over)
+    assert (plain_launches, fused_launches) == (8, 3), (plain_launches, fused_launches)
     otl = G.Timeline(doc)
     otl.dir = "/synthetic"
     want = G.ImageGraph(otl, lambda p: src if p == path else None).render(G.RT(2.0, 24.0))

@@ -138,7 +138,7 @@ def test_plugins_resolve_parameters_through_the_host_suites(tmp_path):
         "toucan:ColorConvert 1 1 6 0 0 [] []",                          # effective default of "premult" is 0
         "toucan:Premult 1 1 4 0 0 [] []",
         "toucan:Unpremult 1 1 5 0 0 [] []",
-        "toucan:Blur 0 0 -1 0 0 [] []",                                 # not a pointwise effect
+        "toucan:Blur 1 1 11 10 0 [] []",                                # a convolution node: may START a chain (TC_CHAIN_BLUR, radius)
         "toucan:Pow 0 0 -1 0 0 [] []",                                  # output-size override
     ], out
 

@@ -452,6 +452,44 @@ def test_pointwise_chain_equals_the_nodes_one_by_one(dt, chain):
     assert_close(got, ref, f"chain {chain} vs oracle", tol=2e-5, lsb=2)
 
 
+CONV_CHAINS = [
+    # data/MultipleEffects.otio's first clip below its Flip: Blur (clip), Invert (track), CompNode over the Fill frame, Pow 3 (stack):
+    # simple followers -> the Blur kernel's epilogue, one launch
+    [("blur", 20.0), ("invert",), ("over_fill", (0.0, 0.0, 0.0, 1.0), True), ("pow", 3.0)],
+    [("blur", 10.0), ("over_fill", (0.2, 0.4, 0.6, 1.0), True)],
+    # SURVEY 8d config 2's tail: UnsharpMask, then CompNode over the Fill frame
+    [("unsharp", "gaussian", 10.0, 1.0, 0.0), ("over_fill", (0.0, 0.0, 0.0, 1.0), True)],
+    [("unsharp", "gaussian", 3.0, 0.7, 0.05), ("premult",), ("pow", 2.0), ("invert",)],
+    # followers the epilogue does not cover (Saturate, ColorMap, Pow 2.2): convolution into a temporary, then the rest as one launch
+    [("blur", 7.0), ("saturate", 0.5), ("color_map", "plasma"), ("invert",)],
+    [("blur", 13.0), ("pow", 2.2), ("over_fill", (0.0, 0.0, 0.0, 1.0), True)],
+]
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+@pytest.mark.parametrize("chain", range(len(CONV_CHAINS)))
+@pytest.mark.parametrize("size", [(332, 217), (333, 217)])  # TMA kernel / typed-load kernel (odd 8/16-bit row pitch: not fusable into the kernel)
+def test_chain_with_a_convolution_head_equals_the_nodes_one_by_one(dt, chain, size):
+    from toucan_b200 import capi, ops
+
+    steps = CONV_CHAINS[chain]
+    src = rand_img(size[0], size[1], dt, 70 + chain, alpha="mixed")
+    n0 = capi.launch_count()
+    got = ops.pointwise_chain(to_dev(src), steps)
+    launches = capi.launch_count() - n0
+    seq = to_dev(src)
+    for st in steps:
+        if st[0] == "blur":
+            seq = ops.blur(seq, st[1])
+        elif st[0] == "unsharp":
+            seq = ops.unsharp_mask(seq, st[1], st[2], st[3], st[4])
+        else:
+            seq = _single(ops, seq, st)
+    assert_exact(got, to_host(seq), f"conv chain {chain} vs per-node kernels")
+    aligned = (size[0] * 4 * np.dtype(dt).itemsize) % 16 == 0
+    assert launches == (1 if (chain < 4 and aligned) else 2), launches
+
+
 def test_pointwise_chain_rejects():
     from toucan_b200 import capi, ops
 

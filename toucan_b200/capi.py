@@ -32,7 +32,7 @@ class tc_chain_op(ctypes.Structure):
 
 
 CHAIN_KINDS = {"invert": 0, "pow": 1, "saturate": 2, "color_map": 3, "premult": 4, "unpremult": 5, "color_convert": 6,
-               "over_fill": 8, "flip": 9, "flop": 10}
+               "over_fill": 8, "flip": 9, "flop": 10, "blur": 11, "unsharp": 12}
 
 
 class tc_stack_layer(ctypes.Structure):

@@ -26,6 +26,17 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes);
         if (_st != TC_OK) return _st;                      \
     } while (0)
 
+// Blur / UnsharpMask with an epilogue of simple chain steps (tc_conv.cu; called by tc_pointwise_chain for a chain that starts
+// with a convolution node).  *fused = 0 when the case is not covered (nothing launched then).
+struct EpiSteps {
+    int n, type;
+    int kind[8];     // TC_CHAIN_INVERT, _PREMULT, _POW (value 2 or 3 only), _OVER_FILL
+    float v[8];      // Pow exponent
+    int premult[8];  // OVER_FILL: premultiply first
+    float color[8][4];
+};
+int gauss_with_epilogue(const tc_image* dst, const tc_image* src, const tc_chain_op& head, const EpiSteps& epi, tc_stream s, int* fused);
+
 // Device-side image view.
 struct Img {
     void* p;

@@ -204,13 +204,59 @@ __device__ __forceinline__ float4 staged_px(const unsigned char* tile, int byte_
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// The epilogue: simple same-position graph nodes that follow the convolution node, applied to the finished pixel in registers.
+// Explicit round-to-nearest operations (no contraction): bit-identical to the pointwise kernels' functors (tc_pointwise.cu).
+template <int TYPE>
+__device__ __forceinline__ float4 epi_apply(const EpiSteps& e, float4 p)
+{
+    p = quant4(p, TYPE); // the convolution node's own typed output
+    for (int i = 0; i < e.n; ++i) {
+        switch (e.kind[i]) {
+        case TC_CHAIN_INVERT:
+            p.x = __fadd_rn(__fmul_rn(p.x, -1.0f), 1.0f);
+            p.y = __fadd_rn(__fmul_rn(p.y, -1.0f), 1.0f);
+            p.z = __fadd_rn(__fmul_rn(p.z, -1.0f), 1.0f);
+            break;
+        case TC_CHAIN_PREMULT:
+            if (p.w != 1.0f) {
+                p.x = __fmul_rn(p.x, p.w);
+                p.y = __fmul_rn(p.y, p.w);
+                p.z = __fmul_rn(p.z, p.w);
+            }
+            break;
+        case TC_CHAIN_POW:
+            if (e.v[i] == 2.0f) p = make_float4(__fmul_rn(p.x, p.x), __fmul_rn(p.y, p.y), __fmul_rn(p.z, p.z), __fmul_rn(p.w, p.w));
+            else p = make_float4(__fmul_rn(__fmul_rn(p.x, p.x), p.x), __fmul_rn(__fmul_rn(p.y, p.y), p.y), __fmul_rn(__fmul_rn(p.z, p.z), p.z),
+                                 __fmul_rn(__fmul_rn(p.w, p.w), p.w));
+            break;
+        default: { // TC_CHAIN_OVER_FILL
+            if (e.premult[i]) {
+                if (p.w != 1.0f) {
+                    p.x = __fmul_rn(p.x, p.w);
+                    p.y = __fmul_rn(p.y, p.w);
+                    p.z = __fmul_rn(p.z, p.w);
+                }
+                p = quant4(p, TYPE);
+            }
+            const float oma = __fsub_rn(1.0f, fminf(fmaxf(p.w, 0.0f), 1.0f));
+            p = make_float4(__fadd_rn(p.x, __fmul_rn(oma, e.color[i][0])), __fadd_rn(p.y, __fmul_rn(oma, e.color[i][1])),
+                            __fadd_rn(p.z, __fmul_rn(oma, e.color[i][2])), __fadd_rn(p.w, __fmul_rn(oma, e.color[i][3])));
+            break;
+        }
+        }
+        if (i + 1 < e.n) p = quant4(p, TYPE);
+    }
+    return p;
+}
+
 struct GtParams {
     int w, h, tiles_x, n_tiles;
     ConvParams c;
+    EpiSteps epi;
     alignas(64) CUtensorMap map;
 };
 
-template <int R, int TYPE, bool UNSHARP, int NBUF, int OCC>
+template <int R, int TYPE, bool UNSHARP, int NBUF, int OCC, bool EPI>
 __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict__ dstp, const __grid_constant__ GtParams Q)
 {
     using T = GtTile<R, TYPE, NBUF>;
@@ -348,7 +394,7 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict_
         if (x < Q.w) {
 #pragma unroll
             for (int k = 0; k < PX; ++k)
-                if (y + k < Q.h) store_px(dstp, TYPE, (size_t)(y + k) * Q.w + x, f[k]);
+                if (y + k < Q.h) store_px(dstp, TYPE, (size_t)(y + k) * Q.w + x, EPI ? epi_apply<TYPE>(Q.epi, f[k]) : f[k]);
         }
     }
 }
@@ -476,8 +522,8 @@ static bool gt_use_tma()
     return on;
 }
 
-template <int R, int TYPE, bool UNSHARP>
-static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
+template <int R, int TYPE, bool UNSHARP, bool EPI = false>
+static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi = nullptr)
 {
     // two staging buffers per CTA unless that leaves one CTA (8 warps) per SM: then one buffer and two CTAs, which cover each
     // other's copy latency (float frames from R = 6 up)
@@ -491,26 +537,37 @@ static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const Conv
     Q.tiles_x = (dst->w + ST_TW - 1) / ST_TW;
     Q.n_tiles = Q.tiles_x * ((dst->h + T::TH - 1) / T::TH);
     Q.c = P;
+    if (EPI) Q.epi = *epi;
+    else Q.epi.n = 0;
     const unsigned long long pitch = (unsigned long long)src->w * T::B;
     int e = tensor_map_2d(src->data, T::ELEM, pitch / T::ELEM, (unsigned long long)src->h, pitch, (unsigned)(T::BW * T::B / T::ELEM), (unsigned)T::IH, &Q.map);
     if (e != TC_OK) return e;
-    e = ensure_dynamic_smem((const void*)k_gauss_tma<R, TYPE, UNSHARP, NBUF, OCC>, T::SMEM);
+    e = ensure_dynamic_smem((const void*)k_gauss_tma<R, TYPE, UNSHARP, NBUF, OCC, EPI>, T::SMEM);
     if (e != TC_OK) return e;
     const int grid = min(Q.n_tiles, num_sms() * OCC);
-    k_gauss_tma<R, TYPE, UNSHARP, NBUF, OCC><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
+    k_gauss_tma<R, TYPE, UNSHARP, NBUF, OCC, EPI><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
     count_launch();
     return check_cuda(cudaGetLastError(), "k_gauss_tma launch");
 }
 
-template <int R, bool UNSHARP>
-static int launch_gauss_tma_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
+template <int R, bool UNSHARP, bool EPI = false>
+static int launch_gauss_tma_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi = nullptr)
 {
     switch (src->type) {
-    case TC_U8: return launch_gauss_tma<R, TC_U8, UNSHARP>(dst, src, P, st);
-    case TC_U16: return launch_gauss_tma<R, TC_U16, UNSHARP>(dst, src, P, st);
-    case TC_F16: return launch_gauss_tma<R, TC_F16, UNSHARP>(dst, src, P, st);
-    default: return launch_gauss_tma<R, TC_F32, UNSHARP>(dst, src, P, st);
+    case TC_U8: return launch_gauss_tma<R, TC_U8, UNSHARP, EPI>(dst, src, P, st, epi);
+    case TC_U16: return launch_gauss_tma<R, TC_U16, UNSHARP, EPI>(dst, src, P, st, epi);
+    case TC_F16: return launch_gauss_tma<R, TC_F16, UNSHARP, EPI>(dst, src, P, st, epi);
+    default: return launch_gauss_tma<R, TC_F32, UNSHARP, EPI>(dst, src, P, st, epi);
     }
+}
+template <bool UNSHARP>
+static int launch_gauss_epi(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi)
+{
+    if (P.R <= 2) return launch_gauss_tma_t<2, UNSHARP, true>(dst, src, P, st, epi);
+    if (P.R <= 4) return launch_gauss_tma_t<4, UNSHARP, true>(dst, src, P, st, epi);
+    if (P.R <= 6) return launch_gauss_tma_t<6, UNSHARP, true>(dst, src, P, st, epi);
+    if (P.R <= 9) return launch_gauss_tma_t<9, UNSHARP, true>(dst, src, P, st, epi);
+    return launch_gauss_tma_t<12, UNSHARP, true>(dst, src, P, st, epi);
 }
 
 // the TMA kernel's preconditions: same-sized, same-typed frames of at least one tile, 16-byte aligned rows
@@ -521,16 +578,14 @@ static bool gauss_tma_ok(const tc_image* dst, const tc_image* src)
     const size_t pitch = (size_t)src->w * 4 * tc_type_size(src->type);
     return !(pitch & 15) && !((uintptr_t)src->data & 15);
 }
-// Which kernel for which case (4K, one B200, profiles/r02_op_bench_blur.md): float frames take the TMA kernel at every radius
-// (r = 10: 0.078 -> 0.047 ms, r = 20: 0.126 -> 0.094 ms); 8/16-bit and half frames are bound by the conversions and the
-// FMA pipe, not by bytes: the TMA kernel converts a staged pixel once per warp that reads it (2-3x per pixel), the typed-load
-// kernel once at staging, which wins from R = 6 up (u8 r = 20: 0.099 vs 0.114 ms).
-static bool gauss_tma_pays(int R, int type) { return type == TC_F32 || R <= 4; }
+// (Half / 8-bit frames at R >= 6 were a few percent faster in round 1's typed-load kernel -- u8 r = 20: 0.099 vs 0.114 ms at 4K --
+// because the TMA kernel converts a staged pixel once per warp that reads it.  They take the TMA kernel all the same: a node chain
+// fused into its epilogue must give the very bits of the node-by-node path, so both have to run the same convolution.)
 
 template <bool UNSHARP>
 static int launch_conv_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st)
 {
-    if (P.R <= 12 && gauss_tma_ok(dst, src) && gauss_tma_pays(P.R, src->type)) {
+    if (P.R <= 12 && gauss_tma_ok(dst, src)) {
         if (P.R <= 2) return launch_gauss_tma_t<2, UNSHARP>(dst, src, P, st);
         if (P.R <= 4) return launch_gauss_tma_t<4, UNSHARP>(dst, src, P, st);
         if (P.R <= 6) return launch_gauss_tma_t<6, UNSHARP>(dst, src, P, st);
@@ -555,6 +610,19 @@ static int launch_conv_t(const tc_image* dst, const tc_image* src, const ConvPar
 static int launch_conv(const tc_image* dst, const tc_image* src, const ConvParams& P, bool unsharp, tc_stream s)
 {
     return unsharp ? launch_conv_t<true>(dst, src, P, (cudaStream_t)s) : launch_conv_t<false>(dst, src, P, (cudaStream_t)s);
+}
+
+int gauss_with_epilogue(const tc_image* dst, const tc_image* src, const tc_chain_op& head, const EpiSteps& epi, tc_stream s, int* fused)
+{
+    *fused = 0;
+    const bool unsharp = TC_CHAIN_UNSHARP == head.kind;
+    if (unsharp && strcmp(head.name_a, "gaussian") != 0) return TC_OK; // (the per-node call reports it)
+    ConvParams P;
+    if (build_params(head.value, &P) != TC_OK || P.R > 12 || !gauss_tma_ok(dst, src)) return TC_OK;
+    P.contrast = unsharp ? head.color[0] : 0.f;
+    P.threshold = unsharp ? head.color[1] : 0.f;
+    *fused = 1;
+    return unsharp ? launch_gauss_epi<true>(dst, src, P, (cudaStream_t)s, &epi) : launch_gauss_epi<false>(dst, src, P, (cudaStream_t)s, &epi);
 }
 
 } // namespace tc

@@ -1198,6 +1198,55 @@ int tc_pointwise_chain(const tc_image* dst, const tc_image* src, const tc_chain_
     TC_VALIDATE(src, "tc_pointwise_chain src");
     if (!ops || n < 1 || n > TC_CHAIN_MAX) return fail(TC_ERR_INVALID, "tc_pointwise_chain: %d ops (1..%d)", n, TC_CHAIN_MAX);
     if (dst->type != src->type) return fail(TC_ERR_INVALID, "tc_pointwise_chain: source and destination storage types differ");
+    if (TC_CHAIN_BLUR == ops[0].kind || TC_CHAIN_UNSHARP == ops[0].kind) {
+        // A chain that starts with a convolution node.  Simple followers (Invert, Premult, Pow 2 / 3, over-Fill) run as the
+        // convolution kernel's epilogue: one launch, no intermediate frame.  Anything else: the convolution into a temporary,
+        // then the rest of the chain -- still one frame pass fewer per fused node.
+        if (src->w != dst->w || src->h != dst->h) return fail(TC_ERR_INVALID, "tc_pointwise_chain: a convolution node needs same-sized frames");
+        for (int i = 1; i < n; ++i)
+            if (TC_CHAIN_BLUR == ops[i].kind || TC_CHAIN_UNSHARP == ops[i].kind)
+                return fail(TC_ERR_INVALID, "tc_pointwise_chain: a convolution node can only start a chain");
+        EpiSteps epi;
+        memset(&epi, 0, sizeof(epi));
+        epi.type = dst->type;
+        bool simple = n - 1 <= 8;
+        for (int i = 1; i < n && simple; ++i) {
+            const tc_chain_op& o = ops[i];
+            const int k = epi.n;
+            switch (o.kind) {
+            case TC_CHAIN_INVERT:
+            case TC_CHAIN_PREMULT: break;
+            case TC_CHAIN_POW: simple = o.value == 2.0f || o.value == 3.0f; break;
+            case TC_CHAIN_OVER_FILL:
+                if (o.w != dst->w || o.h != dst->h) return fail(TC_ERR_INVALID, "tc_pointwise_chain: the Fill frame's size differs from the chain's");
+                epi.premult[k] = o.flag ? 1 : 0;
+                for (int c = 0; c < 4; ++c) epi.color[k][c] = quant_host(o.color[c], TC_U8);
+                break;
+            default: simple = false; break;
+            }
+            epi.kind[k] = o.kind;
+            epi.v[k] = o.value;
+            ++epi.n;
+        }
+        if (simple && n > 1) {
+            int fused = 0;
+            const int e = gauss_with_epilogue(dst, src, ops[0], epi, s, &fused);
+            if (e != TC_OK || fused) return e;
+        }
+        // not fusable into the kernel: convolution node, then the followers
+        const tc_image* conv_dst = dst;
+        tc_image tmp = *dst;
+        if (n > 1) {
+            int e = tc_malloc(&tmp.data, tc_image_bytes(dst->w, dst->h, dst->type), s);
+            if (e != TC_OK) return e;
+            conv_dst = &tmp;
+        }
+        int e = TC_CHAIN_BLUR == ops[0].kind ? tc_blur(conv_dst, src, ops[0].value, s)
+                                             : tc_unsharp_mask(conv_dst, src, ops[0].name_a, ops[0].value, ops[0].color[0], ops[0].color[1], s);
+        if (e == TC_OK && n > 1) e = tc_pointwise_chain(dst, &tmp, ops + 1, n - 1, s);
+        if (n > 1) tc_free(tmp.data, s);
+        return e;
+    }
     ChainSteps steps;
     memset(&steps, 0, sizeof(steps));
     steps.type = dst->type;

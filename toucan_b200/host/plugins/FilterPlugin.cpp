@@ -12,6 +12,8 @@ namespace toucan_ofx
         int blur(const RenderArgs& a, const Params& p)
         {
             const double radius = p.getDouble("radius", 0.0);
+            // in the host's chain fusion a convolution node may START a chain (its followers become the kernel's epilogue)
+            if (a.chain) return chainAppend(a, chainOp(TC_CHAIN_BLUR, static_cast<float>(radius)));
             return tc_blur(&a.output, &a.source[0], static_cast<float>(radius), a.stream);
         }
 
@@ -55,6 +57,14 @@ namespace toucan_ofx
             const double width = p.getDouble("width", 3.0);
             const double contrast = p.getDouble("contrast", 1.0);
             const double threshold = p.getDouble("threshold", 0.0);
+            if (a.chain)
+            {
+                tc_chain_op op = chainOp(TC_CHAIN_UNSHARP, static_cast<float>(width));
+                strncpy(op.name_a, kernel.c_str(), sizeof(op.name_a) - 1);
+                op.color[0] = static_cast<float>(contrast);
+                op.color[1] = static_cast<float>(threshold);
+                return chainAppend(a, op);
+            }
             return tc_unsharp_mask(&a.output, &a.source[0], kernel.c_str(), static_cast<float>(width), static_cast<float>(contrast),
                                    static_cast<float>(threshold), a.stream);
         }
@@ -63,7 +73,7 @@ namespace toucan_ofx
     const std::vector<EffectDef>& effects()
     {
         static const std::vector<EffectDef> table = {
-            { "toucan:Blur", "Blur", Context::Filter, { paramDouble("radius", "Radius", 10.0) }, &blur },
+            { "toucan:Blur", "Blur", Context::Filter, { paramDouble("radius", "Radius", 10.0) }, &blur, true },
             { "toucan:ColorMap", "ColorMap", Context::Filter, { paramString("map_name", "Map Name", "plasma") }, &colorMap, true },
             { "toucan:Invert", "Invert", Context::Filter, {}, &invert, true },
             { "toucan:Pow", "Pow", Context::Filter, { paramDouble("value", "Value", 1.0) }, &pow, true },
@@ -71,7 +81,7 @@ namespace toucan_ofx
             { "toucan:UnsharpMask", "UnsharpMask", Context::Filter,
               { paramString("kernel", "Kernel", "gaussian"), paramDouble("width", "Width", 1.0), paramDouble("contrast", "Contrast", 1.0),
                 paramDouble("threshold", "Threshold", 1.0) },
-              &unsharpMask },
+              &unsharpMask, true },
         };
         return table;
     }

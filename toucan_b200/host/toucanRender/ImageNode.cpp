@@ -46,6 +46,11 @@ namespace toucan
         {
             base = next;
             node = base.get();
+            const int kind = chain.ops[chain.n - 1].kind;
+            if (TC_CHAIN_BLUR == kind || TC_CHAIN_UNSHARP == kind)
+            {
+                break; // a convolution node can only START a chain: what feeds it is evaluated as its source
+            }
         }
         if (chain.n < 2 || !base)
         {

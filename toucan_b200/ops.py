@@ -193,6 +193,12 @@ def pointwise_chain(src, steps):
         elif st[0] == "color_convert":
             arr[i].name_a, arr[i].name_b = st[1].encode(), st[2].encode()
             arr[i].flag = 1 if (len(st) > 3 and st[3]) else 0
+        elif st[0] == "blur":  # ("blur", radius): only as the first step
+            arr[i].value = float(st[1])
+        elif st[0] == "unsharp":  # ("unsharp", kernel, width, contrast, threshold): only as the first step
+            arr[i].name_a = st[1].encode()
+            arr[i].value = float(st[2])
+            arr[i].color[0], arr[i].color[1] = float(st[3]), float(st[4])
         elif st[0] == "over_fill":  # ("over_fill", colour, premult): CompNode over the Fill generator's frame
             for c in range(4):
                 arr[i].color[c] = float(st[1][c])
