@@ -38,18 +38,22 @@ def main():
         assert [f for f, _ in flat] == list(range(frames)), "blocks must tile the timeline once, in order"
         single = [hashlib.sha256(tl.describe(host, float(f)).encode()).hexdigest() for f in range(frames)]
         assert [d for _, d in flat] == single
-        # every rank's 24-frame bench window holds the same mix of plain and transition frames
+        # every rank's bench steps stay inside its block and hold the same 50:50 mix of plain and transition frames; its
+        # end-to-end window is consecutive frames of the block, half of them inside a transition
         sys.path.insert(0, ROOT)
         import bench
 
         cfg = dict(workloads.C5)
-        mixes = []
         for r in range(world):
-            fr = bench.frames_for(r, world, cfg, 24)
+            fr = bench.c5_frames(r, world, cfg, 24)
             lo_r, hi_r = workloads.frame_block(r, world, cfg["frames"])
             assert all(lo_r <= f < hi_r for f in fr)
-            mixes.append(sum(la[1] is not None for f in fr for la in workloads.stack_layers(f, **cfg)))
-        assert len(set(mixes)) == 1, mixes
+            inside = [workloads.stack_layers(f, **cfg)[0][1] is not None for f in fr]
+            assert inside == [False, True] * 12, inside
+            first = bench.c5_e2e_window(r, world, cfg, 20)
+            assert lo_r <= first and first + 20 <= hi_r
+            window = [workloads.stack_layers(f, **cfg)[0][1] is not None for f in range(first, first + 20)]
+            assert window == [False] * 10 + [True] * 10, window
         print("SHARDING_OK", world, flush=True)
     dist.barrier()
     dist.destroy_process_group()
