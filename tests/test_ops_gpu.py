@@ -224,8 +224,9 @@ def test_blur_constant_image(T):
 def test_resize(T, dt):
     src = rand_img(160, 90, dt, 4)
     d = to_dev(src)
-    # (33, 77), (20, 12): more than 16 taps along x -> two-pass path with the staged row pass; (5, 3): beyond that -> gathers
-    for size in [(320, 180), (80, 45), (160, 90), (200, 50), (33, 77), (20, 12), (5, 3)]:
+    # the march kernel with 1 .. 4 staged column spans ((48, 27): 125 staged columns); (33, 77), (20, 12): a footprint beyond its
+    # tile -> two-pass path with the staged row pass; (5, 3): beyond that -> gathers
+    for size in [(320, 180), (80, 45), (160, 90), (200, 50), (48, 27), (33, 77), (20, 12), (5, 3)]:
         assert_close(T.resize(d, size), O.resize(src, size), f"resize {size}")
     assert_close(T.resize(d, (100, 60), "lanczos3", 0.0), O.resize(src, (100, 60), "lanczos3", 0.0), "resize lanczos3")
     assert_close(T.resize(d, (300, 200), "blackman-harris", 0.0), O.resize(src, (300, 200), "blackman-harris", 0.0), "resize bh")

@@ -193,3 +193,68 @@ def test_gap_strip_with_the_png_exports_standing_in_for_svg():
     # no SVG rasteriser here; the shipped Letter_*.png are Inkscape exports of the same drawings at the same size and stand in
     # (tests/media.py), which exercises the Gap -> transparent Fill -> over logic against the reference's render.
     check(errors("Gap"), what="Gap")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ... and the PRODUCT against the same pixels: the CUDA path (C++ host -> OpenFX modules -> kernels) renders the fixtures, the
+# frames are reduced with the same `resize` and compared with the reference's tiles.  Stale strips are rendered from the fixture
+# with the stated parameters put back (a modified .otio document), so every tile is a direct product-vs-reference comparison.
+def _with_params(doc, params):
+    """The fixture with effect parameters replaced: {effect_name: {key: value}}."""
+    if isinstance(doc, dict):
+        out = {k: _with_params(v, params) for k, v in doc.items()}
+        name = doc.get("effect_name")
+        if name in params and isinstance(out.get("metadata"), dict):
+            out["metadata"] = dict(out["metadata"], **params[name])
+        return out
+    if isinstance(doc, list):
+        return [_with_params(v, params) for v in doc]
+    return doc
+
+
+GPU_CASES = [
+    ("Generator", {}, False, None), ("ColorSpace", {}, False, None), ("CompositeTracks", {}, False, None), ("Gap", {}, False, None),
+    ("Filter", {"toucan:Blur": {"radius": 30.0}, "toucan:UnsharpMask": {"width": 30.0}}, False, None),
+    ("MultipleEffects", {"toucan:Pow": {"value": 2.0}, "toucan:Blur": {"radius": 30.0}}, False, None),
+    ("Transition", {}, True, None), ("Transition2", {}, True, None), ("TransitionWipe", {}, True, None),
+    ("Transform", {}, False, {2, 3, 4, 5, 8, 9}),      # Flip, Flop, Rotate (Crop / Resize tiles predate CompNode's fit)
+    ("LinearTimeWarp", {}, False, {0, 1, 2, 3, 5, 7, 9}),  # the tiles today's rounding time warp reproduces
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,params,unassociated,tiles", GPU_CASES, ids=[c[0] for c in GPU_CASES])
+def test_cuda_path_matches_the_reference_strips(cuda, name, params, unassociated, tiles):
+    import json
+
+    from toucan_b200 import render
+
+    render.bind_device(0)
+    host = render.Host()
+    doc = _with_params(json.load(open(os.path.join(TL.DATA, name + ".otio"))), params)
+    decode = media.decode_unassociated if unassociated else media.decode
+    tl = render.Timeline(json_doc=doc, directory=TL.DATA)
+    for f in sorted(os.listdir(TL.DATA)):
+        if f.lower().endswith((".png", ".jpg")):
+            frame = decode(os.path.join(TL.DATA, f))
+            if frame is not None:
+                tl.set_media(os.path.join(TL.DATA, f), frame)
+    for f in TL.SVG_STAND_INS:
+        frame = media.decode(os.path.join(TL.DATA, f))
+        if frame is not None:
+            tl.set_media(os.path.join(TL.DATA, f), frame)
+    tl.prepare()
+    info = tl.info()
+    strip = strip_tiles(name)
+    assert info["frames"] == len(strip)
+    memo = {}
+    for i, tile in enumerate(strip):
+        if tiles is not None and i not in tiles:
+            continue
+        got = tl.render(host, info["start"] + i, max_bytes=1280 * 720 * 16)
+        key = got.tobytes()
+        if key not in memo:
+            memo[key] = np.clip(O.resize(O.convert(got, O.F32), (TILE_W, TILE_H)), 0.0, 1.0)
+        d = np.abs(memo[key] - tile)[2:-2, 2:-2] * 255.0
+        assert d.mean() <= MEAN_BAR and d.max() <= MAX_BAR, f"{name} tile {i}: mean {d.mean():.2f} max {d.max():.1f} (/255)"
+    tl.close()

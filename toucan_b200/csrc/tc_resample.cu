@@ -12,11 +12,14 @@
 // Compiled with -fmad=false so the per-tap arithmetic follows the reference's unfused
 // float sequence; lanczos3 uses OIIO's fast_sinpi polynomial (max abs error 9.2e-4), NOT
 // sinpif -- the difference is far above the 1e-5 tolerance.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "tc_common.cuh"
 #include "tc_tile.cuh"
@@ -153,132 +156,8 @@ __global__ void __launch_bounds__(256) k_resize_cols(const float4* __restrict__ 
     store_px(dst.p, dst.type, (size_t)y * dst.w + x, pel);
 }
 
-// The same two passes fused through shared memory (the north-star layout for Resize: a filtered-resample
-// gather through a shared-memory tile).  A CTA owns a 32 x th block of the destination (th chosen so the
-// block's source footprint is at most 32 rows): it stages the footprint once (clamped, converted to float),
-// runs the row pass into a second, transposed shared tile and the column pass from there -- same weights,
-// same accumulation order as the two kernels above, so the results are identical to theirs; the float
-// scratch image and its HBM round trip are gone.
-//   row pass:    lane = source row, warp = destination column.  Row strides are odd multiples of 16 bytes,
-//                so the 32 rows of one column are bank-conflict free whatever the resize ratio, and the
-//                column's weights are warp-uniform (a zero weight -- which the reference skips -- is a
-//                uniform branch, not a per-lane select);
-//   column pass: lane = destination column, warp = destination row; again uniform weights.
-constexpr int RT_W = 32, RT_ROWS = 32, RT_MH = 33, RT_MAXT = 16, RT_THREADS = 512, RT_MAXH = 32;
-
-struct ResizeTile {
-    int sw;       // shared source tile columns (allocation)
-    int th;       // destination rows per CTA
-    int xtaps, ytaps;
-};
-
-static size_t resize_tile_smem(int sw)
-{
-    return ((size_t)RT_ROWS * (sw | 1) + (size_t)RT_W * RT_MH) * sizeof(float4) + ((size_t)RT_W * RT_MAXT + (size_t)RT_MAXH * RT_MAXT) * sizeof(float) +
-           (RT_W + RT_MAXH) * sizeof(int);
-}
-
-template <int TYPE>
-__global__ void __launch_bounds__(RT_THREADS) k_resize_tile(const Img src_, const Img dst, const int* __restrict__ xf, const float* __restrict__ xw,
-                                                             const float* __restrict__ xt, const int* __restrict__ yf,
-                                                             const float* __restrict__ yw, const float* __restrict__ yt, const ResizeTile T)
-{
-    extern __shared__ float4 rt_smem[];
-    const Img src { src_.p, src_.w, src_.h, TYPE }; // storage type known at compile time: one load path
-    const int swp = T.sw | 1;
-    float4* S = rt_smem;                                 // [RT_ROWS][swp]
-    float4* Mt = S + (size_t)RT_ROWS * swp;              // [RT_W][RT_MH]: row-pass results, transposed
-    float* wxs = reinterpret_cast<float*>(Mt + RT_W * RT_MH); // [RT_W][RT_MAXT]
-    float* wys = wxs + RT_W * RT_MAXT;                   // [RT_MAXH][RT_MAXT]
-    int* fxs = reinterpret_cast<int*>(wys + RT_MAXH * RT_MAXT); // [RT_W]  first tap, relative to the tile
-    int* fys = fxs + RT_W;                               // [RT_MAXH]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * T.th;
-    const int nx = min(RT_W, dst.w - x0), ny = min(T.th, dst.h - y0);
-    const int fx0 = xf[x0], fy0 = yf[y0];
-    const int cols = min(xf[x0 + nx - 1] + T.xtaps - fx0, T.sw);
-    const int rows = min(yf[y0 + ny - 1] + T.ytaps - fy0, RT_ROWS);
-    // stage the footprint: a warp per source row (coalesced along the row), edge-clamped like the per-tap clamp of
-    // the two-pass kernels.  Every load of the thread (32 / warps rows x 3 spans cover 32 rows x 96 columns) is issued before
-    // anything waits on one, and the weight tables are fetched while those loads are in flight.
-    constexpr int WARPS = RT_THREADS / 32;
-    constexpr int KR = RT_ROWS / WARPS, KT = RT_W * RT_MAXT / RT_THREADS;
-    float4 v[KR][3];
-#pragma unroll
-    for (int k = 0; k < KR; ++k) {
-        const size_t rbase = (size_t)min(max(fy0 + min(warp + k * WARPS, rows - 1), 0), src.h - 1) * src.w;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int sx = min(max(fx0 + min(q * 32 + lane, cols - 1), 0), src.w - 1);
-            v[k][q] = load_px(src.p, TYPE, rbase + sx);
-        }
-    }
-    // per-axis tables of this block; a column / row whose weights do not sum (zero total) produces 0
-    float wv[KT], hv[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const int i = tid + k * RT_THREADS;
-        const int x = i / RT_MAXT, t = i - x * RT_MAXT; // also the (row, tap) split of the y table
-        wv[k] = (t < T.xtaps && x < nx && xt[(x0 + x) * 2 + 1] != 0.0f) ? xw[(size_t)(x0 + x) * T.xtaps + t] : 0.0f;
-        hv[k] = (t < T.ytaps && x < ny && yt[(y0 + x) * 2 + 0] != 0.0f) ? yw[(size_t)(y0 + x) * T.ytaps + t] : 0.0f;
-    }
-    int first = 0;
-    if (tid < RT_W) first = min(xf[min(x0 + tid, dst.w - 1)] - fx0, T.sw - T.xtaps);
-    else if (tid < RT_W + RT_MAXH) first = min(yf[min(y0 + tid - RT_W, dst.h - 1)] - fy0, RT_ROWS - T.ytaps);
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        wxs[tid + k * RT_THREADS] = wv[k];
-        wys[tid + k * RT_THREADS] = hv[k];
-    }
-    if (tid < RT_W + RT_MAXH) fxs[tid] = first; // fys follows fxs
-#pragma unroll
-    for (int k = 0; k < KR; ++k) {
-        const int r = warp + k * WARPS;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int c = q * 32 + lane;
-            if (r < rows && c < cols) S[(size_t)r * swp + c] = v[k][q];
-        }
-    }
-    // wider footprints (a resize ratio above ~2.5 along x): the remaining columns, one span at a time
-    for (int c = 96 + lane; c < cols; c += 32) {
-        const int sx = min(max(fx0 + c, 0), src.w - 1);
-        for (int r = warp; r < rows; r += WARPS) S[(size_t)r * swp + c] = load_px(src.p, TYPE, (size_t)min(max(fy0 + r, 0), src.h - 1) * src.w + sx);
-    }
-    __syncthreads();
-    // row pass: Mt(x, r) = sum_i wx_i(x) * S(r, fx(x) + i)
-    {
-        const float4* row = S + (size_t)min(lane, rows - 1) * swp;
-        for (int x = warp; x < RT_W; x += WARPS) {
-            const float4* p = row + fxs[x];
-            const float* w = wxs + x * RT_MAXT;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int t = 0; t < T.xtaps; ++t) {
-                const float wt = w[t];
-                if (wt != 0.0f) acc = fma4p(wt, p[t], acc);
-            }
-            Mt[x * RT_MH + lane] = acc;
-        }
-    }
-    __syncthreads();
-    // column pass: dst(x, y) = sum_j wy_j(y) * Mt(x, fy(y) + j)
-    for (int y = warp; y < ny; y += WARPS) {
-        const float4* p = Mt + lane * RT_MH + fys[y];
-        const float* w = wys + y * RT_MAXT;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int t = 0; t < T.ytaps; ++t) {
-            const float wt = w[t];
-            if (wt != 0.0f) acc = fma4p(wt, p[t], acc);
-        }
-        if (lane < nx) store_px(dst.p, dst.type, (size_t)(y0 + y) * dst.w + x0 + lane, acc);
-    }
-}
-
-// Row pass of the two-pass path through the same kind of shared tile, for footprints the fused kernel cannot hold (more
-// than 16 taps per axis: reductions below ~0.4).  A CTA owns 32 source rows x `xw` destination columns; the rows' common
+// Row pass of the two-pass path through the same kind of shared tile, for footprints the march cannot hold (more
+// than 32 taps per axis or 128 staged columns: reductions below ~0.3).  A CTA owns 32 source rows x `xw` destination columns; the rows' common
 // source span is staged once (coalesced), then lane = row, warp = destination column, weights warp-uniform -- instead of
 // every thread gathering its `taps` source pixels with a stride of 1/ratio pixels through L1.
 constexpr int RR_ROWS = 32, RR_THREADS = 256;
@@ -340,6 +219,292 @@ __global__ void __launch_bounds__(RR_THREADS) k_resize_rows_tile(const Img src_,
             if (wt != 0.0f) acc = fma4p(wt, p[t], acc);
         }
         if (lane < ny) tmp[(size_t)(y0 + lane) * dw + x0 + x] = acc;
+    }
+}
+
+// The two passes fused as a MARCH down the frame (the north-star layout for Resize: a filtered-resample gather through
+// shared-memory tiles; round 1's 32 x 10 output tile re-staged every source row ~3 times at 1/2).  A CTA owns a strip of 32 destination columns and a chunk of
+// destination rows and walks its source rows in bands of 32:
+//   stage    the band's source span (32 rows x the strip's footprint columns, edge-clamped, float) -- each source row
+//            is staged ONCE per strip (plus ytaps warm-up rows per chunk);
+//   row pass lane = source row (odd 16-byte row pitch: conflict-free), warp = a block of 4 destination columns whose
+//            common source span is read once: 4 outputs from span = 3 steps + taps reads (19-20 at 1/2 instead of 52).
+//            The per-block weights are expanded to a span x 4 matrix in shared memory once per CTA (zero where a source
+//            pixel is outside an output's window), so the loop has no per-tap index arithmetic: one 128-bit pixel read,
+//            one broadcast 128-bit weight read, 8 FFMA2.  Results go into a ring of 64 row slots, Mt[column][slot];
+//   column pass lane = destination column (pitch 65: conflict-free), warp = a block of 4 destination rows, same scheme
+//            with the weights expanded per block by the warp; runs for every destination row whose window is complete.
+// Same weights and the same ascending-tap fused accumulation as k_resize_rows / k_resize_cols, so frames are identical
+// to theirs for finite pixels (the expanded matrix adds exact zeros).
+constexpr int RM_W = 32, RM_BAND = 32, RM_RING = 64, RM_MP = RM_RING + 1, RM_THREADS = 256, RM_B = 4, RM_SPAN = 48;
+constexpr int RM_WARPS = RM_THREADS / 32, RM_XBLK = RM_W / RM_B, RM_MAXBANDS = RM_THREADS;
+
+struct ResizeMarch {
+    int sw;       // staged columns (allocation)
+    int ch;       // destination rows per chunk
+    int xtaps, ytaps;
+};
+
+static size_t resize_march_smem(int sw)
+{
+    return ((size_t)RM_BAND * (sw | 1) + (size_t)RM_W * RM_MP + (size_t)(RM_XBLK + RM_WARPS) * RM_SPAN) * sizeof(float4);
+}
+
+// a pixel as stored (1 / 2 / 2 / 4 registers), converted when it is written to the staged tile
+template <int TYPE> struct RawPx { typedef float4 type; };
+template <> struct RawPx<TC_U8> { typedef unsigned type; };
+template <> struct RawPx<TC_U16> { typedef uint2 type; };
+template <> struct RawPx<TC_F16> { typedef uint2 type; };
+// streaming loads that do not allocate in L1: the staged pixels pass through once, the small per-axis tables stay cached
+__device__ __forceinline__ float4 ld_stream(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_stream(const uint2* p)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned ld_stream(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <int TYPE>
+__device__ __forceinline__ typename RawPx<TYPE>::type load_raw(const void* __restrict__ base, size_t i)
+{
+    return ld_stream(reinterpret_cast<const typename RawPx<TYPE>::type*>(base) + i);
+}
+__device__ __forceinline__ float4 raw_px(float4 v, int) { return v; }
+__device__ __forceinline__ float4 raw_px(unsigned v, int)
+{
+    return make_float4(u8_to_f(v & 255u), u8_to_f((v >> 8) & 255u), u8_to_f((v >> 16) & 255u), u8_to_f(v >> 24));
+}
+__device__ __forceinline__ float4 raw_px(uint2 v, int type)
+{
+    if (type == TC_U16) return make_float4(u16_to_f(v.x & 65535u), u16_to_f(v.x >> 16), u16_to_f(v.y & 65535u), u16_to_f(v.y >> 16));
+    const float2 fa = __half22float2(*reinterpret_cast<__half2*>(&v.x)), fb = __half22float2(*reinterpret_cast<__half2*>(&v.y));
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// The y tables of a block of BR destination rows, fetched with INDEPENDENT loads (one level of memory latency instead of
+// first tap -> weight address -> weight): the rows' first taps and totals on lanes 0 .. BR - 1, the rows' BR x ytaps weights
+// (contiguous in the table) spread over the lanes.  The expanded span x BR matrix is then scattered into shared memory.
+template <int BR>
+struct ColTab {
+    int f;
+    float tot;
+    float w[BR];
+};
+template <int BR>
+__device__ __forceinline__ void march_tab_load(ColTab<BR>& t, const int* __restrict__ yf, const float* __restrict__ yw,
+                                               const float* __restrict__ yt, int ytaps, int yb, int yend)
+{
+    const int lane = threadIdx.x & 31;
+    const int rows = min(BR, yend - yb);
+    t.f = 0;
+    t.tot = 0.0f;
+    if (lane < rows) {
+        t.f = yf[yb + lane];
+        t.tot = yt[(yb + lane) * 2 + 0];
+    }
+    const float* w = yw + (size_t)yb * ytaps;
+#pragma unroll
+    for (int j = 0; j < BR; ++j) {
+        const int i = lane + 32 * j;
+        t.w[j] = i < rows * ytaps ? w[i] : 0.0f;
+    }
+}
+
+template <int BR>
+__device__ __forceinline__ void march_cols(ColTab<BR> t, const Img& dst, const float4* Mt, float4* wy, const int* __restrict__ yf,
+                                           const float* __restrict__ yw, const float* __restrict__ yt, int ytaps, int ycur, int yend, int r0,
+                                           int x0, int nx)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int yb = ycur + warp * BR; yb < yend; yb += RM_WARPS * BR) {
+        const int rows = min(BR, yend - yb);
+        const int fb = __shfl_sync(0xffffffffu, t.f, 0);
+        const int span = min(__shfl_sync(0xffffffffu, t.f, rows - 1) + ytaps - fb, RM_SPAN);
+        for (int k = lane; k < span; k += 32) wy[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < BR; ++j) {
+            const int i = lane + 32 * j;
+            int o = 0;
+#pragma unroll
+            for (int q = 1; q < BR; ++q) o += i >= q * ytaps ? 1 : 0;
+            const int k = i - o * ytaps + __shfl_sync(0xffffffffu, t.f, o) - fb;
+            const float tot = __shfl_sync(0xffffffffu, t.tot, o);
+            if (i < rows * ytaps && tot != 0.0f && k < span) reinterpret_cast<float*>(wy + k)[o] = t.w[j];
+        }
+        __syncwarp();
+        // the next block's tables travel while this block is filtered
+        const int ybn = yb + RM_WARPS * BR;
+        if (ybn < yend) march_tab_load<BR>(t, yf, yw, yt, ytaps, ybn, yend);
+        const float4* col = Mt + lane * RM_MP;
+        const int s0 = fb - r0;
+        float4 acc[BR];
+#pragma unroll
+        for (int o = 0; o < BR; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int k = 0; k < span; ++k) {
+            const float4 q = col[(s0 + k) & (RM_RING - 1)];
+            const float4 wk = wy[k];
+            acc[0] = fma4p(wk.x, q, acc[0]);
+            acc[1] = fma4p(wk.y, q, acc[1]);
+            if constexpr (BR > 2) {
+                acc[2] = fma4p(wk.z, q, acc[2]);
+                acc[3] = fma4p(wk.w, q, acc[3]);
+            }
+        }
+        if (lane < nx) {
+#pragma unroll
+            for (int o = 0; o < BR; ++o)
+                if (o < rows) store_px(dst.p, dst.type, (size_t)(yb + o) * dst.w + x0 + lane, acc[o]);
+        }
+        __syncwarp();
+    }
+}
+
+// CS = 32-column spans of the staged tile (cols <= 32 CS).  The loads of band n + 1 are issued into registers (in the
+// storage type) right after band n has been written to the tile, and land while band n runs through both passes.
+template <int TYPE, int CS>
+__global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, const Img dst, const int* __restrict__ xf,
+                                                                 const float* __restrict__ xw, const float* __restrict__ xt,
+                                                                 const int* __restrict__ yf, const float* __restrict__ yw,
+                                                                 const float* __restrict__ yt, const ResizeMarch T)
+{
+    extern __shared__ float4 rm_smem[];
+    __shared__ int s_fxb[RM_XBLK], s_span[RM_XBLK], s_yend[RM_MAXBANDS], s_wsum[RM_WARPS];
+    const Img src { src_.p, src_.w, src_.h, TYPE };
+    const int swp = T.sw | 1;
+    float4* S = rm_smem;                            // [RM_BAND][swp]
+    float4* Mt = S + (size_t)RM_BAND * swp;         // [RM_W][RM_MP]: row-pass results, ring of source rows
+    float4* Wx = Mt + RM_W * RM_MP;                 // [RM_XBLK][RM_SPAN]: expanded x weights of the strip's column blocks
+    float4* Wy = Wx + RM_XBLK * RM_SPAN;            // [RM_WARPS][RM_SPAN]: a warp's expanded y weights of its current row block
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * RM_W, y0 = blockIdx.y * T.ch;
+    const int nx = min(RM_W, dst.w - x0), y1 = min(y0 + T.ch, dst.h);
+    const int fx0 = xf[x0];
+    const int cols = min(min(xf[x0 + nx - 1] + T.xtaps - fx0, T.sw), 32 * CS);
+    const int r0 = yf[y0];                          // first source row of the chunk (may lie above the frame: clamped when staged)
+    const int rlast = yf[y1 - 1] + T.ytaps;         // one past the last source row the chunk needs
+
+    constexpr int RPW = RM_BAND / RM_WARPS;         // rows per warp and band
+    typename RawPx<TYPE>::type v[RPW][CS];
+    int sx[CS];
+#pragma unroll
+    for (int q = 0; q < CS; ++q) sx[q] = min(max(fx0 + min(q * 32 + lane, cols - 1), 0), src.w - 1);
+    auto issue = [&](int band0) {
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const size_t g = (size_t)min(max(band0 + warp + rr * RM_WARPS, 0), src.h - 1) * src.w;
+#pragma unroll
+            for (int q = 0; q < CS; ++q) v[rr][q] = load_raw<TYPE>(src.p, g + sx[q]);
+        }
+    };
+    issue(r0);
+
+    // expanded x weights: Wx[b][k] = weights of staged column fxb[b] + k for the block's four outputs
+    for (int i = tid; i < RM_XBLK * RM_SPAN; i += RM_THREADS) {
+        const int b = i / RM_SPAN, k = i - b * RM_SPAN;
+        float w[RM_B] = { 0.f, 0.f, 0.f, 0.f };
+        if (b * RM_B < nx) {
+            const int fb = xf[x0 + b * RM_B];
+#pragma unroll
+            for (int o = 0; o < RM_B; ++o) {
+                const int x = x0 + b * RM_B + o;
+                if (x < dst.w) {
+                    const int t = k - (xf[x] - fb);
+                    if (t >= 0 && t < T.xtaps && xt[x * 2 + 1] != 0.0f) w[o] = xw[(size_t)x * T.xtaps + t];
+                }
+            }
+        }
+        Wx[i] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    if (tid < RM_XBLK) {
+        const int xa = min(x0 + tid * RM_B, dst.w - 1), xb = min(x0 + tid * RM_B + RM_B - 1, dst.w - 1);
+        const int fb = min(xf[xa] - fx0, max(cols - 1, 0));
+        s_fxb[tid] = fb;
+        s_span[tid] = max(min(min(xf[xb] + T.xtaps - xf[xa], RM_SPAN), cols - fb), 0);
+    }
+
+    // destination rows complete after each band (yf is non-decreasing): counted once per CTA, so the walk below has no
+    // dependent table look-ups in front of the column pass
+    {
+        const int nb = min((rlast - r0 + RM_BAND - 1) / RM_BAND, RM_MAXBANDS);
+        s_yend[tid] = 0;
+        __syncthreads();
+        for (int y = y0 + tid; y < y1; y += RM_THREADS) atomicAdd(&s_yend[min((yf[y] + T.ytaps - r0 + RM_BAND - 1) / RM_BAND - 1, nb - 1)], 1);
+        __syncthreads();
+        int vsum = s_yend[tid];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, vsum, d);
+            if (lane >= d) vsum += u;
+        }
+        if (lane == 31) s_wsum[warp] = vsum;
+        __syncthreads();
+        for (int q = 0; q < warp; ++q) vsum += s_wsum[q];
+        s_yend[tid] = y0 + vsum;
+    }
+
+    int hi = r0; // source rows below `hi` have been through the row pass
+    int ycur = y0;
+    for (int band = 0; ycur < y1; ++band) {
+        // ---- the band's pixels into the tile; then the next band's loads
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+            for (int q = 0; q < CS; ++q) {
+                const int c = q * 32 + lane;
+                if (c < cols) S[(size_t)(warp + rr * RM_WARPS) * swp + c] = raw_px(v[rr][q], TYPE);
+            }
+        __syncthreads();
+        if (hi + RM_BAND < rlast) issue(hi + RM_BAND);
+        const int yend = s_yend[min(band, RM_MAXBANDS - 1)];
+        auto run = [&](auto brc) {
+            constexpr int BR = decltype(brc)::value;
+            // the tables of the warp's first block of destination rows travel during the row pass
+            ColTab<BR> tab;
+            tab.f = 0;
+            tab.tot = 0.0f;
+            if (ycur + warp * BR < yend) march_tab_load<BR>(tab, yf, yw, yt, T.ytaps, ycur + warp * BR, yend);
+            // ---- row pass of the band into the ring
+            if (warp * RM_B < nx) {
+                const float4* row = S + (size_t)lane * swp + s_fxb[warp];
+                const float4* w = Wx + warp * RM_SPAN;
+                const int span = s_span[warp];
+                float4 acc[RM_B];
+#pragma unroll
+                for (int o = 0; o < RM_B; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int k = 0; k < span; ++k) {
+                    const float4 q = row[k];
+                    const float4 wk = w[k];
+                    acc[0] = fma4p(wk.x, q, acc[0]);
+                    acc[1] = fma4p(wk.y, q, acc[1]);
+                    acc[2] = fma4p(wk.z, q, acc[2]);
+                    acc[3] = fma4p(wk.w, q, acc[3]);
+                }
+                const int slot = (hi - r0 + lane) & (RM_RING - 1);
+#pragma unroll
+                for (int o = 0; o < RM_B; ++o) Mt[(warp * RM_B + o) * RM_MP + slot] = acc[o];
+            }
+            __syncthreads();
+            // ---- column pass over the destination rows whose window is now complete: a warp per block of BR rows
+            march_cols<BR>(tab, dst, Mt, Wy + warp * RM_SPAN, yf, yw, yt, T.ytaps, ycur, yend, r0, x0, nx);
+        };
+        // 2 rows per block when the band completes at most 16 rows, so that every warp has a block
+        if (yend - ycur <= 2 * RM_WARPS) run(std::integral_constant<int, 2>());
+        else run(std::integral_constant<int, RM_B>());
+        hi += RM_BAND;
+        ycur = yend;
     }
 }
 
@@ -629,21 +794,20 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
     if (ax.taps > 4096 || ay.taps > 4096) return fail(TC_ERR_UNSUPPORTED, "tc_resize: %d x %d taps", ax.taps, ay.taps);
 
     cudaStream_t st = (cudaStream_t)s;
-    // shared-memory tile path: taps fit the unrolled loops and some block height keeps the footprint within 32 rows
-    ResizeTile T;
-    T.xtaps = ax.taps;
-    T.ytaps = ay.taps;
-    T.sw = (int)ceilf((float)(RT_W - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
-    T.th = 0;
-    for (int th = RT_MAXH; th >= 4 && !T.th; --th)
-        if ((int)ceilf((float)(th - 1) * (float)src->h / (float)dst->h) + ay.taps + 1 <= RT_ROWS) T.th = th;
-    const size_t tile_smem = resize_tile_smem(T.sw);
-    const bool tiled = T.th > 0 && ax.taps <= RT_MAXT && ay.taps <= RT_MAXT && tile_smem <= 100 * 1024;
+    // the march: both tap counts within a band, block spans within the expanded-weight tables, tile within shared memory
+    ResizeMarch M;
+    M.xtaps = ax.taps;
+    M.ytaps = ay.taps;
+    M.sw = (int)ceilf((float)(RM_W - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
+    const int span_x = (int)ceilf((float)(RM_B - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
+    const int span_y = (int)ceilf((float)(RM_B - 1) * (float)src->h / (float)dst->h) + ay.taps + 1;
+    const size_t march_smem = resize_march_smem(M.sw);
+    const bool march = ax.taps <= RM_BAND && ay.taps <= RM_BAND && span_x <= RM_SPAN && span_y <= RM_SPAN && M.sw <= 128 && march_smem <= 99 * 1024;
     // per-axis tables: cached per geometry; built in the call's scratch only if the cache is full
     AxisTable tx, ty;
     const bool cached = axis_table(ax, st, tx) == TC_OK && axis_table(ay, st, ty) == TC_OK;
     // scratch: [tmp (dw x sh float4, two-pass path only) | xf | yf | xtot | ytot | xw | yw (uncached tables only)]
-    const size_t n_tmp = tiled ? 0 : (size_t)dst->w * src->h * 4;
+    const size_t n_tmp = march ? 0 : (size_t)dst->w * src->h * 4;
     const size_t n_int = cached ? 0 : (size_t)dst->w + dst->h;
     const size_t n_tot = cached ? 0 : 2 * ((size_t)dst->w + dst->h);
     const size_t n_w = cached ? 0 : (size_t)dst->w * ax.taps + (size_t)dst->h * ay.taps;
@@ -664,21 +828,36 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
         k_resize_axis<<<(dst->h + 127) / 128, 128, 0, st>>>(ay, yf, yw, yt);
         count_launch(2);
     }
-    if (tiled) {
-        const dim3 grid((dst->w + RT_W - 1) / RT_W, (dst->h + T.th - 1) / T.th);
+    if (march) {
+        // chunks of destination rows: one wave of two CTAs per SM, warm-up rows (ytaps per chunk) kept below ~1/8 of a chunk
+        const int strips = (dst->w + RM_W - 1) / RM_W;
+        int chunks = std::max(1, 2 * num_sms() / strips);
+        chunks = std::min(chunks, std::max(1, src->h / (8 * ay.taps)));
+        chunks = std::max(1, std::min(chunks, dst->h));
+        M.ch = (dst->h + chunks - 1) / chunks;
+        // a chunk walks at most RM_MAXBANDS bands of source rows
+        const int max_rows = std::max(1, (int)((double)(RM_BAND * (RM_MAXBANDS - 2) - ay.taps) * dst->h / src->h));
+        M.ch = std::min(M.ch, max_rows);
+        const dim3 grid(strips, (dst->h + M.ch - 1) / M.ch);
         int e = TC_OK;
-#define TC_RT(TY)                                                                                                                  \
+#define TC_RM2(TY, CS)                                                                                                             \
+    e = ensure_dynamic_smem((const void*)k_resize_march<TY, CS>, march_smem);                                                      \
+    if (e == TC_OK) k_resize_march<TY, CS><<<grid, RM_THREADS, march_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, M);
+#define TC_RM(TY)                                                                                                                  \
     case TY:                                                                                                                       \
-        e = ensure_dynamic_smem((const void*)k_resize_tile<TY>, tile_smem);                                                        \
-        if (e == TC_OK) k_resize_tile<TY><<<grid, RT_THREADS, tile_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, T);   \
+        if (M.sw <= 32) { TC_RM2(TY, 1) }                                                                                          \
+        else if (M.sw <= 64) { TC_RM2(TY, 2) }                                                                                     \
+        else if (M.sw <= 96) { TC_RM2(TY, 3) }                                                                                     \
+        else { TC_RM2(TY, 4) }                                                                                                     \
         break;
         switch (src->type) {
-            TC_RT(TC_U8)
-            TC_RT(TC_U16)
-            TC_RT(TC_F16)
-            TC_RT(TC_F32)
+            TC_RM(TC_U8)
+            TC_RM(TC_U16)
+            TC_RM(TC_F16)
+            TC_RM(TC_F32)
         }
-#undef TC_RT
+#undef TC_RM2
+#undef TC_RM
         if (e != TC_OK) {
             if (scratch) cudaFreeAsync(scratch, st);
             return e;
