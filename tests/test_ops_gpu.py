@@ -123,6 +123,14 @@ def test_noise_bit_exact(T, ntype, a, b, mono, seed):
     assert_exact(T.noise(333, 217, ntype, a, b, mono, seed, t), O.noise(333, 217, ntype, a, b, mono, seed, t), f"noise {ntype} f32")
 
 
+def test_noise_gaussian_bit_exact_over_a_large_sample(T):
+    # 2 x 1920 x 1080 x 4 = 16.6 M float samples: the kernel's Newton / fused-multiply-add evaluation of sqrt(-2 ln r / r) with its
+    # exact-chain decision near float rounding boundaries (tests/cpp/noise_fastpath_check.c) against the oracle's IEEE double chain
+    for seed in (1, 2026):
+        assert_exact(T.noise(1920, 1080, "gaussian", 0.5, 0.25, False, seed, O.F32), O.noise(1920, 1080, "gaussian", 0.5, 0.25, False, seed, O.F32),
+                     f"noise gaussian f32 seed {seed}")
+
+
 @pytest.mark.parametrize("dt", NP_TYPES)
 @pytest.mark.parametrize("size", SIZES)
 def test_exact_unary(T, dt, size):

@@ -196,3 +196,20 @@ def test_colour_matrices_against_published_aces_values():
     out = O.colorconvert(img, "ACEScg", "ACEScct")
     assert abs(float(out[0, 0, 0]) - 0.4135884) < 1e-5
     assert abs(float(out[0, 1, 0]) - (10.5402377416545 * 0.0078125 + 0.0729055341958355)) < 1e-6
+
+
+def test_noise_fast_path_stays_within_its_decision_band(tmp_path):
+    """tests/cpp/noise_fastpath_check.c: the seeded Noise kernel evaluates sqrt(-2 ln r / r) with Newton-refined SFU seeds and
+    fused multiply-adds and hands over to the exact IEEE chain within 1024 double ulps of a float rounding boundary; the C
+    restatement of that fast path must stay within a few ulps of the oracle's chain (full sweep of all 3.2e8 float r: 2 ulps;
+    here every 61st value)."""
+    import subprocess
+
+    O.build()
+    here = os.path.dirname(os.path.abspath(__file__))
+    build = os.path.join(os.path.dirname(here), "oracle", "_build")
+    exe = str(tmp_path / "noise_fastpath_check")
+    subprocess.run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", os.path.join(here, "cpp", "noise_fastpath_check.c"), "-o", exe,
+                    "-L", build, "-loracle", "-lm", f"-Wl,-rpath,{build}"], check=True, capture_output=True)
+    out = subprocess.run([exe, "61"], check=True, capture_output=True, text=True).stdout
+    assert int(out.split("max_ulps")[1]) <= 8, out

@@ -290,22 +290,90 @@ __device__ double det_log(double x)
     if (k == 0) return __dsub_rn(f, __dmul_rn(s, __dsub_rn(f, R)));
     return __dsub_rn(__dmul_rn(dk, ln2_hi), __dsub_rn(__dsub_rn(__dmul_rn(s, __dsub_rn(f, R)), __dmul_rn(dk, ln2_lo)), f));
 }
-// Marsaglia polar method on the position hash.
-__device__ float hashnormal(uint32_t xy, int c, int seed)
+// sqrt(-2 ln(x) / x) for x in (0, 1], FP64 with fused multiply-adds and Newton-refined SFU seeds (see hashnormal): the same
+// fdlibm decomposition as det_log, the quotient f / (2 + f) through a refined reciprocal.
+__device__ __forceinline__ double fast_rcp_d(double b)
 {
-    float xr, yr, r2;
-    int s = seed - 1;
-    do {
-        s++;
+    double r = (double)rcp_approx((float)b);
+    r = fma(r, fma(-b, r, 1.0), r);
+    r = fma(r, fma(-b, r, 1.0), r);
+    return r;
+}
+__device__ __forceinline__ double fast_noise_scale(double x0)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                 Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    int hx = __double2hiint(x0);
+    const int lx = __double2loint(x0);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;
+    const double x = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
+    k += (i >> 20);
+    const double f = x - 1.0, dk = (double)k;
+    const double s = f * fast_rcp_d(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
+    const double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    // ln(x0) = k ln2 + f - (hfsq - s (hfsq + R)), the low parts first
+    const double L = fma(dk, ln2_hi, -((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f));
+    const double q = (-2.0 * L) * fast_rcp_d(x0);
+    double y = (double)rsqrt_approx((float)q);
+    y = y * fma(-0.5 * q * y, y, 1.5);
+    y = y * fma(-0.5 * q * y, y, 1.5);
+    const double m = q * y;
+    return fma(fma(-m, m, q), 0.5 * y, m);
+}
+// Marsaglia polar method on the position hash: candidates (s, s + 139), s = seed, seed + 1, ... until one lies inside the unit
+// circle.  marsaglia_scale finishes an accepted candidate.
+__device__ __forceinline__ float marsaglia_scale(float xr, float r2)
+{
+    // M = (float)sqrt(-2 log(r2) / r2), every step an IEEE double operation in the reference.  Only the FLOAT M is used, so
+    // the double chain is evaluated with reciprocal / rsqrt seeds + Newton steps and fused multiply-adds (~50 FP64
+    // instructions instead of ~180: IEEE division twice, sqrt and the unfused log); its result is within 2 double ulps of
+    // the exact chain (tests/cpp/noise_fastpath_check.c sweeps every float r2), and whenever it lands within 1024 ulps of a float
+    // rounding boundary -- one sample in 2^18 -- or is not a positive normal, the exact chain decides.  Bit-identical to it.
+    const double r2d = (double)r2;
+    const double Mf = fast_noise_scale(r2d);
+    const unsigned low = (unsigned)__double2loint(Mf) & 0x1fffffffu; // the 29 bits below float precision
+    const unsigned dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+    float M;
+    if (dist < 1024u || !(Mf > 1.0e-30)) {
+        const double q = __ddiv_rn(__dmul_rn(-2.0, det_log(r2d)), r2d);
+        M = (float)__dsqrt_rn(q);
+    } else
+        M = (float)Mf;
+    return __fmul_rn(xr, M);
+}
+// The accepted candidates of a pixel's nc channels.  One flat loop over (channel, try) instead of a rejection loop per
+// channel: a warp runs as long as its slowest lane, and the sum of four geometric counts spreads far less than four maxima
+// (8 instead of 13.6 hash rounds per pixel on average).  The FP64 finish runs after the loop, undiverged, four chains deep.
+__device__ __forceinline__ void hashnormal4(uint32_t xy, int seed, int nc, float (&out)[4])
+{
+    float xa[4] = { 0.f, 0.f, 0.f, 0.f }, ra[4] = { 1.f, 1.f, 1.f, 1.f };
+    int c = 0, s = seed;
+    while (c < nc) {
         // (float)(2.0 * (double)h - 1.0): h is k / 2^20, so 2h - 1 has at most 21 significant bits and the float
         // evaluation is exact too (checked for all 2^20 values) -- no trip through the conversion and FP64 pipes
-        xr = __fsub_rn(__fmul_rn(2.0f, hashrand(xy, c, s)), 1.0f);
-        yr = __fsub_rn(__fmul_rn(2.0f, hashrand(xy, c, s + 139)), 1.0f);
-        r2 = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(yr, yr));
-    } while (r2 > 1.0f || r2 == 0.0f);
-    const double q = __ddiv_rn(__dmul_rn(-2.0, det_log((double)r2)), (double)r2);
-    const float M = (float)__dsqrt_rn(q);
-    return __fmul_rn(xr, M);
+        const float xr = __fsub_rn(__fmul_rn(2.0f, hashrand(xy, c, s)), 1.0f);
+        const float yr = __fsub_rn(__fmul_rn(2.0f, hashrand(xy, c, s + 139)), 1.0f);
+        const float r2 = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(yr, yr));
+        if (r2 > 1.0f || r2 == 0.0f) {
+            ++s;
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c == k) xa[k] = xr, ra[k] = r2;
+        ++c;
+        s = seed;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = k < nc ? marsaglia_scale(xa[k], ra[k]) : 0.0f;
 }
 struct NoiseOp {
     TC_OP_0()
@@ -316,10 +384,12 @@ struct NoiseOp {
         const uint32_t xy = bjfinal((uint32_t)x, (uint32_t)y, 0u);
         float p[4] = { 0.f, 0.f, 0.f, 0.f }; // the output buffer is zero-initialised (ImageEffect.cpp:93)
         float n = 0.f;
+        float g[4] = { 0.f, 0.f, 0.f, 0.f };
+        if (type == 0) hashnormal4(xy, seed, mono ? 1 : 4, g);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             if (type == 0) {
-                if (c == 0 || !mono) n = __fadd_rn(A, __fmul_rn(B, hashnormal(xy, c, seed)));
+                if (c == 0 || !mono) n = __fadd_rn(A, __fmul_rn(B, g[c]));
                 p[c] = __fadd_rn(p[c], n);
             } else if (type == 1) {
                 if (c == 0 || !mono) n = __fadd_rn(A, __fmul_rn(__fsub_rn(B, A), hashrand(xy, c, seed)));
