@@ -236,18 +236,20 @@ __global__ void __launch_bounds__(RR_THREADS) k_resize_rows_tile(const Img src_,
 //            with the weights expanded per block by the warp; runs for every destination row whose window is complete.
 // Same weights and the same ascending-tap fused accumulation as k_resize_rows / k_resize_cols, so frames are identical
 // to theirs for finite pixels (the expanded matrix adds exact zeros).
-constexpr int RM_W = 32, RM_BAND = 32, RM_RING = 64, RM_MP = RM_RING + 1, RM_THREADS = 256, RM_B = 4, RM_SPAN = 48;
+constexpr int RM_W = 32, RM_BAND = 32, RM_THREADS = 256, RM_B = 4, RM_SPAN = 48;
 constexpr int RM_WARPS = RM_THREADS / 32, RM_XBLK = RM_W / RM_B, RM_MAXBANDS = RM_THREADS;
 
 struct ResizeMarch {
     int sw;       // staged columns (allocation)
     int ch;       // destination rows per chunk
     int xtaps, ytaps;
+    int ring;     // row slots of the ring: 48 when ytaps <= 16 (a band of 32 new rows + the rows still needed), else 64
+    int wspan;    // row pitch of the expanded weight tables: the longest block span, <= RM_SPAN
 };
 
-static size_t resize_march_smem(int sw)
+static size_t resize_march_smem(int sw, int ring, int wspan)
 {
-    return ((size_t)RM_BAND * (sw | 1) + (size_t)RM_W * RM_MP + (size_t)(RM_XBLK + RM_WARPS) * RM_SPAN) * sizeof(float4);
+    return ((size_t)RM_BAND * (sw | 1) + (size_t)RM_W * (ring + 1) + (size_t)(RM_XBLK + RM_WARPS) * wspan) * sizeof(float4);
 }
 
 // a pixel as stored (1 / 2 / 2 / 4 registers), converted when it is written to the staged tile
@@ -321,7 +323,7 @@ __device__ __forceinline__ void march_tab_load(ColTab<BR>& t, const int* __restr
 }
 
 template <int BR>
-__device__ __forceinline__ void march_cols(ColTab<BR> t, const Img& dst, const float4* Mt, float4* wy, const int* __restrict__ yf,
+__device__ __forceinline__ void march_cols(ColTab<BR> t, const Img& dst, const float4* Mt, int ring, float4* wy, const int* __restrict__ yf,
                                            const float* __restrict__ yw, const float* __restrict__ yt, int ytaps, int ycur, int yend, int r0,
                                            int x0, int nx)
 {
@@ -346,14 +348,15 @@ __device__ __forceinline__ void march_cols(ColTab<BR> t, const Img& dst, const f
         // the next block's tables travel while this block is filtered
         const int ybn = yb + RM_WARPS * BR;
         if (ybn < yend) march_tab_load<BR>(t, yf, yw, yt, ytaps, ybn, yend);
-        const float4* col = Mt + lane * RM_MP;
-        const int s0 = fb - r0;
+        const float4* col = Mt + lane * (ring + 1);
+        const int s0 = (fb - r0) % ring;
         float4 acc[BR];
 #pragma unroll
         for (int o = 0; o < BR; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
         for (int k = 0; k < span; ++k) {
-            const float4 q = col[(s0 + k) & (RM_RING - 1)];
+            const int slot = s0 + k;
+            const float4 q = col[slot >= ring ? slot - ring : slot];
             const float4 wk = wy[k];
             acc[0] = fma4p(wk.x, q, acc[0]);
             acc[1] = fma4p(wk.y, q, acc[1]);
@@ -371,10 +374,11 @@ __device__ __forceinline__ void march_cols(ColTab<BR> t, const Img& dst, const f
     }
 }
 
-// CS = 32-column spans of the staged tile (cols <= 32 CS).  The loads of band n + 1 are issued into registers (in the
-// storage type) right after band n has been written to the tile, and land while band n runs through both passes.
-template <int TYPE, int CS>
-__global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, const Img dst, const int* __restrict__ xf,
+// CS = 32-column spans of the staged tile (cols <= 32 CS).  PF: the loads of band n + 1 are issued into registers (in the
+// storage type) right after band n has been written to the tile and land while band n runs through both passes -- two CTAs
+// per SM (registers); without it three CTAs per SM where the tile leaves room, which hides the same latency with more warps.
+template <int TYPE, int CS, bool PF>
+__global__ void __launch_bounds__(RM_THREADS, PF ? 2 : 3) k_resize_march(const Img src_, const Img dst, const int* __restrict__ xf,
                                                                  const float* __restrict__ xw, const float* __restrict__ xt,
                                                                  const int* __restrict__ yf, const float* __restrict__ yw,
                                                                  const float* __restrict__ yt, const ResizeMarch T)
@@ -384,9 +388,9 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, 
     const Img src { src_.p, src_.w, src_.h, TYPE };
     const int swp = T.sw | 1;
     float4* S = rm_smem;                            // [RM_BAND][swp]
-    float4* Mt = S + (size_t)RM_BAND * swp;         // [RM_W][RM_MP]: row-pass results, ring of source rows
-    float4* Wx = Mt + RM_W * RM_MP;                 // [RM_XBLK][RM_SPAN]: expanded x weights of the strip's column blocks
-    float4* Wy = Wx + RM_XBLK * RM_SPAN;            // [RM_WARPS][RM_SPAN]: a warp's expanded y weights of its current row block
+    float4* Mt = S + (size_t)RM_BAND * swp;         // [RM_W][ring + 1]: row-pass results, ring of source rows
+    float4* Wx = Mt + RM_W * (T.ring + 1);          // [RM_XBLK][wspan]: expanded x weights of the strip's column blocks
+    float4* Wy = Wx + RM_XBLK * T.wspan;            // [RM_WARPS][wspan]: a warp's expanded y weights of its current row block
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int x0 = blockIdx.x * RM_W, y0 = blockIdx.y * T.ch;
     const int nx = min(RM_W, dst.w - x0), y1 = min(y0 + T.ch, dst.h);
@@ -408,11 +412,11 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, 
             for (int q = 0; q < CS; ++q) v[rr][q] = load_raw<TYPE>(src.p, g + sx[q]);
         }
     };
-    issue(r0);
+    if (PF) issue(r0);
 
     // expanded x weights: Wx[b][k] = weights of staged column fxb[b] + k for the block's four outputs
-    for (int i = tid; i < RM_XBLK * RM_SPAN; i += RM_THREADS) {
-        const int b = i / RM_SPAN, k = i - b * RM_SPAN;
+    for (int i = tid; i < RM_XBLK * T.wspan; i += RM_THREADS) {
+        const int b = i / T.wspan, k = i - b * T.wspan;
         float w[RM_B] = { 0.f, 0.f, 0.f, 0.f };
         if (b * RM_B < nx) {
             const int fb = xf[x0 + b * RM_B];
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, 
         const int xa = min(x0 + tid * RM_B, dst.w - 1), xb = min(x0 + tid * RM_B + RM_B - 1, dst.w - 1);
         const int fb = min(xf[xa] - fx0, max(cols - 1, 0));
         s_fxb[tid] = fb;
-        s_span[tid] = max(min(min(xf[xb] + T.xtaps - xf[xa], RM_SPAN), cols - fb), 0);
+        s_span[tid] = max(min(min(xf[xb] + T.xtaps - xf[xa], T.wspan), cols - fb), 0);
     }
 
     // destination rows complete after each band (yf is non-decreasing): counted once per CTA, so the walk below has no
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, 
     int ycur = y0;
     for (int band = 0; ycur < y1; ++band) {
         // ---- the band's pixels into the tile; then the next band's loads
+        if (!PF) issue(hi);
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr)
 #pragma unroll
@@ -466,7 +471,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, 
                 if (c < cols) S[(size_t)(warp + rr * RM_WARPS) * swp + c] = raw_px(v[rr][q], TYPE);
             }
         __syncthreads();
-        if (hi + RM_BAND < rlast) issue(hi + RM_BAND);
+        if (PF && hi + RM_BAND < rlast) issue(hi + RM_BAND);
         const int yend = s_yend[min(band, RM_MAXBANDS - 1)];
         auto run = [&](auto brc) {
             constexpr int BR = decltype(brc)::value;
@@ -478,7 +483,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, 
             // ---- row pass of the band into the ring
             if (warp * RM_B < nx) {
                 const float4* row = S + (size_t)lane * swp + s_fxb[warp];
-                const float4* w = Wx + warp * RM_SPAN;
+                const float4* w = Wx + warp * T.wspan;
                 const int span = s_span[warp];
                 float4 acc[RM_B];
 #pragma unroll
@@ -492,13 +497,14 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_march(const Img src_, 
                     acc[2] = fma4p(wk.z, q, acc[2]);
                     acc[3] = fma4p(wk.w, q, acc[3]);
                 }
-                const int slot = (hi - r0 + lane) & (RM_RING - 1);
+                int slot = (hi - r0) % T.ring + lane;
+                slot = slot >= T.ring ? slot - T.ring : slot;
 #pragma unroll
-                for (int o = 0; o < RM_B; ++o) Mt[(warp * RM_B + o) * RM_MP + slot] = acc[o];
+                for (int o = 0; o < RM_B; ++o) Mt[(warp * RM_B + o) * (T.ring + 1) + slot] = acc[o];
             }
             __syncthreads();
             // ---- column pass over the destination rows whose window is now complete: a warp per block of BR rows
-            march_cols<BR>(tab, dst, Mt, Wy + warp * RM_SPAN, yf, yw, yt, T.ytaps, ycur, yend, r0, x0, nx);
+            march_cols<BR>(tab, dst, Mt, T.ring, Wy + warp * T.wspan, yf, yw, yt, T.ytaps, ycur, yend, r0, x0, nx);
         };
         // 2 rows per block when the band completes at most 16 rows, so that every warp has a block
         if (yend - ycur <= 2 * RM_WARPS) run(std::integral_constant<int, 2>());
@@ -801,7 +807,15 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
     M.sw = (int)ceilf((float)(RM_W - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
     const int span_x = (int)ceilf((float)(RM_B - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
     const int span_y = (int)ceilf((float)(RM_B - 1) * (float)src->h / (float)dst->h) + ay.taps + 1;
-    const size_t march_smem = resize_march_smem(M.sw);
+    M.ring = ay.taps <= 16 ? 48 : 64;
+    M.wspan = std::min(RM_SPAN, (std::max(span_x, span_y) + 3) & ~3);
+    const size_t march_smem = resize_march_smem(M.sw, M.ring, M.wspan);
+    static const int march_occ = [] {
+        const char* e = getenv("TOUCAN_RESIZE_OCC"); // 2: always the register-prefetch variant (two CTAs per SM)
+        return e && *e ? atoi(e) : 3;
+    }();
+    // three CTAs per SM where they fit; a one-span tile (enlargements) holds 4 pixels per thread in flight, measured faster with the prefetch
+    const bool three = march_occ >= 3 && march_smem <= 74 * 1024 && M.sw > 32;
     const bool march = ax.taps <= RM_BAND && ay.taps <= RM_BAND && span_x <= RM_SPAN && span_y <= RM_SPAN && M.sw <= 128 && march_smem <= 99 * 1024;
     // per-axis tables: cached per geometry; built in the call's scratch only if the cache is full
     AxisTable tx, ty;
@@ -829,9 +843,9 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
         count_launch(2);
     }
     if (march) {
-        // chunks of destination rows: one wave of two CTAs per SM, warm-up rows (ytaps per chunk) kept below ~1/8 of a chunk
+        // chunks of destination rows: one wave of two / three CTAs per SM, warm-up rows (ytaps per chunk) kept below ~1/8 of a chunk
         const int strips = (dst->w + RM_W - 1) / RM_W;
-        int chunks = std::max(1, 2 * num_sms() / strips);
+        int chunks = std::max(1, (three ? 3 : 2) * num_sms() / strips);
         chunks = std::min(chunks, std::max(1, src->h / (8 * ay.taps)));
         chunks = std::max(1, std::min(chunks, dst->h));
         M.ch = (dst->h + chunks - 1) / chunks;
@@ -840,15 +854,17 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
         M.ch = std::min(M.ch, max_rows);
         const dim3 grid(strips, (dst->h + M.ch - 1) / M.ch);
         int e = TC_OK;
-#define TC_RM2(TY, CS)                                                                                                             \
-    e = ensure_dynamic_smem((const void*)k_resize_march<TY, CS>, march_smem);                                                      \
-    if (e == TC_OK) k_resize_march<TY, CS><<<grid, RM_THREADS, march_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, M);
-#define TC_RM(TY)                                                                                                                  \
-    case TY:                                                                                                                       \
-        if (M.sw <= 32) { TC_RM2(TY, 1) }                                                                                          \
-        else if (M.sw <= 64) { TC_RM2(TY, 2) }                                                                                     \
-        else if (M.sw <= 96) { TC_RM2(TY, 3) }                                                                                     \
-        else { TC_RM2(TY, 4) }                                                                                                     \
+#define TC_RM3(TY, CS, PF)                                                                                                          \
+    e = ensure_dynamic_smem((const void*)k_resize_march<TY, CS, PF>, march_smem);                                                    \
+    if (e == TC_OK) k_resize_march<TY, CS, PF><<<grid, RM_THREADS, march_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, M);
+#define TC_RM2(TY, CS)                                                                                                              \
+    if (three) { TC_RM3(TY, CS, false) } else { TC_RM3(TY, CS, true) }
+#define TC_RM(TY)                                                                                                                   \
+    case TY:                                                                                                                        \
+        if (M.sw <= 32) { TC_RM2(TY, 1) }                                                                                           \
+        else if (M.sw <= 64) { TC_RM2(TY, 2) }                                                                                      \
+        else if (M.sw <= 96) { TC_RM2(TY, 3) }                                                                                      \
+        else { TC_RM2(TY, 4) }                                                                                                      \
         break;
         switch (src->type) {
             TC_RM(TC_U8)
@@ -856,6 +872,8 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
             TC_RM(TC_F16)
             TC_RM(TC_F32)
         }
+#undef TC_RM
+#undef TC_RM3
 #undef TC_RM2
 #undef TC_RM
         if (e != TC_OK) {
