@@ -23,6 +23,7 @@
 
 #include "tc_common.cuh"
 #include "tc_tile.cuh"
+#include "tc_tma.cuh"
 
 namespace tc {
 
@@ -613,6 +614,25 @@ __device__ __forceinline__ bool rot_filt_zero(float x)
     return FILT == 0 ? fabsf(x) >= 3.0f : (x < -1.0f || x > 1.0f);
 }
 
+// The six live lanczos3 weights of one axis at x_k = b0 + k, k = 0 .. 5, for unit tap spacing and b0 in (-3, -2].  OIIO's
+// parabola sinpi is odd with period 2, so |fast_sinpi(x_k)| is the same for all six taps and its sign runs + - + + - +:
+// ONE evaluation instead of six; |x_k| / 3 <= 1 needs no range reduction.  ~11 instructions per weight instead of ~25,
+// each within float rounding (a few 1e-7 relative) of rot_filt_fast.
+__device__ __forceinline__ void lanczos3_six(float b0, float (&w)[6])
+{
+    const float A = __fmul_rn(fabsf(fast_sinpi_fused(b0)), 0.30396355092701331f); // |sinpi| * 3 / pi^2
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const float x = fabsf(__fadd_rn(b0, (float)k));
+        const float u = __fmul_rn(x, 1.0f / 3.0f);
+        const float y = fmaf(-u, u, u);
+        const float f3 = __fmul_rn(y, fmaf(3.584135056f, y, 3.10396624f));
+        float v = __fmul_rn(__fmul_rn(rcp_approx(__fmul_rn(x, x)), (k == 1 || k == 4) ? -A : A), f3);
+        if (k == 2 || k == 3) v = x < 0.0001f ? 1.0f : v;
+        w[k] = v;
+    }
+}
+
 // The same gather through a shared-memory tile (the north-star layout for Rotate).  A CTA owns a 16 x 16 block
 // of the destination; the inverse map is affine, so the block's source footprint is the bounding box of its
 // four corner footprints.  The box is staged once with black outside the source -- which also removes the
@@ -621,36 +641,52 @@ __device__ __forceinline__ bool rot_filt_zero(float x)
 // live taps only, rows reduced first (see the kernel).
 constexpr int RTT = 16; // destination block edge
 
-struct RotTile { int cols, rows, pitch; }; // allocation of the shared source tile; row pitch in pixels
+struct RotTile {
+    int cols, rows, pitch;                       // allocation of the shared source tile; row pitch in pixels
+    float smn_off, smx_off, tmn_off, tmx_off;    // extent of a block's four corner positions relative to its first pixel's
+};
 
-template <int MAXT, int FILT, int TYPE>
-__global__ void __launch_bounds__(RTT * RTT) k_rotate_tile(const Img src_, const Img dst, const __grid_constant__ RotParams P, const RotTile T)
+// TMA: the source box is fetched by ONE tensor copy (float32 sources; zero fill outside the frame IS rotate's "black outside
+// the source") issued by thread 0 and awaited on an mbarrier only after every thread has evaluated its 12 filter weights --
+// the copy's latency hides behind them.  Otherwise a warp per source row stages the box with bounds-checked loads.
+template <int MAXT, int FILT, int TYPE, bool TMA>
+__global__ void __launch_bounds__(RTT * RTT) k_rotate_tile(const Img src_, const Img dst, const __grid_constant__ RotParams P, const RotTile T,
+                                                           const __grid_constant__ CUtensorMap map)
 {
-    extern __shared__ float4 rot_smem[];
+    extern __shared__ __align__(128) float4 rot_smem[];
+    __shared__ uint64_t bar;
     const Img src { src_.p, src_.w, src_.h, TYPE };
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * RTT, y0 = blockIdx.y * RTT;
     const float ds = fmaxf(1.0f, fmaxf(fabsf(P.m[0]), fabsf(P.m[3])));
     const float dt = fmaxf(1.0f, fmaxf(fabsf(P.m[1]), fabsf(P.m[4])));
     const float rs = __fmul_rn(__fmul_rn(0.5f, ds), P.fw), rt = __fmul_rn(__fmul_rn(0.5f, dt), P.fw);
-    // footprint of the block: extremes of the affine map are at its corner pixels (one pixel of slack for rounding)
-    float smn = 3.0e38f, smx = -3.0e38f, tmn = 3.0e38f, tmx = -3.0e38f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float px = __fadd_rn((float)(x0 + (k & 1) * (RTT - 1)), 0.5f), py = __fadd_rn((float)(y0 + (k >> 1) * (RTT - 1)), 0.5f);
-        const float s = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[0]), __fmul_rn(py, P.m[3])), P.m[6]);
-        const float t = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[1]), __fmul_rn(py, P.m[4])), P.m[7]);
-        smn = fminf(smn, s), smx = fmaxf(smx, s), tmn = fminf(tmn, t), tmx = fmaxf(tmx, t);
-    }
-    const int s0 = (int)floorf(smn - rs) - 1, t0 = (int)floorf(tmn - rt) - 1;
-    const int cols = min((int)ceilf(smx + rs) + 1 - s0, T.cols), rows = min((int)ceilf(tmx + rt) + 1 - t0, T.rows);
+    // footprint of the block: the affine map takes its extremes at the corner pixels -- the first pixel's position plus
+    // the host's corner offsets (two pixels of slack cover the rounding of either form)
+    const float px0 = __fadd_rn((float)x0, 0.5f), py0 = __fadd_rn((float)y0, 0.5f);
+    const float s00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[0]), __fmul_rn(py0, P.m[3])), P.m[6]);
+    const float t00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[1]), __fmul_rn(py0, P.m[4])), P.m[7]);
+    const int s0 = (int)floorf(s00 + T.smn_off - rs) - 1, t0 = (int)floorf(t00 + T.tmn_off - rt) - 1;
+    const int cols = min((int)ceilf(s00 + T.smx_off + rs) + 1 - s0, T.cols), rows = min((int)ceilf(t00 + T.tmx_off + rt) + 1 - t0, T.rows);
     const int pitch = T.pitch;
-    // stage: a warp per source row, black outside the source
-    for (int r = tid >> 5; r < rows; r += RTT * RTT / 32)
-        for (int c = tid & 31; c < cols; c += 32) rot_smem[r * pitch + c] = load_black(src, s0 + c, t0 + r);
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_init_fence();
+            mbar_expect_tx(&bar, (unsigned)(T.rows * T.pitch * 16));
+            tma_load_tile(rot_smem, &map, 2 * s0, t0, &bar);
+        }
+    } else {
+        // stage: a warp per source row, black outside the source
+        for (int r = tid >> 5; r < rows; r += RTT * RTT / 32)
+            for (int c = tid & 31; c < cols; c += 32) rot_smem[r * pitch + c] = load_black(src, s0 + c, t0 + r);
+    }
     __syncthreads();
 
-    const int x = x0 + (tid & (RTT - 1)), y = y0 + tid / RTT;
+    // a warp covers 8 x 4 destination pixels and each quarter warp (one 128-bit shared-memory phase) a compact 4 x 2 block:
+    // its eight footprints start inside a ~3 x 3 patch of the tile instead of along a diagonal of 6 (fewer bank conflicts)
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x = x0 + (warp & 1) * 8 + ((lane >> 3) & 1) * 4 + (lane & 3), y = y0 + (warp >> 1) * 4 + (lane >> 4) * 2 + ((lane >> 2) & 1);
     if (x >= dst.w || y >= dst.h) return;
     const float px = __fadd_rn((float)x, 0.5f), py = __fadd_rn((float)y, 0.5f);
     const float s = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[0]), __fmul_rn(py, P.m[3])), P.m[6]);
@@ -680,20 +716,29 @@ __global__ void __launch_bounds__(RTT * RTT) k_rotate_tile(const Img src_, const
                       (j0 || nt <= LIVE || rot_filt_zero<FILT>(__fmul_rn(__fadd_rn(by, (float)LIVE), ky)));
     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
     float total = 0.0f;
-    if (fast) {
-        const float bx0 = __fadd_rn(bx, (float)i0), by0 = __fadd_rn(by, (float)j0);
+    const float bx0 = __fadd_rn(bx, (float)i0), by0 = __fadd_rn(by, (float)j0);
+    // lanczos3 at unit tap spacing (every plain rotation): the shared-sinpi evaluation; anything else of lanczos3 goes tap by tap
+    const bool six = FILT != 0 || (kx == 1.0f && ky == 1.0f && bx0 > -3.0f && bx0 <= -2.0f && by0 > -3.0f && by0 <= -2.0f);
+    if (fast && six) {
         float ax[LIVE], ay[LIVE];
         float sx = 0.0f, sy = 0.0f;
+        if (FILT == 0) {
+            lanczos3_six(bx0, ax);
+            lanczos3_six(by0, ay);
+        }
 #pragma unroll
         for (int k = 0; k < LIVE; ++k) {
-            const float fx = rot_filt_fast<FILT>(__fmul_rn(__fadd_rn(bx0, (float)k), kx));
-            const float fy = rot_filt_fast<FILT>(__fmul_rn(__fadd_rn(by0, (float)k), ky));
-            ax[k] = i0 + k < ns ? fx : 0.0f;
-            ay[k] = j0 + k < nt ? fy : 0.0f;
+            if (FILT != 0) {
+                ax[k] = rot_filt_fast<FILT>(__fmul_rn(__fadd_rn(bx0, (float)k), kx));
+                ay[k] = rot_filt_fast<FILT>(__fmul_rn(__fadd_rn(by0, (float)k), ky));
+            }
+            ax[k] = i0 + k < ns ? ax[k] : 0.0f;
+            ay[k] = j0 + k < nt ? ay[k] : 0.0f;
             sx = __fadd_rn(sx, ax[k]);
             sy = __fadd_rn(sy, ay[k]);
         }
         total = __fmul_rn(sx, sy);
+        if (TMA) mbar_wait(&bar, 0);
         const float4* row = rot_smem + (rbase + j0) * pitch + cbase + i0;
 #pragma unroll
         for (int j = 0; j < LIVE; ++j, row += pitch) {
@@ -707,6 +752,7 @@ __global__ void __launch_bounds__(RTT * RTT) k_rotate_tile(const Img src_, const
         float wx[MAXT];
 #pragma unroll
         for (int i = 0; i < MAXT; ++i) wx[i] = i < ns ? rot_filt_fast<FILT>(__fmul_rn(__fadd_rn(bx, (float)i), kx)) : 0.0f;
+        if (TMA) mbar_wait(&bar, 0);
 #pragma unroll 1
         for (int j = 0; j < nt; ++j) {
             const float wy = rot_filt_fast<FILT>(__fmul_rn(__fadd_rn(by, (float)j), ky));
@@ -957,22 +1003,36 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
         RotTile T;
         T.cols = (int)ceilf((RTT - 1) * (fabsf(P.m[0]) + fabsf(P.m[3])) + ds * P.fw) + 5;
         T.rows = (int)ceilf((RTT - 1) * (fabsf(P.m[1]) + fabsf(P.m[4])) + dt * P.fw) + 5;
-        // Row pitch: 8 consecutive destination pixels (a quarter warp, one 128-bit shared-memory phase) step through the
-        // source by (m0, m1) each; pick the pitch whose 16-byte slots collide least for that step over a few phases
-        // (at 45 degrees the step is about (+1 row, +1 column), so pitch + 1 must not be a multiple of 8).
+        const float edge = (float)(RTT - 1);
+        T.smn_off = fminf(0.0f, edge * P.m[0]) + fminf(0.0f, edge * P.m[3]);
+        T.smx_off = fmaxf(0.0f, edge * P.m[0]) + fmaxf(0.0f, edge * P.m[3]);
+        T.tmn_off = fminf(0.0f, edge * P.m[1]) + fminf(0.0f, edge * P.m[4]);
+        T.tmx_off = fmaxf(0.0f, edge * P.m[1]) + fmaxf(0.0f, edge * P.m[4]);
+        // Row pitch: a quarter warp (one 128-bit shared-memory phase) is a 4 x 2 block of destination pixels whose footprints
+        // start at (a m0 + b m3, a m1 + b m4) from the first; pick the pitch whose 16-byte slots collide least over a few
+        // sub-pixel phases of that first position.
         int best = 1 << 30;
         T.pitch = T.cols;
         for (int pitch = T.cols; pitch < T.cols + 8; ++pitch) {
             int cost = 0;
             for (int ph = 0; ph < 16; ++ph) {
                 const float sf = 0.25f * (float)(ph & 3), tf = 0.25f * (float)(ph >> 2);
-                int hits[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                // wavefronts of one phase = the most DISTINCT 16-byte slots that share a bank group
+                int slots[8], worst = 0;
                 for (int k = 0; k < 8; ++k) {
-                    const int slot = (int)floorf(tf + 64.0f + (float)k * P.m[1]) * pitch + (int)floorf(sf + 64.0f + (float)k * P.m[0]);
-                    ++hits[slot & 7];
+                    const float a = (float)(k & 3), b = (float)(k >> 2);
+                    slots[k] = (int)floorf(tf + 64.0f + a * P.m[1] + b * P.m[4]) * pitch + (int)floorf(sf + 64.0f + a * P.m[0] + b * P.m[3]);
                 }
-                int worst = 0;
-                for (int k = 0; k < 8; ++k) worst = hits[k] > worst ? hits[k] : worst;
+                for (int g = 0; g < 8; ++g) {
+                    int n = 0;
+                    for (int k = 0; k < 8; ++k) {
+                        if ((slots[k] & 7) != g) continue;
+                        bool seen = false;
+                        for (int q = 0; q < k; ++q) seen = seen || slots[q] == slots[k];
+                        n += seen ? 0 : 1;
+                    }
+                    worst = n > worst ? n : worst;
+                }
                 cost += worst;
             }
             if (cost < best) {
@@ -984,22 +1044,32 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
         if (narrow && smem <= 64 * 1024) {
             const dim3 tgrid((dst->w + RTT - 1) / RTT, (dst->h + RTT - 1) / RTT);
             int e = TC_OK;
+            // float32 sources on a 16-byte aligned base: the box through the copy engine
+            CUtensorMap map;
+            memset(&map, 0, sizeof(map));
+            static const bool rot_tma = [] {
+                const char* e = getenv("TOUCAN_ROTATE_TMA");
+                return !(e && *e == '0');
+            }();
+            const bool tma = rot_tma && src->type == TC_F32 && tma_available() && ((uintptr_t)src->data & 15) == 0 && 2 * T.pitch <= 256 && T.rows <= 256 &&
+                             tensor_map_2d(src->data, 8, 2ull * src->w, (unsigned long long)src->h, 16ull * src->w, 2u * T.pitch, (unsigned)T.rows, &map) == TC_OK;
+#define TC_ROTT2(TY, F, TM)                                                                                             \
+    e = ensure_dynamic_smem((const void*)k_rotate_tile<8, F, TY, TM>, smem);                                            \
+    if (e == TC_OK) k_rotate_tile<8, F, TY, TM><<<tgrid, RTT * RTT, smem, st>>>(vs, vd, P, T, map);
 #define TC_ROTT(TY)                                                                                                     \
     case TY:                                                                                                            \
-        if (id == 0) {                                                                                                  \
-            e = ensure_dynamic_smem((const void*)k_rotate_tile<8, 0, TY>, smem);                                        \
-            if (e == TC_OK) k_rotate_tile<8, 0, TY><<<tgrid, RTT * RTT, smem, st>>>(vs, vd, P, T);                      \
-        } else {                                                                                                        \
-            e = ensure_dynamic_smem((const void*)k_rotate_tile<8, 1, TY>, smem);                                        \
-            if (e == TC_OK) k_rotate_tile<8, 1, TY><<<tgrid, RTT * RTT, smem, st>>>(vs, vd, P, T);                      \
-        }                                                                                                               \
+        if (id == 0) { TC_ROTT2(TY, 0, false) } else { TC_ROTT2(TY, 1, false) }                                         \
         break;
+            if (tma) {
+                if (id == 0) { TC_ROTT2(TC_F32, 0, true) } else { TC_ROTT2(TC_F32, 1, true) }
+            } else
             switch (src->type) {
                 TC_ROTT(TC_U8)
                 TC_ROTT(TC_U16)
                 TC_ROTT(TC_F16)
                 TC_ROTT(TC_F32)
             }
+#undef TC_ROTT2
 #undef TC_ROTT
             if (e != TC_OK) return e;
             count_launch();
