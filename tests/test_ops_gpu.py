@@ -635,3 +635,45 @@ def test_tiled_filters_are_deterministic_with_poisoned_surroundings(T, op):
             first = got.clone()
         else:
             assert torch.equal(first, got), f"{op}: run {rep} differs from run 0"
+
+
+_SWITCH_PROBE = r"""
+import hashlib, sys
+import numpy as np, torch
+sys.path.insert(0, {root!r})
+from toucan_b200 import capi, ops
+capi.check(capi.lib().tc_set_device(0), "tc_set_device")
+rng = np.random.default_rng(77)
+src = torch.from_numpy(rng.random((217, 333, 4), dtype=np.float32)).cuda()
+for name, out in (("rotate", ops.rotate(src, 33.0)), ("resize_down", ops.resize(src, (160, 101))), ("resize_up", ops.resize(src, (700, 450))),
+                  ("blur", ops.blur(src, 10.0))):
+    torch.cuda.synchronize()
+    a = out.cpu().numpy()
+    print(name, hashlib.sha256(a.tobytes()).hexdigest(), float(a.astype(np.float64).sum()))
+"""
+
+
+@pytest.mark.gpu
+def test_kernel_variants_behind_the_switches_agree(T, tmp_path):
+    """TOUCAN_ROTATE_TMA=0 (bounds-checked staging instead of the TMA copy) and TOUCAN_RESIZE_OCC=2 (the register-prefetch march)
+    change how pixels reach shared memory, not the arithmetic: identical frames.  TOUCAN_CONV_TMA=0 selects round 1's Blur kernel:
+    same taps, within float rounding."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "probe.py"
+    script.write_text(_SWITCH_PROBE.format(root=root))
+
+    def run(env):
+        e = dict(os.environ, **env)
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=e)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return {l.split()[0]: (l.split()[1], float(l.split()[2])) for l in r.stdout.splitlines() if l and l.split()[0] in ("rotate", "resize_down", "resize_up", "blur")}
+
+    base = run({})
+    alt = run({"TOUCAN_ROTATE_TMA": "0", "TOUCAN_RESIZE_OCC": "2", "TOUCAN_CONV_TMA": "0"})
+    for k in ("rotate", "resize_down", "resize_up"):
+        assert base[k][0] == alt[k][0], k
+    assert abs(base["blur"][1] - alt["blur"][1]) <= 1e-6 * abs(base["blur"][1]), (base["blur"], alt["blur"])
