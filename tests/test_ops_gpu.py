@@ -236,6 +236,10 @@ def test_resize(T, dt):
     # tile -> two-pass path with the staged row pass; (5, 3): beyond that -> gathers
     for size in [(320, 180), (80, 45), (160, 90), (200, 50), (48, 27), (33, 77), (20, 12), (5, 3)]:
         assert_close(T.resize(d, size), O.resize(src, size), f"resize {size}")
+    # tiny and one-pixel-wide sources, a tall frame (several chunks of bands per strip), a large enlargement (hundreds of rows per band)
+    for (w, h), size in [((1, 1), (7, 5)), ((3, 2), (64, 64)), ((2, 300), (3, 1000)), ((31, 1000), (17, 333)), ((40, 24), (400, 250))]:
+        s2 = rand_img(w, h, dt, 9)
+        assert_close(T.resize(to_dev(s2), size), O.resize(s2, size), f"resize {(w, h)} -> {size}")
     assert_close(T.resize(d, (100, 60), "lanczos3", 0.0), O.resize(src, (100, 60), "lanczos3", 0.0), "resize lanczos3")
     assert_close(T.resize(d, (300, 200), "blackman-harris", 0.0), O.resize(src, (300, 200), "blackman-harris", 0.0), "resize bh")
 
@@ -245,6 +249,15 @@ def test_resize(T, dt):
 def test_rotate(T, dt, angle):
     src = rand_img(160, 90, dt, 5)
     assert_close(T.rotate(to_dev(src), angle), O.rotate(src, angle), f"rotate {angle}")
+
+
+@pytest.mark.parametrize("size", [(1, 1), (37, 5), (5, 37), (64, 48), (333, 217)])
+def test_rotate_small_and_odd_frames(T, size):
+    # frames smaller than the staged box (the TMA copy reads mostly outside the frame: zero fill = the black surround)
+    for dt in (np.float32, np.uint8):
+        src = rand_img(size[0], size[1], dt, 11)
+        for angle in (45.0, -17.0):
+            assert_close(T.rotate(to_dev(src), angle), O.rotate(src, angle), f"rotate {size} {angle}")
 
 
 @pytest.mark.parametrize("dta", NP_TYPES)
