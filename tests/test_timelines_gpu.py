@@ -258,6 +258,11 @@ def test_toucan_render_cli(cuda, tmp_path):
     r = subprocess.run([exe, os.path.join(TL.DATA, "Transition.otio"), str(out3), "-workers", "3"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert open(out3, "rb").read() == open(out, "rb").read()
+    # a frame range (-frames a:b, indices from the timeline's start, inclusive): exactly those frames
+    outr = tmp_path / "transition_3_5.raw"
+    r = subprocess.run([exe, os.path.join(TL.DATA, "Transition.otio"), str(outr), "-frames", "3:5"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert np.fromfile(outr, np.uint8).tobytes() == raw[3:6].tobytes()
 
 
 @pytest.mark.parametrize("interleave", [True, False])

@@ -35,6 +35,7 @@ int main(int argc, char** argv)
         int inflight = 0; // pinned ring slots per worker (0 = the scheduler's default)
         int workers = 1; // render threads per GPU: small frames are bound by the host-side graph build, which overlaps across workers
         bool printStart = false, printDuration = false, printRate = false, printSize = false, verbose = false;
+        int firstFrame = 0, lastFrame = -1; // -frames a:b: frame indices counted from the timeline's start, both inclusive
         for (int i = 1; i < argc; ++i)
         {
             const std::string a = argv[i];
@@ -44,6 +45,13 @@ int main(int argc, char** argv)
             else if (a == "-inflight" && i + 1 < argc) inflight = std::atoi(argv[++i]);
             else if (a == "-raw" && i + 1 < argc) raw = argv[++i];
             else if (a == "-y4m" && i + 1 < argc) y4m = argv[++i];
+            else if (a == "-frames" && i + 1 < argc)
+            {
+                const std::string r = argv[++i];
+                const size_t colon = r.find(':');
+                firstFrame = std::atoi(r.substr(0, colon).c_str());
+                lastFrame = colon == std::string::npos ? firstFrame : (colon + 1 < r.size() ? std::atoi(r.substr(colon + 1).c_str()) : -1);
+            }
             else if (a == "-v") verbose = true;
             else if (a == "-unassociated_alpha") setKeepUnassociatedAlpha(true); // OIIO's "oiio:UnassociatedAlpha" reader hint
 
@@ -56,7 +64,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-cache GiB] [-v] [-unassociated_alpha] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-cache GiB] [-frames a:b] [-v] [-unassociated_alpha] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 
@@ -142,13 +150,16 @@ int main(int argc, char** argv)
         MediaPrefetch prefetch(timelineWrapper->getMediaStore(), timelineWrapper->getStillMedia(), 2);
         FrameScheduler scheduler(context, timelineWrapper, options);
         double firstFrameSeconds = 0.0, halfWaySeconds = 0.0;
-        scheduler.run(0, frames, [&](int frame, const void* pixels, const ImageSpec& spec, size_t bytes)
+        firstFrame = std::max(0, std::min(firstFrame, frames));
+        const int endFrame = lastFrame < 0 ? frames : std::max(firstFrame, std::min(lastFrame + 1, frames));
+        scheduler.run(firstFrame, endFrame, [&](int frame, const void* pixels, const ImageSpec& spec, size_t bytes)
         {
-            if (verbose && (0 == frame || frames / 2 == frame))
+            const int halfWay = firstFrame + (endFrame - firstFrame) / 2;
+            if (verbose && (firstFrame == frame || halfWay == frame))
             {
                 const double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - wallStart).count();
-                if (0 == frame) firstFrameSeconds = t;
-                if (frames / 2 == frame) halfWaySeconds = t;
+                if (firstFrame == frame) firstFrameSeconds = t;
+                if (halfWay == frame) halfWaySeconds = t;
             }
             if (output != "-")
             {
@@ -187,9 +198,10 @@ int main(int argc, char** argv)
             unsigned long long allocCalls = 0, allocNs = 0;
             tc_alloc_stats(&allocCalls, &allocNs);
             const double secondHalf = seconds - halfWaySeconds;
-            std::cerr << "frames: " << frames << "  seconds: " << seconds << "  frames/s: " << (seconds > 0.0 ? frames / seconds : 0.0)
+            const int rendered = endFrame - firstFrame;
+            std::cerr << "frames: " << rendered << "  seconds: " << seconds << "  frames/s: " << (seconds > 0.0 ? rendered / seconds : 0.0)
                       << "  first frame after: " << firstFrameSeconds << " s  second half: "
-                      << (secondHalf > 0.0 ? (frames - frames / 2) / secondHalf : 0.0) << " frames/s"
+                      << (secondHalf > 0.0 ? (rendered - rendered / 2) / secondHalf : 0.0) << " frames/s"
                       << "  kernel launches: " << tc_launch_count() << "  allocator calls: " << allocCalls << " (" << allocNs * 1e-9 << " s)"
                       << "  source uploads: " << timelineWrapper->getMediaStore()->getUploadCount() << " ("
                       << timelineWrapper->getMediaStore()->getUploadBytes() / 1.0e9 << " GB)" << std::endl;
