@@ -62,6 +62,9 @@ int tc_event_destroy(tc_event e);
 int tc_event_record(tc_event e, tc_stream s);
 int tc_event_sync(tc_event e);
 int tc_stream_wait_event(tc_stream s, tc_event e);
+/* timing events (diagnostics: the per-node timers of toucan-render -timers; no reference counterpart) */
+int tc_event_create_timing(tc_event* out);
+int tc_event_elapsed_ms(tc_event start, tc_event stop, float* ms);
 size_t tc_type_size(int type);
 size_t tc_image_bytes(int w, int h, int type);
 /* result type of op(A,B) into an uninitialised destination (OIIO TypeDesc::basetype_merge) */

@@ -139,6 +139,12 @@ void tr_set_fusion(int enabled);
    contiguous blocks (tr_frame_block: consecutive frames per worker). */
 void tr_set_interleave(int enabled);
 
+/* Per-node device timers (the reference has none; `toucan-render -timers`): when on, every effect / composite / fused
+   node brackets its kernels with two timing events.  tr_node_timers_report waits for the pending events, writes one line per
+   node label ("label  calls  total ms  ms/call", largest first) and resets the totals; returns the bytes the text needs. */
+void tr_set_node_timers(int enabled);
+size_t tr_node_timers_report(char* out, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

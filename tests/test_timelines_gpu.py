@@ -409,3 +409,39 @@ def test_node_chains_through_comp_and_flips_are_bit_identical_to_the_node_path(h
     finally:
         render.set_fusion(True)
         tl.close()
+
+
+def test_node_timers_report_device_time_per_node_label(cuda):
+    """toucan::NodeTimers (toucan-render -timers): every effect / composite / fused node brackets its kernels with timing events;
+    the report has one line per label with the calls and the device milliseconds.  Node by node the labels are the effects'
+    names; with fusion on a clip's effects and its composite are ONE chain launch per frame."""
+    from toucan_b200 import render
+
+    render.bind_device(0)
+    host = render.Host()
+    tl = render.Timeline(os.path.join(TL.DATA, "Filter.otio"))
+    info = tl.info()
+
+    def run(fusion):
+        render.set_fusion(fusion)
+        render.set_node_timers(True)
+        try:
+            for i in range(info["frames"]):
+                tl.render(host, info["start"] + i, max_bytes=1280 * 720 * 16)
+            report = render.node_timers_report()
+        finally:
+            render.set_node_timers(False)
+            render.set_fusion(True)
+        rows = {l[:40].strip(): l[40:].split() for l in report.splitlines() if l.strip()}
+        for k, v in rows.items():
+            assert int(v[0]) >= 1 and float(v[2]) > 0.0, (k, v)
+        return rows, report
+
+    rows, report = run(False)
+    for name in ("toucan:Blur", "toucan:UnsharpMask", "toucan:ColorMap", "toucan:Invert", "toucan:Pow", "toucan:Saturate"):
+        assert name in rows and int(rows[name][0]) == 1, report
+    assert any(k.startswith("Comp") for k in rows), report
+    rows, report = run(True)
+    assert sum(int(v[0]) for k, v in rows.items() if k.startswith("node chain")) == info["frames"], report
+    assert render.node_timers_report().strip() == ""  # the report resets the totals
+    tl.close()

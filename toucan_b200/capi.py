@@ -91,6 +91,8 @@ _SIGS = {
     "tc_host_unregister": [ctypes.c_void_p],
     "tc_type_merge": [ctypes.c_int, ctypes.c_int],
     "tc_event_create": [ctypes.POINTER(ctypes.c_void_p)],
+    "tc_event_create_timing": [ctypes.POINTER(ctypes.c_void_p)],
+    "tc_event_elapsed_ms": [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)],
     "tc_event_destroy": [ctypes.c_void_p],
     "tc_event_record": [ctypes.c_void_p, _S],
     "tc_event_sync": [ctypes.c_void_p],

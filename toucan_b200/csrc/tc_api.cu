@@ -192,6 +192,20 @@ int tc_event_create(tc_event* out)
     *out = e;
     return TC_OK;
 }
+int tc_event_create_timing(tc_event* out)
+{
+    if (!out) return fail(TC_ERR_INVALID, "tc_event_create_timing: null");
+    cudaEvent_t e;
+    TC_CUDA(cudaEventCreate(&e));
+    *out = e;
+    return TC_OK;
+}
+int tc_event_elapsed_ms(tc_event start, tc_event stop, float* ms)
+{
+    if (!start || !stop || !ms) return fail(TC_ERR_INVALID, "tc_event_elapsed_ms: null");
+    TC_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return TC_OK;
+}
 int tc_event_destroy(tc_event e)
 {
     if (!e) return TC_OK;

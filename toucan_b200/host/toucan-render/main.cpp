@@ -14,6 +14,7 @@
 //                 [-print_start] [-print_duration] [-print_rate] [-print_size]
 #include <toucanRender/ExrRead.h>
 #include <toucanRender/FrameScheduler.h>
+#include <toucanRender/ImageNode.h>
 #include <toucanRender/PngRead.h>
 #include <toucanRender/TimelineWrapper.h>
 #include <toucanRender/Util.h>
@@ -52,6 +53,7 @@ int main(int argc, char** argv)
                 firstFrame = std::atoi(r.substr(0, colon).c_str());
                 lastFrame = colon == std::string::npos ? firstFrame : (colon + 1 < r.size() ? std::atoi(r.substr(colon + 1).c_str()) : -1);
             }
+            else if (a == "-timers") NodeTimers::setEnabled(true);
             else if (a == "-v") verbose = true;
             else if (a == "-unassociated_alpha") setKeepUnassociatedAlpha(true); // OIIO's "oiio:UnassociatedAlpha" reader hint
 
@@ -64,7 +66,7 @@ int main(int argc, char** argv)
         }
         if (input.empty() || (output.empty() && !(printStart || printDuration || printRate || printSize)))
         {
-            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-cache GiB] [-frames a:b] [-v] [-unassociated_alpha] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
+            std::cerr << "usage: toucan-render input.otio output.raw|- [-raw format | -y4m format] [-gpus N] [-workers K] [-cache GiB] [-frames a:b] [-timers] [-v] [-unassociated_alpha] [-print_start|-print_duration|-print_rate|-print_size]" << std::endl;
             return 1;
         }
 
@@ -191,6 +193,11 @@ int main(int argc, char** argv)
             fwrite(pixels, 1, bytes, f);
         });
         if (f && f != stdout) fclose(f);
+        if (NodeTimers::getEnabled())
+        {
+            // -timers: device time per node label over the whole run, on stderr
+            std::cerr << NodeTimers::report();
+        }
         if (verbose)
         {
             // -v (App.cpp:98-100): run statistics on stderr, so they never mix with a stream on stdout

@@ -140,10 +140,12 @@ namespace toucan
                 // generators render 4-channel UINT8 (ImageEffect.cpp:93)
                 buf = Image(ImageSpec(fgSpec.width, fgSpec.height, 4, tc_type_merge(fgSpec.format, TC_U8)));
                 const tc_image f = fg.view(), o = buf.view();
+                NodeTimers::Scope timer("Comp (over the Fill colour)");
                 tcCheck(tc_over_fill(&o, &f, fillColor, TC_U8, _premultiply ? 1 : 0, DeviceContext::stream()), "tc_over_fill");
                 return buf;
             }
             const Image bg = _inputs[1]->exec();
+            NodeTimers::Scope timer("Comp");
             buf = composite(fg, bg);
         }
         else if (1 == _inputs.size() && _inputs[0])

@@ -283,6 +283,7 @@ namespace toucan
             args.setInt(kOfxImageEffectPropCudaEnabled, 0, 1);
             args.setPointer(kOfxImageEffectPropCudaStream, 0, DeviceContext::stream());
 
+            NodeTimers::Scope timer(_name);
             const OfxStatus status = _effect.ofxPlugin->mainEntry(
                 kOfxImageEffectActionRender,
                 &_self,

@@ -2,7 +2,12 @@
 
 #include "StackFusion.h"
 
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <sstream>
 
 namespace toucan
@@ -30,6 +35,83 @@ namespace toucan
     bool IImageNode::describeChain(tc_chain&, std::shared_ptr<IImageNode>&) const { return false; }
 
     bool IImageNode::sizeHint(int&, int&) const { return false; }
+
+    namespace
+    {
+        struct PendingTimer
+        {
+            std::string label;
+            tc_event start, stop;
+        };
+        std::atomic<bool> timersEnabled{ false };
+        std::mutex timersMutex;
+        std::vector<PendingTimer> timersPending;
+        std::map<std::string, std::pair<unsigned long long, double> > timersTotal; // label -> (calls, ms)
+    }
+
+    void NodeTimers::setEnabled(bool value) { timersEnabled = value; }
+
+    bool NodeTimers::getEnabled() { return timersEnabled; }
+
+    NodeTimers::Scope::Scope(const std::string& label)
+    {
+        if (timersEnabled && DeviceContext::isBound() && TC_OK == tc_event_create_timing(&_start))
+        {
+            _label = label;
+            tc_event_record(_start, DeviceContext::stream());
+        }
+    }
+
+    NodeTimers::Scope::~Scope()
+    {
+        if (_start)
+        {
+            tc_event stop = nullptr;
+            if (TC_OK == tc_event_create_timing(&stop))
+            {
+                tc_event_record(stop, DeviceContext::stream());
+                std::lock_guard<std::mutex> lock(timersMutex);
+                timersPending.push_back({ _label, _start, stop });
+            }
+            else
+            {
+                tc_event_destroy(_start);
+            }
+        }
+    }
+
+    std::string NodeTimers::report(bool reset)
+    {
+        std::lock_guard<std::mutex> lock(timersMutex);
+        for (const auto& p : timersPending)
+        {
+            float ms = 0.F;
+            if (TC_OK == tc_event_sync(p.stop) && TC_OK == tc_event_elapsed_ms(p.start, p.stop, &ms))
+            {
+                auto& t = timersTotal[p.label];
+                t.first += 1;
+                t.second += ms;
+            }
+            tc_event_destroy(p.start);
+            tc_event_destroy(p.stop);
+        }
+        timersPending.clear();
+        std::vector<std::pair<std::string, std::pair<unsigned long long, double> > > rows(timersTotal.begin(), timersTotal.end());
+        std::sort(rows.begin(), rows.end(), [](const auto& a, const auto& b) { return a.second.second > b.second.second; });
+        std::string out;
+        for (const auto& r : rows)
+        {
+            char line[256];
+            snprintf(line, sizeof(line), "%-40s %8llu calls %12.3f ms %10.4f ms/call\n", r.first.c_str(), r.second.first, r.second.second,
+                     r.second.first ? r.second.second / static_cast<double>(r.second.first) : 0.0);
+            out += line;
+        }
+        if (reset)
+        {
+            timersTotal.clear();
+        }
+        return out;
+    }
 
     bool tryNodeChain(const IImageNode& top, Image& out)
     {
@@ -80,6 +162,7 @@ namespace toucan
         }
         out = Image(spec);
         const tc_image src = source.view(), dst = out.view();
+        NodeTimers::Scope timer("node chain (" + top.getName() + " ...)");
         tcCheck(tc_pointwise_chain(&dst, &src, ops, chain.n, DeviceContext::stream()), "tc_pointwise_chain");
         return true;
     }

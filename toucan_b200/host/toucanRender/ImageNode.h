@@ -59,6 +59,30 @@ namespace toucan
         ImageNodeList _inputs;
         OTIO_NS::RationalTime _time;
     };
+    //! Per-node device timers (toucan-render -timers, tr_set_node_timers): a Scope brackets the kernels a node enqueues with
+    //! two timing events on the calling thread's stream; report() waits for the pending events and returns one line per
+    //! label ("label  calls  total ms  mean ms", largest total first).  Off by default: nothing is recorded then.
+    class NodeTimers
+    {
+    public:
+        static void setEnabled(bool);
+        static bool getEnabled();
+        static std::string report(bool reset = true);
+
+        class Scope
+        {
+        public:
+            explicit Scope(const std::string& label);
+            ~Scope();
+            Scope(const Scope&) = delete;
+            Scope& operator=(const Scope&) = delete;
+
+        private:
+            std::string _label;
+            tc_event _start = nullptr;
+        };
+    };
+
     //! Evaluate the chain of same-position nodes that starts at `top` (two or more of them) as ONE kernel over the chain's
     //! source; false when `top` does not start such a chain (nothing has been evaluated then).
     bool tryNodeChain(const IImageNode& top, Image& out);

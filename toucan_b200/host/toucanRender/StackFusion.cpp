@@ -246,6 +246,7 @@ namespace toucan
 
         Image result(ImageSpec(size.x, size.y, 4, TC_F32));
         const tc_image view = result.view();
+        NodeTimers::Scope timer("Comp (fused stack)");
         const int status = tc_stack_f32(&view, color, desc.data(), static_cast<int>(desc.size()), DeviceContext::stream());
         if (TC_ERR_UNSUPPORTED == status)
         {

@@ -14,6 +14,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <sstream>
@@ -481,4 +482,18 @@ extern "C"
     void tr_set_fusion(int enabled) { setStackFusionEnabled(enabled != 0); }
 
     void tr_set_interleave(int enabled) { interleaveFrames = enabled != 0; }
+
+    void tr_set_node_timers(int enabled) { NodeTimers::setEnabled(enabled != 0); }
+
+    size_t tr_node_timers_report(char* out, size_t capacity)
+    {
+        const std::string text = NodeTimers::report();
+        if (out && capacity > 0)
+        {
+            const size_t n = std::min(capacity - 1, text.size());
+            memcpy(out, text.data(), n);
+            out[n] = 0;
+        }
+        return text.size() + 1;
+    }
 }

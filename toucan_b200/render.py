@@ -54,7 +54,7 @@ _SIGS["tr_render_range_raw"] = [_VP, ctypes.c_char_p, _IP, ctypes.c_int, ctypes.
                                 FRAME_CALLBACK, _VP]
 _SIGS["tr_render_range_y4m"] = _SIGS["tr_render_range_raw"]
 _SIGS["tr_y4m_header"] = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
-EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_fit", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion", "tr_set_interleave",
+EXPORTS = sorted(set(_SIGS) | {"tr_frame_block", "tr_fit", "tr_last_error", "tr_host_destroy", "tr_host_plugin_identifier", "tr_timeline_close", "tr_set_fusion", "tr_set_interleave", "tr_set_node_timers", "tr_node_timers_report",
                                   "tr_set_unassociated_alpha", "tr_get_unassociated_alpha"})
 
 
@@ -80,6 +80,10 @@ def lib() -> ctypes.CDLL:
         _lib.tr_set_fusion.restype = None
         _lib.tr_set_interleave.argtypes = [ctypes.c_int]
         _lib.tr_set_interleave.restype = None
+        _lib.tr_set_node_timers.argtypes = [ctypes.c_int]
+        _lib.tr_set_node_timers.restype = None
+        _lib.tr_node_timers_report.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        _lib.tr_node_timers_report.restype = ctypes.c_size_t
     return _lib
 
 
@@ -103,6 +107,17 @@ def sync():
 
 def set_fusion(enabled: bool):
     lib().tr_set_fusion(1 if enabled else 0)
+
+
+def set_node_timers(enabled: bool):
+    """Per-node device timers (toucan::NodeTimers)."""
+    lib().tr_set_node_timers(1 if enabled else 0)
+
+
+def node_timers_report() -> str:
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().tr_node_timers_report(buf, len(buf))
+    return buf.value.decode()
 
 
 def set_interleave(enabled: bool):
