@@ -690,3 +690,29 @@ def test_kernel_variants_behind_the_switches_agree(T, tmp_path):
     for k in ("rotate", "resize_down", "resize_up"):
         assert base[k][0] == alt[k][0], k
     assert abs(base["blur"][1] - alt["blur"][1]) <= 1e-6 * abs(base["blur"][1]), (base["blur"], alt["blur"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_resize_random_geometries(T, seed):
+    """Random source / destination sizes and storage types: every dispatch of tc_resize (the march with 1-4 staged spans, two
+    and three CTAs per SM, chunk boundaries, the ring at 1-32 taps; the two-pass and gather paths beyond) against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(12):
+        w, h = int(rng.integers(1, 420)), int(rng.integers(1, 420))
+        dw, dh = int(rng.integers(1, 420)), int(rng.integers(1, 420))
+        if rng.random() < 0.3:  # near-identity and exact integer ratios are where rounding of the tap positions bites
+            dw, dh = max(1, w * int(rng.integers(1, 4)) // int(rng.integers(1, 4))), max(1, h * int(rng.integers(1, 4)) // int(rng.integers(1, 4)))
+        dt = NP_TYPES[int(rng.integers(0, len(NP_TYPES)))]
+        src = rand_img(w, h, dt, int(rng.integers(0, 1 << 30)))
+        assert_close(T.resize(to_dev(src), (dw, dh)), O.resize(src, (dw, dh)), f"resize {np.dtype(dt).name} {(w, h)} -> {(dw, dh)}")
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_rotate_random_geometries(T, seed):
+    rng = np.random.default_rng(2000 + seed)
+    for _ in range(10):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        angle = float(rng.uniform(-360.0, 360.0)) if rng.random() < 0.8 else float(rng.choice([0.0, 90.0, 180.0, 270.0, 45.0, -45.0]))
+        dt = NP_TYPES[int(rng.integers(0, len(NP_TYPES)))]
+        src = rand_img(w, h, dt, int(rng.integers(0, 1 << 30)))
+        assert_close(T.rotate(to_dev(src), angle), O.rotate(src, angle), f"rotate {np.dtype(dt).name} {(w, h)} by {angle}")
