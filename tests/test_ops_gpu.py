@@ -716,3 +716,41 @@ def test_rotate_random_geometries(T, seed):
         dt = NP_TYPES[int(rng.integers(0, len(NP_TYPES)))]
         src = rand_img(w, h, dt, int(rng.integers(0, 1 << 30)))
         assert_close(T.rotate(to_dev(src), angle), O.rotate(src, angle), f"rotate {np.dtype(dt).name} {(w, h)} by {angle}")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_blur_and_unsharp_random_geometries(T, seed):
+    """Random frame sizes (down to one pixel and narrower than a tile), radii over every tile template and storage types:
+    the TMA kernel, round 1's tile kernel (odd row pitches, narrow types at large radii, frames smaller than a tile) and the
+    wide-radius kernel against the oracle."""
+    rng = np.random.default_rng(3000 + seed)
+    for _ in range(8):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+        radius = float(rng.choice([0.5, 1.0, 2.5, 4.0, 7.0, 10.0, 13.0, 17.5, 20.0, 26.0, 33.0]))
+        dt = NP_TYPES[int(rng.integers(0, len(NP_TYPES)))]
+        src = rand_img(w, h, dt, int(rng.integers(0, 1 << 30)))
+        d = to_dev(src)
+        what = f"{np.dtype(dt).name} {(w, h)} r={radius}"
+        assert_close(T.blur(d, radius), O.blur(src, radius), "blur " + what)
+        assert_close(T.unsharp_mask(d, "gaussian", radius, 0.8, 0.0), O.unsharp_mask(src, "gaussian", radius, 0.8, 0.0), "unsharp " + what)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_crop_and_transitions_random_geometries(T, seed):
+    """Crop boxes that leave the frame, transitions and composites between frames of different sizes and storage types
+    (bit-exact ops: every pixel)."""
+    rng = np.random.default_rng(4000 + seed)
+    for _ in range(8):
+        w, h = int(rng.integers(1, 260)), int(rng.integers(1, 200))
+        dta, dtb = NP_TYPES[int(rng.integers(0, 4))], NP_TYPES[int(rng.integers(0, 4))]
+        a, b = rand_img(w, h, dta, int(rng.integers(0, 1 << 30))), rand_img(w, h, dtb, int(rng.integers(0, 1 << 30)))
+        da, db = to_dev(a), to_dev(b)
+        v = float(rng.choice([0.0, 0.25, 1.0 / 3.0, 0.5, 0.9, 1.0]))
+        what = f"{np.dtype(dta).name}/{np.dtype(dtb).name} {(w, h)} v={v}"
+        assert_exact(T.dissolve(da, db, v), O.dissolve(a, b, v), "dissolve " + what)
+        for vertical in (False, True):
+            assert_exact(T.wipe(da, db, v, vertical), O.wipe(a, b, v, vertical), f"wipe {vertical} " + what)
+        assert_exact(T.over(da, db, premult_fg=True), O.over(O.premult(a), b), "premult+over " + what)
+        pos = (int(rng.integers(-20, w + 10)), int(rng.integers(-20, h + 10)))
+        size = (int(rng.integers(1, w + 30)), int(rng.integers(1, h + 30)))
+        assert_exact(T.crop(da, pos, size), O.crop(a, pos, size), f"crop {pos} {size} " + what)
