@@ -99,7 +99,7 @@ def _tr(j):
 
 # ----------------------------------------------------------------------------------------
 # A light OTIO object model (Timeline/Stack/Track/Clip/Gap/Transition/Effect/LinearTimeWarp)
-@dataclass
+@dataclass(eq=False)  # nodes are compared by identity: two siblings may carry identical JSON
 class Node:
     schema: str
     j: dict
@@ -163,7 +163,7 @@ class Node:
         if self.kind == "Stack":
             d = child.duration()
             return TR(RT(0, d.rate), d)
-        idx = self.children.index(child)
+        idx = next(i for i, c in enumerate(self.children) if c is child)
         d = child.duration()
         start = RT(0, d.rate)
         for c in self.children[:idx]:

@@ -175,3 +175,97 @@ def test_timeline_documents_survive_damage(tmp_path):
     with pytest.raises(capi.TcError):
         render.Timeline(json_doc=None, path=deep[0])
 
+
+
+def _random_timeline(rng):
+    """A random but well-formed .otio document over synthetic stills: 1-3 video tracks (plus an audio track the graph skips) of
+    clips, gaps and transitions, with effect chains and time warps on clips, tracks and the stack."""
+    rate = 24.0
+
+    def rt(v):
+        return {"OTIO_SCHEMA": "RationalTime.1", "rate": rate, "value": float(v)}
+
+    def tr(s, d):
+        return {"OTIO_SCHEMA": "TimeRange.1", "start_time": rt(s), "duration": rt(d)}
+
+    def effect():
+        k = int(rng.integers(0, 12))
+        meta = [("toucan:Invert", {}), ("toucan:Pow", {"value": float(rng.choice([0.5, 2.0, 2.2, 3.0]))}),
+                ("toucan:Saturate", {"value": float(rng.uniform(0, 2))}), ("toucan:Blur", {"radius": float(rng.choice([2.0, 10.0, 20.0]))}),
+                ("toucan:ColorMap", {"map_name": str(rng.choice(["plasma", "inferno", "turbo"]))}), ("toucan:Flip", {}), ("toucan:Flop", {}),
+                ("toucan:Crop", {"pos": [int(rng.integers(0, 4)), int(rng.integers(0, 3))], "size": [int(rng.integers(1, 8)), int(rng.integers(1, 6))]}),
+                ("toucan:Resize", {"size": [int(rng.integers(2, 20)), int(rng.integers(2, 16))]}),
+                ("toucan:Rotate", {"angle": float(rng.uniform(-90, 90))}), ("toucan:UnsharpMask", {"width": 3.0, "contrast": 0.5}),
+                ("nonesuch:Effect", {})][k]
+        return {"OTIO_SCHEMA": "Effect.1", "name": meta[0], "effect_name": meta[0], "metadata": meta[1]}
+
+    def effects(p_warp):
+        out = [effect() for _ in range(int(rng.integers(0, 4)))]
+        if rng.random() < p_warp:
+            out.insert(int(rng.integers(0, len(out) + 1)),
+                       {"OTIO_SCHEMA": "LinearTimeWarp.1", "name": "", "effect_name": "", "metadata": {}, "time_scalar": float(rng.choice([0.5, 1.5, 2.0, -1.0]))})
+        return out
+
+    tracks = []
+    for t in range(int(rng.integers(1, 4))):
+        children = []
+        n = int(rng.integers(1, 6))
+        for i in range(n):
+            dur = int(rng.integers(6, 20))
+            if i > 0 and rng.random() < 0.6:
+                o = int(rng.integers(1, 3))
+                children.append({"OTIO_SCHEMA": "Transition.1", "name": "x", "metadata": {},
+                                 "transition_type": str(rng.choice(["toucan:Dissolve", "toucan:HorizontalWipe", "toucan:VerticalWipe", "SMPTE_Dissolve"])),
+                                 "in_offset": rt(o), "out_offset": rt(int(rng.integers(1, 3)))})
+            if rng.random() < 0.15 and children and children[-1]["OTIO_SCHEMA"] != "Transition.1":
+                children.append({"OTIO_SCHEMA": "Gap.1", "name": "Gap", "metadata": {}, "effects": [], "source_range": tr(0, int(rng.integers(2, 8)))})
+            children.append({
+                "OTIO_SCHEMA": "Clip.2", "name": f"t{t}c{i}", "metadata": {}, "source_range": tr(int(rng.integers(0, 6)), dur),
+                "effects": effects(0.3),
+                "media_references": {"DEFAULT_MEDIA": {"OTIO_SCHEMA": "ExternalReference.1", "name": "", "metadata": {},
+                                                       "available_range": tr(0, 40) if rng.random() < 0.8 else
+                                                       {"OTIO_SCHEMA": "TimeRange.1", "start_time": {"OTIO_SCHEMA": "RationalTime.1", "rate": 30.0, "value": 0.0},
+                                                        "duration": {"OTIO_SCHEMA": "RationalTime.1", "rate": 30.0, "value": 50.0}},
+                                                       "target_url": f"synthetic://m{t}_{i % 3}.png"}},
+                "active_media_reference_key": "DEFAULT_MEDIA"})
+        if rng.random() < 0.15:  # a transition that opens or closes the track (nothing on its far side)
+            x = {"OTIO_SCHEMA": "Transition.1", "name": "edge", "metadata": {}, "transition_type": "toucan:Dissolve", "in_offset": rt(2), "out_offset": rt(2)}
+            children.insert(0, x) if rng.random() < 0.5 else children.append(x)
+        track = {"OTIO_SCHEMA": "Track.1", "name": f"V{t}", "kind": "Video", "metadata": {}, "effects": effects(0.15), "children": children}
+        if rng.random() < 0.2:  # a trimmed track
+            track["source_range"] = tr(int(rng.integers(0, 8)), int(rng.integers(5, 30)))
+        tracks.append(track)
+    tracks.insert(int(rng.integers(0, len(tracks) + 1)),
+                  {"OTIO_SCHEMA": "Track.1", "name": "A1", "kind": "Audio", "metadata": {}, "effects": [], "children": []})
+    return {"OTIO_SCHEMA": "Timeline.1", "name": "random", "metadata": {},
+            "tracks": {"OTIO_SCHEMA": "Stack.1", "name": "tracks", "metadata": {}, "effects": effects(0.15), "children": tracks}}
+
+
+@pytest.mark.parametrize("seed", range(160))
+def test_random_timelines_build_the_oracles_node_trees(host, seed):
+    """ImageGraph::exec of the C++ host against the oracle's restatement of lib/toucanRender/ImageGraph.cpp:144-466 on
+    random timelines: for every frame the same node tree (which clip, which transition and its progress, every effect's
+    resolved parameters, time warps applied at clip / track / stack level, gaps, skipped audio tracks and unknown effects)."""
+    import numpy as np
+
+    from oracle import graph as G
+    from toucan_b200 import render
+
+    rng = np.random.default_rng(7000 + seed)
+    doc = _random_timeline(rng)
+    still = np.zeros((6, 8, 4), np.uint8)
+    tl = render.Timeline(json_doc=doc, directory="/nonexistent")
+    urls = sorted({c["media_references"]["DEFAULT_MEDIA"]["target_url"] for t in doc["tracks"]["children"] for c in t["children"] if c["OTIO_SCHEMA"] == "Clip.2"})
+    for u in urls:
+        tl.set_media(tl.media_path(u), still)
+    tl.prepare()
+    otl = G.Timeline(doc)
+    og = G.ImageGraph(otl, lambda p: still)
+    info = tl.info()
+    times = otl.frames()
+    assert info["frames"] == len(times)
+    for t in times:
+        want = G.describe_tree(og.exec(t))
+        got = tl.describe(host, t.value).rstrip("\n").split("\n")
+        assert got == want, f"seed {seed} @ {t.value}:\n" + "\n".join(got) + "\n--- oracle ---\n" + "\n".join(want)
+    tl.close()

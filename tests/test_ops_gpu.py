@@ -754,3 +754,17 @@ def test_crop_and_transitions_random_geometries(T, seed):
         pos = (int(rng.integers(-20, w + 10)), int(rng.integers(-20, h + 10)))
         size = (int(rng.integers(1, w + 30)), int(rng.integers(1, h + 30)))
         assert_exact(T.crop(da, pos, size), O.crop(a, pos, size), f"crop {pos} {size} " + what)
+
+
+@pytest.mark.parametrize("dt", NP_TYPES)
+def test_chains_of_mirrorings_only(T, dt):
+    """Flip + Flip (cancels: the copy each node makes), Flip + Flop (a copy read backwards along both axes), with and without a
+    pointwise step between them -- found by the random timelines: the chain entry point refused chains without a pointwise step."""
+    from toucan_b200 import ops
+
+    src = rand_img(37, 23, dt, 123)
+    d = to_dev(src)
+    assert_exact(ops.pointwise_chain(d, [("flip",), ("flip",)]), src, "flip flip")
+    assert_exact(ops.pointwise_chain(d, [("flop",), ("flop",)]), src, "flop flop")
+    assert_exact(ops.pointwise_chain(d, [("flip",), ("flop",)]), O.flop(O.flip(src)), "flip flop")
+    assert_exact(ops.pointwise_chain(d, [("flip",), ("invert",), ("flop",)]), O.flop(O.invert(O.flip(src))), "flip invert flop")

@@ -445,3 +445,63 @@ def test_node_timers_report_device_time_per_node_label(cuda):
     assert sum(int(v[0]) for k, v in rows.items() if k.startswith("node chain")) == info["frames"], report
     assert render.node_timers_report().strip() == ""  # the report resets the totals
     tl.close()
+
+
+@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("fusion", [True, False])
+def test_random_timelines_render_like_the_oracle(cuda, host, seed, fusion):
+    """Random timelines (tests/test_host_graph.py::_random_timeline restricted to effects whose output moves smoothly with their
+    input) over random float32 stills, every frame through the C++ host + CUDA path -- fused chains and node by node -- against
+    the oracle's render of the same document.  Float storage: no re-quantisation to amplify a rounding difference."""
+    from tests.test_host_graph import _random_timeline
+    from toucan_b200 import render
+
+    rng = np.random.default_rng(9000 + seed)
+    doc = _random_timeline(rng)
+
+    def tame(effects):
+        out = []
+        for e in effects:
+            n = e.get("effect_name", "")
+            if n in ("toucan:Pow", "toucan:ColorMap", "toucan:UnsharpMask", "toucan:Rotate"):
+                e = dict(e, effect_name="toucan:Invert", name="toucan:Invert", metadata={})
+            out.append(e)
+        return out
+
+    doc["tracks"]["effects"] = tame(doc["tracks"]["effects"])
+    stills = {}
+    for t in doc["tracks"]["children"]:
+        t["effects"] = tame(t["effects"])
+        for c in t["children"]:
+            if c["OTIO_SCHEMA"] == "Clip.2":
+                c["effects"] = tame(c["effects"])
+                u = c["media_references"]["DEFAULT_MEDIA"]["target_url"]
+                if u not in stills:
+                    a = rng.random((30, 48, 4), dtype=np.float32)
+                    a[..., 3] = np.where(rng.random((30, 48)) < 0.3, 1.0, a[..., 3])
+                    stills[u] = np.ascontiguousarray(a)
+    render.set_fusion(fusion)
+    try:
+        tl = render.Timeline(json_doc=doc, directory="/nonexistent")
+        by_path = {}
+        for u, a in stills.items():
+            by_path[tl.media_path(u)] = a
+            tl.set_media(tl.media_path(u), a)
+        tl.prepare()
+        otl = G.Timeline(doc)
+        otl.dir = "/nonexistent"
+        og = G.ImageGraph(otl, lambda p: by_path[p])
+        for t in otl.frames():
+            want = og.render(t)
+            got = tl.render(host, t.value, max_bytes=64 * 64 * 16)
+            if want is None or want.size == 0:
+                assert got.size == 0, f"seed {seed} @ {t.value}: oracle has no image"
+                continue
+            assert got.shape == want.shape and got.dtype == want.dtype, (seed, t.value, got.shape, want.shape, got.dtype, want.dtype)
+            d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+            # (a frame over the u8 Fill through CompNode's fit path takes the background's 8-bit type: +-1 code after the resize)
+            bar = 2e-5 if got.dtype == np.float32 else 1.0
+            assert float(d.max()) <= bar, f"seed {seed} @ {t.value}: max abs diff {d.max():.3e}"
+        tl.close()
+    finally:
+        render.set_fusion(True)

@@ -1382,10 +1382,11 @@ int tc_pointwise_chain(const tc_image* dst, const tc_image* src, const tc_chain_
         op.flipx = flipx;
         op.flipy = flipy;
         op.c = steps;
-        if (0 == steps.n) return flipx && flipy ? fail(TC_ERR_UNSUPPORTED, "tc_pointwise_chain: a chain of flips only") : (flipy ? tc_flip(dst, src, s) : tc_flop(dst, src, s));
-        return launch(op, dst, s);
+        if (0 == steps.n && !(flipx && flipy)) return flipy ? tc_flip(dst, src, s) : tc_flop(dst, src, s);
+        return launch(op, dst, s); // (no steps: Flip + Flop, a copy read backwards along both axes)
     }
-    if (0 == steps.n) return fail(TC_ERR_INVALID, "tc_pointwise_chain: empty chain");
+    // nodes whose mirrorings cancel (Flip, Flip) and nothing else: the copy each of them makes
+    if (0 == steps.n) return tc_convert(dst, src, s);
     ChainOp op;
     memset(&op, 0, sizeof(op));
     op.s = make_src(src, dst);

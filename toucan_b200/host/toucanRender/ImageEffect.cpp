@@ -249,6 +249,14 @@ namespace toucan
         else if (0 == strcmp(context, kOfxImageEffectContextFilter) && inputs.size() >= 1)
         {
             ImageSpec spec = inputs[0].spec();
+            if (spec.width <= 0 || spec.height <= 0)
+            {
+                // No image at this time (missing media, a read past the available range).  The reference would give a
+                // sized effect (Crop, Resize: "size" in the metadata) an output of that size with the empty input's ZERO
+                // channels and call the plug-in on it -- nothing defined comes out.  Here the absence propagates: an
+                // effect over no image yields no image (the oracle's choice as well), never an uninitialised frame.
+                return out;
+            }
             if (size.x > 0 && size.y > 0)
             {
                 spec.width = size.x;
@@ -261,6 +269,10 @@ namespace toucan
         else if (0 == strcmp(context, kOfxImageEffectContextTransition) && inputs.size() >= 2)
         {
             ImageSpec spec = inputs[0].spec();
+            if (spec.width <= 0 || spec.height <= 0)
+            {
+                return out; // no "from" image: no image (see the filter case)
+            }
             if (size.x > 0 && size.y > 0)
             {
                 spec.width = size.x;
