@@ -505,3 +505,59 @@ def test_random_timelines_render_like_the_oracle(cuda, host, seed, fusion):
         tl.close()
     finally:
         render.set_fusion(True)
+
+
+@pytest.mark.parametrize("seed", range(30))
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float16])
+def test_random_timelines_of_exact_effects_are_bit_exact(cuda, host, seed, dtype):
+    """The same random documents restricted to the effects north_star holds to bit-exactness (Invert, Flip, Flop, Crop, Wipes,
+    and Dissolve / premult + over, which the kernels reproduce to the bit including their typed temporaries) over 8 / 16-bit and
+    half stills: every frame identical to the oracle's, fused chains and all."""
+    from tests.test_host_graph import _random_timeline
+    from toucan_b200 import render
+
+    rng = np.random.default_rng(11000 + seed)
+    doc = _random_timeline(rng)
+    exact = ("toucan:Invert", "toucan:Flip", "toucan:Flop", "toucan:Crop", "nonesuch:Effect", "")
+
+    def tame(effects):
+        return [e if e.get("effect_name", "") in exact else dict(e, effect_name="toucan:Flop", name="toucan:Flop", metadata={}) for e in effects]
+
+    doc["tracks"]["effects"] = tame(doc["tracks"]["effects"])
+    stills = {}
+    for t in doc["tracks"]["children"]:
+        t["effects"] = tame(t["effects"])
+        for c in t["children"]:
+            if c["OTIO_SCHEMA"] == "Clip.2":
+                c["effects"] = tame(c["effects"])
+                u = c["media_references"]["DEFAULT_MEDIA"]["target_url"]
+                if u not in stills:
+                    a = rng.random((30, 48, 4))
+                    a[..., 3] = np.where(rng.random((30, 48)) < 0.3, 1.0, a[..., 3])
+                    stills[u] = np.ascontiguousarray((a * 255).astype(np.uint8) if dtype == np.uint8 else (a * 65535).astype(np.uint16) if dtype == np.uint16 else a.astype(np.float16))
+    tl = render.Timeline(json_doc=doc, directory="/nonexistent")
+    by_path = {}
+    for u, a in stills.items():
+        by_path[tl.media_path(u)] = a
+        tl.set_media(tl.media_path(u), a)
+    tl.prepare()
+    otl = G.Timeline(doc)
+    otl.dir = "/nonexistent"
+    og = G.ImageGraph(otl, lambda p: by_path[p])
+    for t in otl.frames():
+        want = og.render(t)
+        got = tl.render(host, t.value, max_bytes=64 * 64 * 16)
+        if want is None or want.size == 0:
+            assert got.size == 0, f"seed {seed} @ {t.value}: oracle has no image"
+            continue
+        assert got.shape == want.shape and got.dtype == want.dtype, (seed, t.value, got.shape, want.shape, got.dtype, want.dtype)
+        tree = tl.describe(host, t.value)
+        if "toucan:Crop" in tree:
+            # a cropped (smaller) frame is fitted into the frame below it by CompNode: a Resize, +-1 code (tests/envelope.py: ordered codes)
+            from tests.envelope import ordered
+
+            assert int(np.abs(ordered(got) - ordered(want)).max()) <= 1, f"seed {seed} @ {t.value}\n" + tree
+            continue
+        same = got.view(np.uint16) == want.view(np.uint16) if got.dtype == np.float16 else got == want
+        assert bool(same.all()), f"seed {seed} @ {t.value}: {int((~same).sum())} samples differ\n" + tree
+    tl.close()
