@@ -768,3 +768,68 @@ def test_chains_of_mirrorings_only(T, dt):
     assert_exact(ops.pointwise_chain(d, [("flop",), ("flop",)]), src, "flop flop")
     assert_exact(ops.pointwise_chain(d, [("flip",), ("flop",)]), O.flop(O.flip(src)), "flip flop")
     assert_exact(ops.pointwise_chain(d, [("flip",), ("invert",), ("flop",)]), O.flop(O.invert(O.flip(src))), "flip invert flop")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_pointwise_chains_equal_the_nodes_one_by_one(seed):
+    """Random chains (2 - 8 steps of every chainable kind, optionally behind a Blur / UnsharpMask head) over random sizes and
+    storage types: the fused launch is bit-identical to the per-node kernels run in sequence."""
+    from toucan_b200 import ops
+
+    rng = np.random.default_rng(5000 + seed)
+    for _ in range(6):
+        dt = NP_TYPES[int(rng.integers(0, 4))]
+        w, h = int(rng.integers(1, 200)), int(rng.integers(1, 120))
+        pool = [("invert",), ("pow", float(rng.choice([2.0, 3.0, 2.2, 0.45]))), ("saturate", float(rng.uniform(0, 2))),
+                ("color_map", str(rng.choice(["plasma", "viridis", "no such map"]))), ("premult",), ("unpremult",), ("flip",), ("flop",),
+                ("over_fill", tuple(float(v) for v in rng.random(4)), bool(rng.integers(0, 2))),
+                ("color_convert", "Linear Rec.709 (sRGB)", str(rng.choice(["ACEScct", "sRGB - Texture", "no such space"])), bool(rng.integers(0, 2)))]
+        steps = [pool[int(rng.integers(0, len(pool)))] for _ in range(int(rng.integers(2, 8)))]
+        src = rand_img(w, h, dt, int(rng.integers(0, 1 << 30)), alpha="mixed")
+        got = ops.pointwise_chain(to_dev(src), steps)
+        seq = to_dev(src)
+        for st in steps:
+            seq = _single(ops, seq, st)
+        assert_exact(got, to_host(seq), f"{np.dtype(dt).name} {(w, h)} {steps}")
+        # a convolution node at the head: the simple followers ride in its epilogue, anything else runs over a temporary
+        head = ("blur", float(rng.choice([2.0, 10.0, 20.0]))) if rng.random() < 0.5 else ("unsharp", "gaussian", 3.0, 0.7, 0.0)
+        got = ops.pointwise_chain(to_dev(src), [head] + steps)
+        seq = ops.blur(to_dev(src), head[1]) if head[0] == "blur" else ops.unsharp_mask(to_dev(src), head[1], head[2], head[3], head[4])
+        for st in steps:
+            seq = _single(ops, seq, st)
+        assert_exact(got, to_host(seq), f"{np.dtype(dt).name} {(w, h)} {[head] + steps}")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_stacks_against_the_oracle(T, seed):
+    """tc_stack_f32 on random stacks: 1 - 14 layers, each a plain, blurred or dissolving (equal or different blurs on its two
+    inputs) float frame, random frame sizes from a few pixels (the fallback kernel) to several tiles (the TMA kernel)."""
+    rng = np.random.default_rng(6000 + seed)
+    w, h = int(rng.integers(3, 400)), int(rng.integers(3, 260))
+    if seed % 3 == 0:
+        w, h = (w + 63) // 64 * 64, (h + 23) // 24 * 24  # whole tiles
+    n = int(rng.integers(1, 15))
+    imgs = [rand_img(w, h, np.float32, int(rng.integers(0, 1 << 30)), alpha="mixed") for _ in range(min(2 * n, 12))]
+    layers, spec = [], []
+    for i in range(n):
+        a = imgs[int(rng.integers(0, len(imgs)))]
+        kind = int(rng.integers(0, 4))
+        ra = float(rng.choice([0.0, 4.0, 10.0, 20.0]))
+        if kind == 0:
+            spec.append((a, None, ra, 0.0, 0.0))
+        else:
+            b = imgs[int(rng.integers(0, len(imgs)))]
+            rb = ra  # (a Dissolve of differently blurred inputs is not a fusable layer: the host leaves it to the node path)
+            spec.append((a, b, ra, rb, float(rng.choice([0.0, 0.25, 0.5, 1.0]))))
+    bgcol = [float(v) for v in rng.random(4)]
+    dev = {id(a): to_dev(a) for a in imgs}
+    for a, b, ra, rb, v in spec:
+        layers.append((dev[id(a)], dev[id(b)] if b is not None else None, ra, rb, v))
+    got = T.stack_f32(w, h, bgcol, layers)
+    acc = O.fill(w, h, bgcol, O.F32)
+    for a, b, ra, rb, v in spec:
+        x = O.blur(a, ra) if ra > 0 else a
+        if b is not None:
+            x = O.dissolve(x, O.blur(b, rb) if rb > 0 else b, v)
+        acc = O.comp(x, acc, True)
+    assert_close(got, acc, f"stack {(w, h)} {[(ra, rb, v, b is not None) for a, b, ra, rb, v in spec]}")
