@@ -5,6 +5,7 @@
 // tiles are staged with clamped coordinates rather than zero-filling bulk copies.
 //
 // Tolerance op (<= 1e-5 abs / +-1 LSB), so FMA contraction is allowed in this file.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -399,6 +400,209 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict_
     }
 }
 
+// k_gauss_march: Blur of float32 frames at large radii (R >= 6) as a MARCH down the frame (round 2).  A tile of k_gauss_tma
+// stages and row-filters TH + 2R rows for TH rows of output -- 42 for 24 at R = 9, three quarters more than it keeps.  Here a
+// CTA owns a strip of 64 columns and a chunk of rows and walks down it in bands of 24 source rows: each band is staged once (TMA,
+// two buffers), row-filtered once into the warp's private RING of 24 + 2R row slots, and the column pass then emits the 24 rows
+// whose window the band completed.  Per output pixel: 2 (2R + 1) taps instead of (2 + 2R / 24)(2R + 1), 57 % of the staged
+// bytes, the same tap order as k_gauss_tma (bit-identical frames).  Frame edges: the left / right surround is patched into the
+// landed band like k_gauss_tma does; rows above / below the frame are never filtered -- the column pass clamps its row index
+// into the ring.
+template <int R, int TH_ = 24, int NBUF_ = 2>
+struct GmTile {
+    static constexpr int TH = TH_, PX = TH_ / 4, NBUF = NBUF_;
+    static constexpr int RING = TH + 2 * R;
+    static constexpr int MP = ST_HB + 1;
+    using G = GtTile<R, TC_F32, 2>;             // box width / pitch of a staged row
+    static constexpr int BAND_BYTES = (TH * G::PITCH + 127) / 128 * 128;
+    static constexpr int RING_BYTES = 8 * RING * MP * 16;
+    static constexpr size_t SMEM = NBUF * BAND_BYTES + RING_BYTES + 64;
+    static constexpr unsigned TILE_BYTES = (unsigned)(TH * G::PITCH);
+};
+
+struct GmParams {
+    int w, h, rows_per_chunk;
+    ConvParams c;
+    EpiSteps epi;
+    alignas(64) CUtensorMap map;
+};
+
+template <int R, bool EPI, int TH_, int NBUF_>
+__global__ void __launch_bounds__(ST_THREADS, 2) k_gauss_march(void* __restrict__ dstp, const __grid_constant__ GmParams Q)
+{
+    using T = GmTile<R, TH_, NBUF_>;
+    constexpr int NBUF = NBUF_;
+    using G = typename T::G;
+    constexpr int PX = T::PX, TH = T::TH, RING = T::RING;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* buf0 = smem_raw;
+    unsigned char* buf1 = smem_raw + (NBUF - 1) * T::BAND_BYTES; // (== buf0 with one staging buffer)
+    float4* rings = (float4*)(smem_raw + NBUF * T::BAND_BYTES);
+    uint64_t* full = (uint64_t*)(smem_raw + NBUF * T::BAND_BYTES + T::RING_BYTES); // [2]
+    int* released = (int*)(full + 2);                                           // [2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x0 = blockIdx.x * ST_TW;
+    const int cy0 = blockIdx.y * Q.rows_per_chunk, cy1 = min(cy0 + Q.rows_per_chunk, Q.h);
+    // band b holds source rows [s0 + TH b, s0 + TH (b + 1)); after it the output rows [s0 - R + TH b, s0 - R + TH (b + 1)) are complete
+    const int s0 = cy0 - R;
+    const int nb = (cy1 - cy0 + 2 * R + TH - 1) / TH;
+
+    auto issue = [&](int s, int band) {
+        mbar_expect_tx(&full[s], T::TILE_BYTES);
+        tma_load_tile(s ? buf1 : buf0, &Q.map, (x0 - G::RA) * (G::B / G::ELEM), s0 + band * TH, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        released[0] = released[1] = 0;
+        mbar_init_fence();
+        issue(0, 0);
+        if (NBUF > 1 && nb > 1) issue(1, 1);
+    }
+    __syncthreads();
+
+    float g[2 * R + 1];
+#pragma unroll
+    for (int t = 0; t <= 2 * R; ++t) {
+        const int sft = t - R + Q.c.R;
+        g[t] = (sft >= 0 && sft <= 2 * Q.c.R) ? Q.c.g[sft] : 0.0f;
+    }
+    float4* ring = rings + warp * (RING * T::MP);
+    const int col = lane % ST_HB, seg = lane / ST_HB;
+    const bool xborder = x0 - G::RA < 0 || x0 - G::RA + G::BW > Q.w;
+    const int x = x0 + warp * ST_HB + col;
+
+    for (int band = 0; band < nb; ++band) {
+        const int s = NBUF > 1 ? (band & 1) : 0;
+        unsigned char* in = s ? buf1 : buf0;
+        const int r_first = s0 + band * TH; // first source row of the band
+        mbar_wait(&full[s], (NBUF > 1 ? (band >> 1) : band) & 1);
+        if (xborder) {
+            // columns outside the frame <- the clamped in-frame column of the same row (TMA filled them with zeros)
+            for (int c = threadIdx.x; c < TH * G::BW; c += ST_THREADS) {
+                const int r = c / G::BW, cc = c - r * G::BW;
+                const int sx = x0 - G::RA + cc;
+                const int cx = min(max(sx, 0), Q.w - 1);
+                if (cx != sx)
+                    *reinterpret_cast<uint4*>(in + r * G::PITCH + cc * 16) = *reinterpret_cast<const uint4*>(in + r * G::PITCH + (cx - (x0 - G::RA)) * 16);
+            }
+            __syncthreads();
+        }
+        __syncwarp();
+        // ---- rows: lane = source row of the band (rows outside the frame are skipped), 8 outputs from 8 + 2R reads
+        {
+            const int row = min(lane, TH - 1);
+            const int r = r_first + row;
+            const uint4* p = reinterpret_cast<const uint4*>(in + row * G::PITCH + (warp * ST_HB) * 16);
+            float4 o[ST_HB];
+#pragma unroll
+            for (int j = 0; j < ST_HB + 2 * R + G::D; ++j) {
+                const uint4 v = p[j];
+                const float4 px = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+#pragma unroll
+                for (int k = 0; k < ST_HB; ++k) {
+                    const int t = j - k - G::D;
+                    if (t == 0) o[k] = mul4p(g[0], px);
+                    else if (t > 0 && t <= 2 * R) o[k] = fma4p(g[t], px, o[k]);
+                }
+            }
+            if (lane < TH && r >= 0 && r < Q.h) {
+                float4* m = ring + (((band * TH + row) % RING) * T::MP);
+#pragma unroll
+                for (int k = 0; k < ST_HB; ++k) m[k] = o[k];
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && release_count(&released[s]) == ST_THREADS / 32 - 1) {
+            released[s] = 0;
+            if (band + NBUF < nb) {
+                fence_proxy_async();
+                issue(s, band + NBUF);
+            }
+        }
+        // ---- columns: lane = column x 4 segments of 6 rows of the 24 output rows this band completed
+        const int o_first = r_first - R;                 // first completed output row
+        const int y = o_first + seg * PX;
+        // ring slot of source row q: (q - s0) mod RING; the window of output row y + k is source rows y + k - R .. y + k + R
+        float4 f[PX];
+        const bool yedge = o_first - R < 0 || o_first + TH + R > Q.h;
+        if (!yedge) {
+            int slot = (y - R - s0) % RING;
+            const float4* base = ring + col;
+#pragma unroll
+            for (int j = 0; j < PX + 2 * R; ++j) {
+                const float4 q = base[slot * T::MP];
+                slot = slot + 1 == RING ? 0 : slot + 1;
+#pragma unroll
+                for (int k = 0; k < PX; ++k) {
+                    const int t = j - k;
+                    if (t == 0) f[k] = mul4p(g[0], q);
+                    else if (t > 0 && t <= 2 * R) f[k] = fma4p(g[t], q, f[k]);
+                }
+            }
+        } else {
+            // a window that reaches over the top / bottom of the frame: the row index clamps (the clamped rows are still in the ring)
+            const float4* base = ring + col;
+#pragma unroll
+            for (int j = 0; j < PX + 2 * R; ++j) {
+                const int qrow = min(max(y - R + j, 0), Q.h - 1);
+                const float4 q = base[((qrow - s0) % RING) * T::MP];
+#pragma unroll
+                for (int k = 0; k < PX; ++k) {
+                    const int t = j - k;
+                    if (t == 0) f[k] = mul4p(g[0], q);
+                    else if (t > 0 && t <= 2 * R) f[k] = fma4p(g[t], q, f[k]);
+                }
+            }
+        }
+        if (x < Q.w) {
+#pragma unroll
+            for (int k = 0; k < PX; ++k)
+                if (y + k >= cy0 && y + k < cy1) store_px(dstp, TC_F32, (size_t)(y + k) * Q.w + x, EPI ? epi_apply<TC_F32>(Q.epi, f[k]) : f[k]);
+        }
+        __syncwarp(); // the ring is rewritten by the next band's row pass
+    }
+}
+
+template <int R, bool EPI>
+static int launch_gauss_march(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi)
+{
+    // 32-row bands (every lane of the row pass has a row, 8 output rows per lane of the column pass) with ONE staging buffer
+    // where that fits two CTAs per SM, which then cover each other's copies; else 24-row bands with two buffers
+    constexpr bool TALL = GmTile<R, 32, 1>::SMEM <= 113 * 1024;
+    using T = GmTile<R, TALL ? 32 : 24, TALL ? 1 : 2>;
+    using G = typename T::G;
+    static_assert(T::SMEM <= 113 * 1024, "two CTAs per SM");
+    GmParams Q;
+    Q.w = dst->w;
+    Q.h = dst->h;
+    Q.c = P;
+    if (EPI) Q.epi = *epi;
+    else Q.epi.n = 0;
+    // chunks of rows: two waves of two CTAs per SM where the frame allows, at least 8 bands per chunk (2R warm-up rows per chunk)
+    const int strips = (dst->w + ST_TW - 1) / ST_TW;
+    int chunks = std::max(1, 4 * num_sms() / strips);
+    chunks = std::min(chunks, std::max(1, dst->h / (8 * T::TH)));
+    Q.rows_per_chunk = ((dst->h + chunks - 1) / chunks + T::TH - 1) / T::TH * T::TH;
+    const unsigned long long pitch = (unsigned long long)src->w * 16;
+    int e = tensor_map_2d(src->data, 8, pitch / 8, (unsigned long long)src->h, pitch, (unsigned)(G::BW * 2), (unsigned)T::TH, &Q.map);
+    if (e != TC_OK) return e;
+    e = ensure_dynamic_smem((const void*)k_gauss_march<R, EPI, T::TH, T::NBUF>, T::SMEM);
+    if (e != TC_OK) return e;
+    const dim3 grid(strips, (dst->h + Q.rows_per_chunk - 1) / Q.rows_per_chunk);
+    k_gauss_march<R, EPI, T::TH, T::NBUF><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "k_gauss_march launch");
+}
+static bool gauss_march_on()
+{
+    static const bool on = [] {
+        const char* e = getenv("TOUCAN_CONV_MARCH");
+        return !(e && *e == '0');
+    }();
+    return on;
+}
+
 // Generic fallback for very wide kernels (R > 12): 32 x 32 tiles, one tap per shared-memory read.
 template <bool UNSHARP>
 __global__ void __launch_bounds__(CONV_THREADS) k_gauss_wide(const Img src, const Img dst, const __grid_constant__ ConvParams P)
@@ -553,6 +757,9 @@ static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const Conv
 template <int R, bool UNSHARP, bool EPI = false>
 static int launch_gauss_tma_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi = nullptr)
 {
+    if constexpr (!UNSHARP && R >= 6 && R <= 9) {
+        if (src->type == TC_F32 && gauss_march_on() && dst->h >= 64) return launch_gauss_march<R, EPI>(dst, src, P, st, epi);
+    }
     switch (src->type) {
     case TC_U8: return launch_gauss_tma<R, TC_U8, UNSHARP, EPI>(dst, src, P, st, epi);
     case TC_U16: return launch_gauss_tma<R, TC_U16, UNSHARP, EPI>(dst, src, P, st, epi);
