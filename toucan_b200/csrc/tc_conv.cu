@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict_
     }
 }
 
-// k_gauss_march: Blur of float32 frames at large radii (R >= 6) as a MARCH down the frame (round 2).  A tile of k_gauss_tma
+// k_gauss_march: Blur at large radii (R = 6 .. 9 live taps per side) as a MARCH down the frame (round 2).  A tile of k_gauss_tma
 // stages and row-filters TH + 2R rows for TH rows of output -- 42 for 24 at R = 9, three quarters more than it keeps.  Here a
 // CTA owns a strip of 64 columns and a chunk of rows and walks down it in bands of 24 source rows: each band is staged once (TMA,
 // two buffers), row-filtered once into the warp's private RING of 24 + 2R row slots, and the column pass then emits the 24 rows
@@ -408,12 +408,12 @@ __global__ void __launch_bounds__(ST_THREADS, OCC) k_gauss_tma(void* __restrict_
 // bytes, the same tap order as k_gauss_tma (bit-identical frames).  Frame edges: the left / right surround is patched into the
 // landed band like k_gauss_tma does; rows above / below the frame are never filtered -- the column pass clamps its row index
 // into the ring.
-template <int R, int TH_ = 24, int NBUF_ = 2>
+template <int R, int TYPE, int TH_ = 24, int NBUF_ = 2>
 struct GmTile {
     static constexpr int TH = TH_, PX = TH_ / 4, NBUF = NBUF_;
     static constexpr int RING = TH + 2 * R;
     static constexpr int MP = ST_HB + 1;
-    using G = GtTile<R, TC_F32, 2>;             // box width / pitch of a staged row
+    using G = GtTile<R, TYPE, 2>;               // box width / pitch / alignment of a staged row in the storage type
     static constexpr int BAND_BYTES = (TH * G::PITCH + 127) / 128 * 128;
     static constexpr int RING_BYTES = 8 * RING * MP * 16;
     static constexpr size_t SMEM = NBUF * BAND_BYTES + RING_BYTES + 64;
@@ -427,10 +427,10 @@ struct GmParams {
     alignas(64) CUtensorMap map;
 };
 
-template <int R, bool EPI, int TH_, int NBUF_>
+template <int R, int TYPE, bool EPI, int TH_, int NBUF_>
 __global__ void __launch_bounds__(ST_THREADS, 2) k_gauss_march(void* __restrict__ dstp, const __grid_constant__ GmParams Q)
 {
-    using T = GmTile<R, TH_, NBUF_>;
+    using T = GmTile<R, TYPE, TH_, NBUF_>;
     constexpr int NBUF = NBUF_;
     using G = typename T::G;
     constexpr int PX = T::PX, TH = T::TH, RING = T::RING;
@@ -461,11 +461,14 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_gauss_march(void* __restrict_
     }
     __syncthreads();
 
-    float g[2 * R + 1];
+    // taps centred on R; the row pass carries the load conversion's scale for integer storage (as in k_gauss_tma)
+    float g[2 * R + 1], gr[2 * R + 1];
+    const float in_scale = TYPE == TC_U8 ? 1.0f / 255.0f : (TYPE == TC_U16 ? 1.0f / 65535.0f : 1.0f);
 #pragma unroll
     for (int t = 0; t <= 2 * R; ++t) {
         const int sft = t - R + Q.c.R;
         g[t] = (sft >= 0 && sft <= 2 * Q.c.R) ? Q.c.g[sft] : 0.0f;
+        gr[t] = g[t] * in_scale;
     }
     float4* ring = rings + warp * (RING * T::MP);
     const int col = lane % ST_HB, seg = lane / ST_HB;
@@ -483,8 +486,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_gauss_march(void* __restrict_
                 const int r = c / G::BW, cc = c - r * G::BW;
                 const int sx = x0 - G::RA + cc;
                 const int cx = min(max(sx, 0), Q.w - 1);
-                if (cx != sx)
-                    *reinterpret_cast<uint4*>(in + r * G::PITCH + cc * 16) = *reinterpret_cast<const uint4*>(in + r * G::PITCH + (cx - (x0 - G::RA)) * 16);
+                if (cx != sx) {
+                    const unsigned char* from = in + r * G::PITCH + (cx - (x0 - G::RA)) * G::B;
+                    unsigned char* to = in + r * G::PITCH + cc * G::B;
+                    if (G::B == 16) *reinterpret_cast<uint4*>(to) = *reinterpret_cast<const uint4*>(from);
+                    else if (G::B == 8) *reinterpret_cast<uint2*>(to) = *reinterpret_cast<const uint2*>(from);
+                    else *reinterpret_cast<unsigned*>(to) = *reinterpret_cast<const unsigned*>(from);
+                }
             }
             __syncthreads();
         }
@@ -493,17 +501,22 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_gauss_march(void* __restrict_
         {
             const int row = min(lane, TH - 1);
             const int r = r_first + row;
-            const uint4* p = reinterpret_cast<const uint4*>(in + row * G::PITCH + (warp * ST_HB) * 16);
+            const uint4* p = reinterpret_cast<const uint4*>(in + row * G::PITCH + (warp * ST_HB) * G::B);
+            constexpr int NVI = (ST_HB + 2 * R + G::D + G::VPX - 1) / G::VPX; // 16-byte reads per row item
             float4 o[ST_HB];
 #pragma unroll
-            for (int j = 0; j < ST_HB + 2 * R + G::D; ++j) {
-                const uint4 v = p[j];
-                const float4 px = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+            for (int v = 0; v < NVI; ++v) {
+                float4 px[G::VPX];
+                unpack_vec<TYPE>(p[v], px);
 #pragma unroll
-                for (int k = 0; k < ST_HB; ++k) {
-                    const int t = j - k - G::D;
-                    if (t == 0) o[k] = mul4p(g[0], px);
-                    else if (t > 0 && t <= 2 * R) o[k] = fma4p(g[t], px, o[k]);
+                for (int e = 0; e < G::VPX; ++e) {
+                    const int j = v * G::VPX + e;
+#pragma unroll
+                    for (int k = 0; k < ST_HB; ++k) {
+                        const int t = j - k - G::D;
+                        if (t == 0) o[k] = mul4p(gr[0], px[e]);
+                        else if (t > 0 && t <= 2 * R) o[k] = fma4p(gr[t], px[e], o[k]);
+                    }
                 }
             }
             if (lane < TH && r >= 0 && r < Q.h) {
@@ -558,19 +571,19 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_gauss_march(void* __restrict_
         if (x < Q.w) {
 #pragma unroll
             for (int k = 0; k < PX; ++k)
-                if (y + k >= cy0 && y + k < cy1) store_px(dstp, TC_F32, (size_t)(y + k) * Q.w + x, EPI ? epi_apply<TC_F32>(Q.epi, f[k]) : f[k]);
+                if (y + k >= cy0 && y + k < cy1) store_px(dstp, TYPE, (size_t)(y + k) * Q.w + x, EPI ? epi_apply<TYPE>(Q.epi, f[k]) : f[k]);
         }
         __syncwarp(); // the ring is rewritten by the next band's row pass
     }
 }
 
-template <int R, bool EPI>
+template <int R, int TYPE, bool EPI>
 static int launch_gauss_march(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi)
 {
     // 32-row bands (every lane of the row pass has a row, 8 output rows per lane of the column pass) with ONE staging buffer
     // where that fits two CTAs per SM, which then cover each other's copies; else 24-row bands with two buffers
-    constexpr bool TALL = GmTile<R, 32, 1>::SMEM <= 113 * 1024;
-    using T = GmTile<R, TALL ? 32 : 24, TALL ? 1 : 2>;
+    constexpr bool TALL = GmTile<R, TYPE, 32, 1>::SMEM <= 113 * 1024;
+    using T = GmTile<R, TYPE, TALL ? 32 : 24, TALL ? 1 : 2>;
     using G = typename T::G;
     static_assert(T::SMEM <= 113 * 1024, "two CTAs per SM");
     GmParams Q;
@@ -584,13 +597,13 @@ static int launch_gauss_march(const tc_image* dst, const tc_image* src, const Co
     int chunks = std::max(1, 4 * num_sms() / strips);
     chunks = std::min(chunks, std::max(1, dst->h / (8 * T::TH)));
     Q.rows_per_chunk = ((dst->h + chunks - 1) / chunks + T::TH - 1) / T::TH * T::TH;
-    const unsigned long long pitch = (unsigned long long)src->w * 16;
-    int e = tensor_map_2d(src->data, 8, pitch / 8, (unsigned long long)src->h, pitch, (unsigned)(G::BW * 2), (unsigned)T::TH, &Q.map);
+    const unsigned long long pitch = (unsigned long long)src->w * G::B;
+    int e = tensor_map_2d(src->data, G::ELEM, pitch / G::ELEM, (unsigned long long)src->h, pitch, (unsigned)(G::BW * G::B / G::ELEM), (unsigned)T::TH, &Q.map);
     if (e != TC_OK) return e;
-    e = ensure_dynamic_smem((const void*)k_gauss_march<R, EPI, T::TH, T::NBUF>, T::SMEM);
+    e = ensure_dynamic_smem((const void*)k_gauss_march<R, TYPE, EPI, T::TH, T::NBUF>, T::SMEM);
     if (e != TC_OK) return e;
     const dim3 grid(strips, (dst->h + Q.rows_per_chunk - 1) / Q.rows_per_chunk);
-    k_gauss_march<R, EPI, T::TH, T::NBUF><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
+    k_gauss_march<R, TYPE, EPI, T::TH, T::NBUF><<<grid, ST_THREADS, T::SMEM, st>>>(dst->data, Q);
     count_launch();
     return check_cuda(cudaGetLastError(), "k_gauss_march launch");
 }
@@ -758,7 +771,14 @@ template <int R, bool UNSHARP, bool EPI = false>
 static int launch_gauss_tma_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi = nullptr)
 {
     if constexpr (!UNSHARP && R >= 6 && R <= 9) {
-        if (src->type == TC_F32 && gauss_march_on() && dst->h >= 64) return launch_gauss_march<R, EPI>(dst, src, P, st, epi);
+        if (gauss_march_on() && dst->h >= 64) {
+            switch (src->type) {
+            case TC_U8: return launch_gauss_march<R, TC_U8, EPI>(dst, src, P, st, epi);
+            case TC_U16: return launch_gauss_march<R, TC_U16, EPI>(dst, src, P, st, epi);
+            case TC_F16: return launch_gauss_march<R, TC_F16, EPI>(dst, src, P, st, epi);
+            default: return launch_gauss_march<R, TC_F32, EPI>(dst, src, P, st, epi);
+            }
+        }
     }
     switch (src->type) {
     case TC_U8: return launch_gauss_tma<R, TC_U8, UNSHARP, EPI>(dst, src, P, st, epi);
