@@ -583,7 +583,8 @@ static int launch_gauss_march(const tc_image* dst, const tc_image* src, const Co
     // 32-row bands (every lane of the row pass has a row, 8 output rows per lane of the column pass) with ONE staging buffer
     // where that fits two CTAs per SM, which then cover each other's copies; else 24-row bands with two buffers
     constexpr bool TALL = GmTile<R, TYPE, 32, 1>::SMEM <= 113 * 1024;
-    using T = GmTile<R, TYPE, TALL ? 32 : 24, TALL ? 1 : 2>;
+    constexpr bool TWO = GmTile<R, TYPE, 24, 2>::SMEM <= 113 * 1024;
+    using T = GmTile<R, TYPE, TALL ? 32 : 24, (TALL || !TWO) ? 1 : 2>;
     using G = typename T::G;
     static_assert(T::SMEM <= 113 * 1024, "two CTAs per SM");
     GmParams Q;
@@ -770,7 +771,7 @@ static int launch_gauss_tma(const tc_image* dst, const tc_image* src, const Conv
 template <int R, bool UNSHARP, bool EPI = false>
 static int launch_gauss_tma_t(const tc_image* dst, const tc_image* src, const ConvParams& P, cudaStream_t st, const EpiSteps* epi = nullptr)
 {
-    if constexpr (!UNSHARP && R >= 6 && R <= 9) {
+    if constexpr (!UNSHARP && R >= 6) {
         if (gauss_march_on() && dst->h >= 64) {
             switch (src->type) {
             case TC_U8: return launch_gauss_march<R, TC_U8, EPI>(dst, src, P, st, epi);
