@@ -668,8 +668,9 @@ for name, out in (("rotate", ops.rotate(src, 33.0)), ("resize_down", ops.resize(
 
 @pytest.mark.gpu
 def test_kernel_variants_behind_the_switches_agree(T, tmp_path):
-    """TOUCAN_ROTATE_TMA=0 (bounds-checked staging instead of the TMA copy) and TOUCAN_RESIZE_OCC=2 (the register-prefetch march)
-    change how pixels reach shared memory, not the arithmetic: identical frames.  TOUCAN_CONV_TMA=0 selects round 1's Blur kernel:
+    """TOUCAN_ROTATE_TMA=0 (bounds-checked staging instead of the TMA copy), TOUCAN_RESIZE_WP=0 (the march instead of the
+    warp-private kernel for float32 reductions) and TOUCAN_RESIZE_OCC=2 (its register-prefetch variant) change how pixels reach
+    shared memory and which warp filters them, not the arithmetic: identical frames.  TOUCAN_CONV_TMA=0 selects round 1's Blur kernel:
     same taps, within float rounding."""
     import os
     import subprocess
@@ -686,7 +687,7 @@ def test_kernel_variants_behind_the_switches_agree(T, tmp_path):
         return {l.split()[0]: (l.split()[1], float(l.split()[2])) for l in r.stdout.splitlines() if l and l.split()[0] in ("rotate", "resize_down", "resize_up", "blur")}
 
     base = run({})
-    alt = run({"TOUCAN_ROTATE_TMA": "0", "TOUCAN_RESIZE_OCC": "2", "TOUCAN_CONV_TMA": "0"})
+    alt = run({"TOUCAN_ROTATE_TMA": "0", "TOUCAN_RESIZE_OCC": "2", "TOUCAN_RESIZE_WP": "0", "TOUCAN_CONV_TMA": "0"})
     for k in ("rotate", "resize_down", "resize_up"):
         assert base[k][0] == alt[k][0], k
     assert abs(base["blur"][1] - alt["blur"][1]) <= 1e-6 * abs(base["blur"][1]), (base["blur"], alt["blur"])

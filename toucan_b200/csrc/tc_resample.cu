@@ -553,6 +553,283 @@ __global__ void __launch_bounds__(RM_THREADS, PF ? 2 : 3) k_resize_march(const I
     }
 }
 
+// Resize of float32 frames with warp-private rings (round 2, after k_gauss_march: the Blur march showed that a band staged by
+// TMA, filtered by warps that never meet at a CTA barrier, beats the same work behind barriers).  A CTA owns 64 destination
+// columns -- two sub-strips of 32, each with its own staged tile because a TMA box is at most 128 pixels wide -- and a chunk of
+// rows; a warp owns 8 of the columns END TO END:
+//   * bands of 16 source rows arrive by TMA (zero fill outside the frame; one staging buffer: the other CTA of the SM covers
+//     the copy), counted on an mbarrier, handed back through a shared-memory counter;
+//   * row pass: lane = (source row 0..15, half 0..1): the 4 outputs of one half of the warp's columns from their common span
+//     (expanded span x 4 weights, one broadcast read per pixel read), into the warp's PRIVATE ring of 32 row slots;
+//   * column pass: lane = (column 0..7, segment 0..3); a segment is a block of BRL consecutive destination rows filtered from
+//     their common span of ring rows with an expanded span x BRL weight matrix -- built per band by the warp from the cached
+//     tables, read as ONE broadcast per ring read (the eight lanes of a quarter warp share the segment);
+//   * frame edges are index arithmetic: the row pass of an edge strip clamps its (uniform) column index, rows outside the frame
+//     are never filtered, and a block whose windows reach over the top / bottom takes a tap-by-tap loop with a clamped row index.
+// Same weights and ascending-tap accumulation as the kernels above: identical frames for finite pixels.
+constexpr int WP_W = 64, WP_BAND = 16, WP_RING = 32, WP_RP = WP_RING + 1, WP_SPAN = 24, WP_WARPS = 8, WP_COLS = 8;
+
+struct ResizeWp {
+    int sw;       // staged columns of one 32-column sub-strip (allocation); the staged row pitch is sw | 1 pixels
+    int ch;       // destination rows per chunk
+    int xtaps, ytaps;
+    int stages;   // staging buffers (each two tiles): 2-4 with two CTAs per SM where they fit, else up to 4 with one CTA per SM
+};
+
+template <int BRL>
+static size_t resize_wp_smem(int sw, int stages)
+{
+    const size_t tile = (((size_t)WP_BAND * (sw | 1) * 16) + 127) / 128 * 128;
+    return (size_t)stages * 2 * tile + (size_t)WP_WARPS * WP_COLS * WP_RP * 16 + (size_t)(WP_W / RM_B) * WP_SPAN * 16 + (size_t)WP_WARPS * 4 * WP_SPAN * BRL * 4 + 64;
+}
+
+template <int BRL>
+__global__ void __launch_bounds__(RM_THREADS, 2) k_resize_wp(const Img src, const Img dst, const int* __restrict__ xf, const float* __restrict__ xw,
+                                                              const float* __restrict__ xt, const int* __restrict__ yf,
+                                                              const float* __restrict__ yw, const float* __restrict__ yt, const ResizeWp T,
+                                                              const __grid_constant__ CUtensorMap map)
+{
+    extern __shared__ __align__(128) unsigned char wp_smem[];
+    __shared__ int s_fxb[WP_W / RM_B], s_span[WP_W / RM_B], s_yend[RM_MAXBANDS], s_wsum[RM_WARPS];
+    const int swp = T.sw | 1;
+    const size_t tile_bytes_al = (((size_t)WP_BAND * swp * 16) + 127) / 128 * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t stage_bytes = 2 * tile_bytes_al;
+    float4* rings = reinterpret_cast<float4*>(wp_smem + (size_t)T.stages * stage_bytes);
+    float4* ring = rings + (size_t)warp * WP_COLS * WP_RP;                       // [8 columns][33]
+    float4* Wx = rings + (size_t)WP_WARPS * WP_COLS * WP_RP;                     // [16 blocks][WP_SPAN]
+    float* WyAll = reinterpret_cast<float*>(Wx + (WP_W / RM_B) * WP_SPAN);       // [8 warps][4 segments][WP_SPAN][BRL]
+    float* Wy = WyAll + (size_t)warp * 4 * WP_SPAN * BRL;
+    uint64_t* full = reinterpret_cast<uint64_t*>(WyAll + (size_t)WP_WARPS * 4 * WP_SPAN * BRL);
+    int* released = reinterpret_cast<int*>(full + 4);
+
+    const int x0 = blockIdx.x * WP_W, y0 = blockIdx.y * T.ch;
+    const int nx = min(WP_W, dst.w - x0), y1 = min(y0 + T.ch, dst.h);
+    // the two sub-strips: first staged column and staged width
+    const int xa0 = x0, xa1 = min(x0 + 31, dst.w - 1);
+    const int xb0 = min(x0 + 32, dst.w - 1), xb1 = min(x0 + 63, dst.w - 1);
+    const int fxa = xf[xa0], fxbb = xf[xb0];
+    const int cols_a = min(xf[xa1] + T.xtaps - fxa, T.sw), cols_b = min(xf[xb1] + T.xtaps - fxbb, T.sw);
+    const bool has_b = nx > 32;
+    const int r0 = yf[y0];
+    const int rlast = min(yf[y1 - 1] + T.ytaps, src.h);
+    const int nb = min((rlast - r0 + WP_BAND - 1) / WP_BAND, RM_MAXBANDS);
+    const unsigned tile_bytes = (unsigned)(WP_BAND * swp * 16);
+
+    auto issue = [&](int band) {
+        const int st = band % T.stages;
+        unsigned char* to = wp_smem + (size_t)st * stage_bytes;
+        mbar_expect_tx(&full[st], has_b ? 2 * tile_bytes : tile_bytes);
+        tma_load_tile(to, &map, 2 * fxa, r0 + band * WP_BAND, &full[st]);
+        if (has_b) tma_load_tile(to + tile_bytes_al, &map, 2 * fxbb, r0 + band * WP_BAND, &full[st]);
+    };
+    if (tid == 0) {
+        for (int st = 0; st < T.stages; ++st) {
+            mbar_init(&full[st], 1);
+            released[st] = 0;
+        }
+        mbar_init_fence();
+        for (int b = 0; b < T.stages && b < nb; ++b) issue(b);
+    }
+    // rings start as zeros: a block's expanded weights are zero outside an output's window, and zero times a stale slot must be zero
+    for (int i = tid; i < WP_WARPS * WP_COLS * WP_RP; i += RM_THREADS) rings[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // expanded x weights of the 16 blocks of 4 columns, relative to their sub-strip's tile
+    for (int i = tid; i < (WP_W / RM_B) * WP_SPAN; i += RM_THREADS) {
+        const int b = i / WP_SPAN, k = i - b * WP_SPAN;
+        float w[RM_B] = { 0.f, 0.f, 0.f, 0.f };
+        if (b * RM_B < nx) {
+            const int fb = xf[x0 + b * RM_B];
+#pragma unroll
+            for (int o = 0; o < RM_B; ++o) {
+                const int x = x0 + b * RM_B + o;
+                if (x < dst.w) {
+                    const int t = k - (xf[x] - fb);
+                    if (t >= 0 && t < T.xtaps && xt[x * 2 + 1] != 0.0f) w[o] = xw[(size_t)x * T.xtaps + t];
+                }
+            }
+        }
+        Wx[i] = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    if (tid < WP_W / RM_B) {
+        const int xa = min(x0 + tid * RM_B, dst.w - 1), xb = min(x0 + tid * RM_B + RM_B - 1, dst.w - 1);
+        const bool in_b = tid >= 8;
+        const int base = in_b ? fxbb : fxa, cols = in_b ? cols_b : cols_a;
+        const int fb = min(xf[xa] - base, max(cols - 1, 0));
+        s_fxb[tid] = fb;
+        s_span[tid] = max(min(min(xf[xb] + T.xtaps - xf[xa], WP_SPAN), cols - fb), 0);
+    }
+    // destination rows complete after each band of 16 source rows (see k_resize_march)
+    s_yend[tid] = 0;
+    __syncthreads();
+    for (int y = y0 + tid; y < y1; y += RM_THREADS)
+        atomicAdd(&s_yend[min(max((min(yf[y] + T.ytaps, src.h) - r0 + WP_BAND - 1) / WP_BAND - 1, 0), max(nb - 1, 0))], 1);
+    __syncthreads();
+    {
+        int vsum = s_yend[tid];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, vsum, d);
+            if (lane >= d) vsum += u;
+        }
+        if (lane == 31) s_wsum[warp] = vsum;
+        __syncthreads();
+        for (int q = 0; q < warp; ++q) vsum += s_wsum[q];
+        s_yend[tid] = y0 + vsum;
+    }
+    __syncthreads();
+
+    // this lane's roles
+    const int rrow = lane & 15, half = lane >> 4;          // row pass
+    const int blk = warp * 2 + half;                        // block of 4 destination columns
+    const bool in_b = warp >= 4;
+    const size_t tile_off = in_b ? tile_bytes_al : 0;
+    const int tile_fx = in_b ? fxbb : fxa, tile_cols = in_b ? cols_b : cols_a;
+    const bool xedge = tile_fx < 0 || tile_fx + tile_cols > src.w;
+    const bool live = blk * RM_B < nx;
+    const int fxb = s_fxb[blk], span = s_span[blk];
+    const float4* wxb = Wx + blk * WP_SPAN;
+    const int ccol = lane & 7, seg = lane >> 3;             // column pass
+    const int xo = x0 + warp * WP_COLS + ccol;
+    const float4* ringcol = ring + ccol * WP_RP;
+
+    int ycur = y0;
+    for (int band = 0; band < nb; ++band) {
+        const int hi = r0 + band * WP_BAND;
+        const int yend = s_yend[band];
+        const int st = band % T.stages;
+        const unsigned char* tile = wp_smem + (size_t)st * stage_bytes + tile_off;
+        mbar_wait(&full[st], (band / T.stages) & 1);
+        // ---- row pass
+        if (live && hi + rrow < src.h && hi + rrow >= 0) {
+            const float4* row = reinterpret_cast<const float4*>(tile) + (size_t)rrow * swp;
+            float4 acc[RM_B];
+#pragma unroll
+            for (int q = 0; q < RM_B; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!xedge) {
+                const float4* p = row + fxb;
+#pragma unroll 4
+                for (int k = 0; k < span; ++k) {
+                    const float4 q = p[k];
+                    const float4 wk = wxb[k];
+                    acc[0] = fma4p(wk.x, q, acc[0]);
+                    acc[1] = fma4p(wk.y, q, acc[1]);
+                    acc[2] = fma4p(wk.z, q, acc[2]);
+                    acc[3] = fma4p(wk.w, q, acc[3]);
+                }
+            } else {
+#pragma unroll 2
+                for (int k = 0; k < span; ++k) {
+                    const float4 q = row[min(max(tile_fx + fxb + k, 0), src.w - 1) - tile_fx];
+                    const float4 wk = wxb[k];
+                    acc[0] = fma4p(wk.x, q, acc[0]);
+                    acc[1] = fma4p(wk.y, q, acc[1]);
+                    acc[2] = fma4p(wk.z, q, acc[2]);
+                    acc[3] = fma4p(wk.w, q, acc[3]);
+                }
+            }
+            const int slot = (hi - r0 + rrow) & (WP_RING - 1);
+#pragma unroll
+            for (int q = 0; q < RM_B; ++q) ring[(half * RM_B + q) * WP_RP + slot] = acc[q];
+        }
+        __syncwarp();
+        // ---- hand the tile back; the last warp to do so starts the next band's copy
+        if (lane == 0 && release_count(&released[st]) == RM_WARPS - 1) {
+            released[st] = 0;
+            if (band + T.stages < nb) {
+                fence_proxy_async();
+                issue(band + T.stages);
+            }
+        }
+        // ---- column pass over the rows this band completed, 4 segments of BRL rows per pass
+        for (int base = ycur; base < yend; base += 4 * BRL) {
+            const int nrows = min(4 * BRL, yend - base);
+            // first taps and totals of the pass's rows on lanes 0 .. nrows - 1
+            int fy = 0;
+            float tot = 0.0f;
+            if (lane < nrows) {
+                fy = yf[base + lane];
+                tot = yt[(base + lane) * 2];
+            }
+            const int seg_first = min(seg * BRL, nrows - 1), seg_last = min(seg * BRL + BRL - 1, nrows - 1);
+            const int fb = __shfl_sync(0xffffffffu, fy, seg_first);
+            const int fl = __shfl_sync(0xffffffffu, fy, seg_last);
+            const bool seg_live = seg * BRL < nrows;
+            const int sspan = seg_live ? min(fl + T.ytaps - fb, WP_SPAN) : 0;
+            int mspan = sspan;
+#pragma unroll
+            for (int d = 8; d < 32; d <<= 1) mspan = max(mspan, __shfl_xor_sync(0xffffffffu, mspan, d));
+            // windows that reach over the top / bottom of the frame: tap by tap with a clamped row index
+            const int f0 = __shfl_sync(0xffffffffu, fy, 0), fe = __shfl_sync(0xffffffffu, fy, nrows - 1);
+            if (f0 < 0 || fe + T.ytaps > src.h) {
+                for (int o = 0; o < BRL; ++o) {
+                    const int r = seg * BRL + o;
+                    if (r >= nrows) break;
+                    const int y = base + r;
+                    const int fyr = yf[y];
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (yt[y * 2] != 0.0f)
+                        for (int t = 0; t < T.ytaps; ++t)
+                            acc = fma4p(yw[(size_t)y * T.ytaps + t], ringcol[(min(max(fyr + t, 0), src.h - 1) - r0) & (WP_RING - 1)], acc);
+                    if (xo < dst.w && warp * WP_COLS + ccol < nx) store_px(dst.p, dst.type, (size_t)y * dst.w + xo, acc);
+                }
+                __syncwarp();
+                continue;
+            }
+            // expanded weights: zero, then scatter the rows' taps (contiguous in the table) to their place in their segment
+            for (int i = lane; i < 4 * WP_SPAN * BRL; i += 32) Wy[i] = 0.0f;
+            __syncwarp();
+            const float* wsrc = yw + (size_t)base * T.ytaps;
+            // (shuffles under a divergent loop bound are avoided: every lane walks the same number of iterations below)
+            const int total = nrows * T.ytaps;
+            for (int i0 = 0; i0 < total; i0 += 32) {
+                const int i = min(i0 + lane, total - 1);
+                const int r = i / T.ytaps, t = i - r * T.ytaps;
+                const int sg = r / BRL, o = r - sg * BRL;
+                const int fr = __shfl_sync(0xffffffffu, fy, r);
+                const int fs = __shfl_sync(0xffffffffu, fy, sg * BRL);
+                const float tr = __shfl_sync(0xffffffffu, tot, r);
+                const int k = t + fr - fs;
+                if (i0 + lane < total && tr != 0.0f && k < WP_SPAN) Wy[(sg * WP_SPAN + k) * BRL + o] = wsrc[i];
+            }
+            __syncwarp();
+            // the block of BRL rows of this lane's column
+            float4 acc[BRL];
+#pragma unroll
+            for (int o = 0; o < BRL; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* wseg = Wy + (size_t)seg * WP_SPAN * BRL;
+            const int s0 = (fb - r0) & (WP_RING - 1);
+#pragma unroll 2
+            for (int k = 0; k < mspan; ++k) {
+                const float4 q = ringcol[(s0 + k) & (WP_RING - 1)];
+                if constexpr (BRL == 2) {
+                    const float2 wk = *reinterpret_cast<const float2*>(wseg + k * 2);
+                    acc[0] = fma4p(wk.x, q, acc[0]);
+                    acc[1] = fma4p(wk.y, q, acc[1]);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < BRL / 4; ++v) {
+                        const float4 wk = *reinterpret_cast<const float4*>(wseg + k * BRL + v * 4);
+                        acc[v * 4 + 0] = fma4p(wk.x, q, acc[v * 4 + 0]);
+                        acc[v * 4 + 1] = fma4p(wk.y, q, acc[v * 4 + 1]);
+                        acc[v * 4 + 2] = fma4p(wk.z, q, acc[v * 4 + 2]);
+                        acc[v * 4 + 3] = fma4p(wk.w, q, acc[v * 4 + 3]);
+                    }
+                }
+            }
+            if (warp * WP_COLS + ccol < nx) {
+#pragma unroll
+                for (int o = 0; o < BRL; ++o) {
+                    const int r = seg * BRL + o;
+                    if (r < nrows) store_px(dst.p, dst.type, (size_t)(base + r) * dst.w + xo, acc[o]);
+                }
+            }
+            __syncwarp();
+        }
+        ycur = yend;
+        __syncwarp();
+    }
+}
+
 struct RotParams {
     float m[9];  // inverse matrix, row-vector convention
     int id;      // filter id
@@ -927,7 +1204,56 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
         k_resize_axis<<<(dst->h + 127) / 128, 128, 0, st>>>(ay, yf, yw, yt);
         count_launch(2);
     }
-    if (march) {
+    // float32 frames on a 16-byte aligned base, up to 16 taps per axis: warp-private rings behind TMA-staged bands
+    static const bool wp_on = [] {
+        const char* e = getenv("TOUCAN_RESIZE_WP");
+        return !(e && *e == '0');
+    }();
+    bool wp_done = false;
+    // (reductions only: enlarging, a band completes many rows and the march's CTA-wide column pass is the faster one -- 0.072 against 0.079 ms at 2K -> 4K)
+    if (march && wp_on && src->type == TC_F32 && dst->type == TC_F32 && dst->h <= src->h && tma_available() && ((uintptr_t)src->data & 15) == 0 && ay.taps <= 16 &&
+        ax.taps <= WP_SPAN) {
+        const float rows_per_band = (float)WP_BAND * (float)dst->h / (float)src->h;
+        const int brl = rows_per_band <= 8.5f ? 2 : (rows_per_band <= 16.5f ? 4 : 8);
+        ResizeWp Q;
+        Q.xtaps = ax.taps;
+        Q.ytaps = ay.taps;
+        Q.sw = (int)ceilf(31.0f * (float)src->w / (float)dst->w) + ax.taps + 1;
+        const int wspan_x = (int)ceilf((float)(RM_B - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
+        const int wspan_y = (int)ceilf((float)(brl - 1) * (float)src->h / (float)dst->h) + ay.taps + 1;
+        auto smem_for = [&](int stages) { return brl == 2 ? resize_wp_smem<2>(Q.sw, stages) : (brl == 4 ? resize_wp_smem<4>(Q.sw, stages) : resize_wp_smem<8>(Q.sw, stages)); };
+        // two CTAs per SM; two staging buffers where they fit next to the rings, else one (the other CTA covers the copy).  Measured
+        // at 4K -> 2K: one buffer at two CTAs per SM 0.075 ms, four buffers at ONE CTA per SM 0.126 ms -- warps, not copies in flight
+        const int per_sm = 2;
+        Q.stages = smem_for(2) <= 112 * 1024 ? 2 : 1;
+        const size_t wp_smem = smem_for(Q.stages);
+        CUtensorMap map;
+        if (wspan_x <= WP_SPAN && wspan_y <= WP_SPAN && 2 * (Q.sw | 1) <= 256 && wp_smem <= 112 * 1024 &&
+            tensor_map_2d(src->data, 8, 2ull * src->w, (unsigned long long)src->h, 16ull * src->w, 2u * (Q.sw | 1), (unsigned)WP_BAND, &map) == TC_OK) {
+            const int strips = (dst->w + WP_W - 1) / WP_W;
+            int chunks = std::max(1, per_sm * num_sms() / strips);
+            chunks = std::min(chunks, std::max(1, src->h / (8 * ay.taps)));
+            chunks = std::max(1, std::min(chunks, dst->h));
+            Q.ch = (dst->h + chunks - 1) / chunks;
+            const int max_rows = std::max(1, (int)((double)(WP_BAND * (RM_MAXBANDS - 2) - ay.taps) * dst->h / src->h));
+            Q.ch = std::min(Q.ch, max_rows);
+            const dim3 grid(strips, (dst->h + Q.ch - 1) / Q.ch);
+            int e = TC_OK;
+#define TC_WP(B)                                                                                                               \
+    e = ensure_dynamic_smem((const void*)k_resize_wp<B>, wp_smem);                                                              \
+    if (e == TC_OK) k_resize_wp<B><<<grid, RM_THREADS, wp_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, Q, map);
+            if (brl == 2) { TC_WP(2) } else if (brl == 4) { TC_WP(4) } else { TC_WP(8) }
+#undef TC_WP
+            if (e != TC_OK) {
+                if (scratch) cudaFreeAsync(scratch, st);
+                return e;
+            }
+            count_launch(1);
+            wp_done = true;
+        }
+    }
+    if (wp_done) {
+    } else if (march) {
         // chunks of destination rows: one wave of two / three CTAs per SM, warm-up rows (ytaps per chunk) kept below ~1/8 of a chunk
         const int strips = (dst->w + RM_W - 1) / RM_W;
         int chunks = std::max(1, (three ? 3 : 2) * num_sms() / strips);
