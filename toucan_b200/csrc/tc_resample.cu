@@ -554,9 +554,9 @@ __global__ void __launch_bounds__(RM_THREADS, PF ? 2 : 3) k_resize_march(const I
 }
 
 // Resize of float32 frames with warp-private rings (round 2, after k_gauss_march: the Blur march showed that a band staged by
-// TMA, filtered by warps that never meet at a CTA barrier, beats the same work behind barriers).  A CTA owns 64 destination
-// columns -- two sub-strips of 32, each with its own staged tile because a TMA box is at most 128 pixels wide -- and a chunk of
-// rows; a warp owns 8 of the columns END TO END:
+// TMA, filtered by warps that never meet at a CTA barrier, beats the same work behind barriers).  A CTA owns NSUB sub-strips of
+// 32 destination columns, each with 4 warps and its own staged tile (a TMA box is at most 128 pixels wide), and a chunk of rows;
+// a warp owns 8 of the columns END TO END:
 //   * bands of 16 source rows arrive by TMA (zero fill outside the frame; one staging buffer: the other CTA of the SM covers
 //     the copy), counted on an mbarrier, handed back through a shared-memory counter;
 //   * row pass: lane = (source row 0..15, half 0..1): the 4 outputs of one half of the warp's columns from their common span
@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(RM_THREADS, PF ? 2 : 3) k_resize_march(const I
 //   * frame edges are index arithmetic: the row pass of an edge strip clamps its (uniform) column index, rows outside the frame
 //     are never filtered, and a block whose windows reach over the top / bottom takes a tap-by-tap loop with a clamped row index.
 // Same weights and ascending-tap accumulation as the kernels above: identical frames for finite pixels.
-constexpr int WP_W = 64, WP_BAND = 16, WP_RING = 32, WP_RP = WP_RING + 1, WP_SPAN = 24, WP_WARPS = 8, WP_COLS = 8;
+constexpr int WP_BAND = 16, WP_RING = 32, WP_RP = WP_RING + 1, WP_SPAN = 24, WP_COLS = 8;
+// NSUB sub-strips of 32 destination columns (4 warps and one staged tile each) per CTA
 
 struct ResizeWp {
     int sw;       // staged columns of one 32-column sub-strip (allocation); the staged row pitch is sw | 1 pixels
@@ -576,25 +577,26 @@ struct ResizeWp {
     int stages;   // staging buffers (each two tiles): 2-4 with two CTAs per SM where they fit, else up to 4 with one CTA per SM
 };
 
-template <int BRL>
+template <int BRL, int NSUB>
 static size_t resize_wp_smem(int sw, int stages)
 {
     const size_t tile = (((size_t)WP_BAND * (sw | 1) * 16) + 127) / 128 * 128;
-    return (size_t)stages * 2 * tile + (size_t)WP_WARPS * WP_COLS * WP_RP * 16 + (size_t)(WP_W / RM_B) * WP_SPAN * 16 + (size_t)WP_WARPS * 4 * WP_SPAN * BRL * 4 + 64;
+    return (size_t)stages * NSUB * tile + (size_t)(4 * NSUB) * WP_COLS * WP_RP * 16 + (size_t)(8 * NSUB) * WP_SPAN * 16 + (size_t)(4 * NSUB) * 4 * WP_SPAN * BRL * 4 + 64;
 }
 
-template <int BRL>
-__global__ void __launch_bounds__(RM_THREADS, 2) k_resize_wp(const Img src, const Img dst, const int* __restrict__ xf, const float* __restrict__ xw,
+template <int BRL, int NSUB>
+__global__ void __launch_bounds__(128 * NSUB, NSUB == 1 ? 4 : 2) k_resize_wp(const Img src, const Img dst, const int* __restrict__ xf, const float* __restrict__ xw,
                                                               const float* __restrict__ xt, const int* __restrict__ yf,
                                                               const float* __restrict__ yw, const float* __restrict__ yt, const ResizeWp T,
                                                               const __grid_constant__ CUtensorMap map)
 {
     extern __shared__ __align__(128) unsigned char wp_smem[];
-    __shared__ int s_fxb[WP_W / RM_B], s_span[WP_W / RM_B], s_yend[RM_MAXBANDS], s_wsum[RM_WARPS];
+    constexpr int WP_W = 32 * NSUB, WP_WARPS = 4 * NSUB, WP_THREADS = 128 * NSUB;
+    __shared__ int s_fxb[WP_W / RM_B], s_span[WP_W / RM_B], s_yend[RM_MAXBANDS];
     const int swp = T.sw | 1;
     const size_t tile_bytes_al = (((size_t)WP_BAND * swp * 16) + 127) / 128 * 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const size_t stage_bytes = 2 * tile_bytes_al;
+    const size_t stage_bytes = NSUB * tile_bytes_al;
     float4* rings = reinterpret_cast<float4*>(wp_smem + (size_t)T.stages * stage_bytes);
     float4* ring = rings + (size_t)warp * WP_COLS * WP_RP;                       // [8 columns][33]
     float4* Wx = rings + (size_t)WP_WARPS * WP_COLS * WP_RP;                     // [16 blocks][WP_SPAN]
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_wp(const Img src, cons
     const int xb0 = min(x0 + 32, dst.w - 1), xb1 = min(x0 + 63, dst.w - 1);
     const int fxa = xf[xa0], fxbb = xf[xb0];
     const int cols_a = min(xf[xa1] + T.xtaps - fxa, T.sw), cols_b = min(xf[xb1] + T.xtaps - fxbb, T.sw);
-    const bool has_b = nx > 32;
+    const bool has_b = NSUB > 1 && nx > 32;
     const int r0 = yf[y0];
     const int rlast = min(yf[y1 - 1] + T.ytaps, src.h);
     const int nb = min((rlast - r0 + WP_BAND - 1) / WP_BAND, RM_MAXBANDS);
@@ -632,9 +634,9 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_wp(const Img src, cons
         for (int b = 0; b < T.stages && b < nb; ++b) issue(b);
     }
     // rings start as zeros: a block's expanded weights are zero outside an output's window, and zero times a stale slot must be zero
-    for (int i = tid; i < WP_WARPS * WP_COLS * WP_RP; i += RM_THREADS) rings[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < WP_WARPS * WP_COLS * WP_RP; i += WP_THREADS) rings[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     // expanded x weights of the 16 blocks of 4 columns, relative to their sub-strip's tile
-    for (int i = tid; i < (WP_W / RM_B) * WP_SPAN; i += RM_THREADS) {
+    for (int i = tid; i < (WP_W / RM_B) * WP_SPAN; i += WP_THREADS) {
         const int b = i / WP_SPAN, k = i - b * WP_SPAN;
         float w[RM_B] = { 0.f, 0.f, 0.f, 0.f };
         if (b * RM_B < nx) {
@@ -659,22 +661,29 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_wp(const Img src, cons
         s_span[tid] = max(min(min(xf[xb] + T.xtaps - xf[xa], WP_SPAN), cols - fb), 0);
     }
     // destination rows complete after each band of 16 source rows (see k_resize_march)
-    s_yend[tid] = 0;
+    for (int i = tid; i < RM_MAXBANDS; i += WP_THREADS) s_yend[i] = 0;
     __syncthreads();
-    for (int y = y0 + tid; y < y1; y += RM_THREADS)
+    for (int y = y0 + tid; y < y1; y += WP_THREADS)
         atomicAdd(&s_yend[min(max((min(yf[y] + T.ytaps, src.h) - r0 + WP_BAND - 1) / WP_BAND - 1, 0), max(nb - 1, 0))], 1);
     __syncthreads();
-    {
-        int vsum = s_yend[tid];
+    if (warp == 0) {
+        // inclusive prefix over the RM_MAXBANDS counts: 8 consecutive entries per lane, then a warp scan of the lane sums
+        constexpr int PER = RM_MAXBANDS / 32;
+        int v[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            sum += s_yend[lane * PER + q];
+            v[q] = sum;
+        }
+        int incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, vsum, d);
-            if (lane >= d) vsum += u;
+            const int u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
         }
-        if (lane == 31) s_wsum[warp] = vsum;
-        __syncthreads();
-        for (int q = 0; q < warp; ++q) vsum += s_wsum[q];
-        s_yend[tid] = y0 + vsum;
+        const int before = incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) s_yend[lane * PER + q] = y0 + before + v[q];
     }
     __syncthreads();
 
@@ -733,7 +742,7 @@ __global__ void __launch_bounds__(RM_THREADS, 2) k_resize_wp(const Img src, cons
         }
         __syncwarp();
         // ---- hand the tile back; the last warp to do so starts the next band's copy
-        if (lane == 0 && release_count(&released[st]) == RM_WARPS - 1) {
+        if (lane == 0 && release_count(&released[st]) == WP_WARPS - 1) {
             released[st] = 0;
             if (band + T.stages < nb) {
                 fence_proxy_async();
@@ -1221,16 +1230,22 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
         Q.sw = (int)ceilf(31.0f * (float)src->w / (float)dst->w) + ax.taps + 1;
         const int wspan_x = (int)ceilf((float)(RM_B - 1) * (float)src->w / (float)dst->w) + ax.taps + 1;
         const int wspan_y = (int)ceilf((float)(brl - 1) * (float)src->h / (float)dst->h) + ay.taps + 1;
-        auto smem_for = [&](int stages) { return brl == 2 ? resize_wp_smem<2>(Q.sw, stages) : (brl == 4 ? resize_wp_smem<4>(Q.sw, stages) : resize_wp_smem<8>(Q.sw, stages)); };
+        // one sub-strip (32 columns, 4 warps, one staged tile) per CTA and four CTAs per SM: 0.073 ms at 4K -> 2K against 0.077 ms
+        // with two sub-strips per CTA and two CTAs per SM (more copies in flight per SM for the same warps)
+        constexpr int wp_nsub = 1;
+        auto smem_for = [&](int stages) {
+            return brl == 2 ? resize_wp_smem<2, 1>(Q.sw, stages) : (brl == 4 ? resize_wp_smem<4, 1>(Q.sw, stages) : resize_wp_smem<8, 1>(Q.sw, stages));
+        };
         // two CTAs per SM; two staging buffers where they fit next to the rings, else one (the other CTA covers the copy).  Measured
         // at 4K -> 2K: one buffer at two CTAs per SM 0.075 ms, four buffers at ONE CTA per SM 0.126 ms -- warps, not copies in flight
-        const int per_sm = 2;
-        Q.stages = smem_for(2) <= 112 * 1024 ? 2 : 1;
+        Q.stages = smem_for(2) <= (wp_nsub == 2 ? 112 : 56) * 1024 ? 2 : 1;
         const size_t wp_smem = smem_for(Q.stages);
+        const int per_sm = std::max(1, std::min(wp_nsub == 2 ? 2 : 4, (int)((size_t)227 * 1024 / (wp_smem + 1024))));
         CUtensorMap map;
         if (wspan_x <= WP_SPAN && wspan_y <= WP_SPAN && 2 * (Q.sw | 1) <= 256 && wp_smem <= 112 * 1024 &&
             tensor_map_2d(src->data, 8, 2ull * src->w, (unsigned long long)src->h, 16ull * src->w, 2u * (Q.sw | 1), (unsigned)WP_BAND, &map) == TC_OK) {
-            const int strips = (dst->w + WP_W - 1) / WP_W;
+            const int strip_w = 32 * wp_nsub;
+            const int strips = (dst->w + strip_w - 1) / strip_w;
             int chunks = std::max(1, per_sm * num_sms() / strips);
             chunks = std::min(chunks, std::max(1, src->h / (8 * ay.taps)));
             chunks = std::max(1, std::min(chunks, dst->h));
@@ -1239,10 +1254,12 @@ int tc_resize(const tc_image* dst, const tc_image* src, const char* filter_name,
             Q.ch = std::min(Q.ch, max_rows);
             const dim3 grid(strips, (dst->h + Q.ch - 1) / Q.ch);
             int e = TC_OK;
-#define TC_WP(B)                                                                                                               \
-    e = ensure_dynamic_smem((const void*)k_resize_wp<B>, wp_smem);                                                              \
-    if (e == TC_OK) k_resize_wp<B><<<grid, RM_THREADS, wp_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, Q, map);
+#define TC_WP2(B, N)                                                                                                            \
+    e = ensure_dynamic_smem((const void*)k_resize_wp<B, N>, wp_smem);                                                            \
+    if (e == TC_OK) k_resize_wp<B, N><<<grid, 128 * N, wp_smem, st>>>(view(src), view(dst), xf, xw, xt, yf, yw, yt, Q, map);
+#define TC_WP(B) TC_WP2(B, 1)
             if (brl == 2) { TC_WP(2) } else if (brl == 4) { TC_WP(4) } else { TC_WP(8) }
+#undef TC_WP2
 #undef TC_WP
             if (e != TC_OK) {
                 if (scratch) cudaFreeAsync(scratch, st);
