@@ -834,3 +834,22 @@ def test_random_stacks_against_the_oracle(T, seed):
             x = O.dissolve(x, O.blur(b, rb) if rb > 0 else b, v)
         acc = O.comp(x, acc, True)
     assert_close(got, acc, f"stack {(w, h)} {[(ra, rb, v, b is not None) for a, b, ra, rb, v in spec]}")
+
+
+def test_color_convert_every_pair_of_spaces(T):
+    """Every ordered pair of the colour spaces the baked path knows (curve -> 3x3 -> curve), float32, with and without the
+    unpremult flag, against the oracle (relative bar where a decode curve reaches large values)."""
+    from oracle.oracle import COLOR_SPACES
+
+    rng = np.random.default_rng(31)
+    src = rng.random((37, 53, 4), dtype=np.float32)
+    src[..., 3] = np.where(rng.random((37, 53)) < 0.3, 1.0, src[..., 3])
+    d = to_dev(src)
+    names = sorted(COLOR_SPACES)
+    for a in names:
+        for b in names:
+            for un in (False, True):
+                # (the ACEScc / ACEScct decodes are 2^(17.52 x - 9.72): a float ulp of that exponent is 1e-6 of the result, and dividing by
+                # a small alpha first sends x far above 1)
+                rtol = 2e-5 if a.startswith("ACEScc") else 2e-6
+                assert_close(T.colorconvert(d, a, b, unpremult=un), O.colorconvert(src, a, b, unpremult=un), f"{a} -> {b} unpremult={un}", tol=2e-5, rtol=rtol)
