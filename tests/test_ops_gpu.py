@@ -853,3 +853,26 @@ def test_color_convert_every_pair_of_spaces(T):
                 # a small alpha first sends x far above 1)
                 rtol = 2e-5 if a.startswith("ACEScc") else 2e-6
                 assert_close(T.colorconvert(d, a, b, unpremult=un), O.colorconvert(src, a, b, unpremult=un), f"{a} -> {b} unpremult={un}", tol=2e-5, rtol=rtol)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_generators_random_parameters_bit_exact(T, seed):
+    """Fill / Checkers / Gradient / Noise with random sizes, colours (also outside [0, 1]), checker sizes, noise kinds and seeds,
+    in every storage type: bit-exact (north_star's bar for the generators and the seeded Noise)."""
+    rng = np.random.default_rng(12000 + seed)
+    types = [O.U8, O.U16, O.F16, O.F32]
+    for _ in range(10):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 200))
+        t = types[int(rng.integers(0, 4))]
+        c1 = [float(v) for v in rng.uniform(-0.2, 1.3, 4)]
+        c2 = [float(v) for v in rng.uniform(-0.2, 1.3, 4)]
+        what = f"{(w, h)} type {t}"
+        assert_exact(T.fill(w, h, c1, t), O.fill(w, h, c1, t), "fill " + what)
+        cw, ch = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        assert_exact(T.checkers(w, h, cw, ch, c1, c2, t), O.checkers(w, h, cw, ch, c1, c2, t), f"checkers {cw}x{ch} " + what)
+        vertical = bool(rng.integers(0, 2))
+        assert_exact(T.gradient(w, h, c1, c2, vertical, t), O.gradient(w, h, c1, c2, vertical, t), f"gradient {vertical} " + what)
+        kind = str(rng.choice(["gaussian", "uniform", "white", "salt", "blue"]))
+        a, b = float(rng.uniform(0, 1)), float(rng.uniform(0, 1))
+        mono, sd = bool(rng.integers(0, 2)), int(rng.integers(0, 1000))
+        assert_exact(T.noise(w, h, kind, a, b, mono, sd, t), O.noise(w, h, kind, a, b, mono, sd, t), f"noise {kind} {a} {b} {mono} {sd} " + what)
