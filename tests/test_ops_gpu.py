@@ -876,3 +876,36 @@ def test_generators_random_parameters_bit_exact(T, seed):
         a, b = float(rng.uniform(0, 1)), float(rng.uniform(0, 1))
         mono, sd = bool(rng.integers(0, 2)), int(rng.integers(0, 1000))
         assert_exact(T.noise(w, h, kind, a, b, mono, sd, t), O.noise(w, h, kind, a, b, mono, sd, t), f"noise {kind} {a} {b} {mono} {sd} " + what)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float16])
+def test_pointwise_ops_on_special_values(T, dt):
+    """Infinities, NaN, negative zero, denormals, negative and > 1 values through the pointwise ops in float storage: same bits as
+    the oracle for the exact ops (NaN patterns compared as NaN), same NaN / infinity pattern and tolerance for the others."""
+    rng = np.random.default_rng(77)
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-40, -1e-40, 6e-8, 65504.0, -65504.0, 0.5, 2.0, 1e-7, 3.0], dtype=np.float32)
+    src = rng.choice(special, size=(24, 32, 4)).astype(dt)
+    src2 = rng.choice(special, size=(24, 32, 4)).astype(dt)
+    d, d2 = to_dev(src), to_dev(src2)
+
+    def same(got, want, what, exact=True):
+        got = to_host(got)
+        assert got.dtype == want.dtype and got.shape == want.shape, what
+        gn, wn = np.isnan(got.astype(np.float32)), np.isnan(want.astype(np.float32))
+        assert np.array_equal(gn, wn), what + ": NaN pattern"
+        if exact:
+            assert np.array_equal(got[~gn].view(np.uint16 if dt == np.float16 else np.uint32), want[~wn].view(np.uint16 if dt == np.float16 else np.uint32)), what
+        else:
+            fin = np.isfinite(want.astype(np.float32)) & ~wn
+            assert np.array_equal(np.isinf(got.astype(np.float32)), np.isinf(want.astype(np.float32))), what + ": infinities"
+            assert np.allclose(got[fin].astype(np.float64), want[fin].astype(np.float64), rtol=2e-3 if dt == np.float16 else 1e-5, atol=1e-5), what
+
+    with np.errstate(all="ignore"):
+        same(T.invert(d), O.invert(src), "invert")
+        same(T.premult(d), O.premult(src), "premult")
+        same(T.flip(d), O.flip(src), "flip")
+        same(T.dissolve(d, d2, 0.25), O.dissolve(src, src2, 0.25), "dissolve")
+        same(T.wipe(d, d2, 0.5, False), O.wipe(src, src2, 0.5, False), "wipe")
+        same(T.over(d, d2, premult_fg=True), O.over(O.premult(src), src2), "premult + over")
+        same(T.saturate(d, 0.3), O.saturate(src, 0.3), "saturate", exact=False)
+        same(T.unpremult(d), O.unpremult(src), "unpremult", exact=False)
