@@ -219,6 +219,21 @@ def _random_timeline(rng):
                                  "in_offset": rt(o), "out_offset": rt(int(rng.integers(1, 3)))})
             if rng.random() < 0.15 and children and children[-1]["OTIO_SCHEMA"] != "Transition.1":
                 children.append({"OTIO_SCHEMA": "Gap.1", "name": "Gap", "metadata": {}, "effects": [], "source_range": tr(0, int(rng.integers(2, 8)))})
+            if rng.random() < 0.2:  # a generator clip (Clip.1 with a single media_reference, as data/Generator.otio has them)
+                kind = str(rng.choice(["toucan:Fill", "toucan:Checkers", "toucan:Gradient", "toucan:Noise"]))
+                params = {"size": [48, 30]}
+                if kind == "toucan:Fill":
+                    params["color"] = [float(v) for v in rng.random(4)]
+                elif kind == "toucan:Checkers":
+                    params.update(checkerSize=[int(rng.integers(1, 20)), int(rng.integers(1, 20))], color1=[float(v) for v in rng.random(4)], color2=[float(v) for v in rng.random(4)])
+                elif kind == "toucan:Gradient":
+                    params.update(color1=[float(v) for v in rng.random(4)], color2=[float(v) for v in rng.random(4)], vertical=bool(rng.integers(0, 2)))
+                else:
+                    params.update(type=str(rng.choice(["gaussian", "uniform", "salt"])), a=float(rng.random()), b=float(rng.random()), mono=bool(rng.integers(0, 2)), seed=int(rng.integers(0, 100)))
+                children.append({"OTIO_SCHEMA": "Clip.1", "name": f"t{t}g{i}", "metadata": {}, "source_range": tr(0, dur), "effects": effects(0.1),
+                                 "media_reference": {"OTIO_SCHEMA": "GeneratorReference.1", "name": "", "metadata": {}, "available_range": tr(0, 40),
+                                                     "generator_kind": kind, "parameters": params}})
+                continue
             children.append({
                 "OTIO_SCHEMA": "Clip.2", "name": f"t{t}c{i}", "metadata": {}, "source_range": tr(int(rng.integers(0, 6)), dur),
                 "effects": effects(0.3),
