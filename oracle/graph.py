@@ -356,7 +356,8 @@ class ImageGraph:
     def _seq_path(self, mr, frame):
         base = self._media_path(mr.get("target_url_base", ""))
         pad = int(mr.get("frame_zero_padding", 0))
-        return os.path.join(base, "%s%s%s" % (mr.get("name_prefix", ""), str(frame).zfill(pad), mr.get("name_suffix", "")))
+        # std::setw(padding) << std::setfill('0') << frame (Util.cpp:46-49): fill characters go LEFT of the sign ("00-1", not "-001")
+        return os.path.join(base, "%s%s%s" % (mr.get("name_prefix", ""), str(frame).rjust(pad, "0"), mr.get("name_suffix", "")))
 
     def _first_path(self, mr):
         if mr["OTIO_SCHEMA"].startswith("ExternalReference"):

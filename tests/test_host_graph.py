@@ -234,6 +234,15 @@ def _random_timeline(rng):
                                  "media_reference": {"OTIO_SCHEMA": "GeneratorReference.1", "name": "", "metadata": {}, "available_range": tr(0, 40),
                                                      "generator_kind": kind, "parameters": params}})
                 continue
+            if rng.random() < 0.15:  # a numbered image sequence: the frame number read follows the clip's (warped) time
+                children.append({
+                    "OTIO_SCHEMA": "Clip.2", "name": f"t{t}s{i}", "metadata": {}, "source_range": tr(int(rng.integers(0, 6)), dur), "effects": effects(0.4),
+                    "media_references": {"DEFAULT_MEDIA": {"OTIO_SCHEMA": "ImageSequenceReference.1", "name": "", "metadata": {},
+                                                           "available_range": tr(int(rng.integers(0, 3)), 40), "target_url_base": f"synthetic://seq{t}/",
+                                                           "name_prefix": "f.", "name_suffix": ".png", "start_frame": int(rng.integers(0, 3)), "frame_step": 1,
+                                                           "rate": rate, "frame_zero_padding": 4, "missing_frame_policy": "error"}},
+                    "active_media_reference_key": "DEFAULT_MEDIA"})
+                continue
             children.append({
                 "OTIO_SCHEMA": "Clip.2", "name": f"t{t}c{i}", "metadata": {}, "source_range": tr(int(rng.integers(0, 6)), dur),
                 "effects": effects(0.3),
@@ -256,6 +265,22 @@ def _random_timeline(rng):
             "tracks": {"OTIO_SCHEMA": "Stack.1", "name": "tracks", "metadata": {}, "effects": effects(0.15), "children": tracks}}
 
 
+def _random_timeline_media(doc):
+    """URLs of every still and of frames -80 .. 199 of every numbered sequence of a _random_timeline document."""
+    urls = set()
+    for t in doc["tracks"]["children"]:
+        for c in t["children"]:
+            mr = (c.get("media_references") or {}).get("DEFAULT_MEDIA")
+            if not mr:
+                continue
+            if mr["OTIO_SCHEMA"].startswith("ExternalReference"):
+                urls.add(mr["target_url"])
+            elif mr["OTIO_SCHEMA"].startswith("ImageSequenceReference"):
+                for n in range(-80, 200):  # (time warps reach before the first frame: "f.00-3.png", Util.cpp:46-49)
+                    urls.add("%s%s%s%s" % (mr["target_url_base"], mr["name_prefix"], str(n).rjust(mr["frame_zero_padding"], "0"), mr["name_suffix"]))
+    return sorted(urls)
+
+
 @pytest.mark.parametrize("seed", range(160))
 def test_random_timelines_build_the_oracles_node_trees(host, seed):
     """ImageGraph::exec of the C++ host against the oracle's restatement of lib/toucanRender/ImageGraph.cpp:144-466 on
@@ -270,8 +295,7 @@ def test_random_timelines_build_the_oracles_node_trees(host, seed):
     doc = _random_timeline(rng)
     still = np.zeros((6, 8, 4), np.uint8)
     tl = render.Timeline(json_doc=doc, directory="/nonexistent")
-    urls = sorted({c["media_references"]["DEFAULT_MEDIA"]["target_url"] for t in doc["tracks"]["children"] for c in t["children"] if c["OTIO_SCHEMA"] == "Clip.2"})
-    for u in urls:
+    for u in _random_timeline_media(doc):
         tl.set_media(tl.media_path(u), still)
     tl.prepare()
     otl = G.Timeline(doc)

@@ -448,6 +448,25 @@ def test_node_timers_report_device_time_per_node_label(cuda):
     tl.close()
 
 
+def _resamples_to_8_bit(og, node):
+    """True if a node of the oracle's tree filters a frame into 8-bit storage (a Resize of a generator's frame, a transition or
+    a CompNode fitting an input of another size to an 8-bit one): the one place a 1e-6 difference may become a whole code."""
+    if node is None or node[0] == "read":
+        return False
+    ins = node[1] if node[0] == "comp" else node[3]
+    if any(_resamples_to_8_bit(og, i) for i in ins):
+        return True
+    vals = [og.eval(i) for i in ins]
+    vals = [v for v in vals if v is not None and v.size]
+    if node[0] == "comp":
+        return len(vals) == 2 and vals[0].shape != vals[1].shape and vals[1].dtype == np.uint8
+    if node[1] == "toucan:Resize":
+        return len(vals) == 1 and vals[0].dtype == np.uint8
+    if len(vals) == 2:  # transitions fit their second input to the first
+        return vals[0].shape != vals[1].shape and vals[1].dtype == np.uint8
+    return False
+
+
 @pytest.mark.parametrize("seed", range(40))
 @pytest.mark.parametrize("fusion", [True, False])
 def test_random_timelines_render_like_the_oracle(cuda, host, seed, fusion):
@@ -470,17 +489,18 @@ def test_random_timelines_render_like_the_oracle(cuda, host, seed, fusion):
         return out
 
     doc["tracks"]["effects"] = tame(doc["tracks"]["effects"])
+    from tests.test_host_graph import _random_timeline_media
+
     stills = {}
     for t in doc["tracks"]["children"]:
         t["effects"] = tame(t["effects"])
         for c in t["children"]:
-            if c["OTIO_SCHEMA"] == "Clip.2":
+            if c["OTIO_SCHEMA"].startswith("Clip"):
                 c["effects"] = tame(c["effects"])
-                u = c["media_references"]["DEFAULT_MEDIA"]["target_url"]
-                if u not in stills:
-                    a = rng.random((30, 48, 4), dtype=np.float32)
-                    a[..., 3] = np.where(rng.random((30, 48)) < 0.3, 1.0, a[..., 3])
-                    stills[u] = np.ascontiguousarray(a)
+    for u in _random_timeline_media(doc):  # stills, and a different image for every frame of a numbered sequence
+        a = rng.random((30, 48, 4), dtype=np.float32)
+        a[..., 3] = np.where(rng.random((30, 48)) < 0.3, 1.0, a[..., 3])
+        stills[u] = np.ascontiguousarray(a)
     render.set_fusion(fusion)
     try:
         tl = render.Timeline(json_doc=doc, directory="/nonexistent")
@@ -491,7 +511,7 @@ def test_random_timelines_render_like_the_oracle(cuda, host, seed, fusion):
         tl.prepare()
         otl = G.Timeline(doc)
         otl.dir = "/nonexistent"
-        og = G.ImageGraph(otl, lambda p: by_path[p])
+        og = G.ImageGraph(otl, lambda p: by_path.get(p))  # (a warped clip may ask for a frame number outside the sequence: no image)
         for t in otl.frames():
             want = og.render(t)
             got = tl.render(host, t.value, max_bytes=64 * 64 * 16)
@@ -500,8 +520,9 @@ def test_random_timelines_render_like_the_oracle(cuda, host, seed, fusion):
                 continue
             assert got.shape == want.shape and got.dtype == want.dtype, (seed, t.value, got.shape, want.shape, got.dtype, want.dtype)
             d = np.abs(got.astype(np.float64) - want.astype(np.float64))
-            # (a frame over the u8 Fill through CompNode's fit path takes the background's 8-bit type: +-1 code after the resize)
-            bar = 2e-5 if got.dtype == np.float32 else 1.0
+            # (a frame over the u8 Fill through CompNode's fit path takes the background's 8-bit type: +-1 code after the resize;
+            #  the same code, scaled by whatever is laid over it, when such a frame is an inner node of a float tree)
+            bar = 1.0 if got.dtype != np.float32 else (1.0 / 255 + 2e-5 if _resamples_to_8_bit(og, og.exec(t)) else 2e-5)
             assert float(d.max()) <= bar, f"seed {seed} @ {t.value}: max abs diff {d.max():.3e}"
         tl.close()
     finally:
@@ -525,17 +546,18 @@ def test_random_timelines_of_exact_effects_are_bit_exact(cuda, host, seed, dtype
         return [e if e.get("effect_name", "") in exact else dict(e, effect_name="toucan:Flop", name="toucan:Flop", metadata={}) for e in effects]
 
     doc["tracks"]["effects"] = tame(doc["tracks"]["effects"])
+    from tests.test_host_graph import _random_timeline_media
+
     stills = {}
     for t in doc["tracks"]["children"]:
         t["effects"] = tame(t["effects"])
         for c in t["children"]:
-            if c["OTIO_SCHEMA"] == "Clip.2":
+            if c["OTIO_SCHEMA"].startswith("Clip"):
                 c["effects"] = tame(c["effects"])
-                u = c["media_references"]["DEFAULT_MEDIA"]["target_url"]
-                if u not in stills:
-                    a = rng.random((30, 48, 4))
-                    a[..., 3] = np.where(rng.random((30, 48)) < 0.3, 1.0, a[..., 3])
-                    stills[u] = np.ascontiguousarray((a * 255).astype(np.uint8) if dtype == np.uint8 else (a * 65535).astype(np.uint16) if dtype == np.uint16 else a.astype(np.float16))
+    for u in _random_timeline_media(doc):
+        a = rng.random((30, 48, 4))
+        a[..., 3] = np.where(rng.random((30, 48)) < 0.3, 1.0, a[..., 3])
+        stills[u] = np.ascontiguousarray((a * 255).astype(np.uint8) if dtype == np.uint8 else (a * 65535).astype(np.uint16) if dtype == np.uint16 else a.astype(np.float16))
     tl = render.Timeline(json_doc=doc, directory="/nonexistent")
     by_path = {}
     for u, a in stills.items():
@@ -544,7 +566,7 @@ def test_random_timelines_of_exact_effects_are_bit_exact(cuda, host, seed, dtype
     tl.prepare()
     otl = G.Timeline(doc)
     otl.dir = "/nonexistent"
-    og = G.ImageGraph(otl, lambda p: by_path[p])
+    og = G.ImageGraph(otl, lambda p: by_path.get(p))
     for t in otl.frames():
         want = og.render(t)
         got = tl.render(host, t.value, max_bytes=64 * 64 * 16)
