@@ -662,6 +662,7 @@ for name, out in (("rotate", ops.rotate(src, 33.0)), ("resize_down", ops.resize(
                   ("blur", ops.blur(src, 10.0))):
     torch.cuda.synchronize()
     a = out.cpu().numpy()
+    np.save(sys.argv[1] + "_" + name + ".npy", a)
     print(name, hashlib.sha256(a.tobytes()).hexdigest(), float(a.astype(np.float64).sum()))
 """
 
@@ -671,7 +672,7 @@ def test_kernel_variants_behind_the_switches_agree(T, tmp_path):
     """TOUCAN_ROTATE_TMA=0 (bounds-checked staging instead of the TMA copy), TOUCAN_RESIZE_WP=0 (the march instead of the
     warp-private kernel for float32 reductions) and TOUCAN_RESIZE_OCC=2 (its register-prefetch variant) change how pixels reach
     shared memory and which warp filters them, not the arithmetic: identical frames.  TOUCAN_CONV_TMA=0 selects round 1's Blur kernel:
-    same taps, within float rounding."""
+    same taps, within float rounding; TOUCAN_ROTATE_QUAD=0 the one-pixel-per-thread Rotate: same weights, another order."""
     import os
     import subprocess
     import sys
@@ -680,17 +681,25 @@ def test_kernel_variants_behind_the_switches_agree(T, tmp_path):
     script = tmp_path / "probe.py"
     script.write_text(_SWITCH_PROBE.format(root=root))
 
-    def run(env):
+    def run(env, tag):
         e = dict(os.environ, **env)
-        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, env=e)
+        r = subprocess.run([sys.executable, str(script), str(tmp_path / tag)], capture_output=True, text=True, timeout=300, env=e)
         assert r.returncode == 0, r.stderr[-2000:]
         return {l.split()[0]: (l.split()[1], float(l.split()[2])) for l in r.stdout.splitlines() if l and l.split()[0] in ("rotate", "resize_down", "resize_up", "blur")}
 
-    base = run({})
-    alt = run({"TOUCAN_ROTATE_TMA": "0", "TOUCAN_RESIZE_OCC": "2", "TOUCAN_RESIZE_WP": "0", "TOUCAN_CONV_TMA": "0"})
+    base = run({"TOUCAN_ROTATE_QUAD": "0"}, "base")
+    alt = run({"TOUCAN_ROTATE_QUAD": "0", "TOUCAN_ROTATE_TMA": "0", "TOUCAN_RESIZE_OCC": "2", "TOUCAN_RESIZE_WP": "0", "TOUCAN_CONV_TMA": "0"}, "alt")
     for k in ("rotate", "resize_down", "resize_up"):
         assert base[k][0] == alt[k][0], k
     assert abs(base["blur"][1] - alt["blur"][1]) <= 1e-6 * abs(base["blur"][1]), (base["blur"], alt["blur"])
+    # the default Rotate of float32 frames (four pixels per thread, k_rotate_quad) sums the same weights in another order; its
+    # per-pixel form for quads that miss the fast conditions is forced by TOUCAN_ROTATE_QUAD=generic
+    run({}, "quad")
+    run({"TOUCAN_ROTATE_QUAD": "generic"}, "generic")
+    ref = np.load(str(tmp_path / "base_rotate.npy"))
+    for tag in ("quad", "generic"):
+        got = np.load(str(tmp_path / (tag + "_rotate.npy")))
+        assert got.shape == ref.shape and float(np.abs(got - ref).max()) <= 2e-6, (tag, float(np.abs(got - ref).max()))
 
 
 @pytest.mark.parametrize("seed", range(6))

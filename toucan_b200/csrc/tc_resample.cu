@@ -968,6 +968,7 @@ constexpr int RTT = 16; // destination block edge
 struct RotTile {
     int cols, rows, pitch;                       // allocation of the shared source tile; row pitch in pixels
     float smn_off, smx_off, tmn_off, tmx_off;    // extent of a block's four corner positions relative to its first pixel's
+    int generic;                                 // k_rotate_quad: every quad through the per-pixel form (TOUCAN_ROTATE_QUAD=generic, tests)
 };
 
 // TMA: the source box is fetched by ONE tensor copy (float32 sources; zero fill outside the frame IS rotate's "black outside
@@ -1094,6 +1095,174 @@ __global__ void __launch_bounds__(RTT * RTT) k_rotate_tile(const Img src_, const
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (total > 0.0f) o = mul4p(rcp_approx(total), sum);
     store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
+}
+
+// Four destination pixels per thread (round 2): a thread owns a 2 x 2 block of the destination.  Under a rotation its four
+// footprints start within two source pixels of each other on either axis, so one 8 x 8 window of the staged tile holds all four
+// 6 x 6 live windows: 16 shared-memory pixel reads per destination pixel instead of 36.  Each pixel's six weights per axis are
+// placed in an 8-wide row at the pixel's offset in the shared window (zeros elsewhere), the window rows are reduced with the four
+// x rows and folded in with the y weights as in k_rotate_tile.  lanczos3 at its default width and unit tap spacing, float32
+// sources through the TMA copy; anything else -- and any quad whose pixels fall outside those conditions by float rounding --
+// takes the per-pixel forms (rot_px_generic here, k_rotate_tile / k_rotate otherwise).  Same weights as k_rotate_tile.
+constexpr int RQ_BW = 32, RQ_BH = 16, RQ_THREADS = 128, RQ_WIN = 8;
+
+__device__ __noinline__ void rot_px_generic(const float4* tile, int pitch, int rows, int s0, int t0, float s, float t, const Img dst, int x, int y)
+{
+    const int smin = (int)floorf(__fsub_rn(s, 3.0f)), smax = (int)ceilf(__fadd_rn(s, 3.0f));
+    const int tmin = (int)floorf(__fsub_rn(t, 3.0f)), tmax = (int)ceilf(__fadd_rn(t, 3.0f));
+    const int ns = min(smax - smin, 8), nt = min(tmax - tmin, 8);
+    const int cbase = min(max(smin - s0, 0), max(pitch - ns, 0)), rbase = min(max(tmin - t0, 0), max(rows - nt, 0));
+    const float bx = __fsub_rn(__fadd_rn((float)smin, 0.5f), s), by = __fsub_rn(__fadd_rn((float)tmin, 0.5f), t);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float total = 0.0f;
+#pragma unroll 1
+    for (int j = 0; j < nt; ++j) {
+        const float wy = rot_filt_fast<0>(__fadd_rn(by, (float)j));
+        const float4* row = tile + (rbase + j) * pitch + cbase;
+#pragma unroll 1
+        for (int i = 0; i < ns; ++i) {
+            const float w = __fmul_rn(rot_filt_fast<0>(__fadd_rn(bx, (float)i)), wy);
+            sum = fma4p(w, row[i], sum);
+            total = __fadd_rn(total, w);
+        }
+    }
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (total > 0.0f) o = mul4p(rcp_approx(total), sum);
+    store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img dst_, const __grid_constant__ RotParams P, const RotTile T,
+                                                                const __grid_constant__ CUtensorMap map)
+{
+    extern __shared__ __align__(128) float4 rot_smem[];
+    __shared__ uint64_t bar;
+    const Img dst { dst_.p, dst_.w, dst_.h, TYPE };
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * RQ_BW, y0 = blockIdx.y * RQ_BH;
+    const float px0 = __fadd_rn((float)x0, 0.5f), py0 = __fadd_rn((float)y0, 0.5f);
+    const float s00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[0]), __fmul_rn(py0, P.m[3])), P.m[6]);
+    const float t00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[1]), __fmul_rn(py0, P.m[4])), P.m[7]);
+    const int s0 = (int)floorf(s00 + T.smn_off - 3.0f) - 1, t0 = (int)floorf(t00 + T.tmn_off - 3.0f) - 1;
+    const int pitch = T.pitch;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+        mbar_expect_tx(&bar, (unsigned)(T.rows * T.pitch * 16));
+        tma_load_tile(rot_smem, &map, 2 * s0, t0, &bar);
+    }
+    __syncthreads();
+
+    // warps 2 x 2 over the block (16 x 8 pixels each), quarter warps 2 x 2 over the warp, threads 4 x 2 over the quarter
+    const int lane = tid & 31, warp = tid >> 5, q = lane >> 3, l = lane & 7;
+    const int x = x0 + (warp & 1) * 16 + (q & 1) * 8 + (l & 3) * 2, y = y0 + (warp >> 1) * 8 + (q >> 1) * 4 + (l >> 2) * 2;
+    if (x >= dst.w || y >= dst.h) return;
+
+    float se[4], te[4];
+    int cs[4], rs[4];
+    bool ok = true;
+    float exw[4][RQ_WIN], eyw[4][RQ_WIN], total[4];
+    int cmin = 1 << 30, rmin = 1 << 30;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float px = __fadd_rn((float)(x + (p & 1)), 0.5f), py = __fadd_rn((float)(y + (p >> 1)), 0.5f);
+        const float s = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[0]), __fmul_rn(py, P.m[3])), P.m[6]);
+        const float t = __fadd_rn(__fadd_rn(__fmul_rn(px, P.m[1]), __fmul_rn(py, P.m[4])), P.m[7]);
+        se[p] = s;
+        te[p] = t;
+        const int smin = (int)floorf(__fsub_rn(s, 3.0f)), smax = (int)ceilf(__fadd_rn(s, 3.0f));
+        const int tmin = (int)floorf(__fsub_rn(t, 3.0f)), tmax = (int)ceilf(__fadd_rn(t, 3.0f));
+        const int ns = smax - smin, nt = tmax - tmin;
+        const float bx = __fsub_rn(__fadd_rn((float)smin, 0.5f), s), by = __fsub_rn(__fadd_rn((float)tmin, 0.5f), t);
+        const int i0 = fabsf(bx) >= 3.0f ? 1 : 0, j0 = fabsf(by) >= 3.0f ? 1 : 0;
+        const float bx0 = __fadd_rn(bx, (float)i0), by0 = __fadd_rn(by, (float)j0);
+        // the conditions of k_rotate_tile's six-weight form, all six taps inside the footprint (anything else is a rounding
+        // accident of the position: per-pixel form)
+        ok = ok & (ns <= 7) & (nt <= 7) & (i0 + 6 <= ns) & (j0 + 6 <= nt) & ((i0 != 0) | (ns <= 6) | (fabsf(__fadd_rn(bx, 6.0f)) >= 3.0f)) &
+             ((j0 != 0) | (nt <= 6) | (fabsf(__fadd_rn(by, 6.0f)) >= 3.0f)) & (bx0 > -3.0f) & (bx0 <= -2.0f) & (by0 > -3.0f) & (by0 <= -2.0f);
+        cs[p] = smin + i0;
+        rs[p] = tmin + j0;
+        cmin = min(cmin, cs[p]);
+        rmin = min(rmin, rs[p]);
+        float ax[6], ay[6];
+        lanczos3_six(bx0, ax);
+        lanczos3_six(by0, ay);
+        float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            sx = __fadd_rn(sx, ax[k]);
+            sy = __fadd_rn(sy, ay[k]);
+            exw[p][k] = ax[k];
+            eyw[p][k] = ay[k];
+        }
+        total[p] = __fmul_rn(sx, sy);
+        exw[p][6] = exw[p][7] = eyw[p][6] = eyw[p][7] = 0.0f;
+    }
+    const int cb = cmin - s0, rb = rmin - t0;
+    ok = ok & (cb >= 0) & (cb + RQ_WIN <= pitch) & (rb >= 0) & (rb + RQ_WIN <= T.rows) & (T.generic == 0);
+    // A quarter warp is one 128-bit shared-memory phase: its eight windows start in arbitrary 16-byte bank groups, two to three
+    // per group.  Each lane therefore walks its window's columns ROTATED -- register slot i holds window column (i + sh) & 7
+    // with sh chosen so that slot i of lane l lies in bank group (l + i) & 7: eight distinct groups in every phase.  The x
+    // weights are rotated the same way once, so the arithmetic does not see it.
+    const int sh = (l - (rb * pitch + cb)) & 7;
+    // each pixel's six weights at its offset (0 .. 2) in the shared window; the x rows then rotated left by sh
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int ox = cs[p] - cmin, oy = rs[p] - rmin;
+        ok = ok & (ox <= 2) & (oy <= 2);
+        const int rot = (sh - ox) & 7; // slot i holds weight index (i + sh - ox) & 7
+#pragma unroll
+        for (int bit = 0; bit < 3; ++bit) {
+            const bool on = (rot >> bit) & 1;
+            float tmp[RQ_WIN];
+#pragma unroll
+            for (int k = 0; k < RQ_WIN; ++k) tmp[k] = exw[p][(k + (1 << bit)) & 7];
+#pragma unroll
+            for (int k = 0; k < RQ_WIN; ++k) exw[p][k] = on ? tmp[k] : exw[p][k];
+        }
+#pragma unroll
+        for (int k = RQ_WIN - 1; k >= 0; --k) {
+            const float b1 = k >= 1 ? eyw[p][k - 1] : 0.0f, b2 = k >= 2 ? eyw[p][k - 2] : 0.0f;
+            eyw[p][k] = oy == 0 ? eyw[p][k] : (oy == 1 ? b1 : b2);
+        }
+    }
+    mbar_wait(&bar, 0);
+    if (!ok) {
+#pragma unroll 1
+        for (int p = 0; p < 4; ++p)
+            if (x + (p & 1) < dst.w && y + (p >> 1) < dst.h) rot_px_generic(rot_smem, pitch, T.rows, s0, t0, se[p], te[p], dst, x + (p & 1), y + (p >> 1));
+        return;
+    }
+    float4 sum[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) sum[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* col[RQ_WIN];
+#pragma unroll
+    for (int i = 0; i < RQ_WIN; ++i) col[i] = rot_smem + rb * pitch + cb + ((i + sh) & 7);
+#pragma unroll
+    for (int j = 0; j < RQ_WIN; ++j) {
+        float4 v[RQ_WIN];
+#pragma unroll
+        for (int i = 0; i < RQ_WIN; ++i) {
+            v[i] = *col[i];
+            col[i] += pitch;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float4 r = mul4p(exw[p][0], v[0]);
+#pragma unroll
+            for (int i = 1; i < RQ_WIN; ++i) r = fma4p(exw[p][i], v[i], r);
+            sum[p] = fma4p(eyw[p][j], r, sum[p]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (x + (p & 1) < dst.w && y + (p >> 1) < dst.h) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (total[p] > 0.0f) o = mul4p(rcp_approx(total[p]), sum[p]);
+            store_px(dst.p, dst.type, (size_t)(y + (p >> 1)) * dst.w + x + (p & 1), o);
+        }
+    }
 }
 
 static int filter_id(const char* name)
@@ -1391,10 +1560,91 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
     const bool narrow = P.fw + 2.0f <= 8.0f;
     const Img vs = view(src), vd = view(dst);
     cudaStream_t st = (cudaStream_t)s;
+    // four pixels per thread: plain rotations with the default lanczos3 of float32 frames
+    {
+        static const int rot_quad_mode = [] {
+            const char* e = getenv("TOUCAN_ROTATE_QUAD");
+            return (e && *e == '0') ? 0 : ((e && !strcmp(e, "generic")) ? 2 : 1);
+        }();
+        const bool rot_quad = rot_quad_mode != 0;
+        const float ds = fmaxf(1.0f, fmaxf(fabsf(P.m[0]), fabsf(P.m[3]))), dt = fmaxf(1.0f, fmaxf(fabsf(P.m[1]), fabsf(P.m[4])));
+        const float spx = fabsf(P.m[0]) + fabsf(P.m[3]), spy = fabsf(P.m[1]) + fabsf(P.m[4]);
+        if (rot_quad && id == 0 && P.fw == 6.0f && ds == 1.0f && dt == 1.0f && spx <= 1.9f && spy <= 1.9f && src->type == TC_F32 && tma_available() &&
+            ((uintptr_t)src->data & 15) == 0) {
+            RotTile T;
+            T.generic = rot_quad_mode == 2 ? 1 : 0;
+            const float ex = (float)(RQ_BW - 1), ey = (float)(RQ_BH - 1);
+            T.cols = (int)ceilf(ex * fabsf(P.m[0]) + ey * fabsf(P.m[3]) + 6.0f) + 7;
+            T.rows = (int)ceilf(ex * fabsf(P.m[1]) + ey * fabsf(P.m[4]) + 6.0f) + 7;
+            T.smn_off = fminf(0.0f, ex * P.m[0]) + fminf(0.0f, ey * P.m[3]);
+            T.smx_off = fmaxf(0.0f, ex * P.m[0]) + fmaxf(0.0f, ey * P.m[3]);
+            T.tmn_off = fminf(0.0f, ex * P.m[1]) + fminf(0.0f, ey * P.m[4]);
+            T.tmx_off = fmaxf(0.0f, ex * P.m[1]) + fmaxf(0.0f, ey * P.m[4]);
+            // row pitch: the eight windows of a quarter warp (threads 4 x 2, two pixels apart) should start in different
+            // 16-byte bank groups
+            int best = 1 << 30;
+            T.pitch = T.cols;
+            for (int pitch = T.cols; pitch < T.cols + 8; ++pitch) {
+                int cost = 0;
+                for (int ph = 0; ph < 16; ++ph) {
+                    const float sf = 0.25f * (float)(ph & 3), tf = 0.25f * (float)(ph >> 2);
+                    int slots[8], worst = 0;
+                    for (int k = 0; k < 8; ++k) {
+                        int c0 = 1 << 30, r0 = 1 << 30;
+                        for (int p4 = 0; p4 < 4; ++p4) {
+                            const float a = (float)(2 * (k & 3) + (p4 & 1)), b = (float)(2 * (k >> 2) + (p4 >> 1));
+                            c0 = std::min(c0, (int)floorf(sf + 64.0f + a * P.m[0] + b * P.m[3]));
+                            r0 = std::min(r0, (int)floorf(tf + 64.0f + a * P.m[1] + b * P.m[4]));
+                        }
+                        slots[k] = r0 * pitch + c0;
+                    }
+                    for (int g = 0; g < 8; ++g) {
+                        int n = 0;
+                        for (int k = 0; k < 8; ++k) {
+                            if ((slots[k] & 7) != g) continue;
+                            bool seen = false;
+                            for (int q = 0; q < k; ++q) seen = seen || slots[q] == slots[k];
+                            n += seen ? 0 : 1;
+                        }
+                        worst = n > worst ? n : worst;
+                    }
+                    cost += worst;
+                }
+                if (cost < best) {
+                    best = cost;
+                    T.pitch = pitch;
+                }
+            }
+            const size_t smem = (size_t)T.rows * T.pitch * sizeof(float4);
+            CUtensorMap map;
+            memset(&map, 0, sizeof(map));
+            if (smem <= 72 * 1024 && 2 * T.pitch <= 256 && T.rows <= 256 &&
+                tensor_map_2d(src->data, 8, 2ull * src->w, (unsigned long long)src->h, 16ull * src->w, 2u * T.pitch, (unsigned)T.rows, &map) == TC_OK) {
+                const dim3 qgrid((dst->w + RQ_BW - 1) / RQ_BW, (dst->h + RQ_BH - 1) / RQ_BH);
+                int e = TC_OK;
+#define TC_ROTQ(TY)                                                                   \
+    case TY:                                                                          \
+        e = ensure_dynamic_smem((const void*)k_rotate_quad<TY>, smem);                \
+        if (e == TC_OK) k_rotate_quad<TY><<<qgrid, RQ_THREADS, smem, st>>>(vd, P, T, map); \
+        break;
+                switch (dst->type) {
+                    TC_ROTQ(TC_U8)
+                    TC_ROTQ(TC_U16)
+                    TC_ROTQ(TC_F16)
+                    TC_ROTQ(TC_F32)
+                }
+#undef TC_ROTQ
+                if (e != TC_OK) return e;
+                count_launch();
+                return check_cuda(cudaGetLastError(), "k_rotate_quad launch");
+            }
+        }
+    }
     // shared-memory tile path: default-width filters whose block footprint fits 64 KB
     {
         const float ds = fmaxf(1.0f, fmaxf(fabsf(P.m[0]), fabsf(P.m[3]))), dt = fmaxf(1.0f, fmaxf(fabsf(P.m[1]), fabsf(P.m[4])));
         RotTile T;
+        T.generic = 0;
         T.cols = (int)ceilf((RTT - 1) * (fabsf(P.m[0]) + fabsf(P.m[3])) + ds * P.fw) + 5;
         T.rows = (int)ceilf((RTT - 1) * (fabsf(P.m[1]) + fabsf(P.m[4])) + dt * P.fw) + 5;
         const float edge = (float)(RTT - 1);
