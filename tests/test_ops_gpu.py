@@ -728,6 +728,17 @@ def test_rotate_random_geometries(T, seed):
         assert_close(T.rotate(to_dev(src), angle), O.rotate(src, angle), f"rotate {np.dtype(dt).name} {(w, h)} by {angle}")
 
 
+@pytest.mark.parametrize("w,h", [(64, 48), (332, 216), (4, 4), (36, 301), (258, 130)])
+@pytest.mark.parametrize("dt", NP_TYPES)
+def test_rotate_storage_type_tiles_through_the_copy_engine(T, dt, w, h):
+    """Row pitches that are multiples of 16 bytes in every storage type: k_rotate_quad's tile arrives by TMA in the storage type
+    (first column rounded down to a 16-byte boundary, converted once per staged pixel) -- partial blocks on every side, frames
+    smaller than a block, several angles including the axis-aligned ones."""
+    src = rand_img(w, h, dt, 4242 + w)
+    for angle in (45.0, -17.3, 90.0, 180.0, 3.0, 211.0):
+        assert_close(T.rotate(to_dev(src), angle), O.rotate(src, angle), f"rotate {np.dtype(dt).name} {(w, h)} by {angle}")
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_blur_and_unsharp_random_geometries(T, seed):
     """Random frame sizes (down to one pixel and narrower than a tile), radii over every tile template and storage types:

@@ -969,6 +969,7 @@ struct RotTile {
     int cols, rows, pitch;                       // allocation of the shared source tile; row pitch in pixels
     float smn_off, smx_off, tmn_off, tmx_off;    // extent of a block's four corner positions relative to its first pixel's
     int generic;                                 // k_rotate_quad: every quad through the per-pixel form (TOUCAN_ROTATE_QUAD=generic, tests)
+    int raw_off;                                 // k_rotate_quad: byte offset of the storage-type tile the copy engine fills
 };
 
 // TMA: the source box is fetched by ONE tensor copy (float32 sources; zero fill outside the frame IS rotate's "black outside
@@ -1131,32 +1132,64 @@ __device__ __noinline__ void rot_px_generic(const float4* tile, int pitch, int r
     store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
 }
 
-template <int TYPE>
-__global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img dst_, const __grid_constant__ RotParams P, const RotTile T,
+template <int TYPE, bool TMA>
+__global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img src_, const Img dst_, const __grid_constant__ RotParams P, const RotTile T,
                                                                 const __grid_constant__ CUtensorMap map)
 {
     extern __shared__ __align__(128) float4 rot_smem[];
     __shared__ uint64_t bar;
+    const Img src { src_.p, src_.w, src_.h, TYPE };
     const Img dst { dst_.p, dst_.w, dst_.h, TYPE };
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * RQ_BW, y0 = blockIdx.y * RQ_BH;
     const float px0 = __fadd_rn((float)x0, 0.5f), py0 = __fadd_rn((float)y0, 0.5f);
     const float s00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[0]), __fmul_rn(py0, P.m[3])), P.m[6]);
     const float t00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[1]), __fmul_rn(py0, P.m[4])), P.m[7]);
-    const int s0 = (int)floorf(s00 + T.smn_off - 3.0f) - 1, t0 = (int)floorf(t00 + T.tmn_off - 3.0f) - 1;
+    // (a box row of the copy starts on a 16-byte boundary of the source row: the first column is rounded down to 4 pixels of
+    //  8 bits, 2 pixels of 16 bits; the host allocates the extra columns)
+    typedef typename RawPx<TYPE>::type Raw;
+    constexpr int ALIGN = TMA ? 16 / (int)sizeof(Raw) : 1;
+    const int s0 = ((int)floorf(s00 + T.smn_off - 3.0f) - 1) & ~(ALIGN > 1 ? ALIGN - 1 : 0), t0 = (int)floorf(t00 + T.tmn_off - 3.0f) - 1;
     const int pitch = T.pitch;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        mbar_init_fence();
-        mbar_expect_tx(&bar, (unsigned)(T.rows * T.pitch * 16));
-        tma_load_tile(rot_smem, &map, 2 * s0, t0, &bar);
+    Raw* raw = reinterpret_cast<Raw*>(reinterpret_cast<unsigned char*>(rot_smem) + T.raw_off);
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_init_fence();
+            mbar_expect_tx(&bar, (unsigned)(T.rows * T.pitch * sizeof(Raw)));
+            tma_load_tile(raw, &map, TYPE == TC_F32 ? 2 * s0 : s0, t0, &bar);
+        }
+    } else {
+        // 8 / 16-bit and half sources (and float32 where the copy engine cannot be used): a warp per source row, converted to
+        // float on the way, black outside the source
+        // (eight independent loads in flight per thread: four rows x two columns)
+        for (int r = tid >> 5; r < T.rows; r += 4 * (RQ_THREADS / 32)) {
+            for (int c0 = 0; c0 < pitch; c0 += 64) {
+                float4 v[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const int rr = r + k * (RQ_THREADS / 32), c = c0 + m * 32 + (tid & 31);
+                        v[k][m] = (rr < T.rows && c < pitch) ? load_black(src, s0 + c, t0 + rr) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const int rr = r + k * (RQ_THREADS / 32), c = c0 + m * 32 + (tid & 31);
+                        if (rr < T.rows && c < pitch) rot_smem[rr * pitch + c] = v[k][m];
+                    }
+            }
+        }
     }
     __syncthreads();
 
     // warps 2 x 2 over the block (16 x 8 pixels each), quarter warps 2 x 2 over the warp, threads 4 x 2 over the quarter
     const int lane = tid & 31, warp = tid >> 5, q = lane >> 3, l = lane & 7;
     const int x = x0 + (warp & 1) * 16 + (q & 1) * 8 + (l & 3) * 2, y = y0 + (warp >> 1) * 8 + (q >> 1) * 4 + (l >> 2) * 2;
-    if (x >= dst.w || y >= dst.h) return;
+    const bool live = x < dst.w && y < dst.h;
+    if ((!TMA || TYPE == TC_F32) && !live) return; // (8 / 16-bit tiles are converted by the whole CTA below)
 
     float se[4], te[4];
     int cs[4], rs[4];
@@ -1226,7 +1259,15 @@ __global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img dst_, c
             eyw[p][k] = oy == 0 ? eyw[p][k] : (oy == 1 ? b1 : b2);
         }
     }
-    mbar_wait(&bar, 0);
+    if (TMA) mbar_wait(&bar, 0);
+    if (TMA && TYPE != TC_F32) {
+        // the tile arrived in the storage type (a quarter / half of the bytes through L2): one conversion per staged pixel
+        const int n = T.rows * pitch;
+#pragma unroll 4
+        for (int i = tid; i < n; i += RQ_THREADS) rot_smem[i] = raw_px(raw[i], TYPE);
+        __syncthreads();
+        if (!live) return;
+    }
     if (!ok) {
 #pragma unroll 1
         for (int p = 0; p < 4; ++p)
@@ -1569,69 +1610,64 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
         const bool rot_quad = rot_quad_mode != 0;
         const float ds = fmaxf(1.0f, fmaxf(fabsf(P.m[0]), fabsf(P.m[3]))), dt = fmaxf(1.0f, fmaxf(fabsf(P.m[1]), fabsf(P.m[4])));
         const float spx = fabsf(P.m[0]) + fabsf(P.m[3]), spy = fabsf(P.m[1]) + fabsf(P.m[4]);
-        if (rot_quad && id == 0 && P.fw == 6.0f && ds == 1.0f && dt == 1.0f && spx <= 1.9f && spy <= 1.9f && src->type == TC_F32 && tma_available() &&
-            ((uintptr_t)src->data & 15) == 0) {
+        if (rot_quad && id == 0 && P.fw == 6.0f && ds == 1.0f && dt == 1.0f && spx <= 1.9f && spy <= 1.9f && src->type == dst->type) {
             RotTile T;
             T.generic = rot_quad_mode == 2 ? 1 : 0;
             const float ex = (float)(RQ_BW - 1), ey = (float)(RQ_BH - 1);
-            T.cols = (int)ceilf(ex * fabsf(P.m[0]) + ey * fabsf(P.m[3]) + 6.0f) + 7;
+            T.cols = (int)ceilf(ex * fabsf(P.m[0]) + ey * fabsf(P.m[3]) + 6.0f) + 7 + (src->type == TC_U8 ? 3 : (src->type == TC_F32 ? 0 : 1));
             T.rows = (int)ceilf(ex * fabsf(P.m[1]) + ey * fabsf(P.m[4]) + 6.0f) + 7;
             T.smn_off = fminf(0.0f, ex * P.m[0]) + fminf(0.0f, ey * P.m[3]);
             T.smx_off = fmaxf(0.0f, ex * P.m[0]) + fmaxf(0.0f, ey * P.m[3]);
             T.tmn_off = fminf(0.0f, ex * P.m[1]) + fminf(0.0f, ey * P.m[4]);
             T.tmx_off = fmaxf(0.0f, ex * P.m[1]) + fmaxf(0.0f, ey * P.m[4]);
-            // row pitch: the eight windows of a quarter warp (threads 4 x 2, two pixels apart) should start in different
-            // 16-byte bank groups
-            int best = 1 << 30;
-            T.pitch = T.cols;
-            for (int pitch = T.cols; pitch < T.cols + 8; ++pitch) {
-                int cost = 0;
-                for (int ph = 0; ph < 16; ++ph) {
-                    const float sf = 0.25f * (float)(ph & 3), tf = 0.25f * (float)(ph >> 2);
-                    int slots[8], worst = 0;
-                    for (int k = 0; k < 8; ++k) {
-                        int c0 = 1 << 30, r0 = 1 << 30;
-                        for (int p4 = 0; p4 < 4; ++p4) {
-                            const float a = (float)(2 * (k & 3) + (p4 & 1)), b = (float)(2 * (k >> 2) + (p4 >> 1));
-                            c0 = std::min(c0, (int)floorf(sf + 64.0f + a * P.m[0] + b * P.m[3]));
-                            r0 = std::min(r0, (int)floorf(tf + 64.0f + a * P.m[1] + b * P.m[4]));
-                        }
-                        slots[k] = r0 * pitch + c0;
-                    }
-                    for (int g = 0; g < 8; ++g) {
-                        int n = 0;
-                        for (int k = 0; k < 8; ++k) {
-                            if ((slots[k] & 7) != g) continue;
-                            bool seen = false;
-                            for (int q = 0; q < k; ++q) seen = seen || slots[q] == slots[k];
-                            n += seen ? 0 : 1;
-                        }
-                        worst = n > worst ? n : worst;
-                    }
-                    cost += worst;
-                }
-                if (cost < best) {
-                    best = cost;
-                    T.pitch = pitch;
-                }
-            }
-            const size_t smem = (size_t)T.rows * T.pitch * sizeof(float4);
+            // row pitch: the kernel's per-lane column rotation removes the bank conflicts for any pitch; a box row of the copy
+            // is a multiple of 16 bytes in the storage type
+            const int pal = src->type == TC_U8 ? 4 : (src->type == TC_F32 ? 1 : 2);
+            T.pitch = (T.cols + pal - 1) / pal * pal;
+            const size_t tile = ((size_t)T.rows * T.pitch * sizeof(float4) + 127) / 128 * 128;
+            const size_t px_bytes = src->type == TC_U8 ? 4 : (src->type == TC_F32 ? 16 : 8);
+            size_t smem = tile;
+            T.raw_off = 0;
             CUtensorMap map;
             memset(&map, 0, sizeof(map));
-            if (smem <= 72 * 1024 && 2 * T.pitch <= 256 && T.rows <= 256 &&
-                tensor_map_2d(src->data, 8, 2ull * src->w, (unsigned long long)src->h, 16ull * src->w, 2u * T.pitch, (unsigned)T.rows, &map) == TC_OK) {
+            if (smem <= 72 * 1024) {
+                static const bool rot_tma = [] {
+                    const char* e = getenv("TOUCAN_ROTATE_TMA");
+                    return !(e && *e == '0');
+                }();
+                // the copy engine wants the source base and row pitch on 16-byte boundaries
+                bool tma = rot_tma && tma_available() && ((uintptr_t)src->data & 15) == 0 && ((size_t)src->w * px_bytes) % 16 == 0 && T.pitch <= 128 && T.rows <= 256;
+                if (tma && src->type == TC_F32)
+                    tma = tensor_map_2d(src->data, 8, 2ull * src->w, (unsigned long long)src->h, 16ull * src->w, 2u * T.pitch, (unsigned)T.rows, &map) == TC_OK;
+                else if (tma) {
+                    tma = tensor_map_2d(src->data, (int)px_bytes, (unsigned long long)src->w, (unsigned long long)src->h, px_bytes * src->w, (unsigned)T.pitch,
+                                        (unsigned)T.rows, &map) == TC_OK;
+                    if (tma) {
+                        T.raw_off = (int)tile;
+                        smem = tile + (size_t)T.rows * T.pitch * px_bytes;
+                    }
+                }
                 const dim3 qgrid((dst->w + RQ_BW - 1) / RQ_BW, (dst->h + RQ_BH - 1) / RQ_BH);
                 int e = TC_OK;
-#define TC_ROTQ(TY)                                                                   \
-    case TY:                                                                          \
-        e = ensure_dynamic_smem((const void*)k_rotate_quad<TY>, smem);                \
-        if (e == TC_OK) k_rotate_quad<TY><<<qgrid, RQ_THREADS, smem, st>>>(vd, P, T, map); \
+#define TC_ROTQ(TY, TM)                                                                         \
+    case TY:                                                                                    \
+        e = ensure_dynamic_smem((const void*)k_rotate_quad<TY, TM>, smem);                      \
+        if (e == TC_OK) k_rotate_quad<TY, TM><<<qgrid, RQ_THREADS, smem, st>>>(vs, vd, P, T, map); \
         break;
-                switch (dst->type) {
-                    TC_ROTQ(TC_U8)
-                    TC_ROTQ(TC_U16)
-                    TC_ROTQ(TC_F16)
-                    TC_ROTQ(TC_F32)
+                if (tma) {
+                    switch (dst->type) {
+                        TC_ROTQ(TC_U8, true)
+                        TC_ROTQ(TC_U16, true)
+                        TC_ROTQ(TC_F16, true)
+                        TC_ROTQ(TC_F32, true)
+                    }
+                } else {
+                    switch (dst->type) {
+                        TC_ROTQ(TC_U8, false)
+                        TC_ROTQ(TC_U16, false)
+                        TC_ROTQ(TC_F16, false)
+                        TC_ROTQ(TC_F32, false)
+                    }
                 }
 #undef TC_ROTQ
                 if (e != TC_OK) return e;
