@@ -1132,56 +1132,31 @@ __device__ __noinline__ void rot_px_generic(const float4* tile, int pitch, int r
     store_px(dst.p, dst.type, (size_t)y * dst.w + x, o);
 }
 
-template <int TYPE, bool TMA>
-__global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img src_, const Img dst_, const __grid_constant__ RotParams P, const RotTile T,
+template <int TYPE>
+__global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img dst_, const __grid_constant__ RotParams P, const RotTile T,
                                                                 const __grid_constant__ CUtensorMap map)
 {
     extern __shared__ __align__(128) float4 rot_smem[];
     __shared__ uint64_t bar;
-    const Img src { src_.p, src_.w, src_.h, TYPE };
     const Img dst { dst_.p, dst_.w, dst_.h, TYPE };
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * RQ_BW, y0 = blockIdx.y * RQ_BH;
     const float px0 = __fadd_rn((float)x0, 0.5f), py0 = __fadd_rn((float)y0, 0.5f);
     const float s00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[0]), __fmul_rn(py0, P.m[3])), P.m[6]);
     const float t00 = __fadd_rn(__fadd_rn(__fmul_rn(px0, P.m[1]), __fmul_rn(py0, P.m[4])), P.m[7]);
-    // (a box row of the copy starts on a 16-byte boundary of the source row: the first column is rounded down to 4 pixels of
-    //  8 bits, 2 pixels of 16 bits; the host allocates the extra columns)
+    // The source box arrives by ONE TMA tensor copy in the storage type (zero fill outside the frame IS rotate's black
+    // surround).  A box row starts on a 16-byte boundary of the source row: the first column is rounded down to 4 pixels of
+    // 8 bits, 2 pixels of 16 bits; the host allocates the extra columns.
     typedef typename RawPx<TYPE>::type Raw;
-    constexpr int ALIGN = TMA ? 16 / (int)sizeof(Raw) : 1;
+    constexpr int ALIGN = 16 / (int)sizeof(Raw);
     const int s0 = ((int)floorf(s00 + T.smn_off - 3.0f) - 1) & ~(ALIGN > 1 ? ALIGN - 1 : 0), t0 = (int)floorf(t00 + T.tmn_off - 3.0f) - 1;
     const int pitch = T.pitch;
     Raw* raw = reinterpret_cast<Raw*>(reinterpret_cast<unsigned char*>(rot_smem) + T.raw_off);
-    if (TMA) {
-        if (tid == 0) {
-            mbar_init(&bar, 1);
-            mbar_init_fence();
-            mbar_expect_tx(&bar, (unsigned)(T.rows * T.pitch * sizeof(Raw)));
-            tma_load_tile(raw, &map, TYPE == TC_F32 ? 2 * s0 : s0, t0, &bar);
-        }
-    } else {
-        // 8 / 16-bit and half sources (and float32 where the copy engine cannot be used): a warp per source row, converted to
-        // float on the way, black outside the source
-        // (eight independent loads in flight per thread: four rows x two columns)
-        for (int r = tid >> 5; r < T.rows; r += 4 * (RQ_THREADS / 32)) {
-            for (int c0 = 0; c0 < pitch; c0 += 64) {
-                float4 v[4][2];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        const int rr = r + k * (RQ_THREADS / 32), c = c0 + m * 32 + (tid & 31);
-                        v[k][m] = (rr < T.rows && c < pitch) ? load_black(src, s0 + c, t0 + rr) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        const int rr = r + k * (RQ_THREADS / 32), c = c0 + m * 32 + (tid & 31);
-                        if (rr < T.rows && c < pitch) rot_smem[rr * pitch + c] = v[k][m];
-                    }
-            }
-        }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_init_fence();
+        mbar_expect_tx(&bar, (unsigned)(T.rows * T.pitch * sizeof(Raw)));
+        tma_load_tile(raw, &map, TYPE == TC_F32 ? 2 * s0 : s0, t0, &bar);
     }
     __syncthreads();
 
@@ -1189,7 +1164,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img src_, c
     const int lane = tid & 31, warp = tid >> 5, q = lane >> 3, l = lane & 7;
     const int x = x0 + (warp & 1) * 16 + (q & 1) * 8 + (l & 3) * 2, y = y0 + (warp >> 1) * 8 + (q >> 1) * 4 + (l >> 2) * 2;
     const bool live = x < dst.w && y < dst.h;
-    if ((!TMA || TYPE == TC_F32) && !live) return; // (8 / 16-bit tiles are converted by the whole CTA below)
+    if (TYPE == TC_F32 && !live) return; // (8 / 16-bit tiles are converted by the whole CTA below)
 
     float se[4], te[4];
     int cs[4], rs[4];
@@ -1259,8 +1234,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img src_, c
             eyw[p][k] = oy == 0 ? eyw[p][k] : (oy == 1 ? b1 : b2);
         }
     }
-    if (TMA) mbar_wait(&bar, 0);
-    if (TMA && TYPE != TC_F32) {
+    mbar_wait(&bar, 0);
+    if (TYPE != TC_F32) {
         // the tile arrived in the storage type (a quarter / half of the bytes through L2): one conversion per staged pixel
         const int n = T.rows * pitch;
 #pragma unroll 4
@@ -1601,7 +1576,7 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
     const bool narrow = P.fw + 2.0f <= 8.0f;
     const Img vs = view(src), vd = view(dst);
     cudaStream_t st = (cudaStream_t)s;
-    // four pixels per thread: plain rotations with the default lanczos3 of float32 frames
+    // four pixels per thread: plain rotations with the default lanczos3, tile moved by the copy engine in the storage type
     {
         static const int rot_quad_mode = [] {
             const char* e = getenv("TOUCAN_ROTATE_QUAD");
@@ -1649,30 +1624,24 @@ int tc_rotate(const tc_image* dst, const tc_image* src, float angle, const char*
                 }
                 const dim3 qgrid((dst->w + RQ_BW - 1) / RQ_BW, (dst->h + RQ_BH - 1) / RQ_BH);
                 int e = TC_OK;
-#define TC_ROTQ(TY, TM)                                                                         \
-    case TY:                                                                                    \
-        e = ensure_dynamic_smem((const void*)k_rotate_quad<TY, TM>, smem);                      \
-        if (e == TC_OK) k_rotate_quad<TY, TM><<<qgrid, RQ_THREADS, smem, st>>>(vs, vd, P, T, map); \
+#define TC_ROTQ(TY)                                                                       \
+    case TY:                                                                              \
+        e = ensure_dynamic_smem((const void*)k_rotate_quad<TY>, smem);                    \
+        if (e == TC_OK) k_rotate_quad<TY><<<qgrid, RQ_THREADS, smem, st>>>(vd, P, T, map); \
         break;
                 if (tma) {
                     switch (dst->type) {
-                        TC_ROTQ(TC_U8, true)
-                        TC_ROTQ(TC_U16, true)
-                        TC_ROTQ(TC_F16, true)
-                        TC_ROTQ(TC_F32, true)
+                        TC_ROTQ(TC_U8)
+                        TC_ROTQ(TC_U16)
+                        TC_ROTQ(TC_F16)
+                        TC_ROTQ(TC_F32)
                     }
-                } else {
-                    switch (dst->type) {
-                        TC_ROTQ(TC_U8, false)
-                        TC_ROTQ(TC_U16, false)
-                        TC_ROTQ(TC_F16, false)
-                        TC_ROTQ(TC_F32, false)
-                    }
+                    if (e != TC_OK) return e;
+                    count_launch();
+                    return check_cuda(cudaGetLastError(), "k_rotate_quad launch");
                 }
 #undef TC_ROTQ
-                if (e != TC_OK) return e;
-                count_launch();
-                return check_cuda(cudaGetLastError(), "k_rotate_quad launch");
+                // (no copy engine for this frame -- unaligned base or row pitch: the one-pixel-per-thread kernels below)
             }
         }
     }
