@@ -1162,7 +1162,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 4) k_rotate_quad(const Img dst_, c
 
     // warps 2 x 2 over the block (16 x 8 pixels each), quarter warps 2 x 2 over the warp, threads 4 x 2 over the quarter
     const int lane = tid & 31, warp = tid >> 5, q = lane >> 3, l = lane & 7;
-    const int x = x0 + (warp & 1) * 16 + (q & 1) * 8 + (l & 3) * 2, y = y0 + (warp >> 1) * 8 + (q >> 1) * 4 + (l >> 2) * 2;
+    constexpr int WX = RQ_BW / 16;
+    const int x = x0 + (warp % WX) * 16 + (q & 1) * 8 + (l & 3) * 2, y = y0 + (warp / WX) * 8 + (q >> 1) * 4 + (l >> 2) * 2;
     const bool live = x < dst.w && y < dst.h;
     if (TYPE == TC_F32 && !live) return; // (8 / 16-bit tiles are converted by the whole CTA below)
 
