@@ -1102,9 +1102,10 @@ __global__ void __launch_bounds__(RTT * RTT) k_rotate_tile(const Img src_, const
 // footprints start within two source pixels of each other on either axis, so one 8 x 8 window of the staged tile holds all four
 // 6 x 6 live windows: 16 shared-memory pixel reads per destination pixel instead of 36.  Each pixel's six weights per axis are
 // placed in an 8-wide row at the pixel's offset in the shared window (zeros elsewhere), the window rows are reduced with the four
-// x rows and folded in with the y weights as in k_rotate_tile.  lanczos3 at its default width and unit tap spacing, float32
-// sources through the TMA copy; anything else -- and any quad whose pixels fall outside those conditions by float rounding --
-// takes the per-pixel forms (rot_px_generic here, k_rotate_tile / k_rotate otherwise).  Same weights as k_rotate_tile.
+// x rows and folded in with the y weights as in k_rotate_tile.  lanczos3 at its default width and unit tap spacing, the tile
+// through the TMA copy in the storage type (8 / 16-bit and half tiles converted once per staged pixel); anything else -- and
+// any quad whose pixels fall outside those conditions by float rounding -- takes the per-pixel forms (rot_px_generic here,
+// k_rotate_tile / k_rotate otherwise).  Same weights as k_rotate_tile.
 constexpr int RQ_BW = 32, RQ_BH = 16, RQ_THREADS = 128, RQ_WIN = 8;
 
 __device__ __noinline__ void rot_px_generic(const float4* tile, int pitch, int rows, int s0, int t0, float s, float t, const Img dst, int x, int y)
