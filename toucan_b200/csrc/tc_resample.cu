@@ -945,12 +945,18 @@ __device__ __forceinline__ bool rot_filt_zero(float x)
 __device__ __forceinline__ void lanczos3_six(float b0, float (&w)[6])
 {
     const float A = __fmul_rn(fabsf(fast_sinpi_fused(b0)), 0.30396355092701331f); // |sinpi| * 3 / pi^2
+    // sinpi(x / 3): |x_k| / 3 and |x_(k+3)| / 3 add up to 1 and the parabola u (1 - u) is symmetric about 1/2 -- three evaluations
+    float f3s[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float u = __fmul_rn(fabsf(__fadd_rn(b0, (float)k)), 1.0f / 3.0f);
+        const float y = fmaf(-u, u, u);
+        f3s[k] = __fmul_rn(y, fmaf(3.584135056f, y, 3.10396624f));
+    }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const float x = fabsf(__fadd_rn(b0, (float)k));
-        const float u = __fmul_rn(x, 1.0f / 3.0f);
-        const float y = fmaf(-u, u, u);
-        const float f3 = __fmul_rn(y, fmaf(3.584135056f, y, 3.10396624f));
+        const float f3 = f3s[k < 3 ? k : k - 3];
         float v = __fmul_rn(__fmul_rn(rcp_approx(__fmul_rn(x, x)), (k == 1 || k == 4) ? -A : A), f3);
         if (k == 2 || k == 3) v = x < 0.0001f ? 1.0f : v;
         w[k] = v;
